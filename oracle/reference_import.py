@@ -1,0 +1,47 @@
+"""Make the UNMODIFIED Python reference (/root/reference) importable in the build container.
+
+TEST INFRASTRUCTURE ONLY.  Used by tests/golden/make_golden.py (to generate the committed golden
+vectors) and by optional cross-checks that skip when /root/reference is absent (it does not exist
+on the GPU box).  Nothing in colosseum_b200/ imports this.
+
+What it does: puts oracle/ref_shim (stand-ins for dm_env, gin, toolz, pydtmc,
+sparse, gym -- all absent from the image) and /root/reference on sys.path, and restores two names the
+reference needs that numpy-2 / py3.12 dropped (`numpy.core._exceptions`, `collections.Container`).
+"""
+import collections
+import collections.abc
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("COLOSSEUM_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "colosseum"))
+
+
+def import_reference():
+    """Returns the imported `colosseum` reference package (raises if /root/reference is absent)."""
+    if not reference_available():
+        raise ImportError(f"reference not present at {REFERENCE_ROOT}")
+    for p in (_SHIM, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    if not hasattr(collections, "Container"):
+        collections.Container = collections.abc.Container
+    import numpy as np
+
+    if "numpy.core._exceptions" not in sys.modules:
+        try:
+            import numpy._core._exceptions as _exc
+        except Exception:  # pragma: no cover
+            _exc = types.ModuleType("numpy.core._exceptions")
+            _exc._ArrayMemoryError = MemoryError
+        sys.modules["numpy.core._exceptions"] = _exc
+    import colosseum  # noqa: E402
+
+    colosseum.config.disable_multiprocessing()
+    colosseum.config.VERBOSE_LEVEL = 0
+    return colosseum
