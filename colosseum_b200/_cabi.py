@@ -1,0 +1,143 @@
+"""ctypes binding of libcolosseum_b200.so (include/colosseum_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at first use, loudly.
+PyTorch is used only as the device-buffer / stream provider (tensor.data_ptr(), torch.cuda.current_stream()).
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "_lib", "libcolosseum_b200.so")
+
+OK, OVERFLOW, MAX_ITER, NEEDS_RESET = 0, 1, 2, 3
+FOLD_MAX, FOLD_PI, FOLD_MIN = 0, 1, 2
+STEP_FIRST, STEP_MID, STEP_LAST = 0, 1, 2
+
+
+class ColosseumB200Error(RuntimeError):
+    pass
+
+
+class BackupArgs(C.Structure):
+    """mirror of `colo_backup_args`"""
+
+    _fields_ = [
+        ("T", C.c_void_p), ("R", C.c_void_p), ("pi", C.c_void_p),
+        ("V_in", C.c_void_p), ("V_out", C.c_void_p), ("Q", C.c_void_p),
+        ("t_stride", C.c_longlong), ("r_stride", C.c_longlong), ("pi_stride", C.c_longlong),
+        ("v_in_stride", C.c_longlong), ("v_out_stride", C.c_longlong), ("q_stride", C.c_longlong),
+        ("v_action_stride", C.c_longlong),
+        ("B", C.c_int), ("S", C.c_int), ("A", C.c_int), ("fold", C.c_int),
+        ("gamma", C.c_double), ("r_const", C.c_double),
+        ("resid", C.c_void_p), ("resid_vs_out", C.c_int),
+        ("active", C.c_void_p),
+        ("max_abs", C.c_double), ("overflow_flag", C.c_void_p),
+        ("row0", C.c_int), ("nrows", C.c_int),
+        ("pin_index", C.c_void_p), ("pin_value", C.c_double),
+        ("exclude_index", C.c_void_p), ("exclude_value", C.c_double),
+        ("V_out_peers", C.c_void_p), ("n_peers", C.c_int),
+    ]
+
+
+class MdpTables(C.Structure):
+    """mirror of `colo_mdp_tables` (device pointers)"""
+
+    _fields_ = [
+        ("S", C.c_int), ("A", C.c_int), ("H", C.c_int), ("ld", C.c_int),
+        ("cdf", C.c_void_p),
+        ("succ_cum", C.c_void_p), ("succ_idx", C.c_void_p), ("succ_len", C.c_void_p), ("Ksucc", C.c_int),
+        ("rew_cls_sas", C.c_void_p), ("rew_cls_sa", C.c_void_p), ("rew_cls_succ", C.c_void_p),
+        ("rew_q", C.c_void_p), ("n_cls", C.c_int), ("nq", C.c_int),
+        ("rmin", C.c_float), ("rmax", C.c_float),
+        ("start_cum", C.c_void_p), ("start_idx", C.c_void_p), ("n_start", C.c_int),
+    ]
+
+
+_P = C.c_void_p
+_LL = C.c_longlong
+_ULL = C.c_ulonglong
+_I = C.c_int
+_F = C.c_float
+_D = C.c_double
+
+# name -> (restype, argtypes); every symbol include/colosseum_b200.h declares
+PROTOTYPES = {
+    "colo_last_error": (C.c_char_p, []),
+    "colo_version": (_I, []),
+    "colo_launch_count": (_ULL, []),
+    "colo_reset_launch_count": (None, []),
+    "colo_backup_f32": (_I, [C.POINTER(BackupArgs), _P]),
+    "colo_backup_f64acc": (_I, [C.POINTER(BackupArgs), _P]),
+    "colo_solve_work_bytes": (C.c_size_t, [_LL, _LL, _I]),
+    "colo_solve_discounted_f32": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _LL, _I, _P, _P, _P, _P, _P]),
+    "colo_solve_discounted_f64acc": (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _LL, _I, _P, _P, _P, _P, _P]),
+    "colo_episodic_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "colo_episodic_f64acc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _D, _P, _P, _P]),
+    "colo_diameter_continuous_work_bytes": (C.c_size_t, [_I, _I, _I]),
+    "colo_diameter_continuous_f32": (_I, [_P, _P, _I, _I, _I, _F, _F, _LL, _P, _P, _P]),
+    "colo_diameter_continuous_f64acc": (_I, [_P, _P, _I, _I, _I, _D, _D, _LL, _P, _P, _P]),
+    "colo_diameter_episodic_work_bytes": (C.c_size_t, [_I, _I, _I, _I, _I]),
+    "colo_diameter_episodic_f32": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _LL, _P, _P, _P]),
+    "colo_diameter_episodic_f64acc": (_I, [_P, _P, _I, _I, _I, _I, _D, _D, _LL, _P, _P, _P]),
+    "colo_value_norm_work_bytes": (C.c_size_t, [_I, _I, _I]),
+    "colo_value_norm_f32": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "colo_value_norm_f64acc": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "colo_gaps_f64": (_I, [_P, _P, _P, _LL, _I, _D, _P, _P]),
+    "colo_env_reset": (_I, [C.POINTER(MdpTables), _LL, _P, _ULL, _ULL, _ULL, _P, _P, _P, _P, _P, _P]),
+    "colo_env_step_dense_f32": (_I, [C.POINTER(MdpTables), _LL, _P, _I, _P, _P, _ULL, _ULL, _ULL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "colo_env_step_dense_f64": (_I, [C.POINTER(MdpTables), _LL, _P, _I, _P, _P, _ULL, _ULL, _ULL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "colo_env_step_succ": (_I, [C.POINTER(MdpTables), _LL, _P, _I, _P, _P, _ULL, _ULL, _ULL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),
+    "colo_synth_dense_rows": (_I, [_P, _P, _I, _I, _I, _I, _ULL, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded CUDA library.  Raises ColosseumB200Error if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ColosseumB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m colosseum_b200.build` "
+                "(colosseum_b200 has no CPU or PyTorch fallback path)"
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    msg = lib().colo_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc, what):
+    """raise on CUDA / argument errors; pass the reference-level statuses (0..3) back to the caller"""
+    if rc < 0:
+        raise ColosseumB200Error(f"{what}: {last_error()} (rc={rc})")
+    return rc
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise ColosseumB200Error("colosseum_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    lib()

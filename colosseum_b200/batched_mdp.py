@@ -1,0 +1,213 @@
+"""`BatchedMDP`: N parallel episodes of one MDP advanced on the GPU with the semantics of the reference's
+`BaseMDP.reset/step` (colosseum/mdp/base.py:1268-1355).
+
+    env = BatchedMDP(MDPTables.from_mdp(reference_mdp), n_envs=65536, mode="dense_f32")
+    ts = env.reset()
+    ts = env.step(actions)            # actions: int32 [N] (numpy or CUDA tensor)
+    ts, actions = env.random_step()   # BaseMDP.random_step for every env
+
+With n_envs=1, `ts.scalar()` is the reference's scalar dm_env.TimeStep.  Modes:
+  dense_f32 / dense_f64   warp-cooperative inverse-CDF search over the dense CDF row of T[s,a,:]
+  succ                    successor-list tables in the reference sampler's own order: bit-exact with
+                          NextStateSampler.sample for the same fp64 uniform (mdp/utils/custom_samplers.py:49-72)
+Uniforms may be supplied (`u_next`, `u_reward`) or come from the in-kernel Philox4x32-10 stream keyed by
+(seed; env index, step counter).  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .tables import MDPTables
+from .timestep import BatchedTimeStep
+
+_MODES = {"dense_f32": 0, "dense_f64": 1, "succ": 2}
+
+
+class DeviceTables:
+    """MDPTables uploaded to the current CUDA device + the `colo_mdp_tables` struct pointing at them."""
+
+    def __init__(self, tb: MDPTables, mode: str):
+        import torch
+
+        _cabi.require_cuda()
+        self.host = tb
+        self.mode = mode
+        dev = "cuda"
+        k = {}
+
+        def up(name, arr, dtype):
+            if arr is None:
+                k[name] = None
+            else:
+                k[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype)).to(dev)
+
+        up("start_cum", tb.start_cum, np.float64)
+        up("start_idx", tb.start_idx, np.int32)
+        up("rew_q", tb.rew_q, np.float32)
+        c = _cabi.MdpTables()
+        c.S, c.A, c.H = tb.S, tb.A, tb.H
+        c.rmin, c.rmax = tb.rmin, tb.rmax
+        c.n_cls, c.nq = tb.rew_q.shape
+        c.n_start = tb.n_start
+        if mode == "succ":
+            assert tb.succ_cum is not None, "successor tables are required for mode='succ'"
+            up("succ_cum", tb.succ_cum, np.float64)
+            up("succ_idx", tb.succ_idx, np.int32)
+            up("succ_len", tb.succ_len, np.int32)
+            up("rew_cls_succ", tb.rew_cls_succ, np.int32)
+            c.Ksucc = tb.succ_cum.shape[-1]
+        else:
+            assert tb.T is not None, "a dense T is required for the dense modes"
+            f64 = mode == "dense_f64"
+            up("T", tb.T, np.float32)
+            ld = tb.ld
+            k["cdf"] = torch.empty((tb.S, tb.A, ld), dtype=torch.float64 if f64 else torch.float32, device=dev)
+            rc = _cabi.lib().colo_build_dense_cdf(_cabi.ptr(k["T"]), tb.S, tb.A, ld, _cabi.ptr(k["cdf"]), int(f64),
+                                                  _cabi.current_stream())
+            _cabi.check(rc, "colo_build_dense_cdf")
+            c.ld = ld
+            up("rew_cls_sas", tb.rew_cls_sas, np.uint8)
+            up("rew_cls_sa", tb.rew_cls_sa, np.int32)
+        for name in ("cdf", "succ_cum", "succ_idx", "succ_len", "rew_cls_sas", "rew_cls_sa", "rew_cls_succ", "rew_q",
+                     "start_cum", "start_idx"):
+            setattr(c, name, _cabi.ptr(k.get(name)))
+        self.keep = k
+        self.c = c
+
+
+class BatchedMDP:
+    def __init__(self, tables: MDPTables, n_envs: int, mode: str = "dense_f32", seed: int = 0,
+                 track_visits: bool = True, env_offset: int = 0):
+        import torch
+
+        assert mode in _MODES
+        self.torch = torch
+        self.tables = tables
+        self.dev = DeviceTables(tables, mode)
+        self.mode = mode
+        self.n_envs = int(n_envs)
+        self.seed = int(seed)
+        # env_offset: global index of this shard's first env; the Philox counter is (env_offset + i, t), so a
+        # batch sharded over GPUs draws exactly the numbers of the unsharded batch
+        self.env_offset = int(env_offset)
+        N = self.n_envs
+        self.state = torch.zeros(N, dtype=torch.int32, device="cuda")
+        self.h = torch.zeros(N, dtype=torch.int32, device="cuda")
+        # before the first reset() the reference raises (necessary_reset is unset, base.py:405 vs :1272);
+        # LAST + auto_reset=False reproduces that as an error, LAST + auto_reset=True resets.
+        self.step_type = torch.full((N,), _cabi.STEP_LAST, dtype=torch.uint8, device="cuda")
+        self.reward = torch.zeros(N, dtype=torch.float32, device="cuda")
+        self.obs = torch.zeros(N, dtype=torch.int32, device="cuda")
+        self.action = torch.zeros(N, dtype=torch.int32, device="cuda")
+        self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.visits_s = torch.zeros(tables.S, dtype=torch.int64, device="cuda") if track_visits else None
+        self.visits_sa = torch.zeros((tables.S, tables.A), dtype=torch.int64, device="cuda") if track_visits else None
+        self.t = 0  # launch counter: the Philox stream position
+        self._was_reset = False
+
+    # -- reference attribute surface (base.py:463-503, 1233-1252)
+    @property
+    def n_states(self):
+        return self.tables.S
+
+    @property
+    def n_actions(self):
+        return self.tables.A
+
+    @property
+    def H(self):
+        return self.tables.H if self.tables.H > 0 else None
+
+    def is_episodic(self):
+        return self.tables.H > 0
+
+    def _u(self, u, dtype):
+        if u is None:
+            return None
+        torch = self.torch
+        if isinstance(u, torch.Tensor):
+            return u.to(device="cuda", dtype=dtype).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(u, {torch.float32: np.float32, torch.float64: np.float64}[dtype])).cuda()
+
+    def _timestep(self):
+        torch = self.torch
+        st = self.step_type
+        nan = torch.full_like(self.reward, float("nan"))
+        discount = torch.where(st == _cabi.STEP_MID, torch.ones_like(self.reward),
+                               torch.where(st == _cabi.STEP_LAST, torch.zeros_like(self.reward), nan))
+        return BatchedTimeStep(st.clone(), self.reward.clone(), discount, self.obs.clone())
+
+    def reset(self, u_next=None) -> BatchedTimeStep:
+        """BaseMDP.reset (base.py:1268-1277) for every env."""
+        torch = self.torch
+        u = self._u(u_next, torch.float64)
+        rc = _cabi.lib().colo_env_reset(
+            C.byref(self.dev.c), self.n_envs, _cabi.ptr(u), self.seed, self.t, self.env_offset, _cabi.ptr(self.state),
+            _cabi.ptr(self.h), _cabi.ptr(self.step_type), _cabi.ptr(self.obs), _cabi.ptr(self.visits_s),
+            _cabi.current_stream())
+        _cabi.check(rc, "colo_env_reset")
+        self.t += 1
+        self._was_reset = True
+        self.reward.fill_(float("nan"))
+        return self._timestep()
+
+    def step_async(self, action=None, auto_reset=False, u_next=None, u_reward=None, check=False):
+        """Enqueue one step for all envs on the current stream; results live in self.state / h / step_type /
+        reward / obs (CUDA tensors, overwritten by the next step).  action=None plays uniformly random actions
+        (BaseMDP.random_step, base.py:1341-1355) and records them in self.action."""
+        torch = self.torch
+        random_actions = action is None
+        if not random_actions:
+            if isinstance(action, torch.Tensor):
+                self.action.copy_(action.to(torch.int32), non_blocking=True)
+            else:
+                a = np.ascontiguousarray(np.broadcast_to(np.asarray(action, np.int32), (self.n_envs,)))
+                self.action.copy_(torch.from_numpy(a), non_blocking=True)
+        lib = _cabi.lib()
+        if self.mode == "dense_f32":
+            fn, udt = lib.colo_env_step_dense_f32, torch.float32
+        elif self.mode == "dense_f64":
+            fn, udt = lib.colo_env_step_dense_f64, torch.float64
+        else:
+            fn, udt = lib.colo_env_step_succ, torch.float64
+        un = self._u(u_next, udt)
+        ur = self._u(u_reward, torch.float32)
+        rc = fn(C.byref(self.dev.c), self.n_envs, _cabi.ptr(self.action), int(random_actions), _cabi.ptr(un),
+                _cabi.ptr(ur), self.seed, self.t, self.env_offset, int(bool(auto_reset)), _cabi.ptr(self.state),
+                _cabi.ptr(self.h), _cabi.ptr(self.step_type), _cabi.ptr(self.reward), _cabi.ptr(self.obs),
+                _cabi.ptr(self.visits_s), _cabi.ptr(self.visits_sa), _cabi.ptr(self.status),
+                _cabi.current_stream())
+        _cabi.check(rc, "colo_env_step")
+        self.t += 1
+        if check or not auto_reset:
+            # the reference asserts `not self.necessary_reset` (base.py:1291); stepping before reset() raises too
+            if int(self.status.item()) == _cabi.NEEDS_RESET:
+                self.status.zero_()
+                if not self._was_reset:
+                    raise AttributeError("step() called before reset() (reference: necessary_reset is unset)")
+                raise AssertionError("an episode has terminated: call reset() or step(..., auto_reset=True)")
+
+    def step(self, action, auto_reset=False, u_next=None, u_reward=None) -> BatchedTimeStep:
+        """BaseMDP.step (base.py:1279-1317) for every env."""
+        self.step_async(action, auto_reset, u_next, u_reward)
+        return self._timestep()
+
+    def random_step(self, auto_reset=False):
+        """BaseMDP.random_step (base.py:1341-1355): returns (BatchedTimeStep, actions)."""
+        self.step_async(None, auto_reset)
+        return self._timestep(), self.action.clone()
+
+    def random_steps(self, n, auto_reset=False):
+        """BaseMDP.random_steps (base.py:1319-1339)."""
+        return [self.random_step(auto_reset) for _ in range(n)]
+
+    def get_visitation_counts(self, state_only=True):
+        """base.py:1357-1373, as arrays indexed by state index (and action)."""
+        return self.visits_s if state_only else self.visits_sa
+
+    def reset_visitation_counts(self):
+        """base.py:1375-1382"""
+        if self.visits_s is not None:
+            self.visits_s.zero_()
+            self.visits_sa.zero_()

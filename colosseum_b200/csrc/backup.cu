@@ -1,0 +1,770 @@
+// backup.cu -- the Bellman backup family (hot path B) for sm_100a.
+//
+// One streaming kernel template covers every S x A x S contraction of the path:
+//   value iteration / policy evaluation sweeps   colosseum/dynamic_programming/infinite_horizon.py:121-184
+//   episodic backward-induction layers           colosseum/dynamic_programming/finite_horizon.py:11-42
+//   hitting-time (diameter) sweeps, multi-target  colosseum/hardness/measures/diameter.py:76-106, :285-346
+//   the two passes of the environmental value norm colosseum/hardness/measures/value_norm.py:55-61,85-87
+//
+// It is a memory-bound batched GEMV: T is streamed from HBM exactly once per sweep with 128-bit
+// no-L1-allocate loads; the V vector is re-read through L1 (it is S*4 bytes, shared by every row of the MDP) and
+// each V element loaded is reused across the actions held in registers; the per-state fold over actions
+// (max / pi-weighted sum / min) is a warp-shuffle reduction fused into the same kernel together with the
+// residual max|dV|, the overflow test and the Q store, so a sweep is ONE launch and touches T once.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace colo {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kAT = 4;  // actions held in registers at once
+
+template <typename TV>
+struct VecOf;
+template <>
+struct VecOf<float> {
+  using resid_t = unsigned int;
+};
+template <>
+struct VecOf<double> {
+  using resid_t = unsigned long long;
+};
+
+template <typename TV>
+__device__ __forceinline__ void load_v4(const TV* p, TV (&v)[4]);
+template <>
+__device__ __forceinline__ void load_v4<float>(const float* p, float (&v)[4]) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load_v4<double>(const double* p, double (&v)[4]) {
+  double2 a = __ldg(reinterpret_cast<const double2*>(p));
+  double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// Partial dot products of up to kAT action rows of one state against V, over the j-range owned by this thread.
+// VEC: rows are 16-byte aligned and S % 4 == 0 -> 128-bit streaming loads, two row-quads in flight per action.
+template <typename TV, bool VEC>
+__device__ __forceinline__ void rows_dot(const float* __restrict__ Trow, const TV* __restrict__ Vb,
+                                         long long v_action_stride, int a0, int na, int S, int tid, int nthr,
+                                         TV (&acc)[kAT]) {
+#pragma unroll
+  for (int i = 0; i < kAT; ++i) acc[i] = TV(0);
+  if (VEC) {
+    const int S4 = S >> 2;
+    const float4* T4 = reinterpret_cast<const float4*>(Trow);
+    int j4 = tid;
+    // main loop: two independent column quads per iteration -> 2*na 128-bit loads in flight per thread
+    for (; j4 + nthr < S4; j4 += 2 * nthr) {
+      float4 t0[kAT], t1[kAT];
+#pragma unroll
+      for (int i = 0; i < kAT; ++i)
+        if (i < na) {
+          t0[i] = ldg_stream4(T4 + (size_t)(a0 + i) * S4 + j4);
+          t1[i] = ldg_stream4(T4 + (size_t)(a0 + i) * S4 + j4 + nthr);
+        }
+      if (v_action_stride == 0) {
+        TV v0[4], v1[4];
+        load_v4<TV>(Vb + 4 * (size_t)j4, v0);
+        load_v4<TV>(Vb + 4 * (size_t)(j4 + nthr), v1);
+#pragma unroll
+        for (int i = 0; i < kAT; ++i)
+          if (i < na) {
+            acc[i] += (TV)t0[i].x * v0[0] + (TV)t0[i].y * v0[1] + (TV)t0[i].z * v0[2] + (TV)t0[i].w * v0[3];
+            acc[i] += (TV)t1[i].x * v1[0] + (TV)t1[i].y * v1[1] + (TV)t1[i].z * v1[2] + (TV)t1[i].w * v1[3];
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kAT; ++i)
+          if (i < na) {
+            TV v0[4], v1[4];
+            const TV* Va = Vb + (size_t)(a0 + i) * v_action_stride;
+            load_v4<TV>(Va + 4 * (size_t)j4, v0);
+            load_v4<TV>(Va + 4 * (size_t)(j4 + nthr), v1);
+            acc[i] += (TV)t0[i].x * v0[0] + (TV)t0[i].y * v0[1] + (TV)t0[i].z * v0[2] + (TV)t0[i].w * v0[3];
+            acc[i] += (TV)t1[i].x * v1[0] + (TV)t1[i].y * v1[1] + (TV)t1[i].z * v1[2] + (TV)t1[i].w * v1[3];
+          }
+      }
+    }
+    for (; j4 < S4; j4 += nthr) {
+      float4 t0[kAT];
+#pragma unroll
+      for (int i = 0; i < kAT; ++i)
+        if (i < na) t0[i] = ldg_stream4(T4 + (size_t)(a0 + i) * S4 + j4);
+#pragma unroll
+      for (int i = 0; i < kAT; ++i)
+        if (i < na) {
+          TV v0[4];
+          load_v4<TV>(Vb + (size_t)(a0 + i) * v_action_stride + 4 * (size_t)j4, v0);
+          acc[i] += (TV)t0[i].x * v0[0] + (TV)t0[i].y * v0[1] + (TV)t0[i].z * v0[2] + (TV)t0[i].w * v0[3];
+        }
+    }
+  } else {
+    // unaligned / odd-S rows: coalesced 32-bit streaming loads
+    for (int j = tid; j < S; j += nthr) {
+#pragma unroll
+      for (int i = 0; i < kAT; ++i)
+        if (i < na) {
+          float t = ldg_stream1(Trow + (size_t)(a0 + i) * S + j);
+          acc[i] += (TV)t * __ldg(Vb + (size_t)(a0 + i) * v_action_stride + j);
+        }
+    }
+  }
+}
+
+// GROUP_CTA == false: one warp per (instance, state); GROUP_CTA == true: one CTA per (instance, state).
+template <typename TV, int FOLD, bool VEC, bool GROUP_CTA>
+__global__ void __launch_bounds__(kThreads) backup_kernel(const colo_backup_args p) {
+  using resid_t = typename VecOf<TV>::resid_t;
+  __shared__ TV s_part[kWarps][kAT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = p.S, A = p.A, nrows = p.nrows;
+  const long long items = (long long)p.B * nrows;
+  const long long first = GROUP_CTA ? blockIdx.x : (long long)blockIdx.x * kWarps + warp;
+  const long long step = GROUP_CTA ? gridDim.x : (long long)gridDim.x * kWarps;
+  const int tid = GROUP_CTA ? threadIdx.x : lane;
+  const int nthr = GROUP_CTA ? kThreads : 32;
+  const bool leader = GROUP_CTA ? threadIdx.x == 0 : lane == 0;
+  const TV* V_in = reinterpret_cast<const TV*>(p.V_in);
+  TV* V_out = reinterpret_cast<TV*>(p.V_out);
+  TV* Q = reinterpret_cast<TV*>(p.Q);
+  const TV gamma = (TV)p.gamma;
+
+  for (long long it = first; it < items; it += step) {
+    const int b = (int)(it / nrows);
+    const int sl = (int)(it - (long long)b * nrows);  // shard-local state index
+    const int s = p.row0 + sl;                        // global state index
+    const TV* Vb = V_in + (size_t)b * p.v_in_stride;
+    if (p.active != nullptr && p.active[b] == 0) {
+      // converged instance of a batch: carry V forward so the ping-pong buffers stay consistent
+      if (leader && V_out != nullptr && p.v_action_stride == 0) V_out[(size_t)b * p.v_out_stride + s] = Vb[s];
+      continue;
+    }
+    const float* Trow = p.T + (size_t)b * p.t_stride + (size_t)sl * A * S;
+    const int excl = p.exclude_index ? p.exclude_index[b] : -1;
+    TV folded = FOLD == COLO_FOLD_MIN ? (TV)INFINITY : (FOLD == COLO_FOLD_MAX ? (TV)-INFINITY : (TV)0);
+    for (int a0 = 0; a0 < A; a0 += kAT) {
+      const int na = min(kAT, A - a0);
+      TV acc[kAT];
+      rows_dot<TV, VEC>(Trow, Vb, p.v_action_stride, a0, na, S, tid, nthr, acc);
+#pragma unroll
+      for (int i = 0; i < kAT; ++i) acc[i] = warp_sum(acc[i]);
+      if (GROUP_CTA) {
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < kAT; ++i) s_part[warp][i] = acc[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int i = 0; i < kAT; ++i) {
+            TV t = 0;
+            for (int w = 0; w < kWarps; ++w) t += s_part[w][i];
+            acc[i] = t;
+          }
+        }
+        __syncthreads();
+      }
+      if (leader) {
+#pragma unroll
+        for (int i = 0; i < kAT; ++i)
+          if (i < na) {
+            const int a = a0 + i;
+            TV dot = acc[i];
+            if (excl >= 0)  // one next state's V is replaced by a constant (episodic diameter: the ns == es term)
+              dot += (TV)Trow[(size_t)a * S + excl] * ((TV)p.exclude_value - Vb[(size_t)a * p.v_action_stride + excl]);
+            const TV r = p.R ? (TV)p.R[(size_t)b * p.r_stride + (size_t)sl * A + a] : (TV)p.r_const;
+            const TV q = r + gamma * dot;
+            if (Q) Q[(size_t)b * p.q_stride + (size_t)sl * A + a] = q;
+            if (FOLD == COLO_FOLD_MAX) folded = q > folded ? q : folded;
+            if (FOLD == COLO_FOLD_MIN) folded = q < folded ? q : folded;
+            if (FOLD == COLO_FOLD_PI) folded += q * (TV)p.pi[(size_t)b * p.pi_stride + (size_t)sl * A + a];
+          }
+      }
+    }
+    if (leader && V_out != nullptr) {
+      if (p.pin_index != nullptr && p.pin_index[b] == s) folded = (TV)p.pin_value;
+      TV* vo = V_out + (size_t)b * p.v_out_stride + s;
+      const TV old = p.resid_vs_out ? *vo : Vb[s];
+      *vo = folded;
+      for (int r = 0; r < p.n_peers; ++r)  // fused all-gather: the row also lands in every peer GPU's V
+        reinterpret_cast<TV*>(p.V_out_peers[r])[(size_t)b * p.v_out_stride + s] = folded;
+      if (p.resid != nullptr) {
+        const TV d = fabs(folded - old);
+        if (d > (TV)0) atomic_max_nonneg(reinterpret_cast<resid_t*>(p.resid) + b, d);
+      }
+      if (p.max_abs > 0.0 && fabs((double)folded) > p.max_abs && p.overflow_flag) *p.overflow_flag = 1;
+    }
+  }
+}
+
+template <typename TV, int FOLD, bool VEC>
+static int launch_backup_2(const colo_backup_args& p, bool group_cta, cudaStream_t st) {
+  const long long items = (long long)p.B * p.nrows;
+  if (items == 0) return COLO_OK;
+  const int cap = sm_count() * 32;
+  if (group_cta) {
+    int grid = (int)(items < cap ? items : cap);
+    backup_kernel<TV, FOLD, VEC, true><<<grid, kThreads, 0, st>>>(p);
+  } else {
+    long long blocks = (items + kWarps - 1) / kWarps;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    backup_kernel<TV, FOLD, VEC, false><<<grid, kThreads, 0, st>>>(p);
+  }
+  return check_launch("backup_kernel");
+}
+
+template <typename TV>
+int launch_backup(const colo_backup_args* pp, void* stream) {
+  COLO_ARG_CHECK(pp != nullptr, "args is NULL");
+  colo_backup_args p = *pp;
+  COLO_ARG_CHECK(p.T && p.V_in, "T and V_in are required");
+  COLO_ARG_CHECK(p.B >= 0 && p.S > 0 && p.A > 0, "B,S,A");
+  COLO_ARG_CHECK(p.fold >= 0 && p.fold <= 2, "fold");
+  COLO_ARG_CHECK(p.fold != COLO_FOLD_PI || p.pi, "pi is required for COLO_FOLD_PI");
+  if (p.nrows == 0 && p.row0 == 0) p.nrows = p.S;
+  COLO_ARG_CHECK(p.row0 >= 0 && p.nrows >= 0 && p.row0 + p.nrows <= p.S, "row0/nrows");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (p.S % 4 == 0) && ((uintptr_t)p.T % 16 == 0) && ((uintptr_t)p.V_in % 16 == 0) &&
+                   (p.t_stride % 4 == 0) && (p.v_in_stride % 4 == 0) && (p.v_action_stride % 4 == 0);
+  // one warp per state while that still fills the machine; one CTA per state for few, long rows
+  const long long items = (long long)p.B * p.nrows;
+  const bool group_cta = (items < (long long)sm_count() * 64) && ((long long)p.S * p.A >= 4096);
+#define COLO_DISPATCH(FOLD)                                                            \
+  return vec ? launch_backup_2<TV, FOLD, true>(p, group_cta, st) : launch_backup_2<TV, FOLD, false>(p, group_cta, st)
+  switch (p.fold) {
+    case COLO_FOLD_MAX: COLO_DISPATCH(COLO_FOLD_MAX);
+    case COLO_FOLD_PI: COLO_DISPATCH(COLO_FOLD_PI);
+    default: COLO_DISPATCH(COLO_FOLD_MIN);
+  }
+#undef COLO_DISPATCH
+}
+
+// ---- small helper kernels -----------------------------------------------------------------------------------
+template <typename TV>
+__global__ void finish_sweep_kernel(typename VecOf<TV>::resid_t* resid, unsigned char* active, long long* iters,
+                                    int B, TV eps, int* flags) {
+  // after one sweep: iters++ for the instances that ran it; an instance whose max|dV| < eps stops
+  // (infinite_horizon.py:140-141); flags[0] counts the instances still running.
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int still = 0;
+  if (b < B && active[b]) {
+    TV r;
+    if (sizeof(TV) == 4)
+      r = (TV)__uint_as_float((unsigned int)resid[b]);
+    else
+      r = (TV)__longlong_as_double((long long)resid[b]);
+    iters[b] += 1;
+    if (r < eps)
+      active[b] = 0;
+    else
+      still = 1;
+    resid[b] = 0;
+  }
+  still = __syncthreads_count(still);
+  if (threadIdx.x == 0 && still) atomicAdd(&flags[0], still);
+}
+
+template <typename TV>
+__global__ void fill_kernel(TV* x, long long n, TV v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+
+template <typename TV>
+__global__ void max_reduce_kernel(const TV* x, long long n, TV* out, int take_sqrt) {
+  // single-CTA deterministic max (n is small: S or K*S)
+  __shared__ TV sm[32];
+  TV m = -INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = x[i] > m ? x[i] : m;
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : (TV)-INFINITY;
+    m = warp_max(m);
+    if (threadIdx.x == 0) out[0] = take_sqrt ? (TV)sqrt((double)(m > 0 ? m : 0)) : m;
+  }
+}
+
+template <typename TV>
+__global__ void sqdev_kernel(const TV* V, const TV* Ev, int S, int A, TV* W) {
+  // W[a,j] = (V[j] - Ev[j,a])^2   (value_norm.py:87: Ev indexed by the NEXT state j, sic)
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S * A) {
+    int a = i / S, j = i - a * S;
+    TV d = V[j] - Ev[(size_t)j * A + a];
+    W[i] = d * d;
+  }
+}
+
+__global__ void gaps_kernel(const double* Q, const double* V, const unsigned char* mask, long long NS, int A,
+                            double reg, double* out) {
+  // sum_{n,a} 1/(V[n]-Q[n,a]+reg): fixed thread-strided order + fixed tree -> deterministic
+  __shared__ double sm[1024];
+  double acc = 0.0;
+  for (long long n = threadIdx.x; n < NS; n += blockDim.x) {
+    if (mask && !mask[n]) continue;
+    const double v = V[n];
+    for (int a = 0; a < A; ++a) acc += 1.0 / (v - Q[n * A + a] + reg);
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+template <typename TV>
+__global__ void episodic_last_layer_kernel(const float* start_row, const TV* E, long long e_stride, int S, int H,
+                                           typename VecOf<TV>::resid_t* resid) {
+  // diameter.py:293  ETs[-1] = T[-1,0,0] @ (1 + ETs[0])  for target k = blockIdx.x (every state gets the value);
+  // stored form F = 1 + ETs:  F[H-1,:] = 1 + start . F[0,:]
+  using resid_t = typename VecOf<TV>::resid_t;
+  __shared__ TV sm[32];
+  __shared__ TV s_val;
+  TV* Ek = const_cast<TV*>(E) + (size_t)blockIdx.x * e_stride;
+  TV acc = 0;
+  for (int ns = threadIdx.x; ns < S; ns += blockDim.x) acc += (TV)start_row[ns] * Ek[ns];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    TV t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    s_val = (TV)1 + t;
+  }
+  __syncthreads();
+  const TV v = s_val;
+  TV* last = Ek + (size_t)(H - 1) * S;
+  TV d = 0;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    TV dd = fabs(v - last[j]);
+    d = dd > d ? dd : d;
+    last[j] = v;
+  }
+  d = warp_max(d);
+  if ((threadIdx.x & 31) == 0 && d > 0 && resid) atomic_max_nonneg(reinterpret_cast<resid_t*>(resid) + blockIdx.x, d);
+}
+
+template <typename TV>
+__global__ void episodic_diam_reduce_kernel(const TV* E, int K, int H, int S, TV* out) {
+  // diameter.py:311-314: per state the min over h of the POSITIVE entries, max over states, max over targets
+  __shared__ TV sm[32];
+  TV best = -INFINITY;
+  for (long long i = threadIdx.x; i < (long long)K * S; i += blockDim.x) {
+    const int k = (int)(i / S), s = (int)(i - (long long)k * S);
+    TV mn = INFINITY;
+    for (int h = 0; h < H; ++h) {
+      TV v = E[((size_t)k * H + h) * S + s] - (TV)1;  // stored F = 1 + ETs
+      if (v > 0 && v < mn) mn = v;
+    }
+    best = mn > best ? mn : best;
+  }
+  best = warp_max(best);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : (TV)-INFINITY;
+    best = warp_max(best);
+    if (threadIdx.x == 0) out[0] = best;
+  }
+}
+
+// ---- host-side solvers ----------------------------------------------------------------------------------------
+struct SolveWork {  // carved from the caller's `work` buffer
+  void* v_alt;
+  void* resid;
+  unsigned char* active;
+  long long* iters;
+  int* flags;  // [0] still-running count, [1] overflow
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename TV>
+static size_t solve_work_bytes(long long B, long long S) {
+  size_t n = 0;
+  n += align_up((size_t)B * S * sizeof(TV), 256);
+  n += align_up((size_t)B * sizeof(typename VecOf<TV>::resid_t), 256);
+  n += align_up((size_t)B, 256);
+  n += align_up((size_t)B * sizeof(long long), 256);
+  n += 256;
+  return n;
+}
+
+template <typename TV>
+static SolveWork carve(void* work, long long B, long long S) {
+  char* p = (char*)work;
+  SolveWork w;
+  w.v_alt = p;
+  p += align_up((size_t)B * S * sizeof(TV), 256);
+  w.resid = p;
+  p += align_up((size_t)B * sizeof(typename VecOf<TV>::resid_t), 256);
+  w.active = (unsigned char*)p;
+  p += align_up((size_t)B, 256);
+  w.iters = (long long*)p;
+  p += align_up((size_t)B * sizeof(long long), 256);
+  w.flags = (int*)p;
+  return w;
+}
+
+// Iterate `sweep(V_cur, V_nxt)` until every instance has max|dV| < eps.  The host only looks at two ints every
+// `check` sweeps; instance-level stopping happens on the device (active mask), so late checks cost nothing but
+// idle sweeps of already-frozen instances.
+template <typename TV, typename SweepFn>
+static int iterate_to_convergence(SweepFn sweep, TV* V_user, SolveWork& w, long long B, long long S, TV eps,
+                                  long long max_iter, long long* iters_out_host, long long* sweeps_run,
+                                  cudaStream_t st) {
+  using resid_t = typename VecOf<TV>::resid_t;
+  COLO_CUDA_TRY(cudaMemsetAsync(V_user, 0, (size_t)B * S * sizeof(TV), st));
+  COLO_CUDA_TRY(cudaMemsetAsync(w.resid, 0, (size_t)B * sizeof(resid_t), st));
+  COLO_CUDA_TRY(cudaMemsetAsync(w.active, 1, (size_t)B, st));
+  COLO_CUDA_TRY(cudaMemsetAsync(w.iters, 0, (size_t)B * sizeof(long long), st));
+  COLO_CUDA_TRY(cudaMemsetAsync(w.flags, 0, 2 * sizeof(int), st));
+  TV* cur = V_user;
+  TV* nxt = (TV*)w.v_alt;
+  int rc = COLO_MAX_ITER;
+  long long it = 0;
+  int check = 1;
+  int h_flags[2] = {0, 0};
+  while (it < max_iter) {
+    long long burst = check;
+    if (it + burst > max_iter) burst = max_iter - it;
+    for (long long i = 0; i < burst; ++i) {
+      if (i == burst - 1) COLO_CUDA_TRY(cudaMemsetAsync(w.flags, 0, sizeof(int), st));
+      int r = sweep(cur, nxt);
+      if (r != COLO_OK) return r;
+      finish_sweep_kernel<TV><<<(int)((B + 255) / 256), 256, 0, st>>>((resid_t*)w.resid, w.active, w.iters, (int)B,
+                                                                    eps, w.flags);
+      r = check_launch("finish_sweep_kernel");
+      if (r != COLO_OK) return r;
+      TV* t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+    it += burst;
+    COLO_CUDA_TRY(cudaMemcpyAsync(h_flags, w.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    COLO_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_flags[1]) {
+      rc = COLO_OVERFLOW;
+      break;
+    }
+    if (h_flags[0] == 0) {
+      rc = COLO_OK;
+      break;
+    }
+    if (check < 64) check *= 2;
+  }
+  if (cur != V_user) COLO_CUDA_TRY(cudaMemcpyAsync(V_user, cur, (size_t)B * S * sizeof(TV), cudaMemcpyDeviceToDevice, st));
+  if (iters_out_host)
+    COLO_CUDA_TRY(cudaMemcpyAsync(iters_out_host, w.iters, (size_t)B * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  COLO_CUDA_TRY(cudaStreamSynchronize(st));
+  if (sweeps_run) *sweeps_run = it;
+  return rc;
+}
+
+template <typename TV>
+int solve_discounted(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma, double eps,
+                     double max_abs, long long max_iter, int fold, TV* Q, TV* V, long long* iters_out_host,
+                     void* work, void* stream) {
+  COLO_ARG_CHECK(T && R && V && work, "T, R, V, work are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  SolveWork w = carve<TV>(work, B, S);
+  colo_backup_args a = {};
+  a.T = T; a.R = R; a.pi = pi; a.Q = Q;
+  a.B = B; a.S = S; a.A = A; a.fold = fold; a.gamma = gamma;
+  a.t_stride = (long long)S * A * S; a.r_stride = (long long)S * A; a.pi_stride = (long long)S * A;
+  a.v_in_stride = S; a.v_out_stride = S; a.q_stride = (long long)S * A;
+  a.resid = w.resid; a.active = w.active; a.max_abs = max_abs; a.overflow_flag = w.flags + 1;
+  a.row0 = 0; a.nrows = S;
+  auto sweep = [&](TV* cur, TV* nxt) {
+    a.V_in = cur;
+    a.V_out = nxt;
+    return launch_backup<TV>(&a, stream);
+  };
+  return iterate_to_convergence<TV>(sweep, V, w, B, S, (TV)eps, max_iter, iters_out_host, nullptr, st);
+}
+
+template <typename TV>
+int episodic(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold, double max_value,
+             TV* Q, TV* V, void* stream) {
+  COLO_ARG_CHECK(T && R && V && Q, "T, R, Q, V are required");
+  COLO_ARG_CHECK(H >= 0, "H");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long qs = (long long)(H + 1) * S * A, vs = (long long)(H + 1) * S;
+  int* flag = nullptr;
+  if (max_value > 0) {
+    COLO_CUDA_TRY(cudaMallocAsync(&flag, sizeof(int), st));
+    COLO_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  }
+  // rows H are zero (finite_horizon.py:17-18); cudaMemset2D clears the last layer of every instance
+  COLO_CUDA_TRY(cudaMemset2DAsync(V + (size_t)H * S, vs * sizeof(TV), 0, (size_t)S * sizeof(TV), B, st));
+  COLO_CUDA_TRY(cudaMemset2DAsync(Q + (size_t)H * S * A, qs * sizeof(TV), 0, (size_t)S * A * sizeof(TV), B, st));
+  colo_backup_args a = {};
+  a.T = T; a.R = R;
+  a.B = B; a.S = S; a.A = A; a.fold = fold; a.gamma = 1.0;
+  a.t_stride = (long long)S * A * S; a.r_stride = (long long)S * A; a.pi_stride = (long long)H * S * A;
+  a.v_in_stride = vs; a.v_out_stride = vs; a.q_stride = qs;
+  a.max_abs = fold == COLO_FOLD_MAX ? max_value : 0.0; a.overflow_flag = flag;
+  a.row0 = 0; a.nrows = S;
+  for (int h = H - 1; h >= 0; --h) {
+    a.V_in = V + (size_t)(h + 1) * S;
+    a.V_out = V + (size_t)h * S;
+    a.Q = Q + (size_t)h * S * A;
+    a.pi = pi ? pi + (size_t)h * S * A : nullptr;
+    int r = launch_backup<TV>(&a, stream);
+    if (r != COLO_OK) return r;
+  }
+  if (flag) {
+    int hflag = 0;
+    COLO_CUDA_TRY(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    COLO_CUDA_TRY(cudaStreamSynchronize(st));
+    COLO_CUDA_TRY(cudaFreeAsync(flag, st));
+    if (hflag) return COLO_OVERFLOW;
+  }
+  return COLO_OK;
+}
+
+template <typename TV>
+int diameter_continuous(const float* T, const int* targets, int K, int S, int A, double eps, double max_value,
+                        long long max_iter, void* work, double* out_host, void* stream) {
+  COLO_ARG_CHECK(T && targets && work && out_host, "T, targets, work, out_host are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  // work = E ping [K*S] | solver work (E pong, resid, active, iters, flags) | 1 TV result
+  TV* E = (TV*)work;
+  char* rest = (char*)work + align_up((size_t)K * S * sizeof(TV), 256);
+  SolveWork w = carve<TV>(rest, K, S);
+  TV* d_out = (TV*)(rest + solve_work_bytes<TV>(K, S));
+  colo_backup_args a = {};
+  a.T = T; a.R = nullptr; a.r_const = 1.0;
+  a.B = K; a.S = S; a.A = A; a.fold = COLO_FOLD_MIN; a.gamma = 1.0;
+  a.t_stride = 0;  // every target shares T: row tiles are re-served from L2 across targets
+  a.v_in_stride = S; a.v_out_stride = S;
+  a.pin_index = targets; a.pin_value = 0.0;
+  a.resid = w.resid; a.active = w.active; a.max_abs = max_value; a.overflow_flag = w.flags + 1;
+  a.row0 = 0; a.nrows = S;
+  auto sweep = [&](TV* cur, TV* nxt) {
+    a.V_in = cur;
+    a.V_out = nxt;
+    return launch_backup<TV>(&a, stream);
+  };
+  long long sweeps = 0;
+  int rc = iterate_to_convergence<TV>(sweep, E, w, K, S, (TV)eps, max_iter, nullptr, &sweeps, st);
+  if (rc != COLO_OK && rc != COLO_MAX_ITER) return rc;
+  max_reduce_kernel<TV><<<1, 1024, 0, st>>>(E, (long long)K * S, d_out, 0);
+  int r = check_launch("max_reduce_kernel");
+  if (r != COLO_OK) return r;
+  TV h = 0;
+  COLO_CUDA_TRY(cudaMemcpyAsync(&h, d_out, sizeof(TV), cudaMemcpyDeviceToHost, st));
+  COLO_CUDA_TRY(cudaStreamSynchronize(st));
+  out_host[0] = (double)h;
+  out_host[1] = (double)sweeps;
+  return rc;
+}
+
+template <typename TV>
+int diameter_episodic(const float* T_epi, const int* targets, int K, int H, int S, int A, double eps, double max_value,
+                      long long max_iter, void* work, double* out_host, void* stream) {
+  using resid_t = typename VecOf<TV>::resid_t;
+  COLO_ARG_CHECK(T_epi && targets && work && out_host, "T_epi, targets, work, out_host are required");
+  COLO_ARG_CHECK(H >= 2, "H >= 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  // work = F [K,H,S] | resid [K] | flags [2] | result        (F = 1 + ETs of diameter.py:285-318)
+  char* p = (char*)work;
+  TV* E = (TV*)p;
+  p += align_up((size_t)K * H * S * sizeof(TV), 256);
+  resid_t* resid = (resid_t*)p;
+  p += align_up((size_t)K * sizeof(resid_t), 256);
+  int* flags = (int*)p;
+  p += 256;
+  TV* d_out = (TV*)p;
+  COLO_CUDA_TRY(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+  // F = 1 + ETs is what is stored (ETs = 0 everywhere at the start, diameter.py:289)
+  fill_kernel<TV><<<(int)(((long long)K * H * S + 255) / 256), 256, 0, st>>>(E, (long long)K * H * S, (TV)1);
+  int r = check_launch("fill_kernel");
+  if (r != COLO_OK) return r;
+  colo_backup_args a = {};
+  a.B = K; a.S = S; a.A = A; a.fold = COLO_FOLD_MIN; a.gamma = 1.0;
+  a.t_stride = 0; a.r_stride = 0;
+  a.v_in_stride = (long long)H * S; a.v_out_stride = (long long)H * S;
+  // F[h-1,j] = min_a( 1 + sum_ns T[h-1,j,a,ns] * (ns == es ? 1 : F[h,ns]) );  F[h-1,es] = 1
+  a.r_const = 1.0;
+  a.pin_index = targets; a.pin_value = 1.0; a.exclude_index = targets; a.exclude_value = 1.0;
+  a.resid = resid; a.resid_vs_out = 1; a.max_abs = max_value > 0 ? max_value + 1.0 : 0.0; a.overflow_flag = flags + 1;
+  a.row0 = 0; a.nrows = S;
+  int rc = COLO_MAX_ITER;
+  long long it = 0;
+  int check = 1, since = 0;
+  std::vector<resid_t> h_res((size_t)K);
+  int h_flags[2];
+  for (; it < max_iter;) {
+    COLO_CUDA_TRY(cudaMemsetAsync(resid, 0, (size_t)K * sizeof(resid_t), st));
+    episodic_last_layer_kernel<TV><<<K, 128, 0, st>>>(T_epi + (size_t)(H - 1) * S * A * S, E, (long long)H * S, S, H,
+                                                     resid);
+    r = check_launch("episodic_last_layer_kernel");
+    if (r != COLO_OK) return r;
+    for (int h = H - 1; h >= 1; --h) {
+      a.T = T_epi + (size_t)(h - 1) * S * A * S;
+      a.V_in = E + (size_t)h * S;
+      a.V_out = E + (size_t)(h - 1) * S;
+      r = launch_backup<TV>(&a, stream);
+      if (r != COLO_OK) return r;
+    }
+    ++it;
+    if (++since >= check) {
+      since = 0;
+      COLO_CUDA_TRY(cudaMemcpyAsync(h_res.data(), resid, (size_t)K * sizeof(resid_t), cudaMemcpyDeviceToHost, st));
+      COLO_CUDA_TRY(cudaMemcpyAsync(h_flags, flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      COLO_CUDA_TRY(cudaStreamSynchronize(st));
+      if (h_flags[1]) {
+        rc = COLO_OVERFLOW;
+        break;
+      }
+      resid_t mx = 0;
+      for (auto v : h_res) mx = v > mx ? v : mx;
+      TV res;
+      if (sizeof(TV) == 4) {
+        unsigned int u = (unsigned int)mx;
+        float f;
+        memcpy(&f, &u, 4);
+        res = (TV)f;
+      } else {
+        unsigned long long u = (unsigned long long)mx;
+        double f;
+        memcpy(&f, &u, 8);
+        res = (TV)f;
+      }
+      if (res < (TV)eps) {
+        rc = COLO_OK;
+        break;
+      }
+      if (check < 8) check *= 2;
+    }
+  }
+  if (rc == COLO_OVERFLOW) return rc;
+  episodic_diam_reduce_kernel<TV><<<1, 1024, 0, st>>>(E, K, H, S, d_out);
+  r = check_launch("episodic_diam_reduce_kernel");
+  if (r != COLO_OK) return r;
+  TV hval = 0;
+  COLO_CUDA_TRY(cudaMemcpyAsync(&hval, d_out, sizeof(TV), cudaMemcpyDeviceToHost, st));
+  COLO_CUDA_TRY(cudaStreamSynchronize(st));
+  out_host[0] = (double)hval;
+  out_host[1] = (double)it;
+  return rc;
+}
+
+template <typename TV>
+int value_norm(const float* T, const TV* V, int S, int A, void* work, TV* out, void* stream) {
+  COLO_ARG_CHECK(T && V && work && out, "T, V, work, out are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  TV* Ev = (TV*)work;                                 // [S,A]
+  TV* W = Ev + align_up((size_t)S * A, 64);           // [A,S]
+  TV* rowmax = W + align_up((size_t)S * A, 64);       // [S]
+  colo_backup_args a = {};
+  a.T = T; a.B = 1; a.S = S; a.A = A; a.fold = COLO_FOLD_MAX; a.gamma = 1.0; a.r_const = 0.0;
+  a.v_in_stride = S; a.q_stride = (long long)S * A; a.row0 = 0; a.nrows = S;
+  a.V_in = V; a.V_out = nullptr; a.Q = Ev;  // pass 1: Ev[i,a] = sum_j T[i,a,j] V[j]
+  int r = launch_backup<TV>(&a, stream);
+  if (r != COLO_OK) return r;
+  sqdev_kernel<TV><<<(S * A + 255) / 256, 256, 0, st>>>(V, Ev, S, A, W);
+  r = check_launch("sqdev_kernel");
+  if (r != COLO_OK) return r;
+  // pass 2: sum_j T[i,a,j] * W[a,j], max over a into rowmax[i]
+  a.V_in = W; a.v_action_stride = S; a.V_out = rowmax; a.v_out_stride = S; a.Q = nullptr;
+  r = launch_backup<TV>(&a, stream);
+  if (r != COLO_OK) return r;
+  max_reduce_kernel<TV><<<1, 1024, 0, st>>>(rowmax, S, out, 1);
+  return check_launch("max_reduce_kernel");
+}
+
+}  // namespace colo
+
+// ---- C ABI --------------------------------------------------------------------------------------------------
+extern "C" {
+
+int colo_backup_f32(const colo_backup_args* args, void* stream) { return colo::launch_backup<float>(args, stream); }
+int colo_backup_f64acc(const colo_backup_args* args, void* stream) { return colo::launch_backup<double>(args, stream); }
+
+size_t colo_solve_work_bytes(long long B, long long S, int f64) {
+  return f64 ? colo::solve_work_bytes<double>(B, S) : colo::solve_work_bytes<float>(B, S);
+}
+
+int colo_solve_discounted_f32(const float* T, const float* R, const float* pi, int B, int S, int A, float gamma,
+                              float eps, float max_abs, long long max_iter, int fold, float* Q, float* V,
+                              long long* iters_out_host, void* work, void* stream) {
+  return colo::solve_discounted<float>(T, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_out_host,
+                                       work, stream);
+}
+int colo_solve_discounted_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma,
+                                 double eps, double max_abs, long long max_iter, int fold, double* Q, double* V,
+                                 long long* iters_out_host, void* work, void* stream) {
+  return colo::solve_discounted<double>(T, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_out_host,
+                                        work, stream);
+}
+
+int colo_episodic_f32(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
+                      float max_value, float* Q, float* V, void* stream) {
+  return colo::episodic<float>(T, R, pi, B, S, A, H, fold, max_value, Q, V, stream);
+}
+int colo_episodic_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
+                         double max_value, double* Q, double* V, void* stream) {
+  return colo::episodic<double>(T, R, pi, B, S, A, H, fold, max_value, Q, V, stream);
+}
+
+size_t colo_diameter_continuous_work_bytes(int K, int S, int f64) {
+  size_t e = f64 ? 8 : 4;
+  return colo::align_up((size_t)K * S * e, 256) +
+         (f64 ? colo::solve_work_bytes<double>(K, S) : colo::solve_work_bytes<float>(K, S)) + 256;
+}
+int colo_diameter_continuous_f32(const float* T, const int* targets, int K, int S, int A, float eps, float max_value,
+                                 long long max_iter, void* work, double* out_host, void* stream) {
+  return colo::diameter_continuous<float>(T, targets, K, S, A, eps, max_value, max_iter, work, out_host, stream);
+}
+int colo_diameter_continuous_f64acc(const float* T, const int* targets, int K, int S, int A, double eps,
+                                    double max_value, long long max_iter, void* work, double* out_host,
+                                    void* stream) {
+  return colo::diameter_continuous<double>(T, targets, K, S, A, eps, max_value, max_iter, work, out_host, stream);
+}
+
+size_t colo_diameter_episodic_work_bytes(int K, int H, int S, int A, int f64) {
+  size_t e = f64 ? 8 : 4;
+  (void)A;
+  return colo::align_up((size_t)K * H * S * e, 256) + colo::align_up((size_t)K * 8, 256) + 512;
+}
+int colo_diameter_episodic_f32(const float* T_epi, const int* targets, int K, int H, int S, int A, float eps,
+                               float max_value, long long max_iter, void* work, double* out_host, void* stream) {
+  return colo::diameter_episodic<float>(T_epi, targets, K, H, S, A, eps, max_value, max_iter, work, out_host, stream);
+}
+int colo_diameter_episodic_f64acc(const float* T_epi, const int* targets, int K, int H, int S, int A, double eps,
+                                  double max_value, long long max_iter, void* work, double* out_host, void* stream) {
+  return colo::diameter_episodic<double>(T_epi, targets, K, H, S, A, eps, max_value, max_iter, work, out_host, stream);
+}
+
+size_t colo_value_norm_work_bytes(int S, int A, int f64) {
+  size_t e = f64 ? 8 : 4;
+  return (2 * colo::align_up((size_t)S * A, 64) + colo::align_up((size_t)S, 64)) * e;
+}
+int colo_value_norm_f32(const float* T, const float* V, int S, int A, void* work, float* out, void* stream) {
+  return colo::value_norm<float>(T, V, S, A, work, out, stream);
+}
+int colo_value_norm_f64acc(const float* T, const double* V, int S, int A, void* work, double* out, void* stream) {
+  return colo::value_norm<double>(T, V, S, A, work, out, stream);
+}
+
+int colo_gaps_f64(const double* Q, const double* V, const unsigned char* mask, long long NS, int A, double reg,
+                  double* out, void* stream) {
+  COLO_ARG_CHECK(Q && V && out, "Q, V, out are required");
+  colo::gaps_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(Q, V, mask, NS, A, reg, out);
+  return colo::check_launch("gaps_kernel");
+}
+
+}  // extern "C"

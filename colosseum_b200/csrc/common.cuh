@@ -1,0 +1,106 @@
+// common.cuh -- shared helpers for libcolosseum_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/colosseum_b200.h"
+
+namespace colo {
+
+// ---- error plumbing -------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(unsigned long long n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> COLO_OK / COLO_ERR_CUDA (+ counts one launch)
+
+#define COLO_CUDA_TRY(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      colo::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return COLO_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define COLO_ARG_CHECK(cond, msg)                  \
+  do {                                             \
+    if (!(cond)) {                                 \
+      colo::set_error("bad argument: %s", msg);    \
+      return COLO_ERR_ARG;                         \
+    }                                              \
+  } while (0)
+
+int sm_count();  // SMs of the current device (148 on B200), cached
+
+// ---- device helpers -------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+// streaming 128-bit load: T tiles are read exactly once per sweep -> bypass L1 allocation, keep L1 for V
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    T w = __shfl_xor_sync(FULL, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+
+// non-negative float/double max through integer atomics (IEEE ordering == unsigned ordering for x >= 0)
+__device__ __forceinline__ void atomic_max_nonneg(unsigned int* addr, float v) { atomicMax(addr, __float_as_uint(v)); }
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long* addr, double v) {
+  atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+// ---- Philox4x32-10 (Salmon et al. SC'11): counter = (env lo, env hi, t lo, t hi), key = seed -------------
+struct Philox4 {
+  uint32_t w[4];
+};
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t env, uint64_t t) {
+  uint32_t c0 = (uint32_t)env, c1 = (uint32_t)(env >> 32), c2 = (uint32_t)t, c3 = (uint32_t)(t >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  Philox4 o;
+  o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+  return o;
+}
+// word -> uniform conventions (shared with oracle/colo_oracle.c)
+__host__ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {  // CPython random(): 53 bits
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+__host__ __device__ __forceinline__ float u24(uint32_t a) { return (float)(a >> 8) * (1.0f / 16777216.0f); }
+__host__ __device__ __forceinline__ int act_from_word(uint32_t w, int A) {
+  return (int)(((uint64_t)w * (uint64_t)A) >> 32);
+}
+
+}  // namespace colo

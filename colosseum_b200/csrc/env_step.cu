@@ -1,0 +1,403 @@
+// env_step.cu -- the batched agent/MDP interaction step (hot path A) for sm_100a.
+//
+// Restates BaseMDP.reset / BaseMDP.step (colosseum/mdp/base.py:1268-1317) for N independent episodes:
+//   next state  : inverse-CDF sampling == NextStateSampler.sample == CPython random.choices
+//                 (colosseum/mdp/utils/custom_samplers.py:49-72): bisect_right(cum, u*total, 0, n-1)
+//   reward      : BaseMDP.sample_reward (base.py:1187-1207): a draw of the per-(s,a,s') distribution through its
+//                 tabulated quantile function, then the reference's rescale r*(max-min) - min (sic)
+//   bookkeeping : h, episodic termination (LAST, obs -1), auto-reset, visitation counts on the NEXT node (sic).
+//
+// Dense kernel: a warp owns a tile of 32 consecutive envs.  Env scalars are loaded / stored coalesced (lane i <->
+// env i); the search over the dense CDF row T[s,a,:] is warp-cooperative: the row is read with 128-bit coalesced
+// loads, all issued before any is consumed, and because the row is monotone the bisect position is simply the
+// COUNT of entries <= x, i.e. one integer warp reduction, no branches and no early exit.
+#include "common.cuh"
+
+namespace colo {
+
+constexpr int kStepThreads = 256;
+
+struct StepIO {
+  long long N;
+  int* action;
+  int random_actions;
+  const void* u_next;
+  const float* u_rew;
+  unsigned long long seed, t, env0;
+  int auto_reset;
+  int* state;
+  int* h;
+  unsigned char* step_type;
+  float* reward;
+  int* obs;
+  unsigned long long* visits_s;
+  unsigned long long* visits_sa;
+  int* status;
+};
+
+__device__ __forceinline__ float reward_draw(const colo_mdp_tables& tb, int cls, float u) {
+  const float* q = tb.rew_q + (size_t)cls * tb.nq;
+  const float t = u * (float)(tb.nq - 1);
+  int i = (int)t;
+  i = i > tb.nq - 2 ? tb.nq - 2 : i;
+  const float f = t - (float)i;
+  const float q0 = __ldg(q + i), q1 = __ldg(q + i + 1);
+  const float r0 = fmaf(f, q1 - q0, q0);
+  return fmaf(r0, tb.rmax - tb.rmin, -tb.rmin);
+}
+
+// bisect_right(cum, x, 0, n-1) == number of k in [0, n-2] with cum[k] <= x   (cum is non-decreasing)
+__device__ __forceinline__ int bisect_count(const double* __restrict__ cum, int n, double x) {
+  int pos = 0;
+  for (int k = 0; k < n - 1; ++k) pos += (__ldg(cum + k) <= x) ? 1 : 0;
+  return pos;
+}
+
+__device__ __forceinline__ int sample_start(const colo_mdp_tables& tb, double u) {
+  if (tb.n_start == 1) return __ldg(tb.start_idx);
+  const double total = __ldg(tb.start_cum + tb.n_start - 1) + 0.0;
+  return __ldg(tb.start_idx + bisect_count(tb.start_cum, tb.n_start, u * total));
+}
+
+// warp-aggregated counter increment: lanes with equal keys elect one leader that adds the group size
+__device__ __forceinline__ void aggregated_inc(unsigned long long* base, long long key, bool valid) {
+  const unsigned act = __ballot_sync(FULL, valid);
+  if (!valid) return;
+  const unsigned peers = __match_any_sync(act, key);
+  const int leader = __ffs(peers) - 1;
+  if ((int)(threadIdx.x & 31) == leader) atomicAdd(base + key, (unsigned long long)__popc(peers));
+}
+
+template <typename TC>
+struct Quad;
+template <>
+struct Quad<float> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <>
+struct Quad<double> {
+  double v[4];
+  __device__ __forceinline__ void load(const double* p) {
+    double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+};
+
+// per-env prologue shared by all step kernels: resolves uniforms/actions, handles the reset path.
+// returns true when the env takes a regular step.
+struct EnvIn {
+  int s, a, st;
+  double un64;
+  float un32, ur;
+};
+
+template <bool F32U>
+__device__ __forceinline__ EnvIn load_env(const StepIO& io, const colo_mdp_tables& tb, long long e) {
+  EnvIn in;
+  in.st = io.step_type[e];
+  in.s = io.state[e];
+  Philox4 w;
+  const bool need_rng = io.u_next == nullptr || io.u_rew == nullptr || io.random_actions;
+  if (need_rng) w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, io.t);
+  if (io.u_next) {
+    if (F32U) {
+      in.un32 = reinterpret_cast<const float*>(io.u_next)[e];
+      in.un64 = (double)in.un32;
+    } else {
+      in.un64 = reinterpret_cast<const double*>(io.u_next)[e];
+      in.un32 = 0.f;
+    }
+  } else {
+    in.un64 = u53(w.w[0], w.w[1]);
+    in.un32 = u24(w.w[0]);
+  }
+  in.ur = io.u_rew ? io.u_rew[e] : u24(w.w[2]);
+  in.a = io.random_actions ? act_from_word(w.w[3], tb.A) : io.action[e];
+  return in;
+}
+
+// epilogue of a regular step for one env held by this thread
+__device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tables& tb, long long e, const EnvIn& in,
+                                           int nxt, int cls, bool stepping, bool resetting) {
+  if (resetting) {  // auto_reset path == BaseMDP.reset(): the action is ignored, reward is None (NaN here)
+    nxt = sample_start(tb, in.un64);
+    io.state[e] = nxt;
+    io.h[e] = 0;
+    io.step_type[e] = COLO_STEP_FIRST;
+    io.reward[e] = __int_as_float(0x7fc00000);
+    io.obs[e] = nxt;
+  } else if (stepping) {
+    const int hh = io.h[e] + 1;
+    io.h[e] = hh;
+    io.state[e] = nxt;
+    io.reward[e] = reward_draw(tb, cls, in.ur);
+    if (io.random_actions) io.action[e] = in.a;
+    if (tb.H > 0 && hh >= tb.H) {
+      io.step_type[e] = COLO_STEP_LAST;
+      io.obs[e] = -1;
+    } else {
+      io.step_type[e] = COLO_STEP_MID;
+      io.obs[e] = nxt;
+    }
+  }
+  if (io.visits_s) aggregated_inc(io.visits_s, nxt, stepping || resetting);
+  if (io.visits_sa) aggregated_inc(io.visits_sa, (long long)nxt * tb.A + in.a, stepping);
+}
+
+template <typename TC, int NCH>
+__global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo_mdp_tables tb, const StepIO io) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * kStepThreads + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * kStepThreads) >> 5;
+  const long long n_tiles = (io.N + 31) >> 5;
+  const int S = tb.S, A = tb.A, ld = tb.ld;
+  const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
+  constexpr bool F32U = sizeof(TC) == 4;
+
+  for (long long tile = warp_global; tile < n_tiles; tile += n_warps) {
+    const long long e = tile * 32 + lane;
+    const bool valid = e < io.N;
+    EnvIn in;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    if (valid) in = load_env<F32U>(io, tb, e);
+    const bool is_last = valid && in.st == COLO_STEP_LAST;
+    const bool resetting = is_last && io.auto_reset;
+    const bool stepping = valid && !is_last;
+    if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
+    const unsigned step_mask = __ballot_sync(FULL, stepping);
+
+    int my_next = 0;
+    // the warp walks over the envs of its tile; every lane helps searching env i's row
+    for (int i = 0; i < 32; ++i) {
+      if (!((step_mask >> i) & 1u)) continue;  // warp-uniform
+      const int s_i = __shfl_sync(FULL, in.s, i);
+      const int a_i = __shfl_sync(FULL, in.a, i);
+      const TC u_i = F32U ? (TC)__shfl_sync(FULL, in.un32, i) : (TC)__shfl_sync(FULL, in.un64, i);
+      const TC* row = cdf + ((size_t)s_i * A + a_i) * ld;
+      const TC total = __ldg(row + S - 1);
+      int cnt_le = 0, cnt_lt = 0;
+      for (int g = 0; g < ld; g += 128 * NCH) {
+        Quad<TC> q[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int c = g + k * 128 + lane * 4;
+          if (c < ld) q[k].load(row + c);
+        }
+        const TC x = u_i * total;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int c = g + k * 128 + lane * 4;
+          if (c < ld) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              cnt_le += (q[k].v[m] <= x) ? 1 : 0;      // entries <= x  -> first j with cdf[j] > x
+              cnt_lt += (q[k].v[m] < total) ? 1 : 0;   // entries < total -> last positive-probability index
+            }
+          }
+        }
+      }
+      int j1, j2;
+      if (ld < 65536) {
+        int packed = warp_sum(cnt_le | (cnt_lt << 16));
+        j1 = packed & 0xffff;
+        j2 = packed >> 16;
+      } else {
+        j1 = warp_sum(cnt_le);
+        j2 = warp_sum(cnt_lt);
+      }
+      const int nxt = j1 < j2 ? j1 : j2;
+      if (lane == i) my_next = nxt;
+    }
+    int cls = 0;
+    if (stepping) {
+      if (tb.rew_cls_sas)
+        cls = tb.rew_cls_sas[((size_t)in.s * A + in.a) * S + my_next];
+      else if (tb.rew_cls_sa)
+        cls = tb.rew_cls_sa[(size_t)in.s * A + in.a];
+    }
+    finish_env(io, tb, valid ? e : 0, in, my_next, cls, stepping, resetting);
+  }
+}
+
+__global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_mdp_tables tb, const StepIO io) {
+  const long long n_thr = (long long)gridDim.x * kStepThreads;
+  // round the loop bound up to whole warps: finish_env uses warp collectives
+  const long long n_pad = (io.N + 31) & ~31LL;
+  for (long long e = (long long)blockIdx.x * kStepThreads + threadIdx.x; e < n_pad; e += n_thr) {
+    const bool valid = e < io.N;
+    EnvIn in;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    if (valid) in = load_env<false>(io, tb, e);
+    const bool is_last = valid && in.st == COLO_STEP_LAST;
+    const bool resetting = is_last && io.auto_reset;
+    const bool stepping = valid && !is_last;
+    if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
+    int nxt = 0, cls = 0;
+    if (stepping) {
+      const size_t sa = (size_t)in.s * tb.A + in.a;
+      const size_t base = sa * tb.Ksucc;
+      const int n = __ldg(tb.succ_len + sa);
+      int pos = 0;
+      if (n > 1) {
+        const double total = __ldg(tb.succ_cum + base + n - 1) + 0.0;
+        pos = bisect_count(tb.succ_cum + base, n, in.un64 * total);
+      }
+      nxt = __ldg(tb.succ_idx + base + pos);
+      cls = tb.rew_cls_succ ? __ldg(tb.rew_cls_succ + base + pos) : 0;
+    }
+    finish_env(io, tb, valid ? e : 0, in, nxt, cls, stepping, resetting);
+  }
+}
+
+__global__ void __launch_bounds__(kStepThreads) env_reset_kernel(const colo_mdp_tables tb, long long N,
+                                                                 const double* u_next, unsigned long long seed,
+                                                                 unsigned long long t, unsigned long long env0,
+                                                                 int* state, int* h,
+                                                                 unsigned char* step_type, int* obs,
+                                                                 unsigned long long* visits_s) {
+  const long long n_thr = (long long)gridDim.x * kStepThreads;
+  const long long n_pad = (N + 31) & ~31LL;
+  for (long long e = (long long)blockIdx.x * kStepThreads + threadIdx.x; e < n_pad; e += n_thr) {
+    const bool valid = e < N;
+    int s0 = 0;
+    if (valid) {
+      double u;
+      if (u_next)
+        u = u_next[e];
+      else {
+        Philox4 w = philox4x32_10(seed, env0 + (uint64_t)e, t);
+        u = u53(w.w[0], w.w[1]);
+      }
+      s0 = sample_start(tb, u);
+      state[e] = s0;
+      h[e] = 0;
+      step_type[e] = COLO_STEP_FIRST;
+      obs[e] = s0;
+    }
+    if (visits_s) aggregated_inc(visits_s, s0, valid);
+  }
+}
+
+template <typename TC>
+__global__ void build_dense_cdf_kernel(const float* __restrict__ T, int S, int A, int ld, TC* __restrict__ cdf) {
+  // one thread per (s,a) row: sequential fp64 running sum -- the DEFINED summation order shared with the oracle
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= (long long)S * A) return;
+  const float* row = T + r * S;
+  TC* out = cdf + r * ld;
+  double acc = 0.0;
+  for (int j = 0; j < ld; ++j) {
+    if (j < S) acc += (double)row[j];
+    out[j] = (TC)acc;
+  }
+}
+
+static int grid_for(long long work_items_per_thread_block, long long total) {
+  long long blocks = (total + work_items_per_thread_block - 1) / work_items_per_thread_block;
+  long long cap = (long long)sm_count() * 16;
+  if (blocks < 1) blocks = 1;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+static int check_tables_common(const colo_mdp_tables* tb) {
+  COLO_ARG_CHECK(tb != nullptr, "tables is NULL");
+  COLO_ARG_CHECK(tb->S > 0 && tb->A > 0 && tb->H >= 0, "S, A, H");
+  COLO_ARG_CHECK(tb->rew_q && tb->n_cls > 0 && tb->nq >= 2, "reward quantile table");
+  COLO_ARG_CHECK(tb->start_cum && tb->start_idx && tb->n_start > 0, "start distribution");
+  return COLO_OK;
+}
+
+template <typename TC>
+static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* stream) {
+  int r = check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(tb->cdf && tb->ld >= tb->S && tb->ld % 4 == 0, "dense cdf with ld % 4 == 0 is required");
+  COLO_ARG_CHECK((uintptr_t)tb->cdf % 16 == 0, "cdf must be 16-byte aligned");
+  COLO_ARG_CHECK(io.state && io.h && io.step_type && io.reward && io.obs && io.action, "env buffers");
+  if (io.N == 0) return COLO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(kStepThreads / 32, (io.N + 31) / 32);
+  const int chunks = (tb->ld + 127) / 128;
+  if (chunks <= 1)
+    env_step_dense_kernel<TC, 1><<<grid, kStepThreads, 0, st>>>(*tb, io);
+  else if (chunks <= 2)
+    env_step_dense_kernel<TC, 2><<<grid, kStepThreads, 0, st>>>(*tb, io);
+  else if (chunks <= 4)
+    env_step_dense_kernel<TC, 4><<<grid, kStepThreads, 0, st>>>(*tb, io);
+  else
+    env_step_dense_kernel<TC, 8><<<grid, kStepThreads, 0, st>>>(*tb, io);
+  return check_launch("env_step_dense_kernel");
+}
+
+}  // namespace colo
+
+extern "C" {
+
+int colo_env_reset(const colo_mdp_tables* tb, long long N, const double* u_next, unsigned long long seed,
+                   unsigned long long t, unsigned long long env0, int* state, int* h, unsigned char* step_type, int* obs,
+                   unsigned long long* visits_s, void* stream) {
+  int r = colo::check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(state && h && step_type && obs, "env buffers");
+  if (N == 0) return COLO_OK;
+  const int grid = colo::grid_for(colo::kStepThreads, N);
+  colo::env_reset_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, N, u_next, seed, t, env0, state, h,
+                                                                              step_type, obs, visits_s);
+  return colo::check_launch("env_reset_kernel");
+}
+
+#define COLO_STEP_IO()                                                                                          \
+  colo::StepIO io;                                                                                              \
+  io.N = N; io.action = action; io.random_actions = random_actions; io.u_next = u_next; io.u_rew = u_rew;       \
+  io.seed = seed; io.t = t; io.env0 = env0; io.auto_reset = auto_reset; io.state = state; io.h = h; io.step_type = step_type;   \
+  io.reward = reward; io.obs = obs; io.visits_s = visits_s; io.visits_sa = visits_sa; io.status = status;
+
+int colo_env_step_dense_f32(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
+                            const float* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
+                            unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
+                            unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream) {
+  COLO_STEP_IO();
+  return colo::launch_dense<float>(tb, io, stream);
+}
+
+int colo_env_step_dense_f64(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
+                            const double* u_next, const float* u_rew, unsigned long long seed,
+                            unsigned long long t, unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type,
+                            float* reward, int* obs, unsigned long long* visits_s, unsigned long long* visits_sa,
+                            int* status, void* stream) {
+  COLO_STEP_IO();
+  return colo::launch_dense<double>(tb, io, stream);
+}
+
+int colo_env_step_succ(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
+                       const double* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
+                       unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
+                       unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream) {
+  COLO_STEP_IO();
+  int r = colo::check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
+  COLO_ARG_CHECK(io.state && io.h && io.step_type && io.reward && io.obs && io.action, "env buffers");
+  if (N == 0) return COLO_OK;
+  const int grid = colo::grid_for(colo::kStepThreads, N);
+  colo::env_step_succ_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
+  return colo::check_launch("env_step_succ_kernel");
+}
+
+int colo_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64, void* stream) {
+  COLO_ARG_CHECK(T && cdf && S > 0 && A > 0 && ld >= S, "T, cdf, S, A, ld");
+  const long long rows = (long long)S * A;
+  const int grid = (int)((rows + 127) / 128);
+  if (out_is_f64)
+    colo::build_dense_cdf_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(T, S, A, ld, (double*)cdf);
+  else
+    colo::build_dense_cdf_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(T, S, A, ld, (float*)cdf);
+  return colo::check_launch("build_dense_cdf_kernel");
+}
+
+}  // extern "C"

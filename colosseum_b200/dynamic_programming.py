@@ -1,0 +1,271 @@
+"""B200 twin of `colosseum.dynamic_programming` (same names, argument meaning and error behaviour).
+
+Reference surface mirrored here (all paths under /root/reference/colosseum/):
+  dynamic_programming/__init__.py:5-14      DP_MAX_ITERATION, the four public entry points
+  dynamic_programming/finite_horizon.py:11-42   episodic_value_iteration / episodic_policy_evaluation
+  dynamic_programming/infinite_horizon.py:14-64,121-184,208-219   discounted VI / PE / PI
+  dynamic_programming/utils.py:8,75-100     DynamicProgrammingMaxIterationExceeded, get_policy_from_q_values
+
+Every function accepts what the reference accepts (C-contiguous float32 numpy arrays, never mutated) and returns
+freshly allocated numpy arrays of the reference's shapes; it also accepts CUDA torch tensors (kept resident,
+results returned as CUDA tensors) and a leading batch dimension of independent MDP instances.  All arithmetic
+runs in the hand-written sm_100a kernels behind the C ABI (include/colosseum_b200.h); there is no CPU path.
+
+Iteration order: the reference's dense kernel sweeps states in place (Gauss-Seidel); the GPU sweeps are
+synchronous (Jacobi).  Both converge to the same fixed point, which is where parity is defined; the
+`epsilon` stopping rule (max|dV| < epsilon after a sweep) is the reference's.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import FOLD_MAX, FOLD_MIN, FOLD_PI  # noqa: F401
+
+DP_MAX_ITERATION = int(1e6)
+ARGMAX_SEED = 42
+
+_PRECISION = "f32"  # the reference's arithmetic type; "f64" = fp64 accumulation / fp64 V,Q (1e-6 parity mode)
+
+
+class DynamicProgrammingMaxIterationExceeded(Exception):
+    """colosseum/dynamic_programming/utils.py:8"""
+
+
+def set_precision(p):
+    """'f32' (reference arithmetic type) or 'f64' (fp64 accumulation; V, Q returned as float64)."""
+    global _PRECISION
+    assert p in ("f32", "f64")
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _is_tensor(x):
+    return type(x).__module__.startswith("torch")
+
+
+def to_device(x, np_dtype=np.float32):
+    """numpy (caller-owned, not mutated) -> CUDA tensor; CUDA tensors pass through (made contiguous)."""
+    torch = _torch()
+    _cabi.require_cuda()
+    if x is None:
+        return None
+    if _is_tensor(x):
+        assert x.is_cuda, "tensors passed to colosseum_b200 must live on the GPU"
+        tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32, np.uint8: torch.uint8}[np_dtype]
+        return x.to(tdt).contiguous()
+    a = np.ascontiguousarray(x, dtype=np_dtype)
+    return torch.from_numpy(a).cuda()
+
+
+def _result(t, as_numpy):
+    return t.cpu().numpy() if as_numpy else t
+
+
+def _vdtype(precision):
+    torch = _torch()
+    return torch.float64 if precision == "f64" else torch.float32
+
+
+def _scratch(nbytes):
+    torch = _torch()
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------------ discounted
+def _solve_discounted(T, R, pi, gamma, epsilon, max_abs_value, precision, max_iter=DP_MAX_ITERATION):
+    precision = precision or _PRECISION
+    as_numpy = not _is_tensor(T)
+    torch = _torch()
+    Td, Rd, pid = to_device(T), to_device(R), to_device(pi)
+    batched = Td.dim() == 4
+    if not batched:
+        Td, Rd = Td[None], Rd[None]
+        pid = None if pid is None else pid[None]
+    B, S, A, S2 = Td.shape
+    assert S == S2 and tuple(Rd.shape) == (B, S, A)
+    assert pid is None or tuple(pid.shape) == (B, S, A)
+    vd = _vdtype(precision)
+    Q = torch.empty((B, S, A), dtype=vd, device="cuda")
+    V = torch.empty((B, S), dtype=vd, device="cuda")
+    lib = _cabi.lib()
+    f64 = precision == "f64"
+    work = _scratch(lib.colo_solve_work_bytes(B, S, int(f64)))
+    iters = (C.c_longlong * B)()
+    fold = FOLD_PI if pid is not None else FOLD_MAX
+    fn = lib.colo_solve_discounted_f64acc if f64 else lib.colo_solve_discounted_f32
+    # gamma is cast to float32 first, as the reference does (infinite_horizon.py:127,171)
+    g = float(np.float32(gamma))
+    rc = fn(_cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(pid), B, S, A, g, float(epsilon),
+            float(max_abs_value) if max_abs_value is not None else 0.0, int(max_iter), fold,
+            _cabi.ptr(Q), _cabi.ptr(V), iters, _cabi.ptr(work), _cabi.current_stream())
+    _cabi.check(rc, "colo_solve_discounted")
+    if rc == _cabi.OVERFLOW:
+        return None
+    if rc == _cabi.MAX_ITER:
+        raise DynamicProgrammingMaxIterationExceeded()
+    if not batched:
+        Q, V = Q[0], V[0]
+    out = _result(Q, as_numpy), _result(V, as_numpy)
+    _solve_discounted.last_iterations = list(iters)
+    return out
+
+
+_solve_discounted.last_iterations = []
+
+
+def last_iterations():
+    """sweeps run by each instance of the most recent discounted solve (diagnostics / bench)."""
+    return list(_solve_discounted.last_iterations)
+
+
+def discounted_value_iteration(T, R, gamma=0.99, epsilon=1e-3, max_abs_value=None,
+                               sparse_n_states_threshold=300 * 3 * 300, sparse_nnz_per_threshold=0.2, *,
+                               precision=None):
+    """colosseum/dynamic_programming/infinite_horizon.py:14-44.  Returns (Q[S,A], V[S]) or None on overflow.
+
+    The two `sparse_*` arguments select a pydata-sparse code path in the reference; the GPU path streams the dense
+    tensor at HBM speed for every size, so they are accepted and ignored."""
+    return _solve_discounted(T, R, None, gamma, epsilon, max_abs_value, precision)
+
+
+def discounted_policy_evaluation(T, R, pi, gamma=0.99, epsilon=1e-7, sparse_n_states_threshold=200,
+                                 sparse_nnz_per_threshold=0.2, *, precision=None):
+    """colosseum/dynamic_programming/infinite_horizon.py:47-64.  Returns (Q[S,A], V[S])."""
+    return _solve_discounted(T, R, pi, gamma, epsilon, None, precision)
+
+
+def discounted_policy_iteration(T, R, gamma=0.99, epsilon=1e-7, *, precision=None):
+    """colosseum/dynamic_programming/infinite_horizon.py:208-219.  Returns (Q, V, pi)."""
+    S, A = R.shape[-2], R.shape[-1]
+    rng = np.random.RandomState(ARGMAX_SEED)
+    Q = rng.rand(S, A)
+    pi = get_policy_from_q_values(Q, True)
+    for _ in range(DP_MAX_ITERATION):
+        old_pi = pi.copy()
+        Q, V = discounted_policy_evaluation(T, R, pi, gamma, epsilon, precision=precision)
+        Qh = Q.cpu().numpy() if _is_tensor(Q) else Q
+        pi = get_policy_from_q_values(Qh, True)
+        if (pi != old_pi).sum() == 0:
+            return Q, V, pi
+    raise DynamicProgrammingMaxIterationExceeded()
+
+
+# ------------------------------------------------------------------------------------------------ episodic
+def _episodic(H, T, R, policy, max_value, precision):
+    precision = precision or _PRECISION
+    as_numpy = not _is_tensor(T)
+    torch = _torch()
+    H = int(H)
+    Td, Rd, pid = to_device(T), to_device(R), to_device(policy)
+    batched = Td.dim() == 4
+    if not batched:
+        Td, Rd = Td[None], Rd[None]
+        pid = None if pid is None else pid[None]
+    B, S, A, _ = Td.shape
+    assert pid is None or tuple(pid.shape) == (B, H, S, A), "policy must be [H,S,A]"
+    vd = _vdtype(precision)
+    Q = torch.empty((B, H + 1, S, A), dtype=vd, device="cuda")
+    V = torch.empty((B, H + 1, S), dtype=vd, device="cuda")
+    lib = _cabi.lib()
+    fn = lib.colo_episodic_f64acc if precision == "f64" else lib.colo_episodic_f32
+    rc = fn(_cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(pid), B, S, A, H, FOLD_PI if pid is not None else FOLD_MAX,
+            float(max_value) if max_value is not None else 0.0, _cabi.ptr(Q), _cabi.ptr(V), _cabi.current_stream())
+    _cabi.check(rc, "colo_episodic")
+    if rc == _cabi.OVERFLOW:
+        return None
+    if not batched:
+        Q, V = Q[0], V[0]
+    return _result(Q, as_numpy), _result(V, as_numpy)
+
+
+def episodic_value_iteration(H, T, R, max_value=None, *, precision=None):
+    """colosseum/dynamic_programming/finite_horizon.py:11-26.  Returns (Q[H+1,S,A], V[H+1,S]) or None."""
+    return _episodic(H, T, R, None, max_value, precision)
+
+
+def episodic_policy_evaluation(H, T, R, policy, *, precision=None):
+    """colosseum/dynamic_programming/finite_horizon.py:29-42.  policy is [H,S,A]."""
+    return _episodic(H, T, R, policy, None, precision)
+
+
+# ------------------------------------------------------------------------------------------------ single backups
+def bellman_backup(T, R, V, gamma=0.99, pi=None, fold=None, *, precision=None, return_residual=False):
+    """One synchronous sweep Q = R + gamma T V, V' = fold(Q) (the body of infinite_horizon.py:131-135).
+    Building block for callers that own their iteration (agents, sharded solvers, benchmarks)."""
+    precision = precision or _PRECISION
+    as_numpy = not _is_tensor(T)
+    torch = _torch()
+    f64 = precision == "f64"
+    Td, Rd, pid = to_device(T), to_device(R), to_device(pi)
+    Vd = to_device(V, np.float64 if f64 else np.float32)
+    batched = Td.dim() == 4
+    if not batched:
+        Td = Td[None]
+        Rd = None if Rd is None else Rd[None]
+        Vd = Vd[None]
+        pid = None if pid is None else pid[None]
+    B, S, A, _ = Td.shape
+    vd = _vdtype(precision)
+    Q = torch.empty((B, S, A), dtype=vd, device="cuda")
+    Vn = torch.empty((B, S), dtype=vd, device="cuda")
+    resid = torch.zeros(B, dtype=torch.int64 if f64 else torch.int32, device="cuda")
+    a = _cabi.BackupArgs()
+    a.T, a.R, a.pi = _cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(pid)
+    a.V_in, a.V_out, a.Q = _cabi.ptr(Vd), _cabi.ptr(Vn), _cabi.ptr(Q)
+    a.t_stride, a.r_stride, a.pi_stride = S * A * S, S * A, S * A
+    a.v_in_stride, a.v_out_stride, a.q_stride = S, S, S * A
+    a.B, a.S, a.A = B, S, A
+    a.fold = fold if fold is not None else (FOLD_PI if pid is not None else FOLD_MAX)
+    a.gamma = float(gamma)
+    a.resid = _cabi.ptr(resid)
+    a.row0, a.nrows = 0, S
+    lib = _cabi.lib()
+    rc = (lib.colo_backup_f64acc if f64 else lib.colo_backup_f32)(C.byref(a), _cabi.current_stream())
+    _cabi.check(rc, "colo_backup")
+    if not batched:
+        Q, Vn = Q[0], Vn[0]
+    out = (_result(Q, as_numpy), _result(Vn, as_numpy))
+    if return_residual:
+        r = resid.view(torch.float64 if f64 else torch.float32)
+        out = out + (_result(r, as_numpy),)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ argmax helpers
+def _argmax_rows(Q2, rng):
+    """random tie-broken argmax per row (colosseum/dynamic_programming/utils.py:12-72)."""
+    best = Q2.max(-1, keepdims=True)
+    out = np.empty(Q2.shape[0], np.int32)
+    ties = Q2 == best
+    n_ties = ties.sum(-1)
+    first = ties.argmax(-1)
+    out[:] = first
+    for r in np.nonzero(n_ties > 1)[0]:
+        out[r] = rng.choice(np.nonzero(ties[r])[0])
+    return out
+
+
+def get_policy_from_q_values(Q, stochastic_form=False):
+    """colosseum/dynamic_programming/utils.py:75-100: deterministic policy from Q; ties are broken at random
+    under a fixed seed (ARGMAX_SEED = 42).  NOTE: the reference draws its tie-breaks from numba's private
+    Mersenne-Twister stream; this host helper uses numpy's RandomState(42), so the CHOICE among exactly tied
+    actions can differ -- every choice is an argmax, and the value functions are unaffected."""
+    Qh = Q.cpu().numpy() if _is_tensor(Q) else np.asarray(Q)
+    rng = np.random.RandomState(ARGMAX_SEED)
+    lead = Qh.shape[:-1]
+    idx = _argmax_rows(Qh.reshape(-1, Qh.shape[-1]), rng).reshape(lead)
+    if not stochastic_form:
+        return idx.astype(np.int32)
+    X = np.zeros(Qh.shape, np.float32)
+    np.put_along_axis(X, idx[..., None].astype(np.int64), 1.0, axis=-1)
+    return X

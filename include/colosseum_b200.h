@@ -1,0 +1,264 @@
+/*
+ * colosseum_b200.h -- C ABI of libcolosseum_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the ONE data-parallel hot path of MichelangeloConserva/Colosseum:
+ *   (A) the batched agent/MDP interaction step       -- colosseum/mdp/base.py:1268-1317
+ *   (B) the Bellman backups behind the hardness       -- colosseum/dynamic_programming/{finite,infinite}_horizon.py,
+ *       measures and model-based agents                  colosseum/hardness/measures/*.py
+ *
+ * The reference has no FFI of its own (it is pure Python + numba); these are the entry points a ctypes binding
+ * placed behind the reference's Python signatures would call (INTEGRATION.md shows that binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors on the host side), unless the
+ *     parameter name ends in `_host`;
+ *   - arrays are C-contiguous with the layouts of the reference (T[S,A,S], R[S,A], Q[S,A], V[S], episodic
+ *     Q[H+1,S,A] / V[H+1,S]); batched variants add a leading B;
+ *   - every call takes the cudaStream_t (as void*) it enqueues on and does NOT synchronise unless stated;
+ *   - return value: COLO_OK (0); COLO_OVERFLOW (1) = the reference's `return None` on max_value/max_abs_value;
+ *     COLO_MAX_ITER (2) = the reference's DynamicProgrammingMaxIterationExceeded; COLO_NEEDS_RESET (3) = the
+ *     reference's `assert not self.necessary_reset`; < 0 = CUDA error / bad argument, text in colo_last_error().
+ */
+#ifndef COLOSSEUM_B200_H_
+#define COLOSSEUM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COLO_OK 0
+#define COLO_OVERFLOW 1
+#define COLO_MAX_ITER 2
+#define COLO_NEEDS_RESET 3
+#define COLO_ERR_CUDA (-1)
+#define COLO_ERR_ARG (-2)
+
+/* backup modes: how Q[s,:] is folded into V[s] */
+#define COLO_FOLD_MAX 0 /* value iteration            V[s] = max_a Q[s,a]            */
+#define COLO_FOLD_PI 1  /* policy evaluation          V[s] = sum_a pi[s,a] Q[s,a]    */
+#define COLO_FOLD_MIN 2 /* hitting times (diameter)   V[s] = min_a Q[s,a]            */
+
+/* dm_env.StepType */
+#define COLO_STEP_FIRST 0
+#define COLO_STEP_MID 1
+#define COLO_STEP_LAST 2
+
+/* ---------------------------------------------------------------- library ------------------------------- */
+const char* colo_last_error(void);
+int colo_version(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches) */
+unsigned long long colo_launch_count(void);
+void colo_reset_launch_count(void);
+
+/* ---------------------------------------------------------------- (B) Bellman backups ------------------- */
+/*
+ * One synchronous (Jacobi) backup of B independent MDPs (one kernel launch, T is read once):
+ *     Q[b,s,a] = R[b,s,a] + gamma * sum_j T[b,s,a,j] * V_in[b,j];   V_out[b,s] = fold_a Q[b,s,a]
+ * Restates the sweep body of  colosseum/dynamic_programming/infinite_horizon.py:131-135 (VI), :176-179 (PE),
+ * colosseum/dynamic_programming/finite_horizon.py:21-23, :38-40 (one horizon layer) and the hitting-time sweep of
+ * colosseum/hardness/measures/diameter.py:330-339 as one parallel sweep.  All strides are in ELEMENTS between
+ * consecutive instances b (t_stride = 0 shares one T between all instances, e.g. the K targets of a diameter).
+ *   _f32    : T,R,pi float; V,Q float;  fp32 accumulation (the reference's arithmetic type)
+ *   _f64acc : T,R,pi float; V,Q double; fp64 accumulation (the 1e-6 parity mode of BASELINE.json)
+ */
+typedef struct {
+  const float* T;        /* [B][nrows,A,S] rows row0..row0+nrows of each instance (nrows = S unless row-sharded) */
+  const float* R;        /* [B][nrows,A] or NULL (then r_const is used)                                          */
+  const float* pi;       /* [B][nrows,A], COLO_FOLD_PI only                                                      */
+  const void* V_in;      /* [B][S] (float | double); with v_action_stride != 0: [B][A][S], one vector per action */
+  void* V_out;           /* [B][S] or NULL; only entries row0..row0+nrows are written                            */
+  void* Q;               /* [B][nrows,A] or NULL                                                                 */
+  long long t_stride, r_stride, pi_stride, v_in_stride, v_out_stride, q_stride, v_action_stride;
+  int B, S, A, fold;
+  double gamma, r_const;
+  void* resid;           /* per instance max|V_out - V_in| as the bits of a non-negative float (u32) | double
+                            (u64), accumulated with atomicMax; zero it before the sweep; or NULL                 */
+  int resid_vs_out;      /* != 0: the residual compares with the previous content of V_out instead of V_in      */
+  const unsigned char* active; /* per instance; 0 = converged: V is carried forward, nothing else is touched    */
+  double max_abs;        /* > 0: set *overflow_flag = 1 when |V_out| exceeds it (the reference's `return None`)  */
+  int* overflow_flag;
+  int row0, nrows;       /* nrows == 0 && row0 == 0 means all S rows                                             */
+  const int* pin_index;  /* per instance or NULL: V_out[b, pin_index[b]] = pin_value (absorbing target)          */
+  double pin_value;
+  const int* exclude_index; /* per instance or NULL: V_in[b, exclude_index[b]] is read as exclude_value          */
+  double exclude_value;
+  void* const* V_out_peers; /* device array of n_peers pointers or NULL: V_out rows are ALSO stored into every
+                               listed [B][S] buffer (peer GPUs' V over NVLink: the all-gather of a row-sharded
+                               sweep fused into the backup's epilogue)                    */
+  int n_peers;
+} colo_backup_args;
+
+int colo_backup_f32(const colo_backup_args* args, void* stream);
+int colo_backup_f64acc(const colo_backup_args* args, void* stream);
+
+/*
+ * Discounted value iteration / policy evaluation to convergence for B independent MDPs
+ * (colosseum/dynamic_programming/infinite_horizon.py:14-64,121-184).  V starts at 0.  Sweeps are synchronous
+ * (Jacobi); an instance stops after the sweep in which max_s|dV| < eps (the reference's test, :140-141) and its
+ * Q is the Q of that sweep; returns COLO_OVERFLOW if any |V| > max_abs (pass max_abs <= 0 to disable; :136-138),
+ * COLO_MAX_ITER after max_iter sweeps (:142).  fold = COLO_FOLD_MAX (VI) or COLO_FOLD_PI (PE, pi [B,S,A]).
+ * Synchronises the stream (the host needs the convergence flags).  iters_out_host[b] = sweeps run by b (or NULL).
+ * work: device scratch of colo_solve_work_bytes(B,S,f64) bytes.  Q may be NULL.
+ */
+size_t colo_solve_work_bytes(long long B, long long S, int f64);
+int colo_solve_discounted_f32(const float* T, const float* R, const float* pi, int B, int S, int A, float gamma,
+                              float eps, float max_abs, long long max_iter, int fold, float* Q, float* V,
+                              long long* iters_out_host, void* work, void* stream);
+int colo_solve_discounted_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A,
+                                 double gamma, double eps, double max_abs, long long max_iter, int fold, double* Q,
+                                 double* V, long long* iters_out_host, void* work, void* stream);
+
+/*
+ * Episodic backward induction for B MDPs (colosseum/dynamic_programming/finite_horizon.py:11-42):
+ * Q[b,H]=0, V[b,H]=0; for h=H-1..0: Q[b,h]=R+T@V[b,h+1]; V[b,h]=fold(Q[b,h]) with pi[b,h] for PE
+ * (pi is [B,H,S,A]).  Q is [B,H+1,S,A], V is [B,H+1,S].  max_value<=0 disables the overflow test (:24-25);
+ * with it enabled the call synchronises and may return COLO_OVERFLOW.
+ */
+int colo_episodic_f32(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
+                      float max_value, float* Q, float* V, void* stream);
+int colo_episodic_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
+                         double max_value, double* Q, double* V, void* stream);
+
+/*
+ * Continuous diameter (colosseum/hardness/measures/diameter.py:20-39,76-106; == :321-346 at the fixed point):
+ * multi-target hitting-time iteration  E[k,s] = (s == target[k]) ? 0 : min_a(1 + sum_j T[s,a,j] E[k,j])  over the
+ * K given targets at once (all S for the full diameter), one launch per sweep, each target frozen as soon as its
+ * own max|dE| < eps.  out_host[0] = max_k max_s E, out_host[1] = sweeps run.  COLO_OVERFLOW if a hitting time
+ * exceeds max_value (>0).  Synchronises.  work: colo_diameter_continuous_work_bytes(K,S,f64) device bytes.
+ */
+size_t colo_diameter_continuous_work_bytes(int K, int S, int f64);
+int colo_diameter_continuous_f32(const float* T, const int* targets, int K, int S, int A, float eps,
+                                 float max_value, long long max_iter, void* work, double* out_host, void* stream);
+int colo_diameter_continuous_f64acc(const float* T, const int* targets, int K, int S, int A, double eps,
+                                    double max_value, long long max_iter, void* work, double* out_host,
+                                    void* stream);
+/*
+ * Episodic diameter in the augmented (h,s) space (colosseum/hardness/measures/diameter.py:193-234,285-318) on
+ * T_epi[H,S,A,S] (colosseum/mdp/utils/mdp_creation.py:98-128), iterated to max|dE| < eps for all K targets at once.
+ */
+size_t colo_diameter_episodic_work_bytes(int K, int H, int S, int A, int f64);
+int colo_diameter_episodic_f32(const float* T_epi, const int* targets, int K, int H, int S, int A, float eps,
+                               float max_value, long long max_iter, void* work, double* out_host, void* stream);
+int colo_diameter_episodic_f64acc(const float* T_epi, const int* targets, int K, int H, int S, int A, double eps,
+                                  double max_value, long long max_iter, void* work, double* out_host, void* stream);
+
+/*
+ * Environmental value norm (colosseum/hardness/measures/value_norm.py:55-61,85-87), two passes over T:
+ *   Ev[i,a] = sum_j T[i,a,j] V[j];   out[0] = max_{i,a} sqrt( sum_j T[i,a,j] * (V[j] - Ev[j,a])^2 )
+ * (sic: Ev is indexed by the NEXT state j, reference behaviour).  out: 1 element (device).  Does not synchronise.
+ * work: colo_value_norm_work_bytes(S,A,f64) device bytes.
+ */
+size_t colo_value_norm_work_bytes(int S, int A, int f64);
+int colo_value_norm_f32(const float* T, const float* V, int S, int A, void* work, float* out, void* stream);
+int colo_value_norm_f64acc(const float* T, const double* V, int S, int A, void* work, double* out, void* stream);
+
+/*
+ * Sum of reciprocals of the sub-optimality gaps
+ * (colosseum/hardness/measures/sum_reciprocals_suboptimality_gaps.py:6-28):
+ *   out[0] = sum_{n<NS, a<A, mask[n]} 1 / (V[n] - Q[n,a] + reg)     (mask may be NULL = all; episodic callers
+ * pass NS=(H+1)*S rows and the reachable (h,s) mask).  Deterministic fp64 reduction (fixed order).
+ */
+int colo_gaps_f64(const double* Q, const double* V, const unsigned char* mask, long long NS, int A, double reg,
+                  double* out, void* stream);
+
+/* ---------------------------------------------------------------- (A) interaction step ------------------ */
+/*
+ * Tables of one MDP for the step kernels (built once per MDP by the host, colosseum_b200/tables.py).
+ *
+ * DENSE form (the north-star kernel; any dense T, CustomMDP, synthetic MDPs):
+ *   cdf [S,A,ld]   sequential cumulative sum of T[s,a,:] over the next-state INDEX (fp64 running sum rounded
+ *                  to the storage type), rows padded to ld (multiple of 32 elements) with the row total.
+ *   Sampling restates CPython random.choices as used by NextStateSampler.sample
+ *   (colosseum/mdp/utils/custom_samplers.py:49-72):  x = u*total;  next = first j with cdf[j] > x, clamped to
+ *   the last positive-probability index (bisect_right(cum, x, 0, n-1)).
+ * SUCCESSOR form (the seven benchmark families, <= ~13 successors per (s,a)):
+ *   succ_cum f64 [S,A,Ksucc]  running sum of the sampler's probs IN ITS OWN ORDER (mdp_creation.py:276-310),
+ *                             padded with +inf;  succ_idx i32 [S,A,Ksucc] next-state indices (padded with the
+ *                             last real successor);  succ_len i32 [S,A].
+ *   Bit-exact with the reference's sampler for the same fp64 uniform, including its successor order.
+ *
+ * Rewards (colosseum/mdp/base.py:1187-1207): reward class c = rew_cls[...] selects an inverse-CDF (quantile)
+ * table rew_q[c, 0..nq-1] of the scipy frozen distribution on a uniform grid; a draw is the linear interpolation
+ * at u_rew, then the reference's rescale  r*(rmax-rmin) - rmin  (sic).
+ *   dense:      rew_cls_sas u8 [S,A,S] (or NULL) else rew_cls_sa i32 [S,A] (or NULL -> class 0)
+ *   successor:  rew_cls_succ i32 [S,A,Ksucc]
+ */
+typedef struct {
+  int S, A;
+  int H;                 /* episode length; 0 = continuous (infinite horizon) */
+  int ld;                /* dense row stride in elements */
+  const void* cdf;       /* dense: float or double [S,A,ld] */
+  const double* succ_cum;
+  const int* succ_idx;
+  const int* succ_len;
+  int Ksucc;
+  const unsigned char* rew_cls_sas;
+  const int* rew_cls_sa;
+  const int* rew_cls_succ;
+  const float* rew_q;    /* [n_cls, nq] */
+  int n_cls, nq;
+  float rmin, rmax;      /* rewards_range */
+  const double* start_cum; /* [n_start] running sum of the start distribution (sampler order) */
+  const int* start_idx;    /* [n_start] */
+  int n_start;
+} colo_mdp_tables;
+
+/*
+ * Batched env state: state i32[N], h i32[N], step_type u8[N] (the type of the LAST emitted TimeStep).
+ * Uniforms: u_next (float for the f32 dense kernel, double otherwise) and u_rew float, or NULL to draw them from
+ * the built-in Philox4x32-10 stream keyed by (seed; env0 + env index, step counter t) -- env0 is the global index
+ * of this call's first env, so a batch sharded over GPUs draws exactly the numbers of the unsharded batch.  action i32[N]: read, or -- when
+ * random_actions != 0 -- written with the uniformly random action taken (BaseMDP.random_step, base.py:1341-1355).
+ *
+ * colo_env_reset  -- BaseMDP.reset (base.py:1268-1277): h=0, state ~ start distribution, step_type=FIRST,
+ *                    visits_s[state]++.
+ * colo_env_step_* -- BaseMDP.step (base.py:1279-1317).  Per env: if step_type==LAST: auto_reset ? reset path
+ *                    (reward/obs as reset: reward=NaN for None) : flag COLO_NEEDS_RESET; else h++, sample next,
+ *                    visits_s[next]++, visits_sa[next,a]++ (sic: counted on the NEXT node), reward, and
+ *                    LAST/obs=-1 if episodic and h>=H else MID/obs=next.
+ * status: device int (may be NULL), set to COLO_NEEDS_RESET if any env needed a reset without auto_reset.
+ * visits_s / visits_sa: u64 counters or NULL.
+ */
+int colo_env_reset(const colo_mdp_tables* tb, long long N, const double* u_next, unsigned long long seed,
+                   unsigned long long t, unsigned long long env0, int* state, int* h, unsigned char* step_type, int* obs,
+                   unsigned long long* visits_s, void* stream);
+int colo_env_step_dense_f32(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
+                            const float* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
+                            unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
+                            unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream);
+int colo_env_step_dense_f64(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
+                            const double* u_next, const float* u_rew, unsigned long long seed,
+                            unsigned long long t, unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type,
+                            float* reward, int* obs, unsigned long long* visits_s, unsigned long long* visits_sa,
+                            int* status, void* stream);
+int colo_env_step_succ(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
+                       const double* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
+                       unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
+                       unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream);
+
+/* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
+ * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */
+int colo_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64, void* stream);
+
+/* ---------------------------------------------------------------- multi-GPU ---------------------------- */
+/*
+ * Row-sharded value iteration of ONE large MDP uses colo_backup_* with row0/nrows set to
+ * the rank's row range, T/R/pi/Q pointing at the local shard, V_in the full [S] vector and V_out_peers listing
+ * every rank's next-V buffer (peer-mapped through torch symmetric memory / CUDA IPC).  Independent MDP instances
+ * and parallel envs shard with no communication at all.
+ *
+ * colo_synth_dense_rows fills T_rows[nrows,A,S] / R_rows[nrows,A] with the synthetic dense MDP of config C5
+ * directly on the device (51 GB is never materialised on the host): weights u^8 + 1e-12 from Philox4x32-10 keyed
+ * by (seed; global row index*A+a, column/4), each row normalised in fp32; R ~ U[0,1).  Deterministic in
+ * (seed, global row), hence independent of the sharding.
+ */
+int colo_synth_dense_rows(float* T_rows, float* R_rows, int row0, int nrows, int S, int A, unsigned long long seed,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLOSSEUM_B200_H_ */

@@ -1,0 +1,655 @@
+/*
+ * colo_oracle.c -- CPU restatement of the Colosseum hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle and the `cpu_baseline` of bench.py.  Nothing under colosseum_b200/ may link,
+ * import or call it: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function here against golden vectors that
+ * tests/golden/make_golden.py produced by running the unmodified Python reference (numba DP, NextStateSampler,
+ * BaseMDP.step, hardness measures) and against the reference's own cached_hardness_measures .txt files and executed
+ * notebook outputs.
+ *
+ * Each function cites the reference lines it restates (paths relative to /root/reference/colosseum/).
+ * Build:  make -C oracle   ->  oracle/_build/libcolo_oracle.so
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_OK 0
+#define ORC_OVERFLOW 1
+#define ORC_MAX_ITER 2
+#define ORC_NEEDS_RESET 3
+
+#define FOLD_MAX 0
+#define FOLD_PI 1
+#define FOLD_MIN 2
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (B1) the reference iterate, fp32, in place (Gauss-Seidel):
+ * dynamic_programming/infinite_horizon.py:121-142 (_discounted_value_iteration) and :167-184
+ * (_discounted_policy_evaluation).  V starts at 0; per sweep, for s in order: Q[s]=R[s]+gamma*T[s]@V (V already
+ * holds this sweep's updates for s'<s); V[s]=max_a Q[s,a] (or sum_a Q*pi); overflow -> "None"; stop when
+ * max|V_old-V| < eps.  This is what bench.py times as the CPU baseline ("port" of the numba kernel).
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_discounted_gs_f32(const float* T, const float* R, const float* pi, int S, int A, float gamma, float eps,
+                          float max_abs, long long max_iter, float* Q, float* V, long long* iters) {
+  float* Vold = (float*)malloc(sizeof(float) * (size_t)S);
+  memset(V, 0, sizeof(float) * (size_t)S);
+  memset(Q, 0, sizeof(float) * (size_t)S * A);
+  for (long long it = 0; it < max_iter; ++it) {
+    memcpy(Vold, V, sizeof(float) * (size_t)S);
+    for (int s = 0; s < S; ++s) {
+      float best = -INFINITY, mix = 0.f;
+      for (int a = 0; a < A; ++a) {
+        const float* row = T + ((size_t)s * A + a) * S;
+        float acc = 0.f;
+        for (int j = 0; j < S; ++j) acc += row[j] * V[j];
+        float q = R[(size_t)s * A + a] + gamma * acc;
+        Q[(size_t)s * A + a] = q;
+        if (q > best) best = q;
+        if (pi) mix += q * pi[(size_t)s * A + a];
+      }
+      V[s] = pi ? mix : best;
+      if (max_abs > 0.f && fabsf(V[s]) > max_abs) {
+        free(Vold);
+        if (iters) *iters = it + 1;
+        return ORC_OVERFLOW;
+      }
+    }
+    float diff = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float d = fabsf(Vold[s] - V[s]);
+      if (d > diff) diff = d;
+    }
+    if (diff < eps) {
+      free(Vold);
+      if (iters) *iters = it + 1;
+      return ORC_OK;
+    }
+  }
+  free(Vold);
+  if (iters) *iters = max_iter;
+  return ORC_MAX_ITER;
+}
+
+/* Batch of independent MDPs through (B1), OpenMP over instances -- the reference's own scaling mechanism is a
+ * process pool over instances (hardness/measures/diameter.py:109-124, experiment/experiment_instances.py:160). */
+int orc_discounted_gs_f32_batch(const float* T, const float* R, int B, int S, int A, float gamma, float eps,
+                                long long max_iter, float* Q, float* V, long long* iters) {
+  int rc = ORC_OK;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    int r = orc_discounted_gs_f32(T + (size_t)b * S * A * S, R + (size_t)b * S * A, NULL, S, A, gamma, eps, 0.f,
+                                  max_iter, Q + (size_t)b * S * A, V + (size_t)b * S, iters ? iters + b : NULL);
+    if (r != ORC_OK) {
+#pragma omp critical
+      rc = r;
+    }
+  }
+  return rc;
+}
+
+/* Fixed number of fp32 in-place sweeps over a batch (throughput leg of the CPU baseline: sweeps/s). */
+void orc_sweeps_gs_f32_batch(const float* T, const float* R, int B, int S, int A, float gamma, int n_sweeps,
+                             float* V) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int b = 0; b < B; ++b) {
+    const float* Tb = T + (size_t)b * S * A * S;
+    const float* Rb = R + (size_t)b * S * A;
+    float* Vb = V + (size_t)b * S;
+    for (int it = 0; it < n_sweeps; ++it)
+      for (int s = 0; s < S; ++s) {
+        float best = -INFINITY;
+        for (int a = 0; a < A; ++a) {
+          const float* row = Tb + ((size_t)s * A + a) * S;
+          float acc = 0.f;
+          for (int j = 0; j < S; ++j) acc += row[j] * Vb[j];
+          float q = Rb[(size_t)s * A + a] + gamma * acc;
+          if (q > best) best = q;
+        }
+        Vb[s] = best;
+      }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (B2) fixed-point oracle, fp64: the same recurrence (infinite_horizon.py:131-135 / :176-179) iterated
+ * synchronously in double to |dV|_inf <= tol.  Both sweep orders converge to the same V* (gamma<1), which is
+ * where parity is defined ("Gauss-Seidel vs Jacobi").  gauss_seidel!=0 uses the reference's
+ * in-place order instead.  Q is the Q of the last sweep, as in the reference.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_discounted_f64(const float* T, const float* R, const float* pi, int S, int A, double gamma, double tol,
+                       double max_abs, long long max_iter, int fold, int gauss_seidel, double* Q, double* V,
+                       long long* iters) {
+  double* Vn = (double*)malloc(sizeof(double) * (size_t)S);
+  memset(V, 0, sizeof(double) * (size_t)S);
+  int rc = ORC_MAX_ITER;
+  long long it = 0;
+  for (; it < max_iter; ++it) {
+    double diff = 0.0;
+    for (int s = 0; s < S; ++s) {
+      double best = fold == FOLD_MIN ? INFINITY : -INFINITY, mix = 0.0;
+      for (int a = 0; a < A; ++a) {
+        const float* row = T + ((size_t)s * A + a) * S;
+        double acc = 0.0;
+        for (int j = 0; j < S; ++j) acc += (double)row[j] * V[j];
+        double q = (R ? (double)R[(size_t)s * A + a] : 0.0) + gamma * acc;
+        if (Q) Q[(size_t)s * A + a] = q;
+        if (fold == FOLD_MAX && q > best) best = q;
+        if (fold == FOLD_MIN && q < best) best = q;
+        if (fold == FOLD_PI) mix += q * (double)pi[(size_t)s * A + a];
+      }
+      double v = fold == FOLD_PI ? mix : best;
+      double d = fabs(v - V[s]);
+      if (d > diff) diff = d;
+      if (gauss_seidel)
+        V[s] = v;
+      else
+        Vn[s] = v;
+      if (max_abs > 0.0 && fabs(v) > max_abs) {
+        rc = ORC_OVERFLOW;
+        goto done;
+      }
+    }
+    if (!gauss_seidel) memcpy(V, Vn, sizeof(double) * (size_t)S);
+    if (diff < tol) {
+      rc = ORC_OK;
+      ++it;
+      goto done;
+    }
+  }
+done:
+  if (iters) *iters = it;
+  free(Vn);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (B3) episodic backward induction: dynamic_programming/finite_horizon.py:11-26 (VI), :29-42 (PE).
+ * Q[H+1,S,A], V[H+1,S]; row H is zero; no discount; pi is [H,S,A].  fp64 accumulation of fp32 inputs.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_episodic_f64(const float* T, const float* R, const float* pi, int S, int A, int H, double max_value,
+                     double* Q, double* V) {
+  memset(Q, 0, sizeof(double) * (size_t)(H + 1) * S * A);
+  memset(V, 0, sizeof(double) * (size_t)(H + 1) * S);
+  for (int h = H - 1; h >= 0; --h) {
+    const double* Vn = V + (size_t)(h + 1) * S;
+    for (int s = 0; s < S; ++s) {
+      double best = -INFINITY, mix = 0.0;
+      for (int a = 0; a < A; ++a) {
+        const float* row = T + ((size_t)s * A + a) * S;
+        double acc = 0.0;
+        for (int j = 0; j < S; ++j) acc += (double)row[j] * Vn[j];
+        double q = (double)R[(size_t)s * A + a] + acc;
+        Q[((size_t)h * S + s) * A + a] = q;
+        if (q > best) best = q;
+        if (pi) mix += q * (double)pi[((size_t)h * S + s) * A + a];
+      }
+      V[(size_t)h * S + s] = pi ? mix : best;
+      if (!pi && max_value > 0.0 && best > max_value) return ORC_OVERFLOW;
+    }
+  }
+  return ORC_OK;
+}
+
+/* same in the reference's arithmetic type (fp32), for the CPU baseline timing of config C1 */
+int orc_episodic_f32(const float* T, const float* R, const float* pi, int S, int A, int H, float* Q, float* V) {
+  memset(Q, 0, sizeof(float) * (size_t)(H + 1) * S * A);
+  memset(V, 0, sizeof(float) * (size_t)(H + 1) * S);
+  for (int h = H - 1; h >= 0; --h) {
+    const float* Vn = V + (size_t)(h + 1) * S;
+    for (int s = 0; s < S; ++s) {
+      float best = -INFINITY, mix = 0.f;
+      for (int a = 0; a < A; ++a) {
+        const float* row = T + ((size_t)s * A + a) * S;
+        float acc = 0.f;
+        for (int j = 0; j < S; ++j) acc += row[j] * Vn[j];
+        float q = R[(size_t)s * A + a] + acc;
+        Q[((size_t)h * S + s) * A + a] = q;
+        if (q > best) best = q;
+        if (pi) mix += q * pi[((size_t)h * S + s) * A + a];
+      }
+      V[(size_t)h * S + s] = pi ? mix : best;
+    }
+  }
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (B4) continuous diameter: hardness/measures/diameter.py:76-106.  For target es: make es absorbing, reward -1
+ * elsewhere, VI with gamma=1; d_es = -min V.  Restated as the equivalent hitting-time recurrence
+ * (diameter.py:321-346): E[es]=0, E[j] = min_a (1 + sum_ns T[j,a,ns] E[ns]); iterated synchronously in fp64 to
+ * tolerance `tol` (no early exit -- the reference's early exits make its own value path-dependent at ~1e-5).
+ * E_out (may be NULL) receives the K x S table.  Returns max_k max_s E.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_diameter_continuous_f64(const float* T, const int* targets, int K, int S, int A, double tol,
+                                double max_value, long long max_iter, double* E_out, double* diameter,
+                                long long* sweeps) {
+  int rc = ORC_OK;
+  double diam = 0.0;
+  long long max_sweeps = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < K; ++k) {
+    int es = targets[k];
+    double* E = (double*)calloc((size_t)S, sizeof(double));
+    double* En = (double*)calloc((size_t)S, sizeof(double));
+    long long it = 0;
+    int local_rc = ORC_MAX_ITER;
+    for (; it < max_iter; ++it) {
+      double diff = 0.0, mx = 0.0;
+      for (int j = 0; j < S; ++j) {
+        if (j == es) {
+          En[j] = 0.0;
+          continue;
+        }
+        double best = INFINITY;
+        for (int a = 0; a < A; ++a) {
+          const float* row = T + ((size_t)j * A + a) * S;
+          double acc = 1.0;
+          for (int ns = 0; ns < S; ++ns) acc += (double)row[ns] * E[ns];
+          if (acc < best) best = acc;
+        }
+        En[j] = best;
+        double d = fabs(best - E[j]);
+        if (d > diff) diff = d;
+        if (best > mx) mx = best;
+      }
+      double* t = E;
+      E = En;
+      En = t;
+      if (max_value > 0.0 && mx > max_value) {
+        local_rc = ORC_OVERFLOW;
+        break;
+      }
+      if (diff < tol) {
+        local_rc = ORC_OK;
+        ++it;
+        break;
+      }
+    }
+    double mx = 0.0;
+    for (int j = 0; j < S; ++j)
+      if (E[j] > mx) mx = E[j];
+    if (E_out) memcpy(E_out + (size_t)k * S, E, sizeof(double) * (size_t)S);
+#pragma omp critical
+    {
+      if (mx > diam) diam = mx;
+      if (it > max_sweeps) max_sweeps = it;
+      if (local_rc != ORC_OK) rc = local_rc;
+    }
+    free(E);
+    free(En);
+  }
+  *diameter = diam;
+  if (sweeps) *sweeps = max_sweeps;
+  return rc;
+}
+
+/* the reference's own single-target kernel in ITS arithmetic (fp32, in place, its early exit):
+ * hardness/measures/diameter.py:321-346 -- used for the CPU baseline timing of the diameter. */
+float orc_diameter_target_ref_f32(const float* T, int es, int S, int A, float max_diam, float eps) {
+  float* E = (float*)calloc((size_t)S, sizeof(float));
+  float* Eo = (float*)calloc((size_t)S, sizeof(float));
+  float mx = 0.f;
+  for (long long t = 0; t < 1000000; ++t) {
+    memcpy(Eo, E, sizeof(float) * (size_t)S);
+    for (int j = 0; j < S; ++j) {
+      if (j == es) continue;
+      float best = INFINITY;
+      for (int a = 0; a < A; ++a) {
+        const float* row = T + ((size_t)j * A + a) * S;
+        float acc = 0.f;
+        for (int ns = 0; ns < S; ++ns)
+          if (ns != es) acc += row[ns] * (1.f + E[ns]);
+        acc += row[es];
+        if (acc < best) best = acc;
+      }
+      E[j] = best;
+    }
+    float diff = 0.f;
+    mx = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float d = fabsf(Eo[j] - E[j]);
+      if (d > diff) diff = d;
+      if (E[j] > mx) mx = E[j];
+    }
+    if (diff < eps || (diff < 0.05f && mx - 1.f < max_diam)) break;
+  }
+  free(E);
+  free(Eo);
+  return mx > max_diam ? mx : max_diam;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (B5) episodic diameter in the augmented (h,s) space: hardness/measures/diameter.py:285-318 on
+ * T_epi[H,S,A,S] (mdp/utils/mdp_creation.py:98-128).  Per target es: ETs[H-1,:] = T[H-1,0,0,:]@(1+ETs[0,:]);
+ * for h=H-1..1, j!=es: ETs[h-1,j] = min_a( T[h-1,j,a,es] + sum_{ns!=es} T[h-1,j,a,ns]*(1+ETs[h,ns]) ).
+ * Iterated in the reference's in-place order, fp64, to tolerance `tol` (no early exit).  Per state the minimum
+ * over h of the POSITIVE entries, then the max over states; diameter = max over targets.
+ * ---------------------------------------------------------------------------------------------------------- */
+int orc_diameter_episodic_f64(const float* T, const int* targets, int K, int H, int S, int A, double tol,
+                              long long max_iter, double* diameter, long long* sweeps) {
+  double diam = -INFINITY;
+  long long max_sweeps = 0;
+  int rc = ORC_OK;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < K; ++k) {
+    int es = targets[k];
+    double* E = (double*)calloc((size_t)H * S, sizeof(double));
+    long long it = 0;
+    int local_rc = ORC_MAX_ITER;
+    for (; it < max_iter; ++it) {
+      double diff = 0.0;
+      {
+        const float* row = T + ((size_t)(H - 1) * S * A) * S; /* T[H-1,0,0,:] */
+        double acc = 0.0;
+        for (int ns = 0; ns < S; ++ns) acc += (double)row[ns] * (1.0 + E[ns]);
+        for (int j = 0; j < S; ++j) {
+          double d = fabs(acc - E[(size_t)(H - 1) * S + j]);
+          if (d > diff) diff = d;
+          E[(size_t)(H - 1) * S + j] = acc;
+        }
+      }
+      for (int h = H - 1; h >= 1; --h) {
+        const double* En = E + (size_t)h * S;
+        for (int j = 0; j < S; ++j) {
+          if (j == es) continue;
+          double best = INFINITY;
+          for (int a = 0; a < A; ++a) {
+            const float* row = T + (((size_t)(h - 1) * S + j) * A + a) * S;
+            double acc = (double)row[es];
+            for (int ns = 0; ns < S; ++ns)
+              if (ns != es) acc += (double)row[ns] * (1.0 + En[ns]);
+            if (acc < best) best = acc;
+          }
+          double d = fabs(best - E[(size_t)(h - 1) * S + j]);
+          if (d > diff) diff = d;
+          E[(size_t)(h - 1) * S + j] = best;
+        }
+      }
+      if (diff < tol) {
+        local_rc = ORC_OK;
+        ++it;
+        break;
+      }
+    }
+    double cur = -INFINITY;
+    for (int s = 0; s < S; ++s) {
+      double mn = INFINITY;
+      for (int h = 0; h < H; ++h) {
+        double v = E[(size_t)h * S + s];
+        if (v > 0.0 && v < mn) mn = v;
+      }
+      if (mn > cur) cur = mn;
+    }
+#pragma omp critical
+    {
+      if (cur > diam) diam = cur;
+      if (it > max_sweeps) max_sweeps = it;
+      if (local_rc != ORC_OK) rc = local_rc;
+    }
+    free(E);
+  }
+  *diameter = diam;
+  if (sweeps) *sweeps = max_sweeps;
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (B6) environmental value norm: hardness/measures/value_norm.py:55-61,85-87.
+ * Ev[i,a]=sum_j T[i,a,j]V[j]; norm = max_{i,a} sqrt(sum_j T[i,a,j]*(V[j]-Ev[j,a])^2)  -- Ev indexed by the NEXT
+ * state j (reference behaviour, kept).
+ * ---------------------------------------------------------------------------------------------------------- */
+double orc_value_norm_f64(const float* T, const double* V, int S, int A) {
+  double* Ev = (double*)malloc(sizeof(double) * (size_t)S * A);
+  for (int i = 0; i < S; ++i)
+    for (int a = 0; a < A; ++a) {
+      const float* row = T + ((size_t)i * A + a) * S;
+      double acc = 0.0;
+      for (int j = 0; j < S; ++j) acc += (double)row[j] * V[j];
+      Ev[(size_t)i * A + a] = acc;
+    }
+  double best = 0.0;
+  for (int i = 0; i < S; ++i)
+    for (int a = 0; a < A; ++a) {
+      const float* row = T + ((size_t)i * A + a) * S;
+      double acc = 0.0;
+      for (int j = 0; j < S; ++j) {
+        double d = V[j] - Ev[(size_t)j * A + a];
+        acc += (double)row[j] * d * d;
+      }
+      double n = sqrt(acc);
+      if (n > best) best = n;
+    }
+  free(Ev);
+  return best;
+}
+
+/* (B7) gaps: hardness/measures/sum_reciprocals_suboptimality_gaps.py:6-28 */
+double orc_gaps_f64(const double* Q, const double* V, const unsigned char* mask, long long NS, int A, double reg) {
+  double acc = 0.0;
+  for (long long n = 0; n < NS; ++n) {
+    if (mask && !mask[n]) continue;
+    for (int a = 0; a < A; ++a) acc += 1.0 / (V[n] - Q[n * A + a] + reg);
+  }
+  return acc;
+}
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (A) interaction step.
+ * Philox4x32-10 (Salmon et al., SC'11) counter RNG: counter = (env lo, env hi, t lo, t hi), key = seed.
+ * ---------------------------------------------------------------------------------------------------------- */
+static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+void orc_philox(uint64_t seed, uint64_t env, uint64_t t, uint32_t out[4]) {
+  uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)t, (uint32_t)(t >> 32)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  memcpy(out, c, sizeof(uint32_t) * 4);
+}
+
+/* word -> uniform conventions shared with the CUDA kernels */
+static inline double u53(uint32_t a, uint32_t b) { /* CPython random(): (a>>5, b>>6) -> 53 bits */
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+static inline float u24(uint32_t a) { return (float)(a >> 8) * (1.0f / 16777216.0f); }
+static inline int act_from_word(uint32_t w, int A) { return (int)(((uint64_t)w * (uint64_t)A) >> 32); }
+
+typedef struct {
+  int S, A, H, ld;
+  const void* cdf;
+  const double* succ_cum;
+  const int* succ_idx;
+  const int* succ_len;
+  int Ksucc;
+  const unsigned char* rew_cls_sas;
+  const int* rew_cls_sa;
+  const int* rew_cls_succ;
+  const float* rew_q;
+  int n_cls, nq;
+  float rmin, rmax;
+  const double* start_cum;
+  const int* start_idx;
+  int n_start;
+} orc_tables;
+
+/* reward draw: quantile-table interpolation at u, then mdp/base.py:1205-1207's rescale r*(max-min) - min (sic) */
+static inline float reward_draw(const orc_tables* tb, int cls, float u) {
+  const float* q = tb->rew_q + (size_t)cls * tb->nq;
+  float t = u * (float)(tb->nq - 1);
+  int i = (int)t;
+  if (i > tb->nq - 2) i = tb->nq - 2;
+  float f = t - (float)i;
+  float r0 = fmaf(f, q[i + 1] - q[i], q[i]);
+  return fmaf(r0, tb->rmax - tb->rmin, -tb->rmin);
+}
+
+/* CPython random.choices / NextStateSampler.sample (mdp/utils/custom_samplers.py:49-72):
+ * bisect_right(cum, u*total, 0, n-1) over the sampler's own successor order. */
+static inline int bisect_pos(const double* cum, int n, double x) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi) / 2;
+    if (x < cum[mid])
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+
+static int sample_start(const orc_tables* tb, double u) {
+  if (tb->n_start == 1) return tb->start_idx[0];
+  double total = tb->start_cum[tb->n_start - 1] + 0.0;
+  return tb->start_idx[bisect_pos(tb->start_cum, tb->n_start, u * total)];
+}
+
+/* dense row search: first j with cdf[j] > x, clamped to the first j where the row reaches its total
+ * (= the last positive-probability index = bisect's hi=n-1 clamp on the sampler's successor list) */
+#define DENSE_SEARCH(TYPE, row, S, u, out)             \
+  do {                                                 \
+    TYPE total = (row)[(S)-1];                         \
+    TYPE x = (TYPE)(u) * total;                        \
+    int j1 = (S), j2 = (S)-1;                          \
+    for (int j = 0; j < (S); ++j)                      \
+      if ((row)[j] > x) {                              \
+        j1 = j;                                        \
+        break;                                         \
+      }                                                \
+    for (int j = 0; j < (S); ++j)                      \
+      if ((row)[j] >= total) {                         \
+        j2 = j;                                        \
+        break;                                         \
+      }                                                \
+    (out) = j1 < j2 ? j1 : j2;                         \
+  } while (0)
+
+/* mode: 0 dense f32 cdf (u_next float), 1 dense f64 cdf (u_next double), 2 successor lists (u_next double).
+ * Restates BaseMDP.reset / BaseMDP.step (mdp/base.py:1268-1317) for N independent envs; see SURVEY.md B.1/B.2. */
+int orc_env_step(const orc_tables* tb, int mode, long long N, int* action, int random_actions, const void* u_next,
+                 const float* u_rew, uint64_t seed, uint64_t t, uint64_t env0, int auto_reset, int* state, int* h,
+                 unsigned char* step_type, float* reward, int* obs, unsigned long long* visits_s,
+                 unsigned long long* visits_sa) {
+  int status = ORC_OK;
+  const int S = tb->S, A = tb->A;
+#pragma omp parallel for schedule(static)
+  for (long long e = 0; e < N; ++e) {
+    uint32_t w[4];
+    orc_philox(seed, env0 + (uint64_t)e, t, w);
+    double un64 = u_next ? (mode == 0 ? (double)((const float*)u_next)[e] : ((const double*)u_next)[e]) : u53(w[0], w[1]);
+    float un32 = u_next ? (mode == 0 ? ((const float*)u_next)[e] : 0.f) : u24(w[0]);
+    float ur = u_rew ? u_rew[e] : u24(w[2]);
+    if (step_type[e] == 2) {
+      if (!auto_reset) {
+#pragma omp critical
+        status = ORC_NEEDS_RESET;
+        continue;
+      }
+      int s0 = sample_start(tb, un64);
+      state[e] = s0;
+      h[e] = 0;
+      step_type[e] = 0;
+      reward[e] = NAN;
+      obs[e] = s0;
+      if (visits_s) {
+#pragma omp atomic
+        visits_s[s0] += 1ULL;
+      }
+      continue;
+    }
+    int a = random_actions ? act_from_word(w[3], A) : action[e];
+    if (random_actions) action[e] = a;
+    int s = state[e];
+    int nxt, cls;
+    if (mode == 2) {
+      size_t base = ((size_t)s * A + a) * tb->Ksucc;
+      int n = tb->succ_len[(size_t)s * A + a];
+      int pos = 0;
+      if (n > 1) {
+        double total = tb->succ_cum[base + n - 1] + 0.0;
+        pos = bisect_pos(tb->succ_cum + base, n, un64 * total);
+      }
+      nxt = tb->succ_idx[base + pos];
+      cls = tb->rew_cls_succ ? tb->rew_cls_succ[base + pos] : 0;
+    } else {
+      size_t base = ((size_t)s * A + a) * tb->ld;
+      if (mode == 0) {
+        const float* row = (const float*)tb->cdf + base;
+        DENSE_SEARCH(float, row, S, un32, nxt);
+      } else {
+        const double* row = (const double*)tb->cdf + base;
+        DENSE_SEARCH(double, row, S, un64, nxt);
+      }
+      cls = tb->rew_cls_sas ? tb->rew_cls_sas[((size_t)s * A + a) * S + nxt]
+                            : (tb->rew_cls_sa ? tb->rew_cls_sa[(size_t)s * A + a] : 0);
+    }
+    int hh = h[e] + 1;
+    h[e] = hh;
+    state[e] = nxt;
+    reward[e] = reward_draw(tb, cls, ur);
+    if (visits_s) {
+#pragma omp atomic
+      visits_s[nxt] += 1ULL;
+    }
+    if (visits_sa) {
+#pragma omp atomic
+      visits_sa[(size_t)nxt * A + a] += 1ULL;
+    }
+    if (tb->H > 0 && hh >= tb->H) {
+      step_type[e] = 2;
+      obs[e] = -1;
+    } else {
+      step_type[e] = 1;
+      obs[e] = nxt;
+    }
+  }
+  return status;
+}
+
+int orc_env_reset(const orc_tables* tb, long long N, const double* u_next, uint64_t seed, uint64_t t, uint64_t env0,
+                  int* state,
+                  int* h, unsigned char* step_type, int* obs, unsigned long long* visits_s) {
+  for (long long e = 0; e < N; ++e) {
+    uint32_t w[4];
+    orc_philox(seed, env0 + (uint64_t)e, t, w);
+    double u = u_next ? u_next[e] : u53(w[0], w[1]);
+    int s0 = sample_start(tb, u);
+    state[e] = s0;
+    h[e] = 0;
+    step_type[e] = 0;
+    obs[e] = s0;
+    if (visits_s) visits_s[s0] += 1ULL;
+  }
+  return ORC_OK;
+}
+
+/* dense cdf builder shared with the product's definition: sequential fp64 running sum, rounded to storage type,
+ * padding [S,ld) filled with the row total */
+void orc_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64) {
+  for (size_t r = 0; r < (size_t)S * A; ++r) {
+    double acc = 0.0;
+    for (int j = 0; j < ld; ++j) {
+      if (j < S) acc += (double)T[r * S + j];
+      if (out_is_f64)
+        ((double*)cdf)[r * ld + j] = acc;
+      else
+        ((float*)cdf)[r * ld + j] = (float)acc;
+    }
+  }
+}

@@ -1,0 +1,270 @@
+"""Python face of the CPU oracle (oracle/colo_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import this
+module.  The product package (colosseum_b200/) never does: it has no CPU path at all.
+
+Parity status: PINNED against the unmodified reference -- see tests/test_oracle_golden.py and
+tests/golden/make_golden.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcolo_oracle.so")
+
+OK, OVERFLOW, MAX_ITER, NEEDS_RESET = 0, 1, 2, 3
+FOLD_MAX, FOLD_PI, FOLD_MIN = 0, 1, 2
+
+
+def build(force=False):
+    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "colo_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_value_norm_f64.restype = C.c_double
+        _lib.orc_gaps_f64.restype = C.c_double
+        _lib.orc_diameter_target_ref_f32.restype = C.c_float
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, np.float32)
+
+
+class Tables(C.Structure):
+    """mirror of `orc_tables` / the product's `colo_mdp_tables` (host pointers here)."""
+
+    _fields_ = [
+        ("S", C.c_int), ("A", C.c_int), ("H", C.c_int), ("ld", C.c_int),
+        ("cdf", C.c_void_p),
+        ("succ_cum", C.c_void_p), ("succ_idx", C.c_void_p), ("succ_len", C.c_void_p), ("Ksucc", C.c_int),
+        ("rew_cls_sas", C.c_void_p), ("rew_cls_sa", C.c_void_p), ("rew_cls_succ", C.c_void_p),
+        ("rew_q", C.c_void_p), ("n_cls", C.c_int), ("nq", C.c_int),
+        ("rmin", C.c_float), ("rmax", C.c_float),
+        ("start_cum", C.c_void_p), ("start_idx", C.c_void_p), ("n_start", C.c_int),
+    ]
+
+
+# ---------------------------------------------------------------------------------------------- DP
+def discounted_gs_f32(T, R, pi=None, gamma=0.99, eps=1e-3, max_abs=None, max_iter=int(1e6)):
+    """the reference iterate (infinite_horizon.py:121-142 / :167-184): fp32, in place.  Returns (Q,V,iters)|None."""
+    T, R, pi = _f32(T), _f32(R), _f32(pi)
+    S, A, _ = T.shape
+    Q = np.zeros((S, A), np.float32)
+    V = np.zeros(S, np.float32)
+    it = C.c_longlong(0)
+    rc = lib().orc_discounted_gs_f32(_p(T), _p(R), _p(pi), S, A, C.c_float(gamma), C.c_float(eps),
+                                     C.c_float(max_abs or 0.0), C.c_longlong(max_iter), _p(Q), _p(V), C.byref(it))
+    if rc == OVERFLOW:
+        return None
+    if rc == MAX_ITER:
+        raise RuntimeError("max iterations exceeded")
+    return Q, V, it.value
+
+
+def discounted_f64(T, R, pi=None, gamma=0.99, tol=1e-12, max_abs=None, max_iter=int(1e6), fold=FOLD_MAX,
+                   gauss_seidel=False):
+    """fixed-point oracle in fp64.  Returns (Q,V,iters) | None."""
+    T, R, pi = _f32(T), _f32(R), _f32(pi)
+    S, A, _ = T.shape
+    if pi is not None:
+        fold = FOLD_PI
+    Q = np.zeros((S, A), np.float64)
+    V = np.zeros(S, np.float64)
+    it = C.c_longlong(0)
+    rc = lib().orc_discounted_f64(_p(T), _p(R), _p(pi), S, A, C.c_double(gamma), C.c_double(tol),
+                                  C.c_double(max_abs or 0.0), C.c_longlong(max_iter), fold, int(gauss_seidel),
+                                  _p(Q), _p(V), C.byref(it))
+    if rc == OVERFLOW:
+        return None
+    if rc == MAX_ITER:
+        raise RuntimeError("max iterations exceeded")
+    return Q, V, it.value
+
+
+def jacobi_sweeps_f64(T, R, V0, n, gamma=0.99, pi=None, fold=FOLD_MAX):
+    """n synchronous sweeps from V0 in fp64 (numpy) -- checks single backups / fixed sweep counts."""
+    T64 = np.asarray(T, np.float64)
+    V = np.asarray(V0, np.float64).copy()
+    Q = None
+    for _ in range(n):
+        Q = (0.0 if R is None else np.asarray(R, np.float64)) + gamma * (T64 @ V)
+        if fold == FOLD_PI:
+            V = (Q * np.asarray(pi, np.float64)).sum(-1)
+        elif fold == FOLD_MIN:
+            V = Q.min(-1)
+        else:
+            V = Q.max(-1)
+    return Q, V
+
+
+def episodic_f64(H, T, R, pi=None, max_value=None):
+    """finite_horizon.py:11-42.  Returns (Q[H+1,S,A], V[H+1,S]) | None."""
+    T, R, pi = _f32(T), _f32(R), _f32(pi)
+    S, A, _ = T.shape
+    Q = np.zeros((H + 1, S, A), np.float64)
+    V = np.zeros((H + 1, S), np.float64)
+    rc = lib().orc_episodic_f64(_p(T), _p(R), _p(pi), S, A, H, C.c_double(max_value or 0.0), _p(Q), _p(V))
+    return None if rc == OVERFLOW else (Q, V)
+
+
+def episodic_f32(H, T, R, pi=None):
+    T, R, pi = _f32(T), _f32(R), _f32(pi)
+    S, A, _ = T.shape
+    Q = np.zeros((H + 1, S, A), np.float32)
+    V = np.zeros((H + 1, S), np.float32)
+    lib().orc_episodic_f32(_p(T), _p(R), _p(pi), S, A, H, _p(Q), _p(V))
+    return Q, V
+
+
+# ---------------------------------------------------------------------------------------------- hardness
+def diameter_continuous_f64(T, targets=None, tol=1e-10, max_value=None, max_iter=int(1e6), return_E=False):
+    """hardness/measures/diameter.py:76-106 at the fixed point."""
+    T = _f32(T)
+    S, A, _ = T.shape
+    targets = np.arange(S, dtype=np.int32) if targets is None else np.ascontiguousarray(targets, np.int32)
+    K = len(targets)
+    E = np.zeros((K, S), np.float64) if return_E else None
+    d = C.c_double(0)
+    sw = C.c_longlong(0)
+    rc = lib().orc_diameter_continuous_f64(_p(T), _p(targets), K, S, A, C.c_double(tol), C.c_double(max_value or 0.0),
+                                           C.c_longlong(max_iter), _p(E), C.byref(d), C.byref(sw))
+    if rc == OVERFLOW:
+        return None
+    if rc == MAX_ITER:
+        raise RuntimeError("max iterations exceeded")
+    return (d.value, E, sw.value) if return_E else d.value
+
+
+def diameter_episodic_f64(T_epi, targets=None, tol=1e-10, max_iter=int(1e6)):
+    """hardness/measures/diameter.py:285-318 at the fixed point; T_epi is [H,S,A,S]."""
+    T_epi = _f32(T_epi)
+    H, S, A, _ = T_epi.shape
+    targets = np.arange(S, dtype=np.int32) if targets is None else np.ascontiguousarray(targets, np.int32)
+    d = C.c_double(0)
+    sw = C.c_longlong(0)
+    rc = lib().orc_diameter_episodic_f64(_p(T_epi), _p(targets), len(targets), H, S, A, C.c_double(tol),
+                                         C.c_longlong(max_iter), C.byref(d), C.byref(sw))
+    if rc == MAX_ITER:
+        raise RuntimeError("max iterations exceeded")
+    return d.value
+
+
+def diameter_target_ref_f32(T, es, max_diam=0.0, eps=1e-3):
+    T = _f32(T)
+    S, A, _ = T.shape
+    return float(lib().orc_diameter_target_ref_f32(_p(T), int(es), S, A, C.c_float(max_diam), C.c_float(eps)))
+
+
+def value_norm_f64(T, V):
+    """hardness/measures/value_norm.py:85-87 (Ev indexed by the next state, sic)."""
+    T = _f32(T)
+    V = np.ascontiguousarray(V, np.float64)
+    S, A, _ = T.shape
+    return float(lib().orc_value_norm_f64(_p(T), _p(V), S, A))
+
+
+def gaps_f64(Q, V, mask=None, reg=0.1):
+    """hardness/measures/sum_reciprocals_suboptimality_gaps.py:6-28; Q[...,A], V[...] flattened over leading dims."""
+    Q = np.ascontiguousarray(Q, np.float64)
+    V = np.ascontiguousarray(V, np.float64)
+    A = Q.shape[-1]
+    NS = V.size
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8).reshape(-1)
+    return float(lib().orc_gaps_f64(_p(Q), _p(V), _p(m), C.c_longlong(NS), A, C.c_double(reg)))
+
+
+# ---------------------------------------------------------------------------------------------- step
+def philox(seed, env, t):
+    out = (C.c_uint32 * 4)()
+    lib().orc_philox(C.c_uint64(seed), C.c_uint64(env), C.c_uint64(t), out)
+    return list(out)
+
+
+def build_dense_cdf(T, ld=None, f64=False):
+    T = _f32(T)
+    S, A, _ = T.shape
+    ld = ld or ((S + 31) // 32) * 32
+    cdf = np.zeros((S, A, ld), np.float64 if f64 else np.float32)
+    lib().orc_build_dense_cdf(_p(T), S, A, ld, _p(cdf), int(f64))
+    return cdf
+
+
+class HostTables:
+    """numpy-backed tables for orc_env_step; keeps the arrays alive."""
+
+    def __init__(self, S, A, H=0, cdf=None, succ_cum=None, succ_idx=None, succ_len=None, rew_cls_sas=None,
+                 rew_cls_sa=None, rew_cls_succ=None, rew_q=None, rmin=0.0, rmax=1.0, start_cum=None, start_idx=None):
+        self.keep = dict(
+            cdf=None if cdf is None else np.ascontiguousarray(cdf),
+            succ_cum=None if succ_cum is None else np.ascontiguousarray(succ_cum, np.float64),
+            succ_idx=None if succ_idx is None else np.ascontiguousarray(succ_idx, np.int32),
+            succ_len=None if succ_len is None else np.ascontiguousarray(succ_len, np.int32),
+            rew_cls_sas=None if rew_cls_sas is None else np.ascontiguousarray(rew_cls_sas, np.uint8),
+            rew_cls_sa=None if rew_cls_sa is None else np.ascontiguousarray(rew_cls_sa, np.int32),
+            rew_cls_succ=None if rew_cls_succ is None else np.ascontiguousarray(rew_cls_succ, np.int32),
+            rew_q=np.ascontiguousarray(rew_q if rew_q is not None else np.zeros((1, 2)), np.float32),
+            start_cum=np.ascontiguousarray(start_cum if start_cum is not None else [1.0], np.float64),
+            start_idx=np.ascontiguousarray(start_idx if start_idx is not None else [0], np.int32),
+        )
+        k = self.keep
+        t = Tables()
+        t.S, t.A, t.H = S, A, H
+        t.ld = 0 if k["cdf"] is None else k["cdf"].shape[-1]
+        t.Ksucc = 0 if k["succ_cum"] is None else k["succ_cum"].shape[-1]
+        for name in ("cdf", "succ_cum", "succ_idx", "succ_len", "rew_cls_sas", "rew_cls_sa", "rew_cls_succ", "rew_q",
+                     "start_cum", "start_idx"):
+            setattr(t, name, None if k[name] is None else k[name].ctypes.data)
+        t.n_cls, t.nq = k["rew_q"].shape
+        t.rmin, t.rmax = rmin, rmax
+        t.n_start = len(k["start_idx"])
+        self.c = t
+        self.cdf_is_f64 = k["cdf"] is not None and k["cdf"].dtype == np.float64
+
+
+def env_reset(tb, N, u_next=None, seed=0, t=0, visits_s=None, env0=0):
+    state = np.zeros(N, np.int32)
+    h = np.zeros(N, np.int32)
+    st = np.zeros(N, np.uint8)
+    obs = np.zeros(N, np.int32)
+    u = None if u_next is None else np.ascontiguousarray(u_next, np.float64)
+    lib().orc_env_reset(C.byref(tb.c), C.c_longlong(N), _p(u), C.c_uint64(seed), C.c_uint64(t), C.c_uint64(env0), _p(state),
+                        _p(h), _p(st), _p(obs), _p(visits_s))
+    return state, h, st, obs
+
+
+def env_step(tb, mode, state, h, step_type, action=None, u_next=None, u_rew=None, seed=0, t=0, auto_reset=False,
+             visits_s=None, visits_sa=None, env0=0):
+    """in-place on state/h/step_type (and action when random). mode: 0 dense f32, 1 dense f64, 2 successor.
+    Returns (reward, obs, status)."""
+    N = len(state)
+    random_actions = action is None
+    if random_actions:
+        action = np.zeros(N, np.int32)
+    assert action.dtype == np.int32 and state.dtype == np.int32 and h.dtype == np.int32 and step_type.dtype == np.uint8
+    if u_next is not None:
+        u_next = np.ascontiguousarray(u_next, np.float32 if mode == 0 else np.float64)
+    if u_rew is not None:
+        u_rew = np.ascontiguousarray(u_rew, np.float32)
+    reward = np.zeros(N, np.float32)
+    obs = np.zeros(N, np.int32)
+    rc = lib().orc_env_step(C.byref(tb.c), mode, C.c_longlong(N), _p(action), int(random_actions), _p(u_next),
+                            _p(u_rew), C.c_uint64(seed), C.c_uint64(t), C.c_uint64(env0), int(auto_reset), _p(state), _p(h),
+                            _p(step_type), _p(reward), _p(obs), _p(visits_s), _p(visits_sa))
+    return reward, obs, rc, action

@@ -19,6 +19,7 @@ the product or the oracle):
       vi_tight_Q, vi_tight_V    continuous only: reference numba VI with eps=1e-6 (near fixed point)
       pe_Q, pe_V                reference policy evaluation of the uniform random policy
       diameter, value_norm, gaps        mdp.diameter / mdp.value_norm / mdp.sum_reciprocals_suboptimality_gaps
+      diameter_tight            continuous, S<=110: the reference's per-target VI (diameter.py:76-95) with eps=2e-5
       cached_diameter, cached_value_norm    the reference's own cached_hardness_measures/*.txt (NaN if absent)
       T_epi (episodic)          mdp/utils/mdp_creation.py:98-128
       T_cf, R_cf, vi_cf_V (episodic)    continuous form + its VI (mdp/base_finite.py:167-178)
@@ -114,6 +115,30 @@ def inv_cdf_position(probs, u):
     return _bisect(cum, u * total, 0, len(probs) - 1)
 
 
+def reference_diameter_tight(T, eps=2e-5):
+    """the reference's per-target VI (hardness/measures/diameter.py:76-95) run with a small epsilon instead of its
+    default 1e-3, so that the recorded value sits at the fixed point instead of at the early stop."""
+    from colosseum.dynamic_programming.utils import DynamicProgrammingMaxIterationExceeded
+
+    S = T.shape[0]
+    best = 0.0
+    for es in range(S):
+        T_es = T.copy()
+        T_es[es] = 0
+        T_es[es, :, es] = 1
+        R_es = np.zeros(T.shape[:2], np.float32) - 1.0
+        R_es[es] = 0
+        e = eps
+        while True:
+            try:
+                _, V = _discounted_value_iteration(T_es, R_es, 1.0, e)
+                break
+            except DynamicProgrammingMaxIterationExceeded:
+                e *= 4
+        best = max(best, float(-V.min()))
+    return best
+
+
 def dist_key(d):
     name = d.dist.name
     args = tuple(float(a) for a in d.args)
@@ -196,6 +221,7 @@ def dump_instance(name, mdp, traj_steps=400, do_diameter=True, traj_seed=7):
     out["cached_value_norm"] = cached_measure(mdp, "value_norm")
     if not episodic:
         out["norm_of_vi_V"] = float(calculate_norm_discounted(T, out["vi_V"]))
+        out["diameter_tight"] = reference_diameter_tight(T) if S <= 110 else float("nan")
 
     # ---- a reference trajectory, with the uniforms its samplers consumed ----
     rng = np.random.RandomState(traj_seed)
@@ -289,6 +315,7 @@ def dp_synth():
         pol = rs.dirichlet(np.ones(A), size=(H, S)).astype(np.float32)
         Qpe, Vpe = episodic_policy_evaluation(H, T, R, pol)
         d = get_diameter(T, False)
+        recs[f"diam_tight_{b}"] = reference_diameter_tight(T)
         vn = calculate_norm_discounted(T, V)
         gaps = get_sum_reciprocals_suboptimality_gaps(Q, V)
         recs.update({
