@@ -94,7 +94,7 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_
   o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
   return o;
 }
-// word -> uniform conventions (shared with oracle/colo_oracle.c)
+// word -> uniform conventions (53-bit double as CPython's random(); 24-bit float)
 __host__ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {  // CPython random(): 53 bits
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kStepThreads) env_reset_kernel(const colo_mdp_
 
 template <typename TC>
 __global__ void build_dense_cdf_kernel(const float* __restrict__ T, int S, int A, int ld, TC* __restrict__ cdf) {
-  // one thread per (s,a) row: sequential fp64 running sum -- the DEFINED summation order shared with the oracle
+  // one thread per (s,a) row: sequential fp64 running sum -- the DEFINED summation order of the dense CDF
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= (long long)S * A) return;
   const float* row = T + r * S;

@@ -330,7 +330,15 @@ def dp_synth():
     np.savez_compressed(os.path.join(HERE, "dp_synth.npz"), **recs)
 
 
-def main():
+def main(only=None):
+    global dump_instance
+    if only:
+        _dump = dump_instance
+
+        def dump_instance(name, *a, **k):  # noqa: F811
+            if name in only:
+                _dump(name, *a, **k)
+
     from colosseum.mdp.deep_sea import DeepSeaContinuous, DeepSeaEpisodic
     from colosseum.mdp.frozen_lake import FrozenLakeContinuous, FrozenLakeEpisodic
     from colosseum.mdp.minigrid_empty import MiniGridEmptyContinuous, MiniGridEmptyEpisodic
@@ -340,8 +348,9 @@ def main():
     from colosseum.mdp.taxi import TaxiContinuous, TaxiEpisodic
 
     bench = os.path.join(REFERENCE_ROOT, "colosseum", "benchmark")
-    sampler_kat()
-    dp_synth()
+    if not only:
+        sampler_kat()
+        dp_synth()
 
     # C1: the quick-test RiverSwimEpisodic (BASELINE.json configs[0]); V[0] is the SURVEY parity anchor
     (p,) = gin_param_sets(
@@ -355,6 +364,10 @@ def main():
     # continuous-class instances whose (class, params, seed) have files in the reference's hardness cache
     dump_instance("deepsea20_prand", DeepSeaContinuous(seed=0, size=20, p_rand=0.1))
     dump_instance("deepsea10", DeepSeaContinuous(seed=0, size=10, p_rand=None))
+    # C2 (BASELINE.json configs[1]): DeepSeaContinuous size 30, both variants of SURVEY.md section 8d; the
+    # reference's diameter takes minutes at S=465 and is not recorded
+    dump_instance("c2_deepsea30", DeepSeaContinuous(seed=0, size=30, p_rand=None), do_diameter=False)
+    dump_instance("c2_deepsea30_prand", DeepSeaContinuous(seed=0, size=30, p_rand=0.1), do_diameter=False)
     for cls, gin_dir, picks in [
         (FrozenLakeContinuous, "benchmark_continuous_ergodic", [0]),
         (FrozenLakeContinuous, "benchmark_continuous_communicating", [0]),
@@ -398,4 +411,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only=set(sys.argv[1:]))  # optional: names of the instances to (re)generate

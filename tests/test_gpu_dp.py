@@ -1,0 +1,209 @@
+"""GPU parity: the CUDA Bellman backups (through the C ABI) against the CPU oracle and the reference goldens.
+
+Tolerances (BASELINE.json north_star): value functions within 1e-6 relative in fp64 mode, 1e-4 in fp32 mode, at
+the fixed point of the recurrence (the reference's dense kernel sweeps in place, the GPU sweeps synchronously;
+DESIGN.md explains why parity is defined at the fixed point)."""
+import numpy as np
+import pytest
+
+from conftest import CONTINUOUS, EPISODIC, load_instance
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL64, RTOL32 = 1e-6, 1e-4
+GAM = float(np.float32(0.99))
+
+
+@pytest.fixture(scope="module")
+def dp():
+    import colosseum_b200.dynamic_programming as dp
+
+    return dp
+
+
+def synth(seed, S, A, alpha=0.05):
+    rs = np.random.RandomState(seed)
+    T = rs.dirichlet(np.ones(S) * alpha, size=(S, A)).astype(np.float32)
+    T = (T / T.sum(-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    R = rs.uniform(0, 1, size=(S, A)).astype(np.float32)
+    return T, R
+
+
+@pytest.mark.parametrize("S,A", [(24, 4), (33, 3), (64, 2), (512, 4), (130, 5), (1, 1), (4, 9)])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_single_backup_matches_oracle(dp, S, A, precision):
+    """one synchronous sweep (infinite_horizon.py:131-135), vector and scalar load paths (S % 4 != 0), fold max/pi/min"""
+    T, R = synth(S * 7 + A, S, A, alpha=0.5)
+    rs = np.random.RandomState(1)
+    V0 = rs.uniform(-3, 5, S)
+    pi = rs.dirichlet(np.ones(A), size=S).astype(np.float32)
+    rtol = RTOL64 if precision == "f64" else RTOL32
+    for fold, p in ((orc.FOLD_MAX, None), (orc.FOLD_PI, pi), (orc.FOLD_MIN, None)):
+        Qo, Vo = orc.jacobi_sweeps_f64(T, R, V0, 1, gamma=0.9, pi=p, fold=fold)
+        Q, V, res = dp.bellman_backup(T, R, V0, gamma=0.9, pi=p, fold=fold, precision=precision, return_residual=True)
+        np.testing.assert_allclose(Q, Qo, rtol=rtol, atol=rtol)
+        np.testing.assert_allclose(V, Vo, rtol=rtol, atol=rtol)
+        v0 = V0 if precision == "f64" else V0.astype(np.float32)
+        np.testing.assert_allclose(res, np.abs(Vo - v0).max(), rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_discounted_vi_pe_golden_synth(dp, dp_synth, precision):
+    g = dp_synth
+    rtol = RTOL64 if precision == "f64" else RTOL32
+    eps = 1e-10 if precision == "f64" else 1e-5
+    for b in range(3):
+        T, R, pi = g[f"T_{b}"], g[f"R_{b}"], g[f"pi_{b}"]
+        Qo, Vo, _ = orc.discounted_f64(T, R, gamma=GAM, tol=1e-13)
+        Q, V = dp.discounted_value_iteration(T, R, 0.99, eps, precision=precision)
+        assert Q.shape == Qo.shape and V.shape == Vo.shape
+        assert Q.dtype == (np.float64 if precision == "f64" else np.float32)
+        np.testing.assert_allclose(V, Vo, rtol=rtol)
+        np.testing.assert_allclose(Q, Qo, rtol=rtol)
+        # ... and against the reference itself run to eps=1e-6 (its own fp32 noise bounds this one)
+        np.testing.assert_allclose(V, g[f"Vt_{b}"], rtol=1e-5, atol=2e-4)
+        Qpo, Vpo, _ = orc.discounted_f64(T, R, pi=pi, gamma=GAM, tol=1e-13)
+        Qp, Vp = dp.discounted_policy_evaluation(T, R, pi, 0.99, eps, precision=precision)
+        np.testing.assert_allclose(Vp, Vpo, rtol=rtol)
+        np.testing.assert_allclose(Qp, Qpo, rtol=rtol)
+        np.testing.assert_allclose(Vp, g[f"Vp_{b}"], rtol=3e-5)
+
+
+def test_reference_default_epsilon_semantics(dp, dp_synth):
+    """with the reference's default eps=1e-3 the GPU (Jacobi) result is within eps*gamma/(1-gamma) of the fixed
+    point, exactly like the reference's own (Gauss-Seidel) result -- both are early-stopped iterates"""
+    g = dp_synth
+    T, R = g["T_0"], g["R_0"]
+    Q, V = dp.discounted_value_iteration(T, R)
+    _, Vstar, _ = orc.discounted_f64(T, R, gamma=GAM, tol=1e-13)
+    bound = 1e-3 * GAM / (1 - GAM)
+    assert np.abs(V - Vstar).max() < bound and np.abs(g["V_0"] - Vstar).max() < bound
+    assert V.dtype == np.float32 and Q.dtype == np.float32
+
+
+def test_overflow_and_max_iter_contracts(dp, dp_synth):
+    g = dp_synth
+    T, R = g["T_0"], g["R_0"]
+    assert dp.discounted_value_iteration(T, R, max_abs_value=5.0) is None  # infinite_horizon.py:136-138
+    assert dp.episodic_value_iteration(7, T, R, max_value=1.5) is None  # finite_horizon.py:24-25
+    assert dp.episodic_value_iteration(7, T, R, max_value=1e9) is not None
+    with pytest.raises(dp.DynamicProgrammingMaxIterationExceeded):  # infinite_horizon.py:142
+        dp._solve_discounted(T, R, None, 0.99, 1e-12, None, "f64", max_iter=5)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_batched_instances_converge_independently(dp, precision):
+    """config C4's shape at test size: a batch of independent MDPs, each stopping at its own sweep"""
+    B, S, A = 6, 48, 4
+    Ts, Rs = zip(*[synth(b, S, A) for b in range(B)])
+    T, R = np.stack(Ts), np.stack(Rs)
+    R[3] *= 0.01  # converges much earlier than the others
+    eps = 1e-9 if precision == "f64" else 1e-4
+    Q, V = dp.discounted_value_iteration(T, R, 0.95, eps, precision=precision)
+    iters = dp.last_iterations()
+    assert len(iters) == B and iters[3] < max(iters)
+    rtol = RTOL64 if precision == "f64" else RTOL32
+    for b in range(B):
+        Qo, Vo, _ = orc.discounted_f64(T[b], R[b], gamma=float(np.float32(0.95)), tol=1e-13)
+        np.testing.assert_allclose(V[b], Vo, rtol=rtol, atol=rtol * 1e-2)
+        np.testing.assert_allclose(Q[b], Qo, rtol=rtol, atol=rtol * 1e-2)
+        # and each instance is bit-identical to solving it alone (no cross-instance coupling)
+        Q1, V1 = dp.discounted_value_iteration(T[b], R[b], 0.95, eps, precision=precision)
+        assert np.array_equal(V1, V[b]) and np.array_equal(Q1, Q[b])
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_episodic_golden(dp, dp_synth, precision):
+    g = dp_synth
+    rtol = RTOL64 if precision == "f64" else 2e-5
+    for b in range(3):
+        T, R, H = g[f"T_{b}"], g[f"R_{b}"], int(g[f"H_{b}"])
+        Qo, Vo = orc.episodic_f64(H, T, R)
+        Q, V = dp.episodic_value_iteration(H, T, R, precision=precision)
+        assert Q.shape == (H + 1,) + R.shape and V.shape == (H + 1, R.shape[0])
+        assert (V[H] == 0).all() and (Q[H] == 0).all()  # finite_horizon.py:17-18
+        np.testing.assert_allclose(V, Vo, rtol=rtol, atol=1e-7)
+        np.testing.assert_allclose(Q, Qo, rtol=rtol, atol=1e-7)
+        np.testing.assert_allclose(V, g[f"Ve_{b}"], rtol=1e-5, atol=1e-6)  # the reference's own output
+        pol = g[f"pol_{b}"]
+        Qpo, Vpo = orc.episodic_f64(H, T, R, pi=pol)
+        Qp, Vp = dp.episodic_policy_evaluation(H, T, R, pol, precision=precision)
+        np.testing.assert_allclose(Vp, Vpo, rtol=rtol, atol=1e-7)
+        np.testing.assert_allclose(Vp, g[f"Vpe_{b}"], rtol=1e-5, atol=1e-6)
+
+
+def test_c1_anchor(dp):
+    """BASELINE.json configs[0]: RiverSwimEpisodic size 5, V[0] from SURVEY.md section 8d"""
+    g = load_instance("c1_riverswim_epi")
+    Q, V = dp.episodic_value_iteration(int(g["H"]), g["T"], g["R"])
+    np.testing.assert_allclose(V[0], [0.45454547, 0.36414355, 0.2737823, 0.3346822, 0.4166667], rtol=2e-6)
+    np.testing.assert_allclose(V, g["vi_V"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(Q, g["vi_Q"], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", CONTINUOUS)
+def test_continuous_benchmark_instances(dp, name):
+    g = load_instance(name)
+    T, R = g["T"], g["R"]
+    S, A = R.shape
+    Qo, Vo, _ = orc.discounted_f64(T, R, gamma=GAM, tol=1e-13)
+    Q, V = dp.discounted_value_iteration(T, R, 0.99, 1e-10, precision="f64")
+    np.testing.assert_allclose(V, Vo, rtol=RTOL64)
+    np.testing.assert_allclose(Q, Qo, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(V, g["vi_tight_V"], rtol=1e-5, atol=3e-4)  # reference at eps=1e-6
+    Q32, V32 = dp.discounted_value_iteration(T, R, 0.99, 2e-5, precision="f32")
+    np.testing.assert_allclose(V32, Vo, rtol=RTOL32)
+    pi = np.ones((S, A), np.float32) / A
+    _, Vpo, _ = orc.discounted_f64(T, R, pi=pi, gamma=GAM, tol=1e-13)
+    _, Vp = dp.discounted_policy_evaluation(T, R, pi, precision="f64", epsilon=1e-10)
+    np.testing.assert_allclose(Vp, Vpo, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(Vp, g["pe_V"], rtol=5e-5, atol=1e-5)  # the reference's own output
+
+
+@pytest.mark.parametrize("name", EPISODIC)
+def test_episodic_benchmark_instances(dp, name):
+    g = load_instance(name)
+    T, R, H = g["T"], g["R"], int(g["H"])
+    S, A = R.shape
+    Q, V = dp.episodic_value_iteration(H, T, R, precision="f64")
+    Qo, Vo = orc.episodic_f64(H, T, R)
+    np.testing.assert_allclose(V, Vo, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(Q, Qo, rtol=RTOL64, atol=1e-9)
+    np.testing.assert_allclose(V, g["vi_V"], rtol=2e-5, atol=1e-6)
+    pol = np.ones((H, S, A), np.float32) / A
+    _, Vp = dp.episodic_policy_evaluation(H, T, R, pol, precision="f32")
+    np.testing.assert_allclose(Vp, g["pe_V"], rtol=2e-5, atol=1e-6)
+
+
+def test_full_size_c4_properties(dp):
+    """BASELINE.json configs[3] shape (S=512, A=4), a slice of the batch at full per-MDP size: size-independent
+    properties -- Bellman residual of the returned V is below eps, V is monotone in R, and a converged batch
+    entry equals the stand-alone solve."""
+    import torch
+
+    B, S, A = 8, 512, 4
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    T = torch._standard_gamma(torch.full((B, S, A, S), 0.05, device="cuda"), generator=gen).float() + 1e-30
+    T = (T / T.sum(-1, keepdim=True)).contiguous()
+    R = torch.rand((B, S, A), device="cuda", generator=gen)
+    Q, V = dp.discounted_value_iteration(T, R, 0.99, 1e-4, precision="f32")
+    assert V.is_cuda and V.shape == (B, S)
+    Q2, V2, res = dp.bellman_backup(T, R, V, gamma=GAM, precision="f32", return_residual=True)
+    assert float(res.max()) < 1e-4 * 1.5  # one more sweep moves V by less than eps
+    Qhi, Vhi = dp.discounted_value_iteration(T, R + 0.1, 0.99, 1e-4, precision="f32")
+    assert bool((Vhi >= V).all())  # monotone in R
+    np.testing.assert_allclose((Vhi - V).cpu().numpy(), 0.1 / (1 - GAM), rtol=2e-3)  # V(R+c) = V(R) + c/(1-gamma)
+    # oracle on one full-size instance
+    _, Vo, _ = orc.discounted_f64(T[5].cpu().numpy(), R[5].cpu().numpy(), gamma=GAM, tol=1e-11)
+    np.testing.assert_allclose(V[5].cpu().numpy(), Vo, rtol=RTOL32)
+
+
+def test_get_policy_from_q_values(dp):
+    Q = np.array([[0.0, 1.0, 0.5], [2.0, 2.0, 1.0], [3.0, 1.0, 3.0]], np.float32)
+    pi = dp.get_policy_from_q_values(Q)
+    assert pi.dtype == np.int32 and pi[0] == 1 and pi[1] in (0, 1) and pi[2] in (0, 2)
+    X = dp.get_policy_from_q_values(Q, True)
+    assert X.shape == Q.shape and (X.sum(-1) == 1).all() and (Q[np.arange(3), X.argmax(-1)] == Q.max(-1)).all()
+    X3 = dp.get_policy_from_q_values(np.stack([Q, Q]), True)
+    assert X3.shape == (2, 3, 3)

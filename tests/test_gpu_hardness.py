@@ -1,0 +1,116 @@
+"""GPU parity: diameter / environmental value norm / sub-optimality gaps against the oracle, the reference's own
+outputs (goldens), its cached_hardness_measures files and its executed notebooks."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CONTINUOUS, EPISODIC, GOLDEN, load_instance
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+GAM = float(np.float32(0.99))
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+@pytest.fixture(scope="module")
+def hd():
+    import colosseum_b200.hardness as hd
+
+    return hd
+
+
+@pytest.fixture(scope="module")
+def dp():
+    import colosseum_b200.dynamic_programming as dp
+
+    return dp
+
+
+def test_doc_notebook_goldens(hd, dp):
+    """docs/_sources/mds/hardness-analysis.ipynb:83-193"""
+    doc = json.load(open(os.path.join(GOLDEN, "doc_goldens.json")))
+    g = load_instance("doc_simplegrid4")
+    T, R = g["T"], g["R"]
+    d = hd.get_diameter(T, False)
+    assert rel(d, float(g["diameter_tight"])) < 2e-5 and rel(d, doc["diameter"]) < 2e-3
+    # fed with the reference's own (early-stopped) Q, V the measures reproduce the notebook to fp32 accuracy
+    assert rel(hd.calculate_norm_discounted(T, g["vi_V"]), doc["value_norm"]) < 1e-5
+    assert rel(hd.get_sum_reciprocals_suboptimality_gaps(g["vi_Q"], g["vi_V"]), doc["suboptimal_gaps"]) < 1e-5
+    # end to end on the GPU (converged V instead of the early-stopped one)
+    Q, V = dp.discounted_value_iteration(T, R, 0.99, 1e-10, precision="f64")
+    assert rel(hd.calculate_norm_discounted(T, V), doc["value_norm"]) < 2e-3
+    assert rel(hd.get_sum_reciprocals_suboptimality_gaps(Q, V), doc["suboptimal_gaps"]) < 2e-3
+
+
+@pytest.mark.parametrize("name", CONTINUOUS)
+def test_continuous_measures(hd, dp, name):
+    g = load_instance(name)
+    T = g["T"]
+    S = T.shape[0]
+    d, sweeps = hd.get_diameter(T, False, return_sweeps=True)
+    assert sweeps > 0
+    if np.isfinite(float(g["diameter_tight"])):
+        assert rel(d, float(g["diameter_tight"])) < 2e-5  # reference's VI kernel at eps=2e-5
+    if np.isfinite(float(g["diameter"])):
+        assert rel(d, float(g["diameter"])) < 2e-3  # reference default (early stop)
+    if np.isfinite(float(g["cached_diameter"])):
+        assert rel(d, float(g["cached_diameter"])) < 2e-3  # the reference's cached_hardness_measures file
+    if S <= 110:
+        assert rel(d, orc.diameter_continuous_f64(T)) < 1e-6
+    d32 = hd.get_diameter(T, False, precision="f32")
+    assert rel(d32, d) < 1e-4
+    if not bool(g["all_deterministic"]):
+        vn = hd.calculate_norm_discounted(T, g["vi_V"])
+        assert rel(vn, orc.value_norm_f64(T, g["vi_V"])) < 1e-6
+        assert rel(vn, float(g["value_norm"])) < 5e-5
+        assert rel(hd.calculate_norm_discounted(T, g["vi_V"], precision="f32"), vn) < 1e-4
+    gp = hd.get_sum_reciprocals_suboptimality_gaps(g["vi_Q"], g["vi_V"])
+    assert rel(gp, orc.gaps_f64(g["vi_Q"], g["vi_V"])) < 1e-12
+    assert rel(gp, float(g["gaps"])) < 1e-5
+
+
+def test_diameter_subset_of_targets_and_max_value(hd):
+    g = load_instance("taxicontinuous_ergo0")
+    T = g["T"]
+    tg = np.array([0, 5, 17, 50, 107], np.int32)
+    d = hd.get_diameter(T, False, targets=tg)
+    assert rel(d, orc.diameter_continuous_f64(T, targets=tg)) < 1e-6
+    assert hd.get_diameter(T, False, max_value=10.0) is None  # diameter.py:101-102
+    assert hd.get_diameter(T, False, max_value=1e6) is not None
+    with pytest.raises(AssertionError):  # diameter.py:29
+        hd.get_diameter(T, True)
+
+
+@pytest.mark.parametrize("name", EPISODIC)
+def test_episodic_measures(hd, name):
+    g = load_instance(name)
+    T_epi = g["T_epi"]
+    H, S = T_epi.shape[:2]
+    d = hd.get_diameter(T_epi, True)
+    assert rel(d, float(g["diameter"])) < 2e-3  # reference stops at eps=1e-3 with early exits
+    if S * H <= 1500:
+        assert rel(d, orc.diameter_episodic_f64(T_epi)) < 1e-6
+    assert rel(hd.get_diameter(T_epi, True, precision="f32"), d) < 1e-4
+    mask_pairs = list(zip(g["reach_h"].tolist(), g["reach_s"].tolist()))
+    gp = hd.get_sum_reciprocals_suboptimality_gaps(g["vi_Q"], g["vi_V"], mask_pairs)
+    assert rel(gp, float(g["gaps"])) < 1e-5
+    vn = hd.calculate_norm_discounted(g["T_cf"], g["vi_cf_V"])
+    assert rel(vn, float(g["value_norm"])) < 5e-5
+    with pytest.raises(AssertionError):
+        hd.get_sum_reciprocals_suboptimality_gaps(g["vi_Q"], g["vi_V"])  # reachable_states is mandatory
+
+
+def test_dp_synth_measures(hd, dp_synth):
+    g = dp_synth
+    for b in range(3):
+        T = g[f"T_{b}"]
+        d = hd.get_diameter(T, False)
+        assert rel(d, float(g[f"diam_tight_{b}"])) < 2e-5
+        assert rel(d, orc.diameter_continuous_f64(T)) < 1e-6
+        assert rel(hd.calculate_norm_discounted(T, g[f"V_{b}"]), float(g[f"vnorm_{b}"])) < 5e-5
+        assert rel(hd.get_sum_reciprocals_suboptimality_gaps(g[f"Q_{b}"], g[f"V_{b}"]), float(g[f"gaps_{b}"])) < 1e-5

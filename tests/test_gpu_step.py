@@ -1,0 +1,235 @@
+"""GPU parity: the batched interaction step (BaseMDP.reset/step, colosseum/mdp/base.py:1268-1317).
+
+Bit-exact bar (BASELINE.json north_star): next-state / observation / step-type / h / visitation results are
+identical to the reference's inverse-CDF given identical supplied uniforms -- checked (i) against trajectories
+recorded from the reference itself (successor-order tables), (ii) against CPython random.choices draws, and
+(iii) against the CPU oracle for the dense kernels and the built-in Philox stream; plus a chi-square test of the
+sampled frequencies against T."""
+import numpy as np
+import pytest
+
+from conftest import CONTINUOUS, EPISODIC, load_instance
+from colosseum_b200.tables import MDPTables
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def bm():
+    import colosseum_b200.batched_mdp as bm
+
+    return bm
+
+
+def host_tables(tb, mode, cdf=None):
+    if mode == 2:
+        return orc.HostTables(tb.S, tb.A, H=tb.H, succ_cum=tb.succ_cum, succ_idx=tb.succ_idx, succ_len=tb.succ_len,
+                              rew_cls_succ=tb.rew_cls_succ, rew_q=tb.rew_q, rmin=tb.rmin, rmax=tb.rmax,
+                              start_cum=tb.start_cum, start_idx=tb.start_idx)
+    return orc.HostTables(tb.S, tb.A, H=tb.H, cdf=cdf, rew_cls_sas=tb.rew_cls_sas, rew_cls_sa=tb.rew_cls_sa,
+                          rew_q=tb.rew_q, rmin=tb.rmin, rmax=tb.rmax, start_cum=tb.start_cum, start_idx=tb.start_idx)
+
+
+@pytest.mark.parametrize("name", CONTINUOUS + EPISODIC)
+def test_reference_trajectory_replay(bm, name):
+    """the reference's own reset/step trajectory (auto_reset=True), replayed with the uniforms its samplers
+    consumed, 3 identical envs in parallel: every TimeStep field and the visitation counts are identical."""
+    g = load_instance(name)
+    tb = MDPTables.from_golden(g)
+    N = 3
+    env = bm.BatchedMDP(tb, N, mode="succ")
+    acts, us = g["traj_action"], np.nan_to_num(g["traj_u"], nan=0.5)
+    ts = env.reset(u_next=np.full(N, us[0]))
+    assert (ts.step_type.cpu().numpy() == g["traj_step_type"][0]).all()
+    assert (ts.observation.cpu().numpy() == g["traj_obs"][0]).all()
+    assert ts.scalar(0).reward is None and ts.scalar(0).discount is None and ts.scalar(0).first()
+    det = all(k == "deterministic" for k, _ in tb.rew_kinds)
+    for t in range(1, len(acts)):
+        ts = env.step(np.full(N, acts[t], np.int32), auto_reset=True, u_next=np.full(N, us[t]),
+                      u_reward=np.zeros(N, np.float32))
+        st = ts.step_type.cpu().numpy()
+        assert (st == g["traj_step_type"][t]).all(), f"step {t}"
+        assert (ts.observation.cpu().numpy() == g["traj_obs"][t]).all(), f"step {t}"
+        one = ts.scalar(1)
+        if st[0] != 0:
+            assert one.discount == float(g["traj_discount"][t])
+            if det:
+                assert abs(one.reward - float(g["traj_reward"][t])) < 1e-6
+        else:
+            assert one.reward is None and one.discount is None
+    assert (env.get_visitation_counts().cpu().numpy() == N * g["traj_visits_s"]).all()
+    assert (env.get_visitation_counts(False).cpu().numpy() == N * g["traj_visits_sa"]).all()
+
+
+def test_cpython_choices_kat(bm, sampler_kat):
+    """5 x 5000 draws of random.Random(seed).choices (custom_samplers.py:49-72), succ and dense-f64 kernels"""
+    for i in range(5):
+        probs, us, chosen = sampler_kat[f"probs_{i}"], sampler_kat[f"u_{i}"], sampler_kat[f"chosen_{i}"]
+        n = len(probs)
+        tb = MDPTables.from_successors(n, 1, np.tile(np.arange(n, dtype=np.int32), (n, 1, 1)),
+                                       np.tile(probs, (n, 1, 1)), np.full((n, 1), n), np.zeros((n, 1, n), np.int32),
+                                       [("deterministic", (0.0,))], [0], [1.0])
+        N = len(us)
+        env = bm.BatchedMDP(tb, N, mode="succ")
+        env.reset()
+        env.state.zero_()
+        env.step(np.zeros(N, np.int32), u_next=us, u_reward=np.zeros(N, np.float32))
+        assert (env.state.cpu().numpy() == chosen).all(), f"kat {i}"
+
+
+MODES = [("dense_f32", 0), ("dense_f64", 1), ("succ", 2)]
+
+
+@pytest.mark.parametrize("name", ["taxicontinuous_ergo0", "c1_riverswim_epi", "frozenlakecontinuous_ergo0",
+                                  "minigridempty5_epi", "c2_deepsea30_prand"])
+@pytest.mark.parametrize("mode,omode", MODES)
+def test_kernels_match_oracle_bit_exact(bm, name, mode, omode):
+    """N ragged (not a multiple of 32), supplied uniforms for 6 steps then the built-in Philox stream with random
+    actions for 30 more, auto-reset on: every output array equals the oracle's, bit for bit"""
+    import torch
+
+    g = load_instance(name)
+    tb = MDPTables.from_golden(g)
+    N = 1000 + 37
+    env = bm.BatchedMDP(tb, N, mode=mode, seed=1234)
+    cdf = None
+    if omode != 2:
+        cdf = env.dev.keep["cdf"].cpu().numpy()
+        # the device-built dense CDF equals the oracle's definition (sequential fp64 sum rounded to storage type)
+        assert np.array_equal(cdf, orc.build_dense_cdf(tb.T, ld=tb.ld, f64=(omode == 1)))
+    ht = host_tables(tb, omode, cdf)
+    rs = np.random.RandomState(5)
+    vis_s = np.zeros(tb.S, np.uint64)
+    vis_sa = np.zeros((tb.S, tb.A), np.uint64)
+    u0 = rs.random_sample(N)
+    ts = env.reset(u_next=u0)
+    state, h, st, obs = orc.env_reset(ht, N, u_next=u0, visits_s=vis_s)
+    assert np.array_equal(env.state.cpu().numpy(), state)
+    for t in range(36):
+        if t < 6:
+            a = rs.randint(tb.A, size=N).astype(np.int32)
+            un = rs.random_sample(N)
+            if omode == 0:
+                un = un.astype(np.float32)
+            ur = rs.random_sample(N).astype(np.float32)
+            ts = env.step(a, auto_reset=True, u_next=un, u_reward=ur)
+            r, obs, rc, _ = orc.env_step(ht, omode, state, h, st, action=a.copy(), u_next=un, u_rew=ur,
+                                         auto_reset=True, visits_s=vis_s, visits_sa=vis_sa)
+        else:
+            tcount = env.t
+            ts, acts = env.random_step(auto_reset=True)
+            r, obs, rc, a_o = orc.env_step(ht, omode, state, h, st, action=None, seed=1234, t=tcount,
+                                           auto_reset=True, visits_s=vis_s, visits_sa=vis_sa)
+            stepping = st != 0
+            assert np.array_equal(acts.cpu().numpy()[stepping], a_o[stepping])
+        assert rc == 0
+        assert np.array_equal(env.state.cpu().numpy(), state), f"t={t}"
+        assert np.array_equal(env.h.cpu().numpy(), h)
+        assert np.array_equal(ts.step_type.cpu().numpy(), st)
+        assert np.array_equal(ts.observation.cpu().numpy(), obs)
+        rg = ts.reward.cpu().numpy()
+        assert np.array_equal(np.isnan(rg), np.isnan(r)) and np.array_equal(rg[~np.isnan(r)], r[~np.isnan(r)])
+        d = ts.discount.cpu().numpy()
+        assert ((d == 1.0) == (st == 1)).all() and ((d == 0.0) == (st == 2)).all()
+    assert np.array_equal(env.visits_s.cpu().numpy(), vis_s.astype(np.int64))
+    assert np.array_equal(env.visits_sa.cpu().numpy(), vis_sa.astype(np.int64))
+    assert int(env.visits_s.sum()) == N * 37 and int(env.visits_sa.sum()) == N * 36 - int((vis_s.sum() - N) - vis_sa.sum())
+
+
+@pytest.mark.parametrize("mode", ["dense_f32", "dense_f64", "succ"])
+def test_chi_square_against_T(bm, mode):
+    """sampled next-state frequencies vs T[s,a,:] (Taxi: up to 10 successors), built-in Philox stream"""
+    import scipy.stats
+    import torch
+
+    g = load_instance("taxicontinuous_ergo0")
+    tb = MDPTables.from_golden(g)
+    N = 1 << 16
+    env = bm.BatchedMDP(tb, N, mode=mode, seed=99)
+    env.reset()
+    s, a = int(np.argmax((g["succ_len"] >= 8).any(-1))), int(np.argmax(g["succ_len"].max(0) >= 8))
+    s, a = [(i, j) for i in range(tb.S) for j in range(tb.A) if g["succ_len"][i, j] >= 8][0]
+    env.state.fill_(s)
+    env.step(np.full(N, a, np.int32))
+    counts = np.bincount(env.state.cpu().numpy(), minlength=tb.S).astype(np.float64)
+    p = tb.T[s, a].astype(np.float64)
+    assert counts[p == 0].sum() == 0  # zero-probability states are never produced
+    sel = p > 0
+    chi2 = ((counts[sel] - N * p[sel]) ** 2 / (N * p[sel])).sum()
+    pval = scipy.stats.chi2.sf(chi2, sel.sum() - 1)
+    assert pval > 1e-4, (chi2, pval)
+
+
+def test_episodic_termination_and_reset_contract(bm):
+    g = load_instance("c1_riverswim_epi")
+    tb = MDPTables.from_golden(g)
+    env = bm.BatchedMDP(tb, 5, mode="succ")
+    with pytest.raises(AttributeError):  # step before reset (reference: necessary_reset unset, base.py:405 vs :1272)
+        env.step(np.zeros(5, np.int32))
+    env.reset()
+    for t in range(tb.H):
+        ts = env.step(np.ones(5, np.int32))
+    assert bool(ts.last().all()) and bool((ts.observation == -1).all()) and bool((ts.discount == 0).all())
+    with pytest.raises(AssertionError):  # base.py:1291
+        env.step(np.zeros(5, np.int32))
+    ts = env.step(np.zeros(5, np.int32), auto_reset=True)
+    assert bool(ts.first().all()) and bool((env.h == 0).all())
+    assert env.H == tb.H and env.is_episodic() and env.n_states == 5 and env.n_actions == 2
+
+
+def test_reward_distribution_on_device(bm):
+    """rewards drawn on the GPU from the heavy-tailed C1 distributions vs scipy (base.py:1196-1207's rescale incl.)"""
+    import scipy.stats
+
+    g = load_instance("c1_riverswim_epi")
+    tb = MDPTables.from_golden(g)
+    N = 1 << 17
+    env = bm.BatchedMDP(tb, N, mode="succ", seed=3)
+    env.reset()
+    # state 4 (rightmost), action RIGHT=1 -> the "optimal" Beta(0.01, 0.11) class on the self-loop
+    env.state.fill_(4)
+    env.step(np.ones(N, np.int32))
+    r = env.reward.cpu().numpy().astype(np.float64)
+    nxt = env.state.cpu().numpy()
+    cls = tb.rew_cls_succ[4, 1]
+    for k in range(int(tb.succ_len[4, 1])):
+        sel = nxt == tb.succ_idx[4, 1, k]
+        kind, args = tb.rew_kinds[cls[k]]
+        dist = getattr(scipy.stats, kind)(*args)
+        x = (r[sel] + tb.rmin) / (tb.rmax - tb.rmin)  # undo r*(max-min) - min
+        assert abs(x.mean() - dist.mean()) < 5 * dist.std() / np.sqrt(sel.sum()) + 1e-4
+        xs = np.concatenate([np.logspace(-30, -1, 200), np.linspace(0.1, 1.0, 200)])
+        emp = np.searchsorted(np.sort(x), xs, side="right") / sel.sum()
+        assert np.abs(emp - dist.cdf(xs)).max() < 0.01
+
+
+def test_c2_full_size_properties(bm):
+    """BASELINE.json configs[1]: DeepSeaContinuous size 30, 65,536 envs.  Size-independent properties: the depth
+    coordinate is deterministic in DeepSea, so all envs share h-dependent state sets; sharding the batch over two
+    env_offset halves reproduces the unsharded run exactly; visitation totals are conserved."""
+    g = load_instance("c2_deepsea30_prand")
+    tb = MDPTables.from_golden(g)
+    N = 65536
+    full = bm.BatchedMDP(tb, N, mode="dense_f32", seed=1234)
+    lo = bm.BatchedMDP(tb, N // 2, mode="dense_f32", seed=1234, env_offset=0)
+    hi = bm.BatchedMDP(tb, N // 2, mode="dense_f32", seed=1234, env_offset=N // 2)
+    for e in (full, lo, hi):
+        e.reset()
+    for _ in range(40):
+        for e in (full, lo, hi):
+            e.random_step()
+    import torch
+
+    assert torch.equal(full.state, torch.cat([lo.state, hi.state]))
+    assert torch.equal(full.reward, torch.cat([lo.reward, hi.reward]))
+    assert torch.equal(full.visits_sa, lo.visits_sa + hi.visits_sa)
+    assert int(full.visits_s.sum()) == N * 41
+    # oracle on a prefix of the batch (same Philox stream)
+    cdf = full.dev.keep["cdf"].cpu().numpy()
+    ht = host_tables(tb, 0, cdf)
+    M = 2048
+    state, h, st, obs = orc.env_reset(ht, M, seed=1234, t=0)
+    for t in range(1, 41):
+        orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t)
+    assert np.array_equal(full.state[:M].cpu().numpy(), state)

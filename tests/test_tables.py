@@ -1,0 +1,67 @@
+"""CPU: host-side table extraction (colosseum_b200/tables.py) against the arrays recorded from the reference."""
+import numpy as np
+import pytest
+
+from conftest import CONTINUOUS, EPISODIC, load_instance
+from colosseum_b200.tables import MDPTables, quantile_table, running_sum
+
+
+@pytest.mark.parametrize("name", CONTINUOUS + EPISODIC)
+def test_tables_from_golden(name):
+    g = load_instance(name)
+    tb = MDPTables.from_golden(g)
+    S, A = tb.S, tb.A
+    # dense T rebuilt from the successor lists (duplicates summed) == the reference's T (mdp_creation.py:80)
+    tb2 = MDPTables.from_successors(S, A, g["succ_idx"], g["succ_prob"], g["succ_len"], g["rew_cls"],
+                                    tb.rew_kinds, g["start_idx"], g["start_prob"], H=tb.H)
+    np.testing.assert_allclose(tb2.T, g["T"], rtol=0, atol=2e-7)  # the reference sums duplicates in fp32
+    # expected rewards from (p, reward class means) == the reference's R (mdp_creation.py:71-81)
+    np.testing.assert_allclose(tb.expected_rewards(), g["R"], rtol=1e-5, atol=1e-6)
+    # running sums: last finite entry is the row total ~ 1, padding is +inf, indices padded with the last successor
+    last = np.take_along_axis(tb.succ_cum, (tb.succ_len - 1)[..., None].astype(np.int64), -1)[..., 0]
+    np.testing.assert_allclose(last, 1.0, atol=1e-9)
+    K = tb.succ_cum.shape[-1]
+    pad = np.arange(K)[None, None, :] >= tb.succ_len[..., None]
+    assert np.isinf(tb.succ_cum[pad]).all()
+    assert (tb.succ_cum[..., 1:] >= tb.succ_cum[..., :-1]).all()  # non-decreasing, +inf padding included
+    assert tb.rew_cls_sas.shape == (S, A, S) and tb.rew_q.shape[0] == len(tb.rew_kinds)
+    assert tb.ld % 32 == 0 and tb.ld >= S
+    assert abs(tb.start_cum[-1] - 1.0) < 1e-9 and tb.n_start == len(g["start_idx"])
+
+
+def test_running_sum_is_sequential():
+    p = np.random.RandomState(0).dirichlet(np.ones(13))
+    acc, ref = 0.0, []
+    for x in p:
+        acc = acc + x
+        ref.append(acc)
+    assert (running_sum(p) == np.asarray(ref)).all()  # bit-for-bit itertools.accumulate
+
+
+def test_quantile_tables():
+    q = quantile_table("deterministic", (0.25,), 17)
+    assert (q == np.float32(0.25)).all()
+    q = quantile_table("beta", (2.4, 24.0), 1025)
+    assert q[0] == 0.0 and q[-1] == 1.0 and (np.diff(q) >= 0).all()
+    q = quantile_table("norm", (0.0, 1.0), 1025)
+    assert np.isfinite(q).all() and (np.diff(q) > 0).all()
+
+
+@pytest.mark.reference
+def test_from_mdp_matches_golden_recording():
+    """the duck-typed extractor on a live reference object == what make_golden.py recorded (build container only)"""
+    from oracle.reference_import import import_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    import_reference()
+    import colosseum.mdp  # noqa: F401
+    from colosseum.mdp.simple_grid import SimpleGridContinuous
+
+    mdp = SimpleGridContinuous(seed=0, size=4, p_rand=0.01, n_starting_states=3)
+    tb = MDPTables.from_mdp(mdp)
+    g = load_instance("doc_simplegrid4")
+    ref = MDPTables.from_golden(g)
+    for f in ("succ_idx", "succ_cum", "succ_len", "rew_cls_succ", "T", "rew_cls_sas", "start_idx", "start_cum", "rew_q"):
+        assert np.array_equal(getattr(tb, f), getattr(ref, f)), f
+    assert tb.rew_kinds == ref.rew_kinds and (tb.S, tb.A, tb.H) == (ref.S, ref.A, ref.H)
