@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for colosseum_b200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload step|vi|all]
+
+Headline workload (BASELINE.json configs[1], "C2"): DeepSeaContinuous(size=30, p_rand=0.1) -- S=465, A=2 -- with
+65,536 parallel envs PER GPU advanced by the batched step kernel; metric = batched env-steps/sec over all GPUs.
+One "step" = one launch of the step kernel over every env of the rank (inputs resident in HBM).  The JSON line also
+carries, under "vi", value-iteration MDP-sweeps/sec on config C4's shape (B x (S=512, A=4) synthetic Dirichlet
+MDPs, one sweep = one launch of the backup kernel over the whole batch) with its own roofline.
+
+`--impl reference` times the reference's CPU algorithm for the same workload on the host cores (the C oracle port
+under oracle/, all threads) -- the only other place this file touches oracle/.  /root/reference does not exist on
+the GPU box and is never read here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_INSTANCE = "c2_deepsea30_prand"
+C2_ENVS_PER_GPU = 65536
+STEP_BYTES = lambda S: 4 * S + 28  # dense CDF row + 28 B of state I/O per env-step
+L2_FLUSH_BYTES = 256 << 20
+
+
+def vi_sweep_bytes(S, A, store_q=True):
+    """4*S*A*S (T) + 4*S*A (R) + 4*S (V read) + 4*S (V write) [+ 4*S*A Q] per MDP-sweep"""
+    return 4 * S * A * S + 4 * S * A + 8 * S + (4 * S * A if store_q else 0)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(key):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get(key)
+    return None
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_c2_tables():
+    from colosseum_b200.tables import MDPTables
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"inst_{C2_INSTANCE}.npz"))
+    return MDPTables.from_golden(g)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def dist_setup(n_gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier_sync(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch
+
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_step_gpu(args, rank, world):
+    """kernel-resident number (`value`) and end-to-end number (`e2e`) for the batched step"""
+    import torch
+
+    from colosseum_b200 import _cabi
+    from colosseum_b200.batched_mdp import BatchedMDP
+
+    tb = load_c2_tables()
+    N = C2_ENVS_PER_GPU
+    env = BatchedMDP(tb, N, mode="dense_f32", seed=1234, env_offset=rank * N)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    n_act = 8
+    actions = [torch.randint(0, tb.A, (N,), dtype=torch.int32, device="cuda", generator=gen) for _ in range(n_act)]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    lib = _cabi.lib()
+
+    def one_step(i):
+        env.step_async(actions[i % n_act], auto_reset=True)
+
+    for i in range(args.warmup):
+        flush.zero_()
+        one_step(i)
+    barrier_sync(world)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    lib.colo_reset_launch_count()
+    for i in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (256 MiB write > 126 MB L2); not timed
+        starts[i].record()
+        one_step(i)
+        stops[i].record()
+    barrier_sync(world)
+    launches = int(lib.colo_launch_count())
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+    ms = max_over_ranks(ms, world)
+    assert int(env.status.item()) == 0
+
+    # ---- end to end through the public API: pinned host actions in, TimeStep fields out, every step
+    h_act = [a.cpu().pin_memory() for a in actions]
+    h_out = torch.empty(9 * N, dtype=torch.uint8).pin_memory()  # obs | reward | step_type
+
+    def e2e_step(i):
+        env.step_async(h_act[i % n_act], auto_reset=True)  # pinned host tensor -> H2D inside
+        env.fetch_async(h_out)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the TimeStep before choosing the next action
+
+    for i in range(max(3, args.warmup)):
+        e2e_step(i)
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier_sync(world)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N)
+
+
+def make_c4_batch(B, S, A, seed):
+    """C4's generator on the device: T[b,s,a,:] ~ Dirichlet(0.05), rows renormalised in fp32; R ~ U[0,1)"""
+    import torch
+
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    T = torch.empty((B, S, A, S), dtype=torch.float32, device="cuda")
+    chunk = max(1, min(B, 256))
+    for b0 in range(0, B, chunk):
+        b1 = min(B, b0 + chunk)
+        g = torch._standard_gamma(torch.full((b1 - b0, S, A, S), 0.05, device="cuda"), generator=gen) + 1e-30
+        T[b0:b1] = g / g.sum(-1, keepdim=True)
+    R = torch.rand((B, S, A), device="cuda", generator=gen)
+    return T, R
+
+
+def bench_vi_gpu(args, rank, world):
+    """VI sweeps on C4's shape: one step = one synchronous sweep of the whole resident batch (T > L2: no flush)"""
+    import torch
+
+    from colosseum_b200 import _cabi
+    from colosseum_b200.dynamic_programming import BatchedValueIteration
+
+    B, S, A = args.vi_batch, 512, 4
+    T, R = make_c4_batch(B, S, A, seed=100 + rank)
+    vi = BatchedValueIteration(T, R, gamma=0.99, precision="f32")
+    lib = _cabi.lib()
+    steps = max(5, min(args.steps, 50))
+    for _ in range(max(3, args.warmup)):
+        vi.sweep()
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.colo_reset_launch_count()
+    e0.record()
+    vi.sweep(steps)
+    e1.record()
+    barrier_sync(world)
+    launches = int(lib.colo_launch_count())
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    return dict(B=B, S=S, A=A, steps=steps, ms=ms, launches=launches)
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_step_rate(tb, n_envs, seconds):
+    """the reference algorithm for the step (oracle port, C + OpenMP, all host threads), bounded sample"""
+    from oracle import oracle as orc
+
+    cdf = orc.build_dense_cdf(tb.T, ld=tb.ld, f64=False)
+    ht = orc.HostTables(tb.S, tb.A, H=tb.H, cdf=cdf, rew_cls_sas=tb.rew_cls_sas, rew_q=tb.rew_q, rmin=tb.rmin,
+                        rmax=tb.rmax, start_cum=tb.start_cum, start_idx=tb.start_idx)
+    state, h, st, obs = orc.env_reset(ht, n_envs, seed=1234, t=0)
+    vs = np.zeros(tb.S, np.uint64)
+    vsa = np.zeros((tb.S, tb.A), np.uint64)
+    t, n = 1, 0
+    for _ in range(3):
+        orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
+        t += 1
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
+        t += 1
+        n += 1
+    dt = time.perf_counter() - t0
+    return n * n_envs / dt, n, dt
+
+
+def cpu_vi_rate(B, S, A, seconds):
+    """reference VI iterate (fp32 in-place sweeps, infinite_horizon.py:121-142) over a batch, all host threads"""
+    import ctypes as C
+
+    from oracle import oracle as orc
+
+    rs = np.random.RandomState(0)
+    T = rs.dirichlet(np.ones(S) * 0.05, size=(B, S, A)).astype(np.float32)
+    R = rs.uniform(0, 1, size=(B, S, A)).astype(np.float32)
+    V = np.zeros((B, S), np.float32)
+    lib = orc.lib()
+    fn = lib.orc_sweeps_gs_f32_batch
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    fn(p(T), p(R), B, S, A, C.c_float(0.99), 2, p(V))
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        fn(p(T), p(R), B, S, A, C.c_float(0.99), 5, p(V))
+        n += 5
+    dt = time.perf_counter() - t0
+    return n * B / dt, n, dt
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU algorithm (oracle port), all host threads, same config/metric"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tb = load_c2_tables()
+    cores = os.cpu_count()
+    N = C2_ENVS_PER_GPU
+    from oracle import oracle as orc
+
+    cdf = orc.build_dense_cdf(tb.T, ld=tb.ld, f64=False)
+    ht = orc.HostTables(tb.S, tb.A, H=tb.H, cdf=cdf, rew_cls_sas=tb.rew_cls_sas, rew_q=tb.rew_q, rmin=tb.rmin,
+                        rmax=tb.rmax, start_cum=tb.start_cum, start_idx=tb.start_idx)
+    state, h, st, obs = orc.env_reset(ht, N, seed=1234, t=0)
+    vs = np.zeros(tb.S, np.uint64)
+    vsa = np.zeros((tb.S, tb.A), np.uint64)
+    t = 1
+    steps = min(args.steps, 2000)
+    for _ in range(args.warmup):
+        orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
+        t += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
+        t += 1
+    dt = time.perf_counter() - t0
+    value = steps * N / dt
+    vi_rate, vi_n, vi_dt = cpu_vi_rate(64, 512, 4, 5.0)
+    line = {
+        "impl": "reference", "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2 DeepSeaContinuous(size=30,p_rand=0.1) S={tb.S} A={tb.A}, {N} envs, dense-CDF "
+                               "inverse-CDF step, random actions, auto-reset, visitation counts on",
+                   "where": "host CPU cores (reference algorithm; the reference has no GPU path)"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} batched steps of {N} envs, C+OpenMP oracle port of "
+                                   "BaseMDP.step/NextStateSampler.sample"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "vi": {"metric": "value-iteration MDP-sweeps/sec", "value": vi_rate, "unit": "MDP-sweeps/s",
+               "sample": f"{vi_n} in-place fp32 sweeps x 64 MDPs (S=512,A=4) in {vi_dt:.1f}s, {cores} threads"},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all", "step", "vi"])
+    ap.add_argument("--vi-batch", type=int, default=1024, help="MDP instances per GPU for the VI leg (C4 is 4096/g)")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    import torch
+
+    from colosseum_b200 import _cabi
+
+    _cabi.require_cuda()  # fails loudly without the CUDA library / a GPU: there is no fallback
+    rank, world, local = dist_setup(args.gpus)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    step = bench_step_gpu(args, rank, world) if args.workload in ("all", "step") else None
+    vi = bench_vi_gpu(args, rank, world) if args.workload in ("all", "vi") else None
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    line = {"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "clocks": clocks}
+    if vi is not None:
+        per_sweep_bytes = vi_sweep_bytes(vi["S"], vi["A"]) * vi["B"]
+        sec = vi["ms"] / 1e3 / vi["steps"]
+        vi_line = {
+            "metric": "value-iteration MDP-sweeps/sec", "value": world * vi["B"] / sec, "unit": "MDP-sweeps/s",
+            "steps": vi["steps"], "ms_per_step": 1e3 * sec, "gpu_launches": vi["launches"],
+            "config": {"workload": f"C4 shape: {vi['B']} synthetic Dirichlet(0.05) MDPs per GPU, S=512 A=4 fp32, "
+                                   "gamma=0.99, one synchronous sweep of the whole batch per step, Q stored",
+                       "l2": f"batch T = {vi['B'] * 4 * 512 * 4 * 512 / 2**30:.1f} GiB per GPU >> 126 MB L2, no flush"},
+            "roofline": {"bound": "hbm", "achieved": per_sweep_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": per_sweep_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("backup_kernel"),
+                         "peak_source": peak_src, "kernel": "backup_kernel<float,MAX,VEC,warp>",
+                         "algorithmic_bytes_per_launch": per_sweep_bytes},
+        }
+    if step is not None:
+        tb, N = step["tb"], step["N"]
+        sec = step["ms"] / 1e3 / args.steps
+        bytes_per_launch = STEP_BYTES(tb.S) * N
+        line.update({
+            "metric": "batched env-steps/sec", "value": world * N / sec, "unit": "env-steps/s", "steps": args.steps,
+            "ms_per_step": 1e3 * sec, "gpu_launches": step["launches"],
+            "config": {"workload": f"C2 DeepSeaContinuous(size=30,p_rand=0.1) S={tb.S} A={tb.A}, {N} envs per GPU, "
+                                   "dense-CDF warp-cooperative inverse-CDF step, supplied actions, in-kernel Philox "
+                                   "uniforms, auto-reset, visitation counts on",
+                       "l2": "flushed between timed steps (256 MiB write), each step timed with its own CUDA events"},
+            "e2e": {"value": world * N * args.steps / (step["e2e_ms"] / 1e3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": step["h2d"], "d2h_bytes_per_step": step["d2h"],
+                    "what": "BatchedMDP.step_async from pinned host actions + obs/reward/step_type read back to pinned "
+                            "host memory and stream sync, every step"},
+            "roofline": {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("env_step_dense_short_kernel"),
+                         "peak_source": peak_src, "kernel": "env_step_dense_short_kernel<float,4,4>",
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "note": "T (1.8 MB) is L2/L1-resident by construction in C2: algorithmic bytes are served "
+                                 "on chip, so frac can exceed 1; see DESIGN.md and `traffic`"},
+        })
+        if world == 1:
+            rate, n, dt = cpu_step_rate(tb, N, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{n} batched steps of {N} envs in {dt:.1f}s (C+OpenMP oracle port of "
+                                              "BaseMDP.step; the Python reference itself runs ~5e4 steps/s/core)"}
+        if vi is not None:
+            line["vi"] = vi_line
+    else:
+        line.update(vi_line)
+    if vi is not None and world == 1:
+        rate, n, dt = cpu_vi_rate(64, 512, 4, args.cpu_seconds)
+        tgt = line["vi"] if step is not None else line
+        tgt["cpu_baseline"] = {"value": rate, "unit": "MDP-sweeps/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"{n} in-place fp32 sweeps x 64 MDPs (S=512,A=4) in {dt:.1f}s (C+OpenMP port "
+                                         "of _discounted_value_iteration's sweep)"}
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

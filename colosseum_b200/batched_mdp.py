@@ -95,16 +95,28 @@ class BatchedMDP:
         self.state = torch.zeros(N, dtype=torch.int32, device="cuda")
         self.h = torch.zeros(N, dtype=torch.int32, device="cuda")
         # before the first reset() the reference raises (necessary_reset is unset, base.py:405 vs :1272);
-        # LAST + auto_reset=False reproduces that as an error, LAST + auto_reset=True resets.
-        self.step_type = torch.full((N,), _cabi.STEP_LAST, dtype=torch.uint8, device="cuda")
-        self.reward = torch.zeros(N, dtype=torch.float32, device="cuda")
-        self.obs = torch.zeros(N, dtype=torch.int32, device="cuda")
+        # step_type = LAST + auto_reset=False reproduces that as an error, LAST + auto_reset=True resets.
+        # the three TimeStep fields a host-side agent reads back live in ONE buffer (obs | reward | step_type), so an
+        # end-to-end step is a single device->host copy
+        self._out = torch.zeros(9 * N, dtype=torch.uint8, device="cuda")
+        self.obs = self._out[: 4 * N].view(torch.int32)
+        self.reward = self._out[4 * N: 8 * N].view(torch.float32)
+        self.step_type = self._out[8 * N:]
+        self.step_type.fill_(_cabi.STEP_LAST)
         self.action = torch.zeros(N, dtype=torch.int32, device="cuda")
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.visits_s = torch.zeros(tables.S, dtype=torch.int64, device="cuda") if track_visits else None
         self.visits_sa = torch.zeros((tables.S, tables.A), dtype=torch.int64, device="cuda") if track_visits else None
         self.t = 0  # launch counter: the Philox stream position
         self._was_reset = False
+        # static launch arguments, resolved once (a step is then one ctypes call)
+        lib = _cabi.lib()
+        self._step_fn = {"dense_f32": (lib.colo_env_step_dense_f32, torch.float32),
+                         "dense_f64": (lib.colo_env_step_dense_f64, torch.float64),
+                         "succ": (lib.colo_env_step_succ, torch.float64)}[mode]
+        self._tb_ref = C.byref(self.dev.c)
+        self._ptrs = {k: _cabi.ptr(getattr(self, k)) for k in
+                      ("action", "state", "h", "step_type", "reward", "obs", "visits_s", "visits_sa", "status")}
 
     # -- reference attribute surface (base.py:463-503, 1233-1252)
     @property
@@ -158,27 +170,25 @@ class BatchedMDP:
         (BaseMDP.random_step, base.py:1341-1355) and records them in self.action."""
         torch = self.torch
         random_actions = action is None
+        act_ptr = self._ptrs["action"]
         if not random_actions:
             if isinstance(action, torch.Tensor):
-                self.action.copy_(action.to(torch.int32), non_blocking=True)
+                if action.is_cuda and action.dtype == torch.int32 and action.is_contiguous():
+                    act_ptr = action.data_ptr()  # read in place: no staging copy
+                else:
+                    self.action.copy_(action, non_blocking=True)  # pinned host tensors: async H2D
             else:
-                a = np.ascontiguousarray(np.broadcast_to(np.asarray(action, np.int32), (self.n_envs,)))
+                a = np.array(np.broadcast_to(np.asarray(action, np.int32), (self.n_envs,)))
                 self.action.copy_(torch.from_numpy(a), non_blocking=True)
-        lib = _cabi.lib()
-        if self.mode == "dense_f32":
-            fn, udt = lib.colo_env_step_dense_f32, torch.float32
-        elif self.mode == "dense_f64":
-            fn, udt = lib.colo_env_step_dense_f64, torch.float64
-        else:
-            fn, udt = lib.colo_env_step_succ, torch.float64
-        un = self._u(u_next, udt)
-        ur = self._u(u_reward, torch.float32)
-        rc = fn(C.byref(self.dev.c), self.n_envs, _cabi.ptr(self.action), int(random_actions), _cabi.ptr(un),
-                _cabi.ptr(ur), self.seed, self.t, self.env_offset, int(bool(auto_reset)), _cabi.ptr(self.state),
-                _cabi.ptr(self.h), _cabi.ptr(self.step_type), _cabi.ptr(self.reward), _cabi.ptr(self.obs),
-                _cabi.ptr(self.visits_s), _cabi.ptr(self.visits_sa), _cabi.ptr(self.status),
-                _cabi.current_stream())
-        _cabi.check(rc, "colo_env_step")
+        fn, udt = self._step_fn
+        un = None if u_next is None else self._u(u_next, udt)
+        ur = None if u_reward is None else self._u(u_reward, torch.float32)
+        p = self._ptrs
+        rc = fn(self._tb_ref, self.n_envs, act_ptr, int(random_actions), _cabi.ptr(un), _cabi.ptr(ur), self.seed,
+                self.t, self.env_offset, int(bool(auto_reset)), p["state"], p["h"], p["step_type"], p["reward"],
+                p["obs"], p["visits_s"], p["visits_sa"], p["status"], torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            _cabi.check(rc, "colo_env_step")
         self.t += 1
         if check or not auto_reset:
             # the reference asserts `not self.necessary_reset` (base.py:1291); stepping before reset() raises too
@@ -187,6 +197,17 @@ class BatchedMDP:
                 if not self._was_reset:
                     raise AttributeError("step() called before reset() (reference: necessary_reset is unset)")
                 raise AssertionError("an episode has terminated: call reset() or step(..., auto_reset=True)")
+
+    def fetch_async(self, host_buffer):
+        """one device->host copy of (obs i32[N] | reward f32[N] | step_type u8[N]) into a pinned uint8 buffer of
+        9*N bytes, enqueued on the current stream; `split_host` views it as the three arrays."""
+        host_buffer.copy_(self._out, non_blocking=True)
+
+    def split_host(self, host_buffer):
+        N = self.n_envs
+        torch = self.torch
+        return (host_buffer[: 4 * N].view(torch.int32), host_buffer[4 * N: 8 * N].view(torch.float32),
+                host_buffer[8 * N:])
 
     def step(self, action, auto_reset=False, u_next=None, u_reward=None) -> BatchedTimeStep:
         """BaseMDP.step (base.py:1279-1317) for every env."""

@@ -15,7 +15,7 @@
 
 namespace colo {
 
-constexpr int kStepThreads = 256;
+constexpr int kStepThreads = 64;  // small CTAs: 2048 warp-tiles at N=65,536 spread evenly over 148 SMs
 
 struct StepIO {
   long long N;
@@ -149,6 +149,44 @@ __device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tabl
   if (io.visits_sa) aggregated_inc(io.visits_sa, (long long)nxt * tb.A + in.a, stepping);
 }
 
+// Position of x in one monotone dense row, warp-cooperative.  The row is read as quads (4 consecutive entries per
+// lane per 128-entry chunk), every load issued before any is consumed.  Because the row is non-decreasing, the
+// number of entries <= x (STRICT: < x) is found hierarchically: one ballot per chunk on each quad's LAST entry
+// counts the quads lying entirely at or below x; only the lane owning the crossing quad then looks at its other
+// three entries.  ~3 instructions per chunk instead of a compare+add per entry and a 5-step shuffle reduction.
+template <typename TC, int NCH, bool STRICT>
+__device__ __forceinline__ int row_count_below(const TC* __restrict__ row, int ld, TC x, int lane) {
+  for (int g = 0; g < ld; g += 128 * NCH) {
+    Quad<TC> q[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = g + k * 128 + lane * 4;
+      if (c < ld) q[k].load(row + c);
+    }
+    int quads = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = g + k * 128 + lane * 4;
+      const bool below = (c < ld) && (STRICT ? (q[k].v[3] < x) : (q[k].v[3] <= x));
+      quads += __popc(__ballot_sync(FULL, below));
+    }
+    const int in_group = min(32 * NCH, (ld - g) >> 2);
+    if (quads < in_group) {  // warp-uniform: the crossing quad is in this group
+      const int kq = quads >> 5, lq = quads & 31;
+      int part = 0;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k)
+        if (k == kq)
+          part = STRICT ? ((q[k].v[0] < x) + (q[k].v[1] < x) + (q[k].v[2] < x))
+                        : ((q[k].v[0] <= x) + (q[k].v[1] <= x) + (q[k].v[2] <= x));
+      return g + 4 * quads + __shfl_sync(FULL, part, lq);
+    }
+  }
+  return ld;
+}
+
+constexpr int kEnvUnroll = 4;  // independent row searches in flight per warp
+
 template <typename TC, int NCH>
 __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo_mdp_tables tb, const StepIO io) {
   const int lane = threadIdx.x & 31;
@@ -169,49 +207,28 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
     const bool resetting = is_last && io.auto_reset;
     const bool stepping = valid && !is_last;
     if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
-    const unsigned step_mask = __ballot_sync(FULL, stepping);
+    // lanes that do not step still take part in the searches with a harmless row (keeps the loop branch-free)
+    const int s_l = stepping ? in.s : 0, a_l = stepping ? in.a : 0;
+    const TC u_l = F32U ? (TC)in.un32 : (TC)in.un64;
 
     int my_next = 0;
-    // the warp walks over the envs of its tile; every lane helps searching env i's row
-    for (int i = 0; i < 32; ++i) {
-      if (!((step_mask >> i) & 1u)) continue;  // warp-uniform
-      const int s_i = __shfl_sync(FULL, in.s, i);
-      const int a_i = __shfl_sync(FULL, in.a, i);
-      const TC u_i = F32U ? (TC)__shfl_sync(FULL, in.un32, i) : (TC)__shfl_sync(FULL, in.un64, i);
-      const TC* row = cdf + ((size_t)s_i * A + a_i) * ld;
-      const TC total = __ldg(row + S - 1);
-      int cnt_le = 0, cnt_lt = 0;
-      for (int g = 0; g < ld; g += 128 * NCH) {
-        Quad<TC> q[NCH];
+    // the warp walks over the 32 envs of its tile; every lane helps searching env i's row
+    for (int i0 = 0; i0 < 32; i0 += kEnvUnroll) {
 #pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          const int c = g + k * 128 + lane * 4;
-          if (c < ld) q[k].load(row + c);
-        }
+      for (int k = 0; k < kEnvUnroll; ++k) {
+        const int i = i0 + k;
+        const int s_i = __shfl_sync(FULL, s_l, i);
+        const int a_i = __shfl_sync(FULL, a_l, i);
+        const TC u_i = __shfl_sync(FULL, u_l, i);
+        const TC* row = cdf + ((size_t)s_i * A + a_i) * ld;
+        const TC total = __ldg(row + S - 1);
         const TC x = u_i * total;
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          const int c = g + k * 128 + lane * 4;
-          if (c < ld) {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              cnt_le += (q[k].v[m] <= x) ? 1 : 0;      // entries <= x  -> first j with cdf[j] > x
-              cnt_lt += (q[k].v[m] < total) ? 1 : 0;   // entries < total -> last positive-probability index
-            }
-          }
-        }
+        // first j with cdf[j] > x  ==  number of entries <= x
+        int nxt = row_count_below<TC, NCH, false>(row, ld, x, lane);
+        if (nxt >= S)  // x >= total (rounding): bisect's hi = n-1 clamp == first index where the row reaches total
+          nxt = row_count_below<TC, NCH, true>(row, ld, total, lane);
+        if (lane == i) my_next = nxt;
       }
-      int j1, j2;
-      if (ld < 65536) {
-        int packed = warp_sum(cnt_le | (cnt_lt << 16));
-        j1 = packed & 0xffff;
-        j2 = packed >> 16;
-      } else {
-        j1 = warp_sum(cnt_le);
-        j2 = warp_sum(cnt_lt);
-      }
-      const int nxt = j1 < j2 ? j1 : j2;
-      if (lane == i) my_next = nxt;
     }
     int cls = 0;
     if (stepping) {
@@ -221,6 +238,84 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
         cls = tb.rew_cls_sa[(size_t)in.s * A + in.a];
     }
     finish_env(io, tb, valid ? e : 0, in, my_next, cls, stepping, resetting);
+  }
+}
+
+// SHORT rows (ld == 128 * NCH, NCH <= 8; the host pads rows of S <= 1024 to whole 128-entry chunks):
+// branch-free, software-pipelined variant.  For U envs at a time the warp issues every row load (U * NCH 128-bit
+// loads per lane in flight), then finds for each env the number G of quads lying entirely at or below x with one
+// ballot + popc per chunk.  The within-quad step is deferred to the epilogue, where lane i finishes env i on its
+// own (one 16-byte gather of quad G, which the warp has just pulled into L1), i.e. it is vectorised over the 32
+// envs of the tile instead of costing shuffles and selects inside the per-env loop.
+template <typename TC, int NCH, int U>
+__global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(const colo_mdp_tables tb, const StepIO io) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * kStepThreads + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * kStepThreads) >> 5;
+  const long long n_tiles = (io.N + 31) >> 5;
+  const int S = tb.S, A = tb.A;
+  constexpr int ld = 128 * NCH;
+  const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
+  constexpr bool F32U = sizeof(TC) == 4;
+
+  for (long long tile = warp_global; tile < n_tiles; tile += n_warps) {
+    const long long e = tile * 32 + lane;
+    const bool valid = e < io.N;
+    EnvIn in;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    if (valid) in = load_env<F32U>(io, tb, e);
+    const bool is_last = valid && in.st == COLO_STEP_LAST;
+    const bool resetting = is_last && io.auto_reset;
+    const bool stepping = valid && !is_last;
+    if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
+    // lanes that do not step take part with row 0 (keeps the loop branch-free); 32-bit element offsets
+    // (the host checks S*A*ld < 2^31)
+    const unsigned off_l = stepping ? (unsigned)(in.s * A + in.a) * (unsigned)ld : 0u;
+    const TC u_l = F32U ? (TC)in.un32 : (TC)in.un64;
+
+    int my_G = 0;
+    for (int i0 = 0; i0 < 32; i0 += U) {
+      Quad<TC> q[U][NCH];
+      TC x[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const unsigned off = __shfl_sync(FULL, off_l, i0 + k);
+        const TC u = __shfl_sync(FULL, u_l, i0 + k);
+        const TC* row = cdf + off;
+        x[k] = u * __ldg(row + S - 1);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) q[k][c].load(row + c * 128 + lane * 4);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        int G = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) G += __popc(__ballot_sync(FULL, q[k][c].v[3] <= x[k]));
+        my_G = (lane == i0 + k) ? G : my_G;
+      }
+    }
+    // per-lane finish: env `lane` of the tile
+    int nxt = 0, cls = 0;
+    if (stepping) {
+      const TC* row = cdf + off_l;
+      const TC total = __ldg(row + S - 1);
+      const TC xl = u_l * total;  // same operands, same product as in the search above
+      nxt = ld;
+      if (my_G < 32 * NCH) {
+        Quad<TC> qq;
+        qq.load(row + 4 * my_G);  // the crossing quad: its last entry is > x, its first three decide
+        nxt = 4 * my_G + (qq.v[0] <= xl) + (qq.v[1] <= xl) + (qq.v[2] <= xl);
+      }
+      if (nxt >= S) {  // x >= total (rounding): bisect's hi = n-1 clamp == first index where the row reaches total
+        nxt = 0;
+        while (nxt < S - 1 && __ldg(row + nxt) < total) ++nxt;
+      }
+      if (tb.rew_cls_sas)
+        cls = tb.rew_cls_sas[((size_t)in.s * A + in.a) * S + nxt];
+      else if (tb.rew_cls_sa)
+        cls = tb.rew_cls_sa[(size_t)in.s * A + in.a];
+    }
+    finish_env(io, tb, valid ? e : 0, in, nxt, cls, stepping, resetting);
   }
 }
 
@@ -322,15 +417,25 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
   if (io.N == 0) return COLO_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for(kStepThreads / 32, (io.N + 31) / 32);
-  const int chunks = (tb->ld + 127) / 128;
-  if (chunks <= 1)
-    env_step_dense_kernel<TC, 1><<<grid, kStepThreads, 0, st>>>(*tb, io);
-  else if (chunks <= 2)
-    env_step_dense_kernel<TC, 2><<<grid, kStepThreads, 0, st>>>(*tb, io);
-  else if (chunks <= 4)
-    env_step_dense_kernel<TC, 4><<<grid, kStepThreads, 0, st>>>(*tb, io);
-  else
+  const int ld = tb->ld;
+  const bool short_rows = ld % 128 == 0 && ld <= 1024 && (long long)tb->S * tb->A * ld < (1LL << 31);
+  if (short_rows) {
+#define COLO_SHORT(NCH, U) \
+  case NCH: env_step_dense_short_kernel<TC, NCH, U><<<grid, kStepThreads, 0, st>>>(*tb, io); break
+    switch (ld / 128) {
+      COLO_SHORT(1, 4);
+      COLO_SHORT(2, 4);
+      COLO_SHORT(3, 4);
+      COLO_SHORT(4, 4);
+      COLO_SHORT(5, 2);
+      COLO_SHORT(6, 2);
+      COLO_SHORT(7, 2);
+      COLO_SHORT(8, 2);
+    }
+#undef COLO_SHORT
+  } else {
     env_step_dense_kernel<TC, 8><<<grid, kStepThreads, 0, st>>>(*tb, io);
+  }
   return check_launch("env_step_dense_kernel");
 }
 

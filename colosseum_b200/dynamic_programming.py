@@ -269,3 +269,71 @@ def get_policy_from_q_values(Q, stochastic_form=False):
     X = np.zeros(Qh.shape, np.float32)
     np.put_along_axis(X, idx[..., None].astype(np.int64), 1.0, axis=-1)
     return X
+
+
+# ------------------------------------------------------------------------------------------------ resident sweeper
+class BatchedValueIteration:
+    """Device-resident synchronous value iteration over a batch of MDPs: T, R stay in HBM, V ping-pongs, and
+    `sweep()` is exactly one launch of the backup kernel (no allocation, no host sync).  This is what bench.py
+    times for config C4/C5 and what a model-based agent that re-plans every episode would hold on to."""
+
+    def __init__(self, T, R, gamma=0.99, pi=None, precision=None, row0=0, S_total=None):
+        torch = _torch()
+        self.precision = precision or _PRECISION
+        self.f64 = self.precision == "f64"
+        self.T, self.R, self.pi = to_device(T), to_device(R), to_device(pi)
+        if self.T.dim() == 3:
+            self.T, self.R = self.T[None], self.R[None]
+            self.pi = None if self.pi is None else self.pi[None]
+        B, nrows, A, S = self.T.shape
+        self.B, self.nrows, self.A, self.S = B, nrows, A, S
+        self.row0 = int(row0)
+        assert S == (S_total or S) and self.row0 + nrows <= S
+        vd = _vdtype(self.precision)
+        self.V = [torch.zeros((B, S), dtype=vd, device="cuda") for _ in range(2)]
+        self.Q = torch.zeros((B, nrows, A), dtype=vd, device="cuda")
+        self.resid = torch.zeros(B, dtype=torch.int64 if self.f64 else torch.int32, device="cuda")
+        self.cur = 0
+        a = _cabi.BackupArgs()
+        a.T, a.R, a.pi, a.Q = _cabi.ptr(self.T), _cabi.ptr(self.R), _cabi.ptr(self.pi), _cabi.ptr(self.Q)
+        a.t_stride, a.r_stride, a.pi_stride = nrows * A * S, nrows * A, nrows * A
+        a.v_in_stride, a.v_out_stride, a.q_stride = S, S, nrows * A
+        a.B, a.S, a.A = B, S, A
+        a.fold = FOLD_PI if self.pi is not None else FOLD_MAX
+        a.gamma = float(np.float32(gamma))
+        a.resid = _cabi.ptr(self.resid)
+        a.row0, a.nrows = self.row0, nrows
+        self.args = a
+        lib = _cabi.lib()
+        self._fn = lib.colo_backup_f64acc if self.f64 else lib.colo_backup_f32
+        self.sweeps = 0
+
+    @property
+    def values(self):
+        return self.V[self.cur]
+
+    def set_peers(self, peer_ptr_tensors):
+        """row-sharded mode: `peer_ptr_tensors[i]` is a CUDA int64 tensor holding every rank's pointer to its V[i]
+        buffer (i = 0, 1: the two ping-pong buffers); the sweep then also stores its rows into the peers."""
+        self._peers = peer_ptr_tensors
+
+    def sweep(self, n=1, store_q=True):
+        a = self.args
+        a.Q = _cabi.ptr(self.Q) if store_q else None
+        stream = _cabi.current_stream()
+        peers = getattr(self, "_peers", None)
+        for _ in range(n):
+            nxt = 1 - self.cur
+            a.V_in, a.V_out = _cabi.ptr(self.V[self.cur]), _cabi.ptr(self.V[nxt])
+            if peers is not None:
+                a.V_out_peers, a.n_peers = _cabi.ptr(peers[nxt]), int(peers[nxt].numel())
+            _cabi.check(self._fn(C.byref(a), stream), "colo_backup")
+            self.cur = nxt
+            self.sweeps += 1
+
+    def residual(self):
+        """max|dV| per instance accumulated since the last call (device tensor); resets the accumulator."""
+        torch = _torch()
+        r = self.resid.view(torch.float64 if self.f64 else torch.float32).clone()
+        self.resid.zero_()
+        return r

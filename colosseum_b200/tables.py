@@ -161,7 +161,10 @@ class MDPTables:
     # ------------------------------------------------------------------------------------------ derived
     @property
     def ld(self):
-        """dense row stride: S rounded up to a multiple of 32 elements (128-byte lines for fp32)"""
+        """dense row stride in elements.  Rows of up to 1024 states are padded to whole 128-entry chunks (one 128-bit
+        load per lane per chunk, no tail predicates in the step kernel); longer rows to a multiple of 32."""
+        if self.S <= 1024:
+            return (self.S + 127) // 128 * 128
         return (self.S + 31) // 32 * 32
 
     @property

@@ -233,3 +233,48 @@ def test_c2_full_size_properties(bm):
     for t in range(1, 41):
         orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t)
     assert np.array_equal(full.state[:M].cpu().numpy(), state)
+
+
+@pytest.mark.parametrize("S,mode,omode", [(1300, "dense_f32", 0), (1300, "dense_f64", 1), (2500, "dense_f32", 0),
+                                          (129, "dense_f32", 0), (700, "dense_f64", 1), (3, "dense_f32", 0)])
+def test_dense_rows_of_any_length(bm, S, mode, omode):
+    """synthetic dense MDPs (CustomMDP-like): long rows (> 1024 states, generic kernel with early exit), rows that
+    fill 2..8 chunks, a 3-state MDP; sparse rows with zero-probability states that must never be produced"""
+    rs = np.random.RandomState(S)
+    A = 2
+    T = rs.dirichlet(np.ones(S) * 0.02, size=(S, A)).astype(np.float32)
+    T[T < 1e-4] = 0
+    T[0, 0] = 0
+    T[0, 0, S - 1] = 1.0  # deterministic row hitting the last state
+    T[1, 1] = 0
+    T[1, 1, 0] = 1.0  # deterministic row hitting the first state
+    T = (T / T.sum(-1, keepdims=True)).astype(np.float32)
+    tb = MDPTables.from_dense(T, rew_kinds=[("deterministic", (0.5,)), ("beta", (2.0, 3.0))],
+                              rew_cls_sa=rs.randint(2, size=(S, A)), start_idx=np.arange(S), start_prob=np.ones(S) / S)
+    N = 777
+    env = bm.BatchedMDP(tb, N, mode=mode, seed=11)
+    cdf = env.dev.keep["cdf"].cpu().numpy()
+    assert np.array_equal(cdf, orc.build_dense_cdf(T, ld=tb.ld, f64=(omode == 1)))
+    ht = host_tables(tb, omode, cdf)
+    env.reset()
+    state, h, st, obs = orc.env_reset(ht, N, seed=11, t=0)
+    assert np.array_equal(env.state.cpu().numpy(), state)
+    for t in range(1, 13):
+        # uniforms at the edges of [0,1) exercise the clamp to the last positive-probability state
+        un = rs.random_sample(N)
+        un[:5] = [0.0, 1.0 - 2.0 ** -24, 1.0 - 2.0 ** -53 if omode else 1.0 - 2.0 ** -24, 0.5, 2.0 ** -30]
+        if omode == 0:
+            un = un.astype(np.float32)
+        a = rs.randint(A, size=N).astype(np.int32)
+        ts = env.step(a, u_next=un)
+        r, obs, rc, _ = orc.env_step(ht, omode, state, h, st, action=a.copy(), u_next=un, seed=11, t=t)
+        nxt = env.state.cpu().numpy()
+        assert np.array_equal(nxt, state), f"t={t}"
+        assert np.array_equal(ts.reward.cpu().numpy(), r)
+        prev = ts.observation  # noqa: F841
+    # zero-probability states are never produced
+    env2 = bm.BatchedMDP(tb, 4096, mode=mode, seed=5)
+    env2.reset()
+    env2.state.fill_(2)
+    env2.step(np.zeros(4096, np.int32))
+    assert (T[2, 0][env2.state.cpu().numpy()] > 0).all()
