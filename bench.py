@@ -45,10 +45,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(key):
+def ncu_traffic(key, units):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/summarize_ncu.py), scaled to this run's units per launch"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(p):
-        return json.load(open(p)).get(key)
+        e = json.load(open(p)).get(key)
+        if e:
+            return e["dram_bytes_per_unit"] * units
     return None
 
 
@@ -395,7 +399,7 @@ def main():
                                    "gamma=0.99, one synchronous sweep of the whole batch per step, Q stored",
                        "l2": f"batch T = {vi['B'] * 4 * 512 * 4 * 512 / 2**30:.1f} GiB per GPU >> 126 MB L2, no flush"},
             "roofline": {"bound": "hbm", "achieved": per_sweep_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": per_sweep_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("backup_kernel"),
+                         "frac": per_sweep_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("backup_kernel", vi["B"]),
                          "peak_source": peak_src, "kernel": "backup_kernel<float,MAX,VEC,warp>",
                          "algorithmic_bytes_per_launch": per_sweep_bytes},
         }
@@ -415,7 +419,7 @@ def main():
                     "what": "BatchedMDP.step_async from pinned host actions + obs/reward/step_type read back to pinned "
                             "host memory and stream sync, every step"},
             "roofline": {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("env_step_dense_short_kernel"),
+                         "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("env_step_dense_short_kernel", N),
                          "peak_source": peak_src, "kernel": "env_step_dense_short_kernel<float,4,4>",
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "note": "T (1.8 MB) is L2/L1-resident by construction in C2: algorithmic bytes are served "

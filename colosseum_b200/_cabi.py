@@ -53,6 +53,17 @@ class MdpTables(C.Structure):
     ]
 
 
+class EnvBatch(C.Structure):
+    """mirror of `colo_env_batch` (device pointers)"""
+
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_ulonglong), ("env0", C.c_ulonglong),
+        ("state", C.c_void_p), ("h", C.c_void_p), ("step_type", C.c_void_p), ("action", C.c_void_p),
+        ("reward", C.c_void_p), ("obs", C.c_void_p), ("visits_s", C.c_void_p), ("visits_sa", C.c_void_p),
+        ("visits_copies", C.c_int), ("status", C.c_void_p),
+    ]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _ULL = C.c_ulonglong
@@ -83,10 +94,10 @@ PROTOTYPES = {
     "colo_value_norm_f32": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "colo_value_norm_f64acc": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "colo_gaps_f64": (_I, [_P, _P, _P, _LL, _I, _D, _P, _P]),
-    "colo_env_reset": (_I, [C.POINTER(MdpTables), _LL, _P, _ULL, _ULL, _ULL, _P, _P, _P, _P, _P, _P]),
-    "colo_env_step_dense_f32": (_I, [C.POINTER(MdpTables), _LL, _P, _I, _P, _P, _ULL, _ULL, _ULL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "colo_env_step_dense_f64": (_I, [C.POINTER(MdpTables), _LL, _P, _I, _P, _P, _ULL, _ULL, _ULL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "colo_env_step_succ": (_I, [C.POINTER(MdpTables), _LL, _P, _I, _P, _P, _ULL, _ULL, _ULL, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "colo_env_reset": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _P, _ULL, _P]),
+    "colo_env_step_dense_f32": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
+    "colo_env_step_dense_f64": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
+    "colo_env_step_succ": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
     "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "colo_synth_dense_rows": (_I, [_P, _P, _I, _I, _I, _I, _ULL, _P]),
 }

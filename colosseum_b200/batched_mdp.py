@@ -77,6 +77,8 @@ class DeviceTables:
 
 
 class BatchedMDP:
+    VISIT_COPIES = 16  # privatised visitation counters (power of two), summed when read
+
     def __init__(self, tables: MDPTables, n_envs: int, mode: str = "dense_f32", seed: int = 0,
                  track_visits: bool = True, env_offset: int = 0):
         import torch
@@ -105,8 +107,10 @@ class BatchedMDP:
         self.step_type.fill_(_cabi.STEP_LAST)
         self.action = torch.zeros(N, dtype=torch.int32, device="cuda")
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
-        self.visits_s = torch.zeros(tables.S, dtype=torch.int64, device="cuda") if track_visits else None
-        self.visits_sa = torch.zeros((tables.S, tables.A), dtype=torch.int64, device="cuda") if track_visits else None
+        vc = self.VISIT_COPIES
+        self._visits_s = torch.zeros((vc, tables.S), dtype=torch.int64, device="cuda") if track_visits else None
+        self._visits_sa = (torch.zeros((vc, tables.S, tables.A), dtype=torch.int64, device="cuda")
+                           if track_visits else None)
         self.t = 0  # launch counter: the Philox stream position
         self._was_reset = False
         # static launch arguments, resolved once (a step is then one ctypes call)
@@ -115,8 +119,15 @@ class BatchedMDP:
                          "dense_f64": (lib.colo_env_step_dense_f64, torch.float64),
                          "succ": (lib.colo_env_step_succ, torch.float64)}[mode]
         self._tb_ref = C.byref(self.dev.c)
-        self._ptrs = {k: _cabi.ptr(getattr(self, k)) for k in
-                      ("action", "state", "h", "step_type", "reward", "obs", "visits_s", "visits_sa", "status")}
+        b = _cabi.EnvBatch()
+        b.N, b.seed, b.env0 = N, self.seed, self.env_offset
+        b.state, b.h, b.step_type = _cabi.ptr(self.state), _cabi.ptr(self.h), _cabi.ptr(self.step_type)
+        b.action, b.reward, b.obs = _cabi.ptr(self.action), _cabi.ptr(self.reward), _cabi.ptr(self.obs)
+        b.visits_s, b.visits_sa, b.visits_copies = _cabi.ptr(self._visits_s), _cabi.ptr(self._visits_sa), vc
+        b.status = _cabi.ptr(self.status)
+        self._batch = b
+        self._batch_ref = C.byref(b)
+        self._own_action_ptr = b.action
 
     # -- reference attribute surface (base.py:463-503, 1233-1252)
     @property
@@ -154,10 +165,7 @@ class BatchedMDP:
         """BaseMDP.reset (base.py:1268-1277) for every env."""
         torch = self.torch
         u = self._u(u_next, torch.float64)
-        rc = _cabi.lib().colo_env_reset(
-            C.byref(self.dev.c), self.n_envs, _cabi.ptr(u), self.seed, self.t, self.env_offset, _cabi.ptr(self.state),
-            _cabi.ptr(self.h), _cabi.ptr(self.step_type), _cabi.ptr(self.obs), _cabi.ptr(self.visits_s),
-            _cabi.current_stream())
+        rc = _cabi.lib().colo_env_reset(self._tb_ref, self._batch_ref, _cabi.ptr(u), self.t, _cabi.current_stream())
         _cabi.check(rc, "colo_env_reset")
         self.t += 1
         self._was_reset = True
@@ -170,7 +178,7 @@ class BatchedMDP:
         (BaseMDP.random_step, base.py:1341-1355) and records them in self.action."""
         torch = self.torch
         random_actions = action is None
-        act_ptr = self._ptrs["action"]
+        act_ptr = self._own_action_ptr
         if not random_actions:
             if isinstance(action, torch.Tensor):
                 if action.is_cuda and action.dtype == torch.int32 and action.is_contiguous():
@@ -183,10 +191,9 @@ class BatchedMDP:
         fn, udt = self._step_fn
         un = None if u_next is None else self._u(u_next, udt)
         ur = None if u_reward is None else self._u(u_reward, torch.float32)
-        p = self._ptrs
-        rc = fn(self._tb_ref, self.n_envs, act_ptr, int(random_actions), _cabi.ptr(un), _cabi.ptr(ur), self.seed,
-                self.t, self.env_offset, int(bool(auto_reset)), p["state"], p["h"], p["step_type"], p["reward"],
-                p["obs"], p["visits_s"], p["visits_sa"], p["status"], torch.cuda.current_stream().cuda_stream)
+        self._batch.action = act_ptr
+        rc = fn(self._tb_ref, self._batch_ref, int(random_actions), _cabi.ptr(un), _cabi.ptr(ur), self.t,
+                int(bool(auto_reset)), torch.cuda.current_stream().cuda_stream)
         if rc != 0:
             _cabi.check(rc, "colo_env_step")
         self.t += 1
@@ -223,12 +230,22 @@ class BatchedMDP:
         """BaseMDP.random_steps (base.py:1319-1339)."""
         return [self.random_step(auto_reset) for _ in range(n)]
 
+    @property
+    def visits_s(self):
+        """state visitation counts i64[S] (sum of the privatised copies)"""
+        return None if self._visits_s is None else self._visits_s.sum(0)
+
+    @property
+    def visits_sa(self):
+        """state-action visitation counts i64[S,A], counted on the NEXT node as in the reference (base.py:1302-1303)"""
+        return None if self._visits_sa is None else self._visits_sa.sum(0)
+
     def get_visitation_counts(self, state_only=True):
         """base.py:1357-1373, as arrays indexed by state index (and action)."""
         return self.visits_s if state_only else self.visits_sa
 
     def reset_visitation_counts(self):
         """base.py:1375-1382"""
-        if self.visits_s is not None:
-            self.visits_s.zero_()
-            self.visits_sa.zero_()
+        if self._visits_s is not None:
+            self._visits_s.zero_()
+            self._visits_sa.zero_()

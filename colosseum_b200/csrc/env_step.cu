@@ -11,6 +11,8 @@
 // env i); the search over the dense CDF row T[s,a,:] is warp-cooperative: the row is read with 128-bit coalesced
 // loads, all issued before any is consumed, and because the row is monotone the bisect position is simply the
 // COUNT of entries <= x, i.e. one integer warp reduction, no branches and no early exit.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace colo {
@@ -32,6 +34,8 @@ struct StepIO {
   int* obs;
   unsigned long long* visits_s;
   unsigned long long* visits_sa;
+  int visits_mask;       // copies - 1
+  long long n_s, n_sa;   // S, S*A: stride between privatised counter copies
   int* status;
 };
 
@@ -145,8 +149,9 @@ __device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tabl
       io.obs[e] = nxt;
     }
   }
-  if (io.visits_s) aggregated_inc(io.visits_s, nxt, stepping || resetting);
-  if (io.visits_sa) aggregated_inc(io.visits_sa, (long long)nxt * tb.A + in.a, stepping);
+  const long long copy = blockIdx.x & io.visits_mask;  // privatised counters: spread same-state atomics over L2
+  if (io.visits_s) aggregated_inc(io.visits_s + copy * io.n_s, nxt, stepping || resetting);
+  if (io.visits_sa) aggregated_inc(io.visits_sa + copy * io.n_sa, (long long)nxt * tb.A + in.a, stepping);
 }
 
 // Position of x in one monotone dense row, warp-cooperative.  The row is read as quads (4 consecutive entries per
@@ -247,20 +252,22 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
 // ballot + popc per chunk.  The within-quad step is deferred to the epilogue, where lane i finishes env i on its
 // own (one 16-byte gather of quad G, which the warp has just pulled into L1), i.e. it is vectorised over the 32
 // envs of the tile instead of costing shuffles and selects inside the per-env loop.
-template <typename TC, int NCH, int U>
+template <typename TC, int NCH, int U, int TILE>
 __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(const colo_mdp_tables tb, const StepIO io) {
+  // TILE envs per warp (lanes >= TILE idle in the per-lane phases): smaller tiles = more warps in flight when the
+  // batch alone cannot fill the machine (65,536 envs / 32 = 14 warps per SM)
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * kStepThreads + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * kStepThreads) >> 5;
-  const long long n_tiles = (io.N + 31) >> 5;
+  const long long n_tiles = (io.N + TILE - 1) / TILE;
   const int S = tb.S, A = tb.A;
   constexpr int ld = 128 * NCH;
   const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
   constexpr bool F32U = sizeof(TC) == 4;
 
   for (long long tile = warp_global; tile < n_tiles; tile += n_warps) {
-    const long long e = tile * 32 + lane;
-    const bool valid = e < io.N;
+    const long long e = tile * TILE + lane;
+    const bool valid = lane < TILE && e < io.N;
     EnvIn in;
     in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<F32U>(io, tb, e);
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
     const TC u_l = F32U ? (TC)in.un32 : (TC)in.un64;
 
     int my_G = 0;
-    for (int i0 = 0; i0 < 32; i0 += U) {
+    for (int i0 = 0; i0 < TILE; i0 += U) {
       Quad<TC> q[U][NCH];
       TC x[U];
 #pragma unroll
@@ -349,32 +356,29 @@ __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_
   }
 }
 
-__global__ void __launch_bounds__(kStepThreads) env_reset_kernel(const colo_mdp_tables tb, long long N,
-                                                                 const double* u_next, unsigned long long seed,
-                                                                 unsigned long long t, unsigned long long env0,
-                                                                 int* state, int* h,
-                                                                 unsigned char* step_type, int* obs,
-                                                                 unsigned long long* visits_s) {
+__global__ void __launch_bounds__(kStepThreads) env_reset_kernel(const colo_mdp_tables tb, const StepIO io) {
   const long long n_thr = (long long)gridDim.x * kStepThreads;
-  const long long n_pad = (N + 31) & ~31LL;
+  const long long n_pad = (io.N + 31) & ~31LL;
+  const double* u_next = reinterpret_cast<const double*>(io.u_next);
   for (long long e = (long long)blockIdx.x * kStepThreads + threadIdx.x; e < n_pad; e += n_thr) {
-    const bool valid = e < N;
+    const bool valid = e < io.N;
     int s0 = 0;
     if (valid) {
       double u;
       if (u_next)
         u = u_next[e];
       else {
-        Philox4 w = philox4x32_10(seed, env0 + (uint64_t)e, t);
+        Philox4 w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, io.t);
         u = u53(w.w[0], w.w[1]);
       }
       s0 = sample_start(tb, u);
-      state[e] = s0;
-      h[e] = 0;
-      step_type[e] = COLO_STEP_FIRST;
-      obs[e] = s0;
+      io.state[e] = s0;
+      io.h[e] = 0;
+      io.step_type[e] = COLO_STEP_FIRST;
+      io.obs[e] = s0;
     }
-    if (visits_s) aggregated_inc(visits_s, s0, valid);
+    const long long copy = blockIdx.x & io.visits_mask;
+    if (io.visits_s) aggregated_inc(io.visits_s + copy * io.n_s, s0, valid);
   }
 }
 
@@ -394,7 +398,7 @@ __global__ void build_dense_cdf_kernel(const float* __restrict__ T, int S, int A
 
 static int grid_for(long long work_items_per_thread_block, long long total) {
   long long blocks = (total + work_items_per_thread_block - 1) / work_items_per_thread_block;
-  long long cap = (long long)sm_count() * 16;
+  long long cap = (long long)sm_count() * 32;  // 64-thread CTAs: up to 32 resident per SM
   if (blocks < 1) blocks = 1;
   return (int)(blocks < cap ? blocks : cap);
 }
@@ -413,15 +417,25 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
   if (r != COLO_OK) return r;
   COLO_ARG_CHECK(tb->cdf && tb->ld >= tb->S && tb->ld % 4 == 0, "dense cdf with ld % 4 == 0 is required");
   COLO_ARG_CHECK((uintptr_t)tb->cdf % 16 == 0, "cdf must be 16-byte aligned");
-  COLO_ARG_CHECK(io.state && io.h && io.step_type && io.reward && io.obs && io.action, "env buffers");
+  COLO_ARG_CHECK(io.reward && io.action, "env buffers");
   if (io.N == 0) return COLO_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = grid_for(kStepThreads / 32, (io.N + 31) / 32);
   const int ld = tb->ld;
   const bool short_rows = ld % 128 == 0 && ld <= 1024 && (long long)tb->S * tb->A * ld < (1LL << 31);
   if (short_rows) {
-#define COLO_SHORT(NCH, U) \
-  case NCH: env_step_dense_short_kernel<TC, NCH, U><<<grid, kStepThreads, 0, st>>>(*tb, io); break
+    // envs per warp: 32 when the batch alone fills the machine, fewer (more warps in flight) otherwise
+    static const int forced = getenv("COLO_STEP_TILE") ? atoi(getenv("COLO_STEP_TILE")) : 0;
+    const long long warps32 = (io.N + 31) / 32;
+    // measured on B200 at N=65,536 (14 warps/SM with 32-env tiles): 32 -> 14.1 us, 16 -> 14.4 us, 8 -> 16.6 us
+    int tile = warps32 >= (long long)sm_count() * 8 ? 32 : (warps32 >= (long long)sm_count() * 4 ? 16 : 8);
+    if (forced == 8 || forced == 16 || forced == 32) tile = forced;
+    const int grid = grid_for(kStepThreads / 32, (io.N + tile - 1) / tile);
+#define COLO_SHORT(NCH, U)                                                                               \
+  case NCH:                                                                                              \
+    if (tile == 32) env_step_dense_short_kernel<TC, NCH, U, 32><<<grid, kStepThreads, 0, st>>>(*tb, io);  \
+    else if (tile == 16) env_step_dense_short_kernel<TC, NCH, U, 16><<<grid, kStepThreads, 0, st>>>(*tb, io); \
+    else env_step_dense_short_kernel<TC, NCH, U, 8><<<grid, kStepThreads, 0, st>>>(*tb, io);             \
+    break
     switch (ld / 128) {
       COLO_SHORT(1, 4);
       COLO_SHORT(2, 4);
@@ -434,6 +448,7 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
     }
 #undef COLO_SHORT
   } else {
+    const int grid = grid_for(kStepThreads / 32, (io.N + 31) / 32);
     env_step_dense_kernel<TC, 8><<<grid, kStepThreads, 0, st>>>(*tb, io);
   }
   return check_launch("env_step_dense_kernel");
@@ -441,55 +456,69 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
 
 }  // namespace colo
 
+static int make_io(const colo_mdp_tables* tb, const colo_env_batch* b, int random_actions, const void* u_next,
+                   const float* u_rew, unsigned long long t, int auto_reset, colo::StepIO* io) {
+  COLO_ARG_CHECK(b != nullptr, "batch is NULL");
+  COLO_ARG_CHECK(b->N >= 0 && b->state && b->h && b->step_type && b->obs, "env buffers");
+  const int copies = b->visits_copies <= 0 ? 1 : b->visits_copies;
+  COLO_ARG_CHECK((copies & (copies - 1)) == 0, "visits_copies must be a power of two");
+  io->N = b->N; io->action = b->action; io->random_actions = random_actions; io->u_next = u_next; io->u_rew = u_rew;
+  io->seed = b->seed; io->t = t; io->env0 = b->env0; io->auto_reset = auto_reset; io->state = b->state; io->h = b->h;
+  io->step_type = b->step_type; io->reward = b->reward; io->obs = b->obs; io->visits_s = b->visits_s;
+  io->visits_sa = b->visits_sa; io->visits_mask = copies - 1; io->n_s = tb->S; io->n_sa = (long long)tb->S * tb->A;
+  io->status = b->status;
+  return COLO_OK;
+}
+
 extern "C" {
 
-int colo_env_reset(const colo_mdp_tables* tb, long long N, const double* u_next, unsigned long long seed,
-                   unsigned long long t, unsigned long long env0, int* state, int* h, unsigned char* step_type, int* obs,
-                   unsigned long long* visits_s, void* stream) {
+int colo_env_reset(const colo_mdp_tables* tb, const colo_env_batch* batch, const double* u_next,
+                   unsigned long long t, void* stream) {
   int r = colo::check_tables_common(tb);
   if (r != COLO_OK) return r;
-  COLO_ARG_CHECK(state && h && step_type && obs, "env buffers");
-  if (N == 0) return COLO_OK;
-  const int grid = colo::grid_for(colo::kStepThreads, N);
-  colo::env_reset_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, N, u_next, seed, t, env0, state, h,
-                                                                              step_type, obs, visits_s);
+  colo::StepIO io;
+  r = make_io(tb, batch, 0, u_next, nullptr, t, 0, &io);
+  if (r != COLO_OK) return r;
+  if (io.N == 0) return COLO_OK;
+  const int grid = colo::grid_for(colo::kStepThreads, io.N);
+  colo::env_reset_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
   return colo::check_launch("env_reset_kernel");
 }
 
-#define COLO_STEP_IO()                                                                                          \
-  colo::StepIO io;                                                                                              \
-  io.N = N; io.action = action; io.random_actions = random_actions; io.u_next = u_next; io.u_rew = u_rew;       \
-  io.seed = seed; io.t = t; io.env0 = env0; io.auto_reset = auto_reset; io.state = state; io.h = h; io.step_type = step_type;   \
-  io.reward = reward; io.obs = obs; io.visits_s = visits_s; io.visits_sa = visits_sa; io.status = status;
-
-int colo_env_step_dense_f32(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
-                            const float* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
-                            unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
-                            unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream) {
-  COLO_STEP_IO();
+int colo_env_step_dense_f32(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
+                            const float* u_next, const float* u_rew, unsigned long long t, int auto_reset,
+                            void* stream) {
+  int r = colo::check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  colo::StepIO io;
+  r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
+  if (r != COLO_OK) return r;
   return colo::launch_dense<float>(tb, io, stream);
 }
 
-int colo_env_step_dense_f64(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
-                            const double* u_next, const float* u_rew, unsigned long long seed,
-                            unsigned long long t, unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type,
-                            float* reward, int* obs, unsigned long long* visits_s, unsigned long long* visits_sa,
-                            int* status, void* stream) {
-  COLO_STEP_IO();
+int colo_env_step_dense_f64(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
+                            const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
+                            void* stream) {
+  int r = colo::check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  colo::StepIO io;
+  r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
+  if (r != COLO_OK) return r;
   return colo::launch_dense<double>(tb, io, stream);
 }
 
-int colo_env_step_succ(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
-                       const double* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
-                       unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
-                       unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream) {
-  COLO_STEP_IO();
+int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
+                       const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
+                       void* stream) {
   int r = colo::check_tables_common(tb);
   if (r != COLO_OK) return r;
+  colo::StepIO io;
+  r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
+  if (r != COLO_OK) return r;
   COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
-  COLO_ARG_CHECK(io.state && io.h && io.step_type && io.reward && io.obs && io.action, "env buffers");
-  if (N == 0) return COLO_OK;
-  const int grid = colo::grid_for(colo::kStepThreads, N);
+  COLO_ARG_CHECK(io.reward && io.action, "env buffers");
+  if (io.N == 0) return COLO_OK;
+  const int grid = colo::grid_for(colo::kStepThreads, io.N);
   colo::env_step_succ_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
   return colo::check_launch("env_step_succ_kernel");
 }

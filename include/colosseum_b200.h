@@ -207,37 +207,53 @@ typedef struct {
 } colo_mdp_tables;
 
 /*
- * Batched env state: state i32[N], h i32[N], step_type u8[N] (the type of the LAST emitted TimeStep).
- * Uniforms: u_next (float for the f32 dense kernel, double otherwise) and u_rew float, or NULL to draw them from
- * the built-in Philox4x32-10 stream keyed by (seed; env0 + env index, step counter t) -- env0 is the global index
- * of this call's first env, so a batch sharded over GPUs draws exactly the numbers of the unsharded batch.  action i32[N]: read, or -- when
- * random_actions != 0 -- written with the uniformly random action taken (BaseMDP.random_step, base.py:1341-1355).
- *
+ * One batch of N parallel episodes (all device pointers): state i32[N], h i32[N], step_type u8[N] (the type of the
+ * LAST emitted TimeStep; initialise to COLO_STEP_LAST so that stepping before reset is flagged), action i32[N]
+ * (read, or -- with random_actions -- written with the uniformly random action taken, BaseMDP.random_step,
+ * base.py:1341-1355), outputs reward f32[N] (NaN where the reference has None) and obs i32[N].
+ * Visitation counters (u64, or NULL): `visits_copies` (a power of two >= 1) privatised copies laid out as
+ * visits_s[copy][S] and visits_sa[copy][S*A]; a block adds to copy (blockIdx & (copies-1)) so that 65,536 envs
+ * sitting on a handful of states do not serialise on a handful of L2 atomics -- the count is the sum over copies.
+ * status: device int (may be NULL), set to COLO_NEEDS_RESET if an env needed a reset without auto_reset.
+ * Philox: when u_next / u_rew are NULL (or random_actions is set) the numbers come from Philox4x32-10 with
+ * counter (env0 + i, t) and key seed -- env0 is the global index of the batch's first env, so a batch sharded
+ * over GPUs draws exactly the numbers of the unsharded batch; t is the caller's step counter.
+ */
+typedef struct {
+  long long N;
+  unsigned long long seed, env0;
+  int* state;
+  int* h;
+  unsigned char* step_type;
+  int* action;
+  float* reward;
+  int* obs;
+  unsigned long long* visits_s;
+  unsigned long long* visits_sa;
+  int visits_copies;
+  int* status;
+} colo_env_batch;
+
+/*
  * colo_env_reset  -- BaseMDP.reset (base.py:1268-1277): h=0, state ~ start distribution, step_type=FIRST,
- *                    visits_s[state]++.
+ *                    obs=state, visits_s[state]++.  u_next: double[N] or NULL (Philox).
  * colo_env_step_* -- BaseMDP.step (base.py:1279-1317).  Per env: if step_type==LAST: auto_reset ? reset path
- *                    (reward/obs as reset: reward=NaN for None) : flag COLO_NEEDS_RESET; else h++, sample next,
+ *                    (reward NaN for None, the action is ignored) : flag COLO_NEEDS_RESET; else h++, sample next,
  *                    visits_s[next]++, visits_sa[next,a]++ (sic: counted on the NEXT node), reward, and
  *                    LAST/obs=-1 if episodic and h>=H else MID/obs=next.
- * status: device int (may be NULL), set to COLO_NEEDS_RESET if any env needed a reset without auto_reset.
- * visits_s / visits_sa: u64 counters or NULL.
+ *                    u_next: float[N] for _dense_f32, double[N] otherwise, or NULL; u_rew: float[N] or NULL.
  */
-int colo_env_reset(const colo_mdp_tables* tb, long long N, const double* u_next, unsigned long long seed,
-                   unsigned long long t, unsigned long long env0, int* state, int* h, unsigned char* step_type, int* obs,
-                   unsigned long long* visits_s, void* stream);
-int colo_env_step_dense_f32(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
-                            const float* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
-                            unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
-                            unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream);
-int colo_env_step_dense_f64(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
-                            const double* u_next, const float* u_rew, unsigned long long seed,
-                            unsigned long long t, unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type,
-                            float* reward, int* obs, unsigned long long* visits_s, unsigned long long* visits_sa,
-                            int* status, void* stream);
-int colo_env_step_succ(const colo_mdp_tables* tb, long long N, int* action, int random_actions,
-                       const double* u_next, const float* u_rew, unsigned long long seed, unsigned long long t,
-                       unsigned long long env0, int auto_reset, int* state, int* h, unsigned char* step_type, float* reward, int* obs,
-                       unsigned long long* visits_s, unsigned long long* visits_sa, int* status, void* stream);
+int colo_env_reset(const colo_mdp_tables* tb, const colo_env_batch* batch, const double* u_next,
+                   unsigned long long t, void* stream);
+int colo_env_step_dense_f32(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
+                            const float* u_next, const float* u_rew, unsigned long long t, int auto_reset,
+                            void* stream);
+int colo_env_step_dense_f64(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
+                            const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
+                            void* stream);
+int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
+                       const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
+                       void* stream);
 
 /* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
  * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */

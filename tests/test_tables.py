@@ -65,3 +65,33 @@ def test_from_mdp_matches_golden_recording():
     for f in ("succ_idx", "succ_cum", "succ_len", "rew_cls_succ", "T", "rew_cls_sas", "start_idx", "start_cum", "rew_q"):
         assert np.array_equal(getattr(tb, f), getattr(ref, f)), f
     assert tb.rew_kinds == ref.rew_kinds and (tb.S, tb.A, tb.H) == (ref.S, ref.A, ref.H)
+
+
+@pytest.mark.reference
+def test_patch_rebinds_reference_names():
+    """colosseum_b200.patch.install() replaces every by-name binding of the hot-path entry points inside the imported
+    reference package, and uninstall() restores them (mechanics only: no GPU call is made here)"""
+    from oracle.reference_import import import_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    import_reference()
+    import colosseum.mdp  # noqa: F401
+    import colosseum.hardness.measures.diameter as ref_diam
+    import colosseum.mdp.base as ref_base
+    import colosseum.mdp.base_finite as ref_fin
+    import colosseum_b200.dynamic_programming as dp
+    import colosseum_b200.hardness as hd
+    import colosseum_b200.patch as patch
+
+    orig = ref_base.get_diameter
+    n = patch.install()
+    try:
+        assert n >= 12
+        assert ref_base.get_diameter is hd.get_diameter and ref_base.calculate_norm_discounted is hd.calculate_norm_discounted
+        assert ref_fin.episodic_value_iteration is dp.episodic_value_iteration
+        assert ref_fin.discounted_value_iteration is dp.discounted_value_iteration
+        assert ref_diam.discounted_value_iteration is dp.discounted_value_iteration
+    finally:
+        assert patch.uninstall() == n
+    assert ref_base.get_diameter is orig
