@@ -31,7 +31,7 @@ class BackupArgs(C.Structure):
         ("gamma", C.c_double), ("r_const", C.c_double),
         ("resid", C.c_void_p), ("resid_vs_out", C.c_int),
         ("active", C.c_void_p),
-        ("max_abs", C.c_double), ("overflow_flag", C.c_void_p),
+        ("max_abs", C.c_double), ("overflow_signed", C.c_int), ("overflow_flag", C.c_void_p),
         ("row0", C.c_int), ("nrows", C.c_int),
         ("pin_index", C.c_void_p), ("pin_value", C.c_double),
         ("exclude_index", C.c_void_p), ("exclude_value", C.c_double),
@@ -50,6 +50,21 @@ class MdpTables(C.Structure):
         ("rew_q", C.c_void_p), ("n_cls", C.c_int), ("nq", C.c_int),
         ("rmin", C.c_float), ("rmax", C.c_float),
         ("start_cum", C.c_void_p), ("start_idx", C.c_void_p), ("n_start", C.c_int),
+    ]
+
+
+class ResidentArgs(C.Structure):
+    """mirror of `colo_resident_args`"""
+
+    _fields_ = [
+        ("T", C.c_void_p), ("R", C.c_void_p), ("pi", C.c_void_p), ("V", C.c_void_p), ("Q", C.c_void_p),
+        ("t_stride", C.c_longlong), ("r_stride", C.c_longlong),
+        ("B", C.c_int), ("S", C.c_int), ("A", C.c_int), ("NV", C.c_int), ("fold", C.c_int),
+        ("gamma", C.c_double), ("r_const", C.c_double), ("eps", C.c_double),
+        ("max_abs", C.c_double), ("overflow_signed", C.c_int),
+        ("max_iter", C.c_longlong), ("episodic_H", C.c_int),
+        ("pin_index", C.c_void_p), ("pin_value", C.c_double),
+        ("iters_out", C.c_void_p), ("status_out", C.c_void_p),
     ]
 
 
@@ -79,6 +94,9 @@ PROTOTYPES = {
     "colo_reset_launch_count": (None, []),
     "colo_backup_f32": (_I, [C.POINTER(BackupArgs), _P]),
     "colo_backup_f64acc": (_I, [C.POINTER(BackupArgs), _P]),
+    "colo_resident_fits": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int)]),
+    "colo_resident_solve_f32": (_I, [C.POINTER(ResidentArgs), _P]),
+    "colo_resident_solve_f64acc": (_I, [C.POINTER(ResidentArgs), _P]),
     "colo_solve_work_bytes": (C.c_size_t, [_LL, _LL, _I]),
     "colo_solve_discounted_f32": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _LL, _I, _P, _P, _P, _P, _P]),
     "colo_solve_discounted_f64acc": (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _LL, _I, _P, _P, _P, _P, _P]),

@@ -17,6 +17,8 @@
 
 #include "common.cuh"
 
+extern "C" size_t colo_diameter_continuous_work_bytes(int K, int S, int f64);
+
 namespace colo {
 
 constexpr int kThreads = 256;
@@ -199,7 +201,9 @@ __global__ void __launch_bounds__(kThreads) backup_kernel(const colo_backup_args
         const TV d = fabs(folded - old);
         if (d > (TV)0) atomic_max_nonneg(reinterpret_cast<resid_t*>(p.resid) + b, d);
       }
-      if (p.max_abs > 0.0 && fabs((double)folded) > p.max_abs && p.overflow_flag) *p.overflow_flag = 1;
+      if (p.max_abs > 0.0 && p.overflow_flag &&
+          (p.overflow_signed ? (double)folded : fabs((double)folded)) > p.max_abs)
+        *p.overflow_flag = 1;
     }
   }
 }
@@ -479,6 +483,28 @@ int solve_discounted(const float* T, const float* R, const float* pi, int B, int
   COLO_ARG_CHECK(T && R && V && work, "T, R, V, work are required");
   cudaStream_t st = (cudaStream_t)stream;
   SolveWork w = carve<TV>(work, B, S);
+  if (resident_enabled() && resident_fits_any(S, A, 1, sizeof(TV) == 8, nullptr)) {
+    // small MDPs: the whole solve is ONE launch of the on-chip resident solver (resident.cu)
+    colo_resident_args ra = {};
+    ra.T = T; ra.R = R; ra.pi = pi; ra.V = V; ra.Q = Q;
+    ra.t_stride = (long long)S * A * S; ra.r_stride = (long long)S * A;
+    ra.B = B; ra.S = S; ra.A = A; ra.NV = 1; ra.fold = fold;
+    ra.gamma = gamma; ra.eps = eps; ra.max_abs = max_abs; ra.max_iter = max_iter;
+    ra.iters_out = w.iters; ra.status_out = (int*)w.resid;
+    int r = resident_solve_any(&ra, sizeof(TV) == 8, stream);
+    if (r != COLO_OK) return r;
+    std::vector<int> h_status((size_t)B);
+    COLO_CUDA_TRY(cudaMemcpyAsync(h_status.data(), w.resid, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (iters_out_host)
+      COLO_CUDA_TRY(cudaMemcpyAsync(iters_out_host, w.iters, (size_t)B * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    COLO_CUDA_TRY(cudaStreamSynchronize(st));
+    int rc = COLO_OK;
+    for (int b = 0; b < B; ++b) {
+      if (h_status[b] == COLO_OVERFLOW) return COLO_OVERFLOW;
+      if (h_status[b] == COLO_MAX_ITER) rc = COLO_MAX_ITER;
+    }
+    return rc;
+  }
   colo_backup_args a = {};
   a.T = T; a.R = R; a.pi = pi; a.Q = Q;
   a.B = B; a.S = S; a.A = A; a.fold = fold; a.gamma = gamma;
@@ -509,12 +535,35 @@ int episodic(const float* T, const float* R, const float* pi, int B, int S, int 
   // rows H are zero (finite_horizon.py:17-18); cudaMemset2D clears the last layer of every instance
   COLO_CUDA_TRY(cudaMemset2DAsync(V + (size_t)H * S, vs * sizeof(TV), 0, (size_t)S * sizeof(TV), B, st));
   COLO_CUDA_TRY(cudaMemset2DAsync(Q + (size_t)H * S * A, qs * sizeof(TV), 0, (size_t)S * A * sizeof(TV), B, st));
+  if (H > 0 && resident_enabled() && resident_fits_any(S, A, 1, sizeof(TV) == 8, nullptr)) {
+    // small MDPs: all H layers in one launch, T resident in shared memory
+    int* status = nullptr;
+    COLO_CUDA_TRY(cudaMallocAsync(&status, (size_t)B * sizeof(int), st));
+    colo_resident_args ra = {};
+    ra.T = T; ra.R = R; ra.pi = pi; ra.V = V; ra.Q = Q;
+    ra.t_stride = (long long)S * A * S; ra.r_stride = (long long)S * A;
+    ra.B = B; ra.S = S; ra.A = A; ra.NV = 1; ra.fold = fold; ra.gamma = 1.0;
+    ra.max_abs = fold == COLO_FOLD_MAX ? max_value : 0.0; ra.overflow_signed = 1;
+    ra.max_iter = H; ra.episodic_H = H; ra.status_out = status;
+    int r = resident_solve_any(&ra, sizeof(TV) == 8, stream);
+    int rc = COLO_OK;
+    if (r == COLO_OK && max_value > 0) {
+      std::vector<int> h_status((size_t)B);
+      COLO_CUDA_TRY(cudaMemcpyAsync(h_status.data(), status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+      COLO_CUDA_TRY(cudaStreamSynchronize(st));
+      for (int b = 0; b < B; ++b)
+        if (h_status[b] == COLO_OVERFLOW) rc = COLO_OVERFLOW;
+    }
+    COLO_CUDA_TRY(cudaFreeAsync(status, st));
+    if (flag) COLO_CUDA_TRY(cudaFreeAsync(flag, st));
+    return r != COLO_OK ? r : rc;
+  }
   colo_backup_args a = {};
   a.T = T; a.R = R;
   a.B = B; a.S = S; a.A = A; a.fold = fold; a.gamma = 1.0;
   a.t_stride = (long long)S * A * S; a.r_stride = (long long)S * A; a.pi_stride = (long long)H * S * A;
   a.v_in_stride = vs; a.v_out_stride = vs; a.q_stride = qs;
-  a.max_abs = fold == COLO_FOLD_MAX ? max_value : 0.0; a.overflow_flag = flag;
+  a.max_abs = fold == COLO_FOLD_MAX ? max_value : 0.0; a.overflow_signed = 1; a.overflow_flag = flag;
   a.row0 = 0; a.nrows = S;
   for (int h = H - 1; h >= 0; --h) {
     a.V_in = V + (size_t)(h + 1) * S;
@@ -544,6 +593,54 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
   char* rest = (char*)work + align_up((size_t)K * S * sizeof(TV), 256);
   SolveWork w = carve<TV>(rest, K, S);
   TV* d_out = (TV*)(rest + solve_work_bytes<TV>(K, S));
+  if (resident_enabled() && resident_fits_any(S, A, 4, sizeof(TV) == 8, nullptr)) {
+    // T fits a cluster's shared memory: tiles of 4 targets, each tile iterated to convergence on chip by its own
+    // cluster in ONE launch (every T quad read from shared memory serves 4 targets)
+    const int K4 = (K + 3) & ~3, tiles = K4 / 4;
+    // carve: E4 [K4][S] | targets4 [K4] | status [tiles] | iters [K4]   (fits: the work buffer holds 2*K*S + extras)
+    char* q = (char*)work;
+    TV* E4 = (TV*)q;
+    q += align_up((size_t)K4 * S * sizeof(TV), 256);
+    int* tg4 = (int*)q;
+    q += align_up((size_t)K4 * sizeof(int), 256);
+    int* status = (int*)q;
+    q += align_up((size_t)tiles * sizeof(int), 256);
+    long long* iters = (long long*)q;
+    q += align_up((size_t)K4 * sizeof(long long), 256);
+    TV* res_out = (TV*)q;
+    COLO_ARG_CHECK((size_t)(q + 256 - (char*)work) <= colo_diameter_continuous_work_bytes(K, S, sizeof(TV) == 8),
+                   "work buffer too small");
+    COLO_CUDA_TRY(cudaMemcpyAsync(tg4, targets, (size_t)K * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    for (int k = K; k < K4; ++k)  // pad the last tile with copies of the last target
+      COLO_CUDA_TRY(cudaMemcpyAsync(tg4 + k, targets + (K - 1), sizeof(int), cudaMemcpyDeviceToDevice, st));
+    colo_resident_args ra = {};
+    ra.T = T; ra.V = E4; ra.t_stride = 0; ra.r_stride = 0;
+    ra.B = tiles; ra.S = S; ra.A = A; ra.NV = 4; ra.fold = COLO_FOLD_MIN;
+    ra.gamma = 1.0; ra.r_const = 1.0; ra.eps = eps; ra.max_abs = max_value; ra.max_iter = max_iter;
+    ra.pin_index = tg4; ra.pin_value = 0.0; ra.iters_out = iters; ra.status_out = status;
+    int r = resident_solve_any(&ra, sizeof(TV) == 8, stream);
+    if (r != COLO_OK) return r;
+    max_reduce_kernel<TV><<<1, 1024, 0, st>>>(E4, (long long)K * S, res_out, 0);
+    r = check_launch("max_reduce_kernel");
+    if (r != COLO_OK) return r;
+    std::vector<int> h_status((size_t)tiles);
+    std::vector<long long> h_iters((size_t)K4);
+    TV h = 0;
+    COLO_CUDA_TRY(cudaMemcpyAsync(h_status.data(), status, (size_t)tiles * sizeof(int), cudaMemcpyDeviceToHost, st));
+    COLO_CUDA_TRY(cudaMemcpyAsync(h_iters.data(), iters, (size_t)K4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    COLO_CUDA_TRY(cudaMemcpyAsync(&h, res_out, sizeof(TV), cudaMemcpyDeviceToHost, st));
+    COLO_CUDA_TRY(cudaStreamSynchronize(st));
+    int rc = COLO_OK;
+    long long mx = 0;
+    for (int t = 0; t < tiles; ++t) {
+      if (h_status[t] == COLO_OVERFLOW) return COLO_OVERFLOW;
+      if (h_status[t] == COLO_MAX_ITER) rc = COLO_MAX_ITER;
+    }
+    for (auto v : h_iters) mx = v > mx ? v : mx;
+    out_host[0] = (double)h;
+    out_host[1] = (double)mx;
+    return rc;
+  }
   colo_backup_args a = {};
   a.T = T; a.R = nullptr; a.r_const = 1.0;
   a.B = K; a.S = S; a.A = A; a.fold = COLO_FOLD_MIN; a.gamma = 1.0;
@@ -722,8 +819,9 @@ int colo_episodic_f64acc(const float* T, const float* R, const float* pi, int B,
 
 size_t colo_diameter_continuous_work_bytes(int K, int S, int f64) {
   size_t e = f64 ? 8 : 4;
-  return colo::align_up((size_t)K * S * e, 256) +
-         (f64 ? colo::solve_work_bytes<double>(K, S) : colo::solve_work_bytes<float>(K, S)) + 256;
+  const int K4 = (K + 3) & ~3;  // the resident path pads the targets to whole tiles of 4
+  return colo::align_up((size_t)K4 * S * e, 256) +
+         (f64 ? colo::solve_work_bytes<double>(K4, S) : colo::solve_work_bytes<float>(K4, S)) + 1024;
 }
 int colo_diameter_continuous_f32(const float* T, const int* targets, int K, int S, int A, float eps, float max_value,
                                  long long max_iter, void* work, double* out_host, void* stream) {

@@ -32,6 +32,11 @@ int check_launch(const char* what);  // cudaGetLastError -> COLO_OK / COLO_ERR_C
 
 int sm_count();  // SMs of the current device (148 on B200), cached
 
+// resident.cu: on-chip resident solver (see there)
+int resident_fits_any(int S, int A, int NV, bool f64, int* cluster_size_out);
+int resident_solve_any(const colo_resident_args* args, bool f64, void* stream);
+bool resident_enabled();  // false when COLO_NO_RESIDENT is set (benchmarking the streaming path)
+
 // ---- device helpers -------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 

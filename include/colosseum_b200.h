@@ -78,7 +78,9 @@ typedef struct {
                             (u64), accumulated with atomicMax; zero it before the sweep; or NULL                 */
   int resid_vs_out;      /* != 0: the residual compares with the previous content of V_out instead of V_in      */
   const unsigned char* active; /* per instance; 0 = converged: V is carried forward, nothing else is touched    */
-  double max_abs;        /* > 0: set *overflow_flag = 1 when |V_out| exceeds it (the reference's `return None`)  */
+  double max_abs;        /* > 0: set *overflow_flag = 1 when |V_out| exceeds it (the reference's `return None`);
+                            with overflow_signed != 0 the test is V_out > max_abs (finite_horizon.py:24-25)      */
+  int overflow_signed;
   int* overflow_flag;
   int row0, nrows;       /* nrows == 0 && row0 == 0 means all S rows                                             */
   const int* pin_index;  /* per instance or NULL: V_out[b, pin_index[b]] = pin_value (absorbing target)          */
@@ -95,6 +97,43 @@ int colo_backup_f32(const colo_backup_args* args, void* stream);
 int colo_backup_f64acc(const colo_backup_args* args, void* stream);
 
 /*
+ * On-chip resident solver: ONE launch runs a whole solve for problems whose T fits the shared memory of a
+ * thread-block cluster (<= 16 CTAs x 227 KB).  Problem b is iterated by cluster b: every CTA keeps its slice of T
+ * rows in shared memory for the entire solve, the value vectors are exchanged through distributed shared memory
+ * with one cluster barrier per sweep, and the stopping rule (max|dV| < eps after a sweep, the reference's
+ * infinite_horizon.py:140-141), the overflow test and the max_iter cap are evaluated on the device.
+ *   NV = 1: B independent MDPs (t_stride/r_stride = elements between their T/R; V [B][S], Q [B][S,A] or NULL).
+ *   NV = 4: tiles of 4 value vectors sharing one T (t_stride = 0): the multi-target hitting-time iteration of the
+ *           diameter (diameter.py:76-106) -- V [B*4][S], pin_index [B*4] = targets, fold MIN, gamma 1, r_const 1.
+ *   episodic_H > 0: exactly H sweeps without a stopping rule; sweep i stores layer H-1-i of V [B][H+1][S] and
+ *           Q [B][H+1][S,A] (finite_horizon.py:11-42; the caller zeroes layer H); pi is then [B][H][S,A].
+ * status_out[b] (device): COLO_OK / COLO_OVERFLOW / COLO_MAX_ITER; iters_out[B*NV] (device, may be NULL).
+ * colo_resident_fits returns 1 (and the cluster size) when (S, A, NV) fits.  Does not synchronise.
+ */
+typedef struct {
+  const float* T;
+  const float* R;      /* or NULL: r_const */
+  const float* pi;     /* COLO_FOLD_PI only */
+  void* V;
+  void* Q;             /* or NULL */
+  long long t_stride, r_stride;
+  int B, S, A, NV, fold;
+  double gamma, r_const, eps;
+  double max_abs;      /* > 0 enables the overflow test: |V| > max_abs, or V > max_abs when overflow_signed != 0 */
+  int overflow_signed;
+  long long max_iter;
+  int episodic_H;
+  const int* pin_index; /* [B*NV] or NULL */
+  double pin_value;
+  long long* iters_out;
+  int* status_out;
+} colo_resident_args;
+
+int colo_resident_fits(int S, int A, int NV, int f64, int* cluster_size_out);
+int colo_resident_solve_f32(const colo_resident_args* args, void* stream);
+int colo_resident_solve_f64acc(const colo_resident_args* args, void* stream);
+
+/*
  * Discounted value iteration / policy evaluation to convergence for B independent MDPs
  * (colosseum/dynamic_programming/infinite_horizon.py:14-64,121-184).  V starts at 0.  Sweeps are synchronous
  * (Jacobi); an instance stops after the sweep in which max_s|dV| < eps (the reference's test, :140-141) and its
@@ -102,6 +141,8 @@ int colo_backup_f64acc(const colo_backup_args* args, void* stream);
  * COLO_MAX_ITER after max_iter sweeps (:142).  fold = COLO_FOLD_MAX (VI) or COLO_FOLD_PI (PE, pi [B,S,A]).
  * Synchronises the stream (the host needs the convergence flags).  iters_out_host[b] = sweeps run by b (or NULL).
  * work: device scratch of colo_solve_work_bytes(B,S,f64) bytes.  Q may be NULL.
+ * Small MDPs (colo_resident_fits) are solved by the resident solver in one launch, larger ones by one streaming
+ * backup launch per sweep; same algorithm (synchronous sweeps) and stopping rule either way.
  */
 size_t colo_solve_work_bytes(long long B, long long S, int f64);
 int colo_solve_discounted_f32(const float* T, const float* R, const float* pi, int B, int S, int A, float gamma,
