@@ -188,14 +188,16 @@ def bench_step_gpu(args, rank, world):
     ms = max_over_ranks(ms, world)
     assert int(env.status.item()) == 0
 
-    # ---- end to end through the public API: pinned host actions in, TimeStep fields out, every step
+    # ---- end to end through the public API: pinned host actions in, TimeStep fields out on the host, every step.
+    # host_io=True: the step kernel reads the pinned action buffer and writes obs/reward/step_type into pinned host
+    # memory itself (zero-copy over PCIe) -- one launch + one stream sync per step, no copy launches.
+    env_h = BatchedMDP(tb, N, mode="dense_f32", seed=1234, env_offset=rank * N, host_io=True)
+    env_h.reset()
     h_act = [a.cpu().pin_memory() for a in actions]
-    h_out = torch.empty(9 * N, dtype=torch.uint8).pin_memory()  # obs | reward | step_type
 
     def e2e_step(i):
-        env.step_async(h_act[i % n_act], auto_reset=True)  # pinned host tensor -> H2D inside
-        env.fetch_async(h_out)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the TimeStep before choosing the next action
+        obs, reward, step_type = env_h.step_host(h_act[i % n_act], auto_reset=True)  # returns after the stream sync:
+        # the caller consumes the TimeStep (host views) before choosing the next action
 
     for i in range(max(3, args.warmup)):
         e2e_step(i)
@@ -207,6 +209,7 @@ def bench_step_gpu(args, rank, world):
     e1.record()
     barrier_sync(world)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    assert int(env_h.status.item()) == 0 and int(env_h.step_type_host.max()) <= 2
     return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N)
 
 
@@ -232,7 +235,7 @@ def bench_vi_gpu(args, rank, world):
     from colosseum_b200 import _cabi
     from colosseum_b200.dynamic_programming import BatchedValueIteration
 
-    B, S, A = args.vi_batch, 512, 4
+    B, S, A = (args.vi_batch or max(1, 4096 // world)), 512, 4
     T, R = make_c4_batch(B, S, A, seed=100 + rank)
     vi = BatchedValueIteration(T, R, gamma=0.99, precision="f32")
     lib = _cabi.lib()
@@ -248,7 +251,62 @@ def bench_vi_gpu(args, rank, world):
     barrier_sync(world)
     launches = int(lib.colo_launch_count())
     ms = max_over_ranks(e0.elapsed_time(e1), world)
-    return dict(B=B, S=S, A=A, steps=steps, ms=ms, launches=launches)
+    # C4 part (2), SURVEY section 8d: solve the whole batch to the reference's default epsilon = 1e-3 through the
+    # public entry point (device tensors in, device tensors out; per-instance stopping on the device)
+    import colosseum_b200.dynamic_programming as dp
+
+    del vi
+    dp.discounted_value_iteration(T[:8], R[:8], 0.99, 1e-3)  # warm-up of the solver path
+    barrier_sync(world)
+    e0.record()
+    Q, V = dp.discounted_value_iteration(T, R, 0.99, 1e-3)
+    e1.record()
+    barrier_sync(world)
+    solve_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    iters = dp.last_iterations()
+    assert bool(torch.isfinite(V).all())
+    del T, R, Q, V
+    torch.cuda.empty_cache()
+    return dict(B=B, S=S, A=A, steps=steps, ms=ms, launches=launches, solve_ms=solve_ms, solve_sweeps_max=max(iters),
+                solve_sweeps_mean=float(np.mean(iters)))
+
+
+def bench_c5_gpu(args, rank, world):
+    """C5: ONE dense synthetic MDP S=40,000 A=8 fp32 (51.2 GB of T), row-sharded over the ranks; every sweep each
+    rank backs up its S/g rows and the new V rows are exchanged (fused peer stores, or NCCL all-gather)."""
+    import torch
+
+    from colosseum_b200 import _cabi
+    from colosseum_b200.dynamic_programming import BatchedValueIteration
+    from colosseum_b200.sharded import RowShardedValueIteration, shard_range
+    from colosseum_b200.synth import synth_dense_rows
+
+    S, A = args.c5_states, 8
+    r0, r1 = shard_range(S, rank, world)
+    T_rows, R_rows = synth_dense_rows(r0, r1 - r0, S, A, seed=7)  # generated on the device, never on the host
+    if world == 1:
+        vi = BatchedValueIteration(T_rows, R_rows, gamma=0.99, precision="f32")
+        transport = "none (1 GPU)"
+    else:
+        transport = args.c5_transport
+        vi = RowShardedValueIteration(T_rows, R_rows, S, gamma=0.99, transport=transport)
+    lib = _cabi.lib()
+    steps = max(5, min(args.steps, 100))
+    vi.sweep(3)
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.colo_reset_launch_count()
+    e0.record()
+    vi.sweep(steps)
+    e1.record()
+    barrier_sync(world)
+    launches = int(lib.colo_launch_count())
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    v = vi.values
+    assert bool(torch.isfinite(v).all()) and float(v.max()) > 0
+    del vi, T_rows, R_rows
+    torch.cuda.empty_cache()
+    return dict(S=S, A=A, steps=steps, ms=ms, launches=launches, transport=transport)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -349,8 +407,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "step", "vi"])
-    ap.add_argument("--vi-batch", type=int, default=1024, help="MDP instances per GPU for the VI leg (C4 is 4096/g)")
+    ap.add_argument("--workload", default="all", choices=["all", "step", "vi", "c5"])
+    ap.add_argument("--vi-batch", type=int, default=0, help="MDP instances per GPU for the C4 leg (default 4096/g)")
+    ap.add_argument("--c5-states", type=int, default=40000, help="S of the row-sharded single MDP (C5: 40,000)")
+    ap.add_argument("--c5-transport", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -376,6 +436,7 @@ def main():
         sampler.start()
     step = bench_step_gpu(args, rank, world) if args.workload in ("all", "step") else None
     vi = bench_vi_gpu(args, rank, world) if args.workload in ("all", "vi") else None
+    c5 = bench_c5_gpu(args, rank, world) if args.workload in ("all", "c5") else None
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
@@ -389,13 +450,36 @@ def main():
     peak, peak_src = measured_peaks()
     line = {"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "clocks": clocks}
+    c5_line = None
+    if c5 is not None:
+        S5, A5 = c5["S"], c5["A"]
+        sec = c5["ms"] / 1e3 / c5["steps"]
+        rows = -(-S5 // world)  # rows of the largest shard
+        per_rank_bytes = 4 * rows * A5 * S5 + 4 * rows * A5 + 4 * S5 + 4 * rows + 4 * rows * A5
+        c5_line = {
+            "metric": "row-sharded value-iteration sweeps/sec (one dense MDP)", "value": 1.0 / sec, "unit": "sweeps/s",
+            "steps": c5["steps"], "ms_per_step": 1e3 * sec, "gpu_launches": c5["launches"], "scaling": "strong",
+            "config": {"workload": f"C5: one synthetic dense MDP S={S5} A={A5} fp32 (T = {4 * S5 * A5 * S5 / 1e9:.1f} GB "
+                                   f"generated on device), gamma=0.99, rows sharded over {world} GPU(s), V exchange: "
+                                   f"{c5['transport']}", "l2": "T per GPU >> 126 MB L2, no flush"},
+            "roofline": {"bound": "hbm", "achieved": per_rank_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": per_rank_bytes / sec / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "backup_kernel<float,MAX,VEC,cta>", "algorithmic_bytes_per_launch": per_rank_bytes,
+                         "note": "per-GPU figure: bytes of the largest row shard / sweep time (max over ranks)"},
+        }
     if vi is not None:
         per_sweep_bytes = vi_sweep_bytes(vi["S"], vi["A"]) * vi["B"]
         sec = vi["ms"] / 1e3 / vi["steps"]
         vi_line = {
             "metric": "value-iteration MDP-sweeps/sec", "value": world * vi["B"] / sec, "unit": "MDP-sweeps/s",
             "steps": vi["steps"], "ms_per_step": 1e3 * sec, "gpu_launches": vi["launches"],
-            "config": {"workload": f"C4 shape: {vi['B']} synthetic Dirichlet(0.05) MDPs per GPU, S=512 A=4 fp32, "
+            "scaling": "strong" if not args.vi_batch else "weak",
+            "solve_to_eps": {"epsilon": 1e-3, "seconds": vi["solve_ms"] / 1e3, "sweeps_max": vi["solve_sweeps_max"],
+                             "sweeps_mean": vi["solve_sweeps_mean"],
+                             "mdp_solves_per_s": world * vi["B"] / (vi["solve_ms"] / 1e3),
+                             "what": "dp.discounted_value_iteration(T, R, 0.99, 1e-3) on the whole batch, device "
+                                     "tensors in/out, per-instance stopping on the device"},
+            "config": {"workload": f"C4: {world * vi['B']} synthetic Dirichlet(0.05) MDPs ({vi['B']} per GPU), S=512 A=4 fp32, "
                                    "gamma=0.99, one synchronous sweep of the whole batch per step, Q stored",
                        "l2": f"batch T = {vi['B'] * 4 * 512 * 4 * 512 / 2**30:.1f} GiB per GPU >> 126 MB L2, no flush"},
             "roofline": {"bound": "hbm", "achieved": per_sweep_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
@@ -416,8 +500,9 @@ def main():
                        "l2": "flushed between timed steps (256 MiB write), each step timed with its own CUDA events"},
             "e2e": {"value": world * N * args.steps / (step["e2e_ms"] / 1e3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": step["h2d"], "d2h_bytes_per_step": step["d2h"],
-                    "what": "BatchedMDP.step_async from pinned host actions + obs/reward/step_type read back to pinned "
-                            "host memory and stream sync, every step"},
+                    "what": "BatchedMDP(host_io=True).step_host: pinned host actions read, and obs/reward/step_type "
+                            "written to pinned host memory, by the step kernel itself over PCIe (zero-copy), then a "
+                            "stream sync, every step"},
             "roofline": {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("env_step_dense_short_kernel", N),
                          "peak_source": peak_src, "kernel": "env_step_dense_short_kernel<float,4,4>",
@@ -432,8 +517,14 @@ def main():
                                               "BaseMDP.step; the Python reference itself runs ~5e4 steps/s/core)"}
         if vi is not None:
             line["vi"] = vi_line
-    else:
+        if c5_line is not None:
+            line["vi_c5"] = c5_line
+    elif vi is not None:
         line.update(vi_line)
+        if c5_line is not None:
+            line["vi_c5"] = c5_line
+    else:
+        line.update(c5_line)
     if vi is not None and world == 1:
         rate, n, dt = cpu_vi_rate(64, 512, 4, args.cpu_seconds)
         tgt = line["vi"] if step is not None else line

@@ -75,7 +75,7 @@ class EnvBatch(C.Structure):
         ("N", C.c_longlong), ("seed", C.c_ulonglong), ("env0", C.c_ulonglong),
         ("state", C.c_void_p), ("h", C.c_void_p), ("step_type", C.c_void_p), ("action", C.c_void_p),
         ("reward", C.c_void_p), ("obs", C.c_void_p), ("visits_s", C.c_void_p), ("visits_sa", C.c_void_p),
-        ("visits_copies", C.c_int), ("status", C.c_void_p),
+        ("visits_copies", C.c_int), ("status", C.c_void_p), ("step_type_mirror", C.c_void_p),
     ]
 
 
@@ -92,6 +92,7 @@ PROTOTYPES = {
     "colo_version": (_I, []),
     "colo_launch_count": (_ULL, []),
     "colo_reset_launch_count": (None, []),
+    "colo_stream_synchronize": (_I, [_P]),
     "colo_backup_f32": (_I, [C.POINTER(BackupArgs), _P]),
     "colo_backup_f64acc": (_I, [C.POINTER(BackupArgs), _P]),
     "colo_resident_fits": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int)]),
@@ -159,9 +160,10 @@ def ptr(t):
 
 
 def current_stream():
+    """raw cudaStream_t of torch's current stream on the current device"""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def require_cuda():

@@ -80,7 +80,11 @@ class BatchedMDP:
     VISIT_COPIES = 16  # privatised visitation counters (power of two), summed when read
 
     def __init__(self, tables: MDPTables, n_envs: int, mode: str = "dense_f32", seed: int = 0,
-                 track_visits: bool = True, env_offset: int = 0):
+                 track_visits: bool = True, env_offset: int = 0, host_io: bool = False):
+        """host_io=True: the TimeStep fields (obs, reward, step_type) live in ONE pinned host buffer that the step
+        kernel writes directly over PCIe (zero-copy), and `step_host` reads the actions straight from a pinned host
+        tensor: an agent running on the host gets its TimeStep with one launch and one stream sync per step, no
+        copy launches (include/colosseum_b200.h, colo_env_batch)."""
         import torch
 
         assert mode in _MODES
@@ -100,11 +104,18 @@ class BatchedMDP:
         # step_type = LAST + auto_reset=False reproduces that as an error, LAST + auto_reset=True resets.
         # the three TimeStep fields a host-side agent reads back live in ONE buffer (obs | reward | step_type), so an
         # end-to-end step is a single device->host copy
-        self._out = torch.zeros(9 * N, dtype=torch.uint8, device="cuda")
+        self.host_io = bool(host_io)
+        if self.host_io:
+            self._out = torch.zeros(9 * N, dtype=torch.uint8).pin_memory()
+            self.step_type = torch.full((N,), _cabi.STEP_LAST, dtype=torch.uint8, device="cuda")  # kernel input too
+            self.step_type_host = self._out[8 * N:]
+            self.step_type_host.fill_(_cabi.STEP_LAST)
+        else:
+            self._out = torch.zeros(9 * N, dtype=torch.uint8, device="cuda")
+            self.step_type = self._out[8 * N:]
+            self.step_type.fill_(_cabi.STEP_LAST)
         self.obs = self._out[: 4 * N].view(torch.int32)
         self.reward = self._out[4 * N: 8 * N].view(torch.float32)
-        self.step_type = self._out[8 * N:]
-        self.step_type.fill_(_cabi.STEP_LAST)
         self.action = torch.zeros(N, dtype=torch.int32, device="cuda")
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
         vc = self.VISIT_COPIES
@@ -125,9 +136,11 @@ class BatchedMDP:
         b.action, b.reward, b.obs = _cabi.ptr(self.action), _cabi.ptr(self.reward), _cabi.ptr(self.obs)
         b.visits_s, b.visits_sa, b.visits_copies = _cabi.ptr(self._visits_s), _cabi.ptr(self._visits_sa), vc
         b.status = _cabi.ptr(self.status)
+        b.step_type_mirror = self.step_type_host.data_ptr() if self.host_io else None
         self._batch = b
         self._batch_ref = C.byref(b)
         self._own_action_ptr = b.action
+        self._sync = lib.colo_stream_synchronize
 
     # -- reference attribute surface (base.py:463-503, 1233-1252)
     @property
@@ -155,7 +168,9 @@ class BatchedMDP:
 
     def _timestep(self):
         torch = self.torch
-        st = self.step_type
+        if self.host_io:  # host-resident fields: wait for the kernel that writes them
+            torch.cuda.current_stream().synchronize()
+        st = self.step_type_host if self.host_io else self.step_type
         nan = torch.full_like(self.reward, float("nan"))
         discount = torch.where(st == _cabi.STEP_MID, torch.ones_like(self.reward),
                                torch.where(st == _cabi.STEP_LAST, torch.zeros_like(self.reward), nan))
@@ -169,6 +184,8 @@ class BatchedMDP:
         _cabi.check(rc, "colo_env_reset")
         self.t += 1
         self._was_reset = True
+        if self.host_io:
+            torch.cuda.current_stream().synchronize()
         self.reward.fill_(float("nan"))
         return self._timestep()
 
@@ -181,8 +198,9 @@ class BatchedMDP:
         act_ptr = self._own_action_ptr
         if not random_actions:
             if isinstance(action, torch.Tensor):
-                if action.is_cuda and action.dtype == torch.int32 and action.is_contiguous():
-                    act_ptr = action.data_ptr()  # read in place: no staging copy
+                if (action.is_cuda or (self.host_io and action.is_pinned())) and action.dtype == torch.int32 \
+                        and action.is_contiguous():
+                    act_ptr = action.data_ptr()  # read in place (device, or pinned host memory over PCIe): no copy
                 else:
                     self.action.copy_(action, non_blocking=True)  # pinned host tensors: async H2D
             else:
@@ -204,6 +222,25 @@ class BatchedMDP:
                 if not self._was_reset:
                     raise AttributeError("step() called before reset() (reference: necessary_reset is unset)")
                 raise AssertionError("an episode has terminated: call reset() or step(..., auto_reset=True)")
+
+    def step_host(self, action, auto_reset=False):
+        """host_io mode: one launch + one stream sync; `action` is a pinned host int32 tensor read by the kernel
+        itself.  Returns host views (obs i32[N], reward f32[N], step_type u8[N]) of the pinned output buffer,
+        valid until the next step."""
+        assert self.host_io, "construct the BatchedMDP with host_io=True"
+        if not (auto_reset and action.dtype == self.torch.int32 and action.is_pinned() and action.is_contiguous()):
+            self.step_async(action, auto_reset=auto_reset)  # general path (checks, staging copies)
+            self._sync(_cabi.current_stream())
+            return self.obs, self.reward, self.step_type_host
+        # lean path: two ctypes calls (launch, wait); everything else was resolved in __init__
+        stream = _cabi.current_stream()
+        self._batch.action = action.data_ptr()
+        rc = self._step_fn[0](self._tb_ref, self._batch_ref, 0, None, None, self.t, 1, stream)
+        if rc != 0:
+            _cabi.check(rc, "colo_env_step")
+        self.t += 1
+        self._sync(stream)
+        return self.obs, self.reward, self.step_type_host
 
     def fetch_async(self, host_buffer):
         """one device->host copy of (obs i32[N] | reward f32[N] | step_type u8[N]) into a pinned uint8 buffer of

@@ -37,6 +37,7 @@ struct StepIO {
   int visits_mask;       // copies - 1
   long long n_s, n_sa;   // S, S*A: stride between privatised counter copies
   int* status;
+  unsigned char* step_type_mirror;  // write-only second target of step_type (pinned host memory) or null
 };
 
 __device__ __forceinline__ float reward_draw(const colo_mdp_tables& tb, int cls, float u) {
@@ -133,6 +134,7 @@ __device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tabl
     io.state[e] = nxt;
     io.h[e] = 0;
     io.step_type[e] = COLO_STEP_FIRST;
+    if (io.step_type_mirror) io.step_type_mirror[e] = COLO_STEP_FIRST;
     io.reward[e] = __int_as_float(0x7fc00000);
     io.obs[e] = nxt;
   } else if (stepping) {
@@ -141,13 +143,11 @@ __device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tabl
     io.state[e] = nxt;
     io.reward[e] = reward_draw(tb, cls, in.ur);
     if (io.random_actions) io.action[e] = in.a;
-    if (tb.H > 0 && hh >= tb.H) {
-      io.step_type[e] = COLO_STEP_LAST;
-      io.obs[e] = -1;
-    } else {
-      io.step_type[e] = COLO_STEP_MID;
-      io.obs[e] = nxt;
-    }
+    const bool last = tb.H > 0 && hh >= tb.H;
+    const unsigned char st = last ? COLO_STEP_LAST : COLO_STEP_MID;
+    io.step_type[e] = st;
+    if (io.step_type_mirror) io.step_type_mirror[e] = st;
+    io.obs[e] = last ? -1 : nxt;
   }
   const long long copy = blockIdx.x & io.visits_mask;  // privatised counters: spread same-state atomics over L2
   if (io.visits_s) aggregated_inc(io.visits_s + copy * io.n_s, nxt, stepping || resetting);
@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(kStepThreads) env_reset_kernel(const colo_mdp_
       io.state[e] = s0;
       io.h[e] = 0;
       io.step_type[e] = COLO_STEP_FIRST;
+      if (io.step_type_mirror) io.step_type_mirror[e] = COLO_STEP_FIRST;
       io.obs[e] = s0;
     }
     const long long copy = blockIdx.x & io.visits_mask;
@@ -467,6 +468,7 @@ static int make_io(const colo_mdp_tables* tb, const colo_env_batch* b, int rando
   io->step_type = b->step_type; io->reward = b->reward; io->obs = b->obs; io->visits_s = b->visits_s;
   io->visits_sa = b->visits_sa; io->visits_mask = copies - 1; io->n_s = tb->S; io->n_sa = (long long)tb->S * tb->A;
   io->status = b->status;
+  io->step_type_mirror = b->step_type_mirror;
   return COLO_OK;
 }
 

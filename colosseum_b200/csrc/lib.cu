@@ -48,4 +48,8 @@ const char* colo_last_error(void) { return colo::g_err; }
 int colo_version(void) { return 100; }
 unsigned long long colo_launch_count(void) { return colo::g_launches.load(); }
 void colo_reset_launch_count(void) { colo::g_launches.store(0); }
+int colo_stream_synchronize(void* stream) {
+  COLO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return COLO_OK;
+}
 }

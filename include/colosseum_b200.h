@@ -51,6 +51,8 @@ const char* colo_last_error(void);
 int colo_version(void);
 /* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches) */
 unsigned long long colo_launch_count(void);
+/* cudaStreamSynchronize(stream): the host-side wait of a zero-copy env step (one ctypes call, no Python layers) */
+int colo_stream_synchronize(void* stream);
 void colo_reset_launch_count(void);
 
 /* ---------------------------------------------------------------- (B) Bellman backups ------------------- */
@@ -256,6 +258,11 @@ typedef struct {
  * visits_s[copy][S] and visits_sa[copy][S*A]; a block adds to copy (blockIdx & (copies-1)) so that 65,536 envs
  * sitting on a handful of states do not serialise on a handful of L2 atomics -- the count is the sum over copies.
  * status: device int (may be NULL), set to COLO_NEEDS_RESET if an env needed a reset without auto_reset.
+ * Zero-copy host I/O: `action` is only read and `reward` / `obs` are only written by the kernels, so each of them may
+ * be a PINNED HOST buffer (cudaHostAlloc memory is mapped into the device's address space under unified addressing):
+ * the kernel then pulls the actions and pushes the TimeStep fields over PCIe itself, lane-coalesced, and an
+ * agent on the host needs no copy launches around the step.  step_type is also an INPUT of the next step and
+ * therefore stays in device memory; `step_type_mirror` (may be NULL) is a second, write-only target for it.
  * Philox: when u_next / u_rew are NULL (or random_actions is set) the numbers come from Philox4x32-10 with
  * counter (env0 + i, t) and key seed -- env0 is the global index of the batch's first env, so a batch sharded
  * over GPUs draws exactly the numbers of the unsharded batch; t is the caller's step counter.
@@ -273,6 +280,7 @@ typedef struct {
   unsigned long long* visits_sa;
   int visits_copies;
   int* status;
+  unsigned char* step_type_mirror;
 } colo_env_batch;
 
 /*

@@ -11,6 +11,7 @@ from conftest import load_instance
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
+GAM = float(np.float32(0.99))  # the reference casts gamma to float32 (infinite_horizon.py:127)
 
 
 @pytest.fixture(scope="module")
@@ -89,14 +90,14 @@ def test_fixed_sweeps_match_streaming_path(env, S, A, f64):
     assert fits(env, S, A, 1, f64)[0] == 1
     T, R = synth(S * 31 + A, S, A)
     n = 37
-    V, Q, status, iters = resident(env, T, R, n_iter=n, f64=f64)
+    V, Q, status, iters = resident(env, T, R, n_iter=n, f64=f64, gamma=GAM)
     assert status[0] == 2 and iters[0] == n  # eps = 0 never converges: COLO_MAX_ITER after exactly n sweeps
     vi = dp.BatchedValueIteration(T, R, gamma=0.99, precision="f64" if f64 else "f32")
     vi.sweep(n)
     tol = 1e-12 if f64 else 2e-6
     np.testing.assert_allclose(V[0], vi.values[0].cpu().numpy(), rtol=tol, atol=tol)
     np.testing.assert_allclose(Q[0], vi.Q[0].cpu().numpy(), rtol=tol, atol=tol)
-    Qo, Vo = orc.jacobi_sweeps_f64(T, R, np.zeros(S), n, gamma=0.99)
+    Qo, Vo = orc.jacobi_sweeps_f64(T, R, np.zeros(S), n, gamma=GAM)
     tol = 1e-9 if f64 else 1e-4
     np.testing.assert_allclose(V[0], Vo, rtol=tol)
     np.testing.assert_allclose(Q[0], Qo, rtol=tol)

@@ -278,3 +278,38 @@ def test_dense_rows_of_any_length(bm, S, mode, omode):
     env2.state.fill_(2)
     env2.step(np.zeros(4096, np.int32))
     assert (T[2, 0][env2.state.cpu().numpy()] > 0).all()
+
+
+@pytest.mark.parametrize("name,mode", [("c2_deepsea30_prand", "dense_f32"), ("taxi_epi", "succ"),
+                                       ("c1_riverswim_epi", "dense_f64")])
+def test_zero_copy_host_io_is_identical(bm, name, mode):
+    """host_io=True (the kernel reads pinned host actions and writes the TimeStep fields into pinned host memory
+    itself) must emit exactly what the device-resident batch emits, step by step, incl. auto-reset and the oracle."""
+    import torch
+
+    g = load_instance(name)
+    tb = MDPTables.from_golden(g)
+    N = 3000  # ragged last warp
+    dev = bm.BatchedMDP(tb, N, mode=mode, seed=11)
+    host = bm.BatchedMDP(tb, N, mode=mode, seed=11, host_io=True)
+    ts_d, ts_h = dev.reset(), host.reset()
+    assert torch.equal(ts_d.observation.cpu(), ts_h.observation) and bool(ts_h.first().all())
+    omode = {"dense_f32": 0, "dense_f64": 1, "succ": 2}[mode]
+    ht = host_tables(tb, omode, None if omode == 2 else dev.dev.keep["cdf"].cpu().numpy())
+    state, h, st, obs = orc.env_reset(ht, N, seed=11, t=0)
+    gen = torch.Generator().manual_seed(3)
+    for t in range(1, 2 * max(tb.H, 10) + 3):
+        a = torch.randint(0, tb.A, (N,), dtype=torch.int32, generator=gen).pin_memory()
+        dev.step_async(a, auto_reset=True)
+        o, r, stp = host.step_host(a, auto_reset=True)
+        ro, oo, rc, _ = orc.env_step(ht, omode, state, h, st, action=a.numpy(), seed=11, t=t, auto_reset=True)
+        assert torch.equal(dev.obs.cpu(), o) and torch.equal(dev.step_type.cpu(), stp)
+        assert np.array_equal(dev.reward.cpu().numpy(), r.numpy(), equal_nan=True)
+        assert np.array_equal(o.numpy(), oo) and np.array_equal(stp.numpy(), st)
+        assert np.array_equal(r.numpy(), ro, equal_nan=True)
+    assert torch.equal(dev.visits_sa, host.visits_sa) and torch.equal(dev.state, host.state)
+    # the general (non-lean) path of step_host: numpy actions, no auto-reset on a continuous MDP
+    if tb.H == 0:
+        o, r, stp = host.step_host(np.zeros(N, np.int32))
+        dev.step_async(np.zeros(N, np.int32))
+        assert torch.equal(dev.obs.cpu(), o) and bool((stp == 1).all())
