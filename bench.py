@@ -309,6 +309,42 @@ def bench_c5_gpu(args, rank, world):
     return dict(S=S, A=A, steps=steps, ms=ms, launches=launches, transport=transport)
 
 
+def bench_c3_gpu(args, rank, world):
+    """C3: the reference's benchmark MDP instances (80 gin parameter sets of the seven families, seed 0, cycled to
+    `--c3-instances`), sharded over the ranks by instance, no communication.  Per instance: `--c3-envs` parallel
+    episodes x `--c3-steps` random-agent steps through the step kernel, then diameter + value norm + gaps."""
+    import torch
+
+    from colosseum_b200 import _cabi
+    from colosseum_b200.sharded import shard_range
+    from colosseum_b200.suite import load_suite, run_instance
+
+    suite = load_suite(os.path.join(ROOT, "tests", "golden", "c3_suite.npz"))
+    B = args.c3_instances
+    i0, i1 = shard_range(B, rank, world)
+    lib = _cabi.lib()
+    run_instance(suite[1], n_envs=args.c3_envs, n_steps=10, seed=0, precision=args.c3_precision)  # warm-up
+    barrier_sync(world)
+    lib.colo_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step_s = hard_s = 0.0
+    worst = (0.0, "")
+    for i in range(i0, i1):
+        inst = suite[i % len(suite)]
+        res, tm = run_instance(inst, n_envs=args.c3_envs, n_steps=args.c3_steps, seed=i, precision=args.c3_precision)
+        step_s += tm["step_s"]
+        hard_s += tm["hardness_s"]
+        if tm["hardness_s"] > worst[0]:
+            worst = (tm["hardness_s"], inst.name)
+        assert res["gaps"] > 0 and res["diameter"] > 0 and res["visits_total"] == args.c3_envs * (args.c3_steps + 1)
+    e1.record()
+    barrier_sync(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    return dict(B=B, per_rank=i1 - i0, ms=ms, launches=int(lib.colo_launch_count()), step_s=step_s, hard_s=hard_s,
+                worst=worst, n_suite=len(suite))
+
+
 # ------------------------------------------------------------------------------------------------ CPU arms
 def cpu_step_rate(tb, n_envs, seconds):
     """the reference algorithm for the step (oracle port, C + OpenMP, all host threads), bounded sample"""
@@ -407,7 +443,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "step", "vi", "c5"])
+    ap.add_argument("--workload", default="all", choices=["all", "step", "vi", "c5", "c3"])
+    ap.add_argument("--c3-instances", type=int, default=1024, help="MDP instances of the C3 suite leg (all ranks)")
+    ap.add_argument("--c3-envs", type=int, default=1024)
+    ap.add_argument("--c3-steps", type=int, default=1000)
+    ap.add_argument("--c3-precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--vi-batch", type=int, default=0, help="MDP instances per GPU for the C4 leg (default 4096/g)")
     ap.add_argument("--c5-states", type=int, default=40000, help="S of the row-sharded single MDP (C5: 40,000)")
     ap.add_argument("--c5-transport", default="fused", choices=["fused", "nccl"])
@@ -437,6 +477,7 @@ def main():
     step = bench_step_gpu(args, rank, world) if args.workload in ("all", "step") else None
     vi = bench_vi_gpu(args, rank, world) if args.workload in ("all", "vi") else None
     c5 = bench_c5_gpu(args, rank, world) if args.workload in ("all", "c5") else None
+    c3 = bench_c3_gpu(args, rank, world) if args.workload == "c3" else None  # minutes: opt-in, not part of "all"
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
@@ -450,6 +491,26 @@ def main():
     peak, peak_src = measured_peaks()
     line = {"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "clocks": clocks}
+    if c3 is not None:
+        sec = c3["ms"] / 1e3
+        line.update({
+            "metric": "benchmark-suite MDP instances/sec (batched step + hardness measures)", "value": c3["B"] / sec,
+            "unit": "instances/s", "steps": c3["B"], "ms_per_step": 1e3 * sec / c3["B"], "scaling": "strong",
+            "gpu_launches": c3["launches"], "dtype": args.c3_precision,
+            "config": {"workload": f"C3: {c3['B']} MDP instances = the reference's {c3['n_suite']} benchmark gin parameter "
+                                   f"sets (7 families, continuous + episodic, seed 0) cycled, {c3['per_rank']} per GPU; per "
+                                   f"instance {args.c3_envs} envs x {args.c3_steps} random-agent steps, then diameter + "
+                                   "value norm + sub-optimality gaps (MiniGrid DoorKey is not in the reference)",
+                       "rank0_seconds": {"step_phase": c3["step_s"], "hardness_phase": c3["hard_s"],
+                                         "slowest_instance": c3["worst"][1], "slowest_hardness_s": c3["worst"][0]}},
+            "env_steps_per_s_step_phase": c3["per_rank"] * args.c3_envs * args.c3_steps / max(c3["step_s"], 1e-9) * world,
+        })
+        print(json.dumps(line))
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return
     c5_line = None
     if c5 is not None:
         S5, A5 = c5["S"], c5["A"]

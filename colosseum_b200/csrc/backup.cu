@@ -11,6 +11,7 @@
 // each V element loaded is reused across the actions held in registers; the per-state fold over actions
 // (max / pi-weighted sum / min) is a warp-shuffle reduction fused into the same kernel together with the
 // residual max|dV|, the overflow test and the Q store, so a sweep is ONE launch and touches T once.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -35,6 +36,10 @@ template <>
 struct VecOf<double> {
   using resid_t = unsigned long long;
 };
+
+}  // namespace colo
+#include "multirhs.cuh"
+namespace colo {
 
 template <typename TV>
 __device__ __forceinline__ void load_v4(const TV* p, TV (&v)[4]);
@@ -593,7 +598,14 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
   char* rest = (char*)work + align_up((size_t)K * S * sizeof(TV), 256);
   SolveWork w = carve<TV>(rest, K, S);
   TV* d_out = (TV*)(rest + solve_work_bytes<TV>(K, S));
-  if (resident_enabled() && resident_fits_any(S, A, 4, sizeof(TV) == 8, nullptr)) {
+  // COLO_DIAM_PATH = resident | gemm | stream forces one of the three implementations (probing); default: automatic
+  static const int diam_path = [] {
+    const char* e = getenv("COLO_DIAM_PATH");
+    if (!e) return 0;
+    return !strcmp(e, "resident") ? 1 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : 0));
+  }();
+  const bool fits = resident_fits_any(S, A, 4, sizeof(TV) == 8, nullptr) != 0;
+  if ((diam_path == 1 || (diam_path == 0 && resident_enabled())) && fits) {
     // T fits a cluster's shared memory: tiles of 4 targets, each tile iterated to convergence on chip by its own
     // cluster in ONE launch (every T quad read from shared memory serves 4 targets)
     const int K4 = (K + 3) & ~3, tiles = K4 / 4;
@@ -641,6 +653,10 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
     out_host[1] = (double)mx;
     return rc;
   }
+  const bool use_gemm = diam_path == 2 || (diam_path == 0 && (long long)K * S >= 128LL * 128);
+  HittingGemmArgs ga = {};
+  ga.T = T; ga.e_stride = S; ga.targets = targets; ga.active = w.active; ga.resid = w.resid;
+  ga.S = S; ga.A = A; ga.K = K; ga.max_value = max_value; ga.overflow_flag = w.flags + 1;
   colo_backup_args a = {};
   a.T = T; a.R = nullptr; a.r_const = 1.0;
   a.B = K; a.S = S; a.A = A; a.fold = COLO_FOLD_MIN; a.gamma = 1.0;
@@ -650,6 +666,11 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
   a.resid = w.resid; a.active = w.active; a.max_abs = max_value; a.overflow_flag = w.flags + 1;
   a.row0 = 0; a.nrows = S;
   auto sweep = [&](TV* cur, TV* nxt) {
+    if (use_gemm) {  // many targets: one tiled GEMM per sweep (multirhs.cuh)
+      ga.E_in = cur;
+      ga.E_out = nxt;
+      return launch_hitting_gemm<TV>(ga, st);
+    }
     a.V_in = cur;
     a.V_out = nxt;
     return launch_backup<TV>(&a, stream);
@@ -698,6 +719,15 @@ int diameter_episodic(const float* T_epi, const int* targets, int K, int H, int 
   a.pin_index = targets; a.pin_value = 1.0; a.exclude_index = targets; a.exclude_value = 1.0;
   a.resid = resid; a.resid_vs_out = 1; a.max_abs = max_value > 0 ? max_value + 1.0 : 0.0; a.overflow_flag = flags + 1;
   a.row0 = 0; a.nrows = S;
+  static const int epi_path = [] {
+    const char* e = getenv("COLO_DIAM_PATH");
+    return !e ? 0 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : 0));
+  }();
+  const bool use_gemm = epi_path == 2 || (epi_path == 0 && (long long)K * S >= 64LL * 64);
+  HittingGemmArgs ga = {};
+  ga.e_stride = (long long)H * S; ga.targets = targets; ga.resid = resid; ga.S = S; ga.A = A; ga.K = K;
+  ga.max_value = a.max_abs; ga.overflow_flag = flags + 1;
+  ga.pin_value = 1.0; ga.exclude_value = 1.0; ga.resid_vs_out = 1;
   int rc = COLO_MAX_ITER;
   long long it = 0;
   int check = 1, since = 0;
@@ -710,10 +740,18 @@ int diameter_episodic(const float* T_epi, const int* targets, int K, int H, int 
     r = check_launch("episodic_last_layer_kernel");
     if (r != COLO_OK) return r;
     for (int h = H - 1; h >= 1; --h) {
-      a.T = T_epi + (size_t)(h - 1) * S * A * S;
-      a.V_in = E + (size_t)h * S;
-      a.V_out = E + (size_t)(h - 1) * S;
-      r = launch_backup<TV>(&a, stream);
+      if (use_gemm) {  // many targets: the layer is one tiled GEMM (multirhs.cuh)
+        ga.T = T_epi + (size_t)(h - 1) * S * A * S;
+        ga.E_in = E + (size_t)h * S;
+        ga.E_out = E + (size_t)(h - 1) * S;
+        ga.exclude = h == H - 1;  // below the last layer F[h, es] is pinned to 1 already: no correction needed
+        r = launch_hitting_gemm<TV>(ga, st);
+      } else {
+        a.T = T_epi + (size_t)(h - 1) * S * A * S;
+        a.V_in = E + (size_t)h * S;
+        a.V_out = E + (size_t)(h - 1) * S;
+        r = launch_backup<TV>(&a, stream);
+      }
       if (r != COLO_OK) return r;
     }
     ++it;

@@ -1,0 +1,141 @@
+"""The benchmark-suite workload (BASELINE.json configs[2], "C3"): many independent MDP instances of the reference's
+families, each driven through the batched step (N parallel episodes x n steps) and then through the three hardness
+measures -- exactly what `colosseum.hardness.analysis.compute_hardness_measure` + an agent/MDP loop do per instance
+(colosseum/hardness/analysis.py:327-421, colosseum/mdp/base.py:996-1114), sharded over the GPUs of one box by
+instance with no communication.
+
+Instances travel in a SPARSE suite file (tests/golden/c3_suite.npz, written by tests/golden/make_c3_suite.py from the
+unmodified reference): successor lists in the samplers' own order, reward distributions, start distribution, H, R.
+The dense T is rebuilt here with the reference's own accumulation (float32 `T[s,a,s'] += p` in successor order,
+colosseum/mdp/utils/mdp_creation.py:71-81) and is checked bit for bit against the CRC of the reference's `mdp.T`.
+"""
+import json
+import time
+import zlib
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .tables import MDPTables
+
+
+@dataclass
+class SuiteInstance:
+    name: str
+    tables: MDPTables
+    R: np.ndarray  # f32 [S,A], the reference's mdp.R
+    ref: Dict[str, float] = field(default_factory=dict)  # the reference's own answers (NaN = not recorded)
+    nodes: Optional[np.ndarray] = None  # episodic: (h, s) pairs in the reference's episodic-graph order
+    T_crc: int = 0
+
+    @property
+    def S(self):
+        return self.tables.S
+
+    @property
+    def A(self):
+        return self.tables.A
+
+    @property
+    def H(self):
+        return self.tables.H
+
+    @property
+    def episodic(self):
+        return self.tables.H > 0
+
+    def check_T(self):
+        """the rebuilt dense T is bit-identical to the reference's mdp.T"""
+        return zlib.crc32(np.ascontiguousarray(self.tables.T, np.float32).tobytes()) == self.T_crc
+
+
+def load_suite(path, only=None) -> List[SuiteInstance]:
+    z = np.load(path, allow_pickle=False)
+    names = json.loads(str(z["names"]))
+    out = []
+    for i, name in enumerate(names):
+        if only is not None and name not in only and i not in only:
+            continue
+        k = f"i{i}_"
+        kinds = [(a, tuple(b)) for a, b in json.loads(str(z[k + "rew_kinds"]))]
+        tb = MDPTables.from_successors(int(z[k + "S"]), int(z[k + "A"]), z[k + "succ_idx"].astype(np.int32),
+                                       z[k + "succ_prob"], z[k + "succ_len"].astype(np.int32),
+                                       z[k + "rew_cls"].astype(np.int32), kinds, z[k + "start_idx"], z[k + "start_prob"],
+                                       H=int(z[k + "H"]), rewards_range=tuple(z[k + "rewards_range"]))
+        ref = {m: float(z[k + m]) for m in ("value_norm", "gaps", "diameter", "cached_diameter", "cached_value_norm")}
+        nodes = None
+        if (k + "reach_h") in z.files:
+            nodes = np.stack([z[k + "reach_h"].astype(np.int64), z[k + "reach_s"].astype(np.int64)], 1)
+        out.append(SuiteInstance(name, tb, np.asarray(z[k + "R"], np.float32), ref, nodes, int(z[k + "T_crc"])))
+    return out
+
+
+def hardness_of_instance(inst: SuiteInstance, precision="f64", max_cf_bytes=8 << 30, diameter=True):
+    """diameter, environmental value norm and sum of reciprocal sub-optimality gaps of one instance on the GPU, with
+    the property layer's choices of the reference: continuous MDPs use T, R and discounted VI
+    (colosseum/mdp/base.py:635-647, :1042-1100); episodic ones use the episodic tensor for the diameter
+    (base.py:996-1016), backward induction + reachable (h,s) pairs for the gaps (base.py:1018-1040) and the
+    continuous form for the value norm (base.py:1049-1056, base_finite.py:167-178).  Returns a dict."""
+    import torch
+
+    from . import dynamic_programming as dp
+    from . import episodic_forms as ef
+    from . import hardness as hd
+
+    tb = inst.tables
+    T = torch.from_numpy(tb.T).cuda()
+    R = torch.from_numpy(inst.R).cuda()
+    start_p = np.diff(tb.start_cum, prepend=0.0)
+    out = {}
+    eps = 1e-9 if precision == "f64" else 1e-5
+    deterministic = bool((tb.succ_len == 1).all()) and all(k == "deterministic" for k, _ in tb.rew_kinds)
+    if not inst.episodic:
+        Q, V = dp.discounted_value_iteration(T, R, 0.99, eps, precision=precision)
+        out["gaps"] = hd.get_sum_reciprocals_suboptimality_gaps(Q, V)
+        out["value_norm"] = 0.0 if deterministic else hd.calculate_norm_discounted(T, V, precision=precision)
+        if diameter:
+            out["diameter"], out["diameter_sweeps"] = hd.get_diameter(T, False, precision=precision, return_sweeps=True)
+    else:
+        H = tb.H
+        Q, V = dp.episodic_value_iteration(H, T, R, precision=precision)
+        T_epi, _, reach = ef.get_episodic_transition_matrix_and_rewards(H, T, R, tb.start_idx, start_p, return_reach=True)
+        nodes = inst.nodes if inst.nodes is not None else torch.nonzero(reach).cpu().numpy()
+        out["gaps"] = hd.get_sum_reciprocals_suboptimality_gaps(Q, V, [tuple(x) for x in np.asarray(nodes).tolist()])
+        n = len(nodes)
+        if deterministic:
+            out["value_norm"] = 0.0
+        elif 4 * n * n * tb.A <= max_cf_bytes:
+            T_cf, R_cf = ef.get_continuous_form_episodic_transition_matrix_and_rewards(H, T, R, tb.start_idx, start_p,
+                                                                                       nodes=nodes)
+            _, V_cf = dp.discounted_value_iteration(T_cf, R_cf, 0.99, eps, precision=precision)
+            out["value_norm"] = hd.calculate_norm_discounted(T_cf, V_cf, precision=precision)
+            del T_cf, R_cf
+        else:  # the reference raises "Its continuous form is too large" (mdp_creation.py:152-155)
+            out["value_norm"] = float("nan")
+        if diameter:
+            out["diameter"], out["diameter_sweeps"] = hd.get_diameter(T_epi, True, precision=precision, return_sweeps=True)
+    return out
+
+
+def run_instance(inst: SuiteInstance, n_envs=1024, n_steps=1000, seed=0, mode="succ", precision="f64", diameter=True):
+    """one C3 work item: `n_envs` parallel episodes x `n_steps` random-agent steps (BaseMDP.random_steps with
+    auto_reset, base.py:1319-1355), then the hardness measures.  Returns (results dict, seconds per phase)."""
+    import torch
+
+    from .batched_mdp import BatchedMDP
+
+    t0 = time.perf_counter()
+    env = BatchedMDP(inst.tables, n_envs, mode=mode, seed=seed)
+    env.reset()
+    for _ in range(n_steps):
+        env.step_async(None, auto_reset=True)
+    visits = env.visits_s
+    total = int(visits.sum().item())  # syncs
+    t1 = time.perf_counter()
+    res = hardness_of_instance(inst, precision=precision, diameter=diameter)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    res["visits_total"] = total
+    res["mean_reward_last_step"] = float(torch.nan_to_num(env.reward, nan=0.0).mean().item())
+    return res, {"step_s": t1 - t0, "hardness_s": t2 - t1}

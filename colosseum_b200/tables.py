@@ -88,10 +88,13 @@ class MDPTables:
         assert len(tb.rew_kinds) <= 256, "at most 256 distinct reward distributions per MDP"
         # dense twins: T (duplicates summed, as mdp/utils/mdp_creation.py:80 does) and the (s,a,s') class table
         if T is None:
-            T64 = np.zeros((S, A, S), np.float64)
+            # the reference's own accumulation: a float32 array, `T[s,a,s'] += p` once per successor in sampler order
+            # (mdp_creation.py:67-80; under numpy 2 the Python float p is rounded to float32 before the add).
+            # np.add.at is unbuffered and applies the updates in index order, i.e. in that same order.
+            T = np.zeros((S, A, S), np.float32)
             sa = np.broadcast_to(np.arange(S * A).reshape(S, A, 1), succ_idx.shape)
-            np.add.at(T64.reshape(S * A, S), (sa[valid], succ_idx[valid]), np.asarray(succ_prob, np.float64)[valid])
-            T = T64.astype(np.float32)
+            np.add.at(T.reshape(S * A, S), (sa[valid], succ_idx[valid]),
+                      np.asarray(succ_prob, np.float64)[valid].astype(np.float32))
         tb.T = np.ascontiguousarray(T, np.float32)
         sas = np.zeros((S, A, S), np.uint8)
         sa = np.broadcast_to(np.arange(S * A).reshape(S, A, 1), succ_idx.shape)

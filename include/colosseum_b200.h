@@ -207,6 +207,26 @@ int colo_value_norm_f64acc(const float* T, const double* V, int S, int A, void* 
 int colo_gaps_f64(const double* Q, const double* V, const unsigned char* mask, long long NS, int A, double reg,
                   double* out, void* stream);
 
+/* ---------------------------------------------------------------- episodic tensor builders --------------- */
+/*
+ * colo_build_episodic_tensor -- get_episodic_transition_matrix_and_rewards (colosseum/mdp/utils/mdp_creation.py:98-128):
+ *   T_epi[0, sn] = T[sn] and T_epi[H-1, :, :, sn] = p for every start state (sn, p); for 0 < h < H-1,
+ *   T_epi[h, s] = T[s] iff s is reachable at step h (some T_epi[h-1, :, :, s] > 0); R_epi = tile(R, H), last layer 0.
+ *   Outputs: T_epi f32[H,S,A,S], R_epi f32[H,S,A] (or NULL), reach u8[H,S] (1 = state reachable at step h; the set
+ *   of (h,s) pairs of EpisodicMDP.reachable_states, base_finite.py:138-150).  H >= 2.  Does not synchronise.
+ * colo_build_continuous_form -- get_continuous_form_episodic_transition_matrix_and_rewards (:131-176): the MDP over
+ *   the n reachable (h,s) nodes, listed by the caller in node_h/node_s (any order; the reference's is its DFS
+ *   order) with pos[h*S+s] = node index or -1: T_cf f32[n,A,n], R_cf f32[n,A].  Reference quirk kept: the rows of
+ *   the last layer put the start probabilities in column start_idx[k] (the start state's ORIGINAL index, :168), not in
+ *   the column of node (0, start_idx[k]).  *lost_mass_flag (device int) is set
+ *   to 1 if a positive-probability successor is missing from the node list (the reference asserts row sums == 1).
+ */
+int colo_build_episodic_tensor(const float* T, const float* R, const int* start_idx, const double* start_prob, int n_start,
+                          int H, int S, int A, float* T_epi, float* R_epi, unsigned char* reach, void* stream);
+int colo_build_continuous_form(const float* T, const float* R, const int* node_h, const int* node_s, int n,
+                               const int* pos, const int* start_idx, const double* start_prob, int n_start, int H,
+                               int S, int A, float* T_cf, float* R_cf, int* lost_mass_flag, void* stream);
+
 /* ---------------------------------------------------------------- (A) interaction step ------------------ */
 /*
  * Tables of one MDP for the step kernels (built once per MDP by the host, colosseum_b200/tables.py).

@@ -268,3 +268,48 @@ def env_step(tb, mode, state, h, step_type, action=None, u_next=None, u_rew=None
                             _p(u_rew), C.c_uint64(seed), C.c_uint64(t), C.c_uint64(env0), int(auto_reset), _p(state), _p(h),
                             _p(step_type), _p(reward), _p(obs), _p(visits_s), _p(visits_sa))
     return reward, obs, rc, action
+
+
+# ---------------------------------------------------------------------------------------------- episodic tensor forms
+def episodic_T(H, T, R, start_idx, start_prob):
+    """get_episodic_transition_matrix_and_rewards (colosseum/mdp/utils/mdp_creation.py:98-128) restated in numpy.
+    Returns (T_epi f32[H,S,A,S], R_epi f32[H,S,A], reach bool[H,S])."""
+    T, R = _f32(T), _f32(R)
+    S, A, _ = T.shape
+    T_epi = np.zeros((H, S, A, S), np.float32)
+    for sn, p in zip(start_idx, start_prob):  # :117-120
+        T_epi[0, sn] = T[sn]
+        T_epi[H - 1, :, :, sn] = p
+    for h in range(1, H - 1):  # :121-124
+        live = T_epi[h - 1].sum((0, 1)) > 0
+        T_epi[h, live] = T[live]
+    R_epi = np.tile(R, (H, 1, 1))  # :125-126
+    R_epi[-1] = 0.0
+    reach = np.zeros((H, S), bool)  # base_finite.py:138-150 (graph reachability == numeric reachability of T)
+    reach[0, np.asarray(start_idx)] = True
+    adj = (T > 0).any(1)
+    for h in range(1, H):
+        reach[h] = adj[reach[h - 1]].any(0)
+    return T_epi, R_epi, reach
+
+
+def continuous_form(H, T, R, start_idx, start_prob, nodes):
+    """get_continuous_form_episodic_transition_matrix_and_rewards (mdp_creation.py:131-176) restated in numpy;
+    `nodes` = the (h, s) pairs in row/column order (the reference's episodic-graph node order)."""
+    T, R = _f32(T), _f32(R)
+    S, A, _ = T.shape
+    nodes = [(int(h), int(s)) for h, s in nodes]
+    n = len(nodes)
+    index = {hs: i for i, hs in enumerate(nodes)}
+    T_cf = np.zeros((n, A, n), np.float32)
+    R_cf = np.zeros((n, A), np.float32)
+    for i, (h, s) in enumerate(nodes):
+        R_cf[i] = R[s]
+        if h == H - 1:  # :166-168 -- sic: the column is node_to_index[sn], the start state's index in the ORIGINAL
+            # MDP, not the position of (0, sn) in the node list; kept (the reference's episodic value norm runs on it)
+            for sn, p in zip(start_idx, start_prob):
+                T_cf[i, :, int(sn)] = p
+        else:  # :170-172 (graph successors == next states with positive probability under some action)
+            for ns in np.nonzero((T[s] > 0).any(0))[0]:
+                T_cf[i, :, index[(h + 1, int(ns))]] = T[s, :, ns]
+    return T_cf, R_cf

@@ -114,3 +114,26 @@ def test_dp_synth_measures(hd, dp_synth):
         assert rel(d, orc.diameter_continuous_f64(T)) < 1e-6
         assert rel(hd.calculate_norm_discounted(T, g[f"V_{b}"]), float(g[f"vnorm_{b}"])) < 5e-5
         assert rel(hd.get_sum_reciprocals_suboptimality_gaps(g[f"Q_{b}"], g[f"V_{b}"]), float(g[f"gaps_{b}"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", EPISODIC)
+def test_episodic_tensor_builders(name):
+    """device builders of T_epi / T_cf (mdp_creation.py:98-176) vs the tensors the reference itself built: bit exact"""
+    import colosseum_b200.episodic_forms as ef
+
+    g = load_instance(name)
+    H = int(g["H"])
+    T_epi, R_epi, reach = ef.get_episodic_transition_matrix_and_rewards(H, g["T"], g["R"], g["start_idx"],
+                                                                        g["start_prob"], return_reach=True)
+    assert T_epi.dtype == np.float32 and np.array_equal(T_epi, g["T_epi"])
+    To, Ro, reach_o = orc.episodic_T(H, g["T"], g["R"], g["start_idx"], g["start_prob"])
+    assert np.array_equal(R_epi, Ro) and np.array_equal(reach, reach_o)
+    nodes = list(zip(g["reach_h"].tolist(), g["reach_s"].tolist()))
+    assert sorted(ef.reachable_states(H, g["T"], g["start_idx"], g["start_prob"])) == sorted(nodes)
+    T_cf, R_cf = ef.get_continuous_form_episodic_transition_matrix_and_rewards(H, g["T"], g["R"], g["start_idx"],
+                                                                               g["start_prob"], nodes=nodes)
+    assert np.array_equal(T_cf, g["T_cf"]) and np.array_equal(R_cf, g["R_cf"])
+    # default (sorted) node order: the same MDP up to a relabelling of the nodes that are not start columns
+    T2, R2 = ef.get_continuous_form_episodic_transition_matrix_and_rewards(H, g["T"], g["R"], g["start_idx"],
+                                                                           g["start_prob"])
+    assert T2.shape == T_cf.shape and np.allclose(T2.sum(-1), 1.0, atol=1e-5)

@@ -237,3 +237,15 @@ def test_reward_tables_match_scipy():
         ks = np.abs(emp - dist.cdf(xs)).max()
         assert ks < 0.005, (kind, args, ks)
         assert abs(draw.mean() - dist.mean()) < 4 * dist.std() / np.sqrt(N) + 1e-4
+
+
+@pytest.mark.parametrize("name", EPISODIC)
+def test_episodic_tensor_forms_restatement(name):
+    """oracle restatement of mdp_creation.py:98-176 vs the tensors the reference itself built"""
+    g = load_instance(name)
+    H = int(g["H"])
+    T_epi, R_epi, reach = orc.episodic_T(H, g["T"], g["R"], g["start_idx"], g["start_prob"])
+    assert np.array_equal(T_epi, g["T_epi"])
+    assert set(zip(*np.nonzero(reach))) == set(zip(g["reach_h"].tolist(), g["reach_s"].tolist()))
+    T_cf, R_cf = orc.continuous_form(H, g["T"], g["R"], g["start_idx"], g["start_prob"], zip(g["reach_h"], g["reach_s"]))
+    assert np.array_equal(T_cf, g["T_cf"]) and np.array_equal(R_cf, g["R_cf"])

@@ -1,0 +1,116 @@
+"""The C3 benchmark suite (BASELINE.json configs[2]): the reference's benchmark MDP instances in sparse form.
+
+CPU part: the fixture loads, and the dense T rebuilt from the successor lists is bit-identical to the reference's
+`mdp.T` (CRC recorded by tests/golden/make_c3_suite.py).  GPU part: step + hardness measures of every instance
+against the values the unmodified reference produced (and its cached_hardness_measures files)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from colosseum_b200.suite import load_suite
+from oracle import oracle as orc
+
+SUITE = os.path.join(GOLDEN, "c3_suite.npz")
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+@pytest.fixture(scope="module")
+def suite():
+    return load_suite(SUITE)
+
+
+def test_suite_fixture_is_the_reference_benchmark(suite):
+    assert len(suite) == 80
+    fams = {i.name.split(".")[0] for i in suite}
+    assert len(fams) == 14  # seven families x {Continuous, Episodic}
+    for inst in suite:
+        assert inst.check_T(), inst.name  # rebuilt T == reference mdp.T, bit for bit
+        T = inst.tables.T
+        assert np.allclose(T.sum(-1), 1.0, atol=1e-5)  # mdp_creation.py:93
+        # R recomputed from the tables (sum_s' p E[r], mdp_creation.py:71-81) matches the reference's mdp.R
+        np.testing.assert_allclose(inst.tables.expected_rewards(), inst.R, rtol=2e-6, atol=1e-7)
+        assert (inst.nodes is not None) == inst.episodic
+
+
+def test_oracle_on_small_suite_instances(suite):
+    """the CPU oracle against the reference's recorded measures on the small instances (keeps the CPU suite fast)"""
+    n = 0
+    for inst in suite:
+        if inst.episodic or inst.S > 60 or not np.isfinite(inst.ref["diameter"]):
+            continue
+        d = orc.diameter_continuous_f64(inst.tables.T)
+        assert rel(d, inst.ref["diameter"]) < 2e-3 and rel(d, inst.ref["cached_diameter"]) < 2e-3, inst.name
+        n += 1
+    assert n >= 5
+
+
+@pytest.mark.gpu
+def test_suite_hardness_against_reference(suite):
+    """every instance through hardness_of_instance on the GPU: gaps and value norm against the reference's own
+    numbers (early-stopped VI at eps=1e-3 on its side -> 2e-3), diameter against the reference / its cache files"""
+    from colosseum_b200.suite import hardness_of_instance
+
+    checked = {"gaps": 0, "value_norm": 0, "diameter": 0}
+    for inst in suite:
+        big = inst.S * max(inst.H, 1) > 4000 or inst.S > 420
+        res = hardness_of_instance(inst, diameter=not big)
+        ref = inst.ref
+        if np.isfinite(ref["gaps"]):
+            assert rel(res["gaps"], ref["gaps"]) < 5e-3, (inst.name, res["gaps"], ref["gaps"])
+            checked["gaps"] += 1
+        if np.isfinite(ref["value_norm"]) and np.isfinite(res["value_norm"]):
+            assert abs(res["value_norm"] - ref["value_norm"]) < 5e-3 * max(ref["value_norm"], 0.05), \
+                (inst.name, res["value_norm"], ref["value_norm"])
+            checked["value_norm"] += 1
+        if "diameter" in res:
+            for key in ("diameter", "cached_diameter"):
+                if np.isfinite(ref[key]):
+                    assert rel(res["diameter"], ref[key]) < 2e-3, (inst.name, key, res["diameter"], ref[key])
+                    checked["diameter"] += 1
+    assert checked["gaps"] >= 70 and checked["value_norm"] >= 50 and checked["diameter"] >= 40, checked
+
+
+@pytest.mark.gpu
+def test_suite_step_phase(suite):
+    """the step phase of a C3 work item on one instance per family: visitation totals are conserved and the
+    empirical next-state frequencies follow T (chi-square on the most visited (s,a) pair)"""
+    import scipy.stats
+
+    from colosseum_b200.batched_mdp import BatchedMDP
+
+    seen = set()
+    for inst in suite:
+        fam = inst.name.split(".")[0]
+        if fam in seen or inst.S > 300:
+            continue
+        seen.add(fam)
+        N, n_steps = 2048, 60
+        env = BatchedMDP(inst.tables, N, mode="succ", seed=5)
+        env.reset()
+        s_prev, a_all, s_next = [], [], []
+        for _ in range(n_steps):
+            s0 = env.state.clone()
+            st0 = env.step_type.clone()
+            env.step_async(None, auto_reset=True)
+            keep = (st0 != 2).cpu().numpy()  # envs that took a regular step (not the auto-reset path)
+            s_prev.append(s0.cpu().numpy()[keep]); a_all.append(env.action.cpu().numpy()[keep])
+            s_next.append(env.state.cpu().numpy()[keep])
+        assert int(env.visits_s.sum()) == N * (n_steps + 1)
+        sp, aa, sn = map(np.concatenate, (s_prev, a_all, s_next))
+        key = sp * inst.A + aa
+        top = np.bincount(key).argmax()
+        s, a = divmod(int(top), inst.A)
+        sel = key == top
+        p = inst.tables.T[s, a].astype(np.float64)
+        cnt = np.bincount(sn[sel], minlength=inst.S)
+        assert cnt[p == 0].sum() == 0, inst.name  # zero-probability states are never produced
+        live = p > 0
+        if live.sum() > 1 and sel.sum() * p[live].min() >= 5:
+            chi2 = ((cnt[live] - sel.sum() * p[live] / p[live].sum()) ** 2 / (sel.sum() * p[live] / p[live].sum())).sum()
+            assert scipy.stats.chi2.sf(chi2, live.sum() - 1) > 1e-5, (inst.name, chi2)
+    assert len(seen) >= 10
