@@ -488,6 +488,28 @@ int solve_discounted(const float* T, const float* R, const float* pi, int B, int
   COLO_ARG_CHECK(T && R && V && work, "T, R, V, work are required");
   cudaStream_t st = (cudaStream_t)stream;
   SolveWork w = carve<TV>(work, B, S);
+  static const bool no_sparse = getenv("COLO_NO_SPARSE") != nullptr;
+  SparseRows sp;
+  if (!no_sparse && (long long)B * S * A < (1LL << 31)) {
+    // sparse rows (benchmark families, continuous forms): compressed once, then either the whole solve in one launch
+    // with V in shared memory (S <= 2048) or one compressed-row launch per sweep under the host loop below
+    int rs = sparse_rows_build(T, (long long)B * S * A, S, A, &sp, stream);
+    if (rs != COLO_OK) return rs;
+    if (sp.kmax > 0 && sparse_vi_fits_one_cta(S, sizeof(TV) == 8)) {
+      rs = sparse_solve_resident<TV>(sp, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_out_host, stream);
+      sparse_rows_free(&sp, stream);
+      return rs;
+    }
+  }
+  if (sp.kmax > 0) {
+    auto sweep = [&](TV* cur, TV* nxt) {
+      return sparse_sweep_launch<TV>(sp, R, pi, B, S, A, fold, gamma, cur, nxt, Q, w.resid, w.active, max_abs, w.flags + 1,
+                                     stream);
+    };
+    const int rc = iterate_to_convergence<TV>(sweep, V, w, B, S, (TV)eps, max_iter, iters_out_host, nullptr, st);
+    sparse_rows_free(&sp, stream);
+    return rc;
+  }
   if (resident_enabled() && resident_fits_any(S, A, 1, sizeof(TV) == 8, nullptr)) {
     // small MDPs: the whole solve is ONE launch of the on-chip resident solver (resident.cu)
     colo_resident_args ra = {};
@@ -602,8 +624,14 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
   static const int diam_path = [] {
     const char* e = getenv("COLO_DIAM_PATH");
     if (!e) return 0;
-    return !strcmp(e, "resident") ? 1 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : 0));
+    return !strcmp(e, "resident") ? 1 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : (!strcmp(e, "sparse") ? 4 : 0)));
   }();
+  if (diam_path == 0 || diam_path == 4) {
+    // benchmark-family MDPs (<= 32 successors per row): compressed rows, the whole solve in one launch
+    int handled = 0;
+    const int r = sparse_diameter_continuous<TV>(T, targets, K, S, A, eps, max_value, max_iter, out_host, &handled, stream);
+    if (r < 0 || handled) return r;
+  }
   const bool fits = resident_fits_any(S, A, 4, sizeof(TV) == 8, nullptr) != 0;
   if ((diam_path == 1 || (diam_path == 0 && resident_enabled())) && fits) {
     // T fits a cluster's shared memory: tiles of 4 targets, each tile iterated to convergence on chip by its own
@@ -721,8 +749,14 @@ int diameter_episodic(const float* T_epi, const int* targets, int K, int H, int 
   a.row0 = 0; a.nrows = S;
   static const int epi_path = [] {
     const char* e = getenv("COLO_DIAM_PATH");
-    return !e ? 0 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : 0));
+    return !e ? 0 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : (!strcmp(e, "sparse") ? 4 : 0)));
   }();
+  if (epi_path == 0 || epi_path == 4) {
+    int handled = 0;
+    const int rs = sparse_diameter_episodic<TV>(T_epi, targets, K, H, S, A, eps, max_value, max_iter, out_host, &handled,
+                                               stream);
+    if (rs < 0 || handled) return rs;
+  }
   const bool use_gemm = epi_path == 2 || (epi_path == 0 && (long long)K * S >= 64LL * 64);
   HittingGemmArgs ga = {};
   ga.e_stride = (long long)H * S; ga.targets = targets; ga.resid = resid; ga.S = S; ga.A = A; ga.K = K;

@@ -37,6 +37,33 @@ int resident_fits_any(int S, int A, int NV, bool f64, int* cluster_size_out);
 int resident_solve_any(const colo_resident_args* args, bool f64, void* stream);
 bool resident_enabled();  // false when COLO_NO_RESIDENT is set (benchmarking the streaming path)
 
+// sparse_hitting.cu: diameter on ELL-compressed rows (one launch per solve); *handled = 0 when T is not sparse
+// enough / does not fit shared memory and the dense kernels must be used
+template <typename TV>
+int sparse_diameter_continuous(const float* T, const int* targets, int K, int S, int A, double eps, double max_value,
+                               long long max_iter, double* out_host, int* handled, void* stream);
+template <typename TV>
+int sparse_diameter_episodic(const float* T_epi, const int* targets, int K, int H, int S, int A, double eps,
+                             double max_value, long long max_iter, double* out_host, int* handled, void* stream);
+
+// compressed rows of a dense tensor (kmax = 0: the rows are dense, nothing was kept); see sparse_hitting.cu
+struct SparseRows {
+  int kmax = 0;
+  int* len = nullptr;
+  void* cv = nullptr;  // int2 (column, float bits)
+};
+int sparse_rows_build(const float* T, long long rows, int S, int A, SparseRows* out, void* stream);
+void sparse_rows_free(SparseRows* h, void* stream);
+bool sparse_vi_fits_one_cta(int S, bool f64);
+template <typename TV>
+int sparse_solve_resident(const SparseRows& h, const float* R, const float* pi, int B, int S, int A, double gamma,
+                          double eps, double max_abs, long long max_iter, int fold, TV* Q, TV* V,
+                          long long* iters_out_host, void* stream);
+template <typename TV>
+int sparse_sweep_launch(const SparseRows& h, const float* R, const float* pi, int B, int S, int A, int fold,
+                        double gamma, const TV* V_in, TV* V_out, TV* Q, void* resid, const unsigned char* active,
+                        double max_abs, int* overflow_flag, void* stream);
+
 // ---- device helpers -------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 

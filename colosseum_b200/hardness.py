@@ -91,7 +91,8 @@ def get_sum_reciprocals_suboptimality_gaps(Q, V, reachable_states=None, regulari
         )
         m = np.zeros(tuple(Vd.shape), np.uint8)
         # the reference stacks gaps[h, s] once per listed pair (duplicates would count twice; the list has none)
-        hs = np.asarray(list(reachable_states), np.int64).reshape(-1, 2)
+        hs = (reachable_states if isinstance(reachable_states, np.ndarray)
+              else np.asarray(list(reachable_states), np.int64)).reshape(-1, 2)
         m[hs[:, 0], hs[:, 1]] = 1
         assert m.sum() == len(hs), "duplicate (h, s) pairs in reachable_states"
         mask = torch.from_numpy(m).cuda()

@@ -71,7 +71,7 @@ def load_suite(path, only=None) -> List[SuiteInstance]:
     return out
 
 
-def hardness_of_instance(inst: SuiteInstance, precision="f64", max_cf_bytes=8 << 30, diameter=True):
+def hardness_of_instance(inst: SuiteInstance, precision="f64", max_cf_bytes=8 << 30, diameter=True, timings=None):
     """diameter, environmental value norm and sum of reciprocal sub-optimality gaps of one instance on the GPU, with
     the property layer's choices of the reference: continuous MDPs use T, R and discounted VI
     (colosseum/mdp/base.py:635-647, :1042-1100); episodic ones use the episodic tensor for the diameter
@@ -83,38 +83,59 @@ def hardness_of_instance(inst: SuiteInstance, precision="f64", max_cf_bytes=8 <<
     from . import episodic_forms as ef
     from . import hardness as hd
 
+    def lap(name, _t=[None]):
+        if timings is not None:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            if _t[0] is not None:
+                timings[name] = timings.get(name, 0.0) + now - _t[0]
+            _t[0] = now
+
+    lap(None)
     tb = inst.tables
     T = torch.from_numpy(tb.T).cuda()
     R = torch.from_numpy(inst.R).cuda()
     start_p = np.diff(tb.start_cum, prepend=0.0)
     out = {}
+    lap("upload")
     eps = 1e-9 if precision == "f64" else 1e-5
     deterministic = bool((tb.succ_len == 1).all()) and all(k == "deterministic" for k, _ in tb.rew_kinds)
     if not inst.episodic:
         Q, V = dp.discounted_value_iteration(T, R, 0.99, eps, precision=precision)
+        lap("vi")
         out["gaps"] = hd.get_sum_reciprocals_suboptimality_gaps(Q, V)
+        lap("gaps")
         out["value_norm"] = 0.0 if deterministic else hd.calculate_norm_discounted(T, V, precision=precision)
+        lap("value_norm")
         if diameter:
             out["diameter"], out["diameter_sweeps"] = hd.get_diameter(T, False, precision=precision, return_sweeps=True)
+            lap("diameter")
     else:
         H = tb.H
         Q, V = dp.episodic_value_iteration(H, T, R, precision=precision)
+        lap("vi")
         T_epi, _, reach = ef.get_episodic_transition_matrix_and_rewards(H, T, R, tb.start_idx, start_p, return_reach=True)
         nodes = inst.nodes if inst.nodes is not None else torch.nonzero(reach).cpu().numpy()
-        out["gaps"] = hd.get_sum_reciprocals_suboptimality_gaps(Q, V, [tuple(x) for x in np.asarray(nodes).tolist()])
+        lap("T_epi")
+        out["gaps"] = hd.get_sum_reciprocals_suboptimality_gaps(Q, V, np.asarray(nodes))
+        lap("gaps")
         n = len(nodes)
         if deterministic:
             out["value_norm"] = 0.0
         elif 4 * n * n * tb.A <= max_cf_bytes:
             T_cf, R_cf = ef.get_continuous_form_episodic_transition_matrix_and_rewards(H, T, R, tb.start_idx, start_p,
                                                                                        nodes=nodes)
+            lap("T_cf")
             _, V_cf = dp.discounted_value_iteration(T_cf, R_cf, 0.99, eps, precision=precision)
+            lap("vi_cf")
             out["value_norm"] = hd.calculate_norm_discounted(T_cf, V_cf, precision=precision)
             del T_cf, R_cf
+            lap("value_norm")
         else:  # the reference raises "Its continuous form is too large" (mdp_creation.py:152-155)
             out["value_norm"] = float("nan")
         if diameter:
             out["diameter"], out["diameter_sweeps"] = hd.get_diameter(T_epi, True, precision=precision, return_sweeps=True)
+            lap("diameter")
     return out
 
 
