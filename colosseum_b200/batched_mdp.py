@@ -267,6 +267,19 @@ class BatchedMDP:
         """BaseMDP.random_steps (base.py:1319-1339)."""
         return [self.random_step(auto_reset) for _ in range(n)]
 
+    def random_steps_fused(self, n, auto_reset=True):
+        """n random-agent steps of every env in ONE launch (no per-step TimeStep list: state, h, visitation counts
+        and the last step's TimeStep fields are what remains) -- bit-identical to n calls of random_step()."""
+        self._batch.action = self._own_action_ptr
+        rc = _cabi.lib().colo_env_random_steps(self._tb_ref, self._batch_ref, _MODES[self.mode], int(n), self.t,
+                                               int(bool(auto_reset)), _cabi.current_stream())
+        _cabi.check(rc, "colo_env_random_steps")
+        self.t += int(n)
+        if not auto_reset and int(self.status.item()) == _cabi.NEEDS_RESET:
+            self.status.zero_()
+            raise AssertionError("an episode has terminated: call reset() or use auto_reset=True")
+        return self._timestep()
+
     @property
     def visits_s(self):
         """state visitation counts i64[S] (sum of the privatised copies)"""

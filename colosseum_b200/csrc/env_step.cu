@@ -38,6 +38,7 @@ struct StepIO {
   long long n_s, n_sa;   // S, S*A: stride between privatised counter copies
   int* status;
   unsigned char* step_type_mirror;  // write-only second target of step_type (pinned host memory) or null
+  int n_steps;  // > 1: that many consecutive steps in ONE launch (random actions; Philox counter t, t+1, ...)
 };
 
 __device__ __forceinline__ float reward_draw(const colo_mdp_tables& tb, int cls, float u) {
@@ -102,13 +103,14 @@ struct EnvIn {
 };
 
 template <bool F32U>
-__device__ __forceinline__ EnvIn load_env(const StepIO& io, const colo_mdp_tables& tb, long long e) {
+__device__ __forceinline__ EnvIn load_env(const StepIO& io, const colo_mdp_tables& tb, long long e,
+                                           unsigned long long t) {
   EnvIn in;
   in.st = io.step_type[e];
   in.s = io.state[e];
   Philox4 w;
   const bool need_rng = io.u_next == nullptr || io.u_rew == nullptr || io.random_actions;
-  if (need_rng) w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, io.t);
+  if (need_rng) w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, t);
   if (io.u_next) {
     if (F32U) {
       in.un32 = reinterpret_cast<const float*>(io.u_next)[e];
@@ -202,12 +204,13 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
   const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
   constexpr bool F32U = sizeof(TC) == 4;
 
-  for (long long tile = warp_global; tile < n_tiles; tile += n_warps) {
+  for (long long tile = warp_global; tile < n_tiles; tile += n_warps)
+  for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same lane for every step of the launch
     const long long e = tile * 32 + lane;
     const bool valid = e < io.N;
     EnvIn in;
     in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
-    if (valid) in = load_env<F32U>(io, tb, e);
+    if (valid) in = load_env<F32U>(io, tb, e, io.t + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
     const bool stepping = valid && !is_last;
@@ -265,12 +268,13 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
   const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
   constexpr bool F32U = sizeof(TC) == 4;
 
-  for (long long tile = warp_global; tile < n_tiles; tile += n_warps) {
+  for (long long tile = warp_global; tile < n_tiles; tile += n_warps)
+  for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same lane for every step of the launch
     const long long e = tile * TILE + lane;
     const bool valid = lane < TILE && e < io.N;
     EnvIn in;
     in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
-    if (valid) in = load_env<F32U>(io, tb, e);
+    if (valid) in = load_env<F32U>(io, tb, e, io.t + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
     const bool stepping = valid && !is_last;
@@ -330,11 +334,12 @@ __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_
   const long long n_thr = (long long)gridDim.x * kStepThreads;
   // round the loop bound up to whole warps: finish_env uses warp collectives
   const long long n_pad = (io.N + 31) & ~31LL;
-  for (long long e = (long long)blockIdx.x * kStepThreads + threadIdx.x; e < n_pad; e += n_thr) {
+  for (long long e = (long long)blockIdx.x * kStepThreads + threadIdx.x; e < n_pad; e += n_thr)
+  for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same thread for every step of the launch
     const bool valid = e < io.N;
     EnvIn in;
     in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
-    if (valid) in = load_env<false>(io, tb, e);
+    if (valid) in = load_env<false>(io, tb, e, io.t + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
     const bool stepping = valid && !is_last;
@@ -469,6 +474,7 @@ static int make_io(const colo_mdp_tables* tb, const colo_env_batch* b, int rando
   io->visits_sa = b->visits_sa; io->visits_mask = copies - 1; io->n_s = tb->S; io->n_sa = (long long)tb->S * tb->A;
   io->status = b->status;
   io->step_type_mirror = b->step_type_mirror;
+  io->n_steps = 1;
   return COLO_OK;
 }
 
@@ -517,6 +523,25 @@ int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, i
   colo::StepIO io;
   r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
   if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
+  COLO_ARG_CHECK(io.reward && io.action, "env buffers");
+  if (io.N == 0) return COLO_OK;
+  const int grid = colo::grid_for(colo::kStepThreads, io.N);
+  colo::env_step_succ_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
+  return colo::check_launch("env_step_succ_kernel");
+}
+
+int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch, int mode, int n_steps,
+                          unsigned long long t0, int auto_reset, void* stream) {
+  int r = colo::check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(n_steps >= 1 && mode >= 0 && mode <= 2, "n_steps >= 1, mode in {0,1,2}");
+  colo::StepIO io;
+  r = make_io(tb, batch, 1, nullptr, nullptr, t0, auto_reset, &io);
+  if (r != COLO_OK) return r;
+  io.n_steps = n_steps;
+  if (mode == 0) return colo::launch_dense<float>(tb, io, stream);
+  if (mode == 1) return colo::launch_dense<double>(tb, io, stream);
   COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
   COLO_ARG_CHECK(io.reward && io.action, "env buffers");
   if (io.N == 0) return COLO_OK;

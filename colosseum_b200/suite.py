@@ -149,8 +149,7 @@ def run_instance(inst: SuiteInstance, n_envs=1024, n_steps=1000, seed=0, mode="s
     t0 = time.perf_counter()
     env = BatchedMDP(inst.tables, n_envs, mode=mode, seed=seed)
     env.reset()
-    for _ in range(n_steps):
-        env.step_async(None, auto_reset=True)
+    env.random_steps_fused(n_steps, auto_reset=True)  # one launch: every env walks n_steps with random actions
     visits = env.visits_s
     total = int(visits.sum().item())  # syncs
     t1 = time.perf_counter()

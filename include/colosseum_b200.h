@@ -320,6 +320,15 @@ int colo_env_step_dense_f32(const colo_mdp_tables* tb, const colo_env_batch* bat
 int colo_env_step_dense_f64(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
                             const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
                             void* stream);
+/*
+ * colo_env_random_steps -- BaseMDP.random_steps(n, auto_reset) (base.py:1319-1339) for every env in ONE launch: each
+ * env is advanced n_steps times with uniformly random actions drawn from the Philox stream at counters t0, t0+1, ...
+ * Bit-identical to n_steps calls of colo_env_step_* with random_actions = 1 and t = t0 .. t0+n_steps-1 (state, h,
+ * step_type, visitation counters; reward / obs / action hold the LAST step's values).  mode: 0 dense f32 rows,
+ * 1 dense f64 rows, 2 successor tables.  The caller advances its step counter by n_steps.
+ */
+int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch, int mode, int n_steps,
+                          unsigned long long t0, int auto_reset, void* stream);
 int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
                        const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
                        void* stream);

@@ -313,3 +313,27 @@ def test_zero_copy_host_io_is_identical(bm, name, mode):
         o, r, stp = host.step_host(np.zeros(N, np.int32))
         dev.step_async(np.zeros(N, np.int32))
         assert torch.equal(dev.obs.cpu(), o) and bool((stp == 1).all())
+
+
+@pytest.mark.parametrize("name,mode", [("c2_deepsea30_prand", "dense_f32"), ("taxi_epi", "succ"),
+                                       ("frozenlake4_epi", "dense_f64"), ("minigridempty5_epi", "dense_f32")])
+def test_fused_random_steps_equal_single_steps(bm, name, mode):
+    """colo_env_random_steps: n random-agent steps in one launch == n launches (same Philox counters)"""
+    import torch
+
+    tb = MDPTables.from_golden(load_instance(name))
+    N, n = 3000, 75
+    a = bm.BatchedMDP(tb, N, mode=mode, seed=21)
+    b = bm.BatchedMDP(tb, N, mode=mode, seed=21)
+    a.reset(); b.reset()
+    for _ in range(n):
+        a.step_async(None, auto_reset=True)
+    ts = b.random_steps_fused(n, auto_reset=True)
+    for x, y in ((a.state, b.state), (a.h, b.h), (a.step_type, b.step_type), (a.obs, b.obs), (a.action, b.action),
+                 (a.visits_s, b.visits_s), (a.visits_sa, b.visits_sa)):
+        assert torch.equal(x, y)
+    assert torch.equal(torch.nan_to_num(a.reward, nan=-7.0), torch.nan_to_num(b.reward, nan=-7.0))
+    assert a.t == b.t and ts.observation.shape == (N,)
+    if tb.H > 0:
+        with pytest.raises(AssertionError):
+            b.random_steps_fused(tb.H + 2, auto_reset=False)
