@@ -524,8 +524,9 @@ def main():
                                    f"generated on device), gamma=0.99, rows sharded over {world} GPU(s), V exchange: "
                                    f"{c5['transport']}", "l2": "T per GPU >> 126 MB L2, no flush"},
             "roofline": {"bound": "hbm", "achieved": per_rank_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": per_rank_bytes / sec / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "backup_kernel<float,MAX,VEC,cta>", "algorithmic_bytes_per_launch": per_rank_bytes,
+                         "frac": per_rank_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("backup_c5", rows * A5 * S5),
+                         "peak_source": peak_src,
+                         "kernel": "backup_kernel<float,MAX,VEC,warp>", "algorithmic_bytes_per_launch": per_rank_bytes,
                          "note": "per-GPU figure: bytes of the largest row shard / sweep time (max over ranks)"},
         }
     if vi is not None:
@@ -544,7 +545,7 @@ def main():
                                    "gamma=0.99, one synchronous sweep of the whole batch per step, Q stored",
                        "l2": f"batch T = {vi['B'] * 4 * 512 * 4 * 512 / 2**30:.1f} GiB per GPU >> 126 MB L2, no flush"},
             "roofline": {"bound": "hbm", "achieved": per_sweep_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": per_sweep_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("backup_kernel", vi["B"]),
+                         "frac": per_sweep_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("backup_c4", vi["B"]),
                          "peak_source": peak_src, "kernel": "backup_kernel<float,MAX,VEC,warp>",
                          "algorithmic_bytes_per_launch": per_sweep_bytes},
         }
@@ -565,7 +566,7 @@ def main():
                             "written to pinned host memory, by the step kernel itself over PCIe (zero-copy), then a "
                             "stream sync, every step"},
             "roofline": {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("env_step_dense_short_kernel", N),
+                         "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("step", N),
                          "peak_source": peak_src, "kernel": "env_step_dense_short_kernel<float,4,4>",
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "note": "T (1.8 MB) is L2/L1-resident by construction in C2: algorithmic bytes are served "

@@ -77,6 +77,7 @@ def report(tag, name, rep, n_units):
             tot = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
             traffic[key] = {"dram_bytes_per_launch": tot, "units_per_launch": n_units, "dram_bytes_per_unit": tot / n_units,
                             "source": f"profiles/{tag}_{name}_metrics.csv"}
+            traffic[name] = dict(traffic[key], kernel=kname[:100])  # also under the spec's own name (e.g. backup_c5)
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
 
