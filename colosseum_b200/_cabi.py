@@ -118,7 +118,12 @@ PROTOTYPES = {
     "colo_env_step_dense_f64": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
     "colo_env_step_succ": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
     "colo_env_random_steps": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _I, _ULL, _I, _P]),
+    "colo_emit_observations": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _P, _P]),
     "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),
+    "colo_extended_vi_work_bytes": (C.c_size_t, [_I, _I]),
+    "colo_extended_vi_f32": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P]),
+    "colo_extended_vi_f64acc": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P]),
+    "colo_sample_dirichlet_rows": (_I, [_P, _LL, _I, _LL, _ULL, _ULL, _P, _P]),
     "colo_build_episodic_tensor": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "colo_build_continuous_form": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "colo_synth_dense_rows": (_I, [_P, _P, _I, _I, _I, _I, _ULL, _P]),

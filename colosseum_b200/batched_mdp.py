@@ -267,6 +267,29 @@ class BatchedMDP:
         """BaseMDP.random_steps (base.py:1319-1339)."""
         return [self.random_step(auto_reset) for _ in range(n)]
 
+    def set_emission_table(self, all_observations):
+        """Non-tabular observations (colosseum/emission_maps/base.py:56-76): `all_observations` is the reference's
+        precomputed table, f32 [H,S,...] (episodic) or [S,...] (continuous).  `emit_observations()` then returns the
+        feature rows of the current TimeStep of every env (zeros past the horizon, :131-132)."""
+        torch = self.torch
+        t = all_observations if isinstance(all_observations, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(all_observations, np.float32))
+        t = t.to(device="cuda", dtype=torch.float32).contiguous()
+        lead = 2 if self.tables.H > 0 else 1
+        assert tuple(t.shape[:lead]) == ((self.tables.H, self.tables.S) if lead == 2 else (self.tables.S,))
+        self._emit_shape = tuple(t.shape[lead:])
+        self._emit_table = t.reshape(*t.shape[:lead], -1)
+        self._emit_out = torch.empty((self.n_envs, self._emit_table.shape[-1]), dtype=torch.float32, device="cuda")
+
+    def emit_observations(self):
+        """EmissionMap.get_observation for every env (one gather launch); f32 [N, *shape] CUDA tensor."""
+        D = int(self._emit_table.shape[-1])
+        rc = _cabi.lib().colo_emit_observations(_cabi.ptr(self._emit_table), _cabi.ptr(self.state), _cabi.ptr(self.h),
+                                                _cabi.ptr(self.step_type), self.n_envs, self.tables.H, self.tables.S, D,
+                                                _cabi.ptr(self._emit_out), _cabi.current_stream())
+        _cabi.check(rc, "colo_emit_observations")
+        return self._emit_out.view(self.n_envs, *self._emit_shape)
+
     def random_steps_fused(self, n, auto_reset=True):
         """n random-agent steps of every env in ONE launch (no per-step TimeStep list: state, h, visitation counts
         and the last step's TimeStep fields are what remains) -- bit-identical to n calls of random_step()."""

@@ -402,6 +402,26 @@ __global__ void build_dense_cdf_kernel(const float* __restrict__ T, int S, int A
   }
 }
 
+// Non-tabular observations: EmissionMap.get_observation (colosseum/emission_maps/base.py:110-140) is a row gather from
+// the precomputed table all_observations[h, s, ...] (:56-76); past the horizon (in_episode_time >= H, i.e. the LAST
+// step of an episode) the reference returns zeros (:131-132).  One warp per env copies the D floats of its row.
+__global__ void __launch_bounds__(256) emit_observations_kernel(const float* __restrict__ table, const int* __restrict__ state,
+                                                                const int* __restrict__ h,
+                                                                const unsigned char* __restrict__ step_type, long long N,
+                                                                int H, int S, int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long e = warp; e < N; e += n_warps) {
+    const int s = state[e];
+    const int hh = H > 0 ? h[e] : 0;
+    const bool zero = H > 0 && (hh >= H || step_type[e] == COLO_STEP_LAST);
+    const float* row = table + ((size_t)(H > 0 ? hh : 0) * S + s) * D;
+    float* o = out + (size_t)e * D;
+    for (int j = lane; j < D; j += 32) o[j] = zero ? 0.f : row[j];
+  }
+}
+
 static int grid_for(long long work_items_per_thread_block, long long total) {
   long long blocks = (total + work_items_per_thread_block - 1) / work_items_per_thread_block;
   long long cap = (long long)sm_count() * 32;  // 64-thread CTAs: up to 32 resident per SM
@@ -548,6 +568,17 @@ int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch
   const int grid = colo::grid_for(colo::kStepThreads, io.N);
   colo::env_step_succ_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
   return colo::check_launch("env_step_succ_kernel");
+}
+
+int colo_emit_observations(const float* table, const int* state, const int* h, const unsigned char* step_type,
+                           long long N, int H, int S, int D, float* out, void* stream) {
+  COLO_ARG_CHECK(table && state && h && step_type && out && N >= 0 && H >= 0 && S > 0 && D > 0, "emit_observations");
+  if (N == 0) return COLO_OK;
+  const long long blocks = (N + 7) / 8;
+  const long long cap = (long long)colo::sm_count() * 16;
+  colo::emit_observations_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(table, state, h, step_type,
+                                                                                                       N, H, S, D, out);
+  return colo::check_launch("emit_observations_kernel");
 }
 
 int colo_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64, void* stream) {

@@ -1,0 +1,77 @@
+// posterior.cu -- PSRL's transition-model sample on the GPU.
+//
+//   colosseum/agent/mdp_models/bayesian_models/conjugate_transitions.py:48-60  M_DIR._sample / sample:
+//       r = rng.standard_gamma(hyper_params).astype(float32);  T = r / (1e-5 + r.sum(-1))      (sic: 1e-5 in the denominator)
+//   feeds value iteration every episode: colosseum/agent/agents/episodic/posterior_sampling.py:142-144,
+//   colosseum/agent/agents/infinite_horizon/posterior_sampling.py:177,374.
+//
+// S*A*S gamma draws per sample (Marsaglia-Tsang squeeze, alpha < 1 boosted with u^(1/alpha); fp64 like numpy's
+// standard_gamma, rounded to float32 before the normalisation like the reference's .astype).  One warp per row: draws
+// are written unnormalised while the row sum is reduced, then the row is rescaled in place.  Randomness: Philox4x32-10
+// keyed by `seed`, counter (row*S + j, draw index t, attempt) -- a pure function of its arguments, so a model sharded by
+// rows over GPUs samples exactly what one GPU would.  Parity with the reference is distributional (its numpy stream
+// cannot be reproduced): moments and KS tests against scipy in tests/test_gpu_posterior.py.
+#include "common.cuh"
+
+namespace colo {
+
+__device__ __forceinline__ double gamma_draw(double alpha, uint64_t seed, uint64_t elem, uint64_t t) {
+  if (!(alpha > 0.0)) return 0.0;
+  const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  double g = 0.0;
+  for (uint64_t attempt = 0; attempt < 64; ++attempt) {
+    const Philox4 w = philox4x32_10(seed, elem, (t << 8) | attempt);
+    // Box-Muller normal from two 53/32-bit uniforms, one more uniform for the squeeze test
+    const double u1 = (u53(w.w[0], w.w[1]) + 1.1102230246251565e-16), u2 = (double)w.w[2] * (1.0 / 4294967296.0);
+    const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    const double v0 = 1.0 + c * x;
+    if (v0 <= 0.0) continue;
+    const double v = v0 * v0 * v0;
+    const double u = ((double)w.w[3] + 0.5) * (1.0 / 4294967296.0);
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+      g = d * v;
+      break;
+    }
+  }
+  if (alpha < 1.0) {  // gamma(alpha) = gamma(alpha + 1) * U^(1/alpha)
+    const Philox4 w = philox4x32_10(seed ^ 0x9E3779B97F4A7C15ULL, elem, t);
+    const double u = u53(w.w[0], w.w[1]) + 1.1102230246251565e-16;
+    g *= pow(u, 1.0 / alpha);
+  }
+  return g;
+}
+
+__global__ void __launch_bounds__(256) dirichlet_rows_kernel(const float* __restrict__ hyper, long long rows, int S,
+                                                             long long row0, unsigned long long seed,
+                                                             unsigned long long t, float* __restrict__ T) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += n_warps) {
+    const float* h = hyper + (size_t)r * S;
+    float* out = T + (size_t)r * S;
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) {
+      const float g = (float)gamma_draw((double)h[j], seed, (uint64_t)(row0 + r) * (uint64_t)S + (uint64_t)j, t);
+      out[j] = g;
+      sum += g;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / (1e-5f + sum);  // conjugate_transitions.py:53
+    for (int j = lane; j < S; j += 32) out[j] *= inv;
+  }
+}
+
+}  // namespace colo
+
+extern "C" int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0,
+                                          unsigned long long seed, unsigned long long t, float* T_out, void* stream) {
+  COLO_ARG_CHECK(hyper && T_out && rows >= 0 && S > 0 && row0 >= 0, "hyper, T_out, rows, S, row0");
+  if (rows == 0) return COLO_OK;
+  const long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)colo::sm_count() * 16;
+  colo::dirichlet_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(hyper, rows, S, row0,
+                                                                                                    seed, t, T_out);
+  return colo::check_launch("dirichlet_rows_kernel");
+}

@@ -160,6 +160,38 @@ def discounted_policy_iteration(T, R, gamma=0.99, epsilon=1e-7, *, precision=Non
     raise DynamicProgrammingMaxIterationExceeded()
 
 
+def extended_value_iteration(T, estimated_rewards, beta_r, beta_p, r_max, epsilon=1e-3, *, precision=None,
+                             max_iter=DP_MAX_ITERATION, return_iterations=False):
+    """colosseum/dynamic_programming/infinite_horizon.py:67-118 (UCRL2's optimistic value iteration, with `_max_proba`
+    :222-251).  Returns (span of the value function, Q[S,A], V[S]), or None when the iteration cap is reached.
+    `beta_p` may be [S,A], [S,A,1] or [S,A,S]: like the reference (:230) only element 0 of the last axis is used."""
+    precision = precision or _PRECISION
+    as_numpy = not _is_tensor(T)
+    torch = _torch()
+    Td, Rd = to_device(T), to_device(estimated_rewards)
+    S, A, _ = Td.shape
+    br = to_device(beta_r, np.float64).reshape(S, A)
+    bp = beta_p
+    if getattr(bp, "ndim", 2) == 3 or (hasattr(bp, "dim") and bp.dim() == 3):
+        bp = bp[..., 0]
+    bp = to_device(np.ascontiguousarray(bp) if not _is_tensor(bp) else bp, np.float64).reshape(S, A)
+    f64 = precision == "f64"
+    vd = _vdtype(precision)
+    Q = torch.empty((S, A), dtype=vd, device="cuda")
+    V = torch.empty(S, dtype=vd, device="cuda")
+    lib = _cabi.lib()
+    work = _scratch(lib.colo_extended_vi_work_bytes(S, int(f64)))
+    out = (C.c_double * 2)()
+    fn = lib.colo_extended_vi_f64acc if f64 else lib.colo_extended_vi_f32
+    rc = fn(_cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(br), _cabi.ptr(bp), S, A, float(r_max), float(epsilon), int(max_iter),
+            _cabi.ptr(Q), _cabi.ptr(V), out, _cabi.ptr(work), _cabi.current_stream())
+    _cabi.check(rc, "colo_extended_vi")
+    if rc == _cabi.MAX_ITER:
+        return None
+    res = (float(out[0]), _result(Q, as_numpy), _result(V, as_numpy))
+    return res + (int(out[1]),) if return_iterations else res
+
+
 # ------------------------------------------------------------------------------------------------ episodic
 def _episodic(H, T, R, policy, max_value, precision):
     precision = precision or _PRECISION

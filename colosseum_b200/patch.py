@@ -25,6 +25,7 @@ REPLACEMENTS = {
     ("colosseum.dynamic_programming.infinite_horizon", "discounted_value_iteration"): _dp.discounted_value_iteration,
     ("colosseum.dynamic_programming.infinite_horizon", "discounted_policy_evaluation"): _dp.discounted_policy_evaluation,
     ("colosseum.dynamic_programming.infinite_horizon", "discounted_policy_iteration"): _dp.discounted_policy_iteration,
+    ("colosseum.dynamic_programming.infinite_horizon", "extended_value_iteration"): _dp.extended_value_iteration,
     ("colosseum.hardness.measures.diameter", "get_diameter"): _hd.get_diameter,
     ("colosseum.hardness.measures.value_norm", "calculate_norm_discounted"): _hd.calculate_norm_discounted,
     ("colosseum.hardness.measures.sum_reciprocals_suboptimality_gaps", "get_sum_reciprocals_suboptimality_gaps"):

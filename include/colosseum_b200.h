@@ -207,6 +207,34 @@ int colo_value_norm_f64acc(const float* T, const double* V, int S, int A, void* 
 int colo_gaps_f64(const double* Q, const double* V, const unsigned char* mask, long long NS, int A, double reg,
                   double* out, void* stream);
 
+/* ---------------------------------------------------------------- extended value iteration (UCRL2) --------- */
+/*
+ * extended_value_iteration + _max_proba (colosseum/dynamic_programming/infinite_horizon.py:67-118, :222-251; called by
+ * colosseum/agent/agents/infinite_horizon/ucrl2.py:330).  T f32[S,A,S] (the empirical model), est_rewards f32[S,A],
+ * beta_r f64[S,A], beta_p f64[S,A] (the reference passes [S,A,1] -- or [S,A,S] of which it reads element 0 only,
+ * :230).  Synchronous iterations u1 -> u2 from u = 0 until ptp(u2 - u1) < eps; outputs Q [S,A], V [S] of the stopping
+ * iteration, out_host[0] = ptp(u1) (the span the reference returns), out_host[1] = iterations.  Returns COLO_OK, or
+ * COLO_MAX_ITER after max_iter iterations (the reference then returns None).  Synchronises.  S <= 8192.
+ * work: colo_extended_vi_work_bytes(S, f64) bytes of device scratch.
+ */
+size_t colo_extended_vi_work_bytes(int S, int f64);
+int colo_extended_vi_f32(const float* T, const float* est_rewards, const double* beta_r, const double* beta_p, int S,
+                         int A, double r_max, double eps, long long max_iter, float* Q, float* V, double* out_host,
+                         void* work, void* stream);
+int colo_extended_vi_f64acc(const float* T, const float* est_rewards, const double* beta_r, const double* beta_p, int S,
+                            int A, double r_max, double eps, long long max_iter, double* Q, double* V, double* out_host,
+                            void* work, void* stream);
+
+/* ---------------------------------------------------------------- posterior sampling (PSRL) ---------------- */
+/*
+ * colo_sample_dirichlet_rows -- M_DIR._sample (colosseum/agent/mdp_models/bayesian_models/conjugate_transitions.py:
+ * 48-60): T_out[r, :] = g / (1e-5 + sum(g)), g[j] ~ Gamma(hyper[r, j]) rounded to float32; rows = S*A for a whole
+ * model.  Philox counter = ((row0 + r)*S + j, t): row0 is the global index of the first row (row sharding), t the
+ * caller's draw counter.  Distributional parity with numpy's standard_gamma.  Does not synchronise.
+ */
+int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0, unsigned long long seed,
+                               unsigned long long t, float* T_out, void* stream);
+
 /* ---------------------------------------------------------------- episodic tensor builders --------------- */
 /*
  * colo_build_episodic_tensor -- get_episodic_transition_matrix_and_rewards (colosseum/mdp/utils/mdp_creation.py:98-128):
@@ -329,6 +357,13 @@ int colo_env_step_dense_f64(const colo_mdp_tables* tb, const colo_env_batch* bat
  */
 int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch, int mode, int n_steps,
                           unsigned long long t0, int auto_reset, void* stream);
+/*
+ * colo_emit_observations -- EmissionMap.get_observation (colosseum/emission_maps/base.py:110-140) for every env: the
+ * row of the precomputed table all_observations (:56-76; f32 [H,S,D] episodic, [S,D] continuous with H = 0) at
+ * (h[e], state[e]); zeros for an env whose last TimeStep was LAST (in_episode_time >= H, :131-132).  out f32 [N,D].
+ */
+int colo_emit_observations(const float* table, const int* state, const int* h, const unsigned char* step_type,
+                           long long N, int H, int S, int D, float* out, void* stream);
 int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
                        const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
                        void* stream);

@@ -653,3 +653,96 @@ void orc_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int ou
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * extended value iteration (UCRL2): colosseum/dynamic_programming/infinite_horizon.py:67-118 and _max_proba :222-251,
+ * restated loop for loop.  Types as numba infers them: T, estimated rewards, u1, u2, p2, Q, V are float32; beta_r,
+ * beta_p, min1, s, s2, max1, r_optimal, v are float64; np.dot(vec, u1) of two float32 vectors is float32 (accumulated
+ * here in index order).  argsort ties are broken by index (numpy's quicksort leaves them unspecified).
+ * Returns ORC_OK with *span = ptp(u1), or ORC_MAX_ITER.
+ */
+static const float* g_sort_key;
+static int cmp_idx(const void* a, const void* b) {
+  int ia = *(const int*)a, ib = *(const int*)b;
+  float ka = g_sort_key[ia], kb = g_sort_key[ib];
+  if (ka < kb) return -1;
+  if (ka > kb) return 1;
+  return ia - ib;
+}
+
+int orc_extended_vi_f32(const float* T, const float* est, const double* beta_r, const double* beta_p, int S, int A,
+                        double r_max, double eps, long long max_iter, float* Q, float* V, double* span,
+                        long long* iters) {
+  float* u1 = (float*)calloc((size_t)S, sizeof(float));
+  float* u2 = (float*)calloc((size_t)S, sizeof(float));
+  float* p2 = (float*)calloc((size_t)S, sizeof(float));
+  int* sorted = (int*)malloc((size_t)S * sizeof(int));
+  for (int i = 0; i < S; ++i) sorted[i] = i;
+  int rc = ORC_MAX_ITER;
+  long long it = 0;
+  for (; it < max_iter; ++it) {
+    for (int s = 0; s < S; ++s) {
+      float qmax = -INFINITY;
+      for (int a = 0; a < A; ++a) {
+        const float* p = T + ((size_t)s * A + a) * S;
+        const double beta = beta_p[(size_t)s * A + a];
+        const int best = sorted[S - 1];
+        /* _max_proba */
+        double min1 = p[best] + beta / 2;
+        if (min1 > 1.0) min1 = 1.0;
+        for (int j = 0; j < S; ++j) p2[j] = 0.f;
+        if (min1 == 1.0) {
+          p2[best] = 1.f;
+        } else {
+          for (int j = 0; j < S; ++j) p2[j] = p[j]; /* p2[support_p] = restricted_sorted_p */
+          p2[best] = (float)min1;
+          double sm = 1.0 - p[best] + min1, s2 = sm;
+          for (int j = 0; j < S; ++j) {
+            int id = sorted[j];
+            float proba = p[id];
+            if (proba == 0.f) continue; /* only the support is visited */
+            double max1 = 1.0 - sm + proba;
+            if (max1 < 0.0) max1 = 0.0;
+            s2 += max1 - proba;
+            p2[id] = (float)max1;
+            sm = s2;
+            if (sm <= 1.0) break;
+          }
+        }
+        p2[s] -= 1.f; /* vec[s] -= 1 */
+        double r_opt = (double)est[(size_t)s * A + a] + beta_r[(size_t)s * A + a];
+        if ((double)(float)r_max < r_opt) r_opt = (double)(float)r_max;
+        float dot = 0.f;
+        for (int j = 0; j < S; ++j) dot += p2[j] * u1[j];
+        double v = r_opt + (double)dot;
+        Q[(size_t)s * A + a] = (float)v;
+        if (a == 0 || v + u1[s] > u2[s] || fabs(v + u1[s] - u2[s]) < eps) u2[s] = (float)(v + u1[s]);
+        if ((float)v > qmax) qmax = (float)v;
+      }
+      V[s] = qmax;
+    }
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = 0; i < S; ++i) {
+      float d = u2[i] - u1[i];
+      if (d < lo) lo = d;
+      if (d > hi) hi = d;
+    }
+    if ((double)(hi - lo) < eps) {
+      float ulo = INFINITY, uhi = -INFINITY;
+      for (int i = 0; i < S; ++i) {
+        if (u1[i] < ulo) ulo = u1[i];
+        if (u1[i] > uhi) uhi = u1[i];
+      }
+      *span = (double)(uhi - ulo);
+      rc = ORC_OK;
+      ++it;
+      break;
+    }
+    float* t = u1; u1 = u2; u2 = t;
+    g_sort_key = u1;
+    qsort(sorted, (size_t)S, sizeof(int), cmp_idx);
+  }
+  if (iters) *iters = it;
+  free(u1); free(u2); free(p2); free(sorted);
+  return rc;
+}

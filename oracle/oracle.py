@@ -313,3 +313,20 @@ def continuous_form(H, T, R, start_idx, start_prob, nodes):
             for ns in np.nonzero((T[s] > 0).any(0))[0]:
                 T_cf[i, :, index[(h + 1, int(ns))]] = T[s, :, ns]
     return T_cf, R_cf
+
+
+# ---------------------------------------------------------------------------------------------- extended VI (UCRL2)
+def extended_vi_f32(T, est, beta_r, beta_p, r_max, eps=1e-3, max_iter=int(1e6)):
+    """infinite_horizon.py:67-118 + _max_proba :222-251, restated loop for loop in C.  Returns (span, Q, V, iters) | None."""
+    T, est = _f32(T), _f32(est)
+    S, A, _ = T.shape
+    br = np.ascontiguousarray(beta_r, np.float64).reshape(S, A)
+    bp = np.asarray(beta_p, np.float64)
+    bp = np.ascontiguousarray(bp[..., 0] if bp.ndim == 3 else bp).reshape(S, A)
+    Q = np.zeros((S, A), np.float32)
+    V = np.zeros(S, np.float32)
+    span = C.c_double(0)
+    it = C.c_longlong(0)
+    rc = lib().orc_extended_vi_f32(_p(T), _p(est), _p(br), _p(bp), S, A, C.c_double(r_max), C.c_double(eps),
+                                   C.c_longlong(max_iter), _p(Q), _p(V), C.byref(span), C.byref(it))
+    return None if rc == MAX_ITER else (span.value, Q, V, it.value)

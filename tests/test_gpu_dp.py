@@ -212,3 +212,32 @@ def test_get_policy_from_q_values(dp):
     assert X.shape == Q.shape and (X.sum(-1) == 1).all() and (Q[np.arange(3), X.argmax(-1)] == Q.max(-1)).all()
     X3 = dp.get_policy_from_q_values(np.stack([Q, Q]), True)
     assert X3.shape == (2, 3, 3)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_extended_value_iteration(dp, precision):
+    """UCRL2's optimistic VI (infinite_horizon.py:67-118 + _max_proba) vs the reference's own numba run (goldens) and
+    the oracle; same synchronous iterates, so the bar is the stopping tolerance itself"""
+    import os
+
+    from conftest import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "evi.npz"))
+    for i in range(int(g["n_cases"])):
+        args = (g[f"P_{i}"], g[f"est_{i}"], g[f"beta_r_{i}"], g[f"beta_p_{i}"], 1.0)
+        for tag, eps in (("loose", 1e-3), ("tight", 1e-5)):
+            span, Q, V, it = dp.extended_value_iteration(*args, eps, precision=precision, return_iterations=True)
+            so, Qo, Vo, ito = orc.extended_vi_f32(*args, eps)
+            assert Q.dtype == (np.float64 if precision == "f64" else np.float32) and Q.shape == Qo.shape
+            assert abs(it - ito) <= 1 + ito // 50
+            for ref_span, ref_Q, ref_V in ((so, Qo, Vo), (float(g[f"span_{i}_{tag}"]), g[f"Q_{i}_{tag}"], g[f"V_{i}_{tag}"])):
+                assert abs(span - ref_span) < 2 * eps + 1e-5
+                np.testing.assert_allclose(Q, ref_Q, atol=2 * eps + 3e-6)
+                np.testing.assert_allclose(V, ref_V, atol=2 * eps + 3e-6)
+    # [S,A,S]-shaped beta_p: only element 0 of the last axis is read (:230); iteration cap -> None
+    bp3 = np.repeat(g["beta_p_0"], g["P_0"].shape[0], axis=2) * np.linspace(1, 2, g["P_0"].shape[0])
+    r1 = dp.extended_value_iteration(g["P_0"], g["est_0"], g["beta_r_0"], bp3, 1.0, 1e-3, precision=precision)
+    r2 = dp.extended_value_iteration(g["P_0"], g["est_0"], g["beta_r_0"], g["beta_p_0"], 1.0, 1e-3, precision=precision)
+    assert r1[0] == r2[0] and np.array_equal(r1[1], r2[1])
+    assert dp.extended_value_iteration(g["P_0"], g["est_0"], g["beta_r_0"], g["beta_p_0"], 1.0, 1e-9, precision=precision,
+                                       max_iter=3) is None

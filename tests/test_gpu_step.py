@@ -337,3 +337,24 @@ def test_fused_random_steps_equal_single_steps(bm, name, mode):
     if tb.H > 0:
         with pytest.raises(AssertionError):
             b.random_steps_fused(tb.H + 2, auto_reset=False)
+
+
+@pytest.mark.parametrize("name", ["c1_riverswim_epi", "doc_simplegrid4"])
+def test_emission_table_gather(bm, name):
+    """non-tabular observations: rows of all_observations[h, s] (emission_maps/base.py:56-76,110-140), zeros at LAST"""
+    tb = MDPTables.from_golden(load_instance(name))
+    N = 777
+    env = bm.BatchedMDP(tb, N, mode="succ", seed=2)
+    rs = np.random.RandomState(0)
+    shape = (3, 5)
+    table = rs.normal(size=((tb.H, tb.S) if tb.H else (tb.S,)) + shape).astype(np.float32)
+    env.set_emission_table(table)
+    env.reset()
+    for _ in range(2 * max(tb.H, 3)):
+        env.step_async(None, auto_reset=True)
+        obs = env.emit_observations().cpu().numpy()
+        s, h, st = env.state.cpu().numpy(), env.h.cpu().numpy(), env.step_type.cpu().numpy()
+        exp = table[h.clip(max=max(tb.H - 1, 0)), s] if tb.H else table[s]
+        if tb.H:
+            exp = np.where((st == 2)[:, None, None], 0.0, exp)
+        assert obs.shape == (N,) + shape and np.array_equal(obs, exp.astype(np.float32))

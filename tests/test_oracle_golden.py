@@ -249,3 +249,16 @@ def test_episodic_tensor_forms_restatement(name):
     assert set(zip(*np.nonzero(reach))) == set(zip(g["reach_h"].tolist(), g["reach_s"].tolist()))
     T_cf, R_cf = orc.continuous_form(H, g["T"], g["R"], g["start_idx"], g["start_prob"], zip(g["reach_h"], g["reach_s"]))
     assert np.array_equal(T_cf, g["T_cf"]) and np.array_equal(R_cf, g["R_cf"])
+
+
+def test_extended_value_iteration_restatement():
+    """oracle restatement of UCRL2's extended VI (infinite_horizon.py:67-118, :222-251) vs the reference's numba run"""
+    g = np.load(os.path.join(GOLDEN, "evi.npz"))
+    for i in range(int(g["n_cases"])):
+        for tag, eps in (("loose", 1e-3), ("tight", 1e-5)):
+            span, Q, V, it = orc.extended_vi_f32(g[f"P_{i}"], g[f"est_{i}"], g[f"beta_r_{i}"], g[f"beta_p_{i}"], 1.0, eps)
+            # same float32 iterates; only the order of the float32 dot product may differ from numba's BLAS call, so
+            # the stopping iteration can move by one: differences stay below eps
+            assert abs(span - float(g[f"span_{i}_{tag}"])) < 2 * eps + 1e-5, (i, tag)
+            np.testing.assert_allclose(Q, g[f"Q_{i}_{tag}"], atol=2 * eps + 2e-6)
+            np.testing.assert_allclose(V, g[f"V_{i}_{tag}"], atol=2 * eps + 2e-6)
