@@ -287,6 +287,36 @@ __global__ void fill_kernel(TV* x, long long n, TV v) {
 }
 
 template <typename TV>
+__global__ void normalize_resid_kernel(TV* __restrict__ x_new, const TV* __restrict__ x_old, int S,
+                                       typename VecOf<TV>::resid_t* __restrict__ resid) {
+  // single CTA: x_new /= sum(x_new); resid[0] = max|x_new - x_old| (power iteration on a distribution)
+  using resid_t = typename VecOf<TV>::resid_t;
+  __shared__ double sm[32];
+  __shared__ double s_tot;
+  double part = 0.0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) part += (double)x_new[i];
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    s_tot = t;
+  }
+  __syncthreads();
+  const TV inv = (TV)(1.0 / s_tot);
+  TV d = 0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const TV v = x_new[i] * inv;
+    x_new[i] = v;
+    const TV dd = fabs(v - x_old[i]);
+    d = dd > d ? dd : d;
+  }
+  d = warp_max(d);
+  if ((threadIdx.x & 31) == 0 && d > (TV)0) atomic_max_nonneg(reinterpret_cast<resid_t*>(resid), d);
+}
+
+template <typename TV>
 __global__ void max_reduce_kernel(const TV* x, long long n, TV* out, int take_sqrt) {
   // single-CTA deterministic max (n is small: S or K*S)
   __shared__ TV sm[32];
@@ -432,9 +462,12 @@ static SolveWork carve(void* work, long long B, long long S) {
 template <typename TV, typename SweepFn>
 static int iterate_to_convergence(SweepFn sweep, TV* V_user, SolveWork& w, long long B, long long S, TV eps,
                                   long long max_iter, long long* iters_out_host, long long* sweeps_run,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const TV* V0 = nullptr) {
   using resid_t = typename VecOf<TV>::resid_t;
-  COLO_CUDA_TRY(cudaMemsetAsync(V_user, 0, (size_t)B * S * sizeof(TV), st));
+  if (V0 != nullptr && V0 != V_user)
+    COLO_CUDA_TRY(cudaMemcpyAsync(V_user, V0, (size_t)B * S * sizeof(TV), cudaMemcpyDeviceToDevice, st));
+  else if (V0 == nullptr)
+    COLO_CUDA_TRY(cudaMemsetAsync(V_user, 0, (size_t)B * S * sizeof(TV), st));
   COLO_CUDA_TRY(cudaMemsetAsync(w.resid, 0, (size_t)B * sizeof(resid_t), st));
   COLO_CUDA_TRY(cudaMemsetAsync(w.active, 1, (size_t)B, st));
   COLO_CUDA_TRY(cudaMemsetAsync(w.iters, 0, (size_t)B * sizeof(long long), st));
@@ -484,7 +517,7 @@ static int iterate_to_convergence(SweepFn sweep, TV* V_user, SolveWork& w, long 
 template <typename TV>
 int solve_discounted(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma, double eps,
                      double max_abs, long long max_iter, int fold, TV* Q, TV* V, long long* iters_out_host,
-                     void* work, void* stream) {
+                     void* work, void* stream, const TV* V0 = nullptr, bool normalize = false) {
   COLO_ARG_CHECK(T && R && V && work, "T, R, V, work are required");
   cudaStream_t st = (cudaStream_t)stream;
   SolveWork w = carve<TV>(work, B, S);
@@ -496,21 +529,28 @@ int solve_discounted(const float* T, const float* R, const float* pi, int B, int
     int rs = sparse_rows_build(T, (long long)B * S * A, S, A, &sp, stream);
     if (rs != COLO_OK) return rs;
     if (sp.kmax > 0 && sparse_vi_fits_one_cta(S, sizeof(TV) == 8)) {
-      rs = sparse_solve_resident<TV>(sp, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_out_host, stream);
+      rs = sparse_solve_resident<TV>(sp, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_out_host, stream,
+                                     V0, normalize);
       sparse_rows_free(&sp, stream);
       return rs;
     }
   }
   if (sp.kmax > 0) {
     auto sweep = [&](TV* cur, TV* nxt) {
-      return sparse_sweep_launch<TV>(sp, R, pi, B, S, A, fold, gamma, cur, nxt, Q, w.resid, w.active, max_abs, w.flags + 1,
-                                     stream);
+      int r = sparse_sweep_launch<TV>(sp, R, pi, B, S, A, fold, gamma, cur, nxt, Q, normalize ? nullptr : w.resid, w.active,
+                                      max_abs, w.flags + 1, stream);
+      if (r == COLO_OK && normalize) {
+        normalize_resid_kernel<TV><<<1, 1024, 0, st>>>(nxt, cur, S, (typename VecOf<TV>::resid_t*)w.resid);
+        r = check_launch("normalize_resid_kernel");
+      }
+      return r;
     };
-    const int rc = iterate_to_convergence<TV>(sweep, V, w, B, S, (TV)eps, max_iter, iters_out_host, nullptr, st);
+    const int rc = iterate_to_convergence<TV>(sweep, V, w, B, S, (TV)eps, max_iter, iters_out_host, nullptr, st, V0);
     sparse_rows_free(&sp, stream);
     return rc;
   }
-  if (resident_enabled() && resident_fits_any(S, A, 1, sizeof(TV) == 8, nullptr)) {
+  COLO_ARG_CHECK(!normalize || B == 1, "normalize needs B == 1");
+  if (V0 == nullptr && !normalize && resident_enabled() && resident_fits_any(S, A, 1, sizeof(TV) == 8, nullptr)) {
     // small MDPs: the whole solve is ONE launch of the on-chip resident solver (resident.cu)
     colo_resident_args ra = {};
     ra.T = T; ra.R = R; ra.pi = pi; ra.V = V; ra.Q = Q;
@@ -537,14 +577,19 @@ int solve_discounted(const float* T, const float* R, const float* pi, int B, int
   a.B = B; a.S = S; a.A = A; a.fold = fold; a.gamma = gamma;
   a.t_stride = (long long)S * A * S; a.r_stride = (long long)S * A; a.pi_stride = (long long)S * A;
   a.v_in_stride = S; a.v_out_stride = S; a.q_stride = (long long)S * A;
-  a.resid = w.resid; a.active = w.active; a.max_abs = max_abs; a.overflow_flag = w.flags + 1;
+  a.resid = normalize ? nullptr : w.resid; a.active = w.active; a.max_abs = max_abs; a.overflow_flag = w.flags + 1;
   a.row0 = 0; a.nrows = S;
   auto sweep = [&](TV* cur, TV* nxt) {
     a.V_in = cur;
     a.V_out = nxt;
-    return launch_backup<TV>(&a, stream);
+    int r = launch_backup<TV>(&a, stream);
+    if (r == COLO_OK && normalize) {
+      normalize_resid_kernel<TV><<<1, 1024, 0, st>>>(nxt, cur, S, (typename VecOf<TV>::resid_t*)w.resid);
+      r = check_launch("normalize_resid_kernel");
+    }
+    return r;
   };
-  return iterate_to_convergence<TV>(sweep, V, w, B, S, (TV)eps, max_iter, iters_out_host, nullptr, st);
+  return iterate_to_convergence<TV>(sweep, V, w, B, S, (TV)eps, max_iter, iters_out_host, nullptr, st, V0);
 }
 
 template <typename TV>
@@ -878,6 +923,21 @@ int colo_solve_discounted_f64acc(const float* T, const float* R, const float* pi
                                  long long* iters_out_host, void* work, void* stream) {
   return colo::solve_discounted<double>(T, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_out_host,
                                         work, stream);
+}
+
+size_t colo_power_iteration_work_bytes(int S) {
+  return colo::solve_work_bytes<double>(1, S) + colo::align_up((size_t)S * sizeof(float), 256) + 256;
+}
+int colo_power_iteration_f64(const float* M, int S, const double* x0, double eps, long long max_iter, double* x,
+                             long long* iters_out_host, void* work, void* stream) {
+  // x <- M x from x0 until max|dx| < eps: the synchronous sweep of the backup family with one action, no reward and
+  // gamma = 1, so it runs on the same kernels (compressed rows on chip when M is sparse, streaming otherwise)
+  COLO_ARG_CHECK(M && x0 && x && work && S > 0, "M, x0, x, work, S");
+  float* zeros = (float*)work;
+  COLO_CUDA_TRY(cudaMemsetAsync(zeros, 0, (size_t)S * sizeof(float), (cudaStream_t)stream));
+  void* rest = (char*)work + colo::align_up((size_t)S * sizeof(float), 256);
+  return colo::solve_discounted<double>(M, zeros, nullptr, 1, S, 1, 1.0, eps, 0.0, max_iter, COLO_FOLD_MAX, nullptr, x,
+                                        iters_out_host, rest, stream, x0, true);
 }
 
 int colo_episodic_f32(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,

@@ -58,7 +58,7 @@ bool sparse_vi_fits_one_cta(int S, bool f64);
 template <typename TV>
 int sparse_solve_resident(const SparseRows& h, const float* R, const float* pi, int B, int S, int A, double gamma,
                           double eps, double max_abs, long long max_iter, int fold, TV* Q, TV* V,
-                          long long* iters_out_host, void* stream);
+                          long long* iters_out_host, void* stream, const TV* V0 = nullptr, bool normalize = false);
 template <typename TV>
 int sparse_sweep_launch(const SparseRows& h, const float* R, const float* pi, int B, int S, int A, int fold,
                         double gamma, const TV* V_in, TV* V_out, TV* Q, void* resid, const unsigned char* active,

@@ -340,6 +340,8 @@ struct SparseViArgs {
   long long max_iter;
   void* V;             // out [B][S]
   void* Q;             // out [B][S,A] or null
+  const void* V0;      // initial V [B][S] or null (zeros)
+  int normalize;       // != 0: V is rescaled to unit sum after every sweep (power iteration on a distribution)
   long long* iters;    // [B]
   int* status;         // [B]
 };
@@ -376,7 +378,8 @@ __global__ void __launch_bounds__(kSpThreads) sparse_vi_kernel(const SparseViArg
   const int S = p.S, A = p.A, kS = p.kmax * p.S;
   const int b = blockIdx.x;
   TV* Vs = reinterpret_cast<TV*>(smem_raw);  // [2][S]
-  for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) Vs[i] = TV(0);
+  const TV* V0 = p.V0 ? reinterpret_cast<const TV*>(p.V0) + (size_t)b * S : nullptr;
+  for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) Vs[i] = (V0 && i < S) ? V0[i] : TV(0);
   if (threadIdx.x == 0) s_overflow = 0;
   __syncthreads();
   const float* R = p.R + (size_t)b * S * A;
@@ -390,15 +393,38 @@ __global__ void __launch_bounds__(kSpThreads) sparse_vi_kernel(const SparseViArg
   TV* Qg = p.Q ? reinterpret_cast<TV*>(p.Q) + (size_t)b * S * A : nullptr;
   int cur = 0, status = COLO_MAX_ITER;
   long long it = 0;
+  __shared__ double s_part[kSpThreads / 32];
   while (true) {
     const TV* Vin = Vs + cur * S;
     TV* Vout = Vs + (cur ^ 1) * S;
     bool conv = true;
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      const TV folded = sparse_row_fold<TV, FOLD>(len, cv, R, pi, S, A, kS, s, gamma, Vin, nullptr);
-      conv = conv && ((float)fabs(folded - Vin[s]) < p.eps);
-      if (check_max && fabs(folded) > max_abs) s_overflow = 1;
-      Vout[s] = folded;
+    if (!p.normalize) {
+      for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const TV folded = sparse_row_fold<TV, FOLD>(len, cv, R, pi, S, A, kS, s, gamma, Vin, nullptr);
+        conv = conv && ((float)fabs(folded - Vin[s]) < p.eps);
+        if (check_max && fabs(folded) > max_abs) s_overflow = 1;
+        Vout[s] = folded;
+      }
+    } else {
+      // x <- M x / |M x|_1: rows of a float32 matrix sum to 1 +- 1e-7, so the raw iteration drifts; the rescaled one
+      // has the Perron vector as its fixed point and the stopping rule compares rescaled iterates
+      double part = 0.0;
+      for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const TV folded = sparse_row_fold<TV, FOLD>(len, cv, R, pi, S, A, kS, s, gamma, Vin, nullptr);
+        Vout[s] = folded;
+        part += (double)folded;
+      }
+      part = warp_sum(part);
+      if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+      __syncthreads();
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+      const TV inv = (TV)(1.0 / tot);
+      for (int s = threadIdx.x; s < S; s += blockDim.x) {  // each thread rescales the entries it wrote
+        const TV x = Vout[s] * inv;
+        conv = conv && ((float)fabs(x - Vin[s]) < p.eps);
+        Vout[s] = x;
+      }
     }
     const int all_conv = __syncthreads_and(conv);
     ++it;
@@ -407,7 +433,10 @@ __global__ void __launch_bounds__(kSpThreads) sparse_vi_kernel(const SparseViArg
     if (it >= p.max_iter) { status = COLO_MAX_ITER; break; }
     cur ^= 1;
   }
-  if (status != COLO_OVERFLOW) {
+  if (p.normalize) {
+    const TV* Vlast = Vs + (cur ^ 1) * S;  // the rescaled iterate of the stopping sweep
+    for (int s = threadIdx.x; s < S; s += blockDim.x) Vg[s] = Vlast[s];
+  } else if (status != COLO_OVERFLOW) {
     // the stopping sweep is redone from the same V_in, storing the Q and V it produced (the reference returns those)
     const TV* Vin = Vs + cur * S;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
@@ -668,7 +697,7 @@ bool sparse_vi_fits_one_cta(int S, bool f64) {
 template <typename TV>
 int sparse_solve_resident(const SparseRows& h, const float* R, const float* pi, int B, int S, int A, double gamma,
                           double eps, double max_abs, long long max_iter, int fold, TV* Q, TV* V,
-                          long long* iters_out_host, void* stream) {
+                          long long* iters_out_host, void* stream, const TV* V0, bool normalize) {
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)2 * S * sizeof(TV);
   long long* d_it = nullptr;
@@ -677,7 +706,8 @@ int sparse_solve_resident(const SparseRows& h, const float* R, const float* pi, 
   COLO_CUDA_TRY(cudaMallocAsync(&d_st, (size_t)B * sizeof(int), st));
   SparseViArgs a = {};
   a.len = h.len; a.cv = (const int2*)h.cv; a.kmax = h.kmax; a.R = R; a.pi = pi; a.B = B; a.S = S; a.A = A;
-  a.gamma = gamma; a.eps = (float)eps; a.max_abs = max_abs; a.max_iter = max_iter; a.V = V; a.Q = Q;
+  a.gamma = gamma; a.eps = (float)eps; a.max_abs = max_abs; a.max_iter = max_iter; a.V = V; a.Q = Q; a.V0 = V0;
+  a.normalize = normalize ? 1 : 0;
   a.iters = d_it; a.status = d_st;
   const int threads = block_threads(S);
 #define COLO_SPVI(FOLD)                                                                                     \
@@ -729,9 +759,9 @@ int sparse_sweep_launch(const SparseRows& h, const float* R, const float* pi, in
 }
 
 template int sparse_solve_resident<float>(const SparseRows&, const float*, const float*, int, int, int, double, double,
-                                          double, long long, int, float*, float*, long long*, void*);
+                                          double, long long, int, float*, float*, long long*, void*, const float*, bool);
 template int sparse_solve_resident<double>(const SparseRows&, const float*, const float*, int, int, int, double, double,
-                                           double, long long, int, double*, double*, long long*, void*);
+                                           double, long long, int, double*, double*, long long*, void*, const double*, bool);
 template int sparse_sweep_launch<float>(const SparseRows&, const float*, const float*, int, int, int, int, double,
                                         const float*, float*, float*, void*, const unsigned char*, double, int*, void*);
 template int sparse_sweep_launch<double>(const SparseRows&, const float*, const float*, int, int, int, int, double,

@@ -17,6 +17,8 @@ import sys
 
 from . import dynamic_programming as _dp
 from . import hardness as _hd
+from . import indicators as _ind
+from . import markov_chain as _mc
 
 # (module that defines the original, attribute name) -> replacement
 REPLACEMENTS = {
@@ -30,6 +32,15 @@ REPLACEMENTS = {
     ("colosseum.hardness.measures.value_norm", "calculate_norm_discounted"): _hd.calculate_norm_discounted,
     ("colosseum.hardness.measures.sum_reciprocals_suboptimality_gaps", "get_sum_reciprocals_suboptimality_gaps"):
         _hd.get_sum_reciprocals_suboptimality_gaps,
+    # average-reward helpers (mdp/utils/markov_chain.py:12-137) and the episodic regret indicators
+    # (experiment/indicators.py:9-45; that package needs ray & co. to import: skipped when it cannot be imported)
+    ("colosseum.mdp.utils.markov_chain", "get_average_reward"): _mc.get_average_reward,
+    ("colosseum.mdp.utils.markov_chain", "get_average_rewards"): _mc.get_average_rewards,
+    ("colosseum.mdp.utils.markov_chain", "get_transition_probabilities"): _mc.get_transition_probabilities,
+    ("colosseum.mdp.utils.markov_chain", "get_stationary_distribution"): _mc.get_stationary_distribution,
+    ("colosseum.experiment.indicators", "get_episodic_regret_at_time_zero"): _ind.get_episodic_regret_at_time_zero,
+    ("colosseum.experiment.indicators", "get_episodic_regrets_and_average_reward_at_time_zero"):
+        _ind.get_episodic_regrets_and_average_reward_at_time_zero,
 }
 
 _saved = []  # (module, attribute, original object)
@@ -44,7 +55,10 @@ def install(prefix="colosseum"):
     for (mod_name, attr), repl in REPLACEMENTS.items():
         mod = sys.modules.get(mod_name)
         if mod is None:
-            __import__(mod_name)
+            try:
+                __import__(mod_name)
+            except Exception:  # optional parts of the reference whose own dependencies are absent
+                continue
             mod = sys.modules[mod_name]
         originals[id(getattr(mod, attr))] = repl
     for name, mod in list(sys.modules.items()):

@@ -235,6 +235,36 @@ int colo_extended_vi_f64acc(const float* T, const float* est_rewards, const doub
 int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0, unsigned long long seed,
                                unsigned long long t, float* T_out, void* stream);
 
+/* ---------------------------------------------------------------- policy-induced Markov chain -------------- */
+/*
+ * colo_policy_chain -- get_transition_probabilities / get_average_rewards (colosseum/mdp/utils/markov_chain.py:34-51):
+ *   P_out[s,j] = min(1, sum_a T[s,a,j] pi[s,a]) f32 [S,S];  r_out[s] = sum_a R[s,a] pi[s,a] f32 [S] (or NULL).
+ * colo_lazy_transpose -- M_out[j,s] = (P[s,j] + (s == j)) / 2: the matrix of the lazy chain, transposed so that the
+ *   distribution update x <- M x is a row-times-vector product.
+ * colo_power_iteration_f64 -- x <- M x / |M x|_1 from x0 until max|dx| < eps (fp64 accumulation; runs on the backup
+ *   kernels: compressed rows on chip when M is sparse).  A building block for WELL-MIXING chains only: on nearly
+ *   reducible chains the per-step change falls below any eps long before the limit is reached -- use
+ *   colo_stationary_distribution_f64.  Synchronises.  Returns COLO_MAX_ITER after max_iter sweeps.
+ *   work: colo_power_iteration_work_bytes(S).
+ */
+int colo_policy_chain(const float* T, const float* R, const float* pi, int S, int A, float* P_out, float* r_out,
+                      void* stream);
+/*
+ * colo_stationary_distribution_f64 -- get_stationary_distribution (markov_chain.py:64-137): x_out = x0 * lim L^(2^k),
+ * L = (I + P)/2, by repeated squaring in fp64 (rows rescaled to unit sum after every product) until max|L^(2^(k+1)) -
+ * L^(2^k)| < tol or max_squarings products.  Exact limit of the start distribution x0 for every chain: with one
+ * recurrent class THE stationary distribution; with several, their mixture by absorption probabilities (the reference
+ * assigns each start state to the first class it can reach).  Synchronises.  work: colo_stationary_distribution_
+ * work_bytes(S) (two S x S fp64 matrices).
+ */
+size_t colo_stationary_distribution_work_bytes(int S);
+int colo_stationary_distribution_f64(const float* P, int S, const double* x0, double tol, int max_squarings,
+                                     double* x_out, int* squarings_out_host, void* work, void* stream);
+int colo_lazy_transpose(const float* P, int S, float* M_out, void* stream);
+size_t colo_power_iteration_work_bytes(int S);
+int colo_power_iteration_f64(const float* M, int S, const double* x0, double eps, long long max_iter, double* x,
+                             long long* iters_out_host, void* work, void* stream);
+
 /* ---------------------------------------------------------------- episodic tensor builders --------------- */
 /*
  * colo_build_episodic_tensor -- get_episodic_transition_matrix_and_rewards (colosseum/mdp/utils/mdp_creation.py:98-128):

@@ -330,3 +330,26 @@ def extended_vi_f32(T, est, beta_r, beta_p, r_max, eps=1e-3, max_iter=int(1e6)):
     rc = lib().orc_extended_vi_f32(_p(T), _p(est), _p(br), _p(bp), S, A, C.c_double(r_max), C.c_double(eps),
                                    C.c_longlong(max_iter), _p(Q), _p(V), C.byref(span), C.byref(it))
     return None if rc == MAX_ITER else (span.value, Q, V, it.value)
+
+
+# ---------------------------------------------------------------------------------------------- policy Markov chain
+def policy_chain(T, R, pi):
+    """markov_chain.py:34-51: (min(1, einsum('saj,sa->sj', T, pi)), einsum('sa,sa->s', R, pi))"""
+    T, R, pi = _f32(T), _f32(R), _f32(pi)
+    return np.minimum(1.0, np.einsum("saj,sa->sj", T, pi)), np.einsum("sa,sa->s", R, pi)
+
+
+def stationary_distribution_f64(P, x0, tol=1e-14, max_iter=int(1e7)):
+    """limit of x0 under the lazy chain (I + P)/2 in fp64 (repeated squaring of the matrix: log2(n) products) --
+    for a chain with one recurrent class this is THE stationary distribution of markov_chain.py:64-137"""
+    M = 0.5 * (np.eye(len(P)) + np.asarray(P, np.float64))
+    M = M / M.sum(-1, keepdims=True)
+    for _ in range(200):
+        M2 = M @ M
+        M2 = M2 / M2.sum(-1, keepdims=True)  # rows of a float32 T sum to 1 +- 1e-7: keep the powers stochastic
+        if np.abs(M2 - M).max() < tol:
+            M = M2
+            break
+        M = M2
+    x = np.asarray(x0, np.float64) @ M
+    return x / x.sum()

@@ -1,0 +1,94 @@
+"""GPU: the policy-induced Markov chain, its stationary distribution and the average-reward / regret indicators
+(colosseum/mdp/utils/markov_chain.py:12-137, colosseum/experiment/indicators.py:9-45) against values recorded from
+the unmodified reference (tests/golden/avg_reward.npz: the notebook's 0.99599 / 0.004008 / 0.5 among them)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_instance
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(GOLDEN, "avg_reward.npz"))
+
+
+def test_average_reward_against_reference(g):
+    import colosseum_b200.markov_chain as mc
+
+    for name in g["names"]:
+        T, R = g[f"{name}_T"], g[f"{name}_R"]
+        starts = list(zip(g[f"{name}_start_idx"].tolist(), g[f"{name}_start_prob"].tolist()))
+        for k in ("opt", "worst", "rand"):
+            pi = g[f"{name}_{k}_pi"]
+            tps = mc.get_transition_probabilities(T, pi)
+            assert tps.dtype == np.float32
+            np.testing.assert_allclose(tps, g[f"{name}_{k}_tps"], rtol=2e-7, atol=1e-9)
+            np.testing.assert_allclose(mc.get_average_rewards(R, pi), g[f"{name}_{k}_rs"], rtol=1e-6, atol=1e-9)
+            Po, ro = orc.policy_chain(T, R, pi)
+            x0 = np.zeros(len(T)); x0[g[f"{name}_start_idx"]] = g[f"{name}_start_prob"]
+            sd = mc.get_stationary_distribution(tps, starts)
+            sd_o = orc.stationary_distribution_f64(Po, x0)
+            assert abs(sd.sum() - 1) < 1e-9 and sd.min() > -1e-15
+            np.testing.assert_allclose(sd, sd_o, atol=2e-8)
+            ar = mc.get_average_reward(T, R, pi, starts)
+            assert abs(ar - float((sd_o * ro).sum())) < 1e-8
+            # the reference (networkx recurrent classes + GTH, partly float32): identical when the chain has ONE
+            # recurrent class; with several the reference assigns each start state to the first class it can reach
+            ref_sd = g[f"{name}_{k}_sd"]
+            one_class = np.abs(ref_sd - sd_o).max() < 1e-5
+            if one_class:
+                assert abs(ar - float(g[f"{name}_{k}_ar"])) < 2e-6 * max(1.0, abs(ar)), (name, k)
+            else:
+                assert k == "worst", (name, k)  # only adversarial policies split the chain
+
+
+def test_notebook_average_rewards(g):
+    """docs/_sources/mds/mdp-functionalities.ipynb:2369-2411"""
+    import colosseum_b200.markov_chain as mc
+
+    name = "doc_simplegrid4"
+    T, R = g[f"{name}_T"], g[f"{name}_R"]
+    starts = list(zip(g[f"{name}_start_idx"].tolist(), g[f"{name}_start_prob"].tolist()))
+    for k, doc in (("opt", 0.9959919693746492), ("worst", 0.004008056365342812), ("rand", 0.5000000148429536)):
+        assert abs(mc.get_average_reward(T, R, g[f"{name}_{k}_pi"], starts) - doc) < 2e-6
+
+
+def test_episodic_regret_indicators():
+    """experiment/indicators.py:9-45 on a golden episodic instance: GPU PE/VI vs the oracle"""
+    import colosseum_b200.indicators as ind
+
+    gi = load_instance("frozenlake4_epi")
+    T, R, H = gi["T"], gi["R"], int(gi["H"])
+    S, A = R.shape
+    rs = np.random.RandomState(0)
+    pol = rs.dirichlet(np.ones(A), size=(H, S)).astype(np.float32)
+    start = np.zeros(S); start[gi["start_idx"]] = gi["start_prob"]
+    reg, avg = ind.get_episodic_regrets_and_average_reward_at_time_zero(H, T, R, pol, start)
+    _, Vp = orc.episodic_f64(H, T, R, pi=pol)
+    _, Vs = orc.episodic_f64(H, T, R)
+    np.testing.assert_allclose(reg, np.maximum(Vs[0] - Vp[0], 0), atol=2e-5)
+    assert abs(avg - float((Vp[0] * start).sum())) < 2e-5
+    np.testing.assert_allclose(ind.get_episodic_regret_at_time_zero(H, T, R, pol), Vs[0] - Vp[0], atol=2e-5)
+    np.testing.assert_allclose(ind.get_episodic_regret_at_time_zero(H, T, R, pol, gi["vi_V"]), gi["vi_V"][0] - Vp[0], atol=2e-5)
+
+
+def test_power_iteration_building_block(g):
+    """colo_power_iteration_f64 (x <- M x / |M x| on the backup kernels, sparse on-chip and dense streaming paths) on
+    well-mixing chains; and the documented failure mode on a nearly reducible one (why squaring is the default)"""
+    import colosseum_b200.markov_chain as mc
+
+    for name, k in (("deepsea10_prand", "rand"), ("frozenlake5", "rand"), ("doc_simplegrid4", "rand"), ("minigrid6", "opt")):
+        tps = g[f"{name}_{k}_tps"]
+        x0 = np.zeros(len(tps)); x0[g[f"{name}_start_idx"]] = g[f"{name}_start_prob"]
+        x, it = mc.power_iteration(tps, x0, tol=1e-12)
+        assert it > 10 and abs(x.sum() - 1) < 1e-12
+        np.testing.assert_allclose(x, orc.stationary_distribution_f64(tps, x0), atol=1e-7)
+    tps = g["doc_simplegrid4_opt_tps"]
+    x0 = np.zeros(len(tps)); x0[g["doc_simplegrid4_start_idx"]] = g["doc_simplegrid4_start_prob"]
+    x, it = mc.power_iteration(tps, x0, tol=1e-8)  # stops "converged" ...
+    assert np.abs(x - orc.stationary_distribution_f64(tps, x0)).max() > 0.1  # ... far from the limit
