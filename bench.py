@@ -29,6 +29,12 @@ sys.path.insert(0, ROOT)
 C2_INSTANCE = "c2_deepsea30_prand"
 C2_ENVS_PER_GPU = 65536
 STEP_BYTES = lambda S: 4 * S + 28  # dense CDF row + 28 B of state I/O per env-step
+
+
+def c2_workload(S, A, N):
+    """the one description of the headline workload both arms put in config.workload"""
+    return (f"C2 DeepSeaContinuous(size=30,p_rand=0.1) S={S} A={A}, {N} envs per GPU, batched step by inverse-CDF over the "
+            "dense CDF row, auto-reset, visitation counts on")
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -289,7 +295,15 @@ def bench_c5_gpu(args, rank, world):
         transport = "none (1 GPU)"
     else:
         transport = args.c5_transport
-        vi = RowShardedValueIteration(T_rows, R_rows, S, gamma=0.99, transport=transport)
+        try:
+            vi = RowShardedValueIteration(T_rows, R_rows, S, gamma=0.99, transport=transport)
+            vi.sweep(1)
+        except Exception as e:  # symmetric memory unavailable on this box: the NCCL all-gather does the same exchange
+            if transport == "nccl":
+                raise
+            print(f"[bench] fused V exchange unavailable ({type(e).__name__}: {e}); using nccl", file=sys.stderr)
+            transport = "nccl (fused unavailable)"
+            vi = RowShardedValueIteration(T_rows, R_rows, S, gamma=0.99, transport="nccl")
     lib = _cabi.lib()
     steps = max(5, min(args.steps, 100))
     vi.sweep(3)
@@ -423,9 +437,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2 DeepSeaContinuous(size=30,p_rand=0.1) S={tb.S} A={tb.A}, {N} envs, dense-CDF "
-                               "inverse-CDF step, random actions, auto-reset, visitation counts on",
-                   "where": "host CPU cores (reference algorithm; the reference has no GPU path)"},
+        "config": {"workload": c2_workload(tb.S, tb.A, N),
+                   "where": "host CPU cores (reference algorithm, C+OpenMP port; the reference has no GPU path); random "
+                            "actions and uniforms from the same Philox stream as the GPU arm"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} batched steps of {N} envs, C+OpenMP oracle port of "
                                    "BaseMDP.step/NextStateSampler.sample"},
@@ -556,9 +570,8 @@ def main():
         line.update({
             "metric": "batched env-steps/sec", "value": world * N / sec, "unit": "env-steps/s", "steps": args.steps,
             "ms_per_step": 1e3 * sec, "gpu_launches": step["launches"],
-            "config": {"workload": f"C2 DeepSeaContinuous(size=30,p_rand=0.1) S={tb.S} A={tb.A}, {N} envs per GPU, "
-                                   "dense-CDF warp-cooperative inverse-CDF step, supplied actions, in-kernel Philox "
-                                   "uniforms, auto-reset, visitation counts on",
+            "config": {"workload": c2_workload(tb.S, tb.A, N),
+                       "kernel": "warp-cooperative search of the dense CDF row, supplied actions, in-kernel Philox uniforms",
                        "l2": "flushed between timed steps (256 MiB write), each step timed with its own CUDA events"},
             "e2e": {"value": world * N * args.steps / (step["e2e_ms"] / 1e3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": step["h2d"], "d2h_bytes_per_step": step["d2h"],
