@@ -130,6 +130,7 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
