@@ -12,6 +12,7 @@
 // loads, all issued before any is consumed, and because the row is monotone the bisect position is simply the
 // COUNT of entries <= x, i.e. one integer warp reduction, no branches and no early exit.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -485,6 +486,8 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
 static int make_io(const colo_mdp_tables* tb, const colo_env_batch* b, int random_actions, const void* u_next,
                    const float* u_rew, unsigned long long t, int auto_reset, colo::StepIO* io) {
   COLO_ARG_CHECK(b != nullptr, "batch is NULL");
+  memset(io, 0, sizeof(*io));
+  if (b->N == 0) return COLO_OK;  // an empty batch has no buffers to check: every entry point returns COLO_OK
   COLO_ARG_CHECK(b->N >= 0 && b->state && b->h && b->step_type && b->obs, "env buffers");
   const int copies = b->visits_copies <= 0 ? 1 : b->visits_copies;
   COLO_ARG_CHECK((copies & (copies - 1)) == 0, "visits_copies must be a power of two");
@@ -506,8 +509,7 @@ int colo_env_reset(const colo_mdp_tables* tb, const colo_env_batch* batch, const
   if (r != COLO_OK) return r;
   colo::StepIO io;
   r = make_io(tb, batch, 0, u_next, nullptr, t, 0, &io);
-  if (r != COLO_OK) return r;
-  if (io.N == 0) return COLO_OK;
+  if (r != COLO_OK || io.N == 0) return r;
   const int grid = colo::grid_for(colo::kStepThreads, io.N);
   colo::env_reset_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
   return colo::check_launch("env_reset_kernel");
@@ -520,7 +522,7 @@ int colo_env_step_dense_f32(const colo_mdp_tables* tb, const colo_env_batch* bat
   if (r != COLO_OK) return r;
   colo::StepIO io;
   r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
-  if (r != COLO_OK) return r;
+  if (r != COLO_OK || io.N == 0) return r;
   return colo::launch_dense<float>(tb, io, stream);
 }
 
@@ -531,7 +533,7 @@ int colo_env_step_dense_f64(const colo_mdp_tables* tb, const colo_env_batch* bat
   if (r != COLO_OK) return r;
   colo::StepIO io;
   r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
-  if (r != COLO_OK) return r;
+  if (r != COLO_OK || io.N == 0) return r;
   return colo::launch_dense<double>(tb, io, stream);
 }
 
@@ -542,7 +544,7 @@ int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, i
   if (r != COLO_OK) return r;
   colo::StepIO io;
   r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
-  if (r != COLO_OK) return r;
+  if (r != COLO_OK || io.N == 0) return r;
   COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
   COLO_ARG_CHECK(io.reward && io.action, "env buffers");
   if (io.N == 0) return COLO_OK;
@@ -558,7 +560,7 @@ int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch
   COLO_ARG_CHECK(n_steps >= 1 && mode >= 0 && mode <= 2, "n_steps >= 1, mode in {0,1,2}");
   colo::StepIO io;
   r = make_io(tb, batch, 1, nullptr, nullptr, t0, auto_reset, &io);
-  if (r != COLO_OK) return r;
+  if (r != COLO_OK || io.N == 0) return r;
   io.n_steps = n_steps;
   if (mode == 0) return colo::launch_dense<float>(tb, io, stream);
   if (mode == 1) return colo::launch_dense<double>(tb, io, stream);
