@@ -112,6 +112,8 @@ PROTOTYPES = {
     "colo_value_norm_work_bytes": (C.c_size_t, [_I, _I, _I]),
     "colo_value_norm_f32": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "colo_value_norm_f64acc": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "colo_bias_series_work_bytes": (C.c_size_t, [_I]),
+    "colo_bias_series_f64": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "colo_gaps_f64": (_I, [_P, _P, _P, _LL, _I, _D, _P, _P]),
     "colo_env_reset": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _P, _ULL, _P]),
     "colo_env_step_dense_f32": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),

@@ -286,6 +286,24 @@ __global__ void fill_kernel(TV* x, long long n, TV v) {
   if (i < n) x[i] = v;
 }
 
+__global__ void cast_f32_f64_kernel(const float* __restrict__ x, double* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (double)x[i];
+}
+__global__ void bias_init_kernel(const float* __restrict__ r, const double* __restrict__ gain, double* __restrict__ v,
+                                 double* __restrict__ h, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double d = (double)r[i] - gain[i];
+    v[i] = d;
+    h[i] = d;  // the i = 0 term: P^0 (r - gain)
+  }
+}
+__global__ void axpy_kernel(const double* __restrict__ x, double* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+
 template <typename TV>
 __global__ void normalize_resid_kernel(TV* __restrict__ x_new, const TV* __restrict__ x_old, int S,
                                        typename VecOf<TV>::resid_t* __restrict__ resid) {
@@ -938,6 +956,51 @@ int colo_power_iteration_f64(const float* M, int S, const double* x0, double eps
   void* rest = (char*)work + colo::align_up((size_t)S * sizeof(float), 256);
   return colo::solve_discounted<double>(M, zeros, nullptr, 1, S, 1, 1.0, eps, 0.0, max_iter, COLO_FOLD_MAX, nullptr, x,
                                         iters_out_host, rest, stream, x0, true);
+}
+
+size_t colo_bias_series_work_bytes(int S) { return (size_t)4 * colo::align_up((size_t)S * sizeof(double), 256) + 256; }
+int colo_bias_series_f64(const float* P, const float* avg_rewards, int S, int steps, double* h_out, void* work,
+                         void* stream) {
+  // _calculate_gain / _calculate_bias (colosseum/hardness/measures/value_norm.py:64-82):
+  //   gain = P^steps r;  h = sum_{i < steps} P^i (r - gain)  -- 2*steps matrix-vector products on the backup kernel
+  COLO_ARG_CHECK(P && avg_rewards && h_out && work && S > 0 && steps > 0, "P, avg_rewards, h_out, work, S, steps");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t stride = colo::align_up((size_t)S * sizeof(double), 256) / sizeof(double);
+  double* a = (double*)work;
+  double* b = a + stride;
+  double* gain = b + stride;
+  double* c = gain + stride;
+  colo_backup_args g = {};
+  g.T = P; g.B = 1; g.S = S; g.A = 1; g.fold = COLO_FOLD_MAX; g.gamma = 1.0; g.r_const = 0.0;
+  g.t_stride = (long long)S * S; g.v_in_stride = S; g.v_out_stride = S; g.row0 = 0; g.nrows = S;
+  colo::cast_f32_f64_kernel<<<(S + 255) / 256, 256, 0, st>>>(avg_rewards, a, S);
+  int r = colo::check_launch("cast_f32_f64_kernel");
+  if (r != COLO_OK) return r;
+  double* cur = a;
+  double* nxt = b;
+  for (int i = 0; i < steps; ++i) {  // gain = P^steps r
+    g.V_in = cur; g.V_out = nxt;
+    r = colo::launch_backup<double>(&g, stream);
+    if (r != COLO_OK) return r;
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  COLO_CUDA_TRY(cudaMemcpyAsync(gain, cur, (size_t)S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  // v_0 = r - gain; h = sum_i v_i; v_{i+1} = P v_i
+  colo::bias_init_kernel<<<(S + 255) / 256, 256, 0, st>>>(avg_rewards, gain, a, h_out, S);
+  r = colo::check_launch("bias_init_kernel");
+  if (r != COLO_OK) return r;
+  cur = a; nxt = b;
+  for (int i = 1; i < steps; ++i) {
+    g.V_in = cur; g.V_out = nxt;
+    r = colo::launch_backup<double>(&g, stream);
+    if (r != COLO_OK) return r;
+    colo::axpy_kernel<<<(S + 255) / 256, 256, 0, st>>>(nxt, h_out, S);
+    r = colo::check_launch("axpy_kernel");
+    if (r != COLO_OK) return r;
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  (void)c;
+  return COLO_OK;
 }
 
 int colo_episodic_f32(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,

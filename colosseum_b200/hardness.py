@@ -77,6 +77,22 @@ def calculate_norm_discounted(T, V, *, precision="f64"):
     return float(out.item())
 
 
+def calculate_norm_average(T, tps, average_rewards, steps=1000):
+    """colosseum/hardness/measures/value_norm.py:90-93 (with _calculate_bias :69-82): the undiscounted environmental
+    value norm, i.e. the norm of :85-87 taken of the bias vector h = sum_{i<steps} P^i (r - P^steps r)."""
+    torch = _torch()
+    Td, Pd = to_device(T), to_device(tps)
+    rd = to_device(average_rewards).reshape(-1)
+    S, A, _ = Td.shape
+    lib = _cabi.lib()
+    h = torch.empty(S, dtype=torch.float64, device="cuda")
+    work = _scratch(lib.colo_bias_series_work_bytes(S))
+    rc = lib.colo_bias_series_f64(_cabi.ptr(Pd), _cabi.ptr(rd), S, int(steps), _cabi.ptr(h), _cabi.ptr(work),
+                                  _cabi.current_stream())
+    _cabi.check(rc, "colo_bias_series_f64")
+    return calculate_norm_discounted(Td, h, precision="f64")
+
+
 def get_sum_reciprocals_suboptimality_gaps(Q, V, reachable_states=None, regularization=0.1):
     """colosseum/hardness/measures/sum_reciprocals_suboptimality_gaps.py:6-28."""
     torch = _torch()

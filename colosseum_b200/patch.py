@@ -30,6 +30,7 @@ REPLACEMENTS = {
     ("colosseum.dynamic_programming.infinite_horizon", "extended_value_iteration"): _dp.extended_value_iteration,
     ("colosseum.hardness.measures.diameter", "get_diameter"): _hd.get_diameter,
     ("colosseum.hardness.measures.value_norm", "calculate_norm_discounted"): _hd.calculate_norm_discounted,
+    ("colosseum.hardness.measures.value_norm", "calculate_norm_average"): _hd.calculate_norm_average,
     ("colosseum.hardness.measures.sum_reciprocals_suboptimality_gaps", "get_sum_reciprocals_suboptimality_gaps"):
         _hd.get_sum_reciprocals_suboptimality_gaps,
     # average-reward helpers (mdp/utils/markov_chain.py:12-137) and the episodic regret indicators

@@ -204,6 +204,16 @@ int colo_value_norm_f64acc(const float* T, const double* V, int S, int A, void* 
  *   out[0] = sum_{n<NS, a<A, mask[n]} 1 / (V[n] - Q[n,a] + reg)     (mask may be NULL = all; episodic callers
  * pass NS=(H+1)*S rows and the reachable (h,s) mask).  Deterministic fp64 reduction (fixed order).
  */
+/*
+ * colo_bias_series_f64 -- _calculate_gain / _calculate_bias (colosseum/hardness/measures/value_norm.py:64-82), the
+ * vector the UNDISCOUNTED value norm (calculate_norm_average, :90-93) is taken of:  gain = P^steps r,
+ * h = sum_{i < steps} P^i (r - gain), P f32 [S,S] the chain of the policy (colo_policy_chain), r f32 [S] its average
+ * rewards.  fp64 accumulation (the reference mixes float32 matrix_power and float64 sums; its 60 s wall-clock cut-off of
+ * the series is not reproduced).  The norm itself is colo_value_norm_f64acc(T, h).  Does not synchronise.
+ */
+size_t colo_bias_series_work_bytes(int S);
+int colo_bias_series_f64(const float* P, const float* avg_rewards, int S, int steps, double* h_out, void* work,
+                         void* stream);
 int colo_gaps_f64(const double* Q, const double* V, const unsigned char* mask, long long NS, int A, double reg,
                   double* out, void* stream);
 

@@ -47,7 +47,8 @@ def main():
         out[f"{name}_opt_ar"] = float(mdp.optimal_average_reward)
         out[f"{name}_worst_ar"] = float(mdp.worst_average_reward)
         out[f"{name}_rand_ar"] = float(mdp.random_average_reward)
-        print(name, T.shape, out[f"{name}_opt_ar"], out[f"{name}_worst_ar"], out[f"{name}_rand_ar"])
+        out[f"{name}_undisc_norm"] = float(mdp.undiscounted_value_norm)  # hardness/measures/value_norm.py:64-93
+        print(name, T.shape, out[f"{name}_opt_ar"], out[f"{name}_worst_ar"], out[f"{name}_rand_ar"], out[f"{name}_undisc_norm"])
     np.savez_compressed(os.path.join(HERE, "avg_reward.npz"), **out)
 
 

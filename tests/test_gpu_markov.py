@@ -92,3 +92,29 @@ def test_power_iteration_building_block(g):
     x0 = np.zeros(len(tps)); x0[g["doc_simplegrid4_start_idx"]] = g["doc_simplegrid4_start_prob"]
     x, it = mc.power_iteration(tps, x0, tol=1e-8)  # stops "converged" ...
     assert np.abs(x - orc.stationary_distribution_f64(tps, x0)).max() > 0.1  # ... far from the limit
+
+
+def test_undiscounted_value_norm(g):
+    """calculate_norm_average (hardness/measures/value_norm.py:64-93) vs a numpy fp64 restatement of the same two
+    series (1e-9) and vs mdp.undiscounted_value_norm of the reference.  The reference takes the gain from a FLOAT32
+    np.linalg.matrix_power(tps, 1000) (:64-66) and sums 1000 terms of (r - gain): a float32 error d in the gain shifts
+    the bias by ~1000*d, which on the nearly reducible chain of SimpleGrid's optimal policy moves its own result by
+    0.6 % (0.50131 vs 0.49848 in fp64).  Hence 2e-2 against the reference, and the fp64 restatement as the real bar."""
+    import colosseum_b200.hardness as hd
+    import colosseum_b200.markov_chain as mc
+
+    for name in g["names"]:
+        T, R, pi = g[f"{name}_T"], g[f"{name}_R"], g[f"{name}_opt_pi"]
+        tps = mc.get_transition_probabilities(T, pi)
+        ars = mc.get_average_rewards(R, pi)
+        got = hd.calculate_norm_average(T, tps, ars)
+        P = tps.astype(np.float64); r = ars.astype(np.float64)
+        gain = np.linalg.matrix_power(P, 1000) @ r
+        h = np.zeros(len(P)); v = r - gain
+        for _ in range(1000):
+            h += v; v = P @ v
+        T64 = T.astype(np.float64)
+        Eh = np.einsum("iaj,j->ia", T64, h)
+        exp = np.sqrt(np.einsum("iaj,ja->ia", T64, (h.reshape(-1, 1) - Eh) ** 2)).max()
+        assert abs(got - exp) < 1e-9 * max(1.0, exp), (name, got, exp)
+        assert abs(got - float(g[f"{name}_undisc_norm"])) < 2e-2 * max(1.0, exp), (name, got, float(g[f"{name}_undisc_norm"]))
