@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_lib", "libcolosseum_b200.so")
+LIB_PATH = os.environ.get("COLO_B200_LIB") or os.path.join(_PKG, "_lib", "libcolosseum_b200.so")  # env: kernel-variant probes only
 
 OK, OVERFLOW, MAX_ITER, NEEDS_RESET = 0, 1, 2, 3
 FOLD_MAX, FOLD_PI, FOLD_MIN = 0, 1, 2

@@ -127,7 +127,10 @@ __device__ __forceinline__ void rows_dot(const float* __restrict__ Trow, const T
 
 // GROUP_CTA == false: one warp per (instance, state); GROUP_CTA == true: one CTA per (instance, state).
 template <typename TV, int FOLD, bool VEC, bool GROUP_CTA>
-__global__ void __launch_bounds__(kThreads) backup_kernel(const colo_backup_args p) {
+#ifndef COLO_BACKUP_MIN_BLOCKS
+#define COLO_BACKUP_MIN_BLOCKS 3  // measured on B200 (C4): 2 -> 90.6 %, 3 -> 99.5 %, 4 -> 95.6 % of the HBM peak (85 regs, 24 warps/SM)
+#endif
+__global__ void __launch_bounds__(kThreads, COLO_BACKUP_MIN_BLOCKS) backup_kernel(const colo_backup_args p) {
   using resid_t = typename VecOf<TV>::resid_t;
   __shared__ TV s_part[kWarps][kAT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
