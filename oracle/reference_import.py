@@ -40,7 +40,16 @@ def import_reference():
             _exc = types.ModuleType("numpy.core._exceptions")
             _exc._ArrayMemoryError = MemoryError
         sys.modules["numpy.core._exceptions"] = _exc
-    import colosseum  # noqa: E402
+    # importing the reference copies its hardness cache (3,007 files) and creates `tmp/` in the CURRENT directory
+    # (colosseum/config.py:255-270): do the import from a scratch directory so nothing lands in the repository
+    import tempfile
+
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="colosseum_ref_"))
+    try:
+        import colosseum  # noqa: E402
+    finally:
+        os.chdir(cwd)
 
     colosseum.config.disable_multiprocessing()
     colosseum.config.VERBOSE_LEVEL = 0
