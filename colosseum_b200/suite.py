@@ -159,3 +159,33 @@ def run_instance(inst: SuiteInstance, n_envs=1024, n_steps=1000, seed=0, mode="s
     res["visits_total"] = total
     res["mean_reward_last_step"] = float(torch.nan_to_num(env.reward, nan=0.0).mean().item())
     return res, {"step_s": t1 - t0, "hardness_s": t2 - t1}
+
+
+def run_many(work, n_workers=4, **kw):
+    """Run C3 work items `work` = [(SuiteInstance, seed), ...] on the current device with `n_workers` host threads, each
+    on its own CUDA stream.  The instances are independent (no communication), and a single one
+    keeps only a few SMs busy -- the on-chip solvers give one CTA (or one CTA per few targets) to an MDP with a few
+    hundred states -- so several instances in flight fill the GPU; the C ABI is stream-ordered and releases the GIL
+    while it waits.  Returns the list of (results, timings) in the order of `work`."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    dev = torch.cuda.current_device()
+    local = threading.local()
+
+    def one(item):
+        inst, seed = item
+        if not hasattr(local, "stream"):
+            torch.cuda.set_device(dev)
+            local.stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(local.stream):
+            out = run_instance(inst, seed=seed, **kw)
+            local.stream.synchronize()
+        return out
+
+    if n_workers <= 1:
+        return [one(w) for w in work]
+    with ThreadPoolExecutor(max_workers=n_workers) as pool:
+        return list(pool.map(one, work))

@@ -116,3 +116,16 @@ def test_suite_step_phase(suite):
             chi2 = ((cnt[live] - sel.sum() * p[live] / p[live].sum()) ** 2 / (sel.sum() * p[live] / p[live].sum())).sum()
             assert scipy.stats.chi2.sf(chi2, live.sum() - 1) > 1e-5, (inst.name, chi2)
     assert len(seen) >= 10
+
+
+@pytest.mark.gpu
+def test_concurrent_instances_match_sequential(suite):
+    """run_many: several instances in flight (host threads, one stream each) == the same instances one after another"""
+    from colosseum_b200.suite import run_many
+
+    work = [(suite[i], 100 + i) for i in (1, 12, 19, 40, 42, 53, 54, 62)]
+    seq = run_many(work, n_workers=1, n_envs=256, n_steps=50)
+    par = run_many(work, n_workers=4, n_envs=256, n_steps=50)
+    for (a, _), (b, _) in zip(seq, par):
+        for k in ("gaps", "value_norm", "diameter", "visits_total", "mean_reward_last_step"):
+            assert a[k] == b[k] or (np.isnan(a[k]) and np.isnan(b[k])), k
