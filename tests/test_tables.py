@@ -95,3 +95,35 @@ def test_patch_rebinds_reference_names():
     finally:
         assert patch.uninstall() == n
     assert ref_base.get_diameter is orig
+
+
+@pytest.mark.reference
+def test_patched_reference_fails_loudly_without_gpu():
+    """with the GPU path installed behind the reference's names there is NO fallback: on a box without a CUDA device
+    the reference's own properties raise instead of silently running numba"""
+    import torch
+
+    from oracle.reference_import import import_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    import_reference()
+    from colosseum.mdp.river_swim import RiverSwimContinuous
+
+    import colosseum_b200.patch as patch
+    from colosseum_b200._cabi import ColosseumB200Error
+
+    n = patch.install()  # BEFORE constructing MDPs: an MDP object binds its DP function at construction (base.py:476-480)
+    try:
+        assert n > 0
+        mdp = RiverSwimContinuous(seed=0, size=6)
+        with pytest.raises(ColosseumB200Error):
+            mdp.optimal_value_functions
+        with pytest.raises(ColosseumB200Error):
+            mdp.diameter
+    finally:
+        patch.uninstall()
+    mdp = RiverSwimContinuous(seed=0, size=6)
+    assert mdp.optimal_value_functions[1].shape == (6,)  # restored: the reference's numba path again
