@@ -143,8 +143,11 @@ int colo_resident_solve_f64acc(const colo_resident_args* args, void* stream);
  * COLO_MAX_ITER after max_iter sweeps (:142).  fold = COLO_FOLD_MAX (VI) or COLO_FOLD_PI (PE, pi [B,S,A]).
  * Synchronises the stream (the host needs the convergence flags).  iters_out_host[b] = sweeps run by b (or NULL).
  * work: device scratch of colo_solve_work_bytes(B,S,f64) bytes.  Q may be NULL.
- * Small MDPs (colo_resident_fits) are solved by the resident solver in one launch, larger ones by one streaming
- * backup launch per sweep; same algorithm (synchronous sweeps) and stopping rule either way.
+ * The kernel is chosen from the tensor itself, never by a flag: T with sparse rows (<= 256 non-zeros and <= 1/8 of a
+ * row: the benchmark families, continuous forms) is compressed on the device and solved on chip in one launch
+ * (S <= 2048) or with one compressed-row launch per sweep; small dense MDPs (colo_resident_fits) go to the resident
+ * cluster solver in one launch; everything else streams T from HBM, one backup launch per sweep.  Same algorithm
+ * (synchronous sweeps), same stopping rule, same results up to the summation order inside a row.
  */
 size_t colo_solve_work_bytes(long long B, long long S, int f64);
 int colo_solve_discounted_f32(const float* T, const float* R, const float* pi, int B, int S, int A, float gamma,
@@ -168,8 +171,11 @@ int colo_episodic_f64acc(const float* T, const float* R, const float* pi, int B,
 /*
  * Continuous diameter (colosseum/hardness/measures/diameter.py:20-39,76-106; == :321-346 at the fixed point):
  * multi-target hitting-time iteration  E[k,s] = (s == target[k]) ? 0 : min_a(1 + sum_j T[s,a,j] E[k,j])  over the
- * K given targets at once (all S for the full diameter), one launch per sweep, each target frozen as soon as its
- * own max|dE| < eps.  out_host[0] = max_k max_s E, out_host[1] = sweeps run.  COLO_OVERFLOW if a hitting time
+ * K given targets at once (all S for the full diameter), every target (tile of targets) iterated until its own
+ * max|dE| < eps.  Sparse rows: compressed rows, a few targets per CTA with E in shared memory, the whole solve in one
+ * launch; dense T that fits a cluster's shared memory: resident solver, 4 targets per cluster; otherwise one tiled
+ * GEMM launch per sweep (>= 128^2 (target, state) pairs) or one streaming backup launch per sweep.
+ * out_host[0] = max_k max_s E, out_host[1] = sweeps run (max over targets).  COLO_OVERFLOW if a hitting time
  * exceeds max_value (>0).  Synchronises.  work: colo_diameter_continuous_work_bytes(K,S,f64) device bytes.
  */
 size_t colo_diameter_continuous_work_bytes(int K, int S, int f64);
