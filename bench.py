@@ -111,10 +111,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def load_c2_tables():
+def load_c2_tables(instance=C2_INSTANCE):
     from colosseum_b200.tables import MDPTables
 
-    g = np.load(os.path.join(ROOT, "tests", "golden", f"inst_{C2_INSTANCE}.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"inst_{instance}.npz"))
     return MDPTables.from_golden(g)
 
 
@@ -195,6 +195,31 @@ def bench_step_gpu(args, rank, world):
     ms = max_over_ranks(ms, world)
     assert int(env.status.item()) == 0
 
+    # ---- secondary: SURVEY section 8d asks for C2 with p_rand=None too (deterministic rows, 1 non-zero): same kernel,
+    # same protocol, fewer steps
+    det = None
+    try:
+        tbd = load_c2_tables("c2_deepsea30")
+        envd = BatchedMDP(tbd, N, mode="dense_f32", seed=1234, env_offset=rank * N)
+        envd.reset()
+        nd = max(20, min(args.steps, 100))
+        for i in range(5):
+            flush.zero_()
+            envd.step_async(actions[i % n_act], auto_reset=True)
+        barrier_sync(world)
+        ds = [torch.cuda.Event(enable_timing=True) for _ in range(nd)]
+        de = [torch.cuda.Event(enable_timing=True) for _ in range(nd)]
+        for i in range(nd):
+            flush.zero_()
+            ds[i].record()
+            envd.step_async(actions[i % n_act], auto_reset=True)
+            de[i].record()
+        barrier_sync(world)
+        det = dict(ms=max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(ds, de)), world), steps=nd)
+        del envd
+    except Exception as e:
+        det = dict(error=f"{type(e).__name__}: {e}")
+
     # ---- secondary: back-to-back kernel throughput.  The per-step event pair above has a floor of ~10 us on B200
     # (measured with a 32-env launch), i.e. most of the 14 us is launch + event latency, not the kernel.  Here the steps
     # of NB independent env batches (each with its own tables; together larger than L2, so no flush is needed) are
@@ -250,7 +275,7 @@ def bench_step_gpu(args, rank, world):
     barrier_sync(world)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
     assert int(env_h.status.item()) == 0 and int(env_h.step_type_host.max()) <= 2
-    return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N, b2b=b2b)
+    return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N, b2b=b2b, det=det)
 
 
 def make_c4_batch(B, S, A, seed):
@@ -624,6 +649,13 @@ def main():
                          "note": "T (1.8 MB) is L2/L1-resident by construction in C2: algorithmic bytes are served "
                                  "on chip, so frac can exceed 1; see DESIGN.md and `traffic`"},
         })
+        det = step.get("det") or {}
+        if "ms" in det:
+            line["p_rand_none"] = {"value": world * N * det["steps"] / (det["ms"] / 1e3), "unit": "env-steps/s",
+                                   "steps": det["steps"],
+                                   "what": "same kernel and protocol on DeepSeaContinuous(size=30, p_rand=None): deterministic rows"}
+        elif "error" in det:
+            line["p_rand_none"] = {"error": det["error"]}
         b2b = step.get("b2b") or {}
         if "ms" in b2b:
             sec_b = b2b["ms"] / 1e3 / b2b["steps"]
