@@ -330,10 +330,21 @@ def bench_vi_gpu(args, rank, world):
     solve_ms = max_over_ranks(e0.elapsed_time(e1), world)
     iters = dp.last_iterations()
     assert bool(torch.isfinite(V).all())
-    del T, R, Q, V
+    # the same solve with the reference's own in-place (Gauss-Seidel) sweeps: one warp per MDP, one launch
+    dp.discounted_value_iteration(T[:8], R[:8], 0.99, 1e-3, sweep_order="gauss_seidel")
+    barrier_sync(world)
+    e0.record()
+    Qg, Vg = dp.discounted_value_iteration(T, R, 0.99, 1e-3, sweep_order="gauss_seidel")
+    e1.record()
+    barrier_sync(world)
+    gs_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    gs_iters = dp.last_iterations()
+    assert bool(torch.isfinite(Vg).all()) and float((Vg - V).abs().max()) < 0.2  # both within eps*gamma/(1-gamma) of V*
+    del T, R, Q, V, Qg, Vg
     torch.cuda.empty_cache()
     return dict(B=B, S=S, A=A, steps=steps, ms=ms, launches=launches, solve_ms=solve_ms, solve_sweeps_max=max(iters),
-                solve_sweeps_mean=float(np.mean(iters)))
+                solve_sweeps_mean=float(np.mean(iters)), gs_ms=gs_ms, gs_sweeps_max=max(gs_iters),
+                gs_sweeps_mean=float(np.mean(gs_iters)))
 
 
 def bench_c5_gpu(args, rank, world):
@@ -619,6 +630,12 @@ def main():
                              "mdp_solves_per_s": world * vi["B"] / (vi["solve_ms"] / 1e3),
                              "what": "dp.discounted_value_iteration(T, R, 0.99, 1e-3) on the whole batch, device "
                                      "tensors in/out, per-instance stopping on the device"},
+            "solve_to_eps_gauss_seidel": {
+                "epsilon": 1e-3, "seconds": vi["gs_ms"] / 1e3, "sweeps_max": vi["gs_sweeps_max"],
+                "sweeps_mean": vi["gs_sweeps_mean"], "mdp_solves_per_s": world * vi["B"] / (vi["gs_ms"] / 1e3),
+                "t_stream_gbs": vi["gs_sweeps_mean"] * 4 * vi["S"] * vi["A"] * vi["S"] * vi["B"] / (vi["gs_ms"] / 1e3) / 1e9,
+                "what": "the same solve with sweep_order='gauss_seidel': the reference's own in-place iterate "
+                        "(infinite_horizon.py:131-135), one warp per MDP, the whole solve in one launch"},
             "config": {"workload": f"C4: {world * vi['B']} synthetic Dirichlet(0.05) MDPs ({vi['B']} per GPU), S=512 A=4 fp32, "
                                    "gamma=0.99, one synchronous sweep of the whole batch per step, Q stored",
                        "l2": f"batch T = {vi['B'] * 4 * 512 * 4 * 512 / 2**30:.1f} GiB per GPU >> 126 MB L2, no flush"},

@@ -1,0 +1,184 @@
+// gauss_seidel.cu -- the reference's own iterate of discounted VI / PE: in-place (Gauss-Seidel) sweeps.
+//
+//   colosseum/dynamic_programming/infinite_horizon.py:121-142   _discounted_value_iteration
+//   colosseum/dynamic_programming/infinite_horizon.py:167-184   _discounted_policy_evaluation
+//       for s in range(S):  Q[s] = R[s] + gamma * T[s] @ V;  V[s] = max(Q[s])  (or sum(Q[s] * pi[s]))   -- V updated IN PLACE
+//       stop when max|V_old - V| < epsilon after a sweep; return None as soon as |V[s]| > max_abs_value
+//
+// The streaming / resident / compressed-row solvers sweep synchronously (Jacobi): same fixed point, different
+// early-stopped iterates (0.05 absolute at the reference's default epsilon = 1e-3).  This kernel
+// reproduces the reference's iterate itself, for callers that want the numbers the reference returns at ITS stopping
+// sweep: the state loop is sequential by definition, so ONE WARP owns one MDP instance -- V lives in the warp's slice
+// of shared memory and is updated in place, the A row dot products of a state are lane-parallel (128-bit streaming
+// loads of T, V quads from shared memory) and folded with shuffles, and the whole solve (all sweeps, stopping rule,
+// overflow test) is one launch.  A batch of B instances runs B warps side by side: for large batches the kernel is
+// HBM bound like the Jacobi sweep (T is streamed once per sweep) and needs about half the sweeps.
+#include "common.cuh"
+
+namespace colo {
+
+struct GsArgs {
+  const float* T;   // [B][S,A,S]
+  const float* R;   // [B][S,A]
+  const float* pi;  // [B][S,A] or null
+  int B, S, A, fold, warps_per_cta;
+  double gamma, eps, max_abs;
+  long long max_iter;
+  void* V;          // out [B][S]
+  void* Q;          // out [B][S,A]
+  long long* iters; // [B]
+  int* status;      // [B]
+};
+
+template <typename TV>
+__device__ __forceinline__ void lds_v4(const TV* p, TV (&v)[4]);
+template <>
+__device__ __forceinline__ void lds_v4<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void lds_v4<double>(const double* p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+constexpr int kGsAT = 4;  // actions held in registers at once
+
+template <typename TV, bool VEC>
+__global__ void __launch_bounds__(256) gs_solve_kernel(const GsArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = p.S, A = p.A;
+  const int Sp = (S + 3) & ~3;
+  const long long b = (long long)blockIdx.x * p.warps_per_cta + warp;
+  if (warp >= p.warps_per_cta || b >= p.B) return;  // warps are independent: no block-level barrier below
+  TV* Vs = reinterpret_cast<TV*>(smem_raw) + (size_t)warp * Sp;
+  for (int i = lane; i < Sp; i += 32) Vs[i] = TV(0);
+  __syncwarp();
+  const float* T = p.T + (size_t)b * S * A * S;
+  const float* R = p.R + (size_t)b * S * A;
+  const float* pi = p.pi ? p.pi + (size_t)b * S * A : nullptr;
+  TV* Qg = reinterpret_cast<TV*>(p.Q) + (size_t)b * S * A;
+  const TV gamma = (TV)p.gamma;
+  int status = COLO_MAX_ITER;
+  long long it = 0;
+  while (it < p.max_iter) {
+    TV res = 0;
+    bool overflow = false;
+    for (int s = 0; s < S && !overflow; ++s) {
+      const float* Trow = T + (size_t)s * A * S;
+      TV folded = p.fold == COLO_FOLD_MIN ? (TV)INFINITY : (p.fold == COLO_FOLD_MAX ? (TV)-INFINITY : (TV)0);
+      for (int a0 = 0; a0 < A; a0 += kGsAT) {
+        const int na = min(kGsAT, A - a0);
+        TV acc[kGsAT];
+#pragma unroll
+        for (int i = 0; i < kGsAT; ++i) acc[i] = TV(0);
+        if (VEC) {
+          const int S4 = S >> 2;
+          const float4* T4 = reinterpret_cast<const float4*>(Trow);
+          for (int j4 = lane; j4 < S4; j4 += 32) {
+            TV v[4];
+            lds_v4<TV>(Vs + 4 * j4, v);
+#pragma unroll
+            for (int i = 0; i < kGsAT; ++i)
+              if (i < na) {
+                const float4 t = ldg_stream4(T4 + (size_t)(a0 + i) * S4 + j4);
+                acc[i] += (TV)t.x * v[0] + (TV)t.y * v[1] + (TV)t.z * v[2] + (TV)t.w * v[3];
+              }
+          }
+        } else {
+          for (int j = lane; j < S; j += 32) {
+            const TV v = Vs[j];
+#pragma unroll
+            for (int i = 0; i < kGsAT; ++i)
+              if (i < na) acc[i] += (TV)ldg_stream1(Trow + (size_t)(a0 + i) * S + j) * v;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kGsAT; ++i) acc[i] = warp_sum(acc[i]);  // every lane holds the full sums
+#pragma unroll
+        for (int i = 0; i < kGsAT; ++i)
+          if (i < na) {
+            const int a = a0 + i;
+            const TV q = (TV)__ldg(R + (size_t)s * A + a) + gamma * acc[i];
+            if (lane == 0) Qg[(size_t)s * A + a] = q;  // the reference returns the Q rows of the stopping sweep
+            if (p.fold == COLO_FOLD_MAX) folded = q > folded ? q : folded;
+            if (p.fold == COLO_FOLD_MIN) folded = q < folded ? q : folded;
+            if (p.fold == COLO_FOLD_PI) folded += q * (TV)__ldg(pi + (size_t)s * A + a);
+          }
+      }
+      const TV d = fabs(folded - Vs[s]);
+      res = d > res ? d : res;
+      __syncwarp();  // all lanes have read V[s] of the previous sweep
+      if (lane == 0) Vs[s] = folded;  // in place: the following states of THIS sweep see it
+      __syncwarp();
+      if (p.max_abs > 0.0 && fabs((double)folded) > p.max_abs) overflow = true;  // infinite_horizon.py:136-138
+    }
+    ++it;
+    if (overflow) { status = COLO_OVERFLOW; break; }
+    if (res < (TV)p.eps) { status = COLO_OK; break; }  // :139-141
+  }
+  TV* Vg = reinterpret_cast<TV*>(p.V) + (size_t)b * S;
+  for (int i = lane; i < S; i += 32) Vg[i] = Vs[i];
+  if (lane == 0) {
+    p.iters[b] = it;
+    p.status[b] = status;
+  }
+}
+
+template <typename TV>
+int gs_solve(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma, double eps,
+             double max_abs, long long max_iter, int fold, TV* Q, TV* V, long long* iters_dev, int* status_dev,
+             void* stream) {
+  COLO_ARG_CHECK(T && R && Q && V && iters_dev && status_dev, "T, R, Q, V, iters, status are required");
+  COLO_ARG_CHECK(B >= 0 && S > 0 && A > 0 && fold >= 0 && fold <= 2 && (fold != COLO_FOLD_PI || pi), "B, S, A, fold, pi");
+  if (B == 0) return COLO_OK;
+  int dev = 0, max_smem = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) max_smem = 227 * 1024;
+  const size_t per_warp = (size_t)((S + 3) & ~3) * sizeof(TV);
+  if (per_warp > (size_t)max_smem) {
+    set_error("Gauss-Seidel solver: V of %d states does not fit shared memory", S);
+    return COLO_ERR_ARG;
+  }
+  int W = (int)((size_t)max_smem / 2 / per_warp);  // two CTAs per SM
+  W = W < 1 ? 1 : (W > 8 ? 8 : W);
+  if (B < W) W = B;
+  GsArgs a = {};
+  a.T = T; a.R = R; a.pi = pi; a.B = B; a.S = S; a.A = A; a.fold = fold; a.warps_per_cta = W;
+  a.gamma = gamma; a.eps = eps; a.max_abs = max_abs; a.max_iter = max_iter; a.V = V; a.Q = Q;
+  a.iters = iters_dev; a.status = status_dev;
+  const size_t smem = per_warp * W;
+  const bool vec = (S % 4 == 0) && ((uintptr_t)T % 16 == 0);
+  const int grid = (B + W - 1) / W;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) {
+    auto k = gs_solve_kernel<TV, true>;
+    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, W * 32, smem, st>>>(a);
+  } else {
+    auto k = gs_solve_kernel<TV, false>;
+    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, W * 32, smem, st>>>(a);
+  }
+  return check_launch("gs_solve_kernel");
+}
+
+}  // namespace colo
+
+extern "C" {
+
+int colo_solve_discounted_gs_f32(const float* T, const float* R, const float* pi, int B, int S, int A, float gamma,
+                                 float eps, float max_abs, long long max_iter, int fold, float* Q, float* V,
+                                 long long* iters_dev, int* status_dev, void* stream) {
+  return colo::gs_solve<float>(T, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_dev, status_dev, stream);
+}
+int colo_solve_discounted_gs_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma,
+                                    double eps, double max_abs, long long max_iter, int fold, double* Q, double* V,
+                                    long long* iters_dev, int* status_dev, void* stream) {
+  return colo::gs_solve<double>(T, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_dev, status_dev, stream);
+}
+
+}  // extern "C"

@@ -26,6 +26,8 @@ DP_MAX_ITERATION = int(1e6)
 ARGMAX_SEED = 42
 
 _PRECISION = "f32"  # the reference's arithmetic type; "f64" = fp64 accumulation / fp64 V,Q (1e-6 parity mode)
+_SWEEP_ORDER = "jacobi"  # "jacobi": synchronous sweeps (fast; fixed-point parity); "gauss_seidel": the reference's own
+#                          in-place iterate (its early-stopped numbers, one warp per instance)
 
 
 class DynamicProgrammingMaxIterationExceeded(Exception):
@@ -41,6 +43,18 @@ def set_precision(p):
 
 def get_precision():
     return _PRECISION
+
+
+def set_sweep_order(order):
+    """'jacobi' (default) or 'gauss_seidel' (the reference's in-place sweeps, infinite_horizon.py:131-135: the
+    discounted solvers then return the reference's early-stopped iterates instead of synchronous ones)."""
+    global _SWEEP_ORDER
+    assert order in ("jacobi", "gauss_seidel")
+    _SWEEP_ORDER = order
+
+
+def get_sweep_order():
+    return _SWEEP_ORDER
 
 
 def _torch():
@@ -82,8 +96,9 @@ def _scratch(nbytes):
 
 
 # ------------------------------------------------------------------------------------------------ discounted
-def _solve_discounted(T, R, pi, gamma, epsilon, max_abs_value, precision, max_iter=DP_MAX_ITERATION):
+def _solve_discounted(T, R, pi, gamma, epsilon, max_abs_value, precision, max_iter=DP_MAX_ITERATION, sweep_order=None):
     precision = precision or _PRECISION
+    sweep_order = sweep_order or _SWEEP_ORDER
     as_numpy = not _is_tensor(T)
     torch = _torch()
     Td, Rd, pid = to_device(T), to_device(R), to_device(pi)
@@ -102,13 +117,26 @@ def _solve_discounted(T, R, pi, gamma, epsilon, max_abs_value, precision, max_it
     work = _scratch(lib.colo_solve_work_bytes(B, S, int(f64)))
     iters = (C.c_longlong * B)()
     fold = FOLD_PI if pid is not None else FOLD_MAX
-    fn = lib.colo_solve_discounted_f64acc if f64 else lib.colo_solve_discounted_f32
     # gamma is cast to float32 first, as the reference does (infinite_horizon.py:127,171)
     g = float(np.float32(gamma))
-    rc = fn(_cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(pid), B, S, A, g, float(epsilon),
-            float(max_abs_value) if max_abs_value is not None else 0.0, int(max_iter), fold,
-            _cabi.ptr(Q), _cabi.ptr(V), iters, _cabi.ptr(work), _cabi.current_stream())
-    _cabi.check(rc, "colo_solve_discounted")
+    if sweep_order == "gauss_seidel":
+        it_d = torch.zeros(B, dtype=torch.int64, device="cuda")
+        st_d = torch.zeros(B, dtype=torch.int32, device="cuda")
+        fn = lib.colo_solve_discounted_gs_f64acc if f64 else lib.colo_solve_discounted_gs_f32
+        rc = fn(_cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(pid), B, S, A, g, float(epsilon),
+                float(max_abs_value) if max_abs_value is not None else 0.0, int(max_iter), fold,
+                _cabi.ptr(Q), _cabi.ptr(V), _cabi.ptr(it_d), _cabi.ptr(st_d), _cabi.current_stream())
+        _cabi.check(rc, "colo_solve_discounted_gs")
+        st_h = st_d.cpu().numpy()
+        for b, v in enumerate(it_d.cpu().numpy()):
+            iters[b] = int(v)
+        rc = _cabi.OVERFLOW if (st_h == _cabi.OVERFLOW).any() else (_cabi.MAX_ITER if (st_h == _cabi.MAX_ITER).any() else 0)
+    else:
+        fn = lib.colo_solve_discounted_f64acc if f64 else lib.colo_solve_discounted_f32
+        rc = fn(_cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(pid), B, S, A, g, float(epsilon),
+                float(max_abs_value) if max_abs_value is not None else 0.0, int(max_iter), fold,
+                _cabi.ptr(Q), _cabi.ptr(V), iters, _cabi.ptr(work), _cabi.current_stream())
+        _cabi.check(rc, "colo_solve_discounted")
     if rc == _cabi.OVERFLOW:
         return None
     if rc == _cabi.MAX_ITER:
@@ -130,18 +158,18 @@ def last_iterations():
 
 def discounted_value_iteration(T, R, gamma=0.99, epsilon=1e-3, max_abs_value=None,
                                sparse_n_states_threshold=300 * 3 * 300, sparse_nnz_per_threshold=0.2, *,
-                               precision=None):
+                               precision=None, sweep_order=None):
     """colosseum/dynamic_programming/infinite_horizon.py:14-44.  Returns (Q[S,A], V[S]) or None on overflow.
 
     The two `sparse_*` arguments select a pydata-sparse code path in the reference; the GPU path streams the dense
     tensor at HBM speed for every size, so they are accepted and ignored."""
-    return _solve_discounted(T, R, None, gamma, epsilon, max_abs_value, precision)
+    return _solve_discounted(T, R, None, gamma, epsilon, max_abs_value, precision, sweep_order=sweep_order)
 
 
 def discounted_policy_evaluation(T, R, pi, gamma=0.99, epsilon=1e-7, sparse_n_states_threshold=200,
-                                 sparse_nnz_per_threshold=0.2, *, precision=None):
+                                 sparse_nnz_per_threshold=0.2, *, precision=None, sweep_order=None):
     """colosseum/dynamic_programming/infinite_horizon.py:47-64.  Returns (Q[S,A], V[S])."""
-    return _solve_discounted(T, R, pi, gamma, epsilon, None, precision)
+    return _solve_discounted(T, R, pi, gamma, epsilon, None, precision, sweep_order=sweep_order)
 
 
 def discounted_policy_iteration(T, R, gamma=0.99, epsilon=1e-7, *, precision=None):

@@ -47,9 +47,13 @@ REPLACEMENTS = {
 _saved = []  # (module, attribute, original object)
 
 
-def install(prefix="colosseum"):
+def install(prefix="colosseum", reference_iterates=False):
     """Rebind the reference's hot-path entry points to the GPU implementations.  Returns the number of bindings
-    replaced.  Needs the reference package to be imported already (its modules are found in sys.modules)."""
+    replaced.  Needs the reference package to be imported already (its modules are found in sys.modules).
+    reference_iterates=True makes the discounted solvers sweep in place like the reference's numba kernels
+    (`dynamic_programming.set_sweep_order("gauss_seidel")`): they then return the reference's own early-stopped
+    iterates instead of synchronous ones (same fixed point)."""
+    _dp.set_sweep_order("gauss_seidel" if reference_iterates else "jacobi")
     if _saved:
         return len(_saved)
     originals = {}
@@ -76,6 +80,7 @@ def install(prefix="colosseum"):
 def uninstall():
     """Restore every binding `install()` replaced."""
     n = len(_saved)
+    _dp.set_sweep_order("jacobi")
     while _saved:
         mod, attr, obj = _saved.pop()
         setattr(mod, attr, obj)

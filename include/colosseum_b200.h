@@ -158,6 +158,21 @@ int colo_solve_discounted_f64acc(const float* T, const float* R, const float* pi
                                  double* V, long long* iters_out_host, void* work, void* stream);
 
 /*
+ * The reference's OWN iterate: in-place (Gauss-Seidel) sweeps, infinite_horizon.py:121-142 / :167-184 -- for s in
+ * range(S): Q[s] = R[s] + gamma T[s] @ V; V[s] = fold(Q[s]) with V updated in place; stop when max|V_old - V| < eps
+ * after a sweep; COLO_OVERFLOW as soon as |V[s]| > max_abs (> 0).  One warp per instance, V in shared memory, the
+ * whole solve in one launch (does not synchronise): status_dev[b] = COLO_OK / COLO_OVERFLOW / COLO_MAX_ITER and
+ * iters_dev[b] are DEVICE arrays.  Returns the reference's early-stopped (Q, V) up to the summation order of the
+ * row dot products (the colo_solve_discounted_* entry points sweep synchronously: same fixed point, other iterates).
+ */
+int colo_solve_discounted_gs_f32(const float* T, const float* R, const float* pi, int B, int S, int A, float gamma,
+                                 float eps, float max_abs, long long max_iter, int fold, float* Q, float* V,
+                                 long long* iters_dev, int* status_dev, void* stream);
+int colo_solve_discounted_gs_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma,
+                                    double eps, double max_abs, long long max_iter, int fold, double* Q, double* V,
+                                    long long* iters_dev, int* status_dev, void* stream);
+
+/*
  * Episodic backward induction for B MDPs (colosseum/dynamic_programming/finite_horizon.py:11-42):
  * Q[b,H]=0, V[b,H]=0; for h=H-1..0: Q[b,h]=R+T@V[b,h+1]; V[b,h]=fold(Q[b,h]) with pi[b,h] for PE
  * (pi is [B,H,S,A]).  Q is [B,H+1,S,A], V is [B,H+1,S].  max_value<=0 disables the overflow test (:24-25);

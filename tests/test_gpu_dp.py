@@ -241,3 +241,43 @@ def test_extended_value_iteration(dp, precision):
     assert r1[0] == r2[0] and np.array_equal(r1[1], r2[1])
     assert dp.extended_value_iteration(g["P_0"], g["est_0"], g["beta_r_0"], g["beta_p_0"], 1.0, 1e-9, precision=precision,
                                        max_iter=3) is None
+
+
+def test_gauss_seidel_reproduces_the_reference_iterate(dp, dp_synth):
+    """sweep_order='gauss_seidel': the reference's OWN in-place iterate (infinite_horizon.py:121-142, :167-184), i.e. the
+    numbers its numba kernel returns at its default stopping sweep -- against the goldens recorded from the reference
+    and the loop-for-loop oracle.  The only difference left is the summation order of a row dot product, which can
+    move the stopping sweep by one: the bar is the stopping tolerance itself."""
+    g = dp_synth
+    for b in range(3):
+        T, R, pi = g[f"T_{b}"], g[f"R_{b}"], g[f"pi_{b}"]
+        Q, V = dp.discounted_value_iteration(T, R, sweep_order="gauss_seidel")  # reference defaults: 0.99, 1e-3
+        it = dp.last_iterations()[0]
+        Qo, Vo, ito = orc.discounted_gs_f32(T, R, gamma=0.99, eps=1e-3)
+        assert V.dtype == np.float32 and abs(it - ito) <= 1
+        for ref_Q, ref_V in ((Qo, Vo), (g[f"Q_{b}"], g[f"V_{b}"])):
+            np.testing.assert_allclose(V, ref_V, atol=1.5e-3)
+            np.testing.assert_allclose(Q, ref_Q, atol=1.5e-3)
+        # ... while the synchronous sweep, stopped by the same rule, sits elsewhere (why the mode exists)
+        _, Vj = dp.discounted_value_iteration(T, R)
+        assert np.abs(Vj - g[f"V_{b}"]).max() > np.abs(V - g[f"V_{b}"]).max()
+        # tight epsilon: both orders meet at the fixed point
+        Qt, Vt = dp.discounted_value_iteration(T, R, 0.99, 1e-6, sweep_order="gauss_seidel")
+        np.testing.assert_allclose(Vt, g[f"Vt_{b}"], rtol=2e-5, atol=1e-4)
+        Qp, Vp = dp.discounted_policy_evaluation(T, R, pi, sweep_order="gauss_seidel", precision="f64")
+        np.testing.assert_allclose(Vp, g[f"Vp_{b}"], rtol=3e-5)
+    # reference goldens of real MDP instances (their vi_Q / vi_V are the reference's default-epsilon outputs)
+    for name in ("doc_simplegrid4", "taxicontinuous_ergo0", "deepsea20_prand"):
+        gi = load_instance(name)
+        Q, V = dp.discounted_value_iteration(gi["T"], gi["R"], sweep_order="gauss_seidel")
+        np.testing.assert_allclose(V, gi["vi_V"], atol=1.5e-3)
+        np.testing.assert_allclose(Q, gi["vi_Q"], atol=1.5e-3)
+    # contracts: overflow -> None (infinite_horizon.py:136-138); batches; odd S (scalar loads)
+    assert dp.discounted_value_iteration(g["T_0"], g["R_0"], max_abs_value=5.0, sweep_order="gauss_seidel") is None
+    Tb = np.stack([g["T_1"]] * 5); Rb = np.stack([g["R_1"] * (1 + 0.1 * i) for i in range(5)]).astype(np.float32)
+    Qb, Vb = dp.discounted_value_iteration(Tb, Rb, sweep_order="gauss_seidel")
+    for i in range(5):
+        _, Vi, _ = orc.discounted_gs_f32(Tb[i], Rb[i], gamma=0.99, eps=1e-3)
+        np.testing.assert_allclose(Vb[i], Vi, atol=1.5e-3)
+    with pytest.raises(dp.DynamicProgrammingMaxIterationExceeded):
+        dp._solve_discounted(g["T_0"], g["R_0"], None, 0.99, 1e-12, None, "f64", max_iter=5, sweep_order="gauss_seidel")
