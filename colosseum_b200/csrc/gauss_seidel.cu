@@ -13,14 +13,20 @@
 // loads of T, V quads from shared memory) and folded with shuffles, and the whole solve (all sweeps, stopping rule,
 // overflow test) is one launch.  A batch of B instances runs B warps side by side: for large batches the kernel is
 // HBM bound like the Jacobi sweep (T is streamed once per sweep) and needs about half the sweeps.
+#include <vector>
+
 #include "common.cuh"
 
 namespace colo {
 
 struct GsArgs {
-  const float* T;   // [B][S,A,S]
-  const float* R;   // [B][S,A]
+  const float* T;   // [B][S,A,S]  (t_stride = 0: one T shared by all instances)
+  const float* R;   // [B][S,A] or null: r_const
   const float* pi;  // [B][S,A] or null
+  long long t_stride, r_stride;
+  double r_const;
+  const int* pin_index;  // per instance or null: V[pin] is held at pin_value (absorbing target of the diameter)
+  double pin_value;
   int B, S, A, fold, warps_per_cta;
   double gamma, eps, max_abs;
   long long max_iter;
@@ -57,10 +63,11 @@ __global__ void __launch_bounds__(256) gs_solve_kernel(const GsArgs p) {
   TV* Vs = reinterpret_cast<TV*>(smem_raw) + (size_t)warp * Sp;
   for (int i = lane; i < Sp; i += 32) Vs[i] = TV(0);
   __syncwarp();
-  const float* T = p.T + (size_t)b * S * A * S;
-  const float* R = p.R + (size_t)b * S * A;
+  const float* T = p.T + (size_t)b * p.t_stride;
+  const float* R = p.R ? p.R + (size_t)b * p.r_stride : nullptr;
   const float* pi = p.pi ? p.pi + (size_t)b * S * A : nullptr;
-  TV* Qg = reinterpret_cast<TV*>(p.Q) + (size_t)b * S * A;
+  TV* Qg = p.Q ? reinterpret_cast<TV*>(p.Q) + (size_t)b * S * A : nullptr;
+  const int pin = p.pin_index ? p.pin_index[b] : -1;
   const TV gamma = (TV)p.gamma;
   int status = COLO_MAX_ITER;
   long long it = 0;
@@ -68,6 +75,14 @@ __global__ void __launch_bounds__(256) gs_solve_kernel(const GsArgs p) {
     TV res = 0;
     bool overflow = false;
     for (int s = 0; s < S && !overflow; ++s) {
+      if (s == pin) {  // absorbing target: T_es[es,:,es] = 1, R_es[es] = 0 -> V[es] stays at its value (diameter.py:85-90)
+        const TV d0 = fabs((TV)p.pin_value - Vs[s]);
+        res = d0 > res ? d0 : res;
+        __syncwarp();
+        if (lane == 0) Vs[s] = (TV)p.pin_value;
+        __syncwarp();
+        continue;
+      }
       const float* Trow = T + (size_t)s * A * S;
       TV folded = p.fold == COLO_FOLD_MIN ? (TV)INFINITY : (p.fold == COLO_FOLD_MAX ? (TV)-INFINITY : (TV)0);
       for (int a0 = 0; a0 < A; a0 += kGsAT) {
@@ -102,8 +117,8 @@ __global__ void __launch_bounds__(256) gs_solve_kernel(const GsArgs p) {
         for (int i = 0; i < kGsAT; ++i)
           if (i < na) {
             const int a = a0 + i;
-            const TV q = (TV)__ldg(R + (size_t)s * A + a) + gamma * acc[i];
-            if (lane == 0) Qg[(size_t)s * A + a] = q;  // the reference returns the Q rows of the stopping sweep
+            const TV q = (R ? (TV)__ldg(R + (size_t)s * A + a) : (TV)p.r_const) + gamma * acc[i];
+            if (lane == 0 && Qg) Qg[(size_t)s * A + a] = q;  // the reference returns the Q rows of the stopping sweep
             if (p.fold == COLO_FOLD_MAX) folded = q > folded ? q : folded;
             if (p.fold == COLO_FOLD_MIN) folded = q < folded ? q : folded;
             if (p.fold == COLO_FOLD_PI) folded += q * (TV)__ldg(pi + (size_t)s * A + a);
@@ -129,30 +144,22 @@ __global__ void __launch_bounds__(256) gs_solve_kernel(const GsArgs p) {
 }
 
 template <typename TV>
-int gs_solve(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma, double eps,
-             double max_abs, long long max_iter, int fold, TV* Q, TV* V, long long* iters_dev, int* status_dev,
-             void* stream) {
-  COLO_ARG_CHECK(T && R && Q && V && iters_dev && status_dev, "T, R, Q, V, iters, status are required");
-  COLO_ARG_CHECK(B >= 0 && S > 0 && A > 0 && fold >= 0 && fold <= 2 && (fold != COLO_FOLD_PI || pi), "B, S, A, fold, pi");
-  if (B == 0) return COLO_OK;
+static int gs_launch(GsArgs a, void* stream) {
   int dev = 0, max_smem = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) max_smem = 227 * 1024;
-  const size_t per_warp = (size_t)((S + 3) & ~3) * sizeof(TV);
+  const size_t per_warp = (size_t)((a.S + 3) & ~3) * sizeof(TV);
   if (per_warp > (size_t)max_smem) {
-    set_error("Gauss-Seidel solver: V of %d states does not fit shared memory", S);
+    set_error("Gauss-Seidel solver: V of %d states does not fit shared memory", a.S);
     return COLO_ERR_ARG;
   }
   int W = (int)((size_t)max_smem / 2 / per_warp);  // two CTAs per SM
   W = W < 1 ? 1 : (W > 8 ? 8 : W);
-  if (B < W) W = B;
-  GsArgs a = {};
-  a.T = T; a.R = R; a.pi = pi; a.B = B; a.S = S; a.A = A; a.fold = fold; a.warps_per_cta = W;
-  a.gamma = gamma; a.eps = eps; a.max_abs = max_abs; a.max_iter = max_iter; a.V = V; a.Q = Q;
-  a.iters = iters_dev; a.status = status_dev;
+  if (a.B < W) W = a.B;
+  a.warps_per_cta = W;
   const size_t smem = per_warp * W;
-  const bool vec = (S % 4 == 0) && ((uintptr_t)T % 16 == 0);
-  const int grid = (B + W - 1) / W;
+  const bool vec = (a.S % 4 == 0) && ((uintptr_t)a.T % 16 == 0) && (a.t_stride % 4 == 0);
+  const int grid = (a.B + W - 1) / W;
   cudaStream_t st = (cudaStream_t)stream;
   if (vec) {
     auto k = gs_solve_kernel<TV, true>;
@@ -164,6 +171,84 @@ int gs_solve(const float* T, const float* R, const float* pi, int B, int S, int 
     k<<<grid, W * 32, smem, st>>>(a);
   }
   return check_launch("gs_solve_kernel");
+}
+
+template <typename TV>
+int gs_solve(const float* T, const float* R, const float* pi, int B, int S, int A, double gamma, double eps,
+             double max_abs, long long max_iter, int fold, TV* Q, TV* V, long long* iters_dev, int* status_dev,
+             void* stream) {
+  COLO_ARG_CHECK(T && R && Q && V && iters_dev && status_dev, "T, R, Q, V, iters, status are required");
+  COLO_ARG_CHECK(B >= 0 && S > 0 && A > 0 && fold >= 0 && fold <= 2 && (fold != COLO_FOLD_PI || pi), "B, S, A, fold, pi");
+  if (B == 0) return COLO_OK;
+  GsArgs a = {};
+  a.T = T; a.R = R; a.pi = pi; a.B = B; a.S = S; a.A = A; a.fold = fold;
+  a.t_stride = (long long)S * A * S; a.r_stride = (long long)S * A;
+  a.gamma = gamma; a.eps = eps; a.max_abs = max_abs; a.max_iter = max_iter; a.V = V; a.Q = Q;
+  a.iters = iters_dev; a.status = status_dev;
+  return gs_launch<TV>(a, stream);
+}
+
+template <typename TV>
+__global__ void neg_min_per_row_kernel(const TV* __restrict__ V, int K, int S, TV* __restrict__ out) {
+  // out[k] = -min_s V[k,s]   (diameter.py:95); one warp per target
+  const int lane = threadIdx.x & 31;
+  const int k = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (k >= K) return;
+  TV m = INFINITY;
+  for (int s = lane; s < S; s += 32) m = V[(size_t)k * S + s] < m ? V[(size_t)k * S + s] : m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const TV w = __shfl_xor_sync(FULL, m, o);
+    m = w < m ? w : m;
+  }
+  if (lane == 0) out[k] = -m;
+}
+
+// The reference's continuous diameter, iterate for iterate (diameter.py:76-106): for every target es a discounted VI
+// with gamma = 1 on T_es (es absorbing) and R_es = -1 (0 at es), in-place sweeps, eps = 1e-3; diameter = max_es -min V.
+// All K solves share T (t_stride = 0): K warps stream it from L2.
+template <typename TV>
+int gs_diameter(const float* T, const int* targets, int K, int S, int A, double eps, double max_value,
+                long long max_iter, void* work, double* out_host, void* stream) {
+  COLO_ARG_CHECK(T && targets && work && out_host && K > 0 && S > 0 && A > 0, "T, targets, work, out_host, K, S, A");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)work;
+  TV* V = (TV*)w;
+  w += ((size_t)K * S * sizeof(TV) + 255) / 256 * 256;
+  TV* d = (TV*)w;
+  w += ((size_t)K * sizeof(TV) + 255) / 256 * 256;
+  long long* iters = (long long*)w;
+  w += ((size_t)K * sizeof(long long) + 255) / 256 * 256;
+  int* status = (int*)w;
+  GsArgs a = {};
+  a.T = T; a.R = nullptr; a.r_const = -1.0; a.B = K; a.S = S; a.A = A; a.fold = COLO_FOLD_MAX;
+  a.t_stride = 0; a.r_stride = 0; a.pin_index = targets; a.pin_value = 0.0;
+  a.gamma = 1.0; a.eps = eps; a.max_abs = max_value; a.max_iter = max_iter; a.V = V; a.Q = nullptr;
+  a.iters = iters; a.status = status;
+  int r = gs_launch<TV>(a, stream);
+  if (r != COLO_OK) return r;
+  neg_min_per_row_kernel<TV><<<(K * 32 + 255) / 256, 256, 0, st>>>(V, K, S, d);
+  r = check_launch("neg_min_per_row_kernel");
+  if (r != COLO_OK) return r;
+  std::vector<TV> hd((size_t)K);
+  std::vector<long long> hit((size_t)K);
+  std::vector<int> hst((size_t)K);
+  COLO_CUDA_TRY(cudaMemcpyAsync(hd.data(), d, (size_t)K * sizeof(TV), cudaMemcpyDeviceToHost, st));
+  COLO_CUDA_TRY(cudaMemcpyAsync(hit.data(), iters, (size_t)K * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  COLO_CUDA_TRY(cudaMemcpyAsync(hst.data(), status, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost, st));
+  COLO_CUDA_TRY(cudaStreamSynchronize(st));
+  double best = 0.0;
+  long long mx = 0;
+  int rc = COLO_OK;
+  for (int k = 0; k < K; ++k) {
+    if (hst[k] == COLO_OVERFLOW) return COLO_OVERFLOW;
+    if (hst[k] == COLO_MAX_ITER) rc = COLO_MAX_ITER;
+    if ((double)hd[k] > best) best = (double)hd[k];
+    if (hit[k] > mx) mx = hit[k];
+  }
+  out_host[0] = best;
+  out_host[1] = (double)mx;
+  return rc;
 }
 
 }  // namespace colo
@@ -179,6 +264,20 @@ int colo_solve_discounted_gs_f64acc(const float* T, const float* R, const float*
                                     double eps, double max_abs, long long max_iter, int fold, double* Q, double* V,
                                     long long* iters_dev, int* status_dev, void* stream) {
   return colo::gs_solve<double>(T, R, pi, B, S, A, gamma, eps, max_abs, max_iter, fold, Q, V, iters_dev, status_dev, stream);
+}
+
+size_t colo_diameter_continuous_gs_work_bytes(int K, int S, int f64) {
+  const size_t e = f64 ? 8 : 4;
+  return ((size_t)K * S * e + 255) / 256 * 256 + ((size_t)K * e + 255) / 256 * 256 + ((size_t)K * 8 + 255) / 256 * 256 +
+         ((size_t)K * 4 + 255) / 256 * 256 + 256;
+}
+int colo_diameter_continuous_gs_f32(const float* T, const int* targets, int K, int S, int A, float eps, float max_value,
+                                    long long max_iter, void* work, double* out_host, void* stream) {
+  return colo::gs_diameter<float>(T, targets, K, S, A, eps, max_value, max_iter, work, out_host, stream);
+}
+int colo_diameter_continuous_gs_f64acc(const float* T, const int* targets, int K, int S, int A, double eps,
+                                       double max_value, long long max_iter, void* work, double* out_host, void* stream) {
+  return colo::gs_diameter<double>(T, targets, K, S, A, eps, max_value, max_iter, work, out_host, stream);
 }
 
 }  // extern "C"

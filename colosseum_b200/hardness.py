@@ -18,7 +18,7 @@ from .dynamic_programming import _is_tensor, _result, _scratch, _torch, to_devic
 
 
 def get_diameter(T, is_episodic, max_value=None, *, precision="f64", epsilon=None, targets=None,
-                 max_iter=int(1e6), return_sweeps=False):
+                 max_iter=int(1e6), return_sweeps=False, reference_iterates=None):
     """colosseum/hardness/measures/diameter.py:20-39.  T is [S,A,S] (continuous) or the episodic [H,S,A,S] tensor of
     mdp/utils/mdp_creation.py:98-128.  Returns the diameter, or None when a hitting time exceeds max_value.
 
@@ -28,8 +28,17 @@ def get_diameter(T, is_episodic, max_value=None, *, precision="f64", epsilon=Non
     Td = to_device(T)
     assert (is_episodic and Td.dim() == 4) or (not is_episodic and Td.dim() == 3)
     torch = _torch()
+    if reference_iterates is None:
+        from .dynamic_programming import get_sweep_order
+
+        reference_iterates = get_sweep_order() == "gauss_seidel"
+    gs = bool(reference_iterates) and not is_episodic
+    if gs and precision == "f64" and epsilon is None:
+        precision = "f32"  # the reference's arithmetic type: its own iterate is a float32 one
     f64 = precision == "f64"
-    eps = float(epsilon if epsilon is not None else (1e-9 if f64 else 1e-4))
+    # reference_iterates (continuous MDPs): the reference's per-target in-place VI at ITS epsilon = 1e-3
+    # (diameter.py:91 -> infinite_horizon.py:121-142), reproducing its early-stopped value
+    eps = float(epsilon if epsilon is not None else (1e-3 if gs else (1e-9 if f64 else 1e-4)))
     lib = _cabi.lib()
     S, A = int(Td.shape[-1]), int(Td.shape[-2])
     tg = np.arange(S, dtype=np.int32) if targets is None else np.ascontiguousarray(targets, np.int32)
@@ -42,6 +51,11 @@ def get_diameter(T, is_episodic, max_value=None, *, precision="f64", epsilon=Non
         work = _scratch(lib.colo_diameter_episodic_work_bytes(K, H, S, A, int(f64)))
         fn = lib.colo_diameter_episodic_f64acc if f64 else lib.colo_diameter_episodic_f32
         rc = fn(_cabi.ptr(Td), _cabi.ptr(tgd), K, H, S, A, eps, mv, int(max_iter), _cabi.ptr(work), out,
+                _cabi.current_stream())
+    elif gs:
+        work = _scratch(lib.colo_diameter_continuous_gs_work_bytes(K, S, int(f64)))
+        fn = lib.colo_diameter_continuous_gs_f64acc if f64 else lib.colo_diameter_continuous_gs_f32
+        rc = fn(_cabi.ptr(Td), _cabi.ptr(tgd), K, S, A, eps, mv, int(max_iter), _cabi.ptr(work), out,
                 _cabi.current_stream())
     else:
         work = _scratch(lib.colo_diameter_continuous_work_bytes(K, S, int(f64)))

@@ -203,6 +203,18 @@ int colo_diameter_continuous_f64acc(const float* T, const int* targets, int K, i
  * Episodic diameter in the augmented (h,s) space (colosseum/hardness/measures/diameter.py:193-234,285-318) on
  * T_epi[H,S,A,S] (colosseum/mdp/utils/mdp_creation.py:98-128), iterated to max|dE| < eps for all K targets at once.
  */
+/*
+ * The reference's continuous diameter ITERATE FOR ITERATE (diameter.py:76-106): per target es a discounted VI with
+ * gamma = 1 on T_es (es absorbing) and R_es = -1 (0 at es), in-place (Gauss-Seidel) sweeps stopped at max|dV| < eps
+ * (the reference's default 1e-3), diameter = max_es (-min_s V_es).  One warp per target, all targets share T; the whole
+ * computation is one launch + one reduction.  Reproduces the reference's own early-stopped value (which sits up to
+ * ~5e-4 below the fixed point that colo_diameter_continuous_* returns).  Synchronises.
+ */
+size_t colo_diameter_continuous_gs_work_bytes(int K, int S, int f64);
+int colo_diameter_continuous_gs_f32(const float* T, const int* targets, int K, int S, int A, float eps, float max_value,
+                                    long long max_iter, void* work, double* out_host, void* stream);
+int colo_diameter_continuous_gs_f64acc(const float* T, const int* targets, int K, int S, int A, double eps,
+                                       double max_value, long long max_iter, void* work, double* out_host, void* stream);
 size_t colo_diameter_episodic_work_bytes(int K, int H, int S, int A, int f64);
 int colo_diameter_episodic_f32(const float* T_epi, const int* targets, int K, int H, int S, int A, float eps,
                                float max_value, long long max_iter, void* work, double* out_host, void* stream);

@@ -137,3 +137,23 @@ def test_episodic_tensor_builders(name):
     T2, R2 = ef.get_continuous_form_episodic_transition_matrix_and_rewards(H, g["T"], g["R"], g["start_idx"],
                                                                            g["start_prob"])
     assert T2.shape == T_cf.shape and np.allclose(T2.sum(-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", CONTINUOUS)
+def test_reference_iterate_diameter(hd, name):
+    """reference_iterates=True: the reference's per-target in-place VI at its own epsilon (diameter.py:76-106) -- the
+    value `mdp.diameter` itself returned when the goldens were recorded, to the stopping tolerance (1e-3 absolute on
+    hitting times of 6 .. 160), instead of the 2e-3 RELATIVE that separates it from the fixed point"""
+    g = load_instance(name)
+    ref = float(g["diameter"])
+    if not np.isfinite(ref):
+        pytest.skip("the reference diameter of this instance was not recorded (minutes on the CPU)")
+    d, sweeps = hd.get_diameter(g["T"], False, reference_iterates=True, return_sweeps=True)
+    assert abs(d - ref) < 2e-3, (d, ref)
+    fixed_point = hd.get_diameter(g["T"], False)
+    assert d <= fixed_point + 1e-6  # the early-stopped iterate approaches the fixed point from below
+    # the oracle's loop-for-loop restatement of the reference's per-target kernel agrees too
+    es = int(np.argmax([orc.diameter_target_ref_f32(g["T"], k) for k in range(min(g["T"].shape[0], 40))]))
+    dk = hd.get_diameter(g["T"], False, reference_iterates=True, targets=np.array([es], np.int32))
+    assert abs(dk - orc.diameter_target_ref_f32(g["T"], es)) < 2e-3
+    assert hd.get_diameter(g["T"], False, max_value=3.0, reference_iterates=True) is None
