@@ -32,13 +32,16 @@ def get_diameter(T, is_episodic, max_value=None, *, precision="f64", epsilon=Non
         from .dynamic_programming import get_sweep_order
 
         reference_iterates = get_sweep_order() == "gauss_seidel"
-    gs = bool(reference_iterates) and not is_episodic
-    if gs and precision == "f64" and epsilon is None:
+    ref_it = bool(reference_iterates)
+    gs = ref_it and not is_episodic
+    if ref_it and precision == "f64" and epsilon is None:
         precision = "f32"  # the reference's arithmetic type: its own iterate is a float32 one
     f64 = precision == "f64"
-    # reference_iterates (continuous MDPs): the reference's per-target in-place VI at ITS epsilon = 1e-3
-    # (diameter.py:91 -> infinite_horizon.py:121-142), reproducing its early-stopped value
-    eps = float(epsilon if epsilon is not None else (1e-3 if gs else (1e-9 if f64 else 1e-4)))
+    # reference_iterates: the reference's own iterate at ITS epsilon = 1e-3.  Continuous MDPs: per-target in-place VI
+    # (diameter.py:91 -> infinite_horizon.py:121-142).  Episodic MDPs: the layered kernels already sweep like
+    # _episodic_diameter_calculation (diameter.py:285-318: layer h-1 from the freshly updated layer h), so float32 and
+    # the reference's epsilon are all it takes (its order-dependent loose exit, :316, is not reproduced).
+    eps = float(epsilon if epsilon is not None else (1e-3 if ref_it else (1e-9 if f64 else 1e-4)))
     lib = _cabi.lib()
     S, A = int(Td.shape[-1]), int(Td.shape[-2])
     tg = np.arange(S, dtype=np.int32) if targets is None else np.ascontiguousarray(targets, np.int32)

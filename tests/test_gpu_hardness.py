@@ -157,3 +157,13 @@ def test_reference_iterate_diameter(hd, name):
     dk = hd.get_diameter(g["T"], False, reference_iterates=True, targets=np.array([es], np.int32))
     assert abs(dk - orc.diameter_target_ref_f32(g["T"], es)) < 2e-3
     assert hd.get_diameter(g["T"], False, max_value=3.0, reference_iterates=True) is None
+
+
+@pytest.mark.parametrize("name", EPISODIC)
+def test_reference_iterate_episodic_diameter(hd, name):
+    """episodic diameter with reference_iterates=True (float32, the reference's epsilon): the layered kernel sweeps
+    exactly like _episodic_diameter_calculation (diameter.py:285-318) -- the recorded mdp.diameter to 2e-5 absolute
+    (bit-identical on half of the instances)"""
+    g = load_instance(name)
+    d = hd.get_diameter(g["T_epi"], True, reference_iterates=True)
+    assert abs(d - float(g["diameter"])) < 2e-5, (d, float(g["diameter"]))
