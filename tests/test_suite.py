@@ -129,3 +129,35 @@ def test_concurrent_instances_match_sequential(suite):
     for (a, _), (b, _) in zip(seq, par):
         for k in ("gaps", "value_norm", "diameter", "visits_total", "mean_reward_last_step"):
             assert a[k] == b[k] or (np.isnan(a[k]) and np.isnan(b[k])), k
+
+
+@pytest.mark.gpu
+def test_suite_reference_iterates(suite):
+    """the reference's OWN early-stopped iterates (sweep_order='gauss_seidel', reference_iterates=True) on the
+    continuous benchmark instances: measures computed from them sit on the reference's recorded numbers -- value norm
+    to 5e-4, diameter to 2e-3 ABSOLUTE (bit-identical on several), gaps to 1e-4 except where exactly tied actions make
+    1/(V-Q+0.1) hypersensitive (SimpleGrid: 6e-3) -- an order of magnitude closer than the fixed-point comparison of
+    test_suite_hardness_against_reference, as it must be"""
+    import torch
+
+    import colosseum_b200.dynamic_programming as dp
+    import colosseum_b200.hardness as hd
+
+    n = 0
+    for inst in suite:
+        if inst.episodic or inst.S > 420:
+            continue
+        T = torch.from_numpy(inst.tables.T).cuda()
+        R = torch.from_numpy(inst.R).cuda()
+        Q, V = dp.discounted_value_iteration(T, R, sweep_order="gauss_seidel")  # reference defaults: 0.99, 1e-3, f32
+        ref = inst.ref
+        gaps = hd.get_sum_reciprocals_suboptimality_gaps(Q, V)
+        assert rel(gaps, ref["gaps"]) < (6e-3 if "SimpleGrid" in inst.name else 5e-4), (inst.name, gaps, ref["gaps"])
+        det = bool((inst.tables.succ_len == 1).all()) and all(k == "deterministic" for k, _ in inst.tables.rew_kinds)
+        vn = 0.0 if det else hd.calculate_norm_discounted(T, V, precision="f32")
+        assert abs(vn - ref["value_norm"]) < 5e-4 * max(ref["value_norm"], 0.05), (inst.name, vn, ref["value_norm"])
+        if np.isfinite(ref["diameter"]):
+            d = hd.get_diameter(T, False, reference_iterates=True)
+            assert abs(d - ref["diameter"]) < 2e-3, (inst.name, d, ref["diameter"])
+        n += 1
+    assert n >= 18
