@@ -27,6 +27,11 @@ struct GsArgs {
   double r_const;
   const int* pin_index;  // per instance or null: V[pin] is held at pin_value (absorbing target of the diameter)
   double pin_value;
+  // compressed rows (sparse T): row-major ELL, row (s*A + a) holds KMp slots of int2 (column, value bits), column -1 =
+  // padding; KMp is a power of two.  cv_stride = slots between instances (0 = shared T)
+  const int2* cv_rm;
+  int KMp;
+  long long cv_stride;
   int B, S, A, fold, warps_per_cta;
   double gamma, eps, max_abs;
   long long max_iter;
@@ -143,6 +148,134 @@ __global__ void __launch_bounds__(256) gs_solve_kernel(const GsArgs p) {
   }
 }
 
+__global__ void ell_to_row_major_kernel(const int* __restrict__ len, const int2* __restrict__ cv, long long rows, int S,
+                                        int A, int kmax, int KMp, int2* __restrict__ cv_rm) {
+  // slot-major ELL of sparse_hitting.cu (len[(g*A+a)*S+s], cv[((g*A+a)*kmax+i)*S+s]) -> row-major padded rows
+  const long long n = rows * KMp;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / KMp;
+    const int i = (int)(t - r * KMp);
+    const long long gs = r / A;
+    const int a = (int)(r - gs * A);
+    const long long g = gs / S;
+    const int s = (int)(gs - g * S);
+    const long long ga = g * A + a;
+    int2 e = make_int2(-1, 0);
+    if (i < len[ga * S + s]) e = cv[(ga * kmax + i) * S + s];
+    cv_rm[t] = e;
+  }
+}
+
+// In-place sweeps on compressed rows: the state loop stays sequential, the lanes of the warp take the (action, slot)
+// pairs of the current state -- seg = min(KMp, 32) lanes per action, 32/seg actions per pass -- so a state of a
+// benchmark MDP (A*kmax <= 32 entries) costs one load round, a segmented shuffle sum and one warp fold.
+template <typename TV>
+__global__ void __launch_bounds__(256) gs_sparse_kernel(const GsArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = p.S, A = p.A, KMp = p.KMp;
+  const int Sp = (S + 3) & ~3;
+  const long long b = (long long)blockIdx.x * p.warps_per_cta + warp;
+  if (warp >= p.warps_per_cta || b >= p.B) return;
+  TV* Vs = reinterpret_cast<TV*>(smem_raw) + (size_t)warp * Sp;
+  for (int i = lane; i < Sp; i += 32) Vs[i] = TV(0);
+  __syncwarp();
+  const int2* cv = p.cv_rm + (size_t)b * p.cv_stride;
+  const float* R = p.R ? p.R + (size_t)b * p.r_stride : nullptr;
+  const float* pi = p.pi ? p.pi + (size_t)b * S * A : nullptr;
+  TV* Qg = p.Q ? reinterpret_cast<TV*>(p.Q) + (size_t)b * S * A : nullptr;
+  const int pin = p.pin_index ? p.pin_index[b] : -1;
+  const TV gamma = (TV)p.gamma;
+  const int seg = KMp < 32 ? KMp : 32, chunks = KMp / seg, per_pass = 32 / seg;
+  const int il = lane % seg, al = lane / seg;
+  const TV ident = p.fold == COLO_FOLD_MIN ? (TV)INFINITY : (p.fold == COLO_FOLD_MAX ? (TV)-INFINITY : (TV)0);
+  int status = COLO_MAX_ITER;
+  long long it = 0;
+  while (it < p.max_iter) {
+    TV res = 0;
+    bool overflow = false;
+    for (int s = 0; s < S && !overflow; ++s) {
+      TV folded;
+      if (s == pin) {
+        folded = (TV)p.pin_value;
+      } else {
+        folded = ident;
+        for (int a0 = 0; a0 < A; a0 += per_pass) {
+          const int a = a0 + al;
+          TV part = 0;
+          if (a < A) {
+            const int2* row = cv + ((size_t)s * A + a) * KMp;
+            for (int c = 0; c < chunks; ++c) {
+              const int2 e = __ldg(row + c * seg + il);
+              if (e.x >= 0) part += (TV)__int_as_float(e.y) * Vs[e.x];
+            }
+          }
+          for (int o = seg >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+          TV cand = ident;
+          if (a < A) {
+            const TV q = (R ? (TV)__ldg(R + (size_t)s * A + a) : (TV)p.r_const) + gamma * part;
+            if (il == 0 && Qg) Qg[(size_t)s * A + a] = q;
+            if (p.fold == COLO_FOLD_PI) cand = il == 0 ? q * (TV)__ldg(pi + (size_t)s * A + a) : (TV)0;
+            else cand = q;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const TV w = __shfl_xor_sync(FULL, cand, o);
+            if (p.fold == COLO_FOLD_MAX) cand = w > cand ? w : cand;
+            else if (p.fold == COLO_FOLD_MIN) cand = w < cand ? w : cand;
+            else cand += w;
+          }
+          if (p.fold == COLO_FOLD_MAX) folded = cand > folded ? cand : folded;
+          else if (p.fold == COLO_FOLD_MIN) folded = cand < folded ? cand : folded;
+          else folded += cand;
+        }
+      }
+      const TV d = fabs(folded - Vs[s]);
+      res = d > res ? d : res;
+      __syncwarp();
+      if (lane == 0) Vs[s] = folded;
+      __syncwarp();
+      if (p.max_abs > 0.0 && fabs((double)folded) > p.max_abs) overflow = true;
+    }
+    ++it;
+    if (overflow) { status = COLO_OVERFLOW; break; }
+    if (res < (TV)p.eps) { status = COLO_OK; break; }
+  }
+  TV* Vg = reinterpret_cast<TV*>(p.V) + (size_t)b * S;
+  for (int i = lane; i < S; i += 32) Vg[i] = Vs[i];
+  if (lane == 0) {
+    p.iters[b] = it;
+    p.status[b] = status;
+  }
+}
+
+// Compress T (groups = instances, or 1 when shared) into the row-major ELL of gs_sparse_kernel.  *cv_rm_out stays null
+// when the rows are dense.  The caller frees it with cudaFreeAsync.
+static int gs_compress(const float* T, long long groups, int S, int A, int2** cv_rm_out, int* KMp_out, cudaStream_t st) {
+  *cv_rm_out = nullptr;
+  SparseRows sp;
+  int r = sparse_rows_build(T, groups * S * A, S, A, &sp, st);
+  if (r != COLO_OK || sp.kmax == 0) return r;
+  int KMp = 1;
+  while (KMp < sp.kmax) KMp <<= 1;
+  const long long rows = groups * S * A;
+  int2* cv_rm = nullptr;
+  COLO_CUDA_TRY(cudaMallocAsync(&cv_rm, (size_t)rows * KMp * sizeof(int2), st));
+  const long long n = rows * KMp;
+  const long long blocks = (n + 255) / 256;
+  ell_to_row_major_kernel<<<(int)(blocks < 65535 ? blocks : 65535), 256, 0, st>>>(sp.len, (const int2*)sp.cv, rows, S, A,
+                                                                                  sp.kmax, KMp, cv_rm);
+  r = check_launch("ell_to_row_major_kernel");
+  sparse_rows_free(&sp, st);
+  if (r != COLO_OK) {
+    cudaFreeAsync(cv_rm, st);
+    return r;
+  }
+  *cv_rm_out = cv_rm;
+  *KMp_out = KMp;
+  return COLO_OK;
+}
+
 template <typename TV>
 static int gs_launch(GsArgs a, void* stream) {
   int dev = 0, max_smem = 0;
@@ -161,6 +294,12 @@ static int gs_launch(GsArgs a, void* stream) {
   const bool vec = (a.S % 4 == 0) && ((uintptr_t)a.T % 16 == 0) && (a.t_stride % 4 == 0);
   const int grid = (a.B + W - 1) / W;
   cudaStream_t st = (cudaStream_t)stream;
+  if (a.cv_rm != nullptr) {
+    auto k = gs_sparse_kernel<TV>;
+    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, W * 32, smem, st>>>(a);
+    return check_launch("gs_sparse_kernel");
+  }
   if (vec) {
     auto k = gs_solve_kernel<TV, true>;
     COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -185,7 +324,14 @@ int gs_solve(const float* T, const float* R, const float* pi, int B, int S, int 
   a.t_stride = (long long)S * A * S; a.r_stride = (long long)S * A;
   a.gamma = gamma; a.eps = eps; a.max_abs = max_abs; a.max_iter = max_iter; a.V = V; a.Q = Q;
   a.iters = iters_dev; a.status = status_dev;
-  return gs_launch<TV>(a, stream);
+  int2* cv_rm = nullptr;
+  int r = gs_compress(T, B, S, A, &cv_rm, &a.KMp, (cudaStream_t)stream);
+  if (r != COLO_OK) return r;
+  a.cv_rm = cv_rm;
+  a.cv_stride = (long long)S * A * a.KMp;
+  r = gs_launch<TV>(a, stream);
+  if (cv_rm) cudaFreeAsync(cv_rm, (cudaStream_t)stream);
+  return r;
 }
 
 template <typename TV>
@@ -225,7 +371,13 @@ int gs_diameter(const float* T, const int* targets, int K, int S, int A, double 
   a.t_stride = 0; a.r_stride = 0; a.pin_index = targets; a.pin_value = 0.0;
   a.gamma = 1.0; a.eps = eps; a.max_abs = max_value; a.max_iter = max_iter; a.V = V; a.Q = nullptr;
   a.iters = iters; a.status = status;
-  int r = gs_launch<TV>(a, stream);
+  int2* cv_rm = nullptr;
+  int r = gs_compress(T, 1, S, A, &cv_rm, &a.KMp, st);
+  if (r != COLO_OK) return r;
+  a.cv_rm = cv_rm;
+  a.cv_stride = 0;  // every target shares T
+  r = gs_launch<TV>(a, stream);
+  if (cv_rm) cudaFreeAsync(cv_rm, st);
   if (r != COLO_OK) return r;
   neg_min_per_row_kernel<TV><<<(K * 32 + 255) / 256, 256, 0, st>>>(V, K, S, d);
   r = check_launch("neg_min_per_row_kernel");
