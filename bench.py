@@ -275,7 +275,64 @@ def bench_step_gpu(args, rank, world):
     barrier_sync(world)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
     assert int(env_h.status.item()) == 0 and int(env_h.step_type_host.max()) <= 2
-    return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N, b2b=b2b, det=det)
+
+    # ---- the same end-to-end step with the batch split into two groups stepped in a software pipeline
+    # (PipelinedBatchedMDP): while the host handles group g's TimeStep, the other group's kernel is on PCIe
+    pipe = {}
+    try:
+        from colosseum_b200.batched_mdp import PipelinedBatchedMDP
+
+        G = 2
+        env_p = PipelinedBatchedMDP(tb, N, groups=G, mode="dense_f32", seed=1234, env_offset=rank * N)
+        env_p.reset()
+        p_act = [[a[g * (N // G):(g + 1) * (N // G)].clone().pin_memory() for g in range(G)] for a in h_act]
+        for g in range(G):
+            env_p.send(g, p_act[0][g])
+        for i in range(1, max(3, args.warmup)):
+            for g in range(G):
+                env_p.recv(g)                       # group g's TimeStep is on the host ...
+                env_p.send(g, p_act[i % n_act][g])  # ... its next actions go out
+        barrier_sync(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for i in range(args.steps):                 # K steps of every env: K recv/send rounds per group
+            for g in range(G):
+                env_p.recv(g)
+                env_p.send(g, p_act[i % n_act][g])
+        for g in range(G):
+            env_p.recv(g)
+        e1.record()
+        e1.synchronize()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        barrier_sync(world)
+        # the pipeline lives on two side streams: the events on the default stream bracket the same host interval
+        pipe = {"ms": max_over_ranks(max(e0.elapsed_time(e1), wall_ms), world), "groups": G}
+        assert all(int(sh.status.item()) == 0 for sh in env_p.shards)
+    except Exception as exc:  # keep the single-batch number if the pipelined variant cannot run
+        pipe = {"error": repr(exc)[:200]}
+
+    # ---- and through the persistent step server (no launch, no stream sync per step)
+    served = {}
+    try:
+        env_s = BatchedMDP(tb, N, mode="dense_f32", seed=1234, env_offset=rank * N, host_io=True)
+        env_s.reset()
+        s_buf = h_act[0].clone().pin_memory()
+        env_s.serve(s_buf)
+        for i in range(max(3, args.warmup)):
+            env_s.step_served()
+        barrier_sync(world)
+        w0 = time.perf_counter()
+        for i in range(args.steps):
+            env_s.step_served()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        env_s.stop_serving()
+        barrier_sync(world)
+        served = {"ms": max_over_ranks(wall_ms, world)}
+    except Exception as exc:
+        served = {"error": repr(exc)[:200]}
+    return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N, b2b=b2b, det=det,
+                pipe=pipe, served=served)
 
 
 def make_c4_batch(B, S, A, seed):
@@ -666,6 +723,28 @@ def main():
                          "note": "T (1.8 MB) is L2/L1-resident by construction in C2: algorithmic bytes are served "
                                  "on chip, so frac can exceed 1; see DESIGN.md and `traffic`"},
         })
+        single = line["e2e"]
+        pipe, served = step.get("pipe") or {}, step.get("served") or {}
+        if "ms" in pipe:
+            v = world * N * args.steps / (pipe["ms"] / 1e3)
+            line["e2e_single_batch"] = single
+            if v > single["value"]:
+                line["e2e"] = {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": step["h2d"],
+                               "d2h_bytes_per_step": step["d2h"],
+                               "what": f"PipelinedBatchedMDP(groups={pipe['groups']}): the same batch as {pipe['groups']} "
+                                       "host_io groups on their own streams; per group and step: recv (stream sync, "
+                                       "TimeStep in pinned host memory) then send (launch reading the pinned actions); "
+                                       "every env steps once per step, all bytes cross PCIe inside the timed region"}
+            else:
+                line["e2e_pipelined"] = {"value": v, "unit": "env-steps/s", "groups": pipe["groups"]}
+        elif "error" in pipe:
+            line["e2e_pipelined"] = {"error": pipe["error"]}
+        if "ms" in served:
+            line["e2e_served"] = {"value": world * N * args.steps / (served["ms"] / 1e3), "unit": "env-steps/s",
+                                  "what": "BatchedMDP.serve(): persistent step kernel driven by a doorbell in pinned "
+                                          "host memory (no launch / stream sync per step), wall clock"}
+        elif "error" in served:
+            line["e2e_served"] = {"error": served["error"]}
         det = step.get("det") or {}
         if "ms" in det:
             line["p_rand_none"] = {"value": world * N * det["steps"] / (det["ms"] / 1e3), "unit": "env-steps/s",

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COLO_B200_LIB") or os.path.join(_PKG, "_lib", "libcolosseum_b200.so")  # env: kernel-variant probes only
 
-OK, OVERFLOW, MAX_ITER, NEEDS_RESET = 0, 1, 2, 3
+OK, OVERFLOW, MAX_ITER, NEEDS_RESET, SERVER_LAPSED = 0, 1, 2, 3, 4
 FOLD_MAX, FOLD_PI, FOLD_MIN = 0, 1, 2
 STEP_FIRST, STEP_MID, STEP_LAST = 0, 1, 2
 
@@ -79,6 +79,13 @@ class EnvBatch(C.Structure):
     ]
 
 
+class EnvServer(C.Structure):
+    """mirror of `colo_env_server`"""
+
+    _fields_ = [("doorbell_host", C.c_void_p), ("done_host", C.c_void_p), ("ctl_dev", C.c_void_p),
+                ("share", C.c_int), ("idle_timeout_ms", C.c_uint)]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _ULL = C.c_ulonglong
@@ -125,6 +132,10 @@ PROTOTYPES = {
     "colo_env_step_dense_f64": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
     "colo_env_step_succ": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
     "colo_env_random_steps": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _I, _ULL, _I, _P]),
+    "colo_env_server_start": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), C.POINTER(EnvServer), _I, _ULL, _ULL, _P]),
+    "colo_env_server_post": (_ULL, [C.POINTER(EnvServer)]),
+    "colo_env_server_wait": (_I, [C.POINTER(EnvServer), _ULL, C.c_uint]),
+    "colo_env_server_stop": (_I, [C.POINTER(EnvServer), _P]),
     "colo_emit_observations": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _P, _P]),
     "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "colo_extended_vi_work_bytes": (C.c_size_t, [_I, _I]),

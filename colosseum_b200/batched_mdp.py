@@ -80,17 +80,19 @@ class BatchedMDP:
     VISIT_COPIES = 16  # privatised visitation counters (power of two), summed when read
 
     def __init__(self, tables: MDPTables, n_envs: int, mode: str = "dense_f32", seed: int = 0,
-                 track_visits: bool = True, env_offset: int = 0, host_io: bool = False):
+                 track_visits: bool = True, env_offset: int = 0, host_io: bool = False, stream=None,
+                 device_tables=None):
         """host_io=True: the TimeStep fields (obs, reward, step_type) live in ONE pinned host buffer that the step
         kernel writes directly over PCIe (zero-copy), and `step_host` reads the actions straight from a pinned host
         tensor: an agent running on the host gets its TimeStep with one launch and one stream sync per step, no
-        copy launches (include/colosseum_b200.h, colo_env_batch)."""
+        copy launches (include/colosseum_b200.h, colo_env_batch).  stream: a torch.cuda.Stream the host_io lean path
+        (`step_host`, `send_host`/`recv_host`) launches on instead of the current stream (see PipelinedBatchedMDP)."""
         import torch
 
         assert mode in _MODES
         self.torch = torch
         self.tables = tables
-        self.dev = DeviceTables(tables, mode)
+        self.dev = device_tables if device_tables is not None else DeviceTables(tables, mode)  # shards share one copy
         self.mode = mode
         self.n_envs = int(n_envs)
         self.seed = int(seed)
@@ -141,6 +143,8 @@ class BatchedMDP:
         self._batch_ref = C.byref(b)
         self._own_action_ptr = b.action
         self._sync = lib.colo_stream_synchronize
+        self.stream = stream
+        self._stream_ptr = None if stream is None else int(stream.cuda_stream)
 
     # -- reference attribute surface (base.py:463-503, 1233-1252)
     @property
@@ -233,14 +237,101 @@ class BatchedMDP:
             self._sync(_cabi.current_stream())
             return self.obs, self.reward, self.step_type_host
         # lean path: two ctypes calls (launch, wait); everything else was resolved in __init__
-        stream = _cabi.current_stream()
+        self.send_host(action)
+        return self.recv_host()
+
+    def send_host(self, action):
+        """host_io lean path, first half: launch one auto-resetting step reading `action` (pinned int32) in place."""
+        stream = self._stream_ptr if self._stream_ptr is not None else _cabi.current_stream()
         self._batch.action = action.data_ptr()
         rc = self._step_fn[0](self._tb_ref, self._batch_ref, 0, None, None, self.t, 1, stream)
         if rc != 0:
             _cabi.check(rc, "colo_env_step")
         self.t += 1
-        self._sync(stream)
+        self._pending = stream
+
+    def recv_host(self):
+        """second half: wait for the step launched by `send_host`; returns the pinned host views."""
+        self._sync(self._pending)
         return self.obs, self.reward, self.step_type_host
+
+    # -- step server: the step kernel stays resident and is driven through a doorbell in pinned host memory
+    def serve(self, action, idle_timeout_ms=200, share=1):
+        """Start the persistent step kernel (include/colosseum_b200.h, colo_env_server_*).  `action` is the pinned
+        int32 [N] buffer the agent writes its actions into before every `post()`; the TimeStep fields arrive in the
+        pinned views `wait()` returns.  One step then costs no launch and no stream sync, only PCIe round trips.
+        The kernel retires by itself after `idle_timeout_ms` without a step and is restarted transparently."""
+        torch = self.torch
+        assert self.host_io, "construct the BatchedMDP with host_io=True"
+        assert action.dtype == torch.int32 and action.is_pinned() and action.is_contiguous() \
+            and action.numel() == self.n_envs, "action: pinned contiguous int32 [N]"
+        assert getattr(self, "_srv", None) is None, "already serving"
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+            self._stream_ptr = int(self.stream.cuda_stream)
+        torch.cuda.current_stream().synchronize()  # reset()/steps enqueued on the caller's stream are done
+        self._srv_action = action
+        self._batch.action = action.data_ptr()
+        self._srv_words = torch.zeros(32, dtype=torch.int64).pin_memory()  # doorbell [0], done [16]: own cache lines
+        self._srv_ctl = torch.zeros(2, dtype=torch.int64, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        srv = _cabi.EnvServer()
+        srv.doorbell_host = self._srv_words.data_ptr()
+        srv.done_host = self._srv_words.data_ptr() + 128
+        srv.ctl_dev = self._srv_ctl.data_ptr()
+        srv.share, srv.idle_timeout_ms = int(share), int(idle_timeout_ms)
+        self._srv = srv
+        self._srv_ref = C.byref(srv)
+        self._served = 0
+        self._posted = 0
+        lib = _cabi.lib()
+        self._srv_post, self._srv_wait = lib.colo_env_server_post, lib.colo_env_server_wait
+        self._server_launch()
+        return self
+
+    def _server_launch(self):
+        mode = {"dense_f32": 0, "dense_f64": 1, "succ": 2}[self.mode]
+        rc = _cabi.lib().colo_env_server_start(self._tb_ref, self._batch_ref, self._srv_ref, mode, self.t, self._served,
+                                               self._stream_ptr)
+        _cabi.check(rc, "colo_env_server_start")
+
+    def post(self):
+        """ring the doorbell: the actions in the served buffer are final"""
+        self._posted = self._srv_post(self._srv_ref)
+
+    def wait(self, timeout_ms=10000):
+        """block until the posted step's TimeStep is in host memory; returns the pinned views (obs, reward, step_type)"""
+        rc = self._srv_wait(self._srv_ref, self._posted, timeout_ms)
+        if rc != 0:
+            if rc != _cabi.SERVER_LAPSED:
+                _cabi.check(rc, "colo_env_server_wait")
+            self._sync(self._stream_ptr)  # the retired kernel has left the stream
+            self._server_launch()         # the doorbell already holds the pending step
+            rc = self._srv_wait(self._srv_ref, self._posted, timeout_ms)
+            if rc != 0:
+                raise _cabi.ColosseumB200Error(f"colo_env_server_wait: rc={rc} after a restart: {_cabi.last_error()}")
+        if self._served != self._posted:
+            self._served = self._posted
+            self.t += 1
+        return self.obs, self.reward, self.step_type_host
+
+    def step_served(self):
+        self.post()
+        return self.wait()
+
+    def stop_serving(self):
+        if getattr(self, "_srv", None) is None:
+            return
+        rc = _cabi.lib().colo_env_server_stop(self._srv_ref, self._stream_ptr)
+        self._srv = None
+        self._batch.action = self._own_action_ptr
+        _cabi.check(rc, "colo_env_server_stop")
+
+    def __del__(self):
+        try:
+            self.stop_serving()
+        except Exception:
+            pass
 
     def fetch_async(self, host_buffer):
         """one device->host copy of (obs i32[N] | reward f32[N] | step_type u8[N]) into a pinned uint8 buffer of
@@ -322,3 +413,80 @@ class BatchedMDP:
         if self._visits_s is not None:
             self._visits_s.zero_()
             self._visits_sa.zero_()
+
+
+class PipelinedBatchedMDP:
+    """N parallel envs split into `groups` contiguous shards, each a host_io BatchedMDP on its own stream, stepped in
+    a software pipeline: while the host agent reads group g's TimeStep and writes its next actions, the other
+    groups' step kernels are doing their PCIe reads/writes.  Env i of group g is global env g*N/groups + i
+    (`env_offset`), so the trajectories are those of the unsplit batch.
+
+        env = PipelinedBatchedMDP(tables, 65536, groups=2); env.reset()
+        for g in range(env.groups): env.send(g, actions[g])         # prime
+        while ...:
+            for g in range(env.groups):
+                obs, reward, step_type = env.recv(g)                 # group g's TimeStep (pinned host views)
+                ...agent writes actions[g] (pinned int32)...
+                env.send(g, actions[g])
+    """
+
+    def __init__(self, tables: MDPTables, n_envs: int, groups: int = 2, mode: str = "dense_f32", seed: int = 0,
+                 track_visits: bool = True, env_offset: int = 0):
+        import torch
+
+        self._serving = False
+
+        assert groups >= 1 and n_envs % groups == 0, "n_envs must be a multiple of groups"
+        self.groups = int(groups)
+        self.n_envs = int(n_envs)
+        self.per_group = n_envs // groups
+        dev = DeviceTables(tables, mode)
+        self.shards = [BatchedMDP(tables, self.per_group, mode=mode, seed=seed, track_visits=track_visits,
+                                  env_offset=env_offset + g * self.per_group, host_io=True,
+                                  stream=torch.cuda.Stream(), device_tables=dev)
+                       for g in range(groups)]
+        torch.cuda.synchronize()  # the buffers were initialised on the default stream
+
+    def reset(self):
+        import torch
+
+        out = []
+        for sh in self.shards:
+            with torch.cuda.stream(sh.stream):
+                out.append(sh.reset())
+        return out
+
+    def serve(self, actions, idle_timeout_ms=200):
+        """switch every group to its persistent step kernel (BatchedMDP.serve); `actions[g]` is group g's pinned
+        action buffer, from then on `send(g)` takes no argument"""
+        for sh, a in zip(self.shards, actions):
+            sh.serve(a, idle_timeout_ms=idle_timeout_ms, share=self.groups)
+        self._serving = True
+        return self
+
+    def stop_serving(self):
+        for sh in self.shards:
+            sh.stop_serving()
+        self._serving = False
+
+    def send(self, g: int, action=None):
+        if self._serving:
+            self.shards[g].post()
+        else:
+            self.shards[g].send_host(action)
+
+    def recv(self, g: int):
+        return self.shards[g].wait() if self._serving else self.shards[g].recv_host()
+
+    def step_all(self, actions):
+        """one step of every env: launches all groups, then waits for each (actions: list of pinned int32 [N/groups])"""
+        for sh, a in zip(self.shards, actions):
+            sh.send_host(a)
+        return [sh.recv_host() for sh in self.shards]
+
+    def get_visitation_counts(self, state_only=True):
+        tot = None
+        for sh in self.shards:
+            v = sh.get_visitation_counts(state_only)
+            tot = v if tot is None else tot + v
+        return tot

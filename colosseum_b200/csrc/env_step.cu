@@ -13,6 +13,7 @@
 // COUNT of entries <= x, i.e. one integer warp reduction, no branches and no early exit.
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "common.cuh"
 
@@ -40,7 +41,88 @@ struct StepIO {
   int* status;
   unsigned char* step_type_mirror;  // write-only second target of step_type (pinned host memory) or null
   int n_steps;  // > 1: that many consecutive steps in ONE launch (random actions; Philox counter t, t+1, ...)
+  // persistent step server (colo_env_server_*; SERVER kernels only): the kernel stays resident and runs one pass per
+  // doorbell value posted by the host instead of one pass per launch
+  const unsigned long long* srv_doorbell;  // pinned host, written by the host: index of the newest requested step
+  unsigned long long* srv_done;            // pinned host, written by the kernel: index of the newest finished step
+  unsigned long long* srv_go;              // device: the doorbell as relayed by CTA 0
+  unsigned long long* srv_arrive;          // device: CTA passes finished, monotonic
+  unsigned long long srv_seq0;             // steps served before this launch
+  unsigned long long srv_idle_ns;          // the server retires after this long without a doorbell
 };
+
+constexpr unsigned long long kSrvExit = ~0ULL, kSrvLapsed = ~0ULL - 1;
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Server side of the doorbell protocol.  CTA 0 alone polls the host word (one PCIe read per poll) and relays it
+// through a device word the other CTAs poll in L2.  Returns false when the server has to retire (host asked, or no
+// doorbell for srv_idle_ns: a forgotten server must not hold the GPU).
+__device__ __forceinline__ bool server_wait(const StepIO& io, unsigned long long want) {
+  __shared__ unsigned long long s_cmd;
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    if (blockIdx.x == 0) {
+      const unsigned long long t0 = global_ns();
+      for (;;) {
+        v = ld_sys_u64(io.srv_doorbell);
+        if (v == want || v == kSrvExit) break;
+        if (global_ns() - t0 > io.srv_idle_ns) {
+          v = kSrvExit;
+          st_sys_u64(io.srv_done, kSrvLapsed);
+          break;
+        }
+      }
+      __threadfence_system();  // the host wrote the actions before the doorbell: order our reads after it
+      st_release_gpu_u64(io.srv_go, v);
+    } else {
+      for (;;) {
+        v = ld_acquire_gpu_u64(io.srv_go);
+        if (v == want || v == kSrvExit) break;
+        __nanosleep(40);
+      }
+    }
+    s_cmd = v;
+  }
+  __syncthreads();
+  const bool run = s_cmd != kSrvExit;
+  __syncthreads();
+  return run;
+}
+
+// every thread's host writes are fenced to system scope before its CTA arrives; the last CTA publishes the step
+__device__ __forceinline__ void server_done(const StepIO& io, unsigned long long step_index) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long passes = step_index - io.srv_seq0;  // passes finished by every CTA once all arrive
+    const unsigned long long prev = atomicAdd(io.srv_arrive, 1ULL);
+    if (prev + 1 == passes * gridDim.x) {
+      __threadfence_system();
+      st_sys_u64(io.srv_done, step_index);
+    }
+  }
+}
 
 __device__ __forceinline__ float reward_draw(const colo_mdp_tables& tb, int cls, float u) {
   const float* q = tb.rew_q + (size_t)cls * tb.nq;
@@ -125,7 +207,7 @@ __device__ __forceinline__ EnvIn load_env(const StepIO& io, const colo_mdp_table
     in.un32 = u24(w.w[0]);
   }
   in.ur = io.u_rew ? io.u_rew[e] : u24(w.w[2]);
-  in.a = io.random_actions ? act_from_word(w.w[3], tb.A) : io.action[e];
+  in.a = io.random_actions ? act_from_word(w.w[3], tb.A) : (io.srv_go ? __ldcv(io.action + e) : io.action[e]);
   return in;
 }
 
@@ -195,7 +277,7 @@ __device__ __forceinline__ int row_count_below(const TC* __restrict__ row, int l
 
 constexpr int kEnvUnroll = 4;  // independent row searches in flight per warp
 
-template <typename TC, int NCH>
+template <typename TC, int NCH, bool SERVER>
 __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo_mdp_tables tb, const StepIO io) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * kStepThreads + threadIdx.x) >> 5;
@@ -205,13 +287,19 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
   const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
   constexpr bool F32U = sizeof(TC) == 4;
 
+  for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
+  unsigned long long t_pass = io.t;
+  if (SERVER) {
+    if (!server_wait(io, pass)) return;
+    t_pass += pass - io.srv_seq0 - 1;
+  }
   for (long long tile = warp_global; tile < n_tiles; tile += n_warps)
   for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same lane for every step of the launch
     const long long e = tile * 32 + lane;
     const bool valid = e < io.N;
     EnvIn in;
     in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
-    if (valid) in = load_env<F32U>(io, tb, e, io.t + step);
+    if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
     const bool stepping = valid && !is_last;
@@ -248,6 +336,9 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
     }
     finish_env(io, tb, valid ? e : 0, in, my_next, cls, stepping, resetting);
   }
+  if (!SERVER) return;
+  server_done(io, pass);
+  }
 }
 
 // SHORT rows (ld == 128 * NCH, NCH <= 8; the host pads rows of S <= 1024 to whole 128-entry chunks):
@@ -256,7 +347,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
 // ballot + popc per chunk.  The within-quad step is deferred to the epilogue, where lane i finishes env i on its
 // own (one 16-byte gather of quad G, which the warp has just pulled into L1), i.e. it is vectorised over the 32
 // envs of the tile instead of costing shuffles and selects inside the per-env loop.
-template <typename TC, int NCH, int U, int TILE>
+template <typename TC, int NCH, int U, int TILE, bool SERVER>
 __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(const colo_mdp_tables tb, const StepIO io) {
   // TILE envs per warp (lanes >= TILE idle in the per-lane phases): smaller tiles = more warps in flight when the
   // batch alone cannot fill the machine (65,536 envs / 32 = 14 warps per SM)
@@ -269,13 +360,19 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
   const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
   constexpr bool F32U = sizeof(TC) == 4;
 
+  for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
+  unsigned long long t_pass = io.t;
+  if (SERVER) {
+    if (!server_wait(io, pass)) return;
+    t_pass += pass - io.srv_seq0 - 1;
+  }
   for (long long tile = warp_global; tile < n_tiles; tile += n_warps)
   for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same lane for every step of the launch
     const long long e = tile * TILE + lane;
     const bool valid = lane < TILE && e < io.N;
     EnvIn in;
     in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
-    if (valid) in = load_env<F32U>(io, tb, e, io.t + step);
+    if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
     const bool stepping = valid && !is_last;
@@ -329,18 +426,28 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
     }
     finish_env(io, tb, valid ? e : 0, in, nxt, cls, stepping, resetting);
   }
+  if (!SERVER) return;
+  server_done(io, pass);
+  }
 }
 
+template <bool SERVER>
 __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_mdp_tables tb, const StepIO io) {
   const long long n_thr = (long long)gridDim.x * kStepThreads;
   // round the loop bound up to whole warps: finish_env uses warp collectives
   const long long n_pad = (io.N + 31) & ~31LL;
+  for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
+  unsigned long long t_pass = io.t;
+  if (SERVER) {
+    if (!server_wait(io, pass)) return;
+    t_pass += pass - io.srv_seq0 - 1;
+  }
   for (long long e = (long long)blockIdx.x * kStepThreads + threadIdx.x; e < n_pad; e += n_thr)
   for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same thread for every step of the launch
     const bool valid = e < io.N;
     EnvIn in;
     in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
-    if (valid) in = load_env<false>(io, tb, e, io.t + step);
+    if (valid) in = load_env<false>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
     const bool stepping = valid && !is_last;
@@ -359,6 +466,9 @@ __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_
       cls = tb.rew_cls_succ ? __ldg(tb.rew_cls_succ + base + pos) : 0;
     }
     finish_env(io, tb, valid ? e : 0, in, nxt, cls, stepping, resetting);
+  }
+  if (!SERVER) return;
+  server_done(io, pass);
   }
 }
 
@@ -438,8 +548,28 @@ static int check_tables_common(const colo_mdp_tables* tb) {
   return COLO_OK;
 }
 
-template <typename TC>
-static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* stream) {
+// SERVER launches must be wholly co-resident (the CTAs of a pass meet at a counter): the grid is capped at
+// 1/share of what the device holds at once
+template <typename K>
+static int resident_cap(K kernel, int share) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStepThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int cap = per_sm * sm_count() / (share < 1 ? 1 : share);
+  return cap < 1 ? 1 : cap;
+}
+
+template <typename K>
+static void launch_step(K kernel, int grid, bool server, int share, const colo_mdp_tables* tb, const StepIO& io,
+                        cudaStream_t st) {
+  if (server) {
+    const int cap = resident_cap(kernel, share);
+    grid = grid < cap ? grid : cap;
+  }
+  kernel<<<grid, kStepThreads, 0, st>>>(*tb, io);
+}
+
+template <typename TC, bool SERVER>
+static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* stream, int share = 1) {
   int r = check_tables_common(tb);
   if (r != COLO_OK) return r;
   COLO_ARG_CHECK(tb->cdf && tb->ld >= tb->S && tb->ld % 4 == 0, "dense cdf with ld % 4 == 0 is required");
@@ -457,11 +587,11 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
     int tile = warps32 >= (long long)sm_count() * 8 ? 32 : (warps32 >= (long long)sm_count() * 4 ? 16 : 8);
     if (forced == 8 || forced == 16 || forced == 32) tile = forced;
     const int grid = grid_for(kStepThreads / 32, (io.N + tile - 1) / tile);
-#define COLO_SHORT(NCH, U)                                                                               \
-  case NCH:                                                                                              \
-    if (tile == 32) env_step_dense_short_kernel<TC, NCH, U, 32><<<grid, kStepThreads, 0, st>>>(*tb, io);  \
-    else if (tile == 16) env_step_dense_short_kernel<TC, NCH, U, 16><<<grid, kStepThreads, 0, st>>>(*tb, io); \
-    else env_step_dense_short_kernel<TC, NCH, U, 8><<<grid, kStepThreads, 0, st>>>(*tb, io);             \
+#define COLO_SHORT(NCH, U)                                                                                        \
+  case NCH:                                                                                                       \
+    if (tile == 32) launch_step(env_step_dense_short_kernel<TC, NCH, U, 32, SERVER>, grid, SERVER, share, tb, io, st);      \
+    else if (tile == 16) launch_step(env_step_dense_short_kernel<TC, NCH, U, 16, SERVER>, grid, SERVER, share, tb, io, st); \
+    else launch_step(env_step_dense_short_kernel<TC, NCH, U, 8, SERVER>, grid, SERVER, share, tb, io, st);                  \
     break
     switch (ld / 128) {
       COLO_SHORT(1, 4);
@@ -476,9 +606,18 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
 #undef COLO_SHORT
   } else {
     const int grid = grid_for(kStepThreads / 32, (io.N + 31) / 32);
-    env_step_dense_kernel<TC, 8><<<grid, kStepThreads, 0, st>>>(*tb, io);
+    launch_step(env_step_dense_kernel<TC, 8, SERVER>, grid, SERVER, share, tb, io, st);
   }
   return check_launch("env_step_dense_kernel");
+}
+
+template <bool SERVER>
+static int launch_succ(const colo_mdp_tables* tb, const StepIO& io, void* stream, int share = 1) {
+  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
+  COLO_ARG_CHECK(io.reward && io.action, "env buffers");
+  if (io.N == 0) return COLO_OK;
+  launch_step(env_step_succ_kernel<SERVER>, grid_for(kStepThreads, io.N), SERVER, share, tb, io, (cudaStream_t)stream);
+  return check_launch("env_step_succ_kernel");
 }
 
 }  // namespace colo
@@ -523,7 +662,7 @@ int colo_env_step_dense_f32(const colo_mdp_tables* tb, const colo_env_batch* bat
   colo::StepIO io;
   r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
   if (r != COLO_OK || io.N == 0) return r;
-  return colo::launch_dense<float>(tb, io, stream);
+  return colo::launch_dense<float, false>(tb, io, stream);
 }
 
 int colo_env_step_dense_f64(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
@@ -534,7 +673,7 @@ int colo_env_step_dense_f64(const colo_mdp_tables* tb, const colo_env_batch* bat
   colo::StepIO io;
   r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
   if (r != COLO_OK || io.N == 0) return r;
-  return colo::launch_dense<double>(tb, io, stream);
+  return colo::launch_dense<double, false>(tb, io, stream);
 }
 
 int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
@@ -545,12 +684,7 @@ int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, i
   colo::StepIO io;
   r = make_io(tb, batch, random_actions, u_next, u_rew, t, auto_reset, &io);
   if (r != COLO_OK || io.N == 0) return r;
-  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
-  COLO_ARG_CHECK(io.reward && io.action, "env buffers");
-  if (io.N == 0) return COLO_OK;
-  const int grid = colo::grid_for(colo::kStepThreads, io.N);
-  colo::env_step_succ_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
-  return colo::check_launch("env_step_succ_kernel");
+  return colo::launch_succ<false>(tb, io, stream);
 }
 
 int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch, int mode, int n_steps,
@@ -562,14 +696,82 @@ int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch
   r = make_io(tb, batch, 1, nullptr, nullptr, t0, auto_reset, &io);
   if (r != COLO_OK || io.N == 0) return r;
   io.n_steps = n_steps;
-  if (mode == 0) return colo::launch_dense<float>(tb, io, stream);
-  if (mode == 1) return colo::launch_dense<double>(tb, io, stream);
-  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
-  COLO_ARG_CHECK(io.reward && io.action, "env buffers");
-  if (io.N == 0) return COLO_OK;
-  const int grid = colo::grid_for(colo::kStepThreads, io.N);
-  colo::env_step_succ_kernel<<<grid, colo::kStepThreads, 0, (cudaStream_t)stream>>>(*tb, io);
-  return colo::check_launch("env_step_succ_kernel");
+  if (mode == 0) return colo::launch_dense<float, false>(tb, io, stream);
+  if (mode == 1) return colo::launch_dense<double, false>(tb, io, stream);
+  return colo::launch_succ<false>(tb, io, stream);
+}
+
+int colo_env_server_start(const colo_mdp_tables* tb, const colo_env_batch* batch, const colo_env_server* srv, int mode,
+                          unsigned long long t, unsigned long long served, void* stream) {
+  int r = colo::check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(srv && srv->doorbell_host && srv->done_host && srv->ctl_dev, "server control words");
+  COLO_ARG_CHECK(mode >= 0 && mode <= 2 && srv->share >= 1 && srv->idle_timeout_ms > 0, "mode, share, idle_timeout_ms");
+  colo::StepIO io;
+  r = make_io(tb, batch, 0, nullptr, nullptr, t, 1, &io);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(io.N > 0, "a served batch cannot be empty");
+  // `served` steps are finished; the doorbell may already hold served + 1 (a step posted while the last server lapsed)
+  const unsigned long long seq = served;
+  const unsigned long long bell = *(volatile unsigned long long*)srv->doorbell_host;
+  COLO_ARG_CHECK(bell == seq || bell == seq + 1, "doorbell must hold `served` or `served + 1`");
+  __atomic_store_n(srv->done_host, seq, __ATOMIC_SEQ_CST);
+  io.srv_doorbell = srv->doorbell_host;
+  io.srv_done = srv->done_host;
+  io.srv_go = srv->ctl_dev;
+  io.srv_arrive = srv->ctl_dev + 1;
+  io.srv_seq0 = seq;
+  io.srv_idle_ns = (unsigned long long)srv->idle_timeout_ms * 1000000ULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  // go = seq (nothing pending), arrive = 0: written on the launch stream ahead of the kernel
+  const unsigned long long init[2] = {seq, 0ULL};
+  COLO_CUDA_TRY(cudaMemcpyAsync(srv->ctl_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  if (mode == 0) return colo::launch_dense<float, true>(tb, io, stream, srv->share);
+  if (mode == 1) return colo::launch_dense<double, true>(tb, io, stream, srv->share);
+  return colo::launch_succ<true>(tb, io, stream, srv->share);
+}
+
+unsigned long long colo_env_server_post(const colo_env_server* srv) {
+  // the caller finished writing the actions: publish them with the doorbell
+  unsigned long long* d = srv->doorbell_host;
+  const unsigned long long next = *d + 1;
+  __atomic_store_n(d, next, __ATOMIC_SEQ_CST);
+  return next;
+}
+
+int colo_env_server_wait(const colo_env_server* srv, unsigned long long step_index, unsigned timeout_ms) {
+  const unsigned long long* done = srv->done_host;
+  unsigned long long spins = 0;
+  struct timespec t0 = {0, 0};
+  for (;;) {
+    const unsigned long long v = __atomic_load_n(done, __ATOMIC_ACQUIRE);
+    if (v == colo::kSrvLapsed) return COLO_SERVER_LAPSED;
+    if (v >= step_index) return COLO_OK;
+    if ((++spins & 0xfff) == 0) {  // look at the clock every 4096 polls only
+      struct timespec now;
+      clock_gettime(CLOCK_MONOTONIC, &now);
+      if (t0.tv_sec == 0 && t0.tv_nsec == 0) t0 = now;
+      const double ms = (now.tv_sec - t0.tv_sec) * 1e3 + (now.tv_nsec - t0.tv_nsec) * 1e-6;
+      if (ms > (double)timeout_ms) {
+        colo::set_error("colo_env_server_wait: step %llu not finished after %u ms (done = %llu)", step_index, timeout_ms, v);
+        return COLO_ERR_CUDA;
+      }
+    }
+  }
+}
+
+int colo_env_server_stop(const colo_env_server* srv, void* stream) {
+  COLO_ARG_CHECK(srv && srv->doorbell_host, "server control words");
+  unsigned long long* d = srv->doorbell_host;
+  const unsigned long long seq = *d;
+  __atomic_store_n(d, colo::kSrvExit, __ATOMIC_SEQ_CST);
+  const cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  __atomic_store_n(d, seq, __ATOMIC_SEQ_CST);  // the step count survives for the next start
+  if (e != cudaSuccess) {
+    colo::set_error("colo_env_server_stop: %s", cudaGetErrorString(e));
+    return COLO_ERR_CUDA;
+  }
+  return COLO_OK;
 }
 
 int colo_emit_observations(const float* table, const int* state, const int* h, const unsigned char* step_type,

@@ -33,6 +33,7 @@ extern "C" {
 #define COLO_OVERFLOW 1
 #define COLO_MAX_ITER 2
 #define COLO_NEEDS_RESET 3
+#define COLO_SERVER_LAPSED 4
 #define COLO_ERR_CUDA (-1)
 #define COLO_ERR_ARG (-2)
 
@@ -440,6 +441,38 @@ int colo_emit_observations(const float* table, const int* state, const int* h, c
 int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
                        const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
                        void* stream);
+
+/*
+ * Step server -- BaseMDP.step (base.py:1279-1317) for an agent living on the host, without a launch and a stream
+ * synchronisation per step.  colo_env_server_start launches the step kernel of `mode` (0 dense f32 rows, 1 dense f64
+ * rows, 2 successor tables; auto_reset on, Philox uniforms) as a PERSISTENT kernel on `stream` (which must be a
+ * non-blocking stream of its own).  batch->action / reward / obs / step_type_mirror are pinned host buffers, fixed
+ * for the life of the server.  One step = the host writes the actions, colo_env_server_post() rings the doorbell,
+ * the resident kernel reads the actions over PCIe, steps every env with Philox counter t + (step index - served - 1)
+ * and writes the TimeStep fields into the pinned buffers, the last CTA publishes the step index in done_host, and
+ * colo_env_server_wait() returns once it sees it (it spins on host memory; no CUDA call).  Bit-identical to the same
+ * steps through colo_env_step_*.
+ *   doorbell_host, done_host : one pinned u64 each (own cache lines);  ctl_dev : two device u64
+ *   share          : the kernel takes at most 1/share of the CTAs the device can hold at once (servers running side
+ *                    by side must not starve each other: their CTAs meet at a counter and must all be resident)
+ *   idle_timeout_ms: the kernel retires by itself after this long without a doorbell (a forgotten server must not
+ *                    hold the GPU); a wait that meets a retired server returns COLO_SERVER_LAPSED and the caller
+ *                    restarts it with served = steps finished so far (the doorbell may already hold served + 1)
+ * colo_env_server_stop retires the kernel and synchronises `stream`.  Nothing else may be enqueued on `stream` while
+ * the server runs; a device-wide synchronisation blocks until it retires.
+ */
+typedef struct {
+  unsigned long long* doorbell_host;
+  unsigned long long* done_host;
+  unsigned long long* ctl_dev;
+  int share;
+  unsigned idle_timeout_ms;
+} colo_env_server;
+int colo_env_server_start(const colo_mdp_tables* tb, const colo_env_batch* batch, const colo_env_server* srv, int mode,
+                          unsigned long long t, unsigned long long served, void* stream);
+unsigned long long colo_env_server_post(const colo_env_server* srv);
+int colo_env_server_wait(const colo_env_server* srv, unsigned long long step_index, unsigned timeout_ms);
+int colo_env_server_stop(const colo_env_server* srv, void* stream);
 
 /* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
  * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */

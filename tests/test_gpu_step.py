@@ -358,3 +358,82 @@ def test_emission_table_gather(bm, name):
         if tb.H:
             exp = np.where((st == 2)[:, None, None], 0.0, exp)
         assert obs.shape == (N,) + shape and np.array_equal(obs, exp.astype(np.float32))
+
+
+@pytest.mark.parametrize("name,mode", [("c2_deepsea30_prand", "dense_f32"), ("taxi_epi", "succ"),
+                                       ("c1_riverswim_epi", "dense_f64")])
+def test_step_server_is_identical(bm, name, mode):
+    """BatchedMDP.serve(): the persistent step kernel driven by the host doorbell emits, step by step, exactly what
+    one launch per step emits and what the oracle emits -- across an idle lapse (the kernel retires by itself and is
+    restarted) and across stop/serve."""
+    import time
+
+    import torch
+
+    g = load_instance(name)
+    tb = MDPTables.from_golden(g)
+    N = 3000
+    ref = bm.BatchedMDP(tb, N, mode=mode, seed=5, host_io=True)
+    srv = bm.BatchedMDP(tb, N, mode=mode, seed=5, host_io=True)
+    ref.reset(), srv.reset()
+    omode = {"dense_f32": 0, "dense_f64": 1, "succ": 2}[mode]
+    ht = host_tables(tb, omode, None if omode == 2 else ref.dev.keep["cdf"].cpu().numpy())
+    state, h, st, obs = orc.env_reset(ht, N, seed=5, t=0)
+    buf = torch.zeros(N, dtype=torch.int32).pin_memory()
+    srv.serve(buf, idle_timeout_ms=50)
+    gen = torch.Generator().manual_seed(9)
+    n_steps = 2 * max(tb.H, 10) + 3
+    try:
+        for t in range(1, n_steps):
+            a = torch.randint(0, tb.A, (N,), dtype=torch.int32, generator=gen).pin_memory()
+            o1, r1, s1 = [x.clone() for x in ref.step_host(a, auto_reset=True)]
+            buf.copy_(a)
+            o2, r2, s2 = srv.step_served()
+            ro, oo, rc, _ = orc.env_step(ht, omode, state, h, st, action=a.numpy(), seed=5, t=t, auto_reset=True)
+            assert torch.equal(o1, o2) and torch.equal(s1, s2)
+            assert np.array_equal(r1.numpy(), r2.numpy(), equal_nan=True)
+            assert np.array_equal(o2.numpy(), oo) and np.array_equal(r2.numpy(), ro, equal_nan=True)
+            if t == 4:
+                time.sleep(0.25)  # > idle timeout: the server lapses, the next step restarts it
+            if t == 8:
+                srv.stop_serving()
+                srv.serve(buf, idle_timeout_ms=50)
+    finally:
+        srv.stop_serving()
+    assert srv.t == ref.t
+    assert torch.equal(ref.visits_sa, srv.visits_sa) and torch.equal(ref.state, srv.state)
+
+
+def test_pipelined_groups_equal_the_unsplit_batch(bm):
+    """PipelinedBatchedMDP: G groups on their own streams, stepped recv/send in a pipeline, walk the trajectories of
+    the single batch (env_offset keeps the Philox counters); launch-per-step and served modes."""
+    import torch
+
+    tb = MDPTables.from_golden(load_instance("c2_deepsea30_prand"))
+    N, G = 4096, 2
+    gen = torch.Generator().manual_seed(1)
+    acts = [torch.randint(0, tb.A, (N,), dtype=torch.int32, generator=gen).pin_memory() for _ in range(12)]
+    one = bm.BatchedMDP(tb, N, seed=3, host_io=True)
+    one.reset()
+    want = [[x.clone() for x in one.step_host(a, auto_reset=True)] for a in acts]
+    for serving in (False, True):
+        env = bm.PipelinedBatchedMDP(tb, N, groups=G, seed=3)
+        env.reset()
+        bufs = [torch.zeros(N // G, dtype=torch.int32).pin_memory() for _ in range(G)]
+        if serving:
+            env.serve(bufs, idle_timeout_ms=100)
+        try:
+            for k, a in enumerate(acts):
+                parts = []
+                for g in range(G):
+                    bufs[g].copy_(a[g * (N // G):(g + 1) * (N // G)])
+                    env.send(g, None if serving else bufs[g])
+                for g in range(G):
+                    parts.append([x.clone() for x in env.recv(g)])
+                for j in range(3):
+                    got = torch.cat([p[j] for p in parts])
+                    assert np.array_equal(got.numpy(), want[k][j].numpy(), equal_nan=True), (serving, k, j)
+        finally:
+            if serving:
+                env.stop_serving()
+        assert torch.equal(env.get_visitation_counts(False), one.visits_sa)
