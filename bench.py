@@ -335,6 +335,34 @@ def bench_step_gpu(args, rank, world):
                 pipe=pipe, served=served)
 
 
+def bench_agents_gpu(args, rank, world):
+    """N independent (QLearningContinuous agent, env) loops on the C2 MDP, 500 steps per launch"""
+    import torch
+
+    import colosseum_b200.agent_loop as al
+
+    try:
+        tb = load_c2_tables()
+        n_loops, K = 65536, 500
+        ag = al.QLearningContinuous(1234, tb, 10 ** 6, n_loops=n_loops, env_offset=rank * n_loops)
+        ag.steps(50)
+        barrier_sync(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ag.steps(K)
+        e1.record()
+        barrier_sync(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world)
+        assert float(ag.cumulative_reward.min()) >= 0.0 and int(ag.N.sum()) == n_loops * (K + 50)
+        return {"value": world * n_loops * K / (ms / 1e3), "unit": "agent-steps/s", "loops_per_gpu": n_loops,
+                "steps_per_launch": K, "gpu_launches": 1,
+                "what": "QLearningContinuous (select action, env step on the reference's sampler tables, model update) "
+                        f"for {n_loops} independent loops per GPU on the C2 MDP, one thread per loop, agent tables "
+                        f"{n_loops * tb.S * tb.A * 12 / 2**20:.0f} MiB per GPU"}
+    except Exception as exc:
+        return {"error": repr(exc)[:200]}
+
+
 def make_c4_batch(B, S, A, seed):
     """C4's generator on the device: T[b,s,a,:] ~ Dirichlet(0.05), rows renormalised in fp32; R ~ U[0,1)"""
     import torch
@@ -623,6 +651,7 @@ def main():
     vi = bench_vi_gpu(args, rank, world) if args.workload in ("all", "vi") else None
     c5 = bench_c5_gpu(args, rank, world) if args.workload in ("all", "c5") else None
     c3 = bench_c3_gpu(args, rank, world) if args.workload == "c3" else None  # minutes: opt-in, not part of "all"
+    agents = bench_agents_gpu(args, rank, world) if args.workload == "all" else None
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
@@ -783,6 +812,8 @@ def main():
         tgt["cpu_baseline"] = {"value": rate, "unit": "MDP-sweeps/s", "cores": os.cpu_count(), "kind": "port",
                                "sample": f"{n} in-place fp32 sweeps x 64 MDPs (S=512,A=4) in {dt:.1f}s (C+OpenMP port "
                                          "of _discounted_value_iteration's sweep)"}
+    if agents is not None:
+        line["agents"] = agents
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

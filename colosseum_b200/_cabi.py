@@ -86,6 +86,21 @@ class EnvServer(C.Structure):
                 ("share", C.c_int), ("idle_timeout_ms", C.c_uint)]
 
 
+class QLearningArgs(C.Structure):
+    """mirror of `colo_qlearning_args`"""
+
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_ulonglong), ("env0", C.c_ulonglong),
+        ("state", C.c_void_p), ("h", C.c_void_p), ("cnt", C.c_void_p), ("Q", C.c_void_p), ("Q_main", C.c_void_p),
+        ("V", C.c_void_p), ("mu", C.c_void_p), ("sigma", C.c_void_p), ("beta", C.c_void_p),
+        ("ucb_type", C.c_int),
+        ("c_1", C.c_double), ("c_2", C.c_double), ("min_at", C.c_double), ("log_term", C.c_double),
+        ("sqrt_h7sa", C.c_double), ("H_eff", C.c_double), ("gamma", C.c_double), ("span_approx", C.c_double),
+        ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p), ("n_episodes", C.c_void_p),
+        ("trace", C.c_void_p),
+    ]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _ULL = C.c_ulonglong
@@ -136,6 +151,8 @@ PROTOTYPES = {
     "colo_env_server_post": (_ULL, [C.POINTER(EnvServer)]),
     "colo_env_server_wait": (_I, [C.POINTER(EnvServer), _ULL, C.c_uint]),
     "colo_env_server_stop": (_I, [C.POINTER(EnvServer), _P]),
+    "colo_qlearning_episodic_steps": (_I, [C.POINTER(MdpTables), C.POINTER(QLearningArgs), _I, _ULL, _P]),
+    "colo_qlearning_continuous_steps": (_I, [C.POINTER(MdpTables), C.POINTER(QLearningArgs), _I, _ULL, _P]),
     "colo_emit_observations": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _P, _P]),
     "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "colo_extended_vi_work_bytes": (C.c_size_t, [_I, _I]),

@@ -1,0 +1,218 @@
+"""N independent agent/MDP interaction loops on the device.
+
+The reference runs one `MDPLoop` (colosseum/experiment/agent_mdp_interaction.py:160-298) per (agent, MDP, seed) and
+spreads the seeds over processes.  Here the N loops of one (agent class, MDP) pair -- N seeds -- are the lanes of one
+kernel (`csrc/agents.cu`): every loop owns its env and its agent tables, and `log_every` iterations of MDPLoop.run's
+body execute per launch.  Classes keep the reference's names and constructor arguments:
+
+    QLearningEpisodic   colosseum/agent/agents/episodic/q_learning.py:106-240   (Jin et al. 2018; Hoeffding / Bernstein)
+    QLearningContinuous colosseum/agent/agents/infinite_horizon/q_learning.py:114-255 (Wei et al. 2020)
+    BatchedMDPLoop.run(T, log_every)  MDPLoop.run: cumulative reward per loop, and at every log tick the expected
+                        regret of each loop's greedy policy (experiment/indicators.py:29-45 / markov_chain.py:12-31)
+
+`mdp_specs` is replaced by the `MDPTables` of the MDP (the kernel needs the sampler tables, not only the sizes).
+Boltzmann exploration and callable epsilon schedules are not offered on the device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .batched_mdp import DeviceTables
+from .tables import MDPTables
+
+
+def get_H(n_states, n_actions, T, span_approx, confidence):
+    """infinite_horizon/q_learning.py:21-45"""
+    return min(np.sqrt(span_approx * T / n_states / n_actions),
+               (T / n_states / n_actions / np.log(4 * T / confidence)) ** 0.333)
+
+
+class _QLearningBatch:
+    episodic = None
+
+    def _alloc(self, tables: MDPTables, n_loops: int, seed: int, env_offset: int, epsilon_greedy, boltzmann_temperature):
+        import torch
+
+        _cabi.require_cuda()
+        if boltzmann_temperature is not None:
+            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
+        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
+            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        assert (tables.H > 0) == self.episodic, "episodic agents need an episodic MDP and vice versa"
+        self.torch = torch
+        self.tables = tables
+        self.dev = DeviceTables(tables, "succ")
+        self.n_loops = N = int(n_loops)
+        self.seed, self.env_offset = int(seed), int(env_offset)
+        self.t = 0
+        S, A = tables.S, tables.A
+        self.state = torch.zeros(N, dtype=torch.int32, device="cuda")
+        self.h = torch.zeros(N, dtype=torch.int32, device="cuda")
+        self.cumulative_reward = torch.zeros(N, dtype=torch.float64, device="cuda")
+        self.n_episodes = torch.zeros(N, dtype=torch.int64, device="cuda")
+        a = _cabi.QLearningArgs()
+        a.N, a.seed, a.env0 = N, self.seed, self.env_offset
+        a.state, a.h = self.state.data_ptr(), self.h.data_ptr()
+        a.cum_reward, a.n_episodes = self.cumulative_reward.data_ptr(), self.n_episodes.data_ptr()
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        self._args = a
+        self._fn = (_cabi.lib().colo_qlearning_episodic_steps if self.episodic
+                    else _cabi.lib().colo_qlearning_continuous_steps)
+        self.reset_envs()
+        return S, A
+
+    def reset_envs(self):
+        """mdp.reset() for every loop: start states drawn with the env Philox stream at counter t (as colo_env_reset)"""
+        torch = self.torch
+        tb = self.tables
+        if tb.n_start == 1:
+            self.state.fill_(int(tb.start_idx[0]))
+        else:
+            from .batched_mdp import BatchedMDP
+
+            env = BatchedMDP(tb, self.n_loops, mode="succ", seed=self.seed, env_offset=self.env_offset,
+                             track_visits=False)
+            env.t = self.t
+            env.reset()
+            self.state.copy_(env.state)
+        self.h.zero_()
+        self.t += 1
+        torch.cuda.current_stream().synchronize()
+
+    def steps(self, n_steps: int, trace: bool = False):
+        """n_steps iterations of the interaction loop for every loop, one launch.  trace=True returns
+        i32 [n_steps, N, 4] = (s_t, a_t, obs_tp1, reward bits)."""
+        torch = self.torch
+        tr = torch.empty((n_steps, self.n_loops, 4), dtype=torch.int32, device="cuda") if trace else None
+        self._args.trace = None if tr is None else tr.data_ptr()
+        rc = self._fn(C.byref(self.dev.c), C.byref(self._args), int(n_steps), self.t, _cabi.current_stream())
+        _cabi.check(rc, "colo_qlearning_steps")
+        self.t += int(n_steps)
+        return tr
+
+    def current_optimal_stochastic_policy(self, i: int) -> np.ndarray:
+        """get_policy_from_q_values(Q, True) of loop i (q_learning.py:164-166)"""
+        from .dynamic_programming import get_policy_from_q_values
+
+        return get_policy_from_q_values(self.Q[i].cpu().numpy(), True)
+
+
+class QLearningEpisodic(_QLearningBatch):
+    episodic = True
+
+    def __init__(self, seed: int, tables: MDPTables, optimization_horizon: int, p: float, c_1: float,
+                 c_2: float = None, min_at: float = 0, UCB_type="hoeffding", epsilon_greedy=None,
+                 boltzmann_temperature=None, *, n_loops: int = 1, env_offset: int = 0):
+        UCB_type = UCB_type.lower()
+        assert 0 <= min_at < 0.99 and 0 < p < 1 and c_1 > 0 and UCB_type in ("hoeffding", "bernstein")
+        if UCB_type == "bernstein":
+            assert c_2 is not None and c_2 > 0
+        S, A = self._alloc(tables, n_loops, seed, env_offset, epsilon_greedy, boltzmann_temperature)
+        torch, N, H = self.torch, self.n_loops, tables.H
+        self.N = torch.ones((N, H, S, A), dtype=torch.int32, device="cuda")          # q_learning.py:44
+        self.Q = torch.full((N, H, S, A), float(H), dtype=torch.float32, device="cuda")  # :45-47
+        self.V = torch.zeros((N, H + 1, S), dtype=torch.float32, device="cuda")      # :48
+        a = self._args
+        a.cnt, a.Q, a.V = self.N.data_ptr(), self.Q.data_ptr(), self.V.data_ptr()
+        a.ucb_type = 0
+        if UCB_type == "bernstein":
+            self.mu = torch.zeros((N, H, S, A), dtype=torch.float32, device="cuda")
+            self.sigma = torch.zeros_like(self.mu)
+            self.beta = torch.zeros_like(self.mu)
+            a.mu, a.sigma, a.beta = self.mu.data_ptr(), self.sigma.data_ptr(), self.beta.data_ptr()
+            a.ucb_type = 1
+            a.c_2 = float(c_2)
+        a.c_1, a.min_at = float(c_1), float(min_at)
+        a.log_term = float(np.log(S * A * optimization_horizon / p))                 # :43
+        a.sqrt_h7sa = float(np.sqrt(H ** 7 * S * A))
+        self.i = a.log_term
+
+
+class QLearningContinuous(_QLearningBatch):
+    episodic = False
+
+    def __init__(self, seed: int, tables: MDPTables, optimization_horizon: int, min_at: float = 0,
+                 confidence: float = 0.95, span_approx_weight: float = 1, get_span_approx=None, h_weight: float = 1,
+                 get_H=get_H, epsilon_greedy=None, boltzmann_temperature=None, *, n_loops: int = 1,
+                 env_offset: int = 0):
+        assert 0 <= min_at < 0.99 and 0 < confidence < 1 and span_approx_weight > 0 and h_weight > 0
+        S, A = self._alloc(tables, n_loops, seed, env_offset, epsilon_greedy, boltzmann_temperature)
+        torch, N = self.torch, self.n_loops
+        self.min_at = min_at if min_at > 0.009 else 0                                # :62
+        self.span_approx = span_approx_weight
+        if get_span_approx is not None:
+            self.span_approx *= get_span_approx(S, A)
+        self.H = float(h_weight * get_H(S, A, optimization_horizon, self.span_approx, confidence))
+        self.gamma = 1 - 1 / self.H
+        self.N = torch.zeros((N, S, A), dtype=torch.int32, device="cuda")
+        self.Q = torch.full((N, S, A), self.H, dtype=torch.float32, device="cuda")
+        self.Q_main = torch.full((N, S, A), self.H, dtype=torch.float32, device="cuda")
+        self.V = torch.full((N, S), self.H, dtype=torch.float32, device="cuda")
+        a = self._args
+        a.cnt, a.Q, a.Q_main, a.V = self.N.data_ptr(), self.Q.data_ptr(), self.Q_main.data_ptr(), self.V.data_ptr()
+        a.min_at, a.H_eff, a.gamma, a.span_approx = float(self.min_at), self.H, float(self.gamma), float(self.span_approx)
+        a.log_term = float(np.log(2 * optimization_horizon / confidence))
+
+
+class BatchedMDPLoop:
+    """MDPLoop for N loops at once.  `T`, `R` (numpy float32) are only needed for the regret indicators."""
+
+    def __init__(self, agents: _QLearningBatch, T=None, R=None):
+        self.agents = agents
+        self.T, self.R = T, R
+        self.logs = []
+
+    def _expected_regret(self, loops):
+        """per-step expected regret of the greedy policy of each loop in `loops`
+        (agent_mdp_interaction.py:520-578: episodic -> regret at time zero / H; continuous -> optimal minus the
+        policy's average reward)."""
+        from . import dynamic_programming as dp
+        from . import indicators, markov_chain
+
+        ag, tb = self.agents, self.agents.tables
+        out = np.zeros(len(loops))
+        if ag.episodic:
+            start = np.zeros(tb.S, np.float64)
+            prob = np.diff(np.concatenate([[0.0], np.asarray(tb.start_cum, np.float64)]))
+            np.add.at(start, np.asarray(tb.start_idx), prob / prob.sum())
+            if not hasattr(self, "_opt_V"):
+                self._opt_V = dp.episodic_value_iteration(tb.H, self.T, self.R)[1]
+            for k, i in enumerate(loops):
+                pi = ag.current_optimal_stochastic_policy(i)
+                Rs, _ = indicators.get_episodic_regrets_and_average_reward_at_time_zero(
+                    tb.H, self.T, self.R, pi, start, self._opt_V)
+                out[k] = float((np.asarray(Rs) * start).sum()) / tb.H
+        else:
+            if not hasattr(self, "_opt_ar"):
+                Q, _ = dp.discounted_value_iteration(self.T, self.R)
+                self._opt_ar = markov_chain.get_average_reward(self.T, self.R, dp.get_policy_from_q_values(Q, True))
+            states = ag.state.cpu().numpy()
+            for k, i in enumerate(loops):
+                pi = ag.current_optimal_stochastic_policy(i)
+                ar = markov_chain.get_average_reward(self.T, self.R, pi, [(int(states[i]), 1.0)])
+                r = self._opt_ar - ar
+                out[k] = 0.0 if (np.isclose(r, 0.0, atol=1e-3) or r < 0) else r
+        return out
+
+    def run(self, T: int, log_every: int = -1, regret_for=None):
+        """T interaction steps for every loop, `log_every` steps per launch.  Returns the list of log records
+        (steps, cumulative_reward f64[N], n_episodes i64[N], and -- for the loops listed in `regret_for`, when T/R were
+        given -- regret and cumulative_regret)."""
+        ag = self.agents
+        log_every = T if log_every in (0, -1, None) else int(log_every)
+        regret_for = [] if (regret_for is None or self.T is None) else list(regret_for)
+        cum_regret = np.zeros(len(regret_for))
+        done = 0
+        while done < T:
+            n = min(log_every, T - done)
+            ag.steps(n)
+            done += n
+            rec = {"steps": done, "cumulative_reward": ag.cumulative_reward.cpu().numpy(),
+                   "n_episodes": ag.n_episodes.cpu().numpy()}
+            if regret_for:
+                reg = self._expected_regret(regret_for)
+                cum_regret = cum_regret + reg * n  # agent_mdp_interaction.py:503-506
+                rec["regret"], rec["cumulative_regret"] = reg, cum_regret.copy()
+            self.logs.append(rec)
+        return self.logs

@@ -1,0 +1,227 @@
+// agents.cu -- N independent agent/MDP interaction loops on the device ("a batched MDPLoop
+// that drives N envs with vectorised tabular agents").
+//
+// One thread owns one loop: its env (state, h), its agent model (count / Q / V tables) and its Philox streams, and
+// runs n_steps iterations of MDPLoop.run's body (colosseum/experiment/agent_mdp_interaction.py:238-298) in ONE
+// launch:  a = actor.select_action(ts, h);  new_ts = mdp.step(a);  agent.step_update(ts, a, new_ts, h);
+//          cumulative_reward += r;  if new_ts.last(): ts = mdp.reset().
+//   actor   QValuesActor.select_action (colosseum/agent/actors/Q_values_actor.py:58-82): epsilon-greedy, else uniform
+//           among the argmax ties of q[time, s].  (Boltzmann exploration is not offered.)
+//   model   episodic  QValuesModel.step_update  (colosseum/agent/agents/episodic/q_learning.py:53-103), UCB-Hoeffding
+//                     and UCB-Bernstein bonuses, including numpy's type promotion in each sub-expression
+//           continuous _QValuesModel.step_update (colosseum/agent/agents/infinite_horizon/q_learning.py:86-111)
+//   env     BaseMDP.step / reset as in env_step.cu (successor tables == the reference's own sampler)
+// Every floating-point operation is written with round-to-nearest intrinsics (no FMA contraction): the CPU oracle
+// computes the same IEEE operations in the same order, so whole trajectories are compared bit for bit.
+//
+// Memory: the tables of a loop are contiguous ([N][H,S,A]); accesses are 4-byte gathers at (h, s, a) -- latency
+// bound, hidden by running one thread per loop with as many loops as the caller has seeds.
+#include "common.cuh"
+
+namespace colo {
+
+constexpr unsigned long long kAgentKey = 0x9E3779B97F4A7C15ULL;  // the agent's Philox key = seed ^ kAgentKey
+
+struct Step {
+  int nxt, cls;
+};
+
+__device__ __forceinline__ int bisect_count_d(const double* __restrict__ cum, int n, double x) {
+  int pos = 0;
+  for (int k = 0; k < n - 1; ++k) pos += (__ldg(cum + k) <= x) ? 1 : 0;
+  return pos;
+}
+
+__device__ __forceinline__ Step env_succ(const colo_mdp_tables& tb, int s, int a, double u) {
+  const size_t sa = (size_t)s * tb.A + a;
+  const size_t base = sa * tb.Ksucc;
+  const int n = __ldg(tb.succ_len + sa);
+  int pos = 0;
+  if (n > 1) {
+    const double total = __ldg(tb.succ_cum + base + n - 1) + 0.0;
+    pos = bisect_count_d(tb.succ_cum + base, n, __dmul_rn(u, total));
+  }
+  Step r;
+  r.nxt = __ldg(tb.succ_idx + base + pos);
+  r.cls = tb.rew_cls_succ ? __ldg(tb.rew_cls_succ + base + pos) : 0;
+  return r;
+}
+
+__device__ __forceinline__ float reward_from_class(const colo_mdp_tables& tb, int cls, float u) {
+  const float* q = tb.rew_q + (size_t)cls * tb.nq;
+  const float t = __fmul_rn(u, (float)(tb.nq - 1));
+  int i = (int)t;
+  i = i > tb.nq - 2 ? tb.nq - 2 : i;
+  const float f = __fsub_rn(t, (float)i);
+  const float q0 = __ldg(q + i), q1 = __ldg(q + i + 1);
+  const float r0 = fmaf(f, __fsub_rn(q1, q0), q0);
+  return fmaf(r0, __fsub_rn(tb.rmax, tb.rmin), -tb.rmin);
+}
+
+__device__ __forceinline__ int start_state(const colo_mdp_tables& tb, double u) {
+  if (tb.n_start == 1) return __ldg(tb.start_idx);
+  const double total = __ldg(tb.start_cum + tb.n_start - 1) + 0.0;
+  return __ldg(tb.start_idx + bisect_count_d(tb.start_cum, tb.n_start, __dmul_rn(u, total)));
+}
+
+// QValuesActor.select_action on one row of q-values
+__device__ __forceinline__ int select_action(const float* __restrict__ q, int A, double eps, const Philox4& w) {
+  if (eps >= 0.0 && (double)u24(w.w[0]) < eps) return act_from_word(w.w[1], A);
+  float best = q[0];
+  int ties = 1;
+  for (int a = 1; a < A; ++a) {
+    const float v = q[a];
+    if (v > best) {
+      best = v;
+      ties = 1;
+    } else if (v == best) {
+      ++ties;
+    }
+  }
+  int k = act_from_word(w.w[1], ties);
+  for (int a = 0; a < A; ++a)
+    if (q[a] == best && k-- == 0) return a;
+  return A - 1;
+}
+
+template <bool EPISODIC>
+__global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tables tb, const colo_qlearning_args p,
+                                                              int n_steps, unsigned long long t0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N) return;
+  const int S = tb.S, A = tb.A, H = tb.H;
+  const size_t per_q = (size_t)(EPISODIC ? H : 1) * S * A, per_v = (size_t)(EPISODIC ? H + 1 : 1) * S;
+  int* cnt = p.cnt + i * per_q;
+  float* Q = p.Q + i * per_q;
+  float* V = p.V + i * per_v;
+  float* Qm = EPISODIC ? nullptr : p.Q_main + i * per_q;
+  float* mu = p.mu ? p.mu + i * per_q : nullptr;
+  float* sg = p.sigma ? p.sigma + i * per_q : nullptr;
+  float* be = p.beta ? p.beta + i * per_q : nullptr;
+  int s = p.state[i], h = p.h[i];
+  double cum = p.cum_reward[i];
+  long long episodes = p.n_episodes ? p.n_episodes[i] : 0;
+  const double Hd = EPISODIC ? (double)H : p.H_eff;
+  const double H3 = (double)H * H * H;  // exact: H**3 is a python int in the reference
+
+  for (int step = 0; step < n_steps; ++step) {
+    const unsigned long long t = t0 + step;
+    const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, t);
+    const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, t);
+    const size_t row = ((size_t)(EPISODIC ? h : 0) * S + s) * A;
+    const int a = select_action(Q + row, A, p.epsilon_greedy, wa);
+    const Step st = env_succ(tb, s, a, u53(we.w[0], we.w[1]));
+    const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
+    const int hh = h + 1;
+    const bool last = EPISODIC && hh >= H;
+    const int obs = last ? -1 : st.nxt;
+    const int sp = obs < 0 ? S - 1 : obs;  // numpy's negative index: the terminal observation -1 reads state S-1
+    const size_t idx = row + a;
+    const int n = cnt[idx] + 1;
+    cnt[idx] = n;
+    const double alpha = fmax(p.min_at, __ddiv_rn(__dadd_rn(Hd, 1.0), __dadd_rn(Hd, (double)n)));
+    const double om = __dsub_rn(1.0, alpha);
+    if (EPISODIC) {
+      const float vnext = V[(size_t)hh * S + sp];
+      double b;
+      if (p.ucb_type == 0) {
+        b = __dmul_rn(p.c_1, __dsqrt_rn(__ddiv_rn(__dmul_rn(H3, p.log_term), (double)n)));
+      } else {
+        const float m = __fadd_rn(mu[idx], vnext);
+        const float g = __fadd_rn(sg[idx], __fmul_rn(vnext, vnext));
+        mu[idx] = m;
+        sg[idx] = g;
+        const float old_beta = be[idx];
+        const float d = __fsub_rn(g, m);
+        const float hd2 = __fmul_rn((float)H, __fmul_rn(d, d));
+        const int n2 = (int)((unsigned)n * (unsigned)n);  // np.int32 ** 2 wraps
+        const double x = __dadd_rn(__ddiv_rn((double)hd2, (double)n2), (double)H);
+        const double first = __dsqrt_rn(__dmul_rn(x, p.log_term));
+        const double second = __ddiv_rn(__dmul_rn(p.sqrt_h7sa, p.log_term), (double)n);
+        const double v1 = __dmul_rn(p.c_1, __dadd_rn(first, second));
+        const double v2 = __dmul_rn(p.c_2, __dsqrt_rn(__ddiv_rn(__dmul_rn(H3, p.log_term), (double)n)));
+        const float nb = (float)(v2 < v1 ? v2 : v1);  // python min(v1, v2)
+        be[idx] = nb;
+        b = __ddiv_rn(__ddiv_rn(__dsub_rn((double)nb, __dmul_rn(om, (double)old_beta)), 2.0), alpha);
+      }
+      // python float + np.float32 is a float32 sum (NEP 50); the np.float64 bonus then promotes
+      const double target = __dadd_rn((double)__fadd_rn(r, vnext), b);
+      // sic: the reference weighs the OLD estimate with alpha_t (q_learning.py:100-102)
+      Q[idx] = (float)__dadd_rn(__dmul_rn(alpha, (double)Q[idx]), __dmul_rn(om, target));
+      float mx = Q[row];
+      for (int k = 1; k < A; ++k) mx = fmaxf(mx, Q[row + k]);
+      V[(size_t)h * S + s] = fminf((float)H, mx);
+    } else {
+      const double b = __dmul_rn(__dmul_rn(4.0, p.span_approx),
+                                 __dsqrt_rn(__dmul_rn(__ddiv_rn(Hd, (double)n), p.log_term)));
+      const double target = __dadd_rn(__dadd_rn((double)r, __dmul_rn(p.gamma, (double)V[sp])), b);
+      const float qm = (float)__dadd_rn(__dmul_rn(om, (double)Q[idx]), __dmul_rn(alpha, target));
+      Qm[idx] = qm;
+      Q[idx] = fminf(Q[idx], qm);
+      const size_t rp = (size_t)sp * A;
+      float mx = Q[rp];
+      for (int k = 1; k < A; ++k) mx = fmaxf(mx, Q[rp + k]);
+      V[sp] = mx;
+    }
+    cum = __dadd_rn(cum, (double)r);
+    if (p.trace) {
+      int* tr = p.trace + ((size_t)step * p.N + i) * 4;
+      tr[0] = s; tr[1] = a; tr[2] = obs; tr[3] = __float_as_int(r);
+    }
+    if (last) {
+      ++episodes;
+      h = 0;
+      s = start_state(tb, u53(wa.w[2], wa.w[3]));
+    } else {
+      h = hh;
+      s = st.nxt;
+    }
+  }
+  p.state[i] = s;
+  p.h[i] = h;
+  p.cum_reward[i] = cum;
+  if (p.n_episodes) p.n_episodes[i] = episodes;
+}
+
+static int check_args(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps, bool episodic) {
+  COLO_ARG_CHECK(tb && a, "tables / args are NULL");
+  COLO_ARG_CHECK(tb->S > 0 && tb->A > 0 && tb->rew_q && tb->n_cls > 0 && tb->nq >= 2, "tables");
+  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
+  COLO_ARG_CHECK(tb->start_cum && tb->start_idx && tb->n_start > 0, "start distribution");
+  COLO_ARG_CHECK(episodic ? tb->H > 0 : tb->H == 0, "episodic agents need H > 0, continuous agents H == 0");
+  COLO_ARG_CHECK(a->N >= 0 && n_steps >= 1, "N >= 0, n_steps >= 1");
+  if (a->N == 0) return COLO_OK;
+  COLO_ARG_CHECK(a->state && a->h && a->cnt && a->Q && a->V && a->cum_reward, "state, h, cnt, Q, V, cum_reward");
+  if (episodic) {
+    COLO_ARG_CHECK(a->ucb_type == 0 || (a->ucb_type == 1 && a->mu && a->sigma && a->beta && a->c_2 > 0),
+                   "ucb_type 0 (hoeffding) or 1 (bernstein with mu, sigma, beta, c_2)");
+    COLO_ARG_CHECK(a->c_1 > 0, "c_1 > 0");
+  } else {
+    COLO_ARG_CHECK(a->Q_main && a->H_eff > 0, "Q_main, H_eff");
+  }
+  return COLO_OK;
+}
+
+}  // namespace colo
+
+extern "C" {
+
+int colo_qlearning_episodic_steps(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps,
+                                  unsigned long long t0, void* stream) {
+  int r = colo::check_args(tb, a, n_steps, true);
+  if (r != COLO_OK || a->N == 0) return r;
+  const int grid = (int)((a->N + 127) / 128);
+  colo::qlearning_steps_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(*tb, *a, n_steps, t0);
+  return colo::check_launch("qlearning_steps_kernel<episodic>");
+}
+
+int colo_qlearning_continuous_steps(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps,
+                                    unsigned long long t0, void* stream) {
+  int r = colo::check_args(tb, a, n_steps, false);
+  if (r != COLO_OK || a->N == 0) return r;
+  const int grid = (int)((a->N + 127) / 128);
+  colo::qlearning_steps_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(*tb, *a, n_steps, t0);
+  return colo::check_launch("qlearning_steps_kernel<continuous>");
+}
+
+}  // extern "C"

@@ -474,6 +474,49 @@ unsigned long long colo_env_server_post(const colo_env_server* srv);
 int colo_env_server_wait(const colo_env_server* srv, unsigned long long step_index, unsigned timeout_ms);
 int colo_env_server_stop(const colo_env_server* srv, void* stream);
 
+/*
+ * Batched agent/MDP interaction loops: N independent (Q-learning agent, env) pairs on one
+ * MDP, one thread per loop, n_steps iterations of MDPLoop.run's body (experiment/agent_mdp_interaction.py:238-298)
+ * per launch: QValuesActor.select_action (agent/actors/Q_values_actor.py:58-82; epsilon-greedy or uniform among the
+ * argmax ties), BaseMDP.step on the successor tables, the model update, cumulative reward, reset after LAST.
+ *   colo_qlearning_episodic_steps   QValuesModel.step_update (agent/agents/episodic/q_learning.py:53-103):
+ *       cnt i32[N,H,S,A] (init 1), Q f32[N,H,S,A] (init H), V f32[N,H+1,S] (init 0);
+ *       ucb_type 0 = Hoeffding bonus c_1*sqrt(H^3*log_term/n); 1 = Bernstein (mu, sigma, beta f32[N,H,S,A], init 0)
+ *       log_term = log(S*A*optimization_horizon/p), sqrt_h7sa = sqrt(H^7*S*A)
+ *   colo_qlearning_continuous_steps _QValuesModel.step_update (agent/agents/infinite_horizon/q_learning.py:86-111):
+ *       cnt i32[N,S,A] (init 0), Q, Q_main f32[N,S,A] (init H_eff), V f32[N,S] (init H_eff);
+ *       log_term = log(2*optimization_horizon/confidence), gamma = 1 - 1/H_eff
+ * Randomness: env draws from Philox4x32-10 keyed (seed; env0+i, t) exactly as colo_env_step_succ, the agent's from
+ * (seed ^ 0x9E3779B97F4A7C15; env0+i, t): word 0 epsilon test, word 1 random action / tie break, words 2-3 the
+ * start-state draw of the reset after LAST.  t runs t0 .. t0+n_steps-1; the caller advances its counter.
+ * trace (optional) i32[n_steps,N,4] = (s_t, a_t, observation of ts_tp1 (-1 at LAST), reward bits) per step.
+ * Does not synchronise.
+ */
+typedef struct {
+  long long N;
+  unsigned long long seed, env0;
+  int* state;
+  int* h;
+  int* cnt;
+  float* Q;
+  float* Q_main;
+  float* V;
+  float* mu;
+  float* sigma;
+  float* beta;
+  int ucb_type;
+  double c_1, c_2, min_at, log_term, sqrt_h7sa;
+  double H_eff, gamma, span_approx;
+  double epsilon_greedy; /* < 0: greedy */
+  double* cum_reward;    /* f64[N], accumulated across calls */
+  long long* n_episodes; /* i64[N] or NULL */
+  int* trace;
+} colo_qlearning_args;
+int colo_qlearning_episodic_steps(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps,
+                                  unsigned long long t0, void* stream);
+int colo_qlearning_continuous_steps(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps,
+                                    unsigned long long t0, void* stream);
+
 /* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
  * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */
 int colo_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64, void* stream);

@@ -746,3 +746,158 @@ int orc_extended_vi_f32(const float* T, const float* est, const double* beta_r, 
   free(u1); free(u2); free(p2); free(sorted);
   return rc;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * N independent Q-learning agent/MDP loops.  Restates, per loop and per step, MDPLoop.run's body
+ * (colosseum/experiment/agent_mdp_interaction.py:238-298): QValuesActor.select_action
+ * (colosseum/agent/actors/Q_values_actor.py:58-82), BaseMDP.step on the reference's own successor sampler, then
+ *   episodic   QValuesModel.step_update  (colosseum/agent/agents/episodic/q_learning.py:53-103)
+ *   continuous _QValuesModel.step_update (colosseum/agent/agents/infinite_horizon/q_learning.py:86-111)
+ * with numpy's (NEP 50) type of every sub-expression: float32 where the reference's operands are float32 arrays and
+ * python scalars, float64 as soon as a numpy float64 scalar (alpha_t, self.i) takes part.  Randomness is supplied by
+ * Philox (env key = seed, agent key = seed ^ 0x9E3779B97F4A7C15) because numpy's RandomState stream cannot be
+ * reproduced on a GPU; the update rule itself is pinned against the reference's model classes replayed on this
+ * function's trace (tests/golden/make_qlearning_golden.py). */
+typedef struct {
+  long long N;
+  uint64_t seed, env0;
+  int* state;
+  int* h;
+  int* cnt;
+  float* Q;
+  float* Q_main;
+  float* V;
+  float* mu;
+  float* sigma;
+  float* beta;
+  int ucb_type;
+  double c_1, c_2, min_at, log_term, sqrt_h7sa;
+  double H_eff, gamma, span_approx;
+  double epsilon_greedy;
+  double* cum_reward;
+  long long* n_episodes;
+  int* trace;
+} orc_qlearning_args;
+
+static int orc_select_action(const float* q, int A, double eps, const uint32_t w[4]) {
+  if (eps >= 0.0 && (double)u24(w[0]) < eps) return act_from_word(w[1], A);
+  float best = q[0];
+  for (int a = 1; a < A; ++a)
+    if (q[a] > best) best = q[a];
+  int ties = 0;
+  for (int a = 0; a < A; ++a) ties += q[a] == best;
+  int k = act_from_word(w[1], ties); /* np.where(q == q.max())[0][k] */
+  for (int a = 0; a < A; ++a)
+    if (q[a] == best && k-- == 0) return a;
+  return A - 1;
+}
+
+int orc_qlearning_steps(const orc_tables* tb, const orc_qlearning_args* p, int episodic, int n_steps, uint64_t t0) {
+  const int S = tb->S, A = tb->A, H = tb->H;
+  const size_t per_q = (size_t)(episodic ? H : 1) * S * A, per_v = (size_t)(episodic ? H + 1 : 1) * S;
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < p->N; ++i) {
+    int* cnt = p->cnt + i * per_q;
+    float* Q = p->Q + i * per_q;
+    float* V = p->V + i * per_v;
+    float* Qm = episodic ? NULL : p->Q_main + i * per_q;
+    float* mu = p->mu ? p->mu + i * per_q : NULL;
+    float* sg = p->sigma ? p->sigma + i * per_q : NULL;
+    float* be = p->beta ? p->beta + i * per_q : NULL;
+    int s = p->state[i], h = p->h[i];
+    double cum = p->cum_reward[i];
+    const double Hd = episodic ? (double)H : p->H_eff;
+    const double H3 = (double)H * H * H;
+    for (int step = 0; step < n_steps; ++step) {
+      const uint64_t t = t0 + (uint64_t)step;
+      uint32_t we[4], wa[4];
+      orc_philox(p->seed, p->env0 + (uint64_t)i, t, we);
+      orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, t, wa);
+      const size_t row = ((size_t)(episodic ? h : 0) * S + s) * A;
+      const int a = orc_select_action(Q + row, A, p->epsilon_greedy, wa);
+      /* BaseMDP.step: NextStateSampler.sample + sample_reward (as orc_env_step, mode 2) */
+      const size_t base = ((size_t)s * A + a) * tb->Ksucc;
+      const int nsucc = tb->succ_len[(size_t)s * A + a];
+      int pos = 0;
+      if (nsucc > 1) {
+        const double total = tb->succ_cum[base + nsucc - 1] + 0.0;
+        pos = bisect_pos(tb->succ_cum + base, nsucc, u53(we[0], we[1]) * total);
+      }
+      const int nxt = tb->succ_idx[base + pos];
+      const int cls = tb->rew_cls_succ ? tb->rew_cls_succ[base + pos] : 0;
+      const float r = reward_draw(tb, cls, u24(we[2]));
+      const int hh = h + 1;
+      const int last = episodic && hh >= H;
+      const int obs = last ? -1 : nxt;
+      const int sp = obs < 0 ? S - 1 : obs; /* numpy negative index */
+      const size_t idx = row + a;
+      const int n = cnt[idx] + 1;
+      cnt[idx] = n;
+      double alpha = (Hd + 1.0) / (Hd + (double)n);
+      if (p->min_at > alpha) alpha = p->min_at;
+      const double om = 1.0 - alpha;
+      if (episodic) {
+        const float vnext = V[(size_t)hh * S + sp];
+        double b;
+        if (p->ucb_type == 0) {
+          b = p->c_1 * sqrt(H3 * p->log_term / (double)n);
+        } else {
+          const float m = mu[idx] + vnext;
+          const float g = sg[idx] + vnext * vnext;
+          mu[idx] = m;
+          sg[idx] = g;
+          const float old_beta = be[idx];
+          const float d = g - m;
+          const float hd2 = (float)H * (d * d);
+          const int n2 = (int)((unsigned)n * (unsigned)n);
+          const double x = (double)hd2 / (double)n2 + (double)H;
+          const double first = sqrt(x * p->log_term);
+          const double second = p->sqrt_h7sa * p->log_term / (double)n;
+          const double v1 = p->c_1 * (first + second);
+          const double v2 = p->c_2 * sqrt(H3 * p->log_term / (double)n);
+          const float nb = (float)(v2 < v1 ? v2 : v1);
+          be[idx] = nb;
+          b = ((double)nb - om * (double)old_beta) / 2.0 / alpha;
+        }
+        /* python float + np.float32 is a float32 sum under NEP 50; the np.float64 bonus then promotes */
+        const float rv = r + vnext;
+        const double target = (double)rv + b;
+        Q[idx] = (float)(alpha * (double)Q[idx] + om * target); /* sic: alpha weighs the old estimate */
+        float mx = Q[row];
+        for (int k = 1; k < A; ++k)
+          if (Q[row + k] > mx) mx = Q[row + k];
+        V[(size_t)h * S + s] = mx < (float)H ? mx : (float)H;
+      } else {
+        const double b = 4.0 * p->span_approx * sqrt(Hd / (double)n * p->log_term);
+        const double target = (double)r + p->gamma * (double)V[sp] + b;
+        const float qm = (float)(om * (double)Q[idx] + alpha * target);
+        Qm[idx] = qm;
+        if (qm < Q[idx]) Q[idx] = qm;
+        const size_t rp = (size_t)sp * A;
+        float mx = Q[rp];
+        for (int k = 1; k < A; ++k)
+          if (Q[rp + k] > mx) mx = Q[rp + k];
+        V[sp] = mx;
+      }
+      cum += (double)r;
+      if (p->trace) {
+        int* tr = p->trace + ((size_t)step * p->N + i) * 4;
+        union { float f; int i; } u;
+        u.f = r;
+        tr[0] = s; tr[1] = a; tr[2] = obs; tr[3] = u.i;
+      }
+      if (last) {
+        if (p->n_episodes) p->n_episodes[i] += 1;
+        h = 0;
+        s = sample_start(tb, u53(wa[2], wa[3]));
+      } else {
+        h = hh;
+        s = nxt;
+      }
+    }
+    p->state[i] = s;
+    p->h[i] = h;
+    p->cum_reward[i] = cum;
+  }
+  return ORC_OK;
+}

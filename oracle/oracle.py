@@ -353,3 +353,74 @@ def stationary_distribution_f64(P, x0, tol=1e-14, max_iter=int(1e7)):
         M = M2
     x = np.asarray(x0, np.float64) @ M
     return x / x.sum()
+
+
+# ---------------------------------------------------------------------------------------------- agent loops
+class _QLArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_uint64), ("env0", C.c_uint64),
+        ("state", C.c_void_p), ("h", C.c_void_p), ("cnt", C.c_void_p), ("Q", C.c_void_p), ("Q_main", C.c_void_p),
+        ("V", C.c_void_p), ("mu", C.c_void_p), ("sigma", C.c_void_p), ("beta", C.c_void_p),
+        ("ucb_type", C.c_int),
+        ("c_1", C.c_double), ("c_2", C.c_double), ("min_at", C.c_double), ("log_term", C.c_double),
+        ("sqrt_h7sa", C.c_double), ("H_eff", C.c_double), ("gamma", C.c_double), ("span_approx", C.c_double),
+        ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p), ("n_episodes", C.c_void_p),
+        ("trace", C.c_void_p),
+    ]
+
+
+class QLearningLoops:
+    """CPU restatement of N Q-learning agent/MDP loops (orc_qlearning_steps in colo_oracle.c; reference:
+    agent/agents/episodic/q_learning.py:28-103, agent/agents/infinite_horizon/q_learning.py:48-111,
+    agent/actors/Q_values_actor.py:58-82, experiment/agent_mdp_interaction.py:238-298).  `tb` is a HostTables with
+    successor tables."""
+
+    def __init__(self, tb, n_loops, optimization_horizon, seed=0, env0=0, epsilon_greedy=None, *, p=0.05, c_1=1.0,
+                 c_2=None, min_at=0.0, UCB_type="hoeffding", confidence=0.95, span_approx_weight=1.0, h_weight=1.0):
+        self.tb, self.N, self.seed, self.env0 = tb, int(n_loops), int(seed), int(env0)
+        S, A, H = tb.c.S, tb.c.A, tb.c.H
+        self.episodic = H > 0
+        N = self.N
+        self.state, self.h, _, _ = env_reset(tb, N, seed=seed, t=0, env0=env0)
+        self.t = 1
+        self.cum_reward = np.zeros(N, np.float64)
+        self.n_episodes = np.zeros(N, np.int64)
+        a = _QLArgs()
+        a.N, a.seed, a.env0 = N, self.seed, self.env0
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        if self.episodic:
+            self.cnt = np.ones((N, H, S, A), np.int32)
+            self.Q = np.full((N, H, S, A), H, np.float32)
+            self.V = np.zeros((N, H + 1, S), np.float32)
+            a.ucb_type = 0
+            if UCB_type.lower() == "bernstein":
+                self.mu, self.sigma, self.beta = (np.zeros((N, H, S, A), np.float32) for _ in range(3))
+                a.mu, a.sigma, a.beta, a.ucb_type, a.c_2 = _p(self.mu), _p(self.sigma), _p(self.beta), 1, float(c_2)
+            a.c_1, a.min_at = float(c_1), float(min_at)
+            a.log_term = float(np.log(S * A * optimization_horizon / p))
+            a.sqrt_h7sa = float(np.sqrt(H ** 7 * S * A))
+        else:
+            T_ = optimization_horizon
+            span = span_approx_weight
+            Hf = float(h_weight * min(np.sqrt(span * T_ / S / A), (T_ / S / A / np.log(4 * T_ / confidence)) ** 0.333))
+            self.H_eff, self.gamma = Hf, 1 - 1 / Hf
+            self.cnt = np.zeros((N, S, A), np.int32)
+            self.Q = np.full((N, S, A), Hf, np.float32)
+            self.Q_main = np.full((N, S, A), Hf, np.float32)
+            self.V = np.full((N, S), Hf, np.float32)
+            a.Q_main = _p(self.Q_main)
+            a.min_at = float(min_at if min_at > 0.009 else 0)
+            a.H_eff, a.gamma, a.span_approx = Hf, float(self.gamma), float(span)
+            a.log_term = float(np.log(2 * T_ / confidence))
+        a.state, a.h, a.cnt, a.Q, a.V = _p(self.state), _p(self.h), _p(self.cnt), _p(self.Q), _p(self.V)
+        a.cum_reward, a.n_episodes = _p(self.cum_reward), _p(self.n_episodes)
+        self.args = a
+
+    def steps(self, n_steps, trace=False):
+        tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
+        self.args.trace = _p(tr)
+        rc = lib().orc_qlearning_steps(C.byref(self.tb.c), C.byref(self.args), int(self.episodic), int(n_steps),
+                                       C.c_uint64(self.t))
+        assert rc == 0
+        self.t += n_steps
+        return tr

@@ -1,0 +1,57 @@
+"""CPU: the oracle's Q-learning loops (oracle.QLearningLoops) are pinned to the reference's model classes through
+tests/golden/qlearning.npz (made by tests/golden/make_qlearning_golden.py, which replays the oracle's transitions
+through the unmodified `QValuesModel` / `_QValuesModel`)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_instance
+from colosseum_b200.tables import MDPTables
+from oracle import oracle as orc
+
+sys.path.insert(0, GOLDEN)
+from make_qlearning_golden import CASES, N_LOOPS, N_STEPS, SEED, host_tables  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "qlearning.npz"))
+
+
+@pytest.mark.parametrize("name,inst,kw", CASES, ids=[c[0] for c in CASES])
+def test_oracle_loops_match_reference_models(gold, name, inst, kw):
+    tb = MDPTables.from_golden(load_instance(inst))
+    loops = orc.QLearningLoops(host_tables(tb), N_LOOPS, seed=SEED, **kw)
+    assert np.array_equal(loops.state, gold[f"{name}.start"])
+    trace = loops.steps(N_STEPS, trace=True)
+    assert np.array_equal(trace, gold[f"{name}.trace"])
+    ours = {"N": loops.cnt, "Q": loops.Q, "V": loops.V}
+    for f in ("Q_main", "mu", "sigma", "beta"):
+        if hasattr(loops, f):
+            ours[f] = getattr(loops, f)
+    for f, v in ours.items():
+        ref = gold[f"{name}.ref_{f}"]
+        if tb.H > 0:
+            # episodic model: every operation restated with numpy's own promotion -> bit-identical tables
+            assert np.array_equal(v, ref.astype(v.dtype)), f
+        else:
+            # continuous model: under numpy >= 2 the reference's `np.zeros(float32) + np.float64` tables silently
+            # become float64; the restatement keeps the declared float32 -> agreement to float32 rounding
+            np.testing.assert_allclose(v, ref, rtol=1e-6, atol=0, err_msg=f)
+    # the trajectory is a real interaction: actions cover the action set, episodes end where they should
+    assert set(np.unique(trace[..., 1])) <= set(range(tb.A))
+    if tb.H > 0:
+        assert int(loops.n_episodes.min()) == N_STEPS // tb.H
+        assert ((trace[..., 2] == -1).sum(0) == N_STEPS // tb.H).all()
+
+
+def test_chunked_steps_equal_one_call():
+    tb = MDPTables.from_golden(load_instance("frozenlake4_epi"))
+    kw = dict(optimization_horizon=1000, p=0.05, c_1=0.5, c_2=0.5, UCB_type="bernstein")
+    a = orc.QLearningLoops(host_tables(tb), 5, seed=3, **kw)
+    b = orc.QLearningLoops(host_tables(tb), 5, seed=3, **kw)
+    ta = a.steps(200, trace=True)
+    tb_ = np.concatenate([b.steps(70, trace=True), b.steps(130, trace=True)])
+    assert np.array_equal(ta, tb_) and np.array_equal(a.Q, b.Q) and np.array_equal(a.cum_reward, b.cum_reward)
