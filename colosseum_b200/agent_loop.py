@@ -155,6 +155,115 @@ class QLearningContinuous(_QLearningBatch):
         a.log_term = float(np.log(2 * optimization_horizon / confidence))
 
 
+class PSRLEpisodic:
+    """N PSRLEpisodic loops (colosseum/agent/agents/episodic/posterior_sampling.py:20-147; Osband et al. 2013) with
+    the N_NIG reward model and the M_DIR transition model (the agent's defaults,
+    agent/mdp_models/bayesian_model.py:44-57).  Every H steps: one Dirichlet sample of all N*S*A rows
+    (colo_sample_dirichlet_rows), one Normal-Inverse-Gamma sample (colo_sample_nig_rewards), one batched episodic value
+    iteration (colo_episodic_f32, B = N); in between, `colo_psrl_episodic_steps` acts and updates the posteriors.
+    The sampled models never leave HBM."""
+
+    episodic = True
+
+    def __init__(self, seed: int, tables: MDPTables, optimization_horizon: int, reward_prior_model=None,
+                 transitions_prior_model=None, rewards_prior_prms=None, transitions_prior_prms=None,
+                 epsilon_greedy=None, boltzmann_temperature=None, *, n_loops: int = 1, env_offset: int = 0):
+        import torch
+
+        _cabi.require_cuda()
+        assert reward_prior_model in (None, "N_NIG") and transitions_prior_model in (None, "M_DIR"), \
+            "the batched PSRL offers the N_NIG / M_DIR conjugate models"
+        if boltzmann_temperature is not None:
+            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
+        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
+            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        assert tables.H > 0, "PSRLEpisodic needs an episodic MDP"
+        self.torch, self.tables = torch, tables
+        self.dev = DeviceTables(tables, "succ")
+        self.n_loops = N = int(n_loops)
+        self.seed, self.env_offset = int(seed), int(env_offset)
+        S, A, H = tables.S, tables.A, tables.H
+        rp = [tables.rmax, 1, 1, 1] if rewards_prior_prms is None else rewards_prior_prms       # bayesian_model.py:46-48
+        tp = [1.0 / S] if transitions_prior_prms is None else transitions_prior_prms              # :49-51
+        hp = np.tile(rp, (S, A, 1)).astype(np.float32)                                            # base_conjugate.py:44-47
+        mu, n_mu, tau, n_tau = (hp[..., k].copy() for k in range(4))
+        hp[..., 2], hp[..., 3] = n_tau * 0.5, (0.5 * n_tau) / tau                                # conjugate_rewards.py:45-54
+        self.nig_hyper = torch.from_numpy(np.tile(hp, (N, 1, 1, 1))).cuda()
+        self.dir_hyper = torch.full((N, S, A, S), float(np.float32(tp[0])), dtype=torch.float32, device="cuda")
+        self.T_sample = torch.empty((N, S, A, S), dtype=torch.float32, device="cuda")
+        self.R_sample = torch.empty((N, S, A), dtype=torch.float32, device="cuda")
+        self.Q = torch.zeros((N, H + 1, S, A), dtype=torch.float32, device="cuda")
+        self.state = torch.zeros(N, dtype=torch.int32, device="cuda")
+        self.h = torch.zeros(N, dtype=torch.int32, device="cuda")
+        self.cumulative_reward = torch.zeros(N, dtype=torch.float64, device="cuda")
+        self.n_episodes = torch.zeros(N, dtype=torch.int64, device="cuda")
+        self.t = 0          # Philox counter of the interaction steps
+        self.n_samples = 0  # Philox counter of the posterior samples
+        self._h_episode = 0
+        a = _cabi.PsrlArgs()
+        a.N, a.seed, a.env0 = N, self.seed, self.env_offset
+        a.state, a.h, a.Q = self.state.data_ptr(), self.h.data_ptr(), self.Q.data_ptr()
+        a.dir_hyper, a.nig_hyper = self.dir_hyper.data_ptr(), self.nig_hyper.data_ptr()
+        a.cum_reward, a.n_episodes = self.cumulative_reward.data_ptr(), self.n_episodes.data_ptr()
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        self._args = a
+        _QLearningBatch.reset_envs(self)
+        self.episode_end_update()  # before_start_interacting (:146-147)
+
+    def sample(self):
+        """BayesianMDPModel.sample for every loop (bayesian_model.py:59-63): fills T_sample, R_sample"""
+        lib = _cabi.lib()
+        N, S, A = self.n_loops, self.tables.S, self.tables.A
+        rows, row0 = N * S * A, self.env_offset * S * A
+        st = _cabi.current_stream()
+        rc = lib.colo_sample_dirichlet_rows(self.dir_hyper.data_ptr(), rows, S, row0, self.seed, self.n_samples,
+                                            self.T_sample.data_ptr(), st)
+        _cabi.check(rc, "colo_sample_dirichlet_rows")
+        rc = lib.colo_sample_nig_rewards(self.nig_hyper.data_ptr(), rows, row0, self.seed, self.n_samples,
+                                         self.R_sample.data_ptr(), st)
+        _cabi.check(rc, "colo_sample_nig_rewards")
+        self.n_samples += 1
+        return self.T_sample, self.R_sample
+
+    def episode_end_update(self):
+        """posterior_sampling.py:142-144: Q = episodic_value_iteration(H, *model.sample())"""
+        from .dynamic_programming import episodic_value_iteration
+
+        T, R = self.sample()
+        Q, _ = episodic_value_iteration(self.tables.H, T, R, precision="f32")
+        self.Q.copy_(Q)
+
+    def steps(self, n_steps: int, trace: bool = False):
+        """n_steps interaction steps for every loop; the posterior is resampled at every episode end"""
+        torch, H = self.torch, self.tables.H
+        tr = torch.empty((n_steps, self.n_loops, 4), dtype=torch.int32, device="cuda") if trace else None
+        done = 0
+        while done < n_steps:
+            n = min(H - self._h_episode, n_steps - done)
+            self._args.trace = None if tr is None else tr[done:].data_ptr()
+            rc = _cabi.lib().colo_psrl_episodic_steps(C.byref(self.dev.c), C.byref(self._args), n, self.t,
+                                                      _cabi.current_stream())
+            _cabi.check(rc, "colo_psrl_episodic_steps")
+            self.t += n
+            done += n
+            self._h_episode = (self._h_episode + n) % H
+            if self._h_episode == 0:
+                self.episode_end_update()
+        return tr
+
+    def get_map_estimate(self):
+        """BayesianMDPModel.get_map_estimate (bayesian_model.py:71-76) for every loop"""
+        return self.dir_hyper / self.dir_hyper.sum(-1, keepdim=True), self.nig_hyper[..., 0]
+
+    def current_optimal_stochastic_policy(self, i: int) -> np.ndarray:
+        """posterior_sampling.py:76-80: greedy policy of the MAP model"""
+        from .dynamic_programming import episodic_value_iteration, get_policy_from_q_values
+
+        T_map, R_map = self.get_map_estimate()
+        Q, _ = episodic_value_iteration(self.tables.H, T_map[i].contiguous(), R_map[i].contiguous(), precision="f32")
+        return get_policy_from_q_values(Q.cpu().numpy(), True)
+
+
 class BatchedMDPLoop:
     """MDPLoop for N loops at once.  `T`, `R` (numpy float32) are only needed for the regret indicators."""
 

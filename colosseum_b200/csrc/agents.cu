@@ -183,6 +183,65 @@ __global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tab
   if (p.n_episodes) p.n_episodes[i] = episodes;
 }
 
+// PSRLEpisodic between two posterior samples (colosseum/agent/agents/episodic/posterior_sampling.py:142-147): act
+// greedily on the Q of the sampled model, BayesianMDPModel.step_update (agent/mdp_models/bayesian_model.py:78-92):
+// N_NIG.update_sa with one reward (bayesian_models/conjugate_rewards.py:56-74) and, unless the step was the last of the
+// episode, M_DIR.update_sa (conjugate_transitions.py:43-45).  Same numpy type promotion rules as above.
+__global__ void __launch_bounds__(128) psrl_steps_kernel(const colo_mdp_tables tb, const colo_psrl_args p, int n_steps,
+                                                         unsigned long long t0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N) return;
+  const int S = tb.S, A = tb.A, H = tb.H;
+  const float* Q = p.Q + (size_t)i * (H + 1) * S * A;
+  float* dir = p.dir_hyper + (size_t)i * S * A * S;
+  float* nig = p.nig_hyper + (size_t)i * S * A * 4;
+  int s = p.state[i], h = p.h[i];
+  double cum = p.cum_reward[i];
+  long long episodes = p.n_episodes ? p.n_episodes[i] : 0;
+  for (int step = 0; step < n_steps; ++step) {
+    const unsigned long long t = t0 + step;
+    const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, t);
+    const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, t);
+    const int a = select_action(Q + ((size_t)h * S + s) * A, A, p.epsilon_greedy, wa);
+    const Step st = env_succ(tb, s, a, u53(we.w[0], we.w[1]));
+    const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
+    const int hh = h + 1;
+    const bool last = hh >= H;
+    float* hp = nig + ((size_t)s * A + a) * 4;
+    const float mu0 = hp[0], l0 = hp[1], a0 = hp[2], b0 = hp[3];
+    const double y = (double)r;
+    const float l1 = __fadd_rn(l0, 1.0f);
+    const double mu1 = __ddiv_rn(__dadd_rn((double)__fmul_rn(l0, mu0), y), (double)l1);
+    const double dy = __dsub_rn(y, (double)mu0);
+    const double disc = __ddiv_rn(__dmul_rn((double)l0, __dmul_rn(dy, dy)), (double)l1);
+    hp[0] = (float)mu1;
+    hp[1] = l1;
+    hp[2] = __fadd_rn(a0, 0.5f);
+    hp[3] = (float)__dadd_rn((double)b0, __dmul_rn(0.5, __dadd_rn(0.0, disc)));
+    if (!last) {
+      float* c = dir + ((size_t)s * A + a) * S + st.nxt;
+      *c = __fadd_rn(*c, 1.0f);
+    }
+    cum = __dadd_rn(cum, (double)r);
+    if (p.trace) {
+      int* tr = p.trace + ((size_t)step * p.N + i) * 4;
+      tr[0] = s; tr[1] = a; tr[2] = last ? -1 : st.nxt; tr[3] = __float_as_int(r);
+    }
+    if (last) {
+      ++episodes;
+      h = 0;
+      s = start_state(tb, u53(wa.w[2], wa.w[3]));
+    } else {
+      h = hh;
+      s = st.nxt;
+    }
+  }
+  p.state[i] = s;
+  p.h[i] = h;
+  p.cum_reward[i] = cum;
+  if (p.n_episodes) p.n_episodes[i] = episodes;
+}
+
 static int check_args(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps, bool episodic) {
   COLO_ARG_CHECK(tb && a, "tables / args are NULL");
   COLO_ARG_CHECK(tb->S > 0 && tb->A > 0 && tb->rew_q && tb->n_cls > 0 && tb->nq >= 2, "tables");
@@ -222,6 +281,21 @@ int colo_qlearning_continuous_steps(const colo_mdp_tables* tb, const colo_qlearn
   const int grid = (int)((a->N + 127) / 128);
   colo::qlearning_steps_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(*tb, *a, n_steps, t0);
   return colo::check_launch("qlearning_steps_kernel<continuous>");
+}
+
+int colo_psrl_episodic_steps(const colo_mdp_tables* tb, const colo_psrl_args* a, int n_steps, unsigned long long t0,
+                             void* stream) {
+  COLO_ARG_CHECK(tb && a, "tables / args are NULL");
+  COLO_ARG_CHECK(tb->S > 0 && tb->A > 0 && tb->H > 0 && tb->rew_q && tb->n_cls > 0 && tb->nq >= 2, "episodic tables");
+  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
+  COLO_ARG_CHECK(tb->start_cum && tb->start_idx && tb->n_start > 0, "start distribution");
+  COLO_ARG_CHECK(a->N >= 0 && n_steps >= 1, "N >= 0, n_steps >= 1");
+  if (a->N == 0) return COLO_OK;
+  COLO_ARG_CHECK(a->state && a->h && a->Q && a->dir_hyper && a->nig_hyper && a->cum_reward,
+                 "state, h, Q, dir_hyper, nig_hyper, cum_reward");
+  const int grid = (int)((a->N + 127) / 128);
+  colo::psrl_steps_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*tb, *a, n_steps, t0);
+  return colo::check_launch("psrl_steps_kernel");
 }
 
 }  // extern "C"

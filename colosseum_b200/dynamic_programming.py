@@ -232,6 +232,10 @@ def _episodic(H, T, R, policy, max_value, precision):
         Td, Rd = Td[None], Rd[None]
         pid = None if pid is None else pid[None]
     B, S, A, _ = Td.shape
+    if pid is not None and pid.shape[1] == H + 1:
+        # a policy derived from the (H+1)-row Q of episodic_value_iteration (PSRLEpisodic.current_optimal_stochastic_
+        # policy, posterior_sampling.py:76-80): the reference only ever reads rows 0..H-1 (finite_horizon.py:36-40)
+        pid = pid[:, :H].contiguous()
     assert pid is None or tuple(pid.shape) == (B, H, S, A), "policy must be [H,S,A]"
     vd = _vdtype(precision)
     Q = torch.empty((B, H + 1, S, A), dtype=vd, device="cuda")

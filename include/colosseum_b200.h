@@ -276,6 +276,13 @@ int colo_extended_vi_f64acc(const float* T, const float* est_rewards, const doub
  * model.  Philox counter = ((row0 + r)*S + j, t): row0 is the global index of the first row (row sharding), t the
  * caller's draw counter.  Distributional parity with numpy's standard_gamma.  Does not synchronise.
  */
+/*
+ * colo_sample_nig_rewards -- N_NIG.sample (bayesian_models/conjugate_rewards.py:76-92): for each row (mu, lambda,
+ * alpha, beta) f32[rows,4]: tau ~ Gamma(alpha, scale 1/beta) -> float32, R_out[r] ~ Normal(mu, sqrt(1/(lambda*tau)))
+ * -> float32.  Philox counter (row0 + r, t).  Distributional parity.  Does not synchronise.
+ */
+int colo_sample_nig_rewards(const float* hyper, long long rows, long long row0, unsigned long long seed,
+                            unsigned long long t, float* R_out, void* stream);
 int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0, unsigned long long seed,
                                unsigned long long t, float* T_out, void* stream);
 
@@ -516,6 +523,31 @@ int colo_qlearning_episodic_steps(const colo_mdp_tables* tb, const colo_qlearnin
                                   unsigned long long t0, void* stream);
 int colo_qlearning_continuous_steps(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps,
                                     unsigned long long t0, void* stream);
+
+/*
+ * colo_psrl_episodic_steps -- PSRLEpisodic between two posterior samples (agent/agents/episodic/posterior_sampling.py:
+ * 142-147) for N independent loops: greedy / epsilon-greedy action on Q f32[N,H+1,S,A] (the episodic value iteration of
+ * each loop's sampled model), BaseMDP.step, BayesianMDPModel.step_update (agent/mdp_models/bayesian_model.py:78-92):
+ * N_NIG.update_sa with the one reward on nig_hyper f32[N,S,A,4] = (mu, lambda, alpha, beta)
+ * (bayesian_models/conjugate_rewards.py:56-74) and, unless the step ended the episode, dir_hyper[N,S,A,S][s,a,s'] += 1
+ * (conjugate_transitions.py:43-45).  Randomness, trace and counters as colo_qlearning_*.  The caller resamples the
+ * models (colo_sample_dirichlet_rows, colo_sample_nig_rewards) and re-solves (colo_episodic_f32, B = N) every H steps.
+ */
+typedef struct {
+  long long N;
+  unsigned long long seed, env0;
+  int* state;
+  int* h;
+  const float* Q;
+  float* dir_hyper;
+  float* nig_hyper;
+  double epsilon_greedy;
+  double* cum_reward;
+  long long* n_episodes;
+  int* trace;
+} colo_psrl_args;
+int colo_psrl_episodic_steps(const colo_mdp_tables* tb, const colo_psrl_args* a, int n_steps, unsigned long long t0,
+                             void* stream);
 
 /* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
  * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */

@@ -901,3 +901,84 @@ int orc_qlearning_steps(const orc_tables* tb, const orc_qlearning_args* p, int e
   }
   return ORC_OK;
 }
+
+/* PSRLEpisodic between two posterior samples (colosseum/agent/agents/episodic/posterior_sampling.py:142-147): greedy
+ * action on Q[N,H+1,S,A], BaseMDP.step, BayesianMDPModel.step_update (agent/mdp_models/bayesian_model.py:78-92) =
+ * N_NIG.update_sa with one reward (bayesian_models/conjugate_rewards.py:56-74) + M_DIR.update_sa unless the episode
+ * ended (conjugate_transitions.py:43-45), in numpy's types. */
+typedef struct {
+  long long N;
+  uint64_t seed, env0;
+  int* state;
+  int* h;
+  const float* Q;
+  float* dir_hyper;
+  float* nig_hyper;
+  double epsilon_greedy;
+  double* cum_reward;
+  long long* n_episodes;
+  int* trace;
+} orc_psrl_args;
+
+int orc_psrl_steps(const orc_tables* tb, const orc_psrl_args* p, int n_steps, uint64_t t0) {
+  const int S = tb->S, A = tb->A, H = tb->H;
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < p->N; ++i) {
+    const float* Q = p->Q + (size_t)i * (H + 1) * S * A;
+    float* dir = p->dir_hyper + (size_t)i * S * A * S;
+    float* nig = p->nig_hyper + (size_t)i * S * A * 4;
+    int s = p->state[i], h = p->h[i];
+    double cum = p->cum_reward[i];
+    for (int step = 0; step < n_steps; ++step) {
+      const uint64_t t = t0 + (uint64_t)step;
+      uint32_t we[4], wa[4];
+      orc_philox(p->seed, p->env0 + (uint64_t)i, t, we);
+      orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, t, wa);
+      const int a = orc_select_action(Q + ((size_t)h * S + s) * A, A, p->epsilon_greedy, wa);
+      const size_t base = ((size_t)s * A + a) * tb->Ksucc;
+      const int nsucc = tb->succ_len[(size_t)s * A + a];
+      int pos = 0;
+      if (nsucc > 1) {
+        const double total = tb->succ_cum[base + nsucc - 1] + 0.0;
+        pos = bisect_pos(tb->succ_cum + base, nsucc, u53(we[0], we[1]) * total);
+      }
+      const int nxt = tb->succ_idx[base + pos];
+      const int cls = tb->rew_cls_succ ? tb->rew_cls_succ[base + pos] : 0;
+      const float r = reward_draw(tb, cls, u24(we[2]));
+      const int hh = h + 1;
+      const int last = hh >= H;
+      float* hp = nig + ((size_t)s * A + a) * 4;
+      const float mu0 = hp[0], l0 = hp[1], a0 = hp[2], b0 = hp[3];
+      const double y = (double)r; /* np.mean([r]) */
+      const float l1 = l0 + 1.0f;
+      const float lm = l0 * mu0;
+      const double mu1 = ((double)lm + y) / (double)l1;
+      const double dy = y - (double)mu0;
+      const double disc = (double)l0 * (dy * dy) / (double)l1;
+      hp[0] = (float)mu1;
+      hp[1] = l1;
+      hp[2] = a0 + 0.5f;
+      hp[3] = (float)((double)b0 + 0.5 * (0.0 + disc));
+      if (!last) dir[((size_t)s * A + a) * S + nxt] += 1.0f;
+      cum += (double)r;
+      if (p->trace) {
+        int* tr = p->trace + ((size_t)step * p->N + i) * 4;
+        union { float f; int i; } u;
+        u.f = r;
+        tr[0] = s; tr[1] = a; tr[2] = last ? -1 : nxt; tr[3] = u.i;
+      }
+      if (last) {
+        if (p->n_episodes) p->n_episodes[i] += 1;
+        h = 0;
+        s = sample_start(tb, u53(wa[2], wa[3]));
+      } else {
+        h = hh;
+        s = nxt;
+      }
+    }
+    p->state[i] = s;
+    p->h[i] = h;
+    p->cum_reward[i] = cum;
+  }
+  return ORC_OK;
+}

@@ -424,3 +424,55 @@ class QLearningLoops:
         assert rc == 0
         self.t += n_steps
         return tr
+
+
+class _PsrlArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_uint64), ("env0", C.c_uint64),
+        ("state", C.c_void_p), ("h", C.c_void_p), ("Q", C.c_void_p), ("dir_hyper", C.c_void_p),
+        ("nig_hyper", C.c_void_p), ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p),
+        ("n_episodes", C.c_void_p), ("trace", C.c_void_p),
+    ]
+
+
+class PSRLLoops:
+    """CPU restatement of N PSRLEpisodic loops BETWEEN posterior samples (orc_psrl_steps): the caller supplies the Q
+    of each loop's sampled model (`set_q`), as the product does after colo_sample_* + episodic VI.  Priors as
+    BayesianMDPModel (agent/mdp_models/bayesian_model.py:44-57) and N_NIG.__init__'s reparametrisation
+    (bayesian_models/conjugate_rewards.py:45-54)."""
+
+    def __init__(self, tb, n_loops, seed=0, env0=0, epsilon_greedy=None, rewards_prior_prms=None,
+                 transitions_prior_prms=None):
+        self.tb, self.N, self.seed, self.env0 = tb, int(n_loops), int(seed), int(env0)
+        S, A, H = tb.c.S, tb.c.A, tb.c.H
+        N = self.N
+        self.state, self.h, _, _ = env_reset(tb, N, seed=seed, t=0, env0=env0)
+        self.t = 1
+        self.cum_reward = np.zeros(N, np.float64)
+        self.n_episodes = np.zeros(N, np.int64)
+        rp = [tb.c.rmax, 1, 1, 1] if rewards_prior_prms is None else rewards_prior_prms
+        tp = [1.0 / S] if transitions_prior_prms is None else transitions_prior_prms
+        hp = np.tile(rp, (S, A, 1)).astype(np.float32)
+        mu, n_mu, tau, n_tau = hp[..., 0].copy(), hp[..., 1].copy(), hp[..., 2].copy(), hp[..., 3].copy()
+        hp[..., 0], hp[..., 1], hp[..., 2], hp[..., 3] = mu, n_mu, n_tau * 0.5, (0.5 * n_tau) / tau
+        self.nig_hyper = np.tile(hp, (N, 1, 1, 1)).astype(np.float32)
+        self.dir_hyper = np.tile(np.float32(tp[0]), (N, S, A, S)).astype(np.float32)
+        self.Q = np.zeros((N, H + 1, S, A), np.float32)
+        a = _PsrlArgs()
+        a.N, a.seed, a.env0 = N, self.seed, self.env0
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        a.state, a.h, a.Q = _p(self.state), _p(self.h), _p(self.Q)
+        a.dir_hyper, a.nig_hyper = _p(self.dir_hyper), _p(self.nig_hyper)
+        a.cum_reward, a.n_episodes = _p(self.cum_reward), _p(self.n_episodes)
+        self.args = a
+
+    def set_q(self, Q):
+        self.Q[...] = Q
+
+    def steps(self, n_steps, trace=False):
+        tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
+        self.args.trace = _p(tr)
+        rc = lib().orc_psrl_steps(C.byref(self.tb.c), C.byref(self.args), int(n_steps), C.c_uint64(self.t))
+        assert rc == 0
+        self.t += n_steps
+        return tr

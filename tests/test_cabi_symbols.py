@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     for cname, mirror in (("colo_backup_args", _cabi.BackupArgs), ("colo_mdp_tables", _cabi.MdpTables),
                           ("colo_env_batch", _cabi.EnvBatch), ("colo_resident_args", _cabi.ResidentArgs),
-                          ("colo_env_server", _cabi.EnvServer), ("colo_qlearning_args", _cabi.QLearningArgs)):
+                          ("colo_env_server", _cabi.EnvServer), ("colo_qlearning_args", _cabi.QLearningArgs), ("colo_psrl_args", _cabi.PsrlArgs)):
         end = txt.index("} " + cname + ";")
         body = txt[txt.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
         fields = []

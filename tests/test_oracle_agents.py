@@ -55,3 +55,23 @@ def test_chunked_steps_equal_one_call():
     ta = a.steps(200, trace=True)
     tb_ = np.concatenate([b.steps(70, trace=True), b.steps(130, trace=True)])
     assert np.array_equal(ta, tb_) and np.array_equal(a.Q, b.Q) and np.array_equal(a.cum_reward, b.cum_reward)
+
+
+def test_oracle_psrl_updates_match_reference_conjugate_models():
+    """oracle.PSRLLoops' posterior updates == the reference's BayesianMDPModel.step_update (N_NIG + M_DIR), bit for
+    bit, on the committed trajectories (tests/golden/make_psrl_golden.py)."""
+    from make_psrl_golden import CASES as PCASES, N_EPISODES, N_LOOPS as PN, SEED as PSEED, optimal_q
+
+    gold = np.load(os.path.join(GOLDEN, "psrl.npz"))
+    for inst, kw in PCASES:
+        g = load_instance(inst)
+        tb = MDPTables.from_golden(g)
+        loops = orc.PSRLLoops(host_tables(tb), PN, seed=PSEED, **kw)
+        loops.set_q(optimal_q(g, tb))
+        trace = loops.steps(N_EPISODES * tb.H, trace=True)
+        assert np.array_equal(trace, gold[f"{inst}.trace"]), inst
+        assert np.array_equal(loops.nig_hyper, gold[f"{inst}.ref_nig"]), inst
+        assert np.array_equal(loops.dir_hyper, gold[f"{inst}.ref_dir"]), inst
+        assert (loops.n_episodes == N_EPISODES).all()
+        # transitions into the terminal observation are not counted (bayesian_model.py:89-92)
+        assert np.isclose((loops.dir_hyper - loops.dir_hyper.min()).sum(), PN * N_EPISODES * (tb.H - 1), rtol=1e-3)
