@@ -169,7 +169,9 @@ __global__ void ell_to_row_major_kernel(const int* __restrict__ len, const int2*
 // In-place sweeps on compressed rows: the state loop stays sequential, the lanes of the warp take the (action, slot)
 // pairs of the current state -- seg = min(KMp, 32) lanes per action, 32/seg actions per pass -- so a state of a
 // benchmark MDP (A*kmax <= 32 entries) costs one load round, a segmented shuffle sum and one warp fold.
-template <typename TV>
+// ONEPASS (A * KMp <= 32): every lane holds exactly one (action, slot) entry of a state, so the entry and the reward
+// of state s+1 -- which do not depend on V -- are fetched while state s is still being reduced.
+template <typename TV, bool ONEPASS>
 __global__ void __launch_bounds__(256) gs_sparse_kernel(const GsArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -194,8 +196,43 @@ __global__ void __launch_bounds__(256) gs_sparse_kernel(const GsArgs p) {
   while (it < p.max_iter) {
     TV res = 0;
     bool overflow = false;
+    int2 e_nx = make_int2(-1, 0);
+    TV r_nx = TV(0);
+    if (ONEPASS && al < A) {
+      e_nx = __ldg(cv + (size_t)al * KMp + il);
+      r_nx = R ? (TV)__ldg(R + al) : (TV)p.r_const;
+    }
     for (int s = 0; s < S && !overflow; ++s) {
       TV folded;
+      if (ONEPASS) {
+        const int2 e = e_nx;
+        const TV rr = r_nx;
+        if (s + 1 < S && al < A) {  // state s+1's row and rewards: independent of V, in flight during the reduction
+          e_nx = __ldg(cv + ((size_t)(s + 1) * A + al) * KMp + il);
+          r_nx = R ? (TV)__ldg(R + (size_t)(s + 1) * A + al) : (TV)p.r_const;
+        }
+        if (s == pin) {
+          folded = (TV)p.pin_value;
+        } else {
+          TV part = e.x >= 0 ? (TV)__int_as_float(e.y) * Vs[e.x] : TV(0);
+          for (int o = seg >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+          TV cand = ident;
+          if (al < A) {
+            const TV q = rr + gamma * part;
+            if (il == 0 && Qg) Qg[(size_t)s * A + al] = q;
+            if (p.fold == COLO_FOLD_PI) cand = il == 0 ? q * (TV)__ldg(pi + (size_t)s * A + al) : (TV)0;
+            else cand = q;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const TV w = __shfl_xor_sync(FULL, cand, o);
+            if (p.fold == COLO_FOLD_MAX) cand = w > cand ? w : cand;
+            else if (p.fold == COLO_FOLD_MIN) cand = w < cand ? w : cand;
+            else cand += w;
+          }
+          folded = cand;
+        }
+      } else
       if (s == pin) {
         folded = (TV)p.pin_value;
       } else {
@@ -295,9 +332,15 @@ static int gs_launch(GsArgs a, void* stream) {
   const int grid = (a.B + W - 1) / W;
   cudaStream_t st = (cudaStream_t)stream;
   if (a.cv_rm != nullptr) {
-    auto k = gs_sparse_kernel<TV>;
-    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, W * 32, smem, st>>>(a);
+    if (a.A * a.KMp <= 32) {
+      auto k = gs_sparse_kernel<TV, true>;
+      COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, W * 32, smem, st>>>(a);
+    } else {
+      auto k = gs_sparse_kernel<TV, false>;
+      COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, W * 32, smem, st>>>(a);
+    }
     return check_launch("gs_sparse_kernel");
   }
   if (vec) {
