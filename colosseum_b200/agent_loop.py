@@ -167,10 +167,14 @@ class PSRLEpisodic:
 
     def __init__(self, seed: int, tables: MDPTables, optimization_horizon: int, reward_prior_model=None,
                  transitions_prior_model=None, rewards_prior_prms=None, transitions_prior_prms=None,
-                 epsilon_greedy=None, boltzmann_temperature=None, *, n_loops: int = 1, env_offset: int = 0):
+                 epsilon_greedy=None, boltzmann_temperature=None, *, n_loops: int = 1, env_offset: int = 0,
+                 sampler: str = "fast"):
         import torch
 
         _cabi.require_cuda()
+        assert sampler in ("fast", "f64")
+        self._dirichlet = (_cabi.lib().colo_sample_dirichlet_rows_fast if sampler == "fast"
+                           else _cabi.lib().colo_sample_dirichlet_rows)
         assert reward_prior_model in (None, "N_NIG") and transitions_prior_model in (None, "M_DIR"), \
             "the batched PSRL offers the N_NIG / M_DIR conjugate models"
         if boltzmann_temperature is not None:
@@ -216,8 +220,8 @@ class PSRLEpisodic:
         N, S, A = self.n_loops, self.tables.S, self.tables.A
         rows, row0 = N * S * A, self.env_offset * S * A
         st = _cabi.current_stream()
-        rc = lib.colo_sample_dirichlet_rows(self.dir_hyper.data_ptr(), rows, S, row0, self.seed, self.n_samples,
-                                            self.T_sample.data_ptr(), st)
+        rc = self._dirichlet(self.dir_hyper.data_ptr(), rows, S, row0, self.seed, self.n_samples,
+                             self.T_sample.data_ptr(), st)
         _cabi.check(rc, "colo_sample_dirichlet_rows")
         rc = lib.colo_sample_nig_rewards(self.nig_hyper.data_ptr(), rows, row0, self.seed, self.n_samples,
                                          self.R_sample.data_ptr(), st)

@@ -613,6 +613,125 @@ int solve_discounted(const float* T, const float* R, const float* pi, int B, int
   return iterate_to_convergence<TV>(sweep, V, w, B, S, (TV)eps, max_iter, iters_out_host, nullptr, st, V0);
 }
 
+// Many small MDPs (the batched PSRL agents re-solve N sampled models every episode): one CTA walks one MDP through all
+// H layers of backward induction in a single launch.  L lanes (a power of two <= 32) share a row T[s,a,:] -- short
+// rows do not pay a 32-lane reduction each -- with up to four 128-bit loads in flight per lane; V[h+1] and Q[h] live
+// in shared memory, T is re-read from L2 for every layer (only the first layer touches HBM).
+template <typename TV, int L, bool VEC4>
+__global__ void __launch_bounds__(256) episodic_batched_kernel(const float* __restrict__ T, const float* __restrict__ R,
+                                                               const float* __restrict__ pi, int B, int S, int A, int H,
+                                                               int fold, TV* __restrict__ Q, TV* __restrict__ V) {
+  extern __shared__ __align__(16) unsigned char smem_eb[];
+  TV* Vn = reinterpret_cast<TV*>(smem_eb);           // V[h+1], padded to a multiple of 4
+  TV* Qs = Vn + ((S + 3) & ~3);                      // Q[h]
+  const int tid = threadIdx.x, sub = tid % L, grp = tid / L, groups = blockDim.x / L;
+  const int SA = S * A;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float* Tb = T + (size_t)b * SA * S;
+    const float* Rb = R + (size_t)b * SA;
+    TV* Qb = Q + (size_t)b * (H + 1) * SA;
+    TV* Vb = V + (size_t)b * (H + 1) * S;
+    for (int i = tid; i < SA; i += blockDim.x) Qb[(size_t)H * SA + i] = TV(0);
+    for (int i = tid; i < S; i += blockDim.x) {
+      Vb[(size_t)H * S + i] = TV(0);
+      Vn[i] = TV(0);
+    }
+    __syncthreads();
+    for (int h = H - 1; h >= 0; --h) {
+      for (int base = 0; base < SA; base += groups) {  // warp-uniform trip count: the shuffles below use the full mask
+        const int row = base + grp;
+        TV acc = TV(0);
+        if (row < SA) {
+          const float* t = Tb + (size_t)row * S;
+          if (VEC4) {
+            const float4* t4 = reinterpret_cast<const float4*>(t);
+            const int n4 = S >> 2;
+            for (int j0 = sub; j0 < n4; j0 += 4 * L) {
+              float4 x[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (j0 + u * L < n4) x[u] = __ldg(t4 + j0 + u * L);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (j0 + u * L < n4) {
+                  const int j = (j0 + u * L) << 2;
+                  acc += (TV)x[u].x * Vn[j] + (TV)x[u].y * Vn[j + 1] + (TV)x[u].z * Vn[j + 2] + (TV)x[u].w * Vn[j + 3];
+                }
+            }
+          } else {
+            for (int j = sub; j < S; j += L) acc += (TV)__ldg(t + j) * Vn[j];
+          }
+        }
+#pragma unroll
+        for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (row < SA && sub == 0) {
+          const TV q = (TV)__ldg(Rb + row) + acc;
+          Qs[row] = q;
+          Qb[(size_t)h * SA + row] = q;
+        }
+      }
+      __syncthreads();
+      for (int s0 = tid; s0 < S; s0 += blockDim.x) {
+        TV v;
+        if (fold == COLO_FOLD_PI) {
+          const float* p = pi + ((size_t)b * H + h) * SA + (size_t)s0 * A;
+          v = TV(0);
+          for (int a = 0; a < A; ++a) v += Qs[s0 * A + a] * (TV)__ldg(p + a);
+        } else {
+          v = Qs[s0 * A];
+          for (int a = 1; a < A; ++a) {
+            const TV q = Qs[s0 * A + a];
+            v = fold == COLO_FOLD_MAX ? (q > v ? q : v) : (q < v ? q : v);
+          }
+        }
+        Vn[s0] = v;
+        Vb[(size_t)h * S + s0] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <typename TV, int L>
+static int episodic_batched_launch(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
+                                   TV* Q, TV* V, bool vec4, size_t smem, cudaStream_t st) {
+  // resident CTAs are capped so that the T of the MDPs in flight stays in L2 between layers
+  const size_t t_bytes = (size_t)S * A * S * sizeof(float);
+  long long cap = (long long)(96ull << 20) / (long long)(t_bytes ? t_bytes : 1);
+  const long long lo = sm_count(), hi = (long long)sm_count() * 8;
+  cap = cap < lo ? lo : (cap > hi ? hi : cap);
+  const int grid = (int)(B < cap ? B : cap);
+  if (vec4) {
+    auto k = episodic_batched_kernel<TV, L, true>;
+    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V);
+  } else {
+    auto k = episodic_batched_kernel<TV, L, false>;
+    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V);
+  }
+  return check_launch("episodic_batched_kernel");
+}
+
+// returns COLO_OK with *handled = 1 when the batched kernel took the solve
+template <typename TV>
+static int episodic_batched(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
+                            TV* Q, TV* V, int* handled, cudaStream_t st) {
+  *handled = 0;
+  const size_t smem = ((size_t)((S + 3) & ~3) + (size_t)S * A) * sizeof(TV);
+  static const bool off = getenv("COLO_EPISODIC_BATCHED") && atoi(getenv("COLO_EPISODIC_BATCHED")) == 0;
+  if (off || B < 16 || H < 1 || smem > (size_t)96 * 1024 || (size_t)S * A * S * sizeof(float) > ((size_t)8 << 20)) return COLO_OK;
+  const bool vec4 = (S % 4 == 0) && ((uintptr_t)T % 16 == 0);
+  const int units = vec4 ? S / 4 : S;  // loads per row
+  int r;
+  if (units <= 16) r = episodic_batched_launch<TV, 4>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
+  else if (units <= 32) r = episodic_batched_launch<TV, 8>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
+  else if (units <= 64) r = episodic_batched_launch<TV, 16>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
+  else r = episodic_batched_launch<TV, 32>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
+  if (r == COLO_OK) *handled = 1;
+  return r;
+}
+
 template <typename TV>
 int episodic(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold, double max_value,
              TV* Q, TV* V, void* stream) {
@@ -620,6 +739,11 @@ int episodic(const float* T, const float* R, const float* pi, int B, int S, int 
   COLO_ARG_CHECK(H >= 0, "H");
   cudaStream_t st = (cudaStream_t)stream;
   const long long qs = (long long)(H + 1) * S * A, vs = (long long)(H + 1) * S;
+  if (!(max_value > 0)) {  // many small instances, no overflow test: one CTA per instance, all layers in one launch
+    int handled = 0;
+    const int r = episodic_batched<TV>(T, R, pi, B, S, A, H, fold, Q, V, &handled, st);
+    if (r != COLO_OK || handled) return r;
+  }
   int* flag = nullptr;
   if (max_value > 0) {
     COLO_CUDA_TRY(cudaMallocAsync(&flag, sizeof(int), st));

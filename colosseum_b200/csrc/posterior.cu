@@ -42,6 +42,37 @@ __device__ __forceinline__ double gamma_draw(double alpha, uint64_t seed, uint64
   return g;
 }
 
+// Single-precision variant of gamma_draw for the hot loop of the batched PSRL agents (N*S*A*S draws per episode): one
+// Philox block per attempt feeds the normal (Box-Muller on two 24/32-bit uniforms), the squeeze test and the
+// alpha < 1 boost; log / pow / cos go through the SFU.  The normal is truncated at 5.8 sigma (24-bit uniform) and the
+// transcendental error is ~1e-6 relative: invisible to the float32 result the reference keeps, but not the fp64
+// arithmetic numpy uses -- hence a separate entry point (colo_sample_dirichlet_rows_fast).
+__device__ __forceinline__ float gamma_draw_fast(float alpha, uint64_t seed, uint64_t elem, uint64_t t) {
+  if (!(alpha > 0.f)) return 0.f;
+  const float a = alpha < 1.f ? alpha + 1.f : alpha;
+  const float d = a - (1.f / 3.f), c = rsqrtf(9.f * d);
+  for (uint64_t attempt = 0; attempt < 64; ++attempt) {
+    const Philox4 w = philox4x32_10(seed, elem, (t << 8) | attempt);
+    const float u1 = ((float)(w.w[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (float)w.w[1] * (1.0f / 4294967296.0f);
+    const float x = sqrtf(-2.f * __logf(u1)) * cospif(2.f * u2);
+    const float v0 = 1.f + c * x;
+    if (v0 <= 0.f) continue;
+    const float v = v0 * v0 * v0;
+    const float u = ((float)(w.w[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    if (__logf(u) < 0.5f * x * x + d - d * v + d * __logf(v)) {
+      float g = d * v;
+      if (alpha < 1.f) {  // gamma(alpha) = gamma(alpha + 1) * U^(1/alpha)
+        const float ub = ((float)(w.w[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        g *= exp2f(__log2f(ub) / alpha);
+      }
+      return g;
+    }
+  }
+  return 0.f;
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(256) dirichlet_rows_kernel(const float* __restrict__ hyper, long long rows, int S,
                                                              long long row0, unsigned long long seed,
                                                              unsigned long long t, float* __restrict__ T) {
@@ -53,7 +84,8 @@ __global__ void __launch_bounds__(256) dirichlet_rows_kernel(const float* __rest
     float* out = T + (size_t)r * S;
     float sum = 0.f;
     for (int j = lane; j < S; j += 32) {
-      const float g = (float)gamma_draw((double)h[j], seed, (uint64_t)(row0 + r) * (uint64_t)S + (uint64_t)j, t);
+      const uint64_t elem = (uint64_t)(row0 + r) * (uint64_t)S + (uint64_t)j;
+      const float g = FAST ? gamma_draw_fast(h[j], seed, elem, t) : (float)gamma_draw((double)h[j], seed, elem, t);
       out[j] = g;
       sum += g;
     }
@@ -92,13 +124,27 @@ extern "C" int colo_sample_nig_rewards(const float* hyper, long long rows, long 
   return colo::check_launch("nig_rows_kernel");
 }
 
-extern "C" int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0,
-                                          unsigned long long seed, unsigned long long t, float* T_out, void* stream) {
+static int dirichlet_launch(const float* hyper, long long rows, int S, long long row0, unsigned long long seed,
+                            unsigned long long t, float* T_out, void* stream, bool fast) {
   COLO_ARG_CHECK(hyper && T_out && rows >= 0 && S > 0 && row0 >= 0, "hyper, T_out, rows, S, row0");
   if (rows == 0) return COLO_OK;
   const long long blocks = (rows + 7) / 8;
   const long long cap = (long long)colo::sm_count() * 16;
-  colo::dirichlet_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(hyper, rows, S, row0,
-                                                                                                    seed, t, T_out);
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  if (fast)
+    colo::dirichlet_rows_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(hyper, rows, S, row0, seed, t, T_out);
+  else
+    colo::dirichlet_rows_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(hyper, rows, S, row0, seed, t, T_out);
   return colo::check_launch("dirichlet_rows_kernel");
+}
+
+extern "C" int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0,
+                                          unsigned long long seed, unsigned long long t, float* T_out, void* stream) {
+  return dirichlet_launch(hyper, rows, S, row0, seed, t, T_out, stream, false);
+}
+
+extern "C" int colo_sample_dirichlet_rows_fast(const float* hyper, long long rows, int S, long long row0,
+                                               unsigned long long seed, unsigned long long t, float* T_out,
+                                               void* stream) {
+  return dirichlet_launch(hyper, rows, S, row0, seed, t, T_out, stream, true);
 }

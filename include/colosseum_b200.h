@@ -285,6 +285,10 @@ int colo_sample_nig_rewards(const float* hyper, long long rows, long long row0, 
                             unsigned long long t, float* R_out, void* stream);
 int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0, unsigned long long seed,
                                unsigned long long t, float* T_out, void* stream);
+/* The same sample with single-precision arithmetic (SFU log / pow / cos, normal truncated at 5.8 sigma): another
+ * stream of numbers with the same distribution up to ~1e-6, ~20x the throughput; used by the batched PSRL loops. */
+int colo_sample_dirichlet_rows_fast(const float* hyper, long long rows, int S, long long row0, unsigned long long seed,
+                               unsigned long long t, float* T_out, void* stream);
 
 /* ---------------------------------------------------------------- policy-induced Markov chain -------------- */
 /*

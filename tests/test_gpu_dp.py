@@ -281,3 +281,31 @@ def test_gauss_seidel_reproduces_the_reference_iterate(dp, dp_synth):
         np.testing.assert_allclose(Vb[i], Vi, atol=1.5e-3)
     with pytest.raises(dp.DynamicProgrammingMaxIterationExceeded):
         dp._solve_discounted(g["T_0"], g["R_0"], None, 0.99, 1e-12, None, "f64", max_iter=5, sweep_order="gauss_seidel")
+
+
+@pytest.mark.parametrize("S,A,H", [(5, 2, 5), (36, 2, 8), (108, 6, 7), (130, 3, 4), (200, 4, 3), (465, 2, 3)])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_batched_small_episodic_solves(dp, S, A, H, precision):
+    """B >= 16 instances take the one-CTA-per-MDP kernel (all layers in one launch; 4/8/16/32 lanes per row, 128-bit
+    or scalar loads): VI and PE against the fp64 oracle per instance, and against the per-instance (B = 1) path."""
+    import torch
+
+    B = 19
+    rs = np.random.RandomState(S)
+    T = rs.dirichlet(np.ones(S) * 0.3, size=(B, S, A)).astype(np.float32)
+    R = rs.rand(B, S, A).astype(np.float32)
+    pol = rs.dirichlet(np.ones(A), size=(B, H, S)).astype(np.float32)
+    Td, Rd, pd = torch.from_numpy(T).cuda(), torch.from_numpy(R).cuda(), torch.from_numpy(pol).cuda()
+    Q, V = dp.episodic_value_iteration(H, Td, Rd, precision=precision)
+    Qp, Vp = dp.episodic_policy_evaluation(H, Td, Rd, pd, precision=precision)
+    assert tuple(Q.shape) == (B, H + 1, S, A) and tuple(V.shape) == (B, H + 1, S)
+    tol = 1e-9 if precision == "f64" else 2e-5
+    for b in (0, 7, B - 1):
+        Qo, Vo = orc.episodic_f64(H, T[b], R[b])
+        np.testing.assert_allclose(Q[b].cpu().numpy(), Qo, rtol=tol, atol=tol)
+        np.testing.assert_allclose(V[b].cpu().numpy(), Vo, rtol=tol, atol=tol)
+        Qpo, Vpo = orc.episodic_f64(H, T[b], R[b], pi=pol[b])
+        np.testing.assert_allclose(Vp[b].cpu().numpy(), Vpo, rtol=tol, atol=tol)
+        Q1, V1 = dp.episodic_value_iteration(H, Td[b], Rd[b], precision=precision)
+        np.testing.assert_allclose(V[b].cpu().numpy(), V1.cpu().numpy(), rtol=tol, atol=tol)
+    assert float(Q[:, H].abs().max()) == 0.0 and float(V[:, H].abs().max()) == 0.0

@@ -5,11 +5,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_dirichlet_rows_distribution():
+@pytest.mark.parametrize("fast", [False, True])
+def test_dirichlet_rows_distribution(fast):
+    import functools
+
     import scipy.stats
 
     from colosseum_b200.posterior import sample_transition_model
 
+    sample_transition_model = functools.partial(sample_transition_model, fast=fast)
     rs = np.random.RandomState(0)
     S = 6
     alpha = np.array([0.05, 0.5, 1.0, 2.5, 30.0, 400.0], np.float32)
