@@ -268,6 +268,33 @@ class PSRLEpisodic:
         return get_policy_from_q_values(Q.cpu().numpy(), True)
 
 
+_CKPT_FIELDS = ("state", "h", "cumulative_reward", "n_episodes", "N", "Q", "Q_main", "V", "mu", "sigma", "beta",
+                "dir_hyper", "nig_hyper", "T_sample", "R_sample")
+
+
+def agents_state_dict(agents):
+    """checkpoint of a batch of loops (env state, agent tables, Philox counters): resuming reproduces the run bit for
+    bit"""
+    agents.torch.cuda.current_stream().synchronize()
+    d = {k: getattr(agents, k).cpu() for k in _CKPT_FIELDS if hasattr(agents, k)}
+    d["t"] = agents.t
+    for k in ("n_samples", "_h_episode"):
+        if hasattr(agents, k):
+            d[k] = getattr(agents, k)
+    return d
+
+
+def agents_load_state_dict(agents, d):
+    for k in _CKPT_FIELDS:
+        if k in d:
+            getattr(agents, k).copy_(d[k])
+    agents.t = int(d["t"])
+    for k in ("n_samples", "_h_episode"):
+        if k in d:
+            setattr(agents, k, int(d[k]))
+    agents.torch.cuda.current_stream().synchronize()
+
+
 class BatchedMDPLoop:
     """MDPLoop for N loops at once.  `T`, `R` (numpy float32) are only needed for the regret indicators."""
 

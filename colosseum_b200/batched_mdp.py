@@ -333,6 +333,38 @@ class BatchedMDP:
         except Exception:
             pass
 
+    # -- checkpoint / resume: the whole state of the batch is three small tensors, the Philox counter and the counters
+    def state_dict(self):
+        """everything needed to continue the trajectories bit for bit (checkpoint/resume)"""
+        assert getattr(self, "_srv", None) is None, "stop_serving() before taking a checkpoint"
+        self.torch.cuda.current_stream().synchronize()
+        d = {"n_envs": self.n_envs, "seed": self.seed, "env_offset": self.env_offset, "t": self.t, "mode": self.mode,
+             "was_reset": self._was_reset, "state": self.state.cpu(), "h": self.h.cpu(),
+             "step_type": (self.step_type_host if self.host_io else self.step_type).cpu().clone(),
+             "obs": self.obs.cpu().clone(), "reward": self.reward.cpu().clone()}
+        if self._visits_s is not None:
+            d["visits_s"], d["visits_sa"] = self._visits_s.sum(0).cpu(), self._visits_sa.sum(0).cpu()
+        return d
+
+    def load_state_dict(self, d):
+        assert d["n_envs"] == self.n_envs and d["mode"] == self.mode, "checkpoint of another batch shape / sampler mode"
+        self.seed, self.env_offset, self.t = int(d["seed"]), int(d["env_offset"]), int(d["t"])
+        self._batch.seed, self._batch.env0 = self.seed, self.env_offset
+        self._was_reset = bool(d["was_reset"])
+        self.state.copy_(d["state"])
+        self.h.copy_(d["h"])
+        self.step_type.copy_(d["step_type"])
+        if self.host_io:
+            self.step_type_host.copy_(d["step_type"])
+        self.obs.copy_(d["obs"])
+        self.reward.copy_(d["reward"])
+        if self._visits_s is not None and "visits_s" in d:
+            self._visits_s.zero_()
+            self._visits_sa.zero_()
+            self._visits_s[0].copy_(d["visits_s"])
+            self._visits_sa[0].copy_(d["visits_sa"])
+        self.torch.cuda.current_stream().synchronize()
+
     def fetch_async(self, host_buffer):
         """one device->host copy of (obs i32[N] | reward f32[N] | step_type u8[N]) into a pinned uint8 buffer of
         9*N bytes, enqueued on the current stream; `split_host` views it as the three arrays."""

@@ -166,3 +166,20 @@ def test_psrl_learns_river_swim():
     rnd = al.QLearningEpisodic(0, tb, 5000, p=0.05, c_1=0.05, epsilon_greedy=1.0, n_loops=64)
     rnd.steps(5000)
     assert logs[-1]["cumulative_reward"].mean() > 1.15 * rnd.cumulative_reward.mean().item()
+
+
+def test_agent_checkpoint_resume_is_bit_exact():
+    import colosseum_b200.agent_loop as al
+
+    tb = MDPTables.from_golden(load_instance("frozenlake4_epi"))
+    for make in (lambda s: al.QLearningEpisodic(s, tb, 10 ** 4, p=0.05, c_1=0.4, c_2=0.4, UCB_type="bernstein", n_loops=100),
+                 lambda s: al.PSRLEpisodic(s, tb, 10 ** 4, n_loops=100)):
+        a = make(7)
+        a.steps(5 * tb.H + 3)
+        ck = al.agents_state_dict(a)
+        tr_a = a.steps(4 * tb.H, trace=True).cpu().numpy()
+        b = make(7)
+        al.agents_load_state_dict(b, ck)
+        tr_b = b.steps(4 * tb.H, trace=True).cpu().numpy()
+        assert np.array_equal(tr_a, tr_b)
+        assert np.array_equal(a.cumulative_reward.cpu().numpy(), b.cumulative_reward.cpu().numpy())

@@ -437,3 +437,33 @@ def test_pipelined_groups_equal_the_unsplit_batch(bm):
             if serving:
                 env.stop_serving()
         assert torch.equal(env.get_visitation_counts(False), one.visits_sa)
+
+
+@pytest.mark.parametrize("mode,host_io", [("dense_f32", False), ("succ", True)])
+def test_checkpoint_resume_is_bit_exact(bm, mode, host_io):
+    """state_dict / load_state_dict: a batch restored from a checkpoint (into a fresh object) continues the very same
+    trajectories, rewards and visitation counts"""
+    import torch
+
+    tb = MDPTables.from_golden(load_instance("taxi_epi"))
+    N = 2000
+    gen = torch.Generator().manual_seed(0)
+    acts = [torch.randint(0, tb.A, (N,), dtype=torch.int32, generator=gen) for _ in range(30)]
+    a = bm.BatchedMDP(tb, N, mode=mode, seed=4, host_io=host_io)
+    a.reset()
+    for k in range(10):
+        a.step_async(acts[k].cuda(), auto_reset=True)
+    ck = a.state_dict()
+    tail_a = []
+    for k in range(10, 30):
+        a.step_async(acts[k].cuda(), auto_reset=True)
+        torch.cuda.synchronize()
+        tail_a.append((a.obs.clone().cpu(), a.reward.clone().cpu()))
+    b = bm.BatchedMDP(tb, N, mode=mode, seed=999, host_io=host_io)
+    b.load_state_dict(ck)
+    for k in range(10, 30):
+        b.step_async(acts[k].cuda(), auto_reset=True)
+        torch.cuda.synchronize()
+        o, r = tail_a[k - 10]
+        assert torch.equal(b.obs.cpu(), o) and np.array_equal(b.reward.cpu().numpy(), r.numpy(), equal_nan=True)
+    assert torch.equal(a.visits_sa, b.visits_sa) and torch.equal(a.visits_s, b.visits_s) and a.t == b.t
