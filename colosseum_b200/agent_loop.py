@@ -335,12 +335,62 @@ class BatchedMDPLoop:
                 out[k] = 0.0 if (np.isclose(r, 0.0, atol=1e-3) or r < 0) else r
         return out
 
+    def _expected_regret_all(self, chunk: int = 4096):
+        """episodic: the per-step expected regret of EVERY loop's greedy policy, on the device: one-hot greedy policies
+        (uniformly random among argmax ties under the reference's fixed seed 42, dynamic_programming/utils.py:4,30-38 --
+        the draws themselves differ from numba's stream), all evaluated on the true MDP by one launch of
+        colo_episodic_policies_f32 per chunk of loops, then max(V*[0] - V[0], 0) averaged over the start distribution
+        and divided by H (indicators.py:29-45, agent_mdp_interaction.py:549-566)."""
+        import torch
+
+        from . import dynamic_programming as dp
+
+        ag, tb = self.agents, self.agents.tables
+        assert ag.episodic and self.T is not None
+        S, A, H = tb.S, tb.A, tb.H
+        if not hasattr(self, "_dev_TR"):
+            Td, Rd = dp.to_device(self.T), dp.to_device(self.R)
+            v_star = dp.episodic_value_iteration(H, Td, Rd, precision="f32")[1][0]
+            start = torch.zeros(S, dtype=torch.float64, device="cuda")
+            prob = np.diff(np.concatenate([[0.0], np.asarray(tb.start_cum, np.float64)]))
+            start.index_add_(0, torch.from_numpy(np.asarray(tb.start_idx, np.int64)).cuda(),
+                             torch.from_numpy(prob / prob.sum()).cuda())
+            self._dev_TR = (Td, Rd, v_star.double(), start)
+        Td, Rd, v_star, start = self._dev_TR
+        if isinstance(ag, PSRLEpisodic):  # greedy policy of the MAP model (posterior_sampling.py:76-80)
+            T_map, R_map = ag.get_map_estimate()
+            Qall = dp.episodic_value_iteration(H, T_map.contiguous(), R_map.contiguous(), precision="f32")[0][:, :H]
+        else:
+            Qall = ag.Q
+        out = torch.empty(ag.n_loops, dtype=torch.float64, device="cuda")
+        gen = torch.Generator(device="cuda").manual_seed(dp.ARGMAX_SEED)
+        lib = _cabi.lib()
+        for lo in range(0, ag.n_loops, chunk):
+            Qc = Qall[lo:lo + chunk]
+            n = Qc.shape[0]
+            tie = torch.rand(Qc.shape, generator=gen, device="cuda")
+            idx = torch.where(Qc == Qc.max(-1, keepdim=True).values, tie, torch.full_like(tie, -1.0)).argmax(-1)
+            pi = torch.nn.functional.one_hot(idx, A).to(torch.float32).contiguous()
+            Qp = torch.empty((n, H + 1, S, A), dtype=torch.float32, device="cuda")
+            Vp = torch.empty((n, H + 1, S), dtype=torch.float32, device="cuda")
+            rc = lib.colo_episodic_policies_f32(Td.data_ptr(), Rd.data_ptr(), pi.data_ptr(), n, S, A, H, Qp.data_ptr(),
+                                                Vp.data_ptr(), _cabi.current_stream())
+            _cabi.check(rc, "colo_episodic_policies_f32")
+            reg = (v_star[None, :] - Vp[:, 0].double()).clamp_min(0.0)
+            out[lo:lo + n] = (reg * start[None, :]).sum(-1) / H
+        return out.cpu().numpy()
+
     def run(self, T: int, log_every: int = -1, regret_for=None):
         """T interaction steps for every loop, `log_every` steps per launch.  Returns the list of log records
         (steps, cumulative_reward f64[N], n_episodes i64[N], and -- for the loops listed in `regret_for`, when T/R were
-        given -- regret and cumulative_regret)."""
+        given -- regret and cumulative_regret).  regret_for="all" (episodic agents): every loop, evaluated on the device
+        in one launch per tick."""
         ag = self.agents
         log_every = T if log_every in (0, -1, None) else int(log_every)
+        all_loops = isinstance(regret_for, str) and regret_for == "all"
+        if all_loops:
+            assert ag.episodic and self.T is not None, "regret_for='all' needs an episodic agent batch and T, R"
+            regret_for = list(range(ag.n_loops))
         regret_for = [] if (regret_for is None or self.T is None) else list(regret_for)
         cum_regret = np.zeros(len(regret_for))
         done = 0
@@ -351,7 +401,7 @@ class BatchedMDPLoop:
             rec = {"steps": done, "cumulative_reward": ag.cumulative_reward.cpu().numpy(),
                    "n_episodes": ag.n_episodes.cpu().numpy()}
             if regret_for:
-                reg = self._expected_regret(regret_for)
+                reg = self._expected_regret_all() if all_loops else self._expected_regret(regret_for)
                 cum_regret = cum_regret + reg * n  # agent_mdp_interaction.py:503-506
                 rec["regret"], rec["cumulative_regret"] = reg, cum_regret.copy()
             self.logs.append(rec)

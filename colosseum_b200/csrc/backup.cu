@@ -620,15 +620,16 @@ int solve_discounted(const float* T, const float* R, const float* pi, int B, int
 template <typename TV, int L, bool VEC4>
 __global__ void __launch_bounds__(256) episodic_batched_kernel(const float* __restrict__ T, const float* __restrict__ R,
                                                                const float* __restrict__ pi, int B, int S, int A, int H,
-                                                               int fold, TV* __restrict__ Q, TV* __restrict__ V) {
+                                                               int fold, TV* __restrict__ Q, TV* __restrict__ V,
+                                                               long long t_stride, long long r_stride) {
   extern __shared__ __align__(16) unsigned char smem_eb[];
   TV* Vn = reinterpret_cast<TV*>(smem_eb);           // V[h+1], padded to a multiple of 4
   TV* Qs = Vn + ((S + 3) & ~3);                      // Q[h]
   const int tid = threadIdx.x, sub = tid % L, grp = tid / L, groups = blockDim.x / L;
   const int SA = S * A;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    const float* Tb = T + (size_t)b * SA * S;
-    const float* Rb = R + (size_t)b * SA;
+    const float* Tb = T + (size_t)b * t_stride;  // stride 0: every instance evaluates its policy on the same MDP
+    const float* Rb = R + (size_t)b * r_stride;
     TV* Qb = Q + (size_t)b * (H + 1) * SA;
     TV* Vb = V + (size_t)b * (H + 1) * S;
     for (int i = tid; i < SA; i += blockDim.x) Qb[(size_t)H * SA + i] = TV(0);
@@ -694,21 +695,23 @@ __global__ void __launch_bounds__(256) episodic_batched_kernel(const float* __re
 
 template <typename TV, int L>
 static int episodic_batched_launch(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
-                                   TV* Q, TV* V, bool vec4, size_t smem, cudaStream_t st) {
+                                   TV* Q, TV* V, bool vec4, size_t smem, cudaStream_t st, bool shared_mdp) {
   // resident CTAs are capped so that the T of the MDPs in flight stays in L2 between layers
   const size_t t_bytes = (size_t)S * A * S * sizeof(float);
   long long cap = (long long)(96ull << 20) / (long long)(t_bytes ? t_bytes : 1);
   const long long lo = sm_count(), hi = (long long)sm_count() * 8;
   cap = cap < lo ? lo : (cap > hi ? hi : cap);
+  if (shared_mdp) cap = hi;  // one T for everybody: it stays in L2 whatever the number of CTAs
   const int grid = (int)(B < cap ? B : cap);
+  const long long ts = shared_mdp ? 0 : (long long)S * A * S, rs = shared_mdp ? 0 : (long long)S * A;
   if (vec4) {
     auto k = episodic_batched_kernel<TV, L, true>;
     COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V);
+    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
   } else {
     auto k = episodic_batched_kernel<TV, L, false>;
     COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V);
+    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
   }
   return check_launch("episodic_batched_kernel");
 }
@@ -716,18 +719,24 @@ static int episodic_batched_launch(const float* T, const float* R, const float* 
 // returns COLO_OK with *handled = 1 when the batched kernel took the solve
 template <typename TV>
 static int episodic_batched(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
-                            TV* Q, TV* V, int* handled, cudaStream_t st) {
+                            TV* Q, TV* V, int* handled, cudaStream_t st, bool shared_mdp = false) {
   *handled = 0;
   const size_t smem = ((size_t)((S + 3) & ~3) + (size_t)S * A) * sizeof(TV);
   static const bool off = getenv("COLO_EPISODIC_BATCHED") && atoi(getenv("COLO_EPISODIC_BATCHED")) == 0;
-  if (off || B < 16 || H < 1 || smem > (size_t)96 * 1024 || (size_t)S * A * S * sizeof(float) > ((size_t)8 << 20)) return COLO_OK;
+  if (!shared_mdp &&
+      (off || B < 16 || H < 1 || smem > (size_t)96 * 1024 || (size_t)S * A * S * sizeof(float) > ((size_t)8 << 20)))
+    return COLO_OK;
+  if (shared_mdp && (H < 1 || smem > (size_t)200 * 1024)) {
+    set_error("colo_episodic_policies: S*(A+1) = %d values do not fit shared memory", S * (A + 1));
+    return COLO_ERR_ARG;
+  }
   const bool vec4 = (S % 4 == 0) && ((uintptr_t)T % 16 == 0);
   const int units = vec4 ? S / 4 : S;  // loads per row
   int r;
-  if (units <= 16) r = episodic_batched_launch<TV, 4>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
-  else if (units <= 32) r = episodic_batched_launch<TV, 8>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
-  else if (units <= 64) r = episodic_batched_launch<TV, 16>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
-  else r = episodic_batched_launch<TV, 32>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st);
+  if (units <= 16) r = episodic_batched_launch<TV, 4>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st, shared_mdp);
+  else if (units <= 32) r = episodic_batched_launch<TV, 8>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st, shared_mdp);
+  else if (units <= 64) r = episodic_batched_launch<TV, 16>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st, shared_mdp);
+  else r = episodic_batched_launch<TV, 32>(T, R, pi, B, S, A, H, fold, Q, V, vec4, smem, st, shared_mdp);
   if (r == COLO_OK) *handled = 1;
   return r;
 }
@@ -1134,6 +1143,22 @@ int colo_episodic_f32(const float* T, const float* R, const float* pi, int B, in
                       float max_value, float* Q, float* V, void* stream) {
   return colo::episodic<float>(T, R, pi, B, S, A, H, fold, max_value, Q, V, stream);
 }
+int colo_episodic_policies_f32(const float* T, const float* R, const float* pi, int B, int S, int A, int H, float* Q,
+                               float* V, void* stream) {
+  COLO_ARG_CHECK(T && R && pi && Q && V && B >= 0 && S > 0 && A > 0 && H >= 1, "T, R, pi, Q, V, B, S, A, H");
+  if (B == 0) return COLO_OK;
+  int handled = 0;
+  return colo::episodic_batched<float>(T, R, pi, B, S, A, H, COLO_FOLD_PI, Q, V, &handled, (cudaStream_t)stream, true);
+}
+
+int colo_episodic_policies_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, int H,
+                                  double* Q, double* V, void* stream) {
+  COLO_ARG_CHECK(T && R && pi && Q && V && B >= 0 && S > 0 && A > 0 && H >= 1, "T, R, pi, Q, V, B, S, A, H");
+  if (B == 0) return COLO_OK;
+  int handled = 0;
+  return colo::episodic_batched<double>(T, R, pi, B, S, A, H, COLO_FOLD_PI, Q, V, &handled, (cudaStream_t)stream, true);
+}
+
 int colo_episodic_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
                          double max_value, double* Q, double* V, void* stream) {
   return colo::episodic<double>(T, R, pi, B, S, A, H, fold, max_value, Q, V, stream);

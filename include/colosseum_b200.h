@@ -183,6 +183,15 @@ int colo_episodic_f32(const float* T, const float* R, const float* pi, int B, in
                       float max_value, float* Q, float* V, void* stream);
 int colo_episodic_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
                          double max_value, double* Q, double* V, void* stream);
+/*
+ * B policies pi f32[B,H,S,A] evaluated on ONE episodic MDP (T f32[S,A,S], R f32[S,A]) in one launch: the regret
+ * indicator of every loop of a batched agent run per log tick (colosseum/experiment/indicators.py:29-45 calls
+ * episodic_policy_evaluation once per agent).  Q [B,H+1,S,A], V [B,H+1,S].  Does not synchronise.
+ */
+int colo_episodic_policies_f32(const float* T, const float* R, const float* pi, int B, int S, int A, int H, float* Q,
+                               float* V, void* stream);
+int colo_episodic_policies_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, int H,
+                                  double* Q, double* V, void* stream);
 
 /*
  * Continuous diameter (colosseum/hardness/measures/diameter.py:20-39,76-106; == :321-346 at the fixed point):

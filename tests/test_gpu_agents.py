@@ -183,3 +183,41 @@ def test_agent_checkpoint_resume_is_bit_exact():
         tr_b = b.steps(4 * tb.H, trace=True).cpu().numpy()
         assert np.array_equal(tr_a, tr_b)
         assert np.array_equal(a.cumulative_reward.cpu().numpy(), b.cumulative_reward.cpu().numpy())
+
+
+def test_batched_regret_of_all_loops_matches_per_loop_indicator():
+    """regret_for='all' (one colo_episodic_policies_f32 launch per tick) against the per-loop indicator path, on
+    policies without argmax ties (ties are broken by different random streams), and against the oracle's PE"""
+    import torch
+
+    import colosseum_b200.agent_loop as al
+    from colosseum_b200 import _cabi
+
+    g = load_instance("taxi_epi")
+    tb = MDPTables.from_golden(g)
+    T, R = np.asarray(g["T"], np.float32), np.asarray(g["R"], np.float32)
+    N = 40
+    ag = al.QLearningEpisodic(1, tb, 10 ** 5, p=0.05, c_1=0.3, n_loops=N)
+    ag.steps(500)
+    ag.Q.add_(torch.rand_like(ag.Q))  # no exact ties (float32 spacing at Q = H is 2e-6): same greedy actions on both paths
+    loop = al.BatchedMDPLoop(ag, T=T, R=R)
+    all_reg = loop._expected_regret_all(chunk=16)
+    some = loop._expected_regret([0, 5, 17, 39])
+    np.testing.assert_allclose(all_reg[[0, 5, 17, 39]], some, rtol=1e-5, atol=1e-7)
+    # the shared-MDP policy evaluation itself against the oracle
+    rs = np.random.RandomState(0)
+    pol = rs.dirichlet(np.ones(tb.A), size=(3, tb.H, tb.S)).astype(np.float32)
+    pd = torch.from_numpy(pol).cuda()
+    Q = torch.empty((3, tb.H + 1, tb.S, tb.A), dtype=torch.float64, device="cuda")
+    V = torch.empty((3, tb.H + 1, tb.S), dtype=torch.float64, device="cuda")
+    Td, Rd = torch.from_numpy(T).cuda(), torch.from_numpy(R).cuda()
+    rc = _cabi.lib().colo_episodic_policies_f64acc(Td.data_ptr(), Rd.data_ptr(), pd.data_ptr(), 3, tb.S, tb.A, tb.H,
+                                                   Q.data_ptr(), V.data_ptr(), _cabi.current_stream())
+    assert rc == 0
+    for b in range(3):
+        Qo, Vo = orc.episodic_f64(tb.H, T, R, pi=pol[b])
+        np.testing.assert_allclose(V[b].cpu().numpy(), Vo, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(Q[b].cpu().numpy(), Qo, rtol=1e-9, atol=1e-12)
+    # and through run(): every loop logged
+    logs = loop.run(200, log_every=100, regret_for="all")
+    assert logs[-1]["regret"].shape == (N,) and (logs[-1]["cumulative_regret"] >= logs[0]["cumulative_regret"]).all()
