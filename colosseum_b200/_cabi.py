@@ -168,6 +168,7 @@ PROTOTYPES = {
     "colo_qlearning_continuous_steps": (_I, [C.POINTER(MdpTables), C.POINTER(QLearningArgs), _I, _ULL, _P]),
     "colo_psrl_episodic_steps": (_I, [C.POINTER(MdpTables), C.POINTER(PsrlArgs), _I, _ULL, _P]),
     "colo_sample_nig_rewards": (_I, [_P, _LL, _LL, _ULL, _ULL, _P, _P]),
+    "colo_emit_noise": (_I, [_P, _P, _P, _LL, _I, _I, _I, _I, _D, _ULL, _ULL, _ULL, _P]),
     "colo_emit_observations": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _P, _P]),
     "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "colo_extended_vi_work_bytes": (C.c_size_t, [_I, _I]),

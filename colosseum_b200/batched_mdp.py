@@ -404,13 +404,37 @@ class BatchedMDP:
         self._emit_table = t.reshape(*t.shape[:lead], -1)
         self._emit_out = torch.empty((self.n_envs, self._emit_table.shape[-1]), dtype=torch.float32, device="cuda")
 
+    def set_emission_noise(self, noise_class=None, seed=0, **noise_kwargs):
+        """the `noise_class` / `noise_kwargs` of EmissionMap (emission_maps/base.py:85-104): "GaussianUncorrelated"
+        (scale=0.1) or "StudentTUncorrelated" (df=3), by name or by reference class; None switches the noise off"""
+        name = None if noise_class is None else getattr(noise_class, "__name__", str(noise_class))
+        if name is None:
+            self._emit_noise = None
+        elif name == "GaussianUncorrelated":
+            self._emit_noise = (1, float(noise_kwargs.get("scale", 0.1)), int(seed))
+        elif name == "StudentTUncorrelated":
+            self._emit_noise = (2, float(noise_kwargs.get("df", 3)), int(seed))
+        else:
+            raise NotImplementedError(f"{name}: only the uncorrelated Gaussian / Student-t noises are built")
+        self._emit_t = 0
+
     def emit_observations(self):
-        """EmissionMap.get_observation for every env (one gather launch); f32 [N, *shape] CUDA tensor."""
+        """EmissionMap.get_observation for every env (one gather launch, plus one noise launch when a noise is set);
+        f32 [N, *shape] CUDA tensor."""
         D = int(self._emit_table.shape[-1])
         rc = _cabi.lib().colo_emit_observations(_cabi.ptr(self._emit_table), _cabi.ptr(self.state), _cabi.ptr(self.h),
                                                 _cabi.ptr(self.step_type), self.n_envs, self.tables.H, self.tables.S, D,
                                                 _cabi.ptr(self._emit_out), _cabi.current_stream())
         _cabi.check(rc, "colo_emit_observations")
+        noise = getattr(self, "_emit_noise", None)
+        if noise is not None:
+            kind, param, seed = noise
+            period = D if kind == 1 else max(1, int(np.prod(self._emit_shape[1:])))
+            rc = _cabi.lib().colo_emit_noise(_cabi.ptr(self._emit_out), _cabi.ptr(self.step_type), _cabi.ptr(self.h),
+                                             self.n_envs, self.tables.H, D, period, kind, param, seed, self._emit_t,
+                                             self.env_offset, _cabi.current_stream())
+            _cabi.check(rc, "colo_emit_noise")
+            self._emit_t += 1
         return self._emit_out.view(self.n_envs, *self._emit_shape)
 
     def random_steps_fused(self, n, auto_reset=True):

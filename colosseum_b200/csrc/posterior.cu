@@ -112,7 +112,50 @@ __global__ void __launch_bounds__(256) nig_rows_kernel(const float* __restrict__
   }
 }
 
+// Emission-map noise (colosseum/noises/*.py added in EmissionMap.get_observation, emission_maps/base.py:136-138): every
+// observation row that is not the all-zero terminal observation gets `period` fresh draws, element j of the row using
+// draw j % period.  kind 1: GaussianUncorrelated (noises/gaussian_uncorrelated.py:11-12; period = D);
+// kind 2: StudentTUncorrelated (noises/student_t_uncorrelated.py:11-12 -- sic: the reference samples ONE array of the
+// observation's shape and hands out its slices along the first axis, so a vector observation receives the same scalar
+// on every feature: period = prod(shape[1:])).
+__global__ void __launch_bounds__(256) emit_noise_kernel(float* __restrict__ out, const unsigned char* __restrict__ step_type,
+                                                         const int* __restrict__ h, long long N, int H, int D, int period,
+                                                         int kind, double param, unsigned long long seed,
+                                                         unsigned long long t, unsigned long long env0) {
+  const long long total = N * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long e = idx / D;
+    const int j = (int)(idx - e * D);
+    if (H > 0 && (h[e] >= H || step_type[e] == COLO_STEP_LAST)) continue;  // zeros past the horizon carry no noise
+    const uint64_t elem = (env0 + (uint64_t)e) * (uint64_t)period + (uint64_t)(j % period);
+    const Philox4 w = philox4x32_10(seed ^ 0x5851F42D4C957F2DULL, elem, t);
+    const double u1 = u53(w.w[0], w.w[1]) + 1.1102230246251565e-16, u2 = (double)w.w[2] * (1.0 / 4294967296.0);
+    const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    double x;
+    if (kind == 1) {
+      x = z * param;
+    } else {  // standard_t(df) = z / sqrt(chi2_df / df), chi2_df = 2 * Gamma(df / 2)
+      const double g = gamma_draw(0.5 * param, seed ^ 0x14057B7EF767814FULL, elem, t);
+      x = z / sqrt(2.0 * g / param);
+    }
+    out[idx] += (float)x;
+  }
+}
+
 }  // namespace colo
+
+extern "C" int colo_emit_noise(float* out, const unsigned char* step_type, const int* h, long long N, int H, int D,
+                               int period, int kind, double param, unsigned long long seed, unsigned long long t,
+                               unsigned long long env0, void* stream) {
+  COLO_ARG_CHECK(out && step_type && h && N >= 0 && D > 0 && period > 0 && period <= D && (kind == 1 || kind == 2) && param > 0,
+                 "out, step_type, h, N, D, period, kind in {1,2}, param > 0");
+  if (N == 0) return COLO_OK;
+  const long long blocks = (N * D + 255) / 256;
+  const long long cap = (long long)colo::sm_count() * 16;
+  colo::emit_noise_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(out, step_type, h, N, H, D, period,
+                                                                                                kind, param, seed, t, env0);
+  return colo::check_launch("emit_noise_kernel");
+}
 
 extern "C" int colo_sample_nig_rewards(const float* hyper, long long rows, long long row0, unsigned long long seed,
                                        unsigned long long t, float* R_out, void* stream) {

@@ -458,6 +458,17 @@ int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch
  */
 int colo_emit_observations(const float* table, const int* state, const int* h, const unsigned char* step_type,
                            long long N, int H, int S, int D, float* out, void* stream);
+/*
+ * colo_emit_noise -- the noise EmissionMap.get_observation adds (emission_maps/base.py:136-138) on top of the rows
+ * written by colo_emit_observations, in place; all-zero terminal observations stay zero (:131-132).  kind 1:
+ * GaussianUncorrelated(scale = param) (colosseum/noises/gaussian_uncorrelated.py), period = D; kind 2:
+ * StudentTUncorrelated(df = param) (noises/student_t_uncorrelated.py -- sic: one draw per slice along the first axis of
+ * the observation, i.e. period = prod(shape[1:]), 1 for vector observations).  Element j of env e uses Philox counter
+ * ((env0 + e) * period + j % period, t).  Distributional parity.  The correlated variants are not built.
+ */
+int colo_emit_noise(float* out, const unsigned char* step_type, const int* h, long long N, int H, int D, int period,
+                    int kind, double param, unsigned long long seed, unsigned long long t, unsigned long long env0,
+                    void* stream);
 int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
                        const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
                        void* stream);

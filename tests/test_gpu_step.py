@@ -467,3 +467,34 @@ def test_checkpoint_resume_is_bit_exact(bm, mode, host_io):
         o, r = tail_a[k - 10]
         assert torch.equal(b.obs.cpu(), o) and np.array_equal(b.reward.cpu().numpy(), r.numpy(), equal_nan=True)
     assert torch.equal(a.visits_sa, b.visits_sa) and torch.equal(a.visits_s, b.visits_s) and a.t == b.t
+
+
+def test_emission_noise_distributions(bm):
+    """EmissionMap noise (emission_maps/base.py:136-138): Gaussian per element, Student-t with the reference's
+    one-draw-per-first-axis-slice broadcast; terminal (all-zero) observations stay zero; draws change every call"""
+    import scipy.stats
+
+    tb = MDPTables.from_golden(load_instance("c1_riverswim_epi"))
+    N = 20000
+    env = bm.BatchedMDP(tb, N, mode="succ", seed=2)
+    table = np.zeros((tb.H, tb.S, 4, 6), np.float32)
+    env.set_emission_table(table)
+    env.reset()
+    for _ in range(tb.H - 1):
+        env.step_async(None, auto_reset=True)
+    env.set_emission_noise("GaussianUncorrelated", seed=3, scale=0.25)
+    a = env.emit_observations().cpu().numpy().astype(np.float64)
+    b = env.emit_observations().cpu().numpy().astype(np.float64)
+    assert not np.array_equal(a, b)
+    assert scipy.stats.kstest(a.ravel()[:200000], scipy.stats.norm(0, 0.25).cdf).pvalue > 1e-3
+    assert abs(np.corrcoef(a[:, 0, 0], a[:, 0, 1])[0, 1]) < 0.03  # uncorrelated features
+    env.set_emission_noise("StudentTUncorrelated", seed=3, df=5)
+    c = env.emit_observations().cpu().numpy().astype(np.float64)
+    assert np.array_equal(c[:, 0, :], c[:, 3, :])  # sic: one row of draws broadcast over the first axis
+    assert scipy.stats.kstest(c[:, 0, :].ravel(), scipy.stats.t(5).cdf).pvalue > 1e-3
+    env.step_async(None, auto_reset=True)  # the last step of the episode: terminal observation, no noise
+    d = env.emit_observations().cpu().numpy()
+    assert bool((env.step_type == 2).all()) and float(np.abs(d).max()) == 0.0
+    env.set_emission_noise(None)
+    with pytest.raises(NotImplementedError):
+        env.set_emission_noise("GaussianCorrelated")
