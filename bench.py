@@ -233,21 +233,22 @@ def bench_step_gpu(args, rank, world):
             b.reset()
             b.step_async(actions[0], auto_reset=True)
         torch.cuda.synchronize()
+        for i in range(max(3, args.warmup)):  # untimed warm-up steps, same rotation
+            batches[i % NB].step_async(actions[i % n_act], auto_reset=True)
+        torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for i, b in enumerate(batches):
-                b.step_async(actions[i % n_act], auto_reset=True)
-        for _ in range(3):
-            graph.replay()
+        with torch.cuda.graph(graph):  # EXACTLY args.steps steps: step i runs on env batch i % NB
+            for i in range(args.steps):
+                batches[i % NB].step_async(actions[i % n_act], auto_reset=True)
+        graph.replay()
         barrier_sync(world)
-        reps = max(1, args.steps // NB + 1)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        for _ in range(reps):
-            graph.replay()
+        graph.replay()
         g1.record()
         barrier_sync(world)
-        b2b = dict(ms=max_over_ranks(g0.elapsed_time(g1), world), steps=reps * NB, batches=NB,
+        assert all(int(b.status.item()) == 0 for b in batches)
+        b2b = dict(ms=max_over_ranks(g0.elapsed_time(g1), world), steps=args.steps, batches=NB,
                    bytes_touched=NB * per_batch)
         del graph, batches
     except Exception as e:  # reported, never fatal: the headline above does not depend on it
@@ -732,14 +733,29 @@ def main():
         }
     if step is not None:
         tb, N = step["tb"], step["N"]
-        sec = step["ms"] / 1e3 / args.steps
+        sec_flushed = step["ms"] / 1e3 / args.steps
+        b2b = step.get("b2b") or {}
+        flushed_note = "L2 flushed between timed steps (256 MiB write), each step timed with its own CUDA-event pair"
+        if "ms" in b2b and b2b["steps"] == args.steps:
+            # headline protocol: inputs larger than L2 instead of a flush -- step i runs on env batch i % NB, every batch
+            # with its own tables, the K steps captured in one CUDA graph and timed as ONE region
+            sec = b2b["ms"] / 1e3 / args.steps
+            l2_note = (f"no flush: step i runs on env batch i % {b2b['batches']} ({b2b['batches']} independent batches of "
+                       f"{N} envs, each with its own tables; {b2b['bytes_touched'] / 2**20:.0f} MiB touched per rotation > "
+                       f"126 MB L2), the {args.steps} steps captured in one CUDA graph, one CUDA-event pair around them")
+            launches = args.steps
+        else:
+            sec, l2_note, launches = sec_flushed, flushed_note, step["launches"]
         bytes_per_launch = STEP_BYTES(tb.S) * N
         line.update({
             "metric": "batched env-steps/sec", "value": world * N / sec, "unit": "env-steps/s", "steps": args.steps,
-            "ms_per_step": 1e3 * sec, "gpu_launches": step["launches"],
+            "ms_per_step": 1e3 * sec, "gpu_launches": launches,
             "config": {"workload": c2_workload(tb.S, tb.A, N),
                        "kernel": "warp-cooperative search of the dense CDF row, supplied actions, in-kernel Philox uniforms",
-                       "l2": "flushed between timed steps (256 MiB write), each step timed with its own CUDA events"},
+                       "l2": l2_note},
+            "flushed_per_step": {"value": world * N / sec_flushed, "unit": "env-steps/s", "ms_per_step": 1e3 * sec_flushed,
+                                 "what": flushed_note + " (the event pair alone costs ~10 us on this GPU: a floor, not "
+                                         "the kernel)"},
             "e2e": {"value": world * N * args.steps / (step["e2e_ms"] / 1e3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": step["h2d"], "d2h_bytes_per_step": step["d2h"],
                     "what": "BatchedMDP(host_io=True).step_host: pinned host actions read, and obs/reward/step_type "
@@ -778,18 +794,10 @@ def main():
         if "ms" in det:
             line["p_rand_none"] = {"value": world * N * det["steps"] / (det["ms"] / 1e3), "unit": "env-steps/s",
                                    "steps": det["steps"],
-                                   "what": "same kernel and protocol on DeepSeaContinuous(size=30, p_rand=None): deterministic rows"}
+                                   "what": "same kernel on DeepSeaContinuous(size=30, p_rand=None): deterministic rows; L2-flush protocol, compare with `flushed_per_step`"}
         elif "error" in det:
             line["p_rand_none"] = {"error": det["error"]}
-        b2b = step.get("b2b") or {}
-        if "ms" in b2b:
-            sec_b = b2b["ms"] / 1e3 / b2b["steps"]
-            line["back_to_back"] = {
-                "value": world * N / sec_b, "unit": "env-steps/s", "us_per_step": 1e6 * sec_b, "steps": b2b["steps"],
-                "what": f"the same step kernel replayed from one CUDA graph over {b2b['batches']} independent env batches "
-                        f"(own tables; {b2b['bytes_touched'] / 2**20:.0f} MiB touched per pass > 126 MB L2, no flush): "
-                        "kernel-to-kernel throughput without the ~10 us per-step event/launch floor of `value`"}
-        elif "error" in b2b:
+        if "error" in b2b:
             line["back_to_back"] = {"error": b2b["error"]}
         if world == 1:
             rate, n, dt = cpu_step_rate(tb, N, args.cpu_seconds)
