@@ -50,6 +50,7 @@ class MdpTables(C.Structure):
         ("rew_q", C.c_void_p), ("n_cls", C.c_int), ("nq", C.c_int),
         ("rmin", C.c_float), ("rmax", C.c_float),
         ("start_cum", C.c_void_p), ("start_idx", C.c_void_p), ("n_start", C.c_int),
+        ("cdf_mid", C.c_void_p), ("cdf_coarse", C.c_void_p),
     ]
 
 
@@ -171,6 +172,7 @@ PROTOTYPES = {
     "colo_emit_noise": (_I, [_P, _P, _P, _LL, _I, _I, _I, _I, _D, _ULL, _ULL, _ULL, _P]),
     "colo_emit_observations": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _P, _P]),
     "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),
+    "colo_build_cdf_index": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "colo_extended_vi_work_bytes": (C.c_size_t, [_I, _I]),
     "colo_extended_vi_f32": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P]),
     "colo_extended_vi_f64acc": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P]),

@@ -431,6 +431,103 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
   }
 }
 
+// SHORT rows, one THREAD per env: a three-round k-ary search instead of reading the whole row.  The last entries of
+// the row's quads are monotone, so the number G of quads lying entirely at or below x is found from (1) the last entry
+// of every 8th quad (4*NCH independent 4-byte loads, all issued before any is consumed), (2) the last entries of the 8
+// quads of the block that holds the crossing, (3) the crossing quad itself (the same 16-byte gather the warp-
+// cooperative kernel ends with).  With the two-level index of colo_mdp_tables (cdf_coarse / cdf_mid: copies of exactly
+// those entries, contiguous) round 1 is NCH 128-bit loads of a table small enough to live in L1 (60 KB at C2) and
+// round 2 one 32-byte sector: 3 sectors per env beyond L1 instead of the 2 KB row, and 3 dependent memory rounds per
+// env instead of 32/U per tile.  With 65,536 envs every warp is resident at once, so the step time IS the length of
+// that dependency chain.  Same comparisons against the same x => the same index, bit for bit.
+template <typename TC, int NCH, bool SERVER>
+__global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const colo_mdp_tables tb, const StepIO io) {
+  const long long n_thr = (long long)gridDim.x * kStepThreads;
+  const long long n_pad = (io.N + 31) & ~31LL;  // whole warps: finish_env uses warp collectives
+  const int S = tb.S, A = tb.A;
+  constexpr int ld = 128 * NCH, NB = 4 * NCH;  // NB blocks of 8 quads
+  const TC* __restrict__ cdf = reinterpret_cast<const TC*>(tb.cdf);
+  const TC* __restrict__ mid = reinterpret_cast<const TC*>(tb.cdf_mid);
+  const TC* __restrict__ coarse = tb.cdf_mid ? reinterpret_cast<const TC*>(tb.cdf_coarse) : nullptr;
+  constexpr bool F32U = sizeof(TC) == 4;
+  for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
+  unsigned long long t_pass = io.t;
+  if (SERVER) {
+    if (!server_wait(io, pass)) return;
+    t_pass += pass - io.srv_seq0 - 1;
+  }
+  for (long long e = (long long)blockIdx.x * kStepThreads + threadIdx.x; e < n_pad; e += n_thr)
+  for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same thread for every step of the launch
+    const bool valid = e < io.N;
+    EnvIn in;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
+    const bool is_last = valid && in.st == COLO_STEP_LAST;
+    const bool resetting = is_last && io.auto_reset;
+    const bool stepping = valid && !is_last;
+    if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
+    int nxt = 0, cls = 0;
+    if (stepping) {
+      const TC* row = cdf + (size_t)(unsigned)(in.s * A + in.a) * (unsigned)ld;
+      TC total, x;
+      int blk = 0, G = 0;
+      nxt = ld;
+      if (coarse) {  // two-level index: NCH 128-bit loads of a small hot table, then the 8 quad ends of one block
+        const unsigned r = (unsigned)(in.s * A + in.a);
+        Quad<TC> cq[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) cq[k].load(coarse + (size_t)r * NB + 4 * k);
+        total = cq[NCH - 1].v[3];  // row[ld-1]: the padding [S, ld) holds the row total, i.e. the value of row[S-1]
+        x = (F32U ? (TC)in.un32 : (TC)in.un64) * total;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) blk += (cq[k].v[0] <= x) + (cq[k].v[1] <= x) + (cq[k].v[2] <= x) + (cq[k].v[3] <= x);
+        if (blk < NB) {
+          Quad<TC> m0, m1;
+          const TC* mp = mid + (size_t)r * (32 * NCH) + 8 * blk;
+          m0.load(mp);
+          m1.load(mp + 4);
+          G = 8 * blk + (m0.v[0] <= x) + (m0.v[1] <= x) + (m0.v[2] <= x) + (m0.v[3] <= x) + (m1.v[0] <= x) +
+              (m1.v[1] <= x) + (m1.v[2] <= x) + (m1.v[3] <= x);
+        }
+      } else {
+        total = __ldg(row + S - 1);
+        x = (F32U ? (TC)in.un32 : (TC)in.un64) * total;
+        TC c[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) c[k] = __ldg(row + 32 * k + 31);  // last entry of quad 8k+7
+#pragma unroll
+        for (int k = 0; k < NB; ++k) blk += c[k] <= x ? 1 : 0;
+        if (blk < NB) {
+          const TC* b = row + 32 * blk;
+          TC q[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) q[k] = __ldg(b + 4 * k + 3);
+          G = 8 * blk;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) G += q[k] <= x ? 1 : 0;
+        }
+      }
+      if (blk < NB) {
+        Quad<TC> qq;
+        qq.load(row + 4 * G);  // the crossing quad: its last entry is > x, its first three decide
+        nxt = 4 * G + (qq.v[0] <= x) + (qq.v[1] <= x) + (qq.v[2] <= x);
+      }
+      if (nxt >= S) {  // x >= total (rounding): bisect's hi = n-1 clamp == first index where the row reaches total
+        nxt = 0;
+        while (nxt < S - 1 && __ldg(row + nxt) < total) ++nxt;
+      }
+      if (tb.rew_cls_sas)
+        cls = tb.rew_cls_sas[((size_t)in.s * A + in.a) * S + nxt];
+      else if (tb.rew_cls_sa)
+        cls = tb.rew_cls_sa[(size_t)in.s * A + in.a];
+    }
+    finish_env(io, tb, valid ? e : 0, in, nxt, cls, stepping, resetting);
+  }
+  if (!SERVER) return;
+  server_done(io, pass);
+  }
+}
+
 template <bool SERVER>
 __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_mdp_tables tb, const StepIO io) {
   const long long n_thr = (long long)gridDim.x * kStepThreads;
@@ -513,6 +610,20 @@ __global__ void build_dense_cdf_kernel(const float* __restrict__ T, int S, int A
   }
 }
 
+template <typename TC>
+__global__ void build_cdf_index_kernel(const TC* __restrict__ cdf, long long rows, int ld, TC* __restrict__ mid,
+                                       TC* __restrict__ coarse) {
+  const int nq = ld / 4, nb = ld / 32;
+  const long long total = rows * nq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nq;
+    const int q = (int)(i - r * nq);
+    const TC v = cdf[r * ld + 4 * q + 3];
+    mid[i] = v;
+    if ((q & 7) == 7) coarse[r * nb + (q >> 3)] = v;
+  }
+}
+
 // Non-tabular observations: EmissionMap.get_observation (colosseum/emission_maps/base.py:110-140) is a row gather from
 // the precomputed table all_observations[h, s, ...] (:56-76); past the horizon (in_episode_time >= H, i.e. the LAST
 // step of an episode) the reference returns zeros (:131-132).  One warp per env copies the D floats of its row.
@@ -586,6 +697,27 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
     // measured on B200 at N=65,536 (14 warps/SM with 32-env tiles): 32 -> 14.1 us, 16 -> 14.4 us, 8 -> 16.6 us
     int tile = warps32 >= (long long)sm_count() * 8 ? 32 : (warps32 >= (long long)sm_count() * 4 ? 16 : 8);
     if (forced == 8 || forced == 16 || forced == 32) tile = forced;
+    // thread-per-env k-ary search (default) or the warp-cooperative full-row count (COLO_STEP_KERNEL=coop)
+    static const bool coop = getenv("COLO_STEP_KERNEL") && !strcmp(getenv("COLO_STEP_KERNEL"), "coop");
+    if (!coop) {
+      const int gk = grid_for(kStepThreads, io.N);
+#define COLO_KARY(NCH)                                                                              \
+  case NCH:                                                                                         \
+    launch_step(env_step_dense_kary_kernel<TC, NCH, SERVER>, gk, SERVER, share, tb, io, st);        \
+    break
+      switch (ld / 128) {
+        COLO_KARY(1);
+        COLO_KARY(2);
+        COLO_KARY(3);
+        COLO_KARY(4);
+        COLO_KARY(5);
+        COLO_KARY(6);
+        COLO_KARY(7);
+        COLO_KARY(8);
+      }
+#undef COLO_KARY
+      return check_launch("env_step_dense_kary_kernel");
+    }
     const int grid = grid_for(kStepThreads / 32, (io.N + tile - 1) / tile);
 #define COLO_SHORT(NCH, U)                                                                                        \
   case NCH:                                                                                                       \
@@ -783,6 +915,22 @@ int colo_emit_observations(const float* table, const int* state, const int* h, c
   colo::emit_observations_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(table, state, h, step_type,
                                                                                                        N, H, S, D, out);
   return colo::check_launch("emit_observations_kernel");
+}
+
+int colo_build_cdf_index(const void* cdf, int S, int A, int ld, int is_f64, void* cdf_mid, void* cdf_coarse,
+                         void* stream) {
+  COLO_ARG_CHECK(cdf && cdf_mid && cdf_coarse && S > 0 && A > 0 && ld >= S && ld % 128 == 0 && ld <= 1024,
+                 "cdf, cdf_mid, cdf_coarse, ld % 128 == 0, ld <= 1024");
+  const long long rows = (long long)S * A;
+  const long long blocks = (rows * (ld / 4) + 255) / 256;
+  const int grid = (int)(blocks < 65535 ? blocks : 65535);
+  if (is_f64)
+    colo::build_cdf_index_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)cdf, rows, ld, (double*)cdf_mid,
+                                                                              (double*)cdf_coarse);
+  else
+    colo::build_cdf_index_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)cdf, rows, ld, (float*)cdf_mid,
+                                                                             (float*)cdf_coarse);
+  return colo::check_launch("build_cdf_index_kernel");
 }
 
 int colo_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64, void* stream) {

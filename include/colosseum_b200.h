@@ -389,6 +389,11 @@ typedef struct {
   const double* start_cum; /* [n_start] running sum of the start distribution (sampler order) */
   const int* start_idx;    /* [n_start] */
   int n_start;
+  /* optional two-level search index over rows of up to 1024 entries (ld % 128 == 0), built by colo_build_cdf_index:
+   * cdf_mid [S,A,ld/4] = the last entry of every quad of the row, cdf_coarse [S,A,ld/32] = the last entry of every
+   * 8th quad; same element type as cdf.  NULL: the step kernel samples those entries from the row itself. */
+  const void* cdf_mid;
+  const void* cdf_coarse;
 } colo_mdp_tables;
 
 /*
@@ -576,6 +581,10 @@ int colo_psrl_episodic_steps(const colo_mdp_tables* tb, const colo_psrl_args* a,
 /* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
  * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */
 int colo_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64, void* stream);
+/* The search index of colo_mdp_tables (cdf_mid [S,A,ld/4], cdf_coarse [S,A,ld/32]) from a dense cdf with ld % 128 == 0:
+ * plain copies of entries of the row, so searching through the index returns exactly what searching the row returns. */
+int colo_build_cdf_index(const void* cdf, int S, int A, int ld, int is_f64, void* cdf_mid, void* cdf_coarse,
+                         void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU ---------------------------- */
 /*
