@@ -751,7 +751,8 @@ def main():
             "metric": "batched env-steps/sec", "value": world * N / sec, "unit": "env-steps/s", "steps": args.steps,
             "ms_per_step": 1e3 * sec, "gpu_launches": launches,
             "config": {"workload": c2_workload(tb.S, tb.A, N),
-                       "kernel": "warp-cooperative search of the dense CDF row, supplied actions, in-kernel Philox uniforms",
+                       "kernel": "one thread per env: three-round k-ary search of the dense CDF row through its two-level index "
+                                 "(cdf_coarse / cdf_mid), supplied actions, in-kernel Philox uniforms",
                        "l2": l2_note},
             "flushed_per_step": {"value": world * N / sec_flushed, "unit": "env-steps/s", "ms_per_step": 1e3 * sec_flushed,
                                  "what": flushed_note + " (the event pair alone costs ~10 us on this GPU: a floor, not "
@@ -763,7 +764,7 @@ def main():
                             "stream sync, every step"},
             "roofline": {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("step", N),
-                         "peak_source": peak_src, "kernel": "env_step_dense_short_kernel<float,4,4>",
+                         "peak_source": peak_src, "kernel": "env_step_dense_kary_kernel<float,4>",
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "note": "T (1.8 MB) is L2/L1-resident by construction in C2: algorithmic bytes are served "
                                  "on chip, so frac can exceed 1; see DESIGN.md and `traffic`"},
