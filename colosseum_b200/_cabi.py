@@ -50,7 +50,7 @@ class MdpTables(C.Structure):
         ("rew_q", C.c_void_p), ("n_cls", C.c_int), ("nq", C.c_int),
         ("rmin", C.c_float), ("rmax", C.c_float),
         ("start_cum", C.c_void_p), ("start_idx", C.c_void_p), ("n_start", C.c_int),
-        ("cdf_mid", C.c_void_p), ("cdf_coarse", C.c_void_p),
+        ("cdf_mid", C.c_void_p), ("cdf_coarse", C.c_void_p), ("rew_cls_pad", C.c_void_p),
     ]
 
 

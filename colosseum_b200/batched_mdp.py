@@ -67,7 +67,8 @@ class DeviceTables:
                                                   _cabi.current_stream())
             _cabi.check(rc, "colo_build_dense_cdf")
             c.ld = ld
-            if ld % 128 == 0 and ld <= 1024:  # two-level search index of the short-row step kernel
+            short_rows = ld % 128 == 0 and ld <= 1024
+            if short_rows:  # two-level search index of the short-row step kernel
                 k["cdf_mid"] = torch.empty((tb.S, tb.A, ld // 4), dtype=k["cdf"].dtype, device=dev)
                 k["cdf_coarse"] = torch.empty((tb.S, tb.A, ld // 32), dtype=k["cdf"].dtype, device=dev)
                 rc = _cabi.lib().colo_build_cdf_index(_cabi.ptr(k["cdf"]), tb.S, tb.A, ld, int(f64),
@@ -76,8 +77,10 @@ class DeviceTables:
                 _cabi.check(rc, "colo_build_cdf_index")
             up("rew_cls_sas", tb.rew_cls_sas, np.uint8)
             up("rew_cls_sa", tb.rew_cls_sa, np.int32)
+            if short_rows and k["rew_cls_sas"] is not None:  # class rows padded to ld: one aligned read per block
+                k["rew_cls_pad"] = torch.nn.functional.pad(k["rew_cls_sas"], (0, ld - tb.S)).contiguous()
         for name in ("cdf", "succ_cum", "succ_idx", "succ_len", "rew_cls_sas", "rew_cls_sa", "rew_cls_succ", "rew_q",
-                     "start_cum", "start_idx", "cdf_mid", "cdf_coarse"):
+                     "start_cum", "start_idx", "cdf_mid", "cdf_coarse", "rew_cls_pad"):
             setattr(c, name, _cabi.ptr(k.get(name)))
         self.keep = k
         self.c = c

@@ -436,9 +436,12 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
 // of every 8th quad (4*NCH independent 4-byte loads, all issued before any is consumed), (2) the last entries of the 8
 // quads of the block that holds the crossing, (3) the crossing quad itself (the same 16-byte gather the warp-
 // cooperative kernel ends with).  With the two-level index of colo_mdp_tables (cdf_coarse / cdf_mid: copies of exactly
-// those entries, contiguous) round 1 is NCH 128-bit loads of a table small enough to live in L1 (60 KB at C2) and
-// round 2 one 32-byte sector: 3 sectors per env beyond L1 instead of the 2 KB row, and 3 dependent memory rounds per
-// env instead of 32/U per tile.  With 65,536 envs every warp is resident at once, so the step time IS the length of
+// those entries, contiguous) round 1 is NCH 128-bit loads of a 60 KB table and also yields the row total; round 2 is
+// one 32-byte sector of cdf_mid plus, in the same round, the 32-byte sector of reward classes of the block's candidate
+// next states (rew_cls_pad); round 3 the crossing quad.  Three dependent rounds per env after the env scalars, instead
+// of 32/U per tile plus two.  (Tried on one box each: reading the whole 128-byte block in round 2 and skipping round 3
+// -- 5.58 us per step instead of 5.17: four sectors cost more than one extra round; fetching the reward quantiles of
+// every class before the search -- 5.50 us instead of 5.26.)  With 65,536 envs every warp is resident at once, so the step time IS the length of
 // that dependency chain.  Same comparisons against the same x => the same index, bit for bit.
 template <typename TC, int NCH, bool SERVER>
 __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const colo_mdp_tables tb, const StepIO io) {
@@ -471,6 +474,8 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
       const TC* row = cdf + (size_t)(unsigned)(in.s * A + in.a) * (unsigned)ld;
       TC total, x;
       int blk = 0, G = 0;
+      bool have_cls = false;
+      uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
       nxt = ld;
       if (coarse) {  // two-level index: NCH 128-bit loads of a small hot table, then the 8 quad ends of one block
         const unsigned r = (unsigned)(in.s * A + in.a);
@@ -482,10 +487,18 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
 #pragma unroll
         for (int k = 0; k < NCH; ++k) blk += (cq[k].v[0] <= x) + (cq[k].v[1] <= x) + (cq[k].v[2] <= x) + (cq[k].v[3] <= x);
         if (blk < NB) {
+          // round 2: the 8 quad ends of the block (one 32-byte sector of cdf_mid) and, in the same round, the reward
+          // classes of the block's 32 candidate next states (rew_cls_pad: rew_cls_sas with rows padded to ld, so the
+          // slice is one aligned 32-byte sector): the class lookup no longer waits for the search to finish
           Quad<TC> m0, m1;
           const TC* mp = mid + (size_t)r * (32 * NCH) + 8 * blk;
           m0.load(mp);
           m1.load(mp + 4);
+          if (tb.rew_cls_pad) {
+            const uint4* cp = reinterpret_cast<const uint4*>(tb.rew_cls_pad + (size_t)r * ld + 32 * blk);
+            c0 = __ldg(cp);
+            c1 = __ldg(cp + 1);
+          }
           G = 8 * blk + (m0.v[0] <= x) + (m0.v[1] <= x) + (m0.v[2] <= x) + (m0.v[3] <= x) + (m1.v[0] <= x) +
               (m1.v[1] <= x) + (m1.v[2] <= x) + (m1.v[3] <= x);
         }
@@ -511,15 +524,25 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
         Quad<TC> qq;
         qq.load(row + 4 * G);  // the crossing quad: its last entry is > x, its first three decide
         nxt = 4 * G + (qq.v[0] <= x) + (qq.v[1] <= x) + (qq.v[2] <= x);
+        if (coarse && tb.rew_cls_pad && nxt < S) {
+          const int pos = nxt - 32 * blk;
+          const unsigned w = pos < 16 ? (pos < 8 ? (pos < 4 ? c0.x : c0.y) : (pos < 12 ? c0.z : c0.w))
+                                      : (pos < 24 ? (pos < 20 ? c1.x : c1.y) : (pos < 28 ? c1.z : c1.w));
+          cls = (int)((w >> (8 * (pos & 3))) & 0xffu);
+          have_cls = true;
+        }
       }
       if (nxt >= S) {  // x >= total (rounding): bisect's hi = n-1 clamp == first index where the row reaches total
         nxt = 0;
         while (nxt < S - 1 && __ldg(row + nxt) < total) ++nxt;
+        have_cls = false;
       }
-      if (tb.rew_cls_sas)
-        cls = tb.rew_cls_sas[((size_t)in.s * A + in.a) * S + nxt];
-      else if (tb.rew_cls_sa)
-        cls = tb.rew_cls_sa[(size_t)in.s * A + in.a];
+      if (!have_cls) {
+        if (tb.rew_cls_sas)
+          cls = tb.rew_cls_sas[((size_t)in.s * A + in.a) * S + nxt];
+        else if (tb.rew_cls_sa)
+          cls = tb.rew_cls_sa[(size_t)in.s * A + in.a];
+      }
     }
     finish_env(io, tb, valid ? e : 0, in, nxt, cls, stepping, resetting);
   }

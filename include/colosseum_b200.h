@@ -391,9 +391,12 @@ typedef struct {
   int n_start;
   /* optional two-level search index over rows of up to 1024 entries (ld % 128 == 0), built by colo_build_cdf_index:
    * cdf_mid [S,A,ld/4] = the last entry of every quad of the row, cdf_coarse [S,A,ld/32] = the last entry of every
-   * 8th quad; same element type as cdf.  NULL: the step kernel samples those entries from the row itself. */
+   * 8th quad; same element type as cdf.  NULL: the step kernel samples those entries from the row itself.
+   * rew_cls_pad u8 [S,A,ld] (optional, used with the index): rew_cls_sas with its rows padded to ld, so that the
+   * classes of a 32-entry block's candidate next states are one aligned 32-byte read issued with the cdf_mid read. */
   const void* cdf_mid;
   const void* cdf_coarse;
+  const unsigned char* rew_cls_pad;
 } colo_mdp_tables;
 
 /*
