@@ -180,7 +180,7 @@ struct Quad<double> {
 // per-env prologue shared by all step kernels: resolves uniforms/actions, handles the reset path.
 // returns true when the env takes a regular step.
 struct EnvIn {
-  int s, a, st;
+  int s, a, st, h;
   double un64;
   float un32, ur;
 };
@@ -191,6 +191,7 @@ __device__ __forceinline__ EnvIn load_env(const StepIO& io, const colo_mdp_table
   EnvIn in;
   in.st = io.step_type[e];
   in.s = io.state[e];
+  in.h = io.h[e];  // needed only by the epilogue: issued here so that its (cold) latency overlaps the search
   Philox4 w;
   const bool need_rng = io.u_next == nullptr || io.u_rew == nullptr || io.random_actions;
   if (need_rng) w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, t);
@@ -223,7 +224,7 @@ __device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tabl
     io.reward[e] = __int_as_float(0x7fc00000);
     io.obs[e] = nxt;
   } else if (stepping) {
-    const int hh = io.h[e] + 1;
+    const int hh = in.h + 1;
     io.h[e] = hh;
     io.state[e] = nxt;
     io.reward[e] = reward_draw(tb, cls, in.ur);
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
     const long long e = tile * 32 + lane;
     const bool valid = e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
     const long long e = tile * TILE + lane;
     const bool valid = lane < TILE && e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
   for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same thread for every step of the launch
     const bool valid = e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_
   for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same thread for every step of the launch
     const bool valid = e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<false>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
