@@ -696,13 +696,12 @@ __global__ void __launch_bounds__(256) episodic_batched_kernel(const float* __re
 template <typename TV, int L>
 static int episodic_batched_launch(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
                                    TV* Q, TV* V, bool vec4, size_t smem, cudaStream_t st, bool shared_mdp) {
-  // resident CTAs are capped so that the T of the MDPs in flight stays in L2 between layers
-  const size_t t_bytes = (size_t)S * A * S * sizeof(float);
-  long long cap = (long long)(96ull << 20) / (long long)(t_bytes ? t_bytes : 1);
-  const long long lo = sm_count(), hi = (long long)sm_count() * 8;
-  cap = cap < lo ? lo : (cap > hi ? hi : cap);
-  if (shared_mdp) cap = hi;  // one T for everybody: it stays in L2 whatever the number of CTAs
+  // up to 8 CTAs per SM in flight.  (Measured on 1,024 Taxi models: capping the CTAs in flight so that their T stays
+  // L2-resident between layers -- 24/48/64/96/160 MB -- costs 2.71/2.37/1.99/1.60/1.44 ms against 1.31 ms uncapped:
+  // parallelism beats residency.)
+  const long long cap = (long long)sm_count() * 8;
   const int grid = (int)(B < cap ? B : cap);
+  (void)shared_mdp;
   const long long ts = shared_mdp ? 0 : (long long)S * A * S, rs = shared_mdp ? 0 : (long long)S * A;
   if (vec4) {
     auto k = episodic_batched_kernel<TV, L, true>;
