@@ -223,3 +223,19 @@ def test_batched_regret_of_all_loops_matches_per_loop_indicator():
     # and through run(): every loop logged
     logs = loop.run(200, log_every=100, regret_for="all")
     assert logs[-1]["regret"].shape == (N,) and (logs[-1]["cumulative_regret"] >= logs[0]["cumulative_regret"]).all()
+
+
+def test_loops_sharded_over_ranks_equal_the_unsharded_batch():
+    """env_offset: loops [32, 64) run as their own batch (another GPU's shard) walk exactly the trajectories they walk
+    inside the batch of 64 -- Q-learning and PSRL (whose posterior samples are keyed by the global row index)."""
+    import colosseum_b200.agent_loop as al
+
+    tb = MDPTables.from_golden(load_instance("frozenlake4_epi"))
+    for make in (lambda n, off: al.QLearningEpisodic(9, tb, 10 ** 4, p=0.05, c_1=0.4, n_loops=n, env_offset=off),
+                 lambda n, off: al.PSRLEpisodic(9, tb, 10 ** 4, n_loops=n, env_offset=off)):
+        whole, lo, hi = make(64, 0), make(32, 0), make(32, 32)
+        n = 5 * tb.H
+        tw = whole.steps(n, trace=True).cpu().numpy()
+        tl, th = lo.steps(n, trace=True).cpu().numpy(), hi.steps(n, trace=True).cpu().numpy()
+        assert np.array_equal(tw[:, :32], tl) and np.array_equal(tw[:, 32:], th)
+        assert np.array_equal(whole.cumulative_reward.cpu().numpy()[32:], hi.cumulative_reward.cpu().numpy())
