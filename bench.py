@@ -523,6 +523,7 @@ def cpu_step_rate(tb, n_envs, seconds):
     """the reference algorithm for the step (oracle port, C + OpenMP, all host threads), bounded sample"""
     from oracle import oracle as orc
 
+    orc.set_threads()
     cdf = orc.build_dense_cdf(tb.T, ld=tb.ld, f64=False)
     ht = orc.HostTables(tb.S, tb.A, H=tb.H, cdf=cdf, rew_cls_sas=tb.rew_cls_sas, rew_q=tb.rew_q, rmin=tb.rmin,
                         rmax=tb.rmax, start_cum=tb.start_cum, start_idx=tb.start_idx)
@@ -548,6 +549,7 @@ def cpu_vi_rate(B, S, A, seconds):
 
     from oracle import oracle as orc
 
+    orc.set_threads()
     rs = np.random.RandomState(0)
     T = rs.dirichlet(np.ones(S) * 0.05, size=(B, S, A)).astype(np.float32)
     R = rs.uniform(0, 1, size=(B, S, A)).astype(np.float32)
@@ -570,9 +572,10 @@ def run_reference_arm(args):
     if rank != 0:
         return
     tb = load_c2_tables()
-    cores = os.cpu_count()
     N = C2_ENVS_PER_GPU
     from oracle import oracle as orc
+
+    cores = orc.set_threads()  # every host core, also under torchrun (which exports OMP_NUM_THREADS=1)
 
     cdf = orc.build_dense_cdf(tb.T, ld=tb.ld, f64=False)
     ht = orc.HostTables(tb.S, tb.A, H=tb.H, cdf=cdf, rew_cls_sas=tb.rew_cls_sas, rew_q=tb.rew_q, rmin=tb.rmin,

@@ -190,6 +190,20 @@ def gaps_f64(Q, V, mask=None, reg=0.1):
     return float(lib().orc_gaps_f64(_p(Q), _p(V), _p(m), C.c_longlong(NS), A, C.c_double(reg)))
 
 
+def set_threads(n=None):
+    """OpenMP threads of the oracle's parallel loops (torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    silently turn the all-core CPU baseline into a single-thread one).  Returns the count in effect."""
+    n = int(n or os.cpu_count() or 1)
+    lib()  # make sure the OpenMP runtime the oracle links against is loaded
+    for name in ("libgomp.so.1", "libgomp.so"):
+        try:
+            C.CDLL(name).omp_set_num_threads(n)
+            return n
+        except OSError:
+            continue
+    return int(os.environ.get("OMP_NUM_THREADS", "1"))
+
+
 # ---------------------------------------------------------------------------------------------- step
 def philox(seed, env, t):
     out = (C.c_uint32 * 4)()
