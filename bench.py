@@ -609,11 +609,35 @@ def run_reference_arm(args):
         "vi": {"metric": "value-iteration MDP-sweeps/sec", "value": vi_rate, "unit": "MDP-sweeps/s",
                "sample": f"{vi_n} in-place fp32 sweeps x 64 MDPs (S=512,A=4) in {vi_dt:.1f}s, {cores} threads"},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ main
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep a private copy of fd 1 for it and point fd 1 at stderr, so that
+    whatever a library prints on stdout (NCCL's version banner under NCCL_DEBUG=VERSION/WARN, ...) lands on stderr"""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -684,7 +708,7 @@ def main():
                                          "slowest_instance": c3["worst"][1], "slowest_hardness_s": c3["worst"][0]}},
             "env_steps_per_s_step_phase": c3["per_rank"] * args.c3_envs * args.c3_steps / max(c3["step_s"], 1e-9) * world,
         })
-        print(json.dumps(line))
+        emit(line)
         if world > 1:
             import torch.distributed as dist
 
@@ -826,7 +850,7 @@ def main():
                                          "of _discounted_value_iteration's sweep)"}
     if agents is not None:
         line["agents"] = agents
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         import torch.distributed as dist
 
