@@ -14,6 +14,7 @@ body execute per launch.  Classes keep the reference's names and constructor arg
 Boltzmann exploration and callable epsilon schedules are not offered on the device.
 """
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -363,6 +364,7 @@ class BatchedMDPLoop:
         else:
             Qall = ag.Q
         out = torch.empty(ag.n_loops, dtype=torch.float64, device="cuda")
+        avg = torch.empty_like(out)
         gen = torch.Generator(device="cuda").manual_seed(dp.ARGMAX_SEED)
         lib = _cabi.lib()
         for lo in range(0, ag.n_loops, chunk):
@@ -378,7 +380,32 @@ class BatchedMDPLoop:
             _cabi.check(rc, "colo_episodic_policies_f32")
             reg = (v_star[None, :] - Vp[:, 0].double()).clamp_min(0.0)
             out[lo:lo + n] = (reg * start[None, :]).sum(-1) / H
+            avg[lo:lo + n] = (Vp[:, 0].double() * start[None, :]).sum(-1) / H
+        self._agent_average_reward = avg.cpu().numpy()  # agent_mdp_interaction.py:514-518
         return out.cpu().numpy()
+
+    def episodic_baselines(self):
+        """per-step average rewards of the optimal, worst and uniformly random policies of an episodic MDP
+        (mdp/base_finite.py:211-253: start-distribution average of V[0] divided by H; the worst policy is the optimal one
+        of -R, mdp/base.py:649-664) -- the normalisers of MDPLoop's indicators"""
+        import torch
+
+        from . import dynamic_programming as dp
+
+        if not hasattr(self, "_baselines"):
+            tb = self.agents.tables
+            H, S, A = tb.H, tb.S, tb.A
+            Td, Rd = dp.to_device(self.T), dp.to_device(self.R)
+            prob = np.diff(np.concatenate([[0.0], np.asarray(tb.start_cum, np.float64)]))
+            start = np.zeros(S)
+            np.add.at(start, np.asarray(tb.start_idx), prob / prob.sum())
+            v_opt = dp.episodic_value_iteration(H, Td, Rd, precision="f64")[1][0].cpu().numpy()
+            v_worst = -dp.episodic_value_iteration(H, Td, -Rd, precision="f64")[1][0].cpu().numpy()
+            uni = torch.full((H, S, A), 1.0 / A, dtype=torch.float32, device="cuda")
+            v_rand = dp.episodic_policy_evaluation(H, Td, Rd, uni, precision="f64")[1][0].cpu().numpy()
+            self._baselines = {k: float((v * start).sum()) / H for k, v in
+                               (("optimal", v_opt), ("worst", v_worst), ("random", v_rand))}
+        return self._baselines
 
     def run(self, T: int, log_every: int = -1, regret_for=None):
         """T interaction steps for every loop, `log_every` steps per launch.  Returns the list of log records
@@ -393,6 +420,9 @@ class BatchedMDPLoop:
             regret_for = list(range(ag.n_loops))
         regret_for = [] if (regret_for is None or self.T is None) else list(regret_for)
         cum_regret = np.zeros(len(regret_for))
+        cum_expected = np.zeros(len(regret_for))
+        base = self.episodic_baselines() if (all_loops or (regret_for and ag.episodic)) else None
+        t_start = time.perf_counter()
         done = 0
         while done < T:
             n = min(log_every, T - done)
@@ -404,5 +434,17 @@ class BatchedMDPLoop:
                 reg = self._expected_regret_all() if all_loops else self._expected_regret(regret_for)
                 cum_regret = cum_regret + reg * n  # agent_mdp_interaction.py:503-506
                 rec["regret"], rec["cumulative_regret"] = reg, cum_regret.copy()
+                if base is not None:  # the normalised indicators of MDPLoop._update_performance_logs (:395-428)
+                    span = base["optimal"] - base["worst"]
+                    rec["normalized_cumulative_regret"] = cum_regret / span
+                    rec["normalized_cumulative_reward"] = (rec["cumulative_reward"] - done * base["worst"]) / span
+                    for k in ("optimal", "worst", "random"):
+                        rec[f"{k}_cumulative_expected_reward"] = base[k] * done
+                    rec["random_cumulative_regret"] = (base["optimal"] - base["random"]) * done
+                    rec["worst_cumulative_regret"] = span * done
+                    if all_loops:
+                        cum_expected = cum_expected + self._agent_average_reward * n
+                        rec["cumulative_expected_reward"] = cum_expected.copy()
+            rec["steps_per_second"] = done * ag.n_loops / (time.perf_counter() - t_start)
             self.logs.append(rec)
         return self.logs

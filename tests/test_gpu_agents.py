@@ -223,6 +223,24 @@ def test_batched_regret_of_all_loops_matches_per_loop_indicator():
     # and through run(): every loop logged
     logs = loop.run(200, log_every=100, regret_for="all")
     assert logs[-1]["regret"].shape == (N,) and (logs[-1]["cumulative_regret"] >= logs[0]["cumulative_regret"]).all()
+    # MDPLoop's normalised indicators: baselines from the oracle, identities between the log fields
+    Vo = orc.episodic_f64(tb.H, T, R)[1][0]
+    Vw = -orc.episodic_f64(tb.H, T, -R)[1][0]
+    Vr = orc.episodic_f64(tb.H, T, R, pi=np.full((tb.H, tb.S, tb.A), 1.0 / tb.A))[1][0]
+    p0 = np.zeros(tb.S)
+    pr = np.diff(np.concatenate([[0.0], tb.start_cum]))
+    np.add.at(p0, tb.start_idx, pr / pr.sum())
+    base = loop.episodic_baselines()
+    for k, v in (("optimal", Vo), ("worst", Vw), ("random", Vr)):
+        assert abs(base[k] - (v * p0).sum() / tb.H) < 1e-9, k
+    last = logs[-1]
+    span = base["optimal"] - base["worst"]
+    np.testing.assert_allclose(last["normalized_cumulative_regret"], last["cumulative_regret"] / span)
+    assert abs(last["optimal_cumulative_expected_reward"] - base["optimal"] * last["steps"]) < 1e-9
+    # expected reward of the agent + its regret = the optimal expected reward, tick by tick
+    np.testing.assert_allclose(last["cumulative_expected_reward"] + last["cumulative_regret"],
+                               last["optimal_cumulative_expected_reward"], rtol=1e-4)
+    assert last["steps_per_second"] > 0
 
 
 def test_loops_sharded_over_ranks_equal_the_unsharded_batch():
