@@ -498,3 +498,35 @@ def test_emission_noise_distributions(bm):
     env.set_emission_noise(None)
     with pytest.raises(NotImplementedError):
         env.set_emission_noise("GaussianCorrelated")
+
+
+@pytest.mark.parametrize("mode", ["dense_f32", "dense_f64"])
+def test_step_without_search_index_is_identical(bm, mode):
+    """colo_mdp_tables.cdf_mid / cdf_coarse / rew_cls_pad are optional: with NULL pointers the k-ary kernel samples the
+    same entries from the row itself -- bit-identical to the indexed default.  (Running this whole file with
+    COLO_STEP_KERNEL=coop exercises the warp-cooperative kernel against the same oracles.)"""
+    import torch
+
+    tb = MDPTables.from_golden(load_instance("c2_deepsea30_prand"))
+    N = 5000
+    gen = torch.Generator().manual_seed(5)
+    acts = [torch.randint(0, tb.A, (N,), dtype=torch.int32, generator=gen).cuda() for _ in range(25)]
+
+    def run(strip_index):
+        env = bm.BatchedMDP(tb, N, mode=mode, seed=8)
+        if strip_index:
+            env.dev.c.cdf_mid = None
+            env.dev.c.cdf_coarse = None
+            env.dev.c.rew_cls_pad = None
+        env.reset()
+        out = []
+        for a in acts:
+            env.step_async(a, auto_reset=True)
+            out.append((env.obs.clone(), env.reward.clone(), env.step_type.clone()))
+        return out, env.visits_sa.clone()
+
+    ref, vref = run(False)
+    got, vgot = run(True)
+    for (o1, r1, s1), (o2, r2, s2) in zip(ref, got):
+        assert torch.equal(o1, o2) and torch.equal(s1, s2) and torch.equal(r1.view(torch.int32), r2.view(torch.int32))
+    assert torch.equal(vref, vgot)
