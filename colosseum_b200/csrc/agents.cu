@@ -110,28 +110,46 @@ __global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tab
     const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, t);
     const size_t row = ((size_t)(EPISODIC ? h : 0) * S + s) * A;
     const int a = select_action(Q + row, A, p.epsilon_greedy, wa);
+    const size_t idx = row + a;
+    // every table entry the update needs is requested as soon as its address is known, and consumed only after the
+    // sampler's own (dependent) table walk: the loop body is a chain of cold gathers, the fewer in series the better
+    const int n0 = cnt[idx];
+    const float q_old = Q[idx];
+    float mu0 = 0.f, sg0 = 0.f, be0 = 0.f;
+    if (EPISODIC && p.ucb_type != 0) {
+      mu0 = mu[idx];
+      sg0 = sg[idx];
+      be0 = be[idx];
+    }
     const Step st = env_succ(tb, s, a, u53(we.w[0], we.w[1]));
-    const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
     const int hh = h + 1;
     const bool last = EPISODIC && hh >= H;
     const int obs = last ? -1 : st.nxt;
     const int sp = obs < 0 ? S - 1 : obs;  // numpy's negative index: the terminal observation -1 reads state S-1
-    const size_t idx = row + a;
-    const int n = cnt[idx] + 1;
+    const float v_sp = V[EPISODIC ? (size_t)hh * S + sp : (size_t)sp];
+    constexpr int kRowRegs = 8;
+    float qsp[kRowRegs];
+    const size_t rp = (size_t)sp * A;
+    if (!EPISODIC && A <= kRowRegs) {
+#pragma unroll
+      for (int k = 0; k < kRowRegs; ++k) qsp[k] = k < A ? Q[rp + k] : -INFINITY;
+    }
+    const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
+    const int n = n0 + 1;
     cnt[idx] = n;
     const double alpha = fmax(p.min_at, __ddiv_rn(__dadd_rn(Hd, 1.0), __dadd_rn(Hd, (double)n)));
     const double om = __dsub_rn(1.0, alpha);
     if (EPISODIC) {
-      const float vnext = V[(size_t)hh * S + sp];
+      const float vnext = v_sp;
       double b;
       if (p.ucb_type == 0) {
         b = __dmul_rn(p.c_1, __dsqrt_rn(__ddiv_rn(__dmul_rn(H3, p.log_term), (double)n)));
       } else {
-        const float m = __fadd_rn(mu[idx], vnext);
-        const float g = __fadd_rn(sg[idx], __fmul_rn(vnext, vnext));
+        const float m = __fadd_rn(mu0, vnext);
+        const float g = __fadd_rn(sg0, __fmul_rn(vnext, vnext));
         mu[idx] = m;
         sg[idx] = g;
-        const float old_beta = be[idx];
+        const float old_beta = be0;
         const float d = __fsub_rn(g, m);
         const float hd2 = __fmul_rn((float)H, __fmul_rn(d, d));
         const int n2 = (int)((unsigned)n * (unsigned)n);  // np.int32 ** 2 wraps
@@ -147,20 +165,27 @@ __global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tab
       // python float + np.float32 is a float32 sum (NEP 50); the np.float64 bonus then promotes
       const double target = __dadd_rn((double)__fadd_rn(r, vnext), b);
       // sic: the reference weighs the OLD estimate with alpha_t (q_learning.py:100-102)
-      Q[idx] = (float)__dadd_rn(__dmul_rn(alpha, (double)Q[idx]), __dmul_rn(om, target));
+      Q[idx] = (float)__dadd_rn(__dmul_rn(alpha, (double)q_old), __dmul_rn(om, target));
       float mx = Q[row];
       for (int k = 1; k < A; ++k) mx = fmaxf(mx, Q[row + k]);
       V[(size_t)h * S + s] = fminf((float)H, mx);
     } else {
       const double b = __dmul_rn(__dmul_rn(4.0, p.span_approx),
                                  __dsqrt_rn(__dmul_rn(__ddiv_rn(Hd, (double)n), p.log_term)));
-      const double target = __dadd_rn(__dadd_rn((double)r, __dmul_rn(p.gamma, (double)V[sp])), b);
-      const float qm = (float)__dadd_rn(__dmul_rn(om, (double)Q[idx]), __dmul_rn(alpha, target));
+      const double target = __dadd_rn(__dadd_rn((double)r, __dmul_rn(p.gamma, (double)v_sp)), b);
+      const float qm = (float)__dadd_rn(__dmul_rn(om, (double)q_old), __dmul_rn(alpha, target));
       Qm[idx] = qm;
-      Q[idx] = fminf(Q[idx], qm);
-      const size_t rp = (size_t)sp * A;
-      float mx = Q[rp];
-      for (int k = 1; k < A; ++k) mx = fmaxf(mx, Q[rp + k]);
+      const float q_new = fminf(q_old, qm);
+      Q[idx] = q_new;
+      float mx;
+      if (A <= kRowRegs) {  // the row of the next state was fetched before the update: patch it if it is this row
+        mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kRowRegs; ++k) mx = fmaxf(mx, (sp == s && k == a) ? q_new : qsp[k]);
+      } else {
+        mx = Q[rp];
+        for (int k = 1; k < A; ++k) mx = fmaxf(mx, Q[rp + k]);
+      }
       V[sp] = mx;
     }
     cum = __dadd_rn(cum, (double)r);
