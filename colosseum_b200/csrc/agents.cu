@@ -228,12 +228,15 @@ __global__ void __launch_bounds__(128) psrl_steps_kernel(const colo_mdp_tables t
     const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, t);
     const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, t);
     const int a = select_action(Q + ((size_t)h * S + s) * A, A, p.epsilon_greedy, wa);
+    float* hp = nig + ((size_t)s * A + a) * 4;
+    const float4 hp0 = *reinterpret_cast<const float4*>(hp);  // requested before the sampler's dependent table walk
     const Step st = env_succ(tb, s, a, u53(we.w[0], we.w[1]));
-    const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
     const int hh = h + 1;
     const bool last = hh >= H;
-    float* hp = nig + ((size_t)s * A + a) * 4;
-    const float mu0 = hp[0], l0 = hp[1], a0 = hp[2], b0 = hp[3];
+    float* dc = dir + ((size_t)s * A + a) * S + st.nxt;
+    const float d0 = last ? 0.f : *dc;
+    const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
+    const float mu0 = hp0.x, l0 = hp0.y, a0 = hp0.z, b0 = hp0.w;
     const double y = (double)r;
     const float l1 = __fadd_rn(l0, 1.0f);
     const double mu1 = __ddiv_rn(__dadd_rn((double)__fmul_rn(l0, mu0), y), (double)l1);
@@ -243,10 +246,7 @@ __global__ void __launch_bounds__(128) psrl_steps_kernel(const colo_mdp_tables t
     hp[1] = l1;
     hp[2] = __fadd_rn(a0, 0.5f);
     hp[3] = (float)__dadd_rn((double)b0, __dmul_rn(0.5, __dadd_rn(0.0, disc)));
-    if (!last) {
-      float* c = dir + ((size_t)s * A + a) * S + st.nxt;
-      *c = __fadd_rn(*c, 1.0f);
-    }
+    if (!last) *dc = __fadd_rn(d0, 1.0f);
     cum = __dadd_rn(cum, (double)r);
     if (p.trace) {
       int* tr = p.trace + ((size_t)step * p.N + i) * 4;
@@ -318,6 +318,7 @@ int colo_psrl_episodic_steps(const colo_mdp_tables* tb, const colo_psrl_args* a,
   if (a->N == 0) return COLO_OK;
   COLO_ARG_CHECK(a->state && a->h && a->Q && a->dir_hyper && a->nig_hyper && a->cum_reward,
                  "state, h, Q, dir_hyper, nig_hyper, cum_reward");
+  COLO_ARG_CHECK((uintptr_t)a->nig_hyper % 16 == 0, "nig_hyper must be 16-byte aligned (rows are read as one float4)");
   const int grid = (int)((a->N + 127) / 128);
   colo::psrl_steps_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*tb, *a, n_steps, t0);
   return colo::check_launch("psrl_steps_kernel");
