@@ -699,18 +699,24 @@ static int episodic_batched_launch(const float* T, const float* R, const float* 
   // up to 8 CTAs per SM in flight.  (Measured on 1,024 Taxi models: capping the CTAs in flight so that their T stays
   // L2-resident between layers -- 24/48/64/96/160 MB -- costs 2.71/2.37/1.99/1.60/1.44 ms against 1.31 ms uncapped:
   // parallelism beats residency.)
-  const long long cap = (long long)sm_count() * 8;
+  // CTA size from the lanes one layer can use (rows x L).  Measured, us per solve of the whole batch at 64/128/256
+  // threads: 8,192 C1 models (40 lanes) 26/32/54, 8,192 DeepSea-8 models (288 lanes) 128/137/186, 1,024 Taxi models
+  // (5,184 lanes) 2366/1391/1287.
+  static const int forced = getenv("COLO_EPI_THREADS") ? atoi(getenv("COLO_EPI_THREADS")) : 0;
+  const long long lanes = (long long)S * A * L;
+  const int threads = forced ? forced : (lanes <= 512 ? 64 : (lanes <= 2048 ? 128 : 256));
+  const long long cap = (long long)sm_count() * (2048 / threads);
   const int grid = (int)(B < cap ? B : cap);
   (void)shared_mdp;
   const long long ts = shared_mdp ? 0 : (long long)S * A * S, rs = shared_mdp ? 0 : (long long)S * A;
   if (vec4) {
     auto k = episodic_batched_kernel<TV, L, true>;
     COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
+    k<<<grid, threads, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
   } else {
     auto k = episodic_batched_kernel<TV, L, false>;
     COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
+    k<<<grid, threads, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
   }
   return check_launch("episodic_batched_kernel");
 }
