@@ -484,8 +484,9 @@ class BatchedMDP:
 class PipelinedBatchedMDP:
     """N parallel envs split into `groups` contiguous shards, each a host_io BatchedMDP on its own stream, stepped in
     a software pipeline: while the host agent reads group g's TimeStep and writes its next actions, the other
-    groups' step kernels are doing their PCIe reads/writes.  Env i of group g is global env g*N/groups + i
-    (`env_offset`), so the trajectories are those of the unsplit batch.
+    groups' step kernels are doing their PCIe reads/writes.  Env i of group g is global env offsets[g] + i
+    (`env_offset`), so the trajectories are those of the unsplit batch; N need not be a multiple of `groups`
+    (`sizes`, `offsets`).
 
         env = PipelinedBatchedMDP(tables, 65536, groups=2); env.reset()
         for g in range(env.groups): env.send(g, actions[g])         # prime
@@ -502,13 +503,16 @@ class PipelinedBatchedMDP:
 
         self._serving = False
 
-        assert groups >= 1 and n_envs % groups == 0, "n_envs must be a multiple of groups"
+        assert 1 <= groups <= n_envs
         self.groups = int(groups)
         self.n_envs = int(n_envs)
-        self.per_group = n_envs // groups
+        base, extra = divmod(self.n_envs, self.groups)  # the first `extra` groups hold one env more
+        self.sizes = [base + (1 if g < extra else 0) for g in range(self.groups)]
+        self.offsets = [sum(self.sizes[:g]) for g in range(self.groups)]
+        self.per_group = self.sizes[0]
         dev = DeviceTables(tables, mode)
-        self.shards = [BatchedMDP(tables, self.per_group, mode=mode, seed=seed, track_visits=track_visits,
-                                  env_offset=env_offset + g * self.per_group, host_io=True,
+        self.shards = [BatchedMDP(tables, self.sizes[g], mode=mode, seed=seed, track_visits=track_visits,
+                                  env_offset=env_offset + self.offsets[g], host_io=True,
                                   stream=torch.cuda.Stream(), device_tables=dev)
                        for g in range(groups)]
         torch.cuda.synchronize()  # the buffers were initialised on the default stream

@@ -52,6 +52,10 @@ struct StepIO {
 };
 
 constexpr unsigned long long kSrvExit = ~0ULL, kSrvLapsed = ~0ULL - 1;
+#ifndef COLO_SRV_POLL_NS
+#define COLO_SRV_POLL_NS 400
+#endif
+constexpr unsigned kSrvPollNs = COLO_SRV_POLL_NS;  // back-off of the CTAs waiting for the relayed doorbell
 
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -99,7 +103,7 @@ __device__ __forceinline__ bool server_wait(const StepIO& io, unsigned long long
       for (;;) {
         v = ld_acquire_gpu_u64(io.srv_go);
         if (v == want || v == kSrvExit) break;
-        __nanosleep(40);
+        __nanosleep(kSrvPollNs);
       }
     }
     s_cmd = v;

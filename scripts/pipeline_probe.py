@@ -8,11 +8,11 @@ import bench
 
 tb = bench.load_c2_tables()
 N = 65536
-for groups in (1, 2, 4, 8):
+for groups in (1, 2, 3, 4, 5, 6):
     env = PipelinedBatchedMDP(tb, N, groups=groups)
     env.reset()
     rng = np.random.default_rng(0)
-    acts = [[torch.from_numpy(rng.integers(0, tb.A, N // groups).astype(np.int32)).pin_memory() for _ in range(groups)]
+    acts = [[torch.from_numpy(rng.integers(0, tb.A, env.sizes[g]).astype(np.int32)).pin_memory() for g in range(groups)]
             for _ in range(4)]
     for it in range(20):
         env.step_all(acts[it % 4])

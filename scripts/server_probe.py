@@ -34,7 +34,7 @@ def wall(f, n):
     for i in range(n): f()
     return (time.perf_counter() - t0) / n * 1e6
 
-for N in (32, 4096, 65536, 262144):
+for N in (32, 65536):
     buf = torch.from_numpy(rng.integers(0, tb.A, N).astype(np.int32)).pin_memory()
     env = BatchedMDP(tb, N, host_io=True); env.reset()
     t_launch = wall(lambda: env.step_host(buf, auto_reset=True), 500)
@@ -44,9 +44,9 @@ for N in (32, 4096, 65536, 262144):
     print(f"N={N:6d} step_host {t_launch:6.2f} us   served {t_srv:6.2f} us  ({N / t_srv / 1e3:.3f} G env-steps/s)", flush=True)
 
 N = 65536
-for groups in (2, 4):
+for groups in (2, 3, 4):
     env = PipelinedBatchedMDP(tb, N, groups=groups); env.reset()
-    bufs = [torch.from_numpy(rng.integers(0, tb.A, N // groups).astype(np.int32)).pin_memory() for _ in range(groups)]
+    bufs = [torch.from_numpy(rng.integers(0, tb.A, env.sizes[g]).astype(np.int32)).pin_memory() for g in range(groups)]
     env.serve(bufs)
     for g in range(groups): env.send(g)
     K = 500

@@ -410,6 +410,16 @@ def test_pipelined_groups_equal_the_unsplit_batch(bm):
     import torch
 
     tb = MDPTables.from_golden(load_instance("c2_deepsea30_prand"))
+    # uneven split: N need not be a multiple of the number of groups
+    odd = bm.PipelinedBatchedMDP(tb, 1001, groups=3, seed=3)
+    assert odd.sizes == [334, 334, 333] and odd.offsets == [0, 334, 668]
+    whole = bm.BatchedMDP(tb, 1001, seed=3, host_io=True)
+    odd.reset(), whole.reset()
+    a_odd = torch.randint(0, tb.A, (1001,), dtype=torch.int32).pin_memory()
+    want_o = [x.clone() for x in whole.step_host(a_odd, auto_reset=True)]
+    got_o = odd.step_all([a_odd[o:o + n].clone().pin_memory() for o, n in zip(odd.offsets, odd.sizes)])
+    for j in range(3):
+        assert np.array_equal(torch.cat([p[j] for p in got_o]).numpy(), want_o[j].numpy(), equal_nan=True)
     N, G = 4096, 2
     gen = torch.Generator().manual_seed(1)
     acts = [torch.randint(0, tb.A, (N,), dtype=torch.int32, generator=gen).pin_memory() for _ in range(12)]
