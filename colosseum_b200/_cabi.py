@@ -161,6 +161,9 @@ PROTOTYPES = {
     "colo_env_step_dense_f64": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
     "colo_env_step_succ": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, _P, _ULL, _I, _P]),
     "colo_env_random_steps": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _I, _ULL, _I, _P]),
+    "colo_env_stepper_create": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, C.POINTER(C.c_void_p)]),
+    "colo_env_stepper_launch": (_I, [_P, _P, _ULL]),
+    "colo_env_stepper_destroy": (None, [_P]),
     "colo_env_server_start": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), C.POINTER(EnvServer), _I, _ULL, _ULL, _P]),
     "colo_env_server_post": (_ULL, [C.POINTER(EnvServer)]),
     "colo_env_server_wait": (_I, [C.POINTER(EnvServer), _ULL, C.c_uint]),

@@ -155,6 +155,7 @@ class BatchedMDP:
         self._sync = lib.colo_stream_synchronize
         self.stream = stream
         self._stream_ptr = None if stream is None else int(stream.cuda_stream)
+        self._stepper = None
 
     # -- reference attribute surface (base.py:463-503, 1233-1252)
     @property
@@ -251,14 +252,26 @@ class BatchedMDP:
         return self.recv_host()
 
     def send_host(self, action):
-        """host_io lean path, first half: launch one auto-resetting step reading `action` (pinned int32) in place."""
-        stream = self._stream_ptr if self._stream_ptr is not None else _cabi.current_stream()
-        self._batch.action = action.data_ptr()
-        rc = self._step_fn[0](self._tb_ref, self._batch_ref, 0, None, None, self.t, 1, stream)
+        """host_io lean path, first half: launch one auto-resetting step reading `action` (pinned int32) in place.
+        Goes through a prepared stepper (colo_env_stepper_*): three scalar arguments per call instead of two structs
+        and six scalars."""
+        st = self._stepper
+        if st is None:
+            st = self._make_stepper()
+        rc = self._stepper_launch(st, action.data_ptr(), self.t)
         if rc != 0:
-            _cabi.check(rc, "colo_env_step")
+            _cabi.check(rc, "colo_env_stepper_launch")
         self.t += 1
+
+    def _make_stepper(self):
+        stream = self._stream_ptr if self._stream_ptr is not None else _cabi.current_stream()
+        out = C.c_void_p()
+        rc = _cabi.lib().colo_env_stepper_create(self._tb_ref, self._batch_ref, _MODES[self.mode], stream, C.byref(out))
+        _cabi.check(rc, "colo_env_stepper_create")
+        self._stepper = out.value
         self._pending = stream
+        self._stepper_launch = _cabi.lib().colo_env_stepper_launch
+        return self._stepper
 
     def recv_host(self):
         """second half: wait for the step launched by `send_host`; returns the pinned host views."""
@@ -340,6 +353,9 @@ class BatchedMDP:
     def __del__(self):
         try:
             self.stop_serving()
+            if getattr(self, "_stepper", None):
+                _cabi.lib().colo_env_stepper_destroy(self._stepper)
+                self._stepper = None
         except Exception:
             pass
 

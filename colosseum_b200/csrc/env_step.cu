@@ -861,6 +861,43 @@ int colo_env_random_steps(const colo_mdp_tables* tb, const colo_env_batch* batch
   return colo::launch_succ<false>(tb, io, stream);
 }
 
+struct colo_env_stepper {
+  colo_mdp_tables tb;
+  colo::StepIO io;
+  int mode;
+  void* stream;
+};
+
+int colo_env_stepper_create(const colo_mdp_tables* tb, const colo_env_batch* batch, int mode, void* stream,
+                            colo_env_stepper** out) {
+  int r = colo::check_tables_common(tb);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(out && mode >= 0 && mode <= 2, "out, mode in {0,1,2}");
+  colo_env_stepper* h = (colo_env_stepper*)malloc(sizeof(colo_env_stepper));
+  COLO_ARG_CHECK(h != nullptr, "out of host memory");
+  h->tb = *tb;
+  r = make_io(tb, batch, 0, nullptr, nullptr, 0, 1, &h->io);
+  if (r != COLO_OK) {
+    free(h);
+    return r;
+  }
+  h->mode = mode;
+  h->stream = stream;
+  *out = h;
+  return COLO_OK;
+}
+
+int colo_env_stepper_launch(colo_env_stepper* h, const int* action, unsigned long long t) {
+  if (h->io.N == 0) return COLO_OK;
+  h->io.action = const_cast<int*>(action);
+  h->io.t = t;
+  if (h->mode == 0) return colo::launch_dense<float, false>(&h->tb, h->io, h->stream);
+  if (h->mode == 1) return colo::launch_dense<double, false>(&h->tb, h->io, h->stream);
+  return colo::launch_succ<false>(&h->tb, h->io, h->stream);
+}
+
+void colo_env_stepper_destroy(colo_env_stepper* h) { free(h); }
+
 int colo_env_server_start(const colo_mdp_tables* tb, const colo_env_batch* batch, const colo_env_server* srv, int mode,
                           unsigned long long t, unsigned long long served, void* stream) {
   int r = colo::check_tables_common(tb);
