@@ -497,6 +497,15 @@ class BatchedMDP:
             self._visits_sa.zero_()
 
 
+def split_sizes(n: int, groups: int):
+    """sizes and offsets of `groups` contiguous shards of n items, the first n % groups shards one item larger"""
+    assert 1 <= groups <= n
+    base, extra = divmod(int(n), int(groups))
+    sizes = [base + (1 if g < extra else 0) for g in range(groups)]
+    offsets = [sum(sizes[:g]) for g in range(groups)]
+    return sizes, offsets
+
+
 class PipelinedBatchedMDP:
     """N parallel envs split into `groups` contiguous shards, each a host_io BatchedMDP on its own stream, stepped in
     a software pipeline: while the host agent reads group g's TimeStep and writes its next actions, the other
@@ -519,12 +528,9 @@ class PipelinedBatchedMDP:
 
         self._serving = False
 
-        assert 1 <= groups <= n_envs
         self.groups = int(groups)
         self.n_envs = int(n_envs)
-        base, extra = divmod(self.n_envs, self.groups)  # the first `extra` groups hold one env more
-        self.sizes = [base + (1 if g < extra else 0) for g in range(self.groups)]
-        self.offsets = [sum(self.sizes[:g]) for g in range(self.groups)]
+        self.sizes, self.offsets = split_sizes(self.n_envs, self.groups)
         self.per_group = self.sizes[0]
         dev = DeviceTables(tables, mode)
         self.shards = [BatchedMDP(tables, self.sizes[g], mode=mode, seed=seed, track_visits=track_visits,

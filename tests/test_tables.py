@@ -127,3 +127,14 @@ def test_patched_reference_fails_loudly_without_gpu():
         patch.uninstall()
     mdp = RiverSwimContinuous(seed=0, size=6)
     assert mdp.optimal_value_functions[1].shape == (6,)  # restored: the reference's numba path again
+
+
+def test_split_sizes_cover_the_batch_contiguously():
+    """the shards of PipelinedBatchedMDP: contiguous, covering, sizes differing by at most one"""
+    from colosseum_b200.batched_mdp import split_sizes
+
+    for n, g in ((65536, 2), (65536, 3), (1001, 3), (7, 7), (5, 1)):
+        sizes, offsets = split_sizes(n, g)
+        assert sum(sizes) == n and len(sizes) == g and max(sizes) - min(sizes) <= 1
+        assert offsets[0] == 0 and all(offsets[i + 1] == offsets[i] + sizes[i] for i in range(g - 1))
+    assert split_sizes(1001, 3) == ([334, 334, 333], [0, 334, 668])
