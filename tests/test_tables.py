@@ -138,3 +138,24 @@ def test_split_sizes_cover_the_batch_contiguously():
         assert sum(sizes) == n and len(sizes) == g and max(sizes) - min(sizes) <= 1
         assert offsets[0] == 0 and all(offsets[i + 1] == offsets[i] + sizes[i] for i in range(g - 1))
     assert split_sizes(1001, 3) == ([334, 334, 333], [0, 334, 668])
+
+
+def test_batched_apis_fail_loudly_without_gpu():
+    """no CPU fallback anywhere: the batched env, the pipelined groups and the agent loops raise on a box without a
+    CUDA device instead of computing on the host"""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    from conftest import load_instance
+    from colosseum_b200._cabi import ColosseumB200Error
+    from colosseum_b200.tables import MDPTables
+    import colosseum_b200.agent_loop as al
+    import colosseum_b200.batched_mdp as bm
+
+    tb = MDPTables.from_golden(load_instance("c1_riverswim_epi"))
+    for make in (lambda: bm.BatchedMDP(tb, 8), lambda: bm.PipelinedBatchedMDP(tb, 8, groups=2),
+                 lambda: al.QLearningEpisodic(0, tb, 100, p=0.05, c_1=0.5, n_loops=4),
+                 lambda: al.PSRLEpisodic(0, tb, 100, n_loops=4)):
+        with pytest.raises(ColosseumB200Error):
+            make()
