@@ -109,7 +109,7 @@ class PsrlArgs(C.Structure):
         ("N", C.c_longlong), ("seed", C.c_ulonglong), ("env0", C.c_ulonglong),
         ("state", C.c_void_p), ("h", C.c_void_p), ("Q", C.c_void_p), ("dir_hyper", C.c_void_p),
         ("nig_hyper", C.c_void_p), ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p),
-        ("n_episodes", C.c_void_p), ("trace", C.c_void_p),
+        ("n_episodes", C.c_void_p), ("trace", C.c_void_p), ("reward_model", C.c_int),
     ]
 
 
@@ -172,6 +172,7 @@ PROTOTYPES = {
     "colo_qlearning_continuous_steps": (_I, [C.POINTER(MdpTables), C.POINTER(QLearningArgs), _I, _ULL, _P]),
     "colo_psrl_episodic_steps": (_I, [C.POINTER(MdpTables), C.POINTER(PsrlArgs), _I, _ULL, _P]),
     "colo_sample_nig_rewards": (_I, [_P, _LL, _LL, _ULL, _ULL, _P, _P]),
+    "colo_sample_nn_rewards": (_I, [_P, _LL, _LL, _ULL, _ULL, _P, _P]),
     "colo_emit_noise": (_I, [_P, _P, _P, _LL, _I, _I, _I, _I, _D, _ULL, _ULL, _ULL, _P]),
     "colo_emit_observations": (_I, [_P, _P, _P, _P, _LL, _I, _I, _I, _P, _P]),
     "colo_build_dense_cdf": (_I, [_P, _I, _I, _I, _P, _I, _P]),

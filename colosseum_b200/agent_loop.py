@@ -176,8 +176,11 @@ class PSRLEpisodic:
         assert sampler in ("fast", "f64")
         self._dirichlet = (_cabi.lib().colo_sample_dirichlet_rows_fast if sampler == "fast"
                            else _cabi.lib().colo_sample_dirichlet_rows)
-        assert reward_prior_model in (None, "N_NIG") and transitions_prior_model in (None, "M_DIR"), \
-            "the batched PSRL offers the N_NIG / M_DIR conjugate models"
+        rname = getattr(reward_prior_model, "name", reward_prior_model)   # the reference's IntEnum or its name
+        tname = getattr(transitions_prior_model, "name", transitions_prior_model)
+        assert rname in (None, "N_NIG", "N_N") and tname in (None, "M_DIR"), \
+            "the batched PSRL offers the N_NIG / N_N reward models and the M_DIR transition model"
+        self.reward_model = 1 if rname == "N_N" else 0
         if boltzmann_temperature is not None:
             raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
         if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
@@ -190,9 +193,13 @@ class PSRLEpisodic:
         S, A, H = tables.S, tables.A, tables.H
         rp = [tables.rmax, 1, 1, 1] if rewards_prior_prms is None else rewards_prior_prms       # bayesian_model.py:46-48
         tp = [1.0 / S] if transitions_prior_prms is None else transitions_prior_prms              # :49-51
-        hp = np.tile(rp, (S, A, 1)).astype(np.float32)                                            # base_conjugate.py:44-47
-        mu, n_mu, tau, n_tau = (hp[..., k].copy() for k in range(4))
-        hp[..., 2], hp[..., 3] = n_tau * 0.5, (0.5 * n_tau) / tau                                # conjugate_rewards.py:45-54
+        if self.reward_model == 1:  # N_N: (mu, tau) in the first two of the four slots (conjugate_rewards.py:95-110)
+            hp = np.zeros((S, A, 4), np.float32)
+            hp[..., :2] = np.tile(rp, (S, A, 1)).astype(np.float32)
+        else:
+            hp = np.tile(rp, (S, A, 1)).astype(np.float32)                                        # base_conjugate.py:44-47
+            mu, n_mu, tau, n_tau = (hp[..., k].copy() for k in range(4))
+            hp[..., 2], hp[..., 3] = n_tau * 0.5, (0.5 * n_tau) / tau                            # conjugate_rewards.py:45-54
         self.nig_hyper = torch.from_numpy(np.tile(hp, (N, 1, 1, 1))).cuda()
         self.dir_hyper = torch.full((N, S, A, S), float(np.float32(tp[0])), dtype=torch.float32, device="cuda")
         self.T_sample = torch.empty((N, S, A, S), dtype=torch.float32, device="cuda")
@@ -211,6 +218,7 @@ class PSRLEpisodic:
         a.dir_hyper, a.nig_hyper = self.dir_hyper.data_ptr(), self.nig_hyper.data_ptr()
         a.cum_reward, a.n_episodes = self.cumulative_reward.data_ptr(), self.n_episodes.data_ptr()
         a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        a.reward_model = self.reward_model
         self._args = a
         _QLearningBatch.reset_envs(self)
         self.episode_end_update()  # before_start_interacting (:146-147)
@@ -224,9 +232,9 @@ class PSRLEpisodic:
         rc = self._dirichlet(self.dir_hyper.data_ptr(), rows, S, row0, self.seed, self.n_samples,
                              self.T_sample.data_ptr(), st)
         _cabi.check(rc, "colo_sample_dirichlet_rows")
-        rc = lib.colo_sample_nig_rewards(self.nig_hyper.data_ptr(), rows, row0, self.seed, self.n_samples,
-                                         self.R_sample.data_ptr(), st)
-        _cabi.check(rc, "colo_sample_nig_rewards")
+        sample_r = lib.colo_sample_nn_rewards if self.reward_model == 1 else lib.colo_sample_nig_rewards
+        rc = sample_r(self.nig_hyper.data_ptr(), rows, row0, self.seed, self.n_samples, self.R_sample.data_ptr(), st)
+        _cabi.check(rc, "colo_sample_rewards")
         self.n_samples += 1
         return self.T_sample, self.R_sample
 

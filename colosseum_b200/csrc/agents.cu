@@ -237,15 +237,22 @@ __global__ void __launch_bounds__(128) psrl_steps_kernel(const colo_mdp_tables t
     const float d0 = last ? 0.f : *dc;
     const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
     const float mu0 = hp0.x, l0 = hp0.y, a0 = hp0.z, b0 = hp0.w;
-    const double y = (double)r;
-    const float l1 = __fadd_rn(l0, 1.0f);
-    const double mu1 = __ddiv_rn(__dadd_rn((double)__fmul_rn(l0, mu0), y), (double)l1);
-    const double dy = __dsub_rn(y, (double)mu0);
-    const double disc = __ddiv_rn(__dmul_rn((double)l0, __dmul_rn(dy, dy)), (double)l1);
-    hp[0] = (float)mu1;
-    hp[1] = l1;
-    hp[2] = __fadd_rn(a0, 0.5f);
-    hp[3] = (float)__dadd_rn((double)b0, __dmul_rn(0.5, __dadd_rn(0.0, disc)));
+    if (p.reward_model == 1) {
+      // N_N.update_sa: mu1 = (mu0*tau0 + r*1) / tau1, every operand float32 or a weak python scalar -> float32 ops
+      const float t1 = __fadd_rn(l0, 1.0f);
+      hp[0] = __fdiv_rn(__fadd_rn(__fmul_rn(mu0, l0), r), t1);
+      hp[1] = t1;
+    } else {
+      const double y = (double)r;
+      const float l1 = __fadd_rn(l0, 1.0f);
+      const double mu1 = __ddiv_rn(__dadd_rn((double)__fmul_rn(l0, mu0), y), (double)l1);
+      const double dy = __dsub_rn(y, (double)mu0);
+      const double disc = __ddiv_rn(__dmul_rn((double)l0, __dmul_rn(dy, dy)), (double)l1);
+      hp[0] = (float)mu1;
+      hp[1] = l1;
+      hp[2] = __fadd_rn(a0, 0.5f);
+      hp[3] = (float)__dadd_rn((double)b0, __dmul_rn(0.5, __dadd_rn(0.0, disc)));
+    }
     if (!last) *dc = __fadd_rn(d0, 1.0f);
     cum = __dadd_rn(cum, (double)r);
     if (p.trace) {

@@ -142,7 +142,30 @@ __global__ void __launch_bounds__(256) emit_noise_kernel(float* __restrict__ out
   }
 }
 
+// N_N.sample (conjugate_rewards.py:119-127): Normal(mu, scale = tau) -> float32, rows laid out as (mu, tau, -, -)
+__global__ void __launch_bounds__(256) nn_rows_kernel(const float* __restrict__ hyper, long long rows, long long row0,
+                                                      unsigned long long seed, unsigned long long t,
+                                                      float* __restrict__ R) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const float4 h = __ldg(reinterpret_cast<const float4*>(hyper) + r);
+    const Philox4 w = philox4x32_10(seed ^ 0x8CB92BA72F3D8DD7ULL, (uint64_t)(row0 + r), t);
+    const double u1 = u53(w.w[0], w.w[1]) + 1.1102230246251565e-16, u2 = (double)w.w[2] * (1.0 / 4294967296.0);
+    const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    R[r] = (float)((double)h.x + (double)h.y * z);
+  }
+}
+
 }  // namespace colo
+
+extern "C" int colo_sample_nn_rewards(const float* hyper, long long rows, long long row0, unsigned long long seed,
+                                      unsigned long long t, float* R_out, void* stream) {
+  COLO_ARG_CHECK(hyper && R_out && rows >= 0 && row0 >= 0 && (uintptr_t)hyper % 16 == 0, "hyper (16-byte aligned), R_out, rows");
+  if (rows == 0) return COLO_OK;
+  const long long blocks = (rows + 255) / 256;
+  const long long cap = (long long)colo::sm_count() * 8;
+  colo::nn_rows_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(hyper, rows, row0, seed, t, R_out);
+  return colo::check_launch("nn_rows_kernel");
+}
 
 extern "C" int colo_emit_noise(float* out, const unsigned char* step_type, const int* h, long long N, int H, int D,
                                int period, int kind, double param, unsigned long long seed, unsigned long long t,

@@ -292,6 +292,10 @@ int colo_extended_vi_f64acc(const float* T, const float* est_rewards, const doub
  */
 int colo_sample_nig_rewards(const float* hyper, long long rows, long long row0, unsigned long long seed,
                             unsigned long long t, float* R_out, void* stream);
+/* N_N.sample (conjugate_rewards.py:119-127) on the same [rows,4] layout: R_out[r] ~ Normal(mu, scale = tau) (sic: the
+ * reference passes its precision-like second parameter as the scale) -> float32. */
+int colo_sample_nn_rewards(const float* hyper, long long rows, long long row0, unsigned long long seed,
+                           unsigned long long t, float* R_out, void* stream);
 int colo_sample_dirichlet_rows(const float* hyper, long long rows, int S, long long row0, unsigned long long seed,
                                unsigned long long t, float* T_out, void* stream);
 /* The same sample with single-precision arithmetic (SFU log / pow / cos, normal truncated at 5.8 sigma): another
@@ -590,6 +594,7 @@ typedef struct {
   double* cum_reward;
   long long* n_episodes;
   int* trace;
+  int reward_model; /* 0 = N_NIG (mu, lambda, alpha, beta); 1 = N_N (mu, tau, -, -): N_N.update_sa, conjugate_rewards.py:112-117 */
 } colo_psrl_args;
 int colo_psrl_episodic_steps(const colo_mdp_tables* tb, const colo_psrl_args* a, int n_steps, unsigned long long t0,
                              void* stream);

@@ -918,6 +918,7 @@ typedef struct {
   double* cum_reward;
   long long* n_episodes;
   int* trace;
+  int reward_model; /* 0 N_NIG, 1 N_N (conjugate_rewards.py:112-117) */
 } orc_psrl_args;
 
 int orc_psrl_steps(const orc_tables* tb, const orc_psrl_args* p, int n_steps, uint64_t t0) {
@@ -949,16 +950,23 @@ int orc_psrl_steps(const orc_tables* tb, const orc_psrl_args* p, int n_steps, ui
       const int last = hh >= H;
       float* hp = nig + ((size_t)s * A + a) * 4;
       const float mu0 = hp[0], l0 = hp[1], a0 = hp[2], b0 = hp[3];
-      const double y = (double)r; /* np.mean([r]) */
-      const float l1 = l0 + 1.0f;
-      const float lm = l0 * mu0;
-      const double mu1 = ((double)lm + y) / (double)l1;
-      const double dy = y - (double)mu0;
-      const double disc = (double)l0 * (dy * dy) / (double)l1;
-      hp[0] = (float)mu1;
-      hp[1] = l1;
-      hp[2] = a0 + 0.5f;
-      hp[3] = (float)((double)b0 + 0.5 * (0.0 + disc));
+      if (p->reward_model == 1) { /* N_N.update_sa: float32 operands and weak python scalars -> float32 arithmetic */
+        const float t1 = l0 + 1.0f;
+        const float num = mu0 * l0 + r;
+        hp[0] = num / t1;
+        hp[1] = t1;
+      } else {
+        const double y = (double)r; /* np.mean([r]) */
+        const float l1 = l0 + 1.0f;
+        const float lm = l0 * mu0;
+        const double mu1 = ((double)lm + y) / (double)l1;
+        const double dy = y - (double)mu0;
+        const double disc = (double)l0 * (dy * dy) / (double)l1;
+        hp[0] = (float)mu1;
+        hp[1] = l1;
+        hp[2] = a0 + 0.5f;
+        hp[3] = (float)((double)b0 + 0.5 * (0.0 + disc));
+      }
       if (!last) dir[((size_t)s * A + a) * S + nxt] += 1.0f;
       cum += (double)r;
       if (p->trace) {

@@ -445,7 +445,7 @@ class _PsrlArgs(C.Structure):
         ("N", C.c_longlong), ("seed", C.c_uint64), ("env0", C.c_uint64),
         ("state", C.c_void_p), ("h", C.c_void_p), ("Q", C.c_void_p), ("dir_hyper", C.c_void_p),
         ("nig_hyper", C.c_void_p), ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p),
-        ("n_episodes", C.c_void_p), ("trace", C.c_void_p),
+        ("n_episodes", C.c_void_p), ("trace", C.c_void_p), ("reward_model", C.c_int),
     ]
 
 
@@ -456,8 +456,9 @@ class PSRLLoops:
     (bayesian_models/conjugate_rewards.py:45-54)."""
 
     def __init__(self, tb, n_loops, seed=0, env0=0, epsilon_greedy=None, rewards_prior_prms=None,
-                 transitions_prior_prms=None):
+                 transitions_prior_prms=None, reward_prior_model="N_NIG"):
         self.tb, self.N, self.seed, self.env0 = tb, int(n_loops), int(seed), int(env0)
+        self.reward_model = {"N_NIG": 0, "N_N": 1}[reward_prior_model]
         S, A, H = tb.c.S, tb.c.A, tb.c.H
         N = self.N
         self.state, self.h, _, _ = env_reset(tb, N, seed=seed, t=0, env0=env0)
@@ -466,9 +467,13 @@ class PSRLLoops:
         self.n_episodes = np.zeros(N, np.int64)
         rp = [tb.c.rmax, 1, 1, 1] if rewards_prior_prms is None else rewards_prior_prms
         tp = [1.0 / S] if transitions_prior_prms is None else transitions_prior_prms
-        hp = np.tile(rp, (S, A, 1)).astype(np.float32)
-        mu, n_mu, tau, n_tau = hp[..., 0].copy(), hp[..., 1].copy(), hp[..., 2].copy(), hp[..., 3].copy()
-        hp[..., 0], hp[..., 1], hp[..., 2], hp[..., 3] = mu, n_mu, n_tau * 0.5, (0.5 * n_tau) / tau
+        if self.reward_model == 1:  # N_N: (mu, tau), stored in the first two of the four slots
+            hp = np.zeros((S, A, 4), np.float32)
+            hp[..., :2] = np.tile(rp, (S, A, 1)).astype(np.float32)
+        else:
+            hp = np.tile(rp, (S, A, 1)).astype(np.float32)
+            mu, n_mu, tau, n_tau = hp[..., 0].copy(), hp[..., 1].copy(), hp[..., 2].copy(), hp[..., 3].copy()
+            hp[..., 0], hp[..., 1], hp[..., 2], hp[..., 3] = mu, n_mu, n_tau * 0.5, (0.5 * n_tau) / tau
         self.nig_hyper = np.tile(hp, (N, 1, 1, 1)).astype(np.float32)
         self.dir_hyper = np.tile(np.float32(tp[0]), (N, S, A, S)).astype(np.float32)
         self.Q = np.zeros((N, H + 1, S, A), np.float32)
@@ -478,6 +483,7 @@ class PSRLLoops:
         a.state, a.h, a.Q = _p(self.state), _p(self.h), _p(self.Q)
         a.dir_hyper, a.nig_hyper = _p(self.dir_hyper), _p(self.nig_hyper)
         a.cum_reward, a.n_episodes = _p(self.cum_reward), _p(self.n_episodes)
+        a.reward_model = self.reward_model
         self.args = a
 
     def set_q(self, Q):

@@ -20,9 +20,14 @@ from colosseum_b200.tables import MDPTables  # noqa: E402
 from make_qlearning_golden import host_tables  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
-CASES = [("c1_riverswim_epi", dict(epsilon_greedy=0.3)),
-         ("frozenlake4_epi", dict(epsilon_greedy=0.3, rewards_prior_prms=[0.5, 2, 1.5, 3], transitions_prior_prms=[0.25])),
-         ("taxi_epi", dict(epsilon_greedy=0.5))]
+CASES = [("c1_riverswim_epi", "c1_riverswim_epi", dict(epsilon_greedy=0.3)),
+         ("frozenlake4_epi", "frozenlake4_epi", dict(epsilon_greedy=0.3, rewards_prior_prms=[0.5, 2, 1.5, 3],
+                                                      transitions_prior_prms=[0.25])),
+         ("taxi_epi", "taxi_epi", dict(epsilon_greedy=0.5)),
+         ("frozenlake4_nn", "frozenlake4_epi", dict(epsilon_greedy=0.3, reward_prior_model="N_N",
+                                                     rewards_prior_prms=[0.3, 2.0])),
+         ("c1_riverswim_nn", "c1_riverswim_epi", dict(epsilon_greedy=0.4, reward_prior_model="N_N",
+                                                      rewards_prior_prms=[1.0, 1.0]))]
 N_LOOPS, N_EPISODES, SEED = 3, 40, 5
 
 
@@ -39,7 +44,7 @@ def main():
     from colosseum.agent.mdp_models.bayesian_models import RewardsConjugateModel, TransitionsConjugateModel
 
     out = {}
-    for inst, kw in CASES:
+    for name, inst, kw in CASES:
         g = load_instance(inst)
         tb = MDPTables.from_golden(g)
         loops = orc.PSRLLoops(host_tables(tb), N_LOOPS, seed=SEED, **kw)
@@ -50,8 +55,9 @@ def main():
                                      time_horizon=tb.H)
         nig, dirs = [], []
         for i in range(N_LOOPS):
+            rmodel = RewardsConjugateModel.N_N if kw.get("reward_prior_model") == "N_N" else RewardsConjugateModel.N_NIG
             m = BayesianMDPModel(SEED, spec,
-                                 reward_prior_model=RewardsConjugateModel.N_NIG if "rewards_prior_prms" in kw else None,
+                                 reward_prior_model=rmodel if "rewards_prior_prms" in kw else None,
                                  transitions_prior_model=TransitionsConjugateModel.M_DIR if "transitions_prior_prms" in kw else None,
                                  rewards_prior_prms=kw.get("rewards_prior_prms"),
                                  transitions_prior_prms=kw.get("transitions_prior_prms"))
@@ -63,12 +69,14 @@ def main():
                               types.SimpleNamespace(observation=obs, reward=r, last=lambda last=last: last), 0)
             nig.append(np.asarray(m._rewards_model.hyper_params))
             dirs.append(np.asarray(m._transitions_model.hyper_params))
-        out[f"{inst}.trace"] = trace
-        out[f"{inst}.ref_nig"] = np.stack(nig)
-        out[f"{inst}.ref_dir"] = np.stack(dirs)
-        for name, ours, ref in (("nig", loops.nig_hyper, out[f"{inst}.ref_nig"]), ("dir", loops.dir_hyper, out[f"{inst}.ref_dir"])):
+        out[f"{name}.trace"] = trace
+        out[f"{name}.ref_nig"] = np.stack(nig)  # [N,S,A,4] for N_NIG, [N,S,A,2] for N_N
+        out[f"{name}.ref_dir"] = np.stack(dirs)
+        k = out[f"{name}.ref_nig"].shape[-1]
+        for what, ours, ref in (("rew", loops.nig_hyper[..., :k], out[f"{name}.ref_nig"]),
+                                ("dir", loops.dir_hyper, out[f"{name}.ref_dir"])):
             err = np.abs(ours.astype(np.float64) - ref).max() / max(1.0, np.abs(ref).max())
-            print(f"{inst:20s} {name}: max rel err vs reference {err:.2e} exact={np.array_equal(ours, ref.astype(ours.dtype))} dtype {ref.dtype}")
+            print(f"{name:20s} {what}: max rel err vs reference {err:.2e} exact={np.array_equal(ours, ref.astype(ours.dtype))} dtype {ref.dtype}")
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "psrl.npz"), **out)
     print("wrote tests/golden/psrl.npz")
 

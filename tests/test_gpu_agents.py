@@ -100,7 +100,7 @@ def test_psrl_steps_equal_oracle_and_reference_posteriors():
     from make_psrl_golden import CASES as PCASES, N_EPISODES, N_LOOPS as PN, SEED as PSEED, optimal_q
 
     gold = np.load(os.path.join(GOLDEN, "psrl.npz"))
-    for inst, kw in PCASES:
+    for name, inst, kw in PCASES:
         g = load_instance(inst)
         tb = MDPTables.from_golden(g)
         # (1) golden: act on the true optimal Q, no resampling -> the reference's posteriors
@@ -108,9 +108,10 @@ def test_psrl_steps_equal_oracle_and_reference_posteriors():
         dev.episode_end_update = lambda: None
         dev.Q.copy_(torch.from_numpy(optimal_q(g, tb)).cuda()[None].expand_as(dev.Q))
         tr = dev.steps(N_EPISODES * tb.H, trace=True).cpu().numpy()
-        assert np.array_equal(tr, gold[f"{inst}.trace"]), inst
-        assert np.array_equal(dev.nig_hyper.cpu().numpy(), gold[f"{inst}.ref_nig"]), inst
-        assert np.array_equal(dev.dir_hyper.cpu().numpy(), gold[f"{inst}.ref_dir"]), inst
+        assert np.array_equal(tr, gold[f"{name}.trace"]), name
+        k = gold[f"{name}.ref_nig"].shape[-1]  # 4 parameters for N_NIG, 2 for N_N
+        assert np.array_equal(dev.nig_hyper.cpu().numpy()[..., :k], gold[f"{name}.ref_nig"]), name
+        assert np.array_equal(dev.dir_hyper.cpu().numpy(), gold[f"{name}.ref_dir"]), name
         # (2) the real agent (resampling every episode): the oracle follows with the GPU's sampled-model Q
         N = 200
         dev = al.PSRLEpisodic(3, tb, 10 ** 5, n_loops=N, **kw)
@@ -120,7 +121,7 @@ def test_psrl_steps_equal_oracle_and_reference_posteriors():
             cpu.set_q(dev.Q.cpu().numpy())
             td = dev.steps(tb.H, trace=True).cpu().numpy()
             tc = cpu.steps(tb.H, trace=True)
-            assert np.array_equal(td, tc), (inst, ep)
+            assert np.array_equal(td, tc), (name, ep)
         assert np.array_equal(dev.nig_hyper.cpu().numpy(), cpu.nig_hyper)
         assert np.array_equal(dev.dir_hyper.cpu().numpy(), cpu.dir_hyper)
         assert np.array_equal(dev.cumulative_reward.cpu().numpy(), cpu.cum_reward)
