@@ -28,7 +28,10 @@ sys.path.insert(0, ROOT)
 
 C2_INSTANCE = "c2_deepsea30_prand"
 C2_ENVS_PER_GPU = 65536
-STEP_BYTES = lambda S: 4 * S + 28  # dense CDF row + 28 B of state I/O per env-step
+STEP_BYTES = lambda S: 4 * S + 28  # dense CDF row + 28 B of state I/O per env-step (nominal)
+# what one env-step MUST move to and from HBM once the 2.9 MB of tables are on chip: read state 4 + h 4 + step_type 1 +
+# action 4, write state 4 + h 4 + obs 4 + reward 4 + discount 4 + step_type 1
+STEP_IO_BYTES = 34
 
 
 def c2_workload(S, A, N):
@@ -157,8 +160,56 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
+def _rotating_graph(torch, tb, N, rank, actions, n_steps_min, seed0, min_ms, world, track_visits=True):
+    """`value` protocol: inputs larger than L2 instead of a flush.  NB independent env batches of N envs (each with its
+    own tables; together > 1.5 x the 126 MB L2) are stepped in rotation from ONE CUDA graph of max(n_steps_min, NB)
+    launches; the graph is replayed until the timed region is at least `min_ms`.  Returns ms per step (device time,
+    CUDA events on the launching stream, max over ranks), the number of timed steps and the region length."""
+    from colosseum_b200.batched_mdp import BatchedMDP
+
+    per_batch = 38 * N + 4 * tb.S * tb.A * (tb.ld + tb.ld // 4 + tb.ld // 32) + 2 * tb.S * tb.A * tb.ld
+    NB = int(1.5 * (126 << 20) / per_batch) + 1
+    batches = [BatchedMDP(tb, N, mode="dense_f32", seed=seed0 + i, env_offset=rank * N, track_visits=track_visits)
+               for i in range(NB)]
+    n_act = len(actions)
+    for b in batches:
+        b.reset()
+        b.step_async(actions[0], auto_reset=True)
+    torch.cuda.synchronize()
+    for i in range(max(3, min(NB, 8))):  # untimed warm-up steps, same rotation
+        batches[i % NB].step_async(actions[i % n_act], auto_reset=True)
+    torch.cuda.synchronize()
+    per_graph = max(n_steps_min, NB)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):  # step i runs on env batch i % NB
+        for i in range(per_graph):
+            batches[i % NB].step_async(actions[i % n_act], auto_reset=True)
+    graph.replay()
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    graph.replay()
+    g1.record()
+    g1.synchronize()
+    reps = max(1, int(np.ceil(min_ms / max(g0.elapsed_time(g1), 1e-3))))
+    barrier_sync(world)
+    g0.record()
+    for _ in range(reps):
+        graph.replay()
+    g1.record()
+    barrier_sync(world)
+    ms = max_over_ranks(g0.elapsed_time(g1), world)
+    assert all(int(b.status.item()) == 0 for b in batches)
+    out = dict(ms_per_step=ms / (reps * per_graph), timed_steps=reps * per_graph, region_ms=ms, batches=NB,
+               bytes_touched=NB * per_batch, steps_per_graph=per_graph, replays=reps)
+    del graph, batches
+    torch.cuda.empty_cache()
+    return out
+
+
 def bench_step_gpu(args, rank, world):
-    """kernel-resident number (`value`) and end-to-end number (`e2e`) for the batched step"""
+    """kernel-resident number (`value`), the env-count sweep that names the step kernel's bound, and the end-to-end
+    number (`e2e`) for the batched step"""
     import torch
 
     from colosseum_b200 import _cabi
@@ -219,44 +270,64 @@ def bench_step_gpu(args, rank, world):
         del envd
     except Exception as e:
         det = dict(error=f"{type(e).__name__}: {e}")
+    del flush
 
-    # ---- secondary: back-to-back kernel throughput.  The per-step event pair above has a floor of ~10 us on B200
-    # (measured with a 32-env launch), i.e. most of the 14 us is launch + event latency, not the kernel.  Here the steps
-    # of NB independent env batches (each with its own tables; together larger than L2, so no flush is needed) are
-    # captured in one CUDA graph and replayed: kernels run back to back, no CPU in the loop.
+    # ---- headline: back-to-back kernel throughput.  The per-step event pair above has a floor of ~10 us on B200
+    # (measured with a 32-env launch), i.e. most of it is launch + event latency, not the kernel.  Here the steps of
+    # NB independent env batches (each with its own tables; together larger than L2, so no flush is needed) are
+    # captured in one CUDA graph and replayed until the timed region is >= 50 ms: no CPU in the loop.
     b2b = None
     try:
-        per_batch = 22 * N + 4 * tb.S * tb.A * tb.ld + tb.S * tb.A * tb.S
-        NB = int(1.5 * (126 << 20) / per_batch) + 1
-        batches = [BatchedMDP(tb, N, mode="dense_f32", seed=99 + i, env_offset=rank * N) for i in range(NB)]
-        for b in batches:
-            b.reset()
-            b.step_async(actions[0], auto_reset=True)
-        torch.cuda.synchronize()
-        for i in range(max(3, args.warmup)):  # untimed warm-up steps, same rotation
-            batches[i % NB].step_async(actions[i % n_act], auto_reset=True)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):  # EXACTLY args.steps steps: step i runs on env batch i % NB
-            for i in range(args.steps):
-                batches[i % NB].step_async(actions[i % n_act], auto_reset=True)
-        graph.replay()
-        barrier_sync(world)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        graph.replay()
-        g1.record()
-        barrier_sync(world)
-        assert all(int(b.status.item()) == 0 for b in batches)
-        b2b = dict(ms=max_over_ranks(g0.elapsed_time(g1), world), steps=args.steps, batches=NB,
-                   bytes_touched=NB * per_batch)
-        del graph, batches
-    except Exception as e:  # reported, never fatal: the headline above does not depend on it
+        b2b = _rotating_graph(torch, tb, N, rank, actions, args.steps, 99, 50.0, world)
+    except Exception as e:  # reported, never fatal: the flushed number above does not depend on it
         b2b = dict(error=f"{type(e).__name__}: {e}")
+
+    # ---- env-count sweep: what bounds the step kernel.  Same kernel, same protocol (rotating batches > L2, >= 20 ms
+    # regions), N from the headline's 65,536 (0.38 of a wave: one dependency chain) up to 16 Mi envs, where the
+    # env-state stream (STEP_IO_BYTES per env-step to and from HBM) is the compulsory traffic.
+    sweep = []
+    if world == 1 and not args.no_sweep:
+        for n_env in (65536, 262144, 1 << 20, 1 << 22, 1 << 24):
+            try:
+                acts = [torch.randint(0, tb.A, (n_env,), dtype=torch.int32, device="cuda", generator=gen)
+                        for _ in range(2)]
+                r = _rotating_graph(torch, tb, n_env, rank, acts, 4, 500, 20.0, world)
+                sweep.append(dict(n_envs=n_env, ms_per_step=r["ms_per_step"], batches=r["batches"],
+                                  timed_steps=r["timed_steps"], region_ms=r["region_ms"]))
+                del acts
+            except Exception as e:
+                sweep.append(dict(n_envs=n_env, error=f"{type(e).__name__}: {e}"))
+
+    # ---- (c) the on-device-agent case: K random-agent steps of every env fused in ONE launch
+    # (BaseMDP.random_steps, base.py:1319-1339; bit-identical to K launches)
+    fused = None
+    try:
+        K = 1000
+        envf = BatchedMDP(tb, N, mode="dense_f32", seed=4321, env_offset=rank * N)
+        envf.reset()
+        envf.random_steps_fused(50)
+        barrier_sync(world)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 0
+        f0.record()
+        while True:
+            envf.random_steps_fused(K)
+            reps += 1
+            f1.record()
+            f1.synchronize()
+            if f0.elapsed_time(f1) >= 50.0 or reps >= 64:
+                break
+        barrier_sync(world)
+        fused = dict(ms=max_over_ranks(f0.elapsed_time(f1), world), steps=K * reps, per_launch=K)
+        assert int(envf.visits_s.sum()) == N * (K * reps + 51)
+        del envf
+    except Exception as e:
+        fused = dict(error=f"{type(e).__name__}: {e}")
 
     # ---- end to end through the public API: pinned host actions in, TimeStep fields out on the host, every step.
     # host_io=True: the step kernel reads the pinned action buffer and writes obs/reward/step_type into pinned host
     # memory itself (zero-copy over PCIe) -- one launch + one stream sync per step, no copy launches.
+    n_e2e = max(args.steps, 2000)  # >= 50 ms of timed region at ~30 us per step, whatever --steps says
     env_h = BatchedMDP(tb, N, mode="dense_f32", seed=1234, env_offset=rank * N, host_io=True)
     env_h.reset()
     h_act = [a.cpu().pin_memory() for a in actions]
@@ -270,7 +341,7 @@ def bench_step_gpu(args, rank, world):
     barrier_sync(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(n_e2e):
         e2e_step(i)
     e1.record()
     barrier_sync(world)
@@ -297,7 +368,7 @@ def bench_step_gpu(args, rank, world):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         e0.record()
-        for i in range(args.steps):                 # K steps of every env: K recv/send rounds per group
+        for i in range(n_e2e):                 # K steps of every env: K recv/send rounds per group
             for g in range(G):
                 env_p.recv(g)
                 env_p.send(g, p_act[i % n_act][g])
@@ -324,7 +395,7 @@ def bench_step_gpu(args, rank, world):
             env_s.step_served()
         barrier_sync(world)
         w0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(n_e2e):
             env_s.step_served()
         wall_ms = (time.perf_counter() - w0) * 1e3
         env_s.stop_serving()
@@ -333,7 +404,7 @@ def bench_step_gpu(args, rank, world):
     except Exception as exc:
         served = {"error": repr(exc)[:200]}
     return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N, b2b=b2b, det=det,
-                pipe=pipe, served=served)
+                pipe=pipe, served=served, sweep=sweep, fused=fused, n_e2e=n_e2e)
 
 
 def bench_agents_gpu(args, rank, world):
@@ -362,6 +433,72 @@ def bench_agents_gpu(args, rank, world):
                         f"{n_loops * tb.S * tb.A * 12 / 2**20:.0f} MiB per GPU"}
     except Exception as exc:
         return {"error": repr(exc)[:200]}
+
+
+C1_V0 = [0.45454547, 0.36414355, 0.2737823, 0.3346822, 0.4166667]  # SURVEY section 8d, the parity anchor
+
+
+def bench_c1(args):
+    """C1 (BASELINE.json configs[0], the reference's own CPU-runnable case): RiverSwimEpisodic size 5, 10,000
+    random-agent steps with auto-reset + episodic_value_iteration(5, T, R).  CPU: the oracle port on ONE host thread
+    (the reference is a single Python thread) with the measured Python-reference numbers quoted beside it; GPU: the
+    same two calls through the drop-in surface (a single env is the GPU's worst case -- reported, not hidden)."""
+    import torch
+
+    import colosseum_b200.dynamic_programming as dp
+    from colosseum_b200.batched_mdp import BatchedMDP
+    from colosseum_b200.tables import MDPTables
+    from oracle import oracle as orc
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "inst_c1_riverswim_epi.npz"))
+    tb = MDPTables.from_golden(g)
+    T, R, H = g["T"], g["R"], int(g["H"])
+    out = {"workload": "C1 RiverSwimEpisodic(seed=0,size=5,p_lazy=0.1, Beta rewards of the quick-test gin): 10,000 "
+                       "random-agent steps with auto-reset (BaseMDP.random_steps) + episodic_value_iteration(5,T,R)"}
+    # -- GPU, scalar drop-in: per-call steps (launch + sync per step) and the fused random walk (one launch)
+    env = BatchedMDP(tb, 1, mode="succ", seed=0, scalar_api=True)
+    env.reset()
+    for _ in range(200):
+        env.random_step(auto_reset=True)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        ts, a = env.random_step(auto_reset=True)
+    out["gpu_scalar_steps_per_s"] = 2000 / (time.perf_counter() - t0)
+    envb = BatchedMDP(tb, 1, mode="succ", seed=0)
+    envb.reset()
+    envb.random_steps_fused(100)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    envb.random_steps_fused(10000)
+    torch.cuda.synchronize()
+    out["gpu_fused_10k_steps_per_s"] = 10000 / (time.perf_counter() - t0)
+    Q, V = dp.episodic_value_iteration(H, T, R)
+    assert np.allclose(V[0], C1_V0, rtol=2e-5), V[0]
+    t0 = time.perf_counter()
+    for _ in range(200):
+        dp.episodic_value_iteration(H, T, R)
+    out["gpu_episodic_vi_us"] = (time.perf_counter() - t0) / 200 * 1e6
+    out["V0_matches_anchor"] = True
+    # -- CPU port, one thread
+    orc.set_threads(1)
+    ht = orc.HostTables(tb.S, tb.A, H=tb.H, succ_cum=tb.succ_cum, succ_idx=tb.succ_idx, succ_len=tb.succ_len,
+                        rew_cls_succ=tb.rew_cls_succ, rew_q=tb.rew_q, rmin=tb.rmin, rmax=tb.rmax,
+                        start_cum=tb.start_cum, start_idx=tb.start_idx)
+    state, h, st, obs = orc.env_reset(ht, 1, seed=0, t=0)
+    t0 = time.perf_counter()
+    for t in range(1, 10001):
+        orc.env_step(ht, 2, state, h, st, action=None, seed=0, t=t, auto_reset=True)
+    out["cpu_port_steps_per_s"] = 10000 / (time.perf_counter() - t0)
+    orc.episodic_f32(H, T, R)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        Qo, Vo = orc.episodic_f32(H, T, R)
+    out["cpu_port_episodic_vi_us"] = (time.perf_counter() - t0) / 2000 * 1e6
+    assert np.allclose(Vo[0], C1_V0, rtol=2e-6)
+    out["cpu_note"] = ("port = C oracle called through ctypes once per step / per VI, one thread (the call overhead "
+                       "dominates at this size)" + measured_reference())
+    orc.set_threads()
+    return out
 
 
 def make_c4_batch(B, S, A, seed):
@@ -474,9 +611,38 @@ def bench_c5_gpu(args, rank, world):
     ms = max_over_ranks(e0.elapsed_time(e1), world)
     v = vi.values
     assert bool(torch.isfinite(v).all()) and float(v.max()) > 0
-    del vi, T_rows, R_rows
+    # automated multi-GPU parity: one more sweep of the sharded solver, then 64 fixed rows of it recomputed by a
+    # single-rank BatchedValueIteration on this rank's own rows from the same full V_old (rtol 2e-6: a small shard
+    # may use another summation order inside a row); AND-ed over the ranks
+    v_old = v.clone()
+    vi.sweep(1)
+    v_new = vi.values.clone()
+    nrows = r1 - r0
+    pick = torch.unique(torch.linspace(0, nrows - 1, 64, device="cuda").long())
+    # the checker: the picked rows as a row block [0, n) of an S-column problem, fed with the same full V_old
+    chk = BatchedValueIteration(T_rows[pick].contiguous(), R_rows[pick].contiguous(), gamma=0.99, precision="f32",
+                                row0=0, S_total=S)
+    chk.values.view(-1).copy_(v_old.view(-1))
+    chk.sweep(1)
+    ref_rows = chk.values.view(-1)[: pick.numel()]
+    got = v_new.view(-1)[r0 + pick]
+    err = float(((got - ref_rows).abs() / ref_rows.abs().clamp_min(1e-30)).max())
+    ok = err <= 5e-6
+    if world > 1:
+        import torch.distributed as dist
+
+        t_ok = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        ok = bool(t_ok.item())
+        # every rank must also hold the SAME full V (the exchange delivered every shard everywhere)
+        cs = torch.stack([v_new.double().sum(), v_new.double().abs().max()])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = ok and bool((lo == hi).all())
+    del vi, T_rows, R_rows, chk
     torch.cuda.empty_cache()
-    return dict(S=S, A=A, steps=steps, ms=ms, launches=launches, transport=transport)
+    return dict(S=S, A=A, steps=steps, ms=ms, launches=launches, transport=transport, parity_ok=ok, parity_err=err)
 
 
 def bench_c3_gpu(args, rank, world):
@@ -566,6 +732,29 @@ def cpu_vi_rate(B, S, A, seconds):
     return n * B / dt, n, dt
 
 
+def measured_reference():
+    """the UNMODIFIED Python reference timed once in the build container (profiles/reference_python_timing.json,
+    written by scripts/time_reference.py; /root/reference does not exist on the GPU box) -- quoted, never re-run here"""
+    p = os.path.join(ROOT, "profiles", "reference_python_timing.json")
+    if not os.path.isfile(p):
+        return ""
+    d = json.load(open(p))
+    return (f"; the Python reference itself, measured in the build container on {d['cores_used']} core of "
+            f"{d['cpu']}: C1 mdp.random_steps {d['c1_random_steps_per_s']:.3g} steps/s, C2 mdp.step "
+            f"{d['c2_step_per_s']:.3g} steps/s, C1 episodic_value_iteration {d['c1_episodic_vi_us']:.1f} us")
+
+
+def measured_numba():
+    p = os.path.join(ROOT, "profiles", "reference_python_timing.json")
+    if not os.path.isfile(p):
+        return None
+    d = json.load(open(p))
+    return {"mdp_sweeps_per_s": d.get("c4_numba_mdp_sweeps_per_s"), "solve_ms": d.get("c4_numba_solve_ms"),
+            "sweeps": d.get("c4_numba_sweeps"), "cpu": d["cpu"],
+            "what": "the reference's own numba _discounted_value_iteration on one S=512 A=4 MDP, one core, measured in "
+                    "the build container (scripts/time_reference.py)"}
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference's CPU algorithm (oracle port), all host threads, same config/metric"""
     rank = int(os.environ.get("RANK", "0"))
@@ -585,26 +774,31 @@ def run_reference_arm(args):
     vsa = np.zeros((tb.S, tb.A), np.uint64)
     t = 1
     steps = min(args.steps, 2000)
-    for _ in range(args.warmup):
-        orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
+    rs = np.random.RandomState(1234)
+    acts = [rs.randint(0, tb.A, size=N).astype(np.int32) for _ in range(8)]  # supplied actions, as in the GPU arm
+    for i in range(args.warmup):
+        orc.env_step(ht, 0, state, h, st, action=acts[i % 8], seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
         t += 1
     t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.env_step(ht, 0, state, h, st, action=None, seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
+    for i in range(steps):
+        orc.env_step(ht, 0, state, h, st, action=acts[i % 8], seed=1234, t=t, auto_reset=True, visits_s=vs, visits_sa=vsa)
         t += 1
     dt = time.perf_counter() - t0
     value = steps * N / dt
+    measured = measured_reference()
     vi_rate, vi_n, vi_dt = cpu_vi_rate(64, 512, 4, 5.0)
     line = {
         "impl": "reference", "metric": "batched env-steps/sec", "value": value, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": c2_workload(tb.S, tb.A, N),
-                   "where": "host CPU cores (reference algorithm, C+OpenMP port; the reference has no GPU path); random "
-                            "actions and uniforms from the same Philox stream as the GPU arm"},
+                   "implementation": "host CPU cores: the reference algorithm as a C+OpenMP port (the reference is "
+                                     "single-env Python and has no batched or GPU path); supplied actions, uniforms "
+                                     "from the same Philox stream as the GPU arm",
+                   "l2": "n/a (host)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{steps} batched steps of {N} envs, C+OpenMP oracle port of "
-                                   "BaseMDP.step/NextStateSampler.sample"},
+                                   "BaseMDP.step/NextStateSampler.sample, supplied actions" + measured},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "vi": {"metric": "value-iteration MDP-sweeps/sec", "value": vi_rate, "unit": "MDP-sweeps/s",
                "sample": f"{vi_n} in-place fp32 sweeps x 64 MDPs (S=512,A=4) in {vi_dt:.1f}s, {cores} threads"},
@@ -644,7 +838,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="all", choices=["all", "step", "vi", "c5", "c3"])
-    ap.add_argument("--c3-instances", type=int, default=1024, help="MDP instances of the C3 suite leg (all ranks)")
+    ap.add_argument("--c3-instances", type=int, default=0,
+                    help="MDP instances of the C3 suite leg over all ranks (default: 128 per GPU inside --workload all, "
+                         "1,024 for --workload c3)")
     ap.add_argument("--c3-envs", type=int, default=1024)
     ap.add_argument("--c3-steps", type=int, default=1000)
     ap.add_argument("--c3-precision", default="f64", choices=["f64", "f32"])
@@ -653,6 +849,7 @@ def main():
     ap.add_argument("--c5-states", type=int, default=40000, help="S of the row-sharded single MDP (C5: 40,000)")
     ap.add_argument("--c5-transport", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the env-count sweep of the step leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -678,7 +875,12 @@ def main():
     step = bench_step_gpu(args, rank, world) if args.workload in ("all", "step") else None
     vi = bench_vi_gpu(args, rank, world) if args.workload in ("all", "vi") else None
     c5 = bench_c5_gpu(args, rank, world) if args.workload in ("all", "c5") else None
-    c3 = bench_c3_gpu(args, rank, world) if args.workload == "c3" else None  # minutes: opt-in, not part of "all"
+    if args.workload == "all":  # bounded C3 leg inside the default run: 128 instances per GPU
+        args.c3_instances = args.c3_instances or 128 * world
+    elif not args.c3_instances:
+        args.c3_instances = 1024
+    c3 = bench_c3_gpu(args, rank, world) if args.workload in ("all", "c3") else None
+    c1 = bench_c1(args) if args.workload == "all" and world == 1 and rank == 0 else None
     agents = bench_agents_gpu(args, rank, world) if args.workload == "all" else None
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -693,27 +895,31 @@ def main():
     peak, peak_src = measured_peaks()
     line = {"n_gpus": world, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "clocks": clocks}
+    c3_line = None
     if c3 is not None:
         sec = c3["ms"] / 1e3
-        line.update({
+        c3_line = {
             "metric": "benchmark-suite MDP instances/sec (batched step + hardness measures)", "value": c3["B"] / sec,
             "unit": "instances/s", "steps": c3["B"], "ms_per_step": 1e3 * sec / c3["B"], "scaling": "strong",
-            "gpu_launches": c3["launches"], "dtype": args.c3_precision,
-            "config": {"workload": f"C3: {c3['B']} MDP instances = the reference's {c3['n_suite']} benchmark gin parameter "
-                                   f"sets (7 families, continuous + episodic, seed 0) cycled, {c3['per_rank']} per GPU; per "
+            "gpu_launches": c3["launches"], "dtype": args.c3_precision, "timed_region_s": sec,
+            "config": {"workload": f"C3: {c3['B']} MDP instances drawn from the reference's {c3['n_suite']} benchmark "
+                                   f"instances (gin parameter sets of the 7 families, continuous + episodic, x seeds; "
+                                   f"tests/golden/c3_suite.npz) in order, cycled, {c3['per_rank']} per GPU; per "
                                    f"instance {args.c3_envs} envs x {args.c3_steps} random-agent steps, then diameter + "
-                                   "value norm + sub-optimality gaps (MiniGrid DoorKey is not in the reference); "
-                                   f"{args.c3_workers} instances in flight per GPU (host threads, one stream each)",
-                       "rank0_thread_seconds": {"step_phase": c3["step_s"], "hardness_phase": c3["hard_s"],
+                                   "value norm + sub-optimality gaps (MiniGrid DoorKey is not in the reference)",
+                       "rank0_seconds": {"step_phase": c3["step_s"], "hardness_phase": c3["hard_s"],
                                          "slowest_instance": c3["worst"][1], "slowest_hardness_s": c3["worst"][0]}},
             "env_steps_per_s_step_phase": c3["per_rank"] * args.c3_envs * args.c3_steps / max(c3["step_s"], 1e-9) * world,
-        })
-        emit(line)
-        if world > 1:
-            import torch.distributed as dist
+            "parity_ok": c3.get("parity_ok"), "parity_what": c3.get("parity_what"),
+        }
+        if args.workload == "c3":
+            line.update(c3_line)
+            emit(line)
+            if world > 1:
+                import torch.distributed as dist
 
-            dist.destroy_process_group()
-        return
+                dist.destroy_process_group()
+            return
     c5_line = None
     if c5 is not None:
         S5, A5 = c5["S"], c5["A"]
@@ -723,6 +929,10 @@ def main():
         c5_line = {
             "metric": "row-sharded value-iteration sweeps/sec (one dense MDP)", "value": 1.0 / sec, "unit": "sweeps/s",
             "steps": c5["steps"], "ms_per_step": 1e3 * sec, "gpu_launches": c5["launches"], "scaling": "strong",
+            "parity_ok": c5["parity_ok"], "parity_max_rel_err": c5["parity_err"],
+            "parity_what": "after the timed sweeps: one more sharded sweep, 64 fixed rows per rank recomputed by a "
+                           "single-rank BatchedValueIteration from the same full V_old (rtol 5e-6), AND over ranks; all "
+                           "ranks hold the same full V (sum / max equal across ranks)",
             "config": {"workload": f"C5: one synthetic dense MDP S={S5} A={A5} fp32 (T = {4 * S5 * A5 * S5 / 1e9:.1f} GB "
                                    f"generated on device), gamma=0.99, rows sharded over {world} GPU(s), V exchange: "
                                    f"{c5['transport']}", "l2": "T per GPU >> 126 MB L2, no flush"},
@@ -763,47 +973,89 @@ def main():
         sec_flushed = step["ms"] / 1e3 / args.steps
         b2b = step.get("b2b") or {}
         flushed_note = "L2 flushed between timed steps (256 MiB write), each step timed with its own CUDA-event pair"
-        if "ms" in b2b and b2b["steps"] == args.steps:
+        if "ms_per_step" in b2b:
             # headline protocol: inputs larger than L2 instead of a flush -- step i runs on env batch i % NB, every batch
-            # with its own tables, the K steps captured in one CUDA graph and timed as ONE region
-            sec = b2b["ms"] / 1e3 / args.steps
+            # with its own tables, max(K, NB) steps captured in one CUDA graph, replayed until the region is >= 50 ms
+            sec = b2b["ms_per_step"] / 1e3
             l2_note = (f"no flush: step i runs on env batch i % {b2b['batches']} ({b2b['batches']} independent batches of "
                        f"{N} envs, each with its own tables; {b2b['bytes_touched'] / 2**20:.0f} MiB touched per rotation > "
-                       f"126 MB L2), the {args.steps} steps captured in one CUDA graph, one CUDA-event pair around them")
-            launches = args.steps
+                       f"126 MB L2); {b2b['steps_per_graph']} steps per CUDA graph, replayed {b2b['replays']} times inside "
+                       f"ONE CUDA-event pair: {b2b['timed_steps']} timed steps, {b2b['region_ms']:.1f} ms timed region "
+                       "(--steps sets the minimum graph length; the region is never shorter than 50 ms)")
+            launches, region_s = b2b["timed_steps"], b2b["region_ms"] / 1e3
         else:
-            sec, l2_note, launches = sec_flushed, flushed_note, step["launches"]
-        bytes_per_launch = STEP_BYTES(tb.S) * N
+            sec, l2_note, launches, region_s = sec_flushed, flushed_note, step["launches"], step["ms"] / 1e3
+        io_bytes = STEP_IO_BYTES * N
+        # the sweep names the bound: per N, env-steps/s and the env-state stream in GB/s against the HBM peak
+        sweep_out, sat = [], None
+        for e in step.get("sweep") or []:
+            if "error" in e:
+                sweep_out.append(e)
+                continue
+            t = e["ms_per_step"] / 1e3
+            row = {"n_envs": e["n_envs"], "us_per_step": 1e6 * t, "env_steps_per_s": e["n_envs"] / t,
+                   "state_stream_gbs": STEP_IO_BYTES * e["n_envs"] / t / 1e9,
+                   "frac_of_hbm_peak": STEP_IO_BYTES * e["n_envs"] / t / 1e9 / peak,
+                   "waves": e["n_envs"] / (148 * 2048), "timed_steps": e["timed_steps"], "region_ms": e["region_ms"]}
+            sweep_out.append(row)
+            if sat is None or row["env_steps_per_s"] > sat["env_steps_per_s"]:
+                sat = row
         line.update({
             "metric": "batched env-steps/sec", "value": world * N / sec, "unit": "env-steps/s", "steps": args.steps,
-            "ms_per_step": 1e3 * sec, "gpu_launches": launches,
+            "ms_per_step": 1e3 * sec, "gpu_launches": launches, "timed_region_s": region_s,
             "config": {"workload": c2_workload(tb.S, tb.A, N),
-                       "kernel": "one thread per env: three-round k-ary search of the dense CDF row through its two-level index "
-                                 "(cdf_coarse / cdf_mid), supplied actions, in-kernel Philox uniforms",
+                       "implementation": "B200: one thread per env, three-round k-ary search of the dense CDF row through "
+                                         "its two-level index (cdf_coarse / cdf_mid), supplied actions, in-kernel Philox "
+                                         "uniforms",
                        "l2": l2_note},
             "flushed_per_step": {"value": world * N / sec_flushed, "unit": "env-steps/s", "ms_per_step": 1e3 * sec_flushed,
                                  "what": flushed_note + " (the event pair alone costs ~10 us on this GPU: a floor, not "
                                          "the kernel)"},
-            "e2e": {"value": world * N * args.steps / (step["e2e_ms"] / 1e3), "unit": "env-steps/s",
-                    "h2d_bytes_per_step": step["h2d"], "d2h_bytes_per_step": step["d2h"],
+            "e2e": {"value": world * N * step["n_e2e"] / (step["e2e_ms"] / 1e3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": step["h2d"], "d2h_bytes_per_step": step["d2h"], "timed_steps": step["n_e2e"],
+                    "timed_region_s": step["e2e_ms"] / 1e3,
                     "what": "BatchedMDP(host_io=True).step_host: pinned host actions read, and obs/reward/step_type "
                             "written to pinned host memory, by the step kernel itself over PCIe (zero-copy), then a "
                             "stream sync, every step"},
-            "roofline": {"bound": "hbm", "achieved": bytes_per_launch / sec / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": bytes_per_launch / sec / 1e9 / peak, "traffic": ncu_traffic("step", N),
+            # NOT an HBM achievement at this size: 65,536 envs are a fraction of a wave (ncu: 0.38 waves/SM) of one-thread-per-env work and the
+            # 2.9 MB of tables live in L1/L2, so a step is ONE env's dependency chain (env scalars -> coarse index ->
+            # mid index + reward classes -> crossing quad -> reward quantiles), not a stream.  `achieved` is the
+            # env-state stream the launch really has to move (STEP_IO_BYTES per env-step); `at_saturation` is the same
+            # kernel at the env count where that stream is what it waits for.
+            "roofline": {"bound": "latency", "achieved": io_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": io_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("step", N),
                          "peak_source": peak_src, "kernel": "env_step_dense_kary_kernel<float,4>",
-                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "note": "T (1.8 MB) is L2/L1-resident by construction in C2: algorithmic bytes are served "
-                                 "on chip, so frac can exceed 1; see DESIGN.md and `traffic`"},
+                         "algorithmic_bytes_per_launch": io_bytes,
+                         "algorithmic_bytes_per_env_step": STEP_IO_BYTES,
+                         "nominal_bytes_per_env_step_survey_8d": STEP_BYTES(tb.S),
+                         "limiter": "dependent-load latency of one env's chain (4 L2/L1 round trips) plus the graph-node "
+                                    "launch; 0.38 waves per SM at 65,536 envs -- see `env_sweep` for the throughput regime",
+                         "at_saturation": None if sat is None else {
+                             "n_envs": sat["n_envs"], "bound": "hbm", "achieved": sat["state_stream_gbs"], "peak": peak,
+                             "unit": "GB/s", "frac": sat["frac_of_hbm_peak"],
+                             "env_steps_per_s": sat["env_steps_per_s"],
+                             "note": "compulsory HBM traffic = the env-state stream; the table lookups (3 sectors per "
+                                     "env) are served by L1/L2 -- their rates are in profiles/ (ncu of the sweep)"}},
+            "env_sweep": sweep_out,
         })
+        fused = step.get("fused") or {}
+        if "ms" in fused:
+            line["fused_random_walk"] = {
+                "value": world * N * fused["steps"] / (fused["ms"] / 1e3), "unit": "env-steps/s",
+                "steps_per_launch": fused["per_launch"], "timed_region_s": fused["ms"] / 1e3,
+                "what": "BaseMDP.random_steps(n) for every env in ONE launch per 1000 steps (the on-device-agent case: "
+                        "no launch between steps, env state in registers); bit-identical to n single-step launches"}
+        elif "error" in fused:
+            line["fused_random_walk"] = {"error": fused["error"]}
         single = line["e2e"]
         pipe, served = step.get("pipe") or {}, step.get("served") or {}
         if "ms" in pipe:
-            v = world * N * args.steps / (pipe["ms"] / 1e3)
+            v = world * N * step["n_e2e"] / (pipe["ms"] / 1e3)
             line["e2e_single_batch"] = single
             if v > single["value"]:
                 line["e2e"] = {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": step["h2d"],
-                               "d2h_bytes_per_step": step["d2h"],
+                               "d2h_bytes_per_step": step["d2h"], "timed_steps": step["n_e2e"],
+                               "timed_region_s": pipe["ms"] / 1e3,
                                "what": f"PipelinedBatchedMDP(groups={pipe['groups']}): the same batch as {pipe['groups']} "
                                        "host_io groups on their own streams; per group and step: recv (stream sync, "
                                        "TimeStep in pinned host memory) then send (launch reading the pinned actions); "
@@ -813,7 +1065,7 @@ def main():
         elif "error" in pipe:
             line["e2e_pipelined"] = {"error": pipe["error"]}
         if "ms" in served:
-            line["e2e_served"] = {"value": world * N * args.steps / (served["ms"] / 1e3), "unit": "env-steps/s",
+            line["e2e_served"] = {"value": world * N * step["n_e2e"] / (served["ms"] / 1e3), "unit": "env-steps/s",
                                   "what": "BatchedMDP.serve(): persistent step kernel driven by a doorbell in pinned "
                                           "host memory (no launch / stream sync per step), wall clock"}
         elif "error" in served:
@@ -831,7 +1083,7 @@ def main():
             rate, n, dt = cpu_step_rate(tb, N, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{n} batched steps of {N} envs in {dt:.1f}s (C+OpenMP oracle port of "
-                                              "BaseMDP.step; the Python reference itself runs ~5e4 steps/s/core)"}
+                                              "BaseMDP.step, in-oracle random actions)" + measured_reference()}
         if vi is not None:
             line["vi"] = vi_line
         if c5_line is not None:
@@ -846,10 +1098,16 @@ def main():
         rate, n, dt = cpu_vi_rate(64, 512, 4, args.cpu_seconds)
         tgt = line["vi"] if step is not None else line
         tgt["cpu_baseline"] = {"value": rate, "unit": "MDP-sweeps/s", "cores": os.cpu_count(), "kind": "port",
+                               "reference_numba_1core": measured_numba(),
                                "sample": f"{n} in-place fp32 sweeps x 64 MDPs (S=512,A=4) in {dt:.1f}s (C+OpenMP port "
-                                         "of _discounted_value_iteration's sweep)"}
+                                         "of _discounted_value_iteration's sweep, row products as SIMD reductions like "
+                                         "the BLAS sgemv behind the reference's T[s] @ V)"}
     if agents is not None:
         line["agents"] = agents
+    if c3_line is not None:
+        line["c3"] = c3_line
+    if c1 is not None:
+        line["c1"] = c1
     emit(line)
     if world > 1:
         import torch.distributed as dist

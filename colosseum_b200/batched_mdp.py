@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _cabi
 from .tables import MDPTables
-from .timestep import BatchedTimeStep
+from .timestep import BatchedTimeStep, BoundedArray, DiscreteArray
 
 _MODES = {"dense_f32": 0, "dense_f64": 1, "succ": 2}
 
@@ -91,8 +91,11 @@ class BatchedMDP:
 
     def __init__(self, tables: MDPTables, n_envs: int, mode: str = "dense_f32", seed: int = 0,
                  track_visits: bool = True, env_offset: int = 0, host_io: bool = False, stream=None,
-                 device_tables=None):
-        """host_io=True: the TimeStep fields (obs, reward, step_type) live in ONE pinned host buffer that the step
+                 device_tables=None, scalar_api: bool = False):
+        """scalar_api=True (n_envs must be 1): `reset()` / `step(action: int)` / `random_step()` return the reference's
+        SCALAR dm_env.TimeStep (`TimeStep(FIRST, None, None, obs)`, `(MID, r, 1.0, obs)`, `(LAST, r, 0.0, -1)`,
+        mdp/base.py:1277,1316-1317), so the object can stand where a `BaseMDP` stood.
+        host_io=True: the TimeStep fields (obs, reward, step_type) live in ONE pinned host buffer that the step
         kernel writes directly over PCIe (zero-copy), and `step_host` reads the actions straight from a pinned host
         tensor: an agent running on the host gets its TimeStep with one launch and one stream sync per step, no
         copy launches (include/colosseum_b200.h, colo_env_batch).  stream: a torch.cuda.Stream the host_io lean path
@@ -100,6 +103,8 @@ class BatchedMDP:
         import torch
 
         assert mode in _MODES
+        assert not scalar_api or int(n_envs) == 1, "scalar_api: one env, the reference's own regime"
+        self.scalar_api = bool(scalar_api)
         self.torch = torch
         self.tables = tables
         self.dev = device_tables if device_tables is not None else DeviceTables(tables, mode)  # shards share one copy
@@ -117,15 +122,20 @@ class BatchedMDP:
         # the three TimeStep fields a host-side agent reads back live in ONE buffer (obs | reward | step_type), so an
         # end-to-end step is a single device->host copy
         self.host_io = bool(host_io)
+        # (obs | reward | [discount |] step_type).  The device-resident block also carries dm_env's discount, written by
+        # the step kernel's epilogue (no eager-PyTorch tail after a step); the pinned-host block does not (4 more
+        # bytes per env over PCIe): there the discount is derived from step_type on the host when it is asked for.
         if self.host_io:
             self._out = torch.zeros(9 * N, dtype=torch.uint8).pin_memory()
             self.step_type = torch.full((N,), _cabi.STEP_LAST, dtype=torch.uint8, device="cuda")  # kernel input too
             self.step_type_host = self._out[8 * N:]
             self.step_type_host.fill_(_cabi.STEP_LAST)
+            self.discount = None
         else:
-            self._out = torch.zeros(9 * N, dtype=torch.uint8, device="cuda")
-            self.step_type = self._out[8 * N:]
+            self._out = torch.zeros(13 * N, dtype=torch.uint8, device="cuda")
+            self.step_type = self._out[12 * N:]
             self.step_type.fill_(_cabi.STEP_LAST)
+            self.discount = self._out[8 * N: 12 * N].view(torch.float32)
         self.obs = self._out[: 4 * N].view(torch.int32)
         self.reward = self._out[4 * N: 8 * N].view(torch.float32)
         self.action = torch.zeros(N, dtype=torch.int32, device="cuda")
@@ -149,6 +159,7 @@ class BatchedMDP:
         b.visits_s, b.visits_sa, b.visits_copies = _cabi.ptr(self._visits_s), _cabi.ptr(self._visits_sa), vc
         b.status = _cabi.ptr(self.status)
         b.step_type_mirror = self.step_type_host.data_ptr() if self.host_io else None
+        b.discount = _cabi.ptr(self.discount)
         self._batch = b
         self._batch_ref = C.byref(b)
         self._own_action_ptr = b.action
@@ -173,6 +184,42 @@ class BatchedMDP:
     def is_episodic(self):
         return self.tables.H > 0
 
+    @property
+    def T(self):
+        """f32 [S,A,S] (mdp/base.py:463-470)"""
+        return self.tables.T
+
+    @property
+    def R(self):
+        """f32 [S,A] expected rewards (mdp/base.py:472-479)"""
+        return self.tables.R if self.tables.R is not None else self.tables.expected_rewards().astype(np.float32)
+
+    @property
+    def starting_state_distribution(self):
+        return self.tables.starting_state_distribution
+
+    @property
+    def node_to_index(self):
+        return self.tables.node_to_index
+
+    @property
+    def index_to_node(self):
+        return self.tables.index_to_node
+
+    @property
+    def rewards_range(self):
+        return (self.tables.rmin, self.tables.rmax)
+
+    def action_spec(self):
+        """mdp/base.py:1233-1240"""
+        return DiscreteArray(self.tables.A, name="action")
+
+    def observation_spec(self):
+        """mdp/base.py:1242-1252: tabular observations unless an emission table was set"""
+        if getattr(self, "_emit_table", None) is None:
+            return DiscreteArray(self.tables.S, name="observation")
+        return BoundedArray(self._emit_shape, np.float32, -np.inf, np.inf, "observation")
+
     def _u(self, u, dtype):
         if u is None:
             return None
@@ -185,11 +232,18 @@ class BatchedMDP:
         torch = self.torch
         if self.host_io:  # host-resident fields: wait for the kernel that writes them
             torch.cuda.current_stream().synchronize()
-        st = self.step_type_host if self.host_io else self.step_type
-        nan = torch.full_like(self.reward, float("nan"))
-        discount = torch.where(st == _cabi.STEP_MID, torch.ones_like(self.reward),
-                               torch.where(st == _cabi.STEP_LAST, torch.zeros_like(self.reward), nan))
-        return BatchedTimeStep(st.clone(), self.reward.clone(), discount, self.obs.clone())
+        N = self.n_envs
+        out = self._out.clone()  # ONE copy: the fields of this TimeStep survive the next step
+        obs, reward = out[: 4 * N].view(torch.int32), out[4 * N: 8 * N].view(torch.float32)
+        if self.host_io:  # host tensors: derive dm_env's discount from step_type on the host (no GPU work)
+            st = out[8 * N:]
+            discount = torch.full((N,), float("nan"))
+            discount[st == _cabi.STEP_MID] = 1.0
+            discount[st == _cabi.STEP_LAST] = 0.0
+        else:
+            st, discount = out[12 * N:], out[8 * N: 12 * N].view(torch.float32)
+        ts = BatchedTimeStep(st, reward, discount, obs)
+        return ts.scalar(0) if self.scalar_api else ts
 
     def reset(self, u_next=None) -> BatchedTimeStep:
         """BaseMDP.reset (base.py:1268-1277) for every env."""
@@ -199,9 +253,6 @@ class BatchedMDP:
         _cabi.check(rc, "colo_env_reset")
         self.t += 1
         self._was_reset = True
-        if self.host_io:
-            torch.cuda.current_stream().synchronize()
-        self.reward.fill_(float("nan"))
         return self._timestep()
 
     def step_async(self, action=None, auto_reset=False, u_next=None, u_reward=None, check=False):
@@ -368,6 +419,8 @@ class BatchedMDP:
              "was_reset": self._was_reset, "state": self.state.cpu(), "h": self.h.cpu(),
              "step_type": (self.step_type_host if self.host_io else self.step_type).cpu().clone(),
              "obs": self.obs.cpu().clone(), "reward": self.reward.cpu().clone()}
+        if self.discount is not None:
+            d["discount"] = self.discount.cpu().clone()
         if self._visits_s is not None:
             d["visits_s"], d["visits_sa"] = self._visits_s.sum(0).cpu(), self._visits_sa.sum(0).cpu()
         return d
@@ -384,6 +437,8 @@ class BatchedMDP:
             self.step_type_host.copy_(d["step_type"])
         self.obs.copy_(d["obs"])
         self.reward.copy_(d["reward"])
+        if self.discount is not None and "discount" in d:
+            self.discount.copy_(d["discount"])
         if self._visits_s is not None and "visits_s" in d:
             self._visits_s.zero_()
             self._visits_sa.zero_()
@@ -392,15 +447,16 @@ class BatchedMDP:
         self.torch.cuda.current_stream().synchronize()
 
     def fetch_async(self, host_buffer):
-        """one device->host copy of (obs i32[N] | reward f32[N] | step_type u8[N]) into a pinned uint8 buffer of
-        9*N bytes, enqueued on the current stream; `split_host` views it as the three arrays."""
+        """one device->host copy of the TimeStep block (obs i32[N] | reward f32[N] | discount f32[N] | step_type
+        u8[N]; 13*N bytes, 9*N without the discount in host_io mode) into a pinned uint8 buffer, enqueued on the
+        current stream; `split_host` views it as (obs, reward, step_type)."""
         host_buffer.copy_(self._out, non_blocking=True)
 
     def split_host(self, host_buffer):
         N = self.n_envs
         torch = self.torch
         return (host_buffer[: 4 * N].view(torch.int32), host_buffer[4 * N: 8 * N].view(torch.float32),
-                host_buffer[8 * N:])
+                host_buffer[(8 if self.host_io else 12) * N:])
 
     def step(self, action, auto_reset=False, u_next=None, u_reward=None) -> BatchedTimeStep:
         """BaseMDP.step (base.py:1279-1317) for every env."""
@@ -410,6 +466,8 @@ class BatchedMDP:
     def random_step(self, auto_reset=False):
         """BaseMDP.random_step (base.py:1341-1355): returns (BatchedTimeStep, actions)."""
         self.step_async(None, auto_reset)
+        if self.scalar_api:
+            return self._timestep(), int(self.action.item())
         return self._timestep(), self.action.clone()
 
     def random_steps(self, n, auto_reset=False):

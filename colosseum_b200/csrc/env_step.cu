@@ -40,6 +40,7 @@ struct StepIO {
   long long n_s, n_sa;   // S, S*A: stride between privatised counter copies
   int* status;
   unsigned char* step_type_mirror;  // write-only second target of step_type (pinned host memory) or null
+  float* discount;                  // dm_env discount of the emitted TimeStep (1 MID, 0 LAST, NaN FIRST) or null
   int n_steps;  // > 1: that many consecutive steps in ONE launch (random actions; Philox counter t, t+1, ...)
   // persistent step server (colo_env_server_*; SERVER kernels only): the kernel stays resident and runs one pass per
   // doorbell value posted by the host instead of one pass per launch
@@ -226,6 +227,7 @@ __device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tabl
     io.step_type[e] = COLO_STEP_FIRST;
     if (io.step_type_mirror) io.step_type_mirror[e] = COLO_STEP_FIRST;
     io.reward[e] = __int_as_float(0x7fc00000);
+    if (io.discount) io.discount[e] = __int_as_float(0x7fc00000);
     io.obs[e] = nxt;
   } else if (stepping) {
     const int hh = in.h + 1;
@@ -237,6 +239,7 @@ __device__ __forceinline__ void finish_env(const StepIO& io, const colo_mdp_tabl
     const unsigned char st = last ? COLO_STEP_LAST : COLO_STEP_MID;
     io.step_type[e] = st;
     if (io.step_type_mirror) io.step_type_mirror[e] = st;
+    if (io.discount) io.discount[e] = last ? 0.f : 1.f;
     io.obs[e] = last ? -1 : nxt;
   }
   const long long copy = blockIdx.x & io.visits_mask;  // privatised counters: spread same-state atomics over L2
@@ -617,6 +620,8 @@ __global__ void __launch_bounds__(kStepThreads) env_reset_kernel(const colo_mdp_
       io.h[e] = 0;
       io.step_type[e] = COLO_STEP_FIRST;
       if (io.step_type_mirror) io.step_type_mirror[e] = COLO_STEP_FIRST;
+      if (io.discount) io.discount[e] = __int_as_float(0x7fc00000);
+      if (io.reward) io.reward[e] = __int_as_float(0x7fc00000);  // the reference's reward of a FIRST TimeStep is None
       io.obs[e] = s0;
     }
     const long long copy = blockIdx.x & io.visits_mask;
@@ -796,6 +801,7 @@ static int make_io(const colo_mdp_tables* tb, const colo_env_batch* b, int rando
   io->visits_sa = b->visits_sa; io->visits_mask = copies - 1; io->n_s = tb->S; io->n_sa = (long long)tb->S * tb->A;
   io->status = b->status;
   io->step_type_mirror = b->step_type_mirror;
+  io->discount = b->discount;
   io->n_steps = 1;
   return COLO_OK;
 }

@@ -58,6 +58,11 @@ class MDPTables:
     # rewards
     rew_kinds: List[Tuple[str, Tuple[float, ...]]] = field(default_factory=lambda: [("deterministic", (0.0,))])
     rew_q: np.ndarray = None  # f32 [n_cls, nq]
+    # reference attribute surface carried along for the drop-in (mdp/base.py:463-503): expected rewards as the
+    # reference built them, and the node <-> index maps (None when the tables do not come from an MDP object)
+    R: Optional[np.ndarray] = None  # f32 [S,A]
+    node_to_index: Optional[dict] = None
+    index_to_node: Optional[dict] = None
 
     # ------------------------------------------------------------------------------------------ builders
     @staticmethod
@@ -124,9 +129,12 @@ class MDPTables:
         import json
 
         kinds = [(k, tuple(a)) for k, a in json.loads(str(g["rew_kinds"]))]
-        return cls.from_successors(int(g["n_states"]), int(g["n_actions"]), g["succ_idx"], g["succ_prob"],
-                                   g["succ_len"], g["rew_cls"], kinds, g["start_idx"], g["start_prob"],
-                                   H=int(g["H"]), rewards_range=tuple(g["rewards_range"]), T=g["T"], nq=nq)
+        tb = cls.from_successors(int(g["n_states"]), int(g["n_actions"]), g["succ_idx"], g["succ_prob"],
+                                 g["succ_len"], g["rew_cls"], kinds, g["start_idx"], g["start_prob"],
+                                 H=int(g["H"]), rewards_range=tuple(g["rewards_range"]), T=g["T"], nq=nq)
+        if "R" in getattr(g, "files", g):
+            tb.R = np.asarray(g["R"], np.float32)
+        return tb
 
     @classmethod
     def from_mdp(cls, mdp, nq=DEFAULT_NQ):
@@ -156,10 +164,14 @@ class MDPTables:
                         kinds.append(key)
                     rew_cls[i, a, k] = kinds.index(key)
         ss = mdp._starting_node_sampler
-        return cls.from_successors(S, A, succ_idx, succ_prob, succ_len, rew_cls, kinds,
-                                   [n2i[n] for n in ss.next_nodes], list(ss.probs),
-                                   H=int(mdp.H) if mdp.is_episodic() else 0, rewards_range=tuple(mdp.rewards_range),
-                                   T=np.asarray(mdp.T, np.float32), nq=nq)
+        tb = cls.from_successors(S, A, succ_idx, succ_prob, succ_len, rew_cls, kinds,
+                                 [n2i[n] for n in ss.next_nodes], list(ss.probs),
+                                 H=int(mdp.H) if mdp.is_episodic() else 0, rewards_range=tuple(mdp.rewards_range),
+                                 T=np.asarray(mdp.T, np.float32), nq=nq)
+        tb.R = np.asarray(mdp.R, np.float32)
+        tb.node_to_index = dict(n2i)
+        tb.index_to_node = {i: n for n, i in n2i.items()}
+        return tb
 
     # ------------------------------------------------------------------------------------------ derived
     @property
@@ -173,6 +185,13 @@ class MDPTables:
     @property
     def n_start(self):
         return len(self.start_idx)
+
+    @property
+    def starting_state_distribution(self):
+        """f64 [S], the reference's `starting_state_distribution` (mdp/base.py:494-503)"""
+        d = np.zeros(self.S, np.float64)
+        np.add.at(d, np.asarray(self.start_idx, np.int64), np.diff(self.start_cum, prepend=0.0))
+        return d
 
     def expected_rewards(self):
         """R[s,a] = sum_s' p * E[r]  (mdp/utils/mdp_creation.py:71-81) from the tables, for cross-checks."""

@@ -435,6 +435,8 @@ typedef struct {
   int visits_copies;
   int* status;
   unsigned char* step_type_mirror;
+  float* discount; /* f32[N] or NULL: dm_env's discount of the emitted TimeStep (base.py:1316-1317): 1.0 MID,
+                      0.0 LAST, NaN where the reference has None (FIRST) -- written by the step / reset epilogue */
 } colo_env_batch;
 
 /*

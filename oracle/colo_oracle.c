@@ -91,7 +91,9 @@ int orc_discounted_gs_f32_batch(const float* T, const float* R, int B, int S, in
   return rc;
 }
 
-/* Fixed number of fp32 in-place sweeps over a batch (throughput leg of the CPU baseline: sweeps/s). */
+/* Fixed number of fp32 in-place sweeps over a batch (throughput leg of the CPU baseline: sweeps/s).  Timing only, never
+ * a parity oracle: the row product is a SIMD reduction (reassociated partial sums), as the BLAS sgemv behind the
+ * reference's numba `T[s] @ V` (infinite_horizon.py:133) is -- a scalar in-order loop would understate the CPU. */
 void orc_sweeps_gs_f32_batch(const float* T, const float* R, int B, int S, int A, float gamma, int n_sweeps,
                              float* V) {
 #pragma omp parallel for schedule(dynamic, 1)
@@ -105,6 +107,7 @@ void orc_sweeps_gs_f32_batch(const float* T, const float* R, int B, int S, int A
         for (int a = 0; a < A; ++a) {
           const float* row = Tb + ((size_t)s * A + a) * S;
           float acc = 0.f;
+#pragma omp simd reduction(+ : acc)
           for (int j = 0; j < S; ++j) acc += row[j] * Vb[j];
           float q = Rb[(size_t)s * A + a] + gamma * acc;
           if (q > best) best = q;

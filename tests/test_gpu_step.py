@@ -540,3 +540,53 @@ def test_step_without_search_index_is_identical(bm, mode):
     for (o1, r1, s1), (o2, r2, s2) in zip(ref, got):
         assert torch.equal(o1, o2) and torch.equal(s1, s2) and torch.equal(r1.view(torch.int32), r2.view(torch.int32))
     assert torch.equal(vref, vgot)
+
+
+@pytest.mark.parametrize("name", ["c1_riverswim_epi", "doc_simplegrid4"])
+def test_scalar_dropin_surface(bm, name):
+    """n_envs=1, scalar_api=True: reset()/step(int) return the reference's SCALAR dm_env.TimeStep (mdp/base.py:1277,
+    1316-1317) and the object carries BaseMDP's attribute surface (:463-503, :1233-1252).  Replays the reference's own
+    recorded trajectory field by field."""
+    from colosseum_b200.timestep import StepType
+
+    g = load_instance(name)
+    tb = MDPTables.from_golden(g)
+    env = bm.BatchedMDP(tb, 1, mode="succ", scalar_api=True)
+    a_spec, o_spec = env.action_spec(), env.observation_spec()
+    assert a_spec.num_values == tb.A and a_spec.name == "action" and a_spec.shape == ()
+    assert o_spec.num_values == tb.S and o_spec.name == "observation"
+    assert env.n_states == tb.S and env.n_actions == tb.A and env.T.shape == (tb.S, tb.A, tb.S)
+    assert np.allclose(env.R, g["R"]) and abs(env.starting_state_distribution.sum() - 1.0) < 1e-12
+    assert np.array_equal(np.nonzero(env.starting_state_distribution)[0], np.sort(np.unique(tb.start_idx)))
+    assert (env.H == int(g["H"])) if int(g["H"]) > 0 else env.H is None
+    acts, us = g["traj_action"], np.nan_to_num(g["traj_u"], nan=0.5)
+    ts = env.reset(u_next=us[:1])
+    assert ts.step_type == StepType.FIRST and ts.reward is None and ts.discount is None
+    assert ts.observation == int(g["traj_obs"][0]) and isinstance(ts.observation, int)
+    for t in range(1, 60):
+        ts = env.step(int(acts[t]), auto_reset=True, u_next=us[t:t + 1], u_reward=np.zeros(1, np.float32))
+        assert int(ts.step_type) == int(g["traj_step_type"][t]) and ts.observation == int(g["traj_obs"][t])
+        if ts.step_type == StepType.FIRST:
+            assert ts.reward is None and ts.discount is None
+        else:
+            assert ts.discount == float(g["traj_discount"][t]) and isinstance(ts.reward, float)
+    ts, a = env.random_step(auto_reset=True)
+    assert isinstance(a, int) and 0 <= a < tb.A
+
+
+def test_discount_written_by_the_kernel(bm):
+    """dm_env's discount comes out of the step kernel's epilogue (1.0 MID, 0.0 LAST, NaN FIRST): no eager-PyTorch
+    tail after a step; the host_io variant derives it from step_type on the host"""
+    g = load_instance("c1_riverswim_epi")
+    tb = MDPTables.from_golden(g)
+    for host_io in (False, True):
+        env = bm.BatchedMDP(tb, 257, mode="succ", seed=3, host_io=host_io)
+        ts = env.reset()
+        assert bool(np.isnan(ts.discount.cpu().numpy()).all()) and bool(np.isnan(ts.reward.cpu().numpy()).all())
+        seen = set()
+        for _ in range(2 * tb.H + 2):
+            ts, _ = env.random_step(auto_reset=True)
+            st, d = ts.step_type.cpu().numpy(), ts.discount.cpu().numpy()
+            assert (d[st == 1] == 1.0).all() and (d[st == 2] == 0.0).all() and np.isnan(d[st == 0]).all()
+            seen |= set(st.tolist())
+        assert seen == {0, 1, 2}
