@@ -828,7 +828,7 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
   static const int diam_path = [] {
     const char* e = getenv("COLO_DIAM_PATH");
     if (!e) return 0;
-    return !strcmp(e, "resident") ? 1 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : (!strcmp(e, "sparse") ? 4 : 0)));
+    return !strcmp(e, "resident") ? 1 : (!strcmp(e, "gemm") ? 2 : (!strcmp(e, "stream") ? 3 : (!strcmp(e, "sparse") ? 4 : (!strcmp(e, "umma") ? 5 : 0))));
   }();
   if (diam_path == 0 || diam_path == 4) {
     // benchmark-family MDPs (<= 32 successors per row): compressed rows, the whole solve in one launch
@@ -885,7 +885,14 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
     out_host[1] = (double)mx;
     return rc;
   }
-  const bool use_gemm = diam_path == 2 || (diam_path == 0 && (long long)K * S >= 128LL * 128);
+  const bool use_gemm = diam_path == 2 || diam_path == 5 || (diam_path == 0 && (long long)K * S >= 128LL * 128);
+  // f32 mode: the GEMM sweep runs on the tensor cores (hitting_umma.cu); f64acc mode keeps the fp64 SIMT tile
+  UmmaPlan* umma = nullptr;
+  if (sizeof(TV) == 4 && use_gemm && diam_path != 2 && hitting_umma_supported(S, A, K)) {
+    const int r = hitting_umma_plan(T, S, A, K, &umma, st);
+    if (r != COLO_OK) return r;
+  }
+  COLO_ARG_CHECK(diam_path != 5 || umma != nullptr, "COLO_DIAM_PATH=umma: f32 mode, 1 <= A <= 8, S >= 128, K >= 64");
   HittingGemmArgs ga = {};
   ga.T = T; ga.e_stride = S; ga.targets = targets; ga.active = w.active; ga.resid = w.resid;
   ga.S = S; ga.A = A; ga.K = K; ga.max_value = max_value; ga.overflow_flag = w.flags + 1;
@@ -898,6 +905,9 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
   a.resid = w.resid; a.active = w.active; a.max_abs = max_value; a.overflow_flag = w.flags + 1;
   a.row0 = 0; a.nrows = S;
   auto sweep = [&](TV* cur, TV* nxt) {
+    if (umma)
+      return hitting_umma_sweep(umma, (const float*)cur, (float*)nxt, S, targets, w.active, (unsigned*)w.resid, max_value,
+                                w.flags + 1, st);
     if (use_gemm) {  // many targets: one tiled GEMM per sweep (multirhs.cuh)
       ga.E_in = cur;
       ga.E_out = nxt;
@@ -909,6 +919,7 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
   };
   long long sweeps = 0;
   int rc = iterate_to_convergence<TV>(sweep, E, w, K, S, (TV)eps, max_iter, nullptr, &sweeps, st);
+  hitting_umma_free(umma, st);
   if (rc != COLO_OK && rc != COLO_MAX_ITER) return rc;
   max_reduce_kernel<TV><<<1, 1024, 0, st>>>(E, (long long)K * S, d_out, 0);
   int r = check_launch("max_reduce_kernel");

@@ -64,6 +64,14 @@ int sparse_sweep_launch(const SparseRows& h, const float* R, const float* pi, in
                         double gamma, const TV* V_in, TV* V_out, TV* Q, void* resid, const unsigned char* active,
                         double max_abs, int* overflow_flag, void* stream);
 
+// hitting_umma.cu: the multi-target hitting-time sweep on the tensor cores (tcgen05 / TMEM / TMA), fp32 iterates
+struct UmmaPlan;
+bool hitting_umma_supported(int S, int A, int K);
+int hitting_umma_plan(const float* T, int S, int A, int K, UmmaPlan** out, cudaStream_t st);
+int hitting_umma_sweep(UmmaPlan* pl, const float* E_in, float* E_out, long long e_stride, const int* targets,
+                       const unsigned char* active, unsigned* resid, double max_value, int* overflow_flag, cudaStream_t st);
+void hitting_umma_free(UmmaPlan* pl, cudaStream_t st);
+
 // ---- device helpers -------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 

@@ -1,0 +1,468 @@
+// hitting_umma.cu -- the multi-target hitting-time sweep of the continuous diameter on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands staged by TMA behind an mbarrier ring).  sm_100a only.
+//
+// colosseum/hardness/measures/diameter.py:76-106 solves, for every target state k, a value iteration with gamma = 1,
+// reward -1 and k absorbing.  All K targets share T, so one synchronous sweep over all of them is the GEMM
+//     C[(s,a), k] = sum_j T[s,a,j] * E[k,j]              (S*A x S) . (S x K),  2*S*A*S*K flop
+//     E'[k,s]     = (s == target_k) ? 0 : min_a (1 + C[(s,a), k])
+// with a min-over-actions epilogue (multirhs.cuh is the SIMT FFMA version of the same sweep).
+//
+// Precision: the bar is 1e-4 relative in f32 mode (BASELINE.json north_star), which a single TF32 product (10-bit
+// mantissa, truncated operands: ~2.4e-4 biased) does not meet.  Both operands are therefore split into two TF32-exact
+// halves, x = hi + lo with hi = x & 0xffffe000 and lo = x - hi (exact in fp32), and the sweep runs THREE tensor-core
+// products per k-step into the same fp32 TMEM accumulator:  T_hi.E_hi + T_hi.E_lo + T_lo.E_hi   (the dropped
+// T_lo.E_lo term is 2^-22 relative).  T is split once per solve, E' is split by the epilogue that produces it.
+//
+// Layout.  T_split f32 [2][A][Sm][Sk] (part, action, state, next state; Sm = S rounded up to 128, Sk to 32, zero
+// padded): for a fixed (part, action) the 128 states of a CTA are 128 consecutive rows, so ONE 2-D TMA box {32, 128}
+// with SWIZZLE_128B lands a K-major [128][32] fp32 tile exactly as the UMMA shared-memory descriptor wants it.
+// E_split f32 [2 ping/pong][2][Kp][Sk] likewise (rows = targets).  D (TMEM): lane = state of the tile, column =
+// a*BN + target of the tile: every action accumulates into its own BN columns (A*BN <= 512), and the epilogue folds
+// min_a straight out of TMEM with tcgen05.ld -- one thread per state, 16 targets per load.
+//
+// Roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 = TMEM allocator + (lane 0) MMA issuer, warps 2-5 =
+// epilogue (warp w reads the TMEM lanes 32*(w%4) .. +31).  One ring of NS stages {T_hi, T_lo, E_hi, E_lo} with
+// full/empty mbarriers; tcgen05.commit releases a stage when the MMAs that read it have retired, and signals the
+// epilogue after the last one.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace colo {
+
+constexpr int UM_BM = 128;       // states per CTA == UMMA M (cta_group::1)
+constexpr int UM_BK = 32;        // fp32 per k-block == one 128-byte swizzle row; 4 MMAs of K = 8 each
+constexpr int UM_THREADS = 192;
+constexpr int UM_T_TILE = UM_BM * UM_BK * 4;  // 16 KiB
+
+struct UmmaSweepArgs {
+  const float* E_in;   // [K][e_stride] fp32 iterate the sweep reads (its split twin is behind mapE, half `in_buf`)
+  float* E_out;        // [K][e_stride]
+  long long e_stride;
+  float* E_split_out;  // [2][Kp][Sk] split twin of E_out
+  const int* targets;
+  const unsigned char* active;
+  unsigned* resid;
+  int S, A, K, Sm, Sk, Kp, in_buf;
+  float max_value;
+  int* overflow_flag;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, both operands K-major TF32, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO (ignored for swizzled K-major, 1) << 16 | SBO = 1024 B (8 rows) >> 4 << 32 | version 1 << 46
+// | layout type SWIZZLE_128B (2) << 61.  The tile base is 1024-byte aligned (base_offset 0); a k-step of 8 fp32
+// advances the start address by 32 bytes inside the swizzle atom.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A/B TF32 (2 << 7, 2 << 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr int E_TILE = BN * UM_BK * 4;
+  static constexpr int STAGE = 2 * UM_T_TILE + 2 * E_TILE;  // 64 KiB (BN = 128) / 48 KiB (BN = 64)
+  static constexpr int NS = BN == 128 ? 3 : 4;
+  static constexpr int SMEM = NS * STAGE + 1024 /* alignment slack */ + 256 /* barriers, tmem pointer */;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapE,
+                    const UmmaSweepArgs p) {
+  using Cfg = UmmaCfg<BN>;
+  constexpr int NS = Cfg::NS;
+  extern __shared__ unsigned char umma_smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)umma_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024 B
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE);
+  uint64_t* empty = full + NS;
+  uint64_t* accum_full = empty + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  __shared__ int s_any_active;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.S, A = p.A, K = p.K;
+  const int k0 = blockIdx.x * BN, s0 = blockIdx.y * UM_BM;
+  const int nkb = p.Sk / UM_BK;
+  const int total = A * nkb;
+
+  // ---- a tile whose targets have all converged only carries E forward (its split twin is a function of the value)
+  if (threadIdx.x == 0) s_any_active = p.active == nullptr;
+  __syncthreads();
+  if (p.active)
+    for (int n = threadIdx.x; n < BN; n += UM_THREADS)
+      if (k0 + n < K && p.active[k0 + n]) s_any_active = 1;
+  __syncthreads();
+  if (!s_any_active) {
+    for (int i = threadIdx.x; i < UM_BM * BN; i += UM_THREADS) {
+      const int m = i % UM_BM, n = i / UM_BM;
+      const int s = s0 + m, k = k0 + n;
+      if (s < S && k < K) {
+        const float v = p.E_in[(size_t)k * p.e_stride + s];
+        p.E_out[(size_t)k * p.e_stride + s] = v;
+        const float hi = tf32_hi(v);
+        p.E_split_out[(size_t)k * p.Sk + s] = hi;
+        p.E_split_out[((size_t)p.Kp + k) * p.Sk + s] = v - hi;
+      }
+    }
+    return;
+  }
+
+  // ---- one-time setup: barriers (warp 0), TMEM columns (warp 1: a power of two >= A*BN, at least 32)
+  uint32_t ncols = 32;
+  while ((int)ncols < A * BN) ncols <<= 1;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapE) : "memory");
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(empty + i, 1);
+    }
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int it = 0; it < total; ++it) {
+        const int st = it % NS;
+        const uint32_t ph = (uint32_t)(it / NS) & 1u;
+        mbar_wait(empty + st, ph ^ 1u);
+        mbar_expect_tx(full + st, (uint32_t)Cfg::STAGE);
+        const int a = it / nkb, kb = it - a * nkb;
+        unsigned char* sb = smem + st * Cfg::STAGE;
+        tma_load_2d(sb, &mapT, kb * UM_BK, a * p.Sm + s0, full + st);
+        tma_load_2d(sb + UM_T_TILE, &mapT, kb * UM_BK, (A + a) * p.Sm + s0, full + st);
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h) {
+          tma_load_2d(sb + 2 * UM_T_TILE + h * 8192, &mapE, kb * UM_BK, (p.in_buf * 2) * p.Kp + k0 + 64 * h, full + st);
+          tma_load_2d(sb + 2 * UM_T_TILE + Cfg::E_TILE + h * 8192, &mapE, kb * UM_BK,
+                      (p.in_buf * 2 + 1) * p.Kp + k0 + 64 * h, full + st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer: three TF32 products per k-step into the action's own TMEM columns =====
+      constexpr uint32_t idesc = umma_idesc_tf32(UM_BM, BN);
+      for (int it = 0; it < total; ++it) {
+        const int st = it % NS;
+        const uint32_t ph = (uint32_t)(it / NS) & 1u;
+        mbar_wait(full + st, ph);
+        tc_fence_after();
+        const int a = it / nkb, kb = it - a * nkb;
+        const uint32_t sb = smem_u32(smem + st * Cfg::STAGE);
+        const uint64_t d_th = umma_desc_sw128(sb), d_tl = umma_desc_sw128(sb + UM_T_TILE);
+        const uint64_t d_eh = umma_desc_sw128(sb + 2 * UM_T_TILE), d_el = umma_desc_sw128(sb + 2 * UM_T_TILE + Cfg::E_TILE);
+        const uint32_t d = tmem_base + (uint32_t)(a * BN);
+#pragma unroll
+        for (int k = 0; k < UM_BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);  // 8 fp32 = 32 bytes = 2 x 16-byte units of the start address
+          umma_tf32(d, d_th + adv, d_eh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32(d, d_th + adv, d_el + adv, idesc, 1u);
+          umma_tf32(d, d_tl + adv, d_eh + adv, idesc, 1u);
+        }
+        umma_commit(empty + st);  // the stage is free once these MMAs have read it
+      }
+      umma_commit(accum_full);    // every accumulator is final
+    }
+  } else {
+    // ===== epilogue: min over actions out of TMEM, pin / carry / residual, E' and its split twin =====
+    const int q = warp & 3;  // the TMEM lane quarter this warp may read
+    const int s = s0 + q * 32 + lane;
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c = 0; c < BN / 16; ++c) {
+      float best[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) best[i] = INFINITY;
+      for (int a = 0; a < A; ++a) {
+        float v[16];
+        tmem_ld16(lane_base + (uint32_t)(a * BN + c * 16), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) best[i] = fminf(best[i], 1.f + v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = k0 + c * 16 + i;
+        if (k >= K) break;  // warp-uniform
+        const int tgt = __ldg(p.targets + k);
+        const bool act = p.active == nullptr || p.active[k] != 0;
+        float dlt = 0.f;
+        if (s < S) {
+          const float old = p.E_in[(size_t)k * p.e_stride + s];
+          float nv = (s == tgt) ? 0.f : best[i];
+          if (!act) nv = old;
+          p.E_out[(size_t)k * p.e_stride + s] = nv;
+          const float hi = tf32_hi(nv);
+          p.E_split_out[(size_t)k * p.Sk + s] = hi;
+          p.E_split_out[((size_t)p.Kp + k) * p.Sk + s] = nv - hi;
+          dlt = fabsf(nv - old);
+          if (p.max_value > 0.f && nv > p.max_value && p.overflow_flag) *p.overflow_flag = 1;
+        }
+        const unsigned m = __reduce_max_sync(FULL, __float_as_uint(dlt));  // dlt >= 0: IEEE order == unsigned order
+        if (lane == 0 && m != 0u && p.resid) atomicMax(p.resid + k, m);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// T f32 [S,A,S] -> T_split f32 [2][A][Sm][Sk] (TF32-exact hi, remainder lo; zero padding)
+__global__ void __launch_bounds__(256) umma_split_T_kernel(const float* __restrict__ T, int S, int A, int Sm, int Sk,
+                                                           float* __restrict__ out) {
+  const long long n = (long long)A * Sm * Sk;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % Sk);
+    const long long r = i / Sk;
+    const int s = (int)(r % Sm), a = (int)(r / Sm);
+    float v = 0.f;
+    if (s < S && j < S) v = __ldg(T + ((size_t)s * A + a) * S + j);
+    const float hi = tf32_hi(v);
+    out[i] = hi;
+    out[n + i] = v - hi;
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+static int make_map_2d(CUtensorMap* map, float* base, int cols, long long rows, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return COLO_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)UM_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d (cols %d rows %lld box %d)", (int)r, cols, rows, box_rows);
+    return COLO_ERR_CUDA;
+  }
+  return COLO_OK;
+}
+
+struct UmmaPlan {
+  float* T_split = nullptr;  // [2][A][Sm][Sk]
+  float* E_split = nullptr;  // [2][2][Kp][Sk]
+  CUtensorMap mapT, mapE;
+  int S = 0, A = 0, K = 0, Sm = 0, Sk = 0, Kp = 0, BN = 0, cur = 0;
+};
+
+bool hitting_umma_supported(int S, int A, int K) {
+  static const bool off = getenv("COLO_NO_UMMA") != nullptr;
+  return !off && A >= 1 && A <= 8 && S >= 128 && K >= 64 && encode_tiled_fn() != nullptr;
+}
+
+int hitting_umma_plan(const float* T, int S, int A, int K, UmmaPlan** out, cudaStream_t st) {
+  COLO_ARG_CHECK(T && out && A >= 1 && A <= 8 && S >= 1 && K >= 1, "hitting_umma_plan: T, 1 <= A <= 8");
+  UmmaPlan* pl = new UmmaPlan();
+  pl->S = S; pl->A = A; pl->K = K;
+  pl->BN = A <= 4 ? 128 : 64;
+  pl->Sm = (S + UM_BM - 1) / UM_BM * UM_BM;
+  pl->Sk = (S + UM_BK - 1) / UM_BK * UM_BK;
+  pl->Kp = (K + pl->BN - 1) / pl->BN * pl->BN;
+  const size_t t_elems = (size_t)2 * A * pl->Sm * pl->Sk, e_elems = (size_t)4 * pl->Kp * pl->Sk;
+  cudaError_t e = cudaMallocAsync((void**)&pl->T_split, t_elems * 4, st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&pl->E_split, e_elems * 4, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(pl->E_split, 0, e_elems * 4, st);  // E = 0 and finite padding
+  if (e != cudaSuccess) {
+    set_error("hitting_umma_plan: %s", cudaGetErrorString(e));
+    if (pl->T_split) cudaFreeAsync(pl->T_split, st);
+    delete pl;
+    return COLO_ERR_CUDA;
+  }
+  const long long n = (long long)A * pl->Sm * pl->Sk;
+  const int grid = (int)((n + 255) / 256 < (long long)sm_count() * 16 ? (n + 255) / 256 : (long long)sm_count() * 16);
+  umma_split_T_kernel<<<grid, 256, 0, st>>>(T, S, A, pl->Sm, pl->Sk, pl->T_split);
+  int r = check_launch("umma_split_T_kernel");
+  if (r == COLO_OK) r = make_map_2d(&pl->mapT, pl->T_split, pl->Sk, (long long)2 * A * pl->Sm, UM_BM);
+  if (r == COLO_OK) r = make_map_2d(&pl->mapE, pl->E_split, pl->Sk, (long long)4 * pl->Kp, 64);
+  if (r != COLO_OK) {
+    cudaFreeAsync(pl->T_split, st);
+    cudaFreeAsync(pl->E_split, st);
+    delete pl;
+    return r;
+  }
+  *out = pl;
+  return COLO_OK;
+}
+
+void hitting_umma_free(UmmaPlan* pl, cudaStream_t st) {
+  if (!pl) return;
+  cudaFreeAsync(pl->T_split, st);
+  cudaFreeAsync(pl->E_split, st);
+  delete pl;
+}
+
+// overwrite the split twin of the CURRENT iterate from a full fp32 E (a solve that starts from a given E0)
+__global__ void __launch_bounds__(256) umma_split_E_kernel(const float* __restrict__ E, long long e_stride, int K, int S,
+                                                           int Kp, int Sk, float* __restrict__ out) {
+  const long long n = (long long)K * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i % S), k = (int)(i / S);
+    const float v = E[(size_t)k * e_stride + s];
+    const float hi = tf32_hi(v);
+    out[(size_t)k * Sk + s] = hi;
+    out[((size_t)Kp + k) * Sk + s] = v - hi;
+  }
+}
+
+int hitting_umma_set_iterate(UmmaPlan* pl, const float* E, long long e_stride, cudaStream_t st) {
+  const long long n = (long long)pl->K * pl->S;
+  const int grid = (int)((n + 255) / 256 < (long long)sm_count() * 16 ? (n + 255) / 256 : (long long)sm_count() * 16);
+  umma_split_E_kernel<<<grid, 256, 0, st>>>(E, e_stride, pl->K, pl->S, pl->Kp, pl->Sk,
+                                            pl->E_split + (size_t)pl->cur * 2 * pl->Kp * pl->Sk);
+  return check_launch("umma_split_E_kernel");
+}
+
+// one synchronous sweep E_in -> E_out (fp32, [K][e_stride]); the plan keeps the split twins and flips its ping/pong
+int hitting_umma_sweep(UmmaPlan* pl, const float* E_in, float* E_out, long long e_stride, const int* targets,
+                       const unsigned char* active, unsigned* resid, double max_value, int* overflow_flag, cudaStream_t st) {
+  UmmaSweepArgs a;
+  a.E_in = E_in; a.E_out = E_out; a.e_stride = e_stride;
+  a.E_split_out = pl->E_split + (size_t)(1 - pl->cur) * 2 * pl->Kp * pl->Sk;
+  a.targets = targets; a.active = active; a.resid = resid;
+  a.S = pl->S; a.A = pl->A; a.K = pl->K; a.Sm = pl->Sm; a.Sk = pl->Sk; a.Kp = pl->Kp; a.in_buf = pl->cur;
+  a.max_value = (float)max_value; a.overflow_flag = overflow_flag;
+  dim3 grid(pl->Kp / pl->BN, pl->Sm / UM_BM);
+  if (pl->BN == 128) {
+    static const cudaError_t attr = cudaFuncSetAttribute(hitting_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         UmmaCfg<128>::SMEM);
+    COLO_CUDA_TRY(attr);
+    hitting_umma_kernel<128><<<grid, UM_THREADS, UmmaCfg<128>::SMEM, st>>>(pl->mapT, pl->mapE, a);
+  } else {
+    static const cudaError_t attr = cudaFuncSetAttribute(hitting_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         UmmaCfg<64>::SMEM);
+    COLO_CUDA_TRY(attr);
+    hitting_umma_kernel<64><<<grid, UM_THREADS, UmmaCfg<64>::SMEM, st>>>(pl->mapT, pl->mapE, a);
+  }
+  pl->cur ^= 1;
+  return check_launch("hitting_umma_kernel");
+}
+
+}  // namespace colo
+
+extern "C" {
+
+// Fixed number of synchronous hitting-time sweeps on the tensor cores (parity / throughput probe of the kernel behind
+// colo_diameter_continuous_f32's dense path): E f32 [K][S] in place, E = 0 at the start when `zero_start`.
+int colo_hitting_umma_sweeps_f32(const float* T, const int* targets, int K, int S, int A, int n_sweeps, int zero_start,
+                                 float* E, float* E_work, void* stream) {
+  COLO_ARG_CHECK(T && targets && E && E_work && n_sweeps >= 0, "T, targets, E, E_work");
+  COLO_ARG_CHECK(colo::hitting_umma_supported(S, A, K), "shape not supported by the tcgen05 path (1 <= A <= 8, S >= 128, K >= 64)");
+  cudaStream_t st = (cudaStream_t)stream;
+  colo::UmmaPlan* pl = nullptr;
+  int r = colo::hitting_umma_plan(T, S, A, K, &pl, st);
+  if (r != COLO_OK) return r;
+  if (zero_start)
+    COLO_CUDA_TRY(cudaMemsetAsync(E, 0, (size_t)K * S * 4, st));
+  else
+    r = colo::hitting_umma_set_iterate(pl, E, S, st);
+  float* cur = E;
+  float* nxt = E_work;
+  for (int i = 0; i < n_sweeps && r == COLO_OK; ++i) {
+    r = colo::hitting_umma_sweep(pl, cur, nxt, S, targets, nullptr, nullptr, 0.0, nullptr, st);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  if (r == COLO_OK && cur != E) COLO_CUDA_TRY(cudaMemcpyAsync(E, cur, (size_t)K * S * 4, cudaMemcpyDeviceToDevice, st));
+  colo::hitting_umma_free(pl, st);
+  return r;
+}
+
+}  // extern "C"
