@@ -892,7 +892,7 @@ int diameter_continuous(const float* T, const int* targets, int K, int S, int A,
     const int r = hitting_umma_plan(T, S, A, K, &umma, st);
     if (r != COLO_OK) return r;
   }
-  COLO_ARG_CHECK(diam_path != 5 || umma != nullptr, "COLO_DIAM_PATH=umma: f32 mode, 1 <= A <= 8, S >= 128, K >= 64");
+  COLO_ARG_CHECK(diam_path != 5 || umma != nullptr, "COLO_DIAM_PATH=umma: f32 mode, S >= 128, K >= 64");
   HittingGemmArgs ga = {};
   ga.T = T; ga.e_stride = S; ga.targets = targets; ga.active = w.active; ga.resid = w.resid;
   ga.S = S; ga.A = A; ga.K = K; ga.max_value = max_value; ga.overflow_flag = w.flags + 1;

@@ -8,23 +8,28 @@
 // with a min-over-actions epilogue (multirhs.cuh is the SIMT FFMA version of the same sweep).
 //
 // Precision: the bar is 1e-4 relative in f32 mode (BASELINE.json north_star), which a single TF32 product (10-bit
-// mantissa, truncated operands: ~2.4e-4 biased) does not meet.  Both operands are therefore split into two TF32-exact
-// halves, x = hi + lo with hi = x & 0xffffe000 and lo = x - hi (exact in fp32), and the sweep runs THREE tensor-core
-// products per k-step into the same fp32 TMEM accumulator:  T_hi.E_hi + T_hi.E_lo + T_lo.E_hi   (the dropped
-// T_lo.E_lo term is 2^-22 relative).  T is split once per solve, E' is split by the epilogue that produces it.
+// mantissa) does not meet.  Both operands are therefore split into two TF32-exact halves, x = hi + lo with
+// hi = rn_tf32(x) and lo = rn_tf32(x - hi), and the sweep runs THREE tensor-core products per k-step into fp32 TMEM
+// accumulators:  T_hi.E_hi  and  T_hi.E_lo + T_lo.E_hi   (the dropped T_lo.E_lo term is 2^-24 relative).  T is split
+// once per solve, E' is split by the epilogue that produces it.  See the kernel for how the accumulators are kept at
+// fp32 quality (the tensor core truncates when it accumulates).  Measured (scripts/umma_probe.py, 20 sweeps against
+// fp64): 5e-7 max relative error on the S = 948 benchmark instance, 2e-6 on dense S = 2,048; the converged diameter
+// of the S = 948 instance is 9e-7 from the fp64 fixed point.
 //
 // Layout.  T_split f32 [2][A][Sm][Sk] (part, action, state, next state; Sm = S rounded up to 128, Sk to 32, zero
 // padded): for a fixed (part, action) the 128 states of a CTA are 128 consecutive rows, so ONE 2-D TMA box {32, 128}
 // with SWIZZLE_128B lands a K-major [128][32] fp32 tile exactly as the UMMA shared-memory descriptor wants it.
 // E_split f32 [2 ping/pong][2][Kp][Sk] likewise (rows = targets).  D (TMEM): lane = state of the tile, column =
-// a*BN + target of the tile: every action accumulates into its own BN columns (A*BN <= 512), and the epilogue folds
-// min_a straight out of TMEM with tcgen05.ld -- one thread per state, 16 targets per load.
+// target of the tile; 4 * BN columns hold two hi-chain and two lo-chain accumulators (double buffering).
 //
-// Roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 = TMEM allocator + (lane 0) MMA issuer, warps 2-5 =
-// epilogue (warp w reads the TMEM lanes 32*(w%4) .. +31).  One ring of NS stages {T_hi, T_lo, E_hi, E_lo} with
-// full/empty mbarriers; tcgen05.commit releases a stage when the MMAs that read it have retired, and signals the
-// epilogue after the last one.
+// Roles (320 threads): warp 0 lane 0 = TMA producer, warp 1 = TMEM allocator + (lane 0) MMA issuer, warps 2-9 =
+// epilogue (warp w reads the TMEM lanes 32*(w%4) .. +31; the two warps of a lane quarter split the BN targets).
+// One ring of NS stages {T_hi, T_lo, E_hi, E_lo} with full/empty mbarriers (tcgen05.commit frees a stage when the
+// MMAs that read it have retired) and an accumulator ring (acc_full by tcgen05.commit, acc_empty by the epilogue warps).
+// The epilogue keeps the running sum of the action and the min over actions in registers (64 + 64 per thread), then
+// pins the target, carries converged targets forward, writes E' and its split twin and reduces max|dE| per target.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -33,7 +38,8 @@ namespace colo {
 
 constexpr int UM_BM = 128;       // states per CTA == UMMA M (cta_group::1)
 constexpr int UM_BK = 32;        // fp32 per k-block == one 128-byte swizzle row; 4 MMAs of K = 8 each
-constexpr int UM_THREADS = 192;
+constexpr int UM_EPI_WARPS = 8;   // two per TMEM lane quarter, each owning half of the tile's target columns
+constexpr int UM_THREADS = 64 + 32 * UM_EPI_WARPS;  // warp 0 TMA, warp 1 MMA + TMEM, warps 2.. epilogue
 constexpr int UM_T_TILE = UM_BM * UM_BK * 4;  // 16 KiB
 
 struct UmmaSweepArgs {
@@ -45,6 +51,7 @@ struct UmmaSweepArgs {
   const unsigned char* active;
   unsigned* resid;
   int S, A, K, Sm, Sk, Kp, in_buf;
+  int flush;           // k-blocks accumulated in TMEM before the epilogue drains them (see the kernel)
   float max_value;
   int* overflow_flag;
 };
@@ -57,6 +64,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -101,10 +111,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
 // start address >> 4 | LBO (ignored for swizzled K-major, 1) << 16 | SBO = 1024 B (8 rows) >> 4 << 32 | version 1 << 46
@@ -119,7 +129,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// x = hi + lo with both halves exactly representable in TF32: hi = x rounded to nearest TF32, lo = the remainder (exact
+// in fp32, either sign, |lo| <= 2^-11 |x|) rounded to nearest TF32.  Rounding, not truncation: the tensor core
+// truncates whatever low mantissa bits it is given, which for the always-positive operands of this sweep is a
+// one-sided error (measured: -3e-7 relative per sweep with hi = x & 0xffffe000); pre-rounded halves have nothing left
+// to truncate and their errors are two-sided (2^-24 relative).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = tf32_rn(x);
+  lo = tf32_rn(x - hi);
+}
 
 template <int BN>
 struct UmmaCfg {
@@ -127,27 +150,41 @@ struct UmmaCfg {
   static constexpr int STAGE = 2 * UM_T_TILE + 2 * E_TILE;  // 64 KiB (BN = 128) / 48 KiB (BN = 64)
   static constexpr int NS = BN == 128 ? 3 : 4;
   static constexpr int SMEM = NS * STAGE + 1024 /* alignment slack */ + 256 /* barriers, tmem pointer */;
+  static constexpr int NCOLS = 4 * BN;  // two accumulator buffers x {hi chain, lo chain} x BN columns
 };
 
+// Why the accumulators are flushed.  The tensor core adds into its fp32 accumulator with TRUNCATION (round toward
+// zero after aligning the addends), so a chain of n MMAs into one accumulator carries a bias of ~0.4 ulp(acc) per MMA,
+// always downwards for the positive sums of this sweep -- measured here: 2.3e-6 relative per sweep at S = 256 with one
+// chain of 96 MMAs, and the hitting-time fixed point amplifies a relative bias by ~max E.  Two measures keep the sweep
+// at fp32 quality: (1) the two small products (T_hi.E_lo, T_lo.E_hi: 2^-11 of the result) get their own accumulator,
+// so only the T_hi.E_hi chain truncates at full magnitude; (2) every `flush` k-blocks (4 MMAs of that chain each) the
+// epilogue warps drain the accumulators into registers with round-to-nearest adds and the next chain restarts at zero:
+// the bias is then that of `4 * flush` MMAs on a PARTIAL sum, ~1e-7 relative for flush = 1.  The accumulators are
+// double buffered in TMEM (4 * BN columns), so the drain of one group overlaps the MMAs of the next.
 template <int BN>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapE,
                     const UmmaSweepArgs p) {
   using Cfg = UmmaCfg<BN>;
   constexpr int NS = Cfg::NS;
+  constexpr int NE = UM_EPI_WARPS / 4;   // epilogue warps per TMEM lane quarter: each takes BN / NE target columns
+  constexpr int CW = BN / NE;            // columns per epilogue thread
   extern __shared__ unsigned char umma_smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)umma_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024 B
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE);
   uint64_t* empty = full + NS;
-  uint64_t* accum_full = empty + NS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* acc_full = empty + NS;   // [2] MMA -> epilogue: the group's accumulators are final
+  uint64_t* acc_empty = acc_full + 2;  // [2] epilogue -> MMA: drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   __shared__ int s_any_active;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S, A = p.A, K = p.K;
   const int k0 = blockIdx.x * BN, s0 = blockIdx.y * UM_BM;
   const int nkb = p.Sk / UM_BK;
-  const int total = A * nkb;
+  const int G = p.flush;                      // k-blocks per accumulator group
+  const int gpa = (nkb + G - 1) / G;          // groups per action
 
   // ---- a tile whose targets have all converged only carries E forward (its split twin is a function of the value)
   if (threadIdx.x == 0) s_any_active = p.active == nullptr;
@@ -163,17 +200,16 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
       if (s < S && k < K) {
         const float v = p.E_in[(size_t)k * p.e_stride + s];
         p.E_out[(size_t)k * p.e_stride + s] = v;
-        const float hi = tf32_hi(v);
+        float hi, lo;
+        tf32_split(v, hi, lo);
         p.E_split_out[(size_t)k * p.Sk + s] = hi;
-        p.E_split_out[((size_t)p.Kp + k) * p.Sk + s] = v - hi;
+        p.E_split_out[((size_t)p.Kp + k) * p.Sk + s] = lo;
       }
     }
     return;
   }
 
-  // ---- one-time setup: barriers (warp 0), TMEM columns (warp 1: a power of two >= A*BN, at least 32)
-  uint32_t ncols = 32;
-  while ((int)ncols < A * BN) ncols <<= 1;
+  // ---- one-time setup: barriers (warp 0), TMEM columns (warp 1)
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapT) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapE) : "memory");
@@ -181,10 +217,14 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
       mbar_init(full + i, 1);
       mbar_init(empty + i, 1);
     }
-    mbar_init(accum_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, UM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::NCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -195,6 +235,7 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
+      const int total = A * nkb;
       for (int it = 0; it < total; ++it) {
         const int st = it % NS;
         const uint32_t ph = (uint32_t)(it / NS) & 1u;
@@ -213,50 +254,97 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer: three TF32 products per k-step into the action's own TMEM columns =====
+    if (lane == 0) {  // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_tf32(UM_BM, BN);
-      for (int it = 0; it < total; ++it) {
-        const int st = it % NS;
-        const uint32_t ph = (uint32_t)(it / NS) & 1u;
-        mbar_wait(full + st, ph);
-        tc_fence_after();
-        const int a = it / nkb, kb = it - a * nkb;
-        const uint32_t sb = smem_u32(smem + st * Cfg::STAGE);
-        const uint64_t d_th = umma_desc_sw128(sb), d_tl = umma_desc_sw128(sb + UM_T_TILE);
-        const uint64_t d_eh = umma_desc_sw128(sb + 2 * UM_T_TILE), d_el = umma_desc_sw128(sb + 2 * UM_T_TILE + Cfg::E_TILE);
-        const uint32_t d = tmem_base + (uint32_t)(a * BN);
+      int it = 0, f = 0;
+      for (int a = 0; a < A; ++a)
+        for (int g = 0; g < gpa; ++g, ++f) {
+          const int b = f & 1;
+          mbar_wait(acc_empty + b, (((uint32_t)(f >> 1)) & 1u) ^ 1u);  // the epilogue has drained this buffer
+          tc_fence_after();
+          // TMEM columns: [0, 2BN) the hi-chain accumulators of even / odd groups, [2BN, 4BN) the lo-chain
+          // accumulators of even / odd ACTIONS (the small products keep one chain per action, see above)
+          const uint32_t d_hi = tmem_base + (uint32_t)(b * BN), d_lo = tmem_base + (uint32_t)((2 + (a & 1)) * BN);
+          const int kb_end = min(nkb, (g + 1) * G);
+          for (int kb = g * G; kb < kb_end; ++kb, ++it) {
+            const int st = it % NS;
+            const uint32_t ph = (uint32_t)(it / NS) & 1u;
+            mbar_wait(full + st, ph);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem + st * Cfg::STAGE);
+            const uint64_t d_th = umma_desc_sw128(sb), d_tl = umma_desc_sw128(sb + UM_T_TILE);
+            const uint64_t d_eh = umma_desc_sw128(sb + 2 * UM_T_TILE),
+                           d_el = umma_desc_sw128(sb + 2 * UM_T_TILE + Cfg::E_TILE);
+            const bool first = kb == g * G;
 #pragma unroll
-        for (int k = 0; k < UM_BK / 8; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);  // 8 fp32 = 32 bytes = 2 x 16-byte units of the start address
-          umma_tf32(d, d_th + adv, d_eh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_tf32(d, d_th + adv, d_el + adv, idesc, 1u);
-          umma_tf32(d, d_tl + adv, d_eh + adv, idesc, 1u);
+            for (int k = 0; k < UM_BK / 8; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);  // 8 fp32 = 32 bytes = 2 x 16-byte units of the start address
+              umma_tf32(d_hi, d_th + adv, d_eh + adv, idesc, (first && k == 0) ? 0u : 1u);
+              umma_tf32(d_lo, d_th + adv, d_el + adv, idesc, (first && g == 0 && k == 0) ? 0u : 1u);
+              umma_tf32(d_lo, d_tl + adv, d_eh + adv, idesc, 1u);
+            }
+            umma_commit(empty + st);  // the stage is free once these MMAs have read it
+          }
+          umma_commit(acc_full + b);  // this group's accumulators are final
         }
-        umma_commit(empty + st);  // the stage is free once these MMAs have read it
-      }
-      umma_commit(accum_full);    // every accumulator is final
     }
   } else {
-    // ===== epilogue: min over actions out of TMEM, pin / carry / residual, E' and its split twin =====
-    const int q = warp & 3;  // the TMEM lane quarter this warp may read
+    // ===== epilogue: drain the accumulator groups (round-to-nearest adds), min over actions, pin / carry / residual,
+    //       E' and its split twin =====
+    const int ew = warp - 2;
+    const int q = warp & 3;        // the TMEM lane quarter this warp may read
+    const int half = ew / 4;       // which CW columns of the tile
     const int s = s0 + q * 32 + lane;
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c = 0; c < BN / 16; ++c) {
-      float best[16];
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * CW);
+    float best[CW];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) best[i] = INFINITY;
-      for (int a = 0; a < A; ++a) {
-        float v[16];
-        tmem_ld16(lane_base + (uint32_t)(a * BN + c * 16), v);
+    for (int i = 0; i < CW; ++i) best[i] = INFINITY;
+    int f = 0;
+    for (int a = 0; a < A; ++a) {
+      float acc[CW];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) best[i] = fminf(best[i], 1.f + v[i]);
+      for (int i = 0; i < CW; ++i) acc[i] = 0.f;
+      for (int g = 0; g < gpa; ++g, ++f) {
+        const int b = f & 1;
+        mbar_wait(acc_full + b, ((uint32_t)(f >> 1)) & 1u);
+        tc_fence_after();
+        const uint32_t t_hi = lane_base + (uint32_t)(b * BN);
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c) {  // 2 loads in flight, one wait
+          float vh[2][16];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) tmem_ld16(t_hi + (uint32_t)(c * 32 + u * 16), vh[u]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[c * 32 + u * 16 + i] += vh[u][i];
+        }
+        if (g == gpa - 1) {  // the action's last group: its lo chain is final too (commits are cumulative)
+          const uint32_t t_lo = lane_base + (uint32_t)((2 + (a & 1)) * BN);
+#pragma unroll
+          for (int c = 0; c < CW / 32; ++c) {
+            float vl[2][16];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) tmem_ld16(t_lo + (uint32_t)(c * 32 + u * 16), vl[u]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[c * 32 + u * 16 + i] += vl[u][i];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + b);
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int k = k0 + c * 16 + i;
-        if (k >= K) break;  // warp-uniform
+      for (int i = 0; i < CW; ++i) best[i] = fminf(best[i], 1.f + acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      const int k = k0 + half * CW + i;
+      if (k < K) {  // warp-uniform
         const int tgt = __ldg(p.targets + k);
         const bool act = p.active == nullptr || p.active[k] != 0;
         float dlt = 0.f;
@@ -265,9 +353,10 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
           float nv = (s == tgt) ? 0.f : best[i];
           if (!act) nv = old;
           p.E_out[(size_t)k * p.e_stride + s] = nv;
-          const float hi = tf32_hi(nv);
+          float hi, lo;
+          tf32_split(nv, hi, lo);
           p.E_split_out[(size_t)k * p.Sk + s] = hi;
-          p.E_split_out[((size_t)p.Kp + k) * p.Sk + s] = nv - hi;
+          p.E_split_out[((size_t)p.Kp + k) * p.Sk + s] = lo;
           dlt = fabsf(nv - old);
           if (p.max_value > 0.f && nv > p.max_value && p.overflow_flag) *p.overflow_flag = 1;
         }
@@ -281,7 +370,8 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::NCOLS)
+                 : "memory");
   }
 }
 
@@ -295,9 +385,10 @@ __global__ void __launch_bounds__(256) umma_split_T_kernel(const float* __restri
     const int s = (int)(r % Sm), a = (int)(r / Sm);
     float v = 0.f;
     if (s < S && j < S) v = __ldg(T + ((size_t)s * A + a) * S + j);
-    const float hi = tf32_hi(v);
+    float hi, lo;
+    tf32_split(v, hi, lo);
     out[i] = hi;
-    out[n + i] = v - hi;
+    out[n + i] = lo;
   }
 }
 
@@ -341,19 +432,26 @@ struct UmmaPlan {
   float* T_split = nullptr;  // [2][A][Sm][Sk]
   float* E_split = nullptr;  // [2][2][Kp][Sk]
   CUtensorMap mapT, mapE;
-  int S = 0, A = 0, K = 0, Sm = 0, Sk = 0, Kp = 0, BN = 0, cur = 0;
+  int S = 0, A = 0, K = 0, Sm = 0, Sk = 0, Kp = 0, BN = 0, cur = 0, flush = 1;
 };
 
 bool hitting_umma_supported(int S, int A, int K) {
   static const bool off = getenv("COLO_NO_UMMA") != nullptr;
-  return !off && A >= 1 && A <= 8 && S >= 128 && K >= 64 && encode_tiled_fn() != nullptr;
+  return !off && A >= 1 && S >= 128 && K >= 64 && encode_tiled_fn() != nullptr;
 }
 
 int hitting_umma_plan(const float* T, int S, int A, int K, UmmaPlan** out, cudaStream_t st) {
-  COLO_ARG_CHECK(T && out && A >= 1 && A <= 8 && S >= 1 && K >= 1, "hitting_umma_plan: T, 1 <= A <= 8");
+  COLO_ARG_CHECK(T && out && A >= 1 && S >= 1 && K >= 1, "hitting_umma_plan: T, A >= 1");
   UmmaPlan* pl = new UmmaPlan();
   pl->S = S; pl->A = A; pl->K = K;
-  pl->BN = A <= 4 ? 128 : 64;
+  // tile width: 128 targets per CTA, 64 when that grid would leave SMs idle
+  pl->BN = (long long)((K + 127) / 128) * ((S + UM_BM - 1) / UM_BM) >= (long long)sm_count() ? 128 : 64;
+  {
+    const char* e = getenv("COLO_UMMA_FLUSH");  // accuracy / speed probe: k-blocks per TMEM accumulator chain
+    pl->flush = e && atoi(e) >= 1 ? atoi(e) : 1;
+    const char* bn = getenv("COLO_UMMA_BN");
+    if (bn && (atoi(bn) == 64 || atoi(bn) == 128)) pl->BN = atoi(bn);
+  }
   pl->Sm = (S + UM_BM - 1) / UM_BM * UM_BM;
   pl->Sk = (S + UM_BK - 1) / UM_BK * UM_BK;
   pl->Kp = (K + pl->BN - 1) / pl->BN * pl->BN;
@@ -397,9 +495,10 @@ __global__ void __launch_bounds__(256) umma_split_E_kernel(const float* __restri
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(i % S), k = (int)(i / S);
     const float v = E[(size_t)k * e_stride + s];
-    const float hi = tf32_hi(v);
+    float hi, lo;
+    tf32_split(v, hi, lo);
     out[(size_t)k * Sk + s] = hi;
-    out[((size_t)Kp + k) * Sk + s] = v - hi;
+    out[((size_t)Kp + k) * Sk + s] = lo;
   }
 }
 
@@ -420,6 +519,7 @@ int hitting_umma_sweep(UmmaPlan* pl, const float* E_in, float* E_out, long long 
   a.targets = targets; a.active = active; a.resid = resid;
   a.S = pl->S; a.A = pl->A; a.K = pl->K; a.Sm = pl->Sm; a.Sk = pl->Sk; a.Kp = pl->Kp; a.in_buf = pl->cur;
   a.max_value = (float)max_value; a.overflow_flag = overflow_flag;
+  a.flush = pl->flush;
   dim3 grid(pl->Kp / pl->BN, pl->Sm / UM_BM);
   if (pl->BN == 128) {
     static const cudaError_t attr = cudaFuncSetAttribute(hitting_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -445,7 +545,7 @@ extern "C" {
 int colo_hitting_umma_sweeps_f32(const float* T, const int* targets, int K, int S, int A, int n_sweeps, int zero_start,
                                  float* E, float* E_work, void* stream) {
   COLO_ARG_CHECK(T && targets && E && E_work && n_sweeps >= 0, "T, targets, E, E_work");
-  COLO_ARG_CHECK(colo::hitting_umma_supported(S, A, K), "shape not supported by the tcgen05 path (1 <= A <= 8, S >= 128, K >= 64)");
+  COLO_ARG_CHECK(colo::hitting_umma_supported(S, A, K), "shape not supported by the tcgen05 path (S >= 128, K >= 64)");
   cudaStream_t st = (cudaStream_t)stream;
   colo::UmmaPlan* pl = nullptr;
   int r = colo::hitting_umma_plan(T, S, A, K, &pl, st);

@@ -200,7 +200,7 @@ int colo_episodic_policies_f64acc(const float* T, const float* R, const float* p
  * max|dE| < eps.  Sparse rows: compressed rows, a few targets per CTA with E in shared memory, the whole solve in one
  * launch; dense T that fits a cluster's shared memory: resident solver, 4 targets per cluster; otherwise one tiled
  * GEMM launch per sweep (>= 128^2 (target, state) pairs) or one streaming backup launch per sweep.  In f32 mode with
- * A <= 8, S >= 128 and K >= 64 that GEMM runs on the tensor cores (hitting_umma.cu: tcgen05.mma kind::tf32 with both
+ * S >= 128 and K >= 64 that GEMM runs on the tensor cores (hitting_umma.cu: tcgen05.mma kind::tf32 with both
  * operands split hi + lo, three products per k-step into fp32 TMEM accumulators, TMA-fed through an mbarrier ring).
  * out_host[0] = max_k max_s E, out_host[1] = sweeps run (max over targets).  COLO_OVERFLOW if a hitting time
  * exceeds max_value (>0).  Synchronises.  work: colo_diameter_continuous_work_bytes(K,S,f64) device bytes.
@@ -226,7 +226,7 @@ int colo_diameter_continuous_f64acc(const float* T, const int* targets, int K, i
  * colo_hitting_umma_sweeps_f32 -- n_sweeps synchronous sweeps of the multi-target hitting-time iteration above through
  * the tcgen05 kernel alone (parity and throughput probe of that kernel): E f32 [K][S] is iterated in place (zeroed first
  * when zero_start != 0), E_work is a second [K][S] buffer.  COLO_ERR_ARG when the shape is outside the kernel's range
- * (1 <= A <= 8, S >= 128, K >= 64).  Does not synchronise.
+ * (S >= 128, K >= 64).  Does not synchronise.
  */
 int colo_hitting_umma_sweeps_f32(const float* T, const int* targets, int K, int S, int A, int n_sweeps, int zero_start,
                                  float* E, float* E_work, void* stream);
