@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COLO_B200_LIB") or os.path.join(_PKG, "_lib", "libcolosseum_b200.so")  # env: kernel-variant probes only
 
-OK, OVERFLOW, MAX_ITER, NEEDS_RESET, SERVER_LAPSED = 0, 1, 2, 3, 4
+OK, OVERFLOW, MAX_ITER, NEEDS_RESET, SERVER_LAPSED, BAD_ACTION = 0, 1, 2, 3, 4, 5
 FOLD_MAX, FOLD_PI, FOLD_MIN = 0, 1, 2
 STEP_FIRST, STEP_MID, STEP_LAST = 0, 1, 2
 

@@ -337,9 +337,20 @@ class BatchedMDPLoop:
                 Q, _ = dp.discounted_value_iteration(self.T, self.R)
                 self._opt_ar = markov_chain.get_average_reward(self.T, self.R, dp.get_policy_from_q_values(Q, True))
             states = ag.state.cpu().numpy()
+            cache = self.__dict__.setdefault("_ar_cache", {})  # greedy policies repeat from tick to tick and loop to loop
             for k, i in enumerate(loops):
                 pi = ag.current_optimal_stochastic_policy(i)
-                ar = markov_chain.get_average_reward(self.T, self.R, pi, [(int(states[i]), 1.0)])
+                pin = np.ascontiguousarray(pi.cpu().numpy() if hasattr(pi, "cpu") else pi)
+                # the start state matters only for multichain policies (markov_chain.recurrent_class_weights); a
+                # unichain entry is stored under start -1 and serves every start state
+                key = pin.tobytes()
+                ar = cache.get((key, -1), cache.get((key, int(states[i]))))
+                if ar is None:
+                    ar = markov_chain.get_average_reward(self.T, self.R, pi, [(int(states[i]), 1.0)])
+                    one = markov_chain.get_stationary_distribution.last_classes == 1
+                    if len(cache) > 4096:
+                        cache.clear()
+                    cache[(key, -1 if one else int(states[i]))] = ar
                 r = self._opt_ar - ar
                 out[k] = 0.0 if (np.isclose(r, 0.0, atol=1e-3) or r < 0) else r
         return out

@@ -283,7 +283,11 @@ class BatchedMDP:
         self.t += 1
         if check or not auto_reset:
             # the reference asserts `not self.necessary_reset` (base.py:1291); stepping before reset() raises too
-            if int(self.status.item()) == _cabi.NEEDS_RESET:
+            st = int(self.status.item())
+            if st == _cabi.BAD_ACTION:
+                self.status.zero_()
+                raise ValueError(f"an action outside [0, {self.tables.A}) was supplied (the env it belongs to was not stepped)")
+            if st == _cabi.NEEDS_RESET:
                 self.status.zero_()
                 if not self._was_reset:
                     raise AttributeError("step() called before reset() (reference: necessary_reset is unset)")

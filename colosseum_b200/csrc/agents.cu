@@ -137,11 +137,17 @@ __global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tab
     const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
     const int n = n0 + 1;
     cnt[idx] = n;
-    const double alpha = fmax(p.min_at, __ddiv_rn(__dadd_rn(Hd, 1.0), __dadd_rn(Hd, (double)n)));
+    // python's max(min_at, ratio) returns min_at -- a PYTHON float -- unless ratio > min_at; a python float is a weak
+    // scalar under NEP 50: times a float32 table entry it is a float32 product, where the np.float64 ratio promotes
+    const double ratio = __ddiv_rn(__dadd_rn(Hd, 1.0), __dadd_rn(Hd, (double)n));
+    const bool py_alpha = !(ratio > p.min_at);
+    const double alpha = py_alpha ? p.min_at : ratio;
     const double om = __dsub_rn(1.0, alpha);
     if (EPISODIC) {
       const float vnext = v_sp;
-      double b;
+      double b = 0.0;
+      float b32 = 0.f;
+      bool b_is_f32 = false;
       if (p.ucb_type == 0) {
         b = __dmul_rn(p.c_1, __dsqrt_rn(__ddiv_rn(__dmul_rn(H3, p.log_term), (double)n)));
       } else {
@@ -160,12 +166,23 @@ __global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tab
         const double v2 = __dmul_rn(p.c_2, __dsqrt_rn(__ddiv_rn(__dmul_rn(H3, p.log_term), (double)n)));
         const float nb = (float)(v2 < v1 ? v2 : v1);  // python min(v1, v2)
         be[idx] = nb;
-        b = __ddiv_rn(__ddiv_rn(__dsub_rn((double)nb, __dmul_rn(om, (double)old_beta)), 2.0), alpha);
+        if (py_alpha) {  // every operand is float32 or a python scalar: the whole bonus is float32 arithmetic
+          b32 = __fdiv_rn(__fdiv_rn(__fsub_rn(nb, __fmul_rn((float)om, old_beta)), 2.0f), (float)alpha);
+          b_is_f32 = true;
+        } else {
+          b = __ddiv_rn(__ddiv_rn(__dsub_rn((double)nb, __dmul_rn(om, (double)old_beta)), 2.0), alpha);
+        }
       }
       // python float + np.float32 is a float32 sum (NEP 50); the np.float64 bonus then promotes
-      const double target = __dadd_rn((double)__fadd_rn(r, vnext), b);
+      const float rv = __fadd_rn(r, vnext);
       // sic: the reference weighs the OLD estimate with alpha_t (q_learning.py:100-102)
-      Q[idx] = (float)__dadd_rn(__dmul_rn(alpha, (double)q_old), __dmul_rn(om, target));
+      if (b_is_f32) {  // float32 bonus, python-float alpha: the update never leaves float32
+        Q[idx] = __fadd_rn(__fmul_rn((float)alpha, q_old), __fmul_rn((float)om, __fadd_rn(rv, b32)));
+      } else {
+        const double target = __dadd_rn((double)rv, b);
+        const double lhs = py_alpha ? (double)__fmul_rn((float)alpha, q_old) : __dmul_rn(alpha, (double)q_old);
+        Q[idx] = (float)__dadd_rn(lhs, __dmul_rn(om, target));
+      }
       float mx = Q[row];
       for (int k = 1; k < A; ++k) mx = fmaxf(mx, Q[row + k]);
       V[(size_t)h * S + s] = fminf((float)H, mx);

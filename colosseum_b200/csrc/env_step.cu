@@ -185,7 +185,7 @@ struct Quad<double> {
 // per-env prologue shared by all step kernels: resolves uniforms/actions, handles the reset path.
 // returns true when the env takes a regular step.
 struct EnvIn {
-  int s, a, st, h;
+  int s, a, st, h, bad;
   double un64;
   float un32, ur;
 };
@@ -194,6 +194,7 @@ template <bool F32U>
 __device__ __forceinline__ EnvIn load_env(const StepIO& io, const colo_mdp_tables& tb, long long e,
                                            unsigned long long t) {
   EnvIn in;
+  in.bad = 0;
   in.st = io.step_type[e];
   in.s = io.state[e];
   in.h = io.h[e];  // needed only by the epilogue: issued here so that its (cold) latency overlaps the search
@@ -214,6 +215,11 @@ __device__ __forceinline__ EnvIn load_env(const StepIO& io, const colo_mdp_table
   }
   in.ur = io.u_rew ? io.u_rew[e] : u24(w.w[2]);
   in.a = io.random_actions ? act_from_word(w.w[3], tb.A) : (io.srv_go ? __ldcv(io.action + e) : io.action[e]);
+  if ((unsigned)in.a >= (unsigned)tb.A) {  // the reference raises on an unknown action: flag it, touch no table
+    if (io.status) *io.status = COLO_BAD_ACTION;
+    in.a = 0;
+    in.bad = 1;
+  }
   return in;
 }
 
@@ -306,11 +312,11 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
     const long long e = tile * 32 + lane;
     const bool valid = e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.bad = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
-    const bool stepping = valid && !is_last;
+    const bool stepping = valid && !is_last && !in.bad;
     if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
     // lanes that do not step still take part in the searches with a harmless row (keeps the loop branch-free)
     const int s_l = stepping ? in.s : 0, a_l = stepping ? in.a : 0;
@@ -379,11 +385,11 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
     const long long e = tile * TILE + lane;
     const bool valid = lane < TILE && e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.bad = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
-    const bool stepping = valid && !is_last;
+    const bool stepping = valid && !is_last && !in.bad;
     if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
     // lanes that do not step take part with row 0 (keeps the loop branch-free); 32-bit element offsets
     // (the host checks S*A*ld < 2^31)
@@ -471,11 +477,11 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
   for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same thread for every step of the launch
     const bool valid = e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.bad = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<F32U>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
-    const bool stepping = valid && !is_last;
+    const bool stepping = valid && !is_last && !in.bad;
     if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
     int nxt = 0, cls = 0;
     if (stepping) {
@@ -574,11 +580,11 @@ __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_
   for (int step = 0; step < io.n_steps; ++step) {  // an env is owned by the same thread for every step of the launch
     const bool valid = e < io.N;
     EnvIn in;
-    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
+    in.s = 0; in.a = 0; in.st = COLO_STEP_MID; in.h = 0; in.bad = 0; in.un64 = 0.0; in.un32 = 0.f; in.ur = 0.f;
     if (valid) in = load_env<false>(io, tb, e, t_pass + step);
     const bool is_last = valid && in.st == COLO_STEP_LAST;
     const bool resetting = is_last && io.auto_reset;
-    const bool stepping = valid && !is_last;
+    const bool stepping = valid && !is_last && !in.bad;
     if (is_last && !io.auto_reset && io.status) *io.status = COLO_NEEDS_RESET;
     int nxt = 0, cls = 0;
     if (stepping) {

@@ -15,13 +15,19 @@
 
 namespace colo {
 
+// Philox stream separation: every consumer of the caller's `seed` keys its blocks with its own constant, so that no
+// (key, counter) pair is shared with the interaction kernels -- the env step draws with key = seed and counter (env
+// index, step), the agents with key = seed ^ 0x9E3779B97F4A7C15 (agents.cu) -- nor between the gamma body, the
+// alpha < 1 boost, the NIG draws and the emission noise (callers fold their own constant into `seed` on top).
+constexpr uint64_t kGammaBodyKey = 0xA0761D6478BD642FULL, kGammaBoostKey = 0xE7037ED1A0B428DBULL;
+
 __device__ __forceinline__ double gamma_draw(double alpha, uint64_t seed, uint64_t elem, uint64_t t) {
   if (!(alpha > 0.0)) return 0.0;
   const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
   const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
   double g = 0.0;
   for (uint64_t attempt = 0; attempt < 64; ++attempt) {
-    const Philox4 w = philox4x32_10(seed, elem, (t << 8) | attempt);
+    const Philox4 w = philox4x32_10(seed ^ kGammaBodyKey, elem, (t << 8) | attempt);
     // Box-Muller normal from two 53/32-bit uniforms, one more uniform for the squeeze test
     const double u1 = (u53(w.w[0], w.w[1]) + 1.1102230246251565e-16), u2 = (double)w.w[2] * (1.0 / 4294967296.0);
     const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
@@ -35,7 +41,7 @@ __device__ __forceinline__ double gamma_draw(double alpha, uint64_t seed, uint64
     }
   }
   if (alpha < 1.0) {  // gamma(alpha) = gamma(alpha + 1) * U^(1/alpha)
-    const Philox4 w = philox4x32_10(seed ^ 0x9E3779B97F4A7C15ULL, elem, t);
+    const Philox4 w = philox4x32_10(seed ^ kGammaBoostKey, elem, t);
     const double u = u53(w.w[0], w.w[1]) + 1.1102230246251565e-16;
     g *= pow(u, 1.0 / alpha);
   }
@@ -52,7 +58,7 @@ __device__ __forceinline__ float gamma_draw_fast(float alpha, uint64_t seed, uin
   const float a = alpha < 1.f ? alpha + 1.f : alpha;
   const float d = a - (1.f / 3.f), c = rsqrtf(9.f * d);
   for (uint64_t attempt = 0; attempt < 64; ++attempt) {
-    const Philox4 w = philox4x32_10(seed, elem, (t << 8) | attempt);
+    const Philox4 w = philox4x32_10(seed ^ kGammaBodyKey, elem, (t << 8) | attempt);
     const float u1 = ((float)(w.w[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u2 = (float)w.w[1] * (1.0f / 4294967296.0f);
     const float x = sqrtf(-2.f * __logf(u1)) * cospif(2.f * u2);

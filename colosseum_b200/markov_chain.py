@@ -5,9 +5,10 @@ behind `BaseMDP.{optimal,worst,random}_average_reward` (mdp/base.py:895-941) and
 
 The reference finds the recurrent classes with networkx and solves each with GTH elimination / ARPACK.  Here the
 chain of the policy is built in one pass over T and its stationary distribution is the limit of the START distribution
-under the lazy chain (I + P)/2, computed on the GPU by repeated squaring in fp64: identical to the reference whenever
-the policy's chain has a single recurrent class, and weighted by absorption probabilities -- instead of the
-reference's first-reachable-class rule (:113-126) -- when it has several."""
+under the lazy chain (I + P)/2, computed on the GPU by repeated squaring in fp64.  Which start vector: the
+reference's own rule, restated on the host with the same networkx calls -- one recurrent class: that class's
+stationary distribution whatever the start; several: every start state's whole mass goes to the FIRST class (in
+networkx's attracting-component order) it can reach (:113-126)."""
 import ctypes as C
 
 import numpy as np
@@ -42,22 +43,48 @@ def get_transition_probabilities(T, policy):
     return _result(P, not _is_tensor(T))
 
 
-def get_stationary_distribution(tps, starting_states_and_probs=None, sparse_threshold_size=None, *, tol=1e-13,
+def recurrent_class_weights(tps_host, starting_states_and_probs, sparse_threshold_size=500 * 500):
+    """The reference's treatment of multichain policies, restated on the host (markov_chain.py:90-133): the recurrent
+    classes are networkx's attracting components of the chain's graph, in networkx's order; with ONE class the start
+    distribution is irrelevant; with several, each start state's WHOLE mass goes to the first class (in that order) it
+    can reach.  Returns the start vector x0 f64[S] that encodes those weights as mass on one representative state of
+    each class -- started inside a closed class the chain never leaves it, so lim x0 L^n = sum_c w_c pi_c."""
+    import networkx as nx
+
+    S = len(tps_host)
+    if tps_host.size > sparse_threshold_size:
+        from scipy.sparse import coo_matrix
+
+        G = nx.DiGraph(coo_matrix(tps_host))
+    else:
+        G = nx.DiGraph(tps_host)
+    classes = list(map(tuple, nx.attracting_components(G)))
+    x0 = np.zeros(S, np.float64)
+    if len(classes) == 1:
+        x0[classes[0][0]] = 1.0
+        return x0, 1
+    for ss, p in starting_states_and_probs:  # None raises TypeError here, as in the reference
+        for c in classes:
+            if nx.has_path(G, int(ss), c[0]):
+                x0[c[0]] += float(p)
+                break
+    return x0, len(classes)
+
+
+def get_stationary_distribution(tps, starting_states_and_probs=None, sparse_threshold_size=500 * 500, *, tol=1e-13,
                                 max_squarings=200):
-    """markov_chain.py:64-137.  `starting_states_and_probs`: iterable of (state index, probability); None = uniform.
-    Limit of the start distribution under the lazy chain by repeated squaring in fp64 (robust for nearly reducible
-    chains)."""
+    """markov_chain.py:64-137.  `starting_states_and_probs`: iterable of (state index, probability), needed (as in the
+    reference) only when the chain has several recurrent classes.  The class structure and the reference's
+    first-reachable-class rule are resolved on the host (`recurrent_class_weights`); the stationary distributions
+    themselves are the limit of the resulting start vector under the lazy chain (I + P)/2, computed on the GPU by
+    repeated squaring in fp64 (robust for nearly reducible chains)."""
     torch = _torch()
     as_numpy = not _is_tensor(tps)
     P = to_device(tps)
     S = int(P.shape[0])
-    x0 = np.zeros(S, np.float64)
-    if starting_states_and_probs is None:
-        x0[:] = 1.0 / S
-    else:
-        for s, p in starting_states_and_probs:
-            x0[int(s)] += float(p)
-        x0 /= x0.sum()
+    host = np.asarray(tps) if as_numpy else P.cpu().numpy()
+    x0, n_classes = recurrent_class_weights(host, starting_states_and_probs, sparse_threshold_size or 500 * 500)
+    get_stationary_distribution.last_classes = n_classes
     x0d = torch.from_numpy(x0).cuda()
     lib = _cabi.lib()
     x = torch.empty(S, dtype=torch.float64, device="cuda")
@@ -95,6 +122,7 @@ def power_iteration(tps, x0, tol=1e-10, max_iter=int(1e6)):
 
 
 get_stationary_distribution.last_iterations = 0
+get_stationary_distribution.last_classes = 0
 
 
 def get_average_reward(T, R, policy, next_states_and_probs=None, sparse_threshold_size=None, *, tol=1e-13):

@@ -34,6 +34,7 @@ extern "C" {
 #define COLO_MAX_ITER 2
 #define COLO_NEEDS_RESET 3
 #define COLO_SERVER_LAPSED 4
+#define COLO_BAD_ACTION 5 /* a supplied action outside [0, A): flagged in colo_env_batch.status, the env is not stepped */
 #define COLO_ERR_CUDA (-1)
 #define COLO_ERR_ARG (-2)
 
@@ -422,7 +423,8 @@ typedef struct {
  * Visitation counters (u64, or NULL): `visits_copies` (a power of two >= 1) privatised copies laid out as
  * visits_s[copy][S] and visits_sa[copy][S*A]; a block adds to copy (blockIdx & (copies-1)) so that 65,536 envs
  * sitting on a handful of states do not serialise on a handful of L2 atomics -- the count is the sum over copies.
- * status: device int (may be NULL), set to COLO_NEEDS_RESET if an env needed a reset without auto_reset.
+ * status: device int (may be NULL), set to COLO_NEEDS_RESET if an env needed a reset without auto_reset, to
+ * COLO_BAD_ACTION if a supplied action was outside [0, A) (that env keeps its state: the reference raises there).
  * Zero-copy host I/O: `action` is only read and `reward` / `obs` are only written by the kernels, so each of them may
  * be a PINNED HOST buffer (cudaHostAlloc memory is mapped into the device's address space under unified addressing):
  * the kernel then pulls the actions and pushes the TimeStep fields over PCIe itself, lane-coalesced, and an

@@ -837,11 +837,17 @@ int orc_qlearning_steps(const orc_tables* tb, const orc_qlearning_args* p, int e
       const int n = cnt[idx] + 1;
       cnt[idx] = n;
       double alpha = (Hd + 1.0) / (Hd + (double)n);
-      if (p->min_at > alpha) alpha = p->min_at;
+      /* python's max(min_at, ratio) returns min_at -- a PYTHON float -- unless ratio > min_at.  A python float is a
+       * weak scalar under NEP 50: multiplied with a float32 table entry it is rounded to float32 and the product is
+       * a float32 one, where the np.float64 ratio promotes to float64 (q_learning.py:66, :92-102). */
+      const int py_alpha = !(alpha > p->min_at);
+      if (py_alpha) alpha = p->min_at;
       const double om = 1.0 - alpha;
       if (episodic) {
         const float vnext = V[(size_t)hh * S + sp];
-        double b;
+        double b = 0.0;
+        float b32 = 0.f;
+        int b_is_f32 = 0;
         if (p->ucb_type == 0) {
           b = p->c_1 * sqrt(H3 * p->log_term / (double)n);
         } else {
@@ -860,12 +866,28 @@ int orc_qlearning_steps(const orc_tables* tb, const orc_qlearning_args* p, int e
           const double v2 = p->c_2 * sqrt(H3 * p->log_term / (double)n);
           const float nb = (float)(v2 < v1 ? v2 : v1);
           be[idx] = nb;
-          b = ((double)nb - om * (double)old_beta) / 2.0 / alpha;
+          if (py_alpha) { /* every operand is float32 or a python scalar: the whole bonus is float32 arithmetic */
+            const float t1 = (float)om * old_beta;
+            const float t2 = nb - t1;
+            const float t3 = t2 / 2.0f;
+            b32 = t3 / (float)alpha;
+            b_is_f32 = 1;
+          } else {
+            b = ((double)nb - om * (double)old_beta) / 2.0 / alpha;
+          }
         }
         /* python float + np.float32 is a float32 sum under NEP 50; the np.float64 bonus then promotes */
         const float rv = r + vnext;
-        const double target = (double)rv + b;
-        Q[idx] = (float)(alpha * (double)Q[idx] + om * target); /* sic: alpha weighs the old estimate */
+        if (b_is_f32) { /* float32 bonus, python-float alpha: the update never leaves float32 */
+          const float target32 = rv + b32;
+          const float lhs = (float)alpha * Q[idx];
+          const float rhs = (float)om * target32;
+          Q[idx] = lhs + rhs;
+        } else {
+          const double target = (double)rv + b;
+          const double lhs = py_alpha ? (double)((float)alpha * Q[idx]) : alpha * (double)Q[idx];
+          Q[idx] = (float)(lhs + om * target); /* sic: alpha weighs the old estimate */
+        }
         float mx = Q[row];
         for (int k = 1; k < A; ++k)
           if (Q[row + k] > mx) mx = Q[row + k];

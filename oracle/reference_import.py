@@ -14,7 +14,13 @@ import os
 import sys
 import types
 
+# /root/reference in the build container; on the GPU box (where that path does not exist) the same UNMODIFIED package
+# as installed once by `pip install --no-index --no-deps --target baseline/_ref /root/reference` (git-ignored, travels
+# with the gpurun snapshot) -- used only by the live drop-in test tests/test_gpu_dropin_live.py
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFERENCE_ROOT = os.environ.get("COLOSSEUM_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "colosseum")) and os.path.isdir(os.path.join(_REPO, "baseline", "_ref", "colosseum")):
+    REFERENCE_ROOT = os.path.join(_REPO, "baseline", "_ref")
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
 
 

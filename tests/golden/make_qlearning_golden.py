@@ -28,6 +28,10 @@ CASES = [  # name, instance, kwargs of oracle.QLearningLoops
     ("epi_hoeffding", "c1_riverswim_epi", dict(optimization_horizon=2000, p=0.05, c_1=0.7, min_at=0.0, UCB_type="hoeffding")),
     ("epi_bernstein", "frozenlake4_epi", dict(optimization_horizon=3000, p=0.05, c_1=0.4, c_2=0.9, min_at=0.05, UCB_type="bernstein")),
     ("epi_bernstein_taxi", "taxi_epi", dict(optimization_horizon=3000, p=0.05, c_1=1.0, c_2=0.3, min_at=0.0, UCB_type="bernstein", epsilon_greedy=0.1)),
+    # min_at large enough to win python's max() from the first visits on: alpha_t is then a PYTHON float and the
+    # update runs in float32 (NEP 50) -- q_learning.py:66, :92-102
+    ("epi_hoeffding_minat", "c1_riverswim_epi", dict(optimization_horizon=2000, p=0.05, c_1=0.7, min_at=0.5, UCB_type="hoeffding")),
+    ("epi_bernstein_minat", "frozenlake4_epi", dict(optimization_horizon=3000, p=0.05, c_1=0.4, c_2=0.9, min_at=0.4, UCB_type="bernstein")),
     ("cont", "frozenlakecontinuous_ergo0", dict(optimization_horizon=5000, min_at=0.02, confidence=0.95, span_approx_weight=0.6, h_weight=0.8)),
     ("cont_taxi", "taxicontinuous_ergo0", dict(optimization_horizon=4000, min_at=0.0, confidence=0.9, span_approx_weight=1.0, h_weight=1.0, epsilon_greedy=0.05)),
 ]

@@ -20,6 +20,7 @@ def g():
 def test_average_reward_against_reference(g):
     import colosseum_b200.markov_chain as mc
 
+    multi = 0
     for name in g["names"]:
         T, R = g[f"{name}_T"], g[f"{name}_R"]
         starts = list(zip(g[f"{name}_start_idx"].tolist(), g[f"{name}_start_prob"].tolist()))
@@ -32,19 +33,20 @@ def test_average_reward_against_reference(g):
             Po, ro = orc.policy_chain(T, R, pi)
             x0 = np.zeros(len(T)); x0[g[f"{name}_start_idx"]] = g[f"{name}_start_prob"]
             sd = mc.get_stationary_distribution(tps, starts)
-            sd_o = orc.stationary_distribution_f64(Po, x0)
+            n_cls = mc.get_stationary_distribution.last_classes
+            multi += n_cls > 1
+            # the start vector the reference's class rule yields (host logic), then the oracle's fp64 limit of it
+            x0r, _ = mc.recurrent_class_weights(tps, starts)
+            sd_o = orc.stationary_distribution_f64(Po, x0r)
             assert abs(sd.sum() - 1) < 1e-9 and sd.min() > -1e-15
             np.testing.assert_allclose(sd, sd_o, atol=2e-8)
             ar = mc.get_average_reward(T, R, pi, starts)
             assert abs(ar - float((sd_o * ro).sum())) < 1e-8
-            # the reference (networkx recurrent classes + GTH, partly float32): identical when the chain has ONE
-            # recurrent class; with several the reference assigns each start state to the first class it can reach
-            ref_sd = g[f"{name}_{k}_sd"]
-            one_class = np.abs(ref_sd - sd_o).max() < 1e-5
-            if one_class:
-                assert abs(ar - float(g[f"{name}_{k}_ar"])) < 2e-6 * max(1.0, abs(ar)), (name, k)
-            else:
-                assert k == "worst", (name, k)  # only adversarial policies split the chain
+            # ... and the reference's own output (networkx recurrent classes + GTH, partly float32), including the
+            # multichain policies where it assigns each start state's mass to the first class it can reach
+            np.testing.assert_allclose(sd, g[f"{name}_{k}_sd"], atol=2e-5, err_msg=f"{name} {k} ({n_cls} classes)")
+            assert abs(ar - float(g[f"{name}_{k}_ar"])) < 2e-6 * max(1.0, abs(ar)), (name, k)
+    assert multi > 0  # the fixture holds multichain policies (adversarial "worst" policies split the chain)
 
 
 def test_notebook_average_rewards(g):
@@ -118,3 +120,18 @@ def test_undiscounted_value_norm(g):
         exp = np.sqrt(np.einsum("iaj,ja->ia", T64, (h.reshape(-1, 1) - Eh) ** 2)).max()
         assert abs(got - exp) < 1e-9 * max(1.0, exp), (name, got, exp)
         assert abs(got - float(g[f"{name}_undisc_norm"])) < 2e-2 * max(1.0, exp), (name, got, float(g[f"{name}_undisc_norm"]))
+
+
+def test_multichain_policies_follow_the_reference_rule():
+    """chains with several recurrent classes (tests/golden/multichain.npz, recorded from the reference's own
+    get_stationary_distribution): each start state's whole mass goes to the first attracting component it can reach"""
+    import colosseum_b200.markov_chain as mc
+
+    g = np.load(os.path.join(GOLDEN, "multichain.npz"))
+    for name in g["names"]:
+        starts = list(zip(g[f"{name}_start_idx"].tolist(), g[f"{name}_start_prob"].tolist()))
+        sd = mc.get_stationary_distribution(g[f"{name}_tps"], starts)
+        assert mc.get_stationary_distribution.last_classes > 1
+        np.testing.assert_allclose(sd, g[f"{name}_sd"], atol=2e-6, err_msg=str(name))
+    with pytest.raises(TypeError):  # the reference needs the start distribution for a multichain policy
+        mc.get_stationary_distribution(g["two_classes_tps"], None)

@@ -590,3 +590,21 @@ def test_discount_written_by_the_kernel(bm):
             assert (d[st == 1] == 1.0).all() and (d[st == 2] == 0.0).all() and np.isnan(d[st == 0]).all()
             seen |= set(st.tolist())
         assert seen == {0, 1, 2}
+
+
+@pytest.mark.parametrize("mode", ["dense_f32", "succ"])
+def test_out_of_range_action_is_flagged(bm, mode):
+    """the reference raises on an unknown action; the batched step flags COLO_BAD_ACTION, leaves that env untouched
+    and steps the others"""
+    g = load_instance("doc_simplegrid4")
+    tb = MDPTables.from_golden(g)
+    env = bm.BatchedMDP(tb, 64, mode=mode, seed=1)
+    env.reset()
+    before = env.state.cpu().numpy().copy()
+    a = np.zeros(64, np.int32)
+    a[5], a[40] = tb.A, -1
+    with pytest.raises(ValueError):
+        env.step(a)
+    after = env.state.cpu().numpy()
+    assert after[5] == before[5] and after[40] == before[40] and int(env.h[5]) == 0 and int(env.h[6]) == 1
+    env.step(np.zeros(64, np.int32))  # the flag was cleared: the batch goes on
