@@ -46,7 +46,7 @@ def test_average_reward_against_reference(g):
             # multichain policies where it assigns each start state's mass to the first class it can reach
             np.testing.assert_allclose(sd, g[f"{name}_{k}_sd"], atol=2e-5, err_msg=f"{name} {k} ({n_cls} classes)")
             assert abs(ar - float(g[f"{name}_{k}_ar"])) < 2e-6 * max(1.0, abs(ar)), (name, k)
-    assert multi > 0  # the fixture holds multichain policies (adversarial "worst" policies split the chain)
+    assert multi == 0  # every policy of this fixture is unichain; multichain ones: tests/golden/multichain.npz below
 
 
 def test_notebook_average_rewards(g):

@@ -26,7 +26,11 @@ def test_dirichlet_rows_distribution(fast):
         marg = scipy.stats.beta(float(alpha[j]), a0 - float(alpha[j]))  # Dirichlet marginals are Beta
         x = T[:, j].astype(np.float64)
         assert abs(x.mean() - marg.mean()) < 6 * marg.std() / np.sqrt(n) + 1e-6, j
-        assert abs(x.var() - marg.var()) < 0.05 * marg.var() + 1e-9, j
+        # standard error of a sample variance: var * sqrt((kurtosis - 1) / n) -- large for the heavy-tailed alpha << 1
+        # components (Beta(0.05, .): kurtosis > 100), so the bound is 5 standard errors where that exceeds 5 %
+        kurt = float(marg.stats(moments="k")) + 3.0
+        se = marg.var() * np.sqrt(max(kurt - 1.0, 2.0) / n)
+        assert abs(x.var() - marg.var()) < max(0.05 * marg.var(), 5 * se) + 1e-9, j
         if alpha[j] >= 0.5:
             assert scipy.stats.kstest(x, marg.cdf).pvalue > 1e-4, j
     # same numpy recipe as the reference, same moments
