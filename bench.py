@@ -646,42 +646,80 @@ def bench_c5_gpu(args, rank, world):
 
 
 def bench_c3_gpu(args, rank, world):
-    """C3: the reference's benchmark MDP instances (80 gin parameter sets of the seven families, seed 0, cycled to
-    `--c3-instances`), sharded over the ranks by instance, no communication.  Per instance: `--c3-envs` parallel
-    episodes x `--c3-steps` random-agent steps through the step kernel, then diameter + value norm + gaps."""
+    """C3: the reference's benchmark MDP instances (gin parameter sets of the seven families x seeds 0..10 in the
+    order of SURVEY section 8d, cycled to `--c3-instances`), sharded over the ranks by instance, no communication.  Per
+    instance: `--c3-envs` parallel episodes x `--c3-steps` random-agent steps through the step kernel, then diameter +
+    value norm + gaps.  Runner: colo_suite_run (C++ worker threads, one stream each) or the Python path."""
     import torch
 
     from colosseum_b200 import _cabi
     from colosseum_b200.sharded import shard_range
-    from colosseum_b200.suite import load_suite, run_instance
+    from colosseum_b200.suite import load_suite_all, run_instance, run_many, run_many_native, suite_size
 
-    suite = load_suite(os.path.join(ROOT, "tests", "golden", "c3_suite.npz"))
+    gdir = os.path.join(ROOT, "tests", "golden")
+    n_suite = suite_size(gdir)
     B = args.c3_instances
     i0, i1 = shard_range(B, rank, world)
     lib = _cabi.lib()
-    run_instance(suite[1], n_envs=args.c3_envs, n_steps=10, seed=0, precision=args.c3_precision)  # warm-up
+    mine = load_suite_all(gdir, indices=sorted({i % n_suite for i in range(i0, i1)}))
+    by_index = dict(zip(sorted({i % n_suite for i in range(i0, i1)}), mine))
+    work = [(by_index[i % n_suite], 0) for i in range(i0, i1)]
+    suite = mine
+    workers = args.c3_workers or max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))
+    native = args.c3_runner == "native" and args.c3_precision == "f64"
+    if native:
+        run_many_native(work[:2], n_workers=2, n_envs=args.c3_envs, n_steps=10)  # warm-up
+    else:
+        run_instance(suite[0], n_envs=args.c3_envs, n_steps=10, seed=0, precision=args.c3_precision)
     barrier_sync(world)
     lib.colo_reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
     e0.record()
-    from colosseum_b200.suite import run_many
-
-    work = [(suite[i % len(suite)], i) for i in range(i0, i1)]
-    results = run_many(work, n_workers=args.c3_workers, n_envs=args.c3_envs, n_steps=args.c3_steps,
-                       precision=args.c3_precision)
+    if native:
+        results = run_many_native(work, n_workers=workers, n_envs=args.c3_envs, n_steps=args.c3_steps)
+    else:
+        results = run_many(work, n_workers=workers, n_envs=args.c3_envs, n_steps=args.c3_steps,
+                           precision=args.c3_precision)
+    e1.record()
+    e1.synchronize()
+    wall_ms = (time.perf_counter() - w0) * 1e3
     step_s = hard_s = 0.0
     worst = (0.0, "")
+    # parity: every instance against the answers the unmodified reference recorded for it (NaN = not recorded): its own
+    # diameter / value norm / gaps, or the values of its shipped hardness cache (continuous classes)
+    bad, checked = [], 0
     for (inst, _), (res, tm) in zip(work, results):
         step_s += tm["step_s"]
         hard_s += tm["hardness_s"]
         if tm["hardness_s"] > worst[0]:
             worst = (tm["hardness_s"], inst.name)
         assert res["gaps"] > 0 and res["diameter"] > 0 and res["visits_total"] == args.c3_envs * (args.c3_steps + 1)
-    e1.record()
+        for k, ref_k, tol in (("diameter", "diameter", 2e-3), ("diameter", "cached_diameter", 2e-3),
+                              ("value_norm", "value_norm", 3e-3), ("value_norm", "cached_value_norm", 3e-3),
+                              ("gaps", "gaps", 7e-3)):
+            ref = inst.ref.get(ref_k, float("nan"))
+            if ref == ref and res[k] == res[k]:
+                checked += 1
+                if abs(res[k] - ref) > tol * max(abs(ref), 1e-3):
+                    bad.append((inst.name, ref_k, res[k], ref))
     barrier_sync(world)
-    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms), world)
+    ok = len(bad) == 0
+    if world > 1:
+        import torch.distributed as dist
+
+        t_ok = torch.tensor([1 if ok else 0, checked], device="cuda")
+        dist.all_reduce(t_ok[:1], op=dist.ReduceOp.MIN)
+        dist.all_reduce(t_ok[1:], op=dist.ReduceOp.SUM)
+        ok, checked = bool(t_ok[0].item()), int(t_ok[1].item())
+    if bad:
+        print(f"[bench] C3 parity failures on rank {rank}: {bad[:5]}", file=sys.stderr)
     return dict(B=B, per_rank=i1 - i0, ms=ms, launches=int(lib.colo_launch_count()), step_s=step_s, hard_s=hard_s,
-                worst=worst, n_suite=len(suite))
+                worst=worst, n_suite=n_suite, workers=workers, runner="native (colo_suite_run)" if native else "python",
+                parity_ok=ok,
+                parity_what=f"{checked} recorded reference answers (diameter 2e-3, value norm 3e-3, gaps 7e-3 relative: "
+                            "the reference stops early at eps = 1e-3, DESIGN section 2) checked over all ranks")
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -844,7 +882,9 @@ def main():
     ap.add_argument("--c3-envs", type=int, default=1024)
     ap.add_argument("--c3-steps", type=int, default=1000)
     ap.add_argument("--c3-precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--c3-workers", type=int, default=4, help="host threads (one CUDA stream each) per GPU for the C3 leg")
+    ap.add_argument("--c3-workers", type=int, default=0,
+                    help="host threads (one CUDA stream each) per GPU for the C3 leg (default min(8, cores / GPUs))")
+    ap.add_argument("--c3-runner", default="native", choices=["native", "python"])
     ap.add_argument("--vi-batch", type=int, default=0, help="MDP instances per GPU for the C4 leg (default 4096/g)")
     ap.add_argument("--c5-states", type=int, default=40000, help="S of the row-sharded single MDP (C5: 40,000)")
     ap.add_argument("--c5-transport", default="fused", choices=["fused", "nccl"])
@@ -902,11 +942,12 @@ def main():
             "metric": "benchmark-suite MDP instances/sec (batched step + hardness measures)", "value": c3["B"] / sec,
             "unit": "instances/s", "steps": c3["B"], "ms_per_step": 1e3 * sec / c3["B"], "scaling": "strong",
             "gpu_launches": c3["launches"], "dtype": args.c3_precision, "timed_region_s": sec,
-            "config": {"workload": f"C3: {c3['B']} MDP instances drawn from the reference's {c3['n_suite']} benchmark "
-                                   f"instances (gin parameter sets of the 7 families, continuous + episodic, x seeds; "
-                                   f"tests/golden/c3_suite.npz) in order, cycled, {c3['per_rank']} per GPU; per "
+            "config": {"workload": f"C3: {c3['B']} MDP instances = the first {c3['B']} of the reference's {c3['n_suite']} "
+                                   f"benchmark instances (the gin parameter sets of the 7 families, continuous + episodic, "
+                                   f"x seeds 0..10, seed-major; tests/golden/c3_suite*.npz), {c3['per_rank']} per GPU; per "
                                    f"instance {args.c3_envs} envs x {args.c3_steps} random-agent steps, then diameter + "
-                                   "value norm + sub-optimality gaps (MiniGrid DoorKey is not in the reference)",
+                                   "value norm + sub-optimality gaps (MiniGrid DoorKey is not in the reference); "
+                                   f"runner: {c3['runner']}, {c3['workers']} worker threads per GPU",
                        "rank0_seconds": {"step_phase": c3["step_s"], "hardness_phase": c3["hard_s"],
                                          "slowest_instance": c3["worst"][1], "slowest_hardness_s": c3["worst"][0]}},
             "env_steps_per_s_step_phase": c3["per_rank"] * args.c3_envs * args.c3_steps / max(c3["step_s"], 1e-9) * world,

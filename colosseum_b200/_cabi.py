@@ -114,6 +114,35 @@ class PsrlArgs(C.Structure):
     ]
 
 
+class SuiteInstance(C.Structure):
+    """mirror of `colo_suite_instance` (HOST pointers)"""
+
+    _fields_ = [
+        ("S", C.c_int), ("A", C.c_int), ("H", C.c_int), ("K", C.c_int),
+        ("T", C.c_void_p), ("R", C.c_void_p), ("succ_cum", C.c_void_p), ("succ_idx", C.c_void_p),
+        ("succ_len", C.c_void_p), ("rew_cls_succ", C.c_void_p), ("rew_q", C.c_void_p),
+        ("n_cls", C.c_int), ("nq", C.c_int), ("rmin", C.c_float), ("rmax", C.c_float),
+        ("start_idx", C.c_void_p), ("start_cum", C.c_void_p), ("start_prob", C.c_void_p), ("n_start", C.c_int),
+        ("node_h", C.c_void_p), ("node_s", C.c_void_p), ("n_nodes", C.c_int), ("deterministic", C.c_int),
+    ]
+
+
+class SuiteConfig(C.Structure):
+    """mirror of `colo_suite_config`"""
+
+    _fields_ = [("n_envs", C.c_longlong), ("n_steps", C.c_int), ("seed", C.c_ulonglong), ("eps", C.c_double),
+                ("max_cf_bytes", C.c_size_t), ("diameter", C.c_int)]
+
+
+class SuiteResult(C.Structure):
+    """mirror of `colo_suite_result`"""
+
+    _fields_ = [("status", C.c_int), ("visits_total", C.c_double), ("mean_reward_last_step", C.c_double),
+                ("gaps", C.c_double), ("value_norm", C.c_double), ("diameter", C.c_double),
+                ("diameter_sweeps", C.c_double), ("step_s", C.c_double), ("hardness_s", C.c_double),
+                ("error", C.c_char * 160)]
+
+
 _P = C.c_void_p
 _LL = C.c_longlong
 _ULL = C.c_ulonglong
@@ -138,6 +167,9 @@ PROTOTYPES = {
     "colo_solve_discounted_f64acc": (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _LL, _I, _P, _P, _P, _P, _P]),
     "colo_solve_discounted_gs_f32": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _LL, _I, _P, _P, _P, _P, _P]),
     "colo_solve_discounted_gs_f64acc": (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _LL, _I, _P, _P, _P, _P, _P]),
+    "colo_suite_run": (_I, [C.POINTER(SuiteInstance), _I, C.POINTER(SuiteConfig), C.POINTER(SuiteResult), _I]),
+    "colo_continuous_form_values_f32": (_I, [_P, _P, _I, _I, _I, _D, _P, _P, _P, _I, _D, _I, _P, C.POINTER(C.c_double), _P]),
+    "colo_continuous_form_values_f64acc": (_I, [_P, _P, _I, _I, _I, _D, _P, _P, _P, _I, _D, _I, _P, C.POINTER(C.c_double), _P]),
     "colo_hitting_umma_sweeps_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "colo_episodic_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
     "colo_episodic_policies_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),

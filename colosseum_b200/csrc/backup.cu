@@ -814,6 +814,102 @@ int episodic(const float* T, const float* R, const float* pi, int B, int S, int 
   return COLO_OK;
 }
 
+// ---- optimal values of the CONTINUOUS FORM of an episodic MDP, from its structure ----------------------------------
+// mdp/utils/mdp_creation.py:131-176 builds, over the reachable (h, s) nodes, the chain  (h,s) --T[s,a,:]--> (h+1,.)  for
+// h < H-1, and for the last layer ONE row for every action: probability p_k on the column whose INDEX is the original
+// state index of start state k (sic, :168 -- i.e. the node that happens to sit at that position of the node list).
+// mdp/base_finite.py:167-178 then runs discounted_value_iteration on that n x A x n tensor: thousands of sweeps over
+// thousands of nodes (gamma = 0.99 -> 2,062 sweeps to 1e-9), the largest single cost of the C3 hardness phase.
+// The structure makes the fixed point a SCALAR one.  With c = sum_k p_k V[node at position start_k]:
+//     V[H-1, s] = max_a R[s,a] + gamma * c              V[h, s] = max_a R[s,a] + gamma * sum_j T[s,a,j] V[h+1, j]
+// so one backward induction over the ORIGINAL T (H launches of the backup kernel, never the n x A x n tensor) maps c to
+// F(c) = sum_k p_k V[pos_k]; F is increasing, convex, piecewise linear and a contraction (every path back to a start
+// position takes at least one step: slope <= gamma).  c* = F(c*) by safeguarded secant steps; the values at c* are the
+// fixed point of the reference's iteration (same equations, rows of T_cf = rows of T).  Unreachable (h, s) pairs are
+// computed too and ignored: reachable nodes only lead to reachable nodes.
+template <typename TV>
+__global__ void cf_last_layer_kernel(const float* __restrict__ R, int S, int A, double gamma_c, TV* __restrict__ V_last) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  TV best = (TV)__ldg(R + (size_t)s * A);
+  for (int a = 1; a < A; ++a) {
+    const TV r = (TV)__ldg(R + (size_t)s * A + a);
+    best = r > best ? r : best;
+  }
+  V_last[s] = best + (TV)gamma_c;
+}
+
+template <typename TV>
+__global__ void cf_start_value_kernel(const TV* __restrict__ V, const int* __restrict__ pos_h, const int* __restrict__ pos_s,
+                                      const float* __restrict__ p, int n, int S, double* __restrict__ c_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double c = 0.0;  // fixed order, float32 probabilities as stored in the reference's T_cf row
+  for (int k = 0; k < n; ++k) c += (double)p[k] * (double)V[(size_t)pos_h[k] * S + pos_s[k]];
+  *c_out = c;
+}
+
+template <typename TV>
+int continuous_form_values(const float* T, const float* R, int S, int A, int H, double gamma, const int* pos_h,
+                           const int* pos_s, const float* p, int n_start, double eps, int max_eval, TV* V,
+                           double* out_host, void* stream) {
+  COLO_ARG_CHECK(T && R && V && pos_h && pos_s && p && out_host, "T, R, V, start positions, out_host are required");
+  COLO_ARG_CHECK(H >= 1 && n_start >= 1 && gamma > 0.0 && gamma < 1.0 && eps > 0.0, "H >= 1, n_start >= 1, 0 < gamma < 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* d_c = nullptr;
+  COLO_CUDA_TRY(cudaMallocAsync(&d_c, sizeof(double), st));
+  colo_backup_args a = {};
+  a.T = T; a.R = R; a.B = 1; a.S = S; a.A = A; a.fold = COLO_FOLD_MAX; a.gamma = gamma;
+  a.t_stride = 0; a.r_stride = 0; a.v_in_stride = S; a.v_out_stride = S; a.row0 = 0; a.nrows = S;
+  auto F = [&](double c, double* fc) -> int {
+    cf_last_layer_kernel<TV><<<(S + 127) / 128, 128, 0, st>>>(R, S, A, gamma * c, V + (size_t)(H - 1) * S);
+    int r = check_launch("cf_last_layer_kernel");
+    for (int h = H - 2; h >= 0 && r == COLO_OK; --h) {
+      a.V_in = V + (size_t)(h + 1) * S;
+      a.V_out = V + (size_t)h * S;
+      r = launch_backup<TV>(&a, stream);
+    }
+    if (r != COLO_OK) return r;
+    cf_start_value_kernel<TV><<<1, 32, 0, st>>>(V, pos_h, pos_s, p, n_start, S, d_c);
+    r = check_launch("cf_start_value_kernel");
+    if (r != COLO_OK) return r;
+    COLO_CUDA_TRY(cudaMemcpyAsync(fc, d_c, sizeof(double), cudaMemcpyDeviceToHost, st));
+    COLO_CUDA_TRY(cudaStreamSynchronize(st));
+    return COLO_OK;
+  };
+  // |c - c*| <= |F(c) - c| / (1 - gamma), and the values move by at most gamma * |c - c*|
+  const double tol = eps * (1.0 - gamma);
+  double c = 0.0, fc = 0.0, c_prev = 0.0, g_prev = 0.0;
+  bool have_prev = false;
+  int evals = 0, rc = COLO_MAX_ITER;
+  while (evals < max_eval) {
+    const int r = F(c, &fc);
+    ++evals;
+    if (r != COLO_OK) {
+      cudaFreeAsync(d_c, st);
+      return r;
+    }
+    const double g = fc - c;
+    if (fabs(g) <= tol) {
+      rc = COLO_OK;
+      break;
+    }
+    // secant step on g(c) = F(c) - c (g is decreasing: slope of F < 1), kept inside the bracket the contraction gives:
+    // c* lies between F(c) and c + g / (1 - gamma)
+    double next = fc;
+    if (have_prev && g != g_prev) {
+      const double sec = c - g * (c - c_prev) / (g - g_prev);
+      const double lo = g > 0 ? fc : c + g / (1.0 - gamma), hi = g > 0 ? c + g / (1.0 - gamma) : fc;
+      if (sec >= lo && sec <= hi) next = sec;
+    }
+    c_prev = c; g_prev = g; have_prev = true;
+    c = next;
+  }
+  COLO_CUDA_TRY(cudaFreeAsync(d_c, st));
+  out_host[0] = c;
+  out_host[1] = (double)evals;
+  return rc;
+}
+
 template <typename TV>
 int diameter_continuous(const float* T, const int* targets, int K, int S, int A, double eps, double max_value,
                         long long max_iter, void* work, double* out_host, void* stream) {
@@ -1178,6 +1274,17 @@ int colo_episodic_policies_f64acc(const float* T, const float* R, const float* p
 int colo_episodic_f64acc(const float* T, const float* R, const float* pi, int B, int S, int A, int H, int fold,
                          double max_value, double* Q, double* V, void* stream) {
   return colo::episodic<double>(T, R, pi, B, S, A, H, fold, max_value, Q, V, stream);
+}
+
+int colo_continuous_form_values_f32(const float* T, const float* R, int S, int A, int H, double gamma, const int* pos_h,
+                                    const int* pos_s, const float* p, int n_start, double eps, int max_eval, float* V,
+                                    double* out_host, void* stream) {
+  return colo::continuous_form_values<float>(T, R, S, A, H, gamma, pos_h, pos_s, p, n_start, eps, max_eval, V, out_host, stream);
+}
+int colo_continuous_form_values_f64acc(const float* T, const float* R, int S, int A, int H, double gamma, const int* pos_h,
+                                       const int* pos_s, const float* p, int n_start, double eps, int max_eval, double* V,
+                                       double* out_host, void* stream) {
+  return colo::continuous_form_values<double>(T, R, S, A, H, gamma, pos_h, pos_s, p, n_start, eps, max_eval, V, out_host, stream);
 }
 
 size_t colo_diameter_continuous_work_bytes(int K, int S, int f64) {

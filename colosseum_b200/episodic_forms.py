@@ -88,3 +88,47 @@ def get_continuous_form_episodic_transition_matrix_and_rewards(H, T, R, start_id
     # the reference asserts np.isclose(T_cf.sum(-1), 1).all() (mdp_creation.py:174)
     assert int(flag.item()) == 0, "a positive-probability successor is missing from the node list"
     return _result(T_cf, as_numpy), _result(R_cf, as_numpy)
+
+
+def continuous_form_optimal_values(H, T, R, start_idx, start_prob, nodes=None, gamma=0.99, epsilon=None,
+                                   precision="f64", max_evaluations=200):
+    """`mdp.optimal_value_continuous_form[1]` (mdp/base_finite.py:167-178: discounted_value_iteration on T_cf, R_cf) at
+    the FIXED POINT, computed from the structure of the continuous form instead of sweeping its n x A x n tensor
+    (colo_continuous_form_values_*: the fixed point depends on one scalar -- the value the last layer jumps to --
+    found by a handful of backward inductions over the original T).  `nodes` as in
+    get_continuous_form_episodic_transition_matrix_and_rewards; returns V_cf [n] in that node order."""
+    import ctypes as C
+
+    torch = _torch()
+    as_numpy = not _is_tensor(T)
+    Td, Rd = to_device(T), to_device(R)
+    S, A, _ = Td.shape
+    H = int(H)
+    if nodes is None:
+        nodes = reachable_states(H, Td, start_idx, start_prob)
+    hs = np.asarray(list(nodes), np.int64).reshape(-1, 2)
+    si = np.ascontiguousarray(start_idx, np.int64)
+    assert si.max() < len(hs), "a start index beyond the node list (mdp_creation.py:168 writes column node_to_index[start])"
+    f64 = precision == "f64"
+    eps = float(epsilon if epsilon is not None else (1e-9 if f64 else 1e-5))
+    # the node sitting at list position start_k (sic: the reference uses the ORIGINAL state index as a column index)
+    ph = torch.from_numpy(hs[si, 0].astype(np.int32)).cuda()
+    ps = torch.from_numpy(hs[si, 1].astype(np.int32)).cuda()
+    p32 = torch.from_numpy(np.ascontiguousarray(start_prob, np.float64).astype(np.float32)).cuda()
+    V = torch.empty((H, S), dtype=torch.float64 if f64 else torch.float32, device="cuda")
+    out = (C.c_double * 2)()
+    lib = _cabi.lib()
+    fn = lib.colo_continuous_form_values_f64acc if f64 else lib.colo_continuous_form_values_f32
+    rc = fn(_cabi.ptr(Td), _cabi.ptr(Rd), S, A, H, float(np.float32(gamma)), _cabi.ptr(ph), _cabi.ptr(ps), _cabi.ptr(p32),
+            len(si), eps, int(max_evaluations), _cabi.ptr(V), out, _cabi.current_stream())
+    _cabi.check(rc, "colo_continuous_form_values")
+    if rc == _cabi.MAX_ITER:
+        from .dynamic_programming import DynamicProgrammingMaxIterationExceeded
+
+        raise DynamicProgrammingMaxIterationExceeded()
+    continuous_form_optimal_values.last_evaluations = int(out[1])
+    V_cf = V[torch.from_numpy(hs[:, 0]).cuda(), torch.from_numpy(hs[:, 1]).cuda()]
+    return _result(V_cf, as_numpy)
+
+
+continuous_form_optimal_values.last_evaluations = 0

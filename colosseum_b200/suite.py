@@ -71,6 +71,57 @@ def load_suite(path, only=None) -> List[SuiteInstance]:
     return out
 
 
+def suite_files(golden_dir):
+    import os
+
+    files = [os.path.join(golden_dir, "c3_suite.npz")]
+    more = os.path.join(golden_dir, "c3_suite_seeds.npz")
+    if os.path.isfile(more):
+        files.append(more)
+    return files
+
+
+def suite_size(golden_dir) -> int:
+    return sum(len(json.loads(str(np.load(f, allow_pickle=False)["names"]))) for f in suite_files(golden_dir))
+
+
+def load_suite_all(golden_dir, indices=None) -> List[SuiteInstance]:
+    """SURVEY section 8d's C3 list: every gin parameter set of the six benchmark folders x seeds 0..10, seed-major --
+    c3_suite.npz (the 80 sets of the four benchmarks at seed 0, with the reference's own hardness answers) followed
+    by c3_suite_seeds.npz (the 14 quick-test sets at seed 0, then all 94 sets at seeds 1..10) when that file exists.
+    `indices`: positions in that list to load (each instance rebuilds its dense T on the host: load what a rank needs);
+    the result follows the order of `indices`."""
+    sizes, files = [], suite_files(golden_dir)
+    for f in files:
+        sizes.append(len(json.loads(str(np.load(f, allow_pickle=False)["names"]))))
+    if indices is None:
+        out = []
+        for f in files:
+            out += load_suite(f)
+        return out
+    want = {}
+    for i in indices:
+        j, k = int(i), 0
+        while j >= sizes[k]:
+            j -= sizes[k]
+            k += 1
+        want.setdefault(k, set()).add(j)
+    loaded = {}
+    for k, js in want.items():
+        names = json.loads(str(np.load(files[k], allow_pickle=False)["names"]))
+        for inst, j in zip(load_suite(files[k], only=js), sorted(js)):
+            assert inst.name == names[j]
+            loaded[(k, j)] = inst
+    out = []
+    for i in indices:
+        j, k = int(i), 0
+        while j >= sizes[k]:
+            j -= sizes[k]
+            k += 1
+        out.append(loaded[(k, j)])
+    return out
+
+
 def hardness_of_instance(inst: SuiteInstance, precision="f64", max_cf_bytes=8 << 30, diameter=True, timings=None):
     """diameter, environmental value norm and sum of reciprocal sub-optimality gaps of one instance on the GPU, with
     the property layer's choices of the reference: continuous MDPs use T, R and discounted VI
@@ -126,7 +177,10 @@ def hardness_of_instance(inst: SuiteInstance, precision="f64", max_cf_bytes=8 <<
             T_cf, R_cf = ef.get_continuous_form_episodic_transition_matrix_and_rewards(H, T, R, tb.start_idx, start_p,
                                                                                        nodes=nodes)
             lap("T_cf")
-            _, V_cf = dp.discounted_value_iteration(T_cf, R_cf, 0.99, eps, precision=precision)
+            # V* of the continuous form from its structure (a scalar fixed point + backward inductions over T)
+            # instead of ~2,000 sweeps over the n x A x n tensor; same fixed point (tests/test_gpu_hardness.py)
+            V_cf = ef.continuous_form_optimal_values(H, T, R, tb.start_idx, start_p, nodes=nodes, gamma=0.99,
+                                                     epsilon=eps, precision=precision)
             lap("vi_cf")
             out["value_norm"] = hd.calculate_norm_discounted(T_cf, V_cf, precision=precision)
             del T_cf, R_cf
@@ -187,5 +241,71 @@ def run_many(work, n_workers=4, **kw):
 
     if n_workers <= 1:
         return [one(w) for w in work]
-    with ThreadPoolExecutor(max_workers=n_workers) as pool:
-        return list(pool.map(one, work))
+    # the workers alternate between short stretches of Python and GIL-releasing C calls; with CPython's default 5 ms
+    # switch interval a thread coming back from a C call waits up to 5 ms for the GIL while another one runs Python
+    # (measured: 4 workers were no faster than 1).  A short interval hands the GIL over at once.
+    import os
+    import sys
+
+    old = sys.getswitchinterval()
+    sys.setswitchinterval(float(os.environ.get("COLO_SWITCH_INTERVAL", "5e-5")))
+    try:
+        with ThreadPoolExecutor(max_workers=n_workers) as pool:
+            return list(pool.map(one, work))
+    finally:
+        sys.setswitchinterval(old)
+
+
+def run_many_native(work, n_workers=8, n_envs=1024, n_steps=1000, diameter=True, max_cf_bytes=8 << 30, eps=1e-9):
+    """The same C3 work items as `run_many`, scheduled by the library (colo_suite_run, csrc/suite_runner.cu): `n_workers`
+    C++ host threads with one CUDA stream each run whole instances -- every step the public C-ABI entry point the Python
+    path calls, fp64 accumulation, iterations to `eps` -- so many small solves are in flight at once with no
+    interpreter between them.  `work` = [(SuiteInstance, seed), ...]: one seed per call (the first item's).  Returns
+    the list of (results, timings) in the order of `work`, as `run_many` does."""
+    import ctypes as C
+
+    from . import _cabi
+
+    _cabi.require_cuda()
+    n = len(work)
+    arr = (_cabi.SuiteInstance * max(n, 1))()
+    keep = []
+
+    def p(a, dt):
+        a = np.ascontiguousarray(a, dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    for i, (inst, _) in enumerate(work):
+        tb = inst.tables
+        c = arr[i]
+        c.S, c.A, c.H, c.K = tb.S, tb.A, tb.H, tb.succ_cum.shape[-1]
+        c.T, c.R = p(tb.T, np.float32), p(inst.R, np.float32)
+        c.succ_cum, c.succ_idx = p(tb.succ_cum, np.float64), p(tb.succ_idx, np.int32)
+        c.succ_len, c.rew_cls_succ = p(tb.succ_len, np.int32), p(tb.rew_cls_succ, np.int32)
+        c.rew_q = p(tb.rew_q, np.float32)
+        c.n_cls, c.nq = tb.rew_q.shape
+        c.rmin, c.rmax = tb.rmin, tb.rmax
+        c.start_idx, c.start_cum = p(tb.start_idx, np.int32), p(tb.start_cum, np.float64)
+        c.start_prob = p(np.diff(tb.start_cum, prepend=0.0), np.float64)
+        c.n_start = tb.n_start
+        if inst.episodic:
+            assert inst.nodes is not None, "episodic instances carry the reference's (h, s) node order"
+            c.node_h, c.node_s = p(inst.nodes[:, 0], np.int32), p(inst.nodes[:, 1], np.int32)
+            c.n_nodes = len(inst.nodes)
+        c.deterministic = int(bool((tb.succ_len == 1).all()) and all(k == "deterministic" for k, _ in tb.rew_kinds))
+    cfg = _cabi.SuiteConfig(int(n_envs), int(n_steps), int(work[0][1]) if n else 0, float(eps), int(max_cf_bytes),
+                            int(bool(diameter)))
+    res = (_cabi.SuiteResult * max(n, 1))()
+    rc = _cabi.lib().colo_suite_run(arr, n, C.byref(cfg), res, int(n_workers))
+    if rc != 0:
+        bad = [(work[i][0].name, res[i].status, res[i].error.decode(errors="replace")) for i in range(n) if res[i].status]
+        raise _cabi.ColosseumB200Error(f"colo_suite_run: rc={rc}: {bad[:3]}")
+    out = []
+    for i in range(n):
+        r = res[i]
+        out.append(({"gaps": r.gaps, "value_norm": r.value_norm, "diameter": r.diameter,
+                     "diameter_sweeps": int(r.diameter_sweeps) if r.diameter_sweeps == r.diameter_sweeps else 0,
+                     "visits_total": int(r.visits_total), "mean_reward_last_step": r.mean_reward_last_step},
+                    {"step_s": r.step_s, "hardness_s": r.hardness_s}))
+    return out

@@ -195,6 +195,24 @@ int colo_episodic_policies_f64acc(const float* T, const float* R, const float* p
                                   double* Q, double* V, void* stream);
 
 /*
+ * Optimal values of the CONTINUOUS FORM of an episodic MDP (mdp/utils/mdp_creation.py:131-176 +
+ * mdp/base_finite.py:167-178: discounted_value_iteration on the n x A x n tensor over the reachable (h, s) nodes) from
+ * the structure of that tensor, without building it: the fixed point depends on ONE scalar c = sum_k p[k] *
+ * V[pos_h[k], pos_s[k]] (the value the last layer jumps to; pos = the node sitting at list position start_k, sic
+ * :168), one backward induction over the original T maps c to F(c), and c* = F(c*) is found by safeguarded secant
+ * steps.  V [H][S] (device) receives the values of EVERY (h, s) pair at c*, to |error| <= eps; the caller gathers the
+ * reachable nodes in the reference's order.  pos_h, pos_s, p (float32 start probabilities as stored in T_cf): device
+ * arrays of n_start entries.  out_host[0] = c*, out_host[1] = backward inductions run.  COLO_MAX_ITER after max_eval.
+ * Synchronises.
+ */
+int colo_continuous_form_values_f32(const float* T, const float* R, int S, int A, int H, double gamma, const int* pos_h,
+                                    const int* pos_s, const float* p, int n_start, double eps, int max_eval, float* V,
+                                    double* out_host, void* stream);
+int colo_continuous_form_values_f64acc(const float* T, const float* R, int S, int A, int H, double gamma, const int* pos_h,
+                                       const int* pos_s, const float* p, int n_start, double eps, int max_eval, double* V,
+                                       double* out_host, void* stream);
+
+/*
  * Continuous diameter (colosseum/hardness/measures/diameter.py:20-39,76-106; == :321-346 at the fixed point):
  * multi-target hitting-time iteration  E[k,s] = (s == target[k]) ? 0 : min_a(1 + sum_j T[s,a,j] E[k,j])  over the
  * K given targets at once (all S for the full diameter), every target (tile of targets) iterated until its own
@@ -636,6 +654,59 @@ int colo_build_cdf_index(const void* cdf, int S, int A, int ld, int is_f64, void
  */
 int colo_synth_dense_rows(float* T_rows, float* R_rows, int row0, int nrows, int S, int A, unsigned long long seed,
                           void* stream);
+
+/* ---------------------------------------------------------------- benchmark-suite work items (C3) ------------ */
+/*
+ * colo_suite_run -- BASELINE.json configs[2]: for every MDP instance, cfg->n_envs parallel episodes x cfg->n_steps
+ * random-agent steps (BaseMDP.random_steps with auto_reset, mdp/base.py:1319-1355; successor-table sampler, Philox
+ * seed cfg->seed, reset at t = 0, steps at t = 1..), then the hardness measures with the reference's property layer's
+ * choices (mdp/base.py:996-1114): continuous MDPs -- discounted VI on T, R (gamma = float32(0.99)), gaps, value norm
+ * (0 when deterministic), diameter over all S targets; episodic ones -- backward induction + the reachable (h, s)
+ * pairs for the gaps, the episodic tensor for the diameter, the continuous form for the value norm (skipped, NaN,
+ * when 4 n^2 A > cfg->max_cf_bytes).  f64acc arithmetic, every iteration to cfg->eps.  Each step is the public entry
+ * point of this header that colosseum_b200/suite.py calls from Python; what this call adds is the scheduling:
+ * n_workers host threads, one CUDA stream each, pull instances from a shared counter, so that many small latency-bound
+ * solves are in flight at once without an interpreter in between.  ALL pointers of colo_suite_instance are HOST
+ * pointers (numpy arrays of the caller); out[i] receives instance i's results.  Runs on the current device.
+ * Synchronises.  Returns the first non-zero status (out[i].status / out[i].error say which instance and why).
+ */
+typedef struct {
+  int S, A, H, K;                /* H = 0: continuous; K = successor slots per (s, a) */
+  const float* T;                /* f32 [S,A,S] */
+  const float* R;                /* f32 [S,A], the reference's mdp.R */
+  const double* succ_cum;        /* f64 [S,A,K] running sums in sampler order, +inf padded */
+  const int* succ_idx;           /* i32 [S,A,K] */
+  const int* succ_len;           /* i32 [S,A] */
+  const int* rew_cls_succ;       /* i32 [S,A,K] */
+  const float* rew_q;            /* f32 [n_cls, nq] */
+  int n_cls, nq;
+  float rmin, rmax;
+  const int* start_idx;          /* i32 [n_start] */
+  const double* start_cum;       /* f64 [n_start] */
+  const double* start_prob;      /* f64 [n_start] */
+  int n_start;
+  const int* node_h;             /* episodic: the reachable (h, s) pairs in the reference's node order */
+  const int* node_s;
+  int n_nodes;
+  int deterministic;             /* all transitions and rewards deterministic: value norm = 0 (base.py:1069-1074) */
+} colo_suite_instance;
+typedef struct {
+  long long n_envs;
+  int n_steps;
+  unsigned long long seed;
+  double eps;                    /* stopping tolerance of every iteration (1e-9: the fixed point in fp64) */
+  size_t max_cf_bytes;
+  int diameter;                  /* 0: skip the diameter */
+} colo_suite_config;
+typedef struct {
+  int status;
+  double visits_total, mean_reward_last_step;
+  double gaps, value_norm, diameter, diameter_sweeps;
+  double step_s, hardness_s;     /* wall-clock seconds of the two phases of this instance (its worker thread) */
+  char error[160];
+} colo_suite_result;
+int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_config* cfg, colo_suite_result* out,
+                   int n_workers);
 
 #ifdef __cplusplus
 }

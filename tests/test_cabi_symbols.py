@@ -35,7 +35,9 @@ def test_struct_layouts_match_header():
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     for cname, mirror in (("colo_backup_args", _cabi.BackupArgs), ("colo_mdp_tables", _cabi.MdpTables),
                           ("colo_env_batch", _cabi.EnvBatch), ("colo_resident_args", _cabi.ResidentArgs),
-                          ("colo_env_server", _cabi.EnvServer), ("colo_qlearning_args", _cabi.QLearningArgs), ("colo_psrl_args", _cabi.PsrlArgs)):
+                          ("colo_env_server", _cabi.EnvServer), ("colo_qlearning_args", _cabi.QLearningArgs), ("colo_psrl_args", _cabi.PsrlArgs),
+                          ("colo_suite_instance", _cabi.SuiteInstance), ("colo_suite_config", _cabi.SuiteConfig),
+                          ("colo_suite_result", _cabi.SuiteResult)):
         end = txt.index("} " + cname + ";")
         body = txt[txt.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
         fields = []
@@ -44,6 +46,7 @@ def test_struct_layouts_match_header():
             if not decl:
                 continue
             for part in decl.split(","):
+                part = re.sub(r"\[\d+\]", "", part)  # char error[160]
                 fields.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
         assert fields == [f[0] for f in mirror._fields_], cname
 

@@ -161,3 +161,26 @@ def test_suite_reference_iterates(suite):
             assert abs(d - ref["diameter"]) < 2e-3, (inst.name, d, ref["diameter"])
         n += 1
     assert n >= 18
+
+
+@pytest.mark.gpu
+def test_native_runner_equals_the_python_path(suite):
+    """colo_suite_run (C++ worker threads, one stream each) against suite.run_instance (the same C-ABI calls issued from
+    Python) on a mixed set of instances: the same numbers -- the walks bit for bit (same Philox counters), the measures
+    to rounding of identical kernels -- and the reference's recorded answers"""
+    from colosseum_b200.suite import run_instance, run_many_native
+
+    pick = [i for i in suite if i.S <= 260][:14]
+    assert any(i.episodic for i in pick) and any(not i.episodic for i in pick)
+    work = [(inst, 3) for inst in pick]
+    native = run_many_native(work, n_workers=4, n_envs=256, n_steps=50)
+    for (inst, seed), (res, tm) in zip(work, native):
+        ref, _ = run_instance(inst, n_envs=256, n_steps=50, seed=seed)
+        assert res["visits_total"] == ref["visits_total"] == 256 * 51
+        assert abs(res["mean_reward_last_step"] - ref["mean_reward_last_step"]) < 1e-6
+        for k in ("gaps", "value_norm", "diameter"):
+            a, b = res[k], ref[k]
+            assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-9 * max(1.0, abs(b)), (inst.name, k, a, b)
+        if not np.isnan(inst.ref["diameter"]):
+            assert abs(res["diameter"] - inst.ref["diameter"]) < 2e-3 * inst.ref["diameter"], inst.name
+        assert tm["step_s"] > 0 and tm["hardness_s"] > 0
