@@ -711,11 +711,11 @@ static int episodic_batched_launch(const float* T, const float* R, const float* 
   const long long ts = shared_mdp ? 0 : (long long)S * A * S, rs = shared_mdp ? 0 : (long long)S * A;
   if (vec4) {
     auto k = episodic_batched_kernel<TV, L, true>;
-    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int _es = ensure_dynamic_smem((const void*)k, smem); if (_es != COLO_OK) return _es; }
     k<<<grid, threads, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
   } else {
     auto k = episodic_batched_kernel<TV, L, false>;
-    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int _es = ensure_dynamic_smem((const void*)k, smem); if (_es != COLO_OK) return _es; }
     k<<<grid, threads, smem, st>>>(T, R, pi, B, S, A, H, fold, Q, V, ts, rs);
   }
   return check_launch("episodic_batched_kernel");

@@ -31,6 +31,8 @@ int check_launch(const char* what);  // cudaGetLastError -> COLO_OK / COLO_ERR_C
   } while (0)
 
 int sm_count();  // SMs of the current device (148 on B200), cached
+// grow-only, locked cudaFuncAttributeMaxDynamicSharedMemorySize (the entry points run on several host threads)
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 // resident.cu: on-chip resident solver (see there)
 int resident_fits_any(int S, int A, int NV, bool f64, int* cluster_size_out);

@@ -197,7 +197,7 @@ int extended_vi(const float* T, const float* est_r, const double* beta_r, const 
   COLO_CUDA_TRY(cudaMemsetAsync(work, 0, (size_t)(w - (char*)work) + sizeof(EviState), st));
   const size_t smem = (size_t)n_pow2 * (sizeof(TV) + sizeof(int));
   auto sort_kern = evi_check_and_sort_kernel<TV>;
-  COLO_CUDA_TRY(cudaFuncSetAttribute(sort_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int _es = ensure_dynamic_smem((const void*)sort_kern, smem); if (_es != COLO_OK) return _es; }
   const int row_blocks = (int)(((long long)S * 32 + 255) / 256);
   EviState h = {};
   long long launched = 0;

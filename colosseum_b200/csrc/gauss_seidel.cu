@@ -334,22 +334,22 @@ static int gs_launch(GsArgs a, void* stream) {
   if (a.cv_rm != nullptr) {
     if (a.A * a.KMp <= 32) {
       auto k = gs_sparse_kernel<TV, true>;
-      COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int _es = ensure_dynamic_smem((const void*)k, smem); if (_es != COLO_OK) return _es; }
       k<<<grid, W * 32, smem, st>>>(a);
     } else {
       auto k = gs_sparse_kernel<TV, false>;
-      COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      { const int _es = ensure_dynamic_smem((const void*)k, smem); if (_es != COLO_OK) return _es; }
       k<<<grid, W * 32, smem, st>>>(a);
     }
     return check_launch("gs_sparse_kernel");
   }
   if (vec) {
     auto k = gs_solve_kernel<TV, true>;
-    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int _es = ensure_dynamic_smem((const void*)k, smem); if (_es != COLO_OK) return _es; }
     k<<<grid, W * 32, smem, st>>>(a);
   } else {
     auto k = gs_solve_kernel<TV, false>;
-    COLO_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int _es = ensure_dynamic_smem((const void*)k, smem); if (_es != COLO_OK) return _es; }
     k<<<grid, W * 32, smem, st>>>(a);
   }
   return check_launch("gs_solve_kernel");

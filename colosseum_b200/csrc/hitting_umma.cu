@@ -522,14 +522,10 @@ int hitting_umma_sweep(UmmaPlan* pl, const float* E_in, float* E_out, long long 
   a.flush = pl->flush;
   dim3 grid(pl->Kp / pl->BN, pl->Sm / UM_BM);
   if (pl->BN == 128) {
-    static const cudaError_t attr = cudaFuncSetAttribute(hitting_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         UmmaCfg<128>::SMEM);
-    COLO_CUDA_TRY(attr);
+    { const int es = ensure_dynamic_smem((const void*)hitting_umma_kernel<128>, UmmaCfg<128>::SMEM); if (es != COLO_OK) return es; }
     hitting_umma_kernel<128><<<grid, UM_THREADS, UmmaCfg<128>::SMEM, st>>>(pl->mapT, pl->mapE, a);
   } else {
-    static const cudaError_t attr = cudaFuncSetAttribute(hitting_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         UmmaCfg<64>::SMEM);
-    COLO_CUDA_TRY(attr);
+    { const int es = ensure_dynamic_smem((const void*)hitting_umma_kernel<64>, UmmaCfg<64>::SMEM); if (es != COLO_OK) return es; }
     hitting_umma_kernel<64><<<grid, UM_THREADS, UmmaCfg<64>::SMEM, st>>>(pl->mapT, pl->mapE, a);
   }
   pl->cur ^= 1;

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -25,6 +27,26 @@ int check_launch(const char* what) {
   if (e != cudaSuccess) {
     set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
     return COLO_ERR_CUDA;
+  }
+  return COLO_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-kernel STATE: a host thread that lowers it between another
+// thread's set and launch makes that launch fail ("invalid argument").  The library's entry points are called from
+// several host threads (one stream each), so the attribute only ever GROWS, under a lock.
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> current;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = current[kernel];
+  if (bytes > cur) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %zu) failed: %s", bytes, cudaGetErrorString(e));
+      return COLO_ERR_CUDA;
+    }
+    cur = bytes;
   }
   return COLO_OK;
 }

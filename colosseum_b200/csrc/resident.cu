@@ -268,7 +268,7 @@ static ResidentPlan plan_resident(int S, int A, int NV, int max_smem) {
 template <typename TV, int FOLD, int NV>
 static int launch_resident_3(const ResidentArgs& a, size_t smem, cudaStream_t st) {
   auto kern = resident_solve_kernel<TV, FOLD, NV>;
-  COLO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int _es = ensure_dynamic_smem((const void*)kern, smem); if (_es != COLO_OK) return _es; }
   if (a.C > 8) COLO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(a.B * a.C));

@@ -602,7 +602,7 @@ int sparse_diameter_continuous(const float* T, const int* targets, int K, int S,
 #define COLO_SPHIT(N)                                                                                       \
   {                                                                                                         \
     auto kern = sparse_hitting_kernel<TV, N>;                                                               \
-    COLO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    { const int _es = ensure_dynamic_smem((const void*)kern, smem); if (_es != COLO_OK) return _es; }      \
     kern<<<tiles, threads, smem, st>>>(a);                                                                  \
   }
   if (NT == 4) COLO_SPHIT(4)
@@ -642,7 +642,7 @@ int sparse_diameter_episodic(const float* T_epi, const int* targets, int K, int 
   a.H = H; a.S = S; a.A = A; a.K = K; a.targets = targets; a.eps = (float)eps; a.max_value = max_value;
   a.max_iter = max_iter; a.out = d_out; a.iters = d_it; a.status = d_st;
   auto kern = sparse_episodic_kernel<TV>;
-  COLO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int _es = ensure_dynamic_smem((const void*)kern, smem); if (_es != COLO_OK) return _es; }
   kern<<<K, block_threads(S), smem, st>>>(a);
   r = check_launch("sparse_episodic_kernel");
   if (r == COLO_OK) r = collect<TV>(d_out, d_it, d_st, K, out_host, st);
@@ -713,7 +713,7 @@ int sparse_solve_resident(const SparseRows& h, const float* R, const float* pi, 
 #define COLO_SPVI(FOLD)                                                                                     \
   {                                                                                                         \
     auto kern = sparse_vi_kernel<TV, FOLD>;                                                                 \
-    COLO_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    { const int _es = ensure_dynamic_smem((const void*)kern, smem); if (_es != COLO_OK) return _es; }      \
     kern<<<B, threads, smem, st>>>(a);                                                                      \
   }
   if (fold == COLO_FOLD_MAX) COLO_SPVI(COLO_FOLD_MAX)

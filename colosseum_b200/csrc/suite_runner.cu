@@ -83,6 +83,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
   const int S = in.S, A = in.A, H = in.H, K = in.K;
   const size_t SA = (size_t)S * A;
   StreamArena ar(st);
+  cudaGetLastError();  // a failure of this thread's previous instance must not be reported against this one
   const double t0 = now_s();
   // ---------------------------------------------------------------- tables
   float* T = ar.upload(in.T, SA * S);
