@@ -695,13 +695,14 @@ def bench_c3_gpu(args, rank, world):
         if tm["hardness_s"] > worst[0]:
             worst = (tm["hardness_s"], inst.name)
         assert res["gaps"] > 0 and res["diameter"] > 0 and res["visits_total"] == args.c3_envs * (args.c3_steps + 1)
-        for k, ref_k, tol in (("diameter", "diameter", 2e-3), ("diameter", "cached_diameter", 2e-3),
-                              ("value_norm", "value_norm", 3e-3), ("value_norm", "cached_value_norm", 3e-3),
-                              ("gaps", "gaps", 7e-3)):
+        # tolerances of tests/test_suite.py: the reference's own numbers are early-stopped iterates (eps = 1e-3)
+        for k, ref_k, tol, floor in (("diameter", "diameter", 2e-3, 0.0), ("diameter", "cached_diameter", 2e-3, 0.0),
+                                     ("value_norm", "value_norm", 5e-3, 0.2), ("value_norm", "cached_value_norm", 5e-3, 0.2),
+                                     ("gaps", "gaps", 1.5e-2, 0.0)):
             ref = inst.ref.get(ref_k, float("nan"))
             if ref == ref and res[k] == res[k]:
                 checked += 1
-                if abs(res[k] - ref) > tol * max(abs(ref), 1e-3):
+                if abs(res[k] - ref) > tol * max(abs(ref), floor, 1e-9):
                     bad.append((inst.name, ref_k, res[k], ref))
     barrier_sync(world)
     ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms), world)
@@ -718,8 +719,9 @@ def bench_c3_gpu(args, rank, world):
     return dict(B=B, per_rank=i1 - i0, ms=ms, launches=int(lib.colo_launch_count()), step_s=step_s, hard_s=hard_s,
                 worst=worst, n_suite=n_suite, workers=workers, runner="native (colo_suite_run)" if native else "python",
                 parity_ok=ok,
-                parity_what=f"{checked} recorded reference answers (diameter 2e-3, value norm 3e-3, gaps 7e-3 relative: "
-                            "the reference stops early at eps = 1e-3, DESIGN section 2) checked over all ranks")
+                parity_what=f"{checked} recorded reference answers (diameter 2e-3, value norm 5e-3 of max(ref, 0.2), gaps "
+                            "1.5e-2 relative: the reference stops early at eps = 1e-3, DESIGN section 2) checked over "
+                            "all ranks")
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms

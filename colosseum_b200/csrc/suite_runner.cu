@@ -9,8 +9,10 @@
 // 125 / 169 / 120 / 116 instances/s).  Here the workers are C++ threads; every solver call is the public C ABI of
 // include/colosseum_b200.h, exactly what the Python path calls, so the numbers are the same numbers.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <thread>
@@ -269,6 +271,51 @@ int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_conf
   COLO_ARG_CHECK(cfg->n_envs >= 1 && cfg->n_steps >= 1 && cfg->eps > 0.0, "n_envs, n_steps, eps");
   int dev = 0;
   COLO_CUDA_TRY(cudaGetDevice(&dev));
+  // the workers spend their time waiting in cudaStreamSynchronize; the default schedule spins there, which turns
+  // n_workers x ranks waiting threads into as many busy cores.  Ask the runtime to block instead for the duration of
+  // this call (honoured when the primary context accepts a flag change; harmless otherwise).
+  unsigned old_flags = 0;
+  const bool have_flags = cudaGetDeviceFlags(&old_flags) == cudaSuccess;
+  const bool blocking = have_flags && getenv("COLO_SUITE_SPIN") == nullptr &&
+                        cudaSetDeviceFlags((old_flags & ~(unsigned)cudaDeviceScheduleMask) | cudaDeviceScheduleBlockingSync) == cudaSuccess;
+  cudaGetLastError();
+  if (getenv("COLO_SUITE_VERBOSE")) fprintf(stderr, "[colo_suite_run] blocking-sync schedule: %s\n", blocking ? "on" : "unavailable");
+  // Warm the stream-ordered memory pool: every instance allocates its tensors with cudaMallocAsync (T_epi, T_cf: up
+  // to gigabytes), and a pool that has to grow from the OS in the middle of the run stalls every worker (measured: the
+  // first pass over a shard ran at a third of the rate of the second).  Keep freed blocks in the pool and reserve the
+  // footprint of the n_workers largest instances once.
+  {
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ULL;
+      cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+      std::vector<size_t> need((size_t)n);
+      for (int i = 0; i < n; ++i) {
+        const size_t S = inst[i].S, A = inst[i].A, H = inst[i].H, nn = inst[i].n_nodes;
+        size_t b = 4 * S * A * S * 2 + (64u << 20);
+        if (H > 0) {
+          b += 4 * H * S * A * S + 8 * 2 * S * S * H / (H > 0 ? 1 : 1);  // T_epi + the diameter's F [K,H,S] ping-pong
+          if (4 * nn * nn * A <= cfg->max_cf_bytes) b += 4 * nn * nn * A;
+        } else {
+          b += 8 * 4 * S * S;  // the diameter's E buffers
+        }
+        need[(size_t)i] = b;
+      }
+      std::sort(need.begin(), need.end(), [](size_t a, size_t b) { return a > b; });
+      size_t reserve = 0;
+      for (int w = 0; w < n_workers && w < n; ++w) reserve += need[(size_t)w];
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && reserve > free_b / 2) reserve = free_b / 2;
+      unsigned long long have = 0;
+      cudaMemPoolGetAttribute(mp, cudaMemPoolAttrReservedMemCurrent, &have);
+      if (reserve > have) {
+        void* blk = nullptr;
+        if (cudaMallocAsync(&blk, reserve - have, (cudaStream_t)0) == cudaSuccess) cudaFreeAsync(blk, (cudaStream_t)0);
+        cudaStreamSynchronize((cudaStream_t)0);
+      }
+    }
+    cudaGetLastError();
+  }
   std::atomic<int> next{0};
   std::atomic<int> first_error{COLO_OK};
   std::vector<std::thread> pool;
@@ -298,6 +345,8 @@ int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_conf
       cudaStreamDestroy(st);
     });
   for (auto& t : pool) t.join();
+  if (blocking) cudaSetDeviceFlags(old_flags);
+  cudaGetLastError();
   const int r = first_error.load();
   if (r != COLO_OK) colo::set_error("colo_suite_run: at least one instance failed (see colo_suite_result.error)");
   return r;
