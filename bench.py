@@ -665,10 +665,20 @@ def bench_c3_gpu(args, rank, world):
     by_index = dict(zip(sorted({i % n_suite for i in range(i0, i1)}), mine))
     work = [(by_index[i % n_suite], 0) for i in range(i0, i1)]
     suite = mine
-    workers = args.c3_workers or max(2, min(8, (os.cpu_count() or 8) // max(world, 1)))
+    # the workers block in cudaStreamSynchronize (blocking-sync schedule inside colo_suite_run): 8 per GPU whatever the
+    # number of ranks sharing the host
+    workers = args.c3_workers or 8
     native = args.c3_runner == "native" and args.c3_precision == "f64"
     if native:
-        run_many_native(work[:2], n_workers=2, n_envs=args.c3_envs, n_steps=10)  # warm-up
+        # untimed warm-up: one short pass over every distinct (family, size) of the shard, so that module loading and
+        # the growth of the memory pool are not inside the timed region
+        seen, warm = set(), []
+        for inst, sd in work:
+            key = (inst.name.split(".")[0], inst.S, inst.H)
+            if key not in seen:
+                seen.add(key)
+                warm.append((inst, sd))
+        run_many_native(warm[:48], n_workers=workers, n_envs=args.c3_envs, n_steps=10)
     else:
         run_instance(suite[0], n_envs=args.c3_envs, n_steps=10, seed=0, precision=args.c3_precision)
     barrier_sync(world)

@@ -565,6 +565,100 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
   }
 }
 
+// The LEAN form of the k-ary step for the common call: one step per launch, supplied actions, in-kernel Philox uniforms,
+// auto-reset, visitation counters on, two-level index present, fewer than 2^31 envs.  Same loads, same comparisons
+// against the same x, same Philox counters as env_step_dense_kary_kernel -- bit-identical results -- but none of the
+// generality is paid for at run time: no grid-stride / n_steps / server loops, 32-bit env indices, the fp64 start
+// uniform only on the (rare) reset path, no optional-pointer tests on the hot path.  ncu of the general kernel at
+// 4 Mi envs: 505 warp instructions per env-step, issue slots 68 % busy, DRAM 11 % -- the kernel is ISSUE bound once
+// the batch fills the machine, so instructions are what the asymptotic env-steps/s is made of.
+constexpr int kLeanThreads = 128;
+template <int NCH>
+__global__ void __launch_bounds__(kLeanThreads) env_step_kary_lean_kernel(const colo_mdp_tables tb, const StepIO io) {
+  constexpr int ld = 128 * NCH, NB = 4 * NCH;
+  const unsigned e = blockIdx.x * kLeanThreads + threadIdx.x;
+  const bool valid = e < (unsigned)io.N;
+  const int S = tb.S, A = tb.A;
+  int st = COLO_STEP_MID, s = 0, h = 0, a = 0;
+  if (valid) {
+    st = io.step_type[e];
+    s = io.state[e];
+    h = io.h[e];
+    a = io.srv_go ? __ldcv(io.action + e) : io.action[e];
+  }
+  const Philox4 w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, io.t);
+  bool bad = false;
+  if ((unsigned)a >= (unsigned)A) {
+    if (io.status) *io.status = COLO_BAD_ACTION;
+    a = 0;
+    bad = true;
+  }
+  const bool resetting = valid && st == COLO_STEP_LAST;
+  const bool stepping = valid && st != COLO_STEP_LAST && !bad;
+  int nxt = 0, cls = 0;
+  if (stepping) {
+    const unsigned r = (unsigned)(s * A + a);
+    const float* __restrict__ coarse = reinterpret_cast<const float*>(tb.cdf_coarse) + (size_t)r * NB;
+    const float* __restrict__ row = reinterpret_cast<const float*>(tb.cdf) + (size_t)r * ld;
+    float4 cq[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) cq[k] = __ldg(reinterpret_cast<const float4*>(coarse) + k);
+    const float total = cq[NCH - 1].w;
+    const float x = u24(w.w[0]) * total;
+    int blk = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) blk += (cq[k].x <= x) + (cq[k].y <= x) + (cq[k].z <= x) + (cq[k].w <= x);
+    bool have_cls = false;
+    nxt = ld;
+    if (blk < NB) {
+      const float4* mp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tb.cdf_mid) + (size_t)r * (32 * NCH) + 8 * blk);
+      const uint4* cp = reinterpret_cast<const uint4*>(tb.rew_cls_pad + (size_t)r * ld + 32 * blk);
+      const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+      const uint4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+      const int G = 8 * blk + (m0.x <= x) + (m0.y <= x) + (m0.z <= x) + (m0.w <= x) + (m1.x <= x) + (m1.y <= x) +
+                    (m1.z <= x) + (m1.w <= x);
+      const float4 qq = __ldg(reinterpret_cast<const float4*>(row) + G);
+      nxt = 4 * G + (qq.x <= x) + (qq.y <= x) + (qq.z <= x);
+      if (nxt < S) {
+        const int pos = nxt - 32 * blk;
+        const unsigned wsel = pos < 16 ? (pos < 8 ? (pos < 4 ? c0.x : c0.y) : (pos < 12 ? c0.z : c0.w))
+                                       : (pos < 24 ? (pos < 20 ? c1.x : c1.y) : (pos < 28 ? c1.z : c1.w));
+        cls = (int)((wsel >> (8 * (pos & 3))) & 0xffu);
+        have_cls = true;
+      }
+    }
+    if (nxt >= S) {  // x >= total (rounding): bisect's hi = n-1 clamp == first index where the row reaches total
+      nxt = 0;
+      while (nxt < S - 1 && __ldg(row + nxt) < total) ++nxt;
+    }
+    if (!have_cls) cls = tb.rew_cls_sas ? tb.rew_cls_sas[((size_t)s * A + a) * S + nxt] : (tb.rew_cls_sa ? tb.rew_cls_sa[(size_t)s * A + a] : 0);
+  }
+  if (resetting) {  // auto_reset path == BaseMDP.reset(): the action is ignored, reward is None (NaN here)
+    nxt = sample_start(tb, u53(w.w[0], w.w[1]));
+    io.state[e] = nxt;
+    io.h[e] = 0;
+    io.step_type[e] = COLO_STEP_FIRST;
+    if (io.step_type_mirror) io.step_type_mirror[e] = COLO_STEP_FIRST;
+    io.reward[e] = __int_as_float(0x7fc00000);
+    if (io.discount) io.discount[e] = __int_as_float(0x7fc00000);
+    io.obs[e] = nxt;
+  } else if (stepping) {
+    const int hh = h + 1;
+    const bool last = tb.H > 0 && hh >= tb.H;
+    const unsigned char nst = last ? COLO_STEP_LAST : COLO_STEP_MID;
+    io.h[e] = hh;
+    io.state[e] = nxt;
+    io.reward[e] = reward_draw(tb, cls, u24(w.w[2]));
+    io.step_type[e] = nst;
+    if (io.step_type_mirror) io.step_type_mirror[e] = nst;
+    if (io.discount) io.discount[e] = last ? 0.f : 1.f;
+    io.obs[e] = last ? -1 : nxt;
+  }
+  const unsigned copy = blockIdx.x & (unsigned)io.visits_mask;
+  aggregated_inc(io.visits_s + (size_t)copy * io.n_s, nxt, stepping || resetting);
+  aggregated_inc(io.visits_sa + (size_t)copy * io.n_sa, (long long)nxt * A + a, stepping);
+}
+
 template <bool SERVER>
 __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_mdp_tables tb, const StepIO io) {
   const long long n_thr = (long long)gridDim.x * kStepThreads;
@@ -738,6 +832,28 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
     if (forced == 8 || forced == 16 || forced == 32) tile = forced;
     // thread-per-env k-ary search (default) or the warp-cooperative full-row count (COLO_STEP_KERNEL=coop)
     static const bool coop = getenv("COLO_STEP_KERNEL") && !strcmp(getenv("COLO_STEP_KERNEL"), "coop");
+    static const bool no_lean = getenv("COLO_STEP_KERNEL") && !strcmp(getenv("COLO_STEP_KERNEL"), "general");
+    if (!coop && !no_lean && !SERVER && sizeof(TC) == 4 && io.n_steps == 1 && !io.random_actions && io.u_next == nullptr &&
+        io.u_rew == nullptr && io.auto_reset && tb->cdf_mid && tb->cdf_coarse && tb->rew_cls_pad && io.visits_s &&
+        io.visits_sa && io.N < (1LL << 31) - kLeanThreads) {
+      const int gl = (int)((io.N + kLeanThreads - 1) / kLeanThreads);
+#define COLO_LEAN(NCH)                                                              \
+  case NCH:                                                                         \
+    env_step_kary_lean_kernel<NCH><<<gl, kLeanThreads, 0, st>>>(*tb, io);           \
+    break
+      switch (ld / 128) {
+        COLO_LEAN(1);
+        COLO_LEAN(2);
+        COLO_LEAN(3);
+        COLO_LEAN(4);
+        COLO_LEAN(5);
+        COLO_LEAN(6);
+        COLO_LEAN(7);
+        COLO_LEAN(8);
+      }
+#undef COLO_LEAN
+      return check_launch("env_step_kary_lean_kernel");
+    }
     if (!coop) {
       const int gk = grid_for(kStepThreads, io.N);
 #define COLO_KARY(NCH)                                                                              \
