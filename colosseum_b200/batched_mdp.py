@@ -632,6 +632,33 @@ class PipelinedBatchedMDP:
     def recv(self, g: int):
         return self.shards[g].wait() if self._serving else self.shards[g].recv_host()
 
+    def run_native(self, action_ring, n_steps, on_timestep=None):
+        """`n_steps` steps of every env with the recv/send loop run by the library (colo_env_pipeline_run): step i of
+        group g reads `action_ring[i % len(action_ring)][g]` (pinned int32 tensors).  `on_timestep`: an optional
+        ctypes callback `void(void* user, int group, int step)` -- a host agent written in C -- called when group g's
+        TimeStep of `step` is in the pinned views (`shards[g].obs / reward / step_type_host`) and before its next
+        launch.  Bit-identical to `n_steps` rounds of recv / send."""
+        import ctypes as C
+
+        assert not self._serving
+        G, Rn = self.groups, len(action_ring)
+        for sh in self.shards:
+            if sh._stepper is None:
+                sh._make_stepper()
+        hs = (C.c_void_p * G)(*[sh._stepper for sh in self.shards])
+        ring = (C.c_void_p * (Rn * G))()
+        for i, acts in enumerate(action_ring):
+            for g, a in enumerate(acts):
+                assert a.dtype == self.shards[g].torch.int32 and a.is_pinned() and a.numel() == self.sizes[g]
+                ring[i * G + g] = a.data_ptr()
+        t0 = self.shards[0].t
+        assert all(sh.t == t0 for sh in self.shards)
+        rc = _cabi.lib().colo_env_pipeline_run(hs, G, ring, Rn, t0, int(n_steps), on_timestep, None)
+        _cabi.check(rc, "colo_env_pipeline_run")
+        for sh in self.shards:
+            sh.t += int(n_steps)
+        return [(sh.obs, sh.reward, sh.step_type_host) for sh in self.shards]
+
     def step_all(self, actions):
         """one step of every env: launches all groups, then waits for each (actions: list of pinned int32 [N/groups])"""
         for sh, a in zip(self.shards, actions):

@@ -1026,6 +1026,26 @@ int colo_env_stepper_launch(colo_env_stepper* h, const int* action, unsigned lon
 
 void colo_env_stepper_destroy(colo_env_stepper* h) { free(h); }
 
+int colo_env_pipeline_run(colo_env_stepper* const* steppers, int n_groups, const int* const* action_ring, int ring,
+                          unsigned long long t0, int n_steps, colo_env_pipeline_callback on_timestep, void* user) {
+  COLO_ARG_CHECK(steppers && action_ring && n_groups >= 1 && ring >= 1 && n_steps >= 1, "steppers, action_ring, n_groups, ring, n_steps");
+  // software pipeline over the groups: while the host handles group g's TimeStep the other groups' kernels are on PCIe
+  for (int g = 0; g < n_groups; ++g) {
+    const int r = colo_env_stepper_launch(steppers[g], action_ring[(size_t)0 * n_groups + g], t0);
+    if (r != COLO_OK) return r;
+  }
+  for (int i = 1; i <= n_steps; ++i)
+    for (int g = 0; g < n_groups; ++g) {
+      COLO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)steppers[g]->stream));  // step i-1 of group g is in host memory
+      if (on_timestep) on_timestep(user, g, i - 1);
+      if (i < n_steps) {
+        const int r = colo_env_stepper_launch(steppers[g], action_ring[(size_t)(i % ring) * n_groups + g], t0 + (unsigned long long)i);
+        if (r != COLO_OK) return r;
+      }
+    }
+  return COLO_OK;
+}
+
 int colo_env_server_start(const colo_mdp_tables* tb, const colo_env_batch* batch, const colo_env_server* srv, int mode,
                           unsigned long long t, unsigned long long served, void* stream) {
   int r = colo::check_tables_common(tb);

@@ -42,21 +42,27 @@ def allgather_rows_host(local_rows: np.ndarray, n_items: int, group=None):
 class RowShardedValueIteration:
     """Value iteration on ONE dense MDP whose T is row-sharded over the ranks of `group` (config C5)."""
 
-    def __init__(self, T_rows, R_rows, S, gamma=0.99, transport="nccl", group=None, precision="f32"):
+    def __init__(self, T_rows, R_rows, S, gamma=0.99, transport="nccl", group=None, precision="f32", local_vi=None):
+        """local_vi: the object that backs up this rank's rows -- anything with `.sweep(1)`, `.values` ([1, S] tensor
+        whose rows [row0, row1) the sweep rewrites from the full vector), `.residual()` and `.cur`; default: the CUDA
+        BatchedValueIteration on (T_rows, R_rows).  The exchange logic below only sees that interface, which is how the
+        world-size-2 gloo tests drive THIS class on CPU tensors (tests/test_sharding_cpu.py)."""
         import torch
         import torch.distributed as dist
-
-        from .dynamic_programming import BatchedValueIteration
 
         self.dist, self.torch = dist, torch
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.S = int(S)
         self.row0, self.row1 = shard_range(S, self.rank, self.world)
-        assert T_rows.shape[0] == self.row1 - self.row0, "T_rows must hold exactly this rank's rows"
+        assert T_rows is None or T_rows.shape[0] == self.row1 - self.row0, "T_rows must hold exactly this rank's rows"
         self.transport = transport
-        self.vi = BatchedValueIteration(T_rows[None], R_rows[None], gamma=gamma, precision=precision,
-                                        row0=self.row0, S_total=S)
+        if local_vi is None:
+            from .dynamic_programming import BatchedValueIteration
+
+            local_vi = BatchedValueIteration(T_rows[None], R_rows[None], gamma=gamma, precision=precision,
+                                             row0=self.row0, S_total=S)
+        self.vi = local_vi
         self.sizes = shard_sizes(S, self.world)
         self.even = len(set(self.sizes)) == 1
         if transport == "fused":

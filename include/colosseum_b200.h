@@ -530,6 +530,19 @@ int colo_env_stepper_create(const colo_mdp_tables* tb, const colo_env_batch* bat
                             colo_env_stepper** out);
 int colo_env_stepper_launch(colo_env_stepper* h, const int* action, unsigned long long t);
 void colo_env_stepper_destroy(colo_env_stepper* h);
+/*
+ * colo_env_pipeline_run -- n_steps steps of every env of n_groups prepared steppers (host_io groups of one batch, each on
+ * its own stream) as a software pipeline run by the library: prime every group, then per step and group: wait for the
+ * group's stream (its TimeStep of the previous step is in the pinned buffers), call on_timestep(user, group, step) if
+ * given -- the host agent reads the TimeStep and writes the next actions there -- and launch the next step reading
+ * action_ring[(step % ring) * n_groups + group] (pinned int32 buffers).  The same recv/send order as the Python loop
+ * over colo_env_stepper_launch + colo_stream_synchronize, without an interpreter between the calls (measured from
+ * Python: ~9 us per group-step, which bounds a 25 us step).  Philox counters t0, t0 + 1, ...; bit-identical to
+ * stepping the groups one call at a time.  Synchronises every group before it returns.
+ */
+typedef void (*colo_env_pipeline_callback)(void* user, int group, int step);
+int colo_env_pipeline_run(colo_env_stepper* const* steppers, int n_groups, const int* const* action_ring, int ring,
+                          unsigned long long t0, int n_steps, colo_env_pipeline_callback on_timestep, void* user);
 
 /*
  * Step server -- BaseMDP.step (base.py:1279-1317) for an agent living on the host, without a launch and a stream

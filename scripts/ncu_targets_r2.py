@@ -28,10 +28,11 @@ if what == "step":
 elif what in ("backup_c4", "backup_c5"):
     if what == "backup_c4":  # the bench shape: 4,096 MDPs S=512 A=4 (17.2 GB)
         T, R = bench.make_c4_batch(4096, 512, 4, seed=100)
-    else:  # the bench shape: one MDP S=40,000 A=8 (51.2 GB)
+    else:  # the C5 kernel on one MDP S=16,384 A=8 (8.6 GB: what ncu's save / restore handles in minutes; bench: 40,000)
         from colosseum_b200.synth import synth_dense_rows
 
-        T, R = synth_dense_rows(0, 40000, 40000, 8, seed=7)
+        S5 = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+        T, R = synth_dense_rows(0, S5, S5, 8, seed=7)
     vi = dp.BatchedValueIteration(T, R, gamma=0.99, precision="f32")
     vi.sweep(5)
 elif what == "gs":

@@ -608,3 +608,31 @@ def test_out_of_range_action_is_flagged(bm, mode):
     after = env.state.cpu().numpy()
     assert after[5] == before[5] and after[40] == before[40] and int(env.h[5]) == 0 and int(env.h[6]) == 1
     env.step(np.zeros(64, np.int32))  # the flag was cleared: the batch goes on
+
+
+def test_native_pipeline_loop_is_identical(bm):
+    """colo_env_pipeline_run (the recv/send loop inside the library) == the same loop from Python, bit for bit"""
+    import torch
+
+    g = load_instance("c2_deepsea30_prand")
+    tb = MDPTables.from_golden(g)
+    N, G, K = 4096 + 7, 2, 9
+    gen = torch.Generator().manual_seed(3)
+    a = bm.PipelinedBatchedMDP(tb, N, groups=G, seed=11)
+    b = bm.PipelinedBatchedMDP(tb, N, groups=G, seed=11)
+    a.reset(); b.reset()
+    ring = [[torch.randint(0, tb.A, (a.sizes[k],), dtype=torch.int32, generator=gen).pin_memory() for k in range(G)]
+            for _ in range(4)]
+    for k in range(G):
+        a.send(k, ring[0][k])
+    for i in range(1, K):
+        for k in range(G):
+            a.recv(k)
+            a.send(k, ring[i % 4][k])
+    outs_a = [tuple(x.clone() for x in a.recv(k)) for k in range(G)]
+    outs_b = b.run_native(ring, K)
+    for k in range(G):
+        for x, y in zip(outs_a[k], outs_b[k]):
+            assert torch.equal(x, y) or (torch.isnan(x) == torch.isnan(y)).all() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+        assert torch.equal(a.shards[k].state, b.shards[k].state) and a.shards[k].t == b.shards[k].t
+    assert torch.equal(a.get_visitation_counts(), b.get_visitation_counts())

@@ -28,6 +28,43 @@ def _free_port():
     return p
 
 
+class _HostRowsVI:
+    """the local-VI interface of RowShardedValueIteration on CPU tensors: this rank's rows backed up from the full V by
+    the oracle's fp64 arithmetic (test double of the CUDA BatchedValueIteration; the class under test is the sharded
+    solver's partition / exchange logic, which only sees this interface)"""
+
+    def __init__(self, T_rows, R_rows, S, row0, gamma):
+        import torch
+
+        self.T, self.R, self.row0, self.gamma = T_rows.astype(np.float64), R_rows.astype(np.float64), row0, gamma
+        self.V = [torch.zeros((1, S), dtype=torch.float64) for _ in range(2)]
+        self.cur = 0
+        self._res = 0.0
+
+    @property
+    def values(self):
+        return self.V[self.cur]
+
+    def sweep(self, n=1):
+        import torch
+
+        for _ in range(n):
+            v = self.V[self.cur].view(-1).numpy()
+            new = (self.R + self.gamma * (self.T @ v)).max(-1)
+            nxt = 1 - self.cur
+            out = self.V[nxt].view(-1)
+            r1 = self.row0 + len(new)
+            self._res = max(self._res, float(np.abs(new - v[self.row0:r1]).max()))
+            out[self.row0:r1] = torch.from_numpy(new)
+            self.cur = nxt
+
+    def residual(self):
+        import torch
+
+        r, self._res = self._res, 0.0
+        return torch.tensor([r], dtype=torch.float64)
+
+
 def _worker(rank, world, port, S, A, q):
     import torch.distributed as dist
 
@@ -36,6 +73,23 @@ def _worker(rank, world, port, S, A, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import oracle as orc
+        from colosseum_b200.sharded import RowShardedValueIteration
+
+        # ---- the REAL RowShardedValueIteration (transport "nccl" == torch.distributed collectives, gloo here), even
+        # and uneven shards, driven through its public interface with a host-side local VI
+        rs0 = np.random.RandomState(1)
+        Tm = rs0.dirichlet(np.ones(S) * 0.1, size=(S, A)).astype(np.float32)
+        Rm = rs0.uniform(0, 1, (S, A)).astype(np.float32)
+        a0, a1 = shard_range(S, rank, world)
+        sh = RowShardedValueIteration(None, None, S, gamma=0.9, transport="nccl",
+                                      local_vi=_HostRowsVI(Tm[a0:a1], Rm[a0:a1], S, a0, 0.9))
+        assert (sh.row0, sh.row1) == (a0, a1)
+        sh.sweep(25)
+        _, V_ref25 = orc.jacobi_sweeps_f64(Tm, Rm, np.zeros(S), 25, gamma=0.9)
+        ok_class = bool(np.array_equal(sh.values.numpy(), V_ref25))
+        res = sh.residual()  # max over ranks of the local residuals since the start
+        _, V_ref1 = orc.jacobi_sweeps_f64(Tm, Rm, np.zeros(S), 1, gamma=0.9)
+        ok_class = ok_class and abs(res - float(np.abs(V_ref1).max())) < 1e-12
 
         rs = np.random.RandomState(0)  # every rank builds the same MDP, keeps only its rows
         T = rs.dirichlet(np.ones(S) * 0.1, size=(S, A)).astype(np.float32)
@@ -62,7 +116,7 @@ def _worker(rank, world, port, S, A, q):
         st_f, h_f, ty_f, _ = orc.env_reset(ht, N, seed=9, t=0)
         for t in range(1, 6):
             orc.env_step(ht, 0, st_f, h_f, ty_f, action=None, seed=9, t=t)
-        q.put((rank, ok_vi, bool(np.array_equal(full, st_f))))
+        q.put((rank, ok_vi and ok_class, bool(np.array_equal(full, st_f))))
     finally:
         dist.destroy_process_group()
 
