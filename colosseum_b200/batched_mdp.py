@@ -494,7 +494,8 @@ class BatchedMDP:
 
     def set_emission_noise(self, noise_class=None, seed=0, **noise_kwargs):
         """the `noise_class` / `noise_kwargs` of EmissionMap (emission_maps/base.py:85-104): "GaussianUncorrelated"
-        (scale=0.1) or "StudentTUncorrelated" (df=3), by name or by reference class; None switches the noise off"""
+        (scale=0.1), "StudentTUncorrelated" (df=3), "GaussianCorrelated" (scale=0.1) or "StudentTCorrelated" (scale=0.1),
+        by name or by reference class; None switches the noise off"""
         name = None if noise_class is None else getattr(noise_class, "__name__", str(noise_class))
         if name is None:
             self._emit_noise = None
@@ -502,8 +503,20 @@ class BatchedMDP:
             self._emit_noise = (1, float(noise_kwargs.get("scale", 0.1)), int(seed))
         elif name == "StudentTUncorrelated":
             self._emit_noise = (2, float(noise_kwargs.get("df", 3)), int(seed))
+        elif name in ("GaussianCorrelated", "StudentTCorrelated"):
+            # the covariance the reference draws ONCE per emission map (noises/gaussian_correlated.py:14-17): the same
+            # scipy call on the same RandomState(seed) -> the same W; its Cholesky factor goes to the device
+            import scipy.stats
+
+            D = int(self._emit_table.shape[-1])
+            rng = np.random.RandomState(int(seed))
+            W = np.atleast_2d(scipy.stats.wishart(scale=[float(noise_kwargs.get("scale", 0.1))] * D).rvs(1, rng))
+            self._emit_cov = W
+            chol = np.linalg.cholesky(W).astype(np.float32)
+            self._emit_chol = self.torch.from_numpy(np.ascontiguousarray(chol)).cuda()
+            self._emit_noise = (3 if name == "GaussianCorrelated" else 4, float(noise_kwargs.get("df", 1.0)), int(seed))
         else:
-            raise NotImplementedError(f"{name}: only the uncorrelated Gaussian / Student-t noises are built")
+            raise NotImplementedError(f"{name}: unknown noise class")
         self._emit_t = 0
 
     def emit_observations(self):
@@ -515,7 +528,14 @@ class BatchedMDP:
                                                 _cabi.ptr(self._emit_out), _cabi.current_stream())
         _cabi.check(rc, "colo_emit_observations")
         noise = getattr(self, "_emit_noise", None)
-        if noise is not None:
+        if noise is not None and noise[0] >= 3:
+            kind, df, seed = noise
+            rc = _cabi.lib().colo_emit_noise_correlated(_cabi.ptr(self._emit_out), _cabi.ptr(self.step_type), _cabi.ptr(self.h),
+                                                        self.n_envs, self.tables.H, D, _cabi.ptr(self._emit_chol), kind - 2, df,
+                                                        seed, self._emit_t, self.env_offset, _cabi.current_stream())
+            _cabi.check(rc, "colo_emit_noise_correlated")
+            self._emit_t += 1
+        elif noise is not None:
             kind, param, seed = noise
             period = D if kind == 1 else max(1, int(np.prod(self._emit_shape[1:])))
             rc = _cabi.lib().colo_emit_noise(_cabi.ptr(self._emit_out), _cabi.ptr(self.step_type), _cabi.ptr(self.h),

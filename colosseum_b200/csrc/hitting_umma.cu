@@ -41,6 +41,7 @@ constexpr int UM_BK = 32;        // fp32 per k-block == one 128-byte swizzle row
 constexpr int UM_EPI_WARPS = 8;   // two per TMEM lane quarter, each owning half of the tile's target columns
 constexpr int UM_THREADS = 64 + 32 * UM_EPI_WARPS;  // warp 0 TMA, warp 1 MMA + TMEM, warps 2.. epilogue
 constexpr int UM_T_TILE = UM_BM * UM_BK * 4;  // 16 KiB
+constexpr int UM_NH = 3;  // hi-chain accumulators in flight: the drain of a group has two groups of MMAs to hide behind
 
 struct UmmaSweepArgs {
   const float* E_in;   // [K][e_stride] fp32 iterate the sweep reads (its split twin is behind mapE, half `in_buf`)
@@ -87,6 +88,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint16_t mask) {
+  // multicast: the box lands at the same shared-memory offset, and completes on the mbarrier at the same offset, in
+  // every CTA of the cluster named by `mask`
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], "
+      "[%4], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -113,6 +133,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -150,7 +183,7 @@ struct UmmaCfg {
   static constexpr int STAGE = 2 * UM_T_TILE + 2 * E_TILE;  // 64 KiB (BN = 128) / 48 KiB (BN = 64)
   static constexpr int NS = BN == 128 ? 3 : 4;
   static constexpr int SMEM = NS * STAGE + 1024 /* alignment slack */ + 256 /* barriers, tmem pointer */;
-  static constexpr int NCOLS = 4 * BN;  // two accumulator buffers x {hi chain, lo chain} x BN columns
+  static constexpr int NCOLS = 4 * BN;  // UM_NH = 3 hi-chain accumulators + 1 lo-chain accumulator, BN columns each
 };
 
 // Why the accumulators are flushed.  The tensor core adds into its fp32 accumulator with TRUNCATION (round toward
@@ -162,7 +195,13 @@ struct UmmaCfg {
 // epilogue warps drain the accumulators into registers with round-to-nearest adds and the next chain restarts at zero:
 // the bias is then that of `4 * flush` MMAs on a PARTIAL sum, ~1e-7 relative for flush = 1.  The accumulators are
 // double buffered in TMEM (4 * BN columns), so the drain of one group overlaps the MMAs of the next.
-template <int BN>
+// MC = true: launched as 2 x 2 thread-block clusters.  The two CTAs of a cluster row (same state tile, neighbouring target
+// tiles) need the same T tiles, the two of a cluster column (same target tile) the same E tiles: every CTA loads HALF of
+// each (64 T rows, BN/2 E rows, hi and lo) and the TMA multicasts it into both CTAs that need it -- the same 64 KiB land
+// in every CTA's stage, but each byte is read from L2 once per pair instead of once per CTA (the L2 feed is what the
+// kernel waits for at S >= 2,048).  A stage may be refilled only when all three writers' consumers have released it:
+// the MMA issuer's tcgen05.commit is multicast to itself and to its row / column peers (empty barriers count 3).
+template <int BN, bool MC>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapE,
                     const UmmaSweepArgs p) {
@@ -174,9 +213,9 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
   unsigned char* smem = (unsigned char*)(((uintptr_t)umma_smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024 B
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE);
   uint64_t* empty = full + NS;
-  uint64_t* acc_full = empty + NS;   // [2] MMA -> epilogue: the group's accumulators are final
-  uint64_t* acc_empty = acc_full + 2;  // [2] epilogue -> MMA: drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = empty + NS;   // [NH] MMA -> epilogue: the group's accumulators are final
+  uint64_t* acc_empty = acc_full + UM_NH;  // [NH] epilogue -> MMA: drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + UM_NH);
   __shared__ int s_any_active;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -193,7 +232,7 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
     for (int n = threadIdx.x; n < BN; n += UM_THREADS)
       if (k0 + n < K && p.active[k0 + n]) s_any_active = 1;
   __syncthreads();
-  if (!s_any_active) {
+  if (!MC && !s_any_active) {  // (a cluster keeps every CTA in the protocol: its peers wait for this CTA's halves)
     for (int i = threadIdx.x; i < UM_BM * BN; i += UM_THREADS) {
       const int m = i % UM_BM, n = i / UM_BM;
       const int s = s0 + m, k = k0 + n;
@@ -215,9 +254,9 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapE) : "memory");
     for (int i = 0; i < NS; ++i) {
       mbar_init(full + i, 1);
-      mbar_init(empty + i, 1);
+      mbar_init(empty + i, MC ? 3 : 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < UM_NH; ++i) {
       mbar_init(acc_full + i, 1);
       mbar_init(acc_empty + i, UM_EPI_WARPS);
     }
@@ -232,6 +271,11 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // cluster geometry (MC): rank = cx + 2 cy; row peer = rank ^ 1 (same states), column peer = rank ^ 2 (same targets)
+  const int cx = blockIdx.x & 1, cy = blockIdx.y & 1;
+  const uint16_t mask_T = (uint16_t)(0x3u << (2 * cy)), mask_E = (uint16_t)(0x5u << cx);
+  const uint16_t mask_release = (uint16_t)((1u << (cx + 2 * cy)) | (1u << ((cx ^ 1) + 2 * cy)) | (1u << (cx + 2 * (cy ^ 1))));
+  if (MC) cluster_sync_all();  // every CTA's barriers are initialised before a peer's copy or commit can reach them
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
@@ -243,13 +287,24 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
         mbar_expect_tx(full + st, (uint32_t)Cfg::STAGE);
         const int a = it / nkb, kb = it - a * nkb;
         unsigned char* sb = smem + st * Cfg::STAGE;
-        tma_load_2d(sb, &mapT, kb * UM_BK, a * p.Sm + s0, full + st);
-        tma_load_2d(sb + UM_T_TILE, &mapT, kb * UM_BK, (A + a) * p.Sm + s0, full + st);
+        if (MC) {
+          // my half of the shared tiles: 64 of the 128 state rows (mapT box {32, 64}), BN/2 of the BN target rows
+          // (mapE box {32, BN/2}), each multicast to the two CTAs that use it
+          const int tr = 64 * cx, er = (BN / 2) * cy;
+          tma_load_2d_mc(sb + tr * 128, &mapT, kb * UM_BK, a * p.Sm + s0 + tr, full + st, mask_T);
+          tma_load_2d_mc(sb + UM_T_TILE + tr * 128, &mapT, kb * UM_BK, (A + a) * p.Sm + s0 + tr, full + st, mask_T);
+          tma_load_2d_mc(sb + 2 * UM_T_TILE + er * 128, &mapE, kb * UM_BK, (p.in_buf * 2) * p.Kp + k0 + er, full + st, mask_E);
+          tma_load_2d_mc(sb + 2 * UM_T_TILE + Cfg::E_TILE + er * 128, &mapE, kb * UM_BK, (p.in_buf * 2 + 1) * p.Kp + k0 + er,
+                         full + st, mask_E);
+        } else {
+          tma_load_2d(sb, &mapT, kb * UM_BK, a * p.Sm + s0, full + st);
+          tma_load_2d(sb + UM_T_TILE, &mapT, kb * UM_BK, (A + a) * p.Sm + s0, full + st);
 #pragma unroll
-        for (int h = 0; h < BN / 64; ++h) {
-          tma_load_2d(sb + 2 * UM_T_TILE + h * 8192, &mapE, kb * UM_BK, (p.in_buf * 2) * p.Kp + k0 + 64 * h, full + st);
-          tma_load_2d(sb + 2 * UM_T_TILE + Cfg::E_TILE + h * 8192, &mapE, kb * UM_BK,
-                      (p.in_buf * 2 + 1) * p.Kp + k0 + 64 * h, full + st);
+          for (int h = 0; h < BN / 64; ++h) {
+            tma_load_2d(sb + 2 * UM_T_TILE + h * 8192, &mapE, kb * UM_BK, (p.in_buf * 2) * p.Kp + k0 + 64 * h, full + st);
+            tma_load_2d(sb + 2 * UM_T_TILE + Cfg::E_TILE + h * 8192, &mapE, kb * UM_BK,
+                        (p.in_buf * 2 + 1) * p.Kp + k0 + 64 * h, full + st);
+          }
         }
       }
     }
@@ -259,12 +314,15 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
       int it = 0, f = 0;
       for (int a = 0; a < A; ++a)
         for (int g = 0; g < gpa; ++g, ++f) {
-          const int b = f & 1;
-          mbar_wait(acc_empty + b, (((uint32_t)(f >> 1)) & 1u) ^ 1u);  // the epilogue has drained this buffer
+          const int b = f % UM_NH;
+          mbar_wait(acc_empty + b, (((uint32_t)(f / UM_NH)) & 1u) ^ 1u);  // the epilogue has drained this buffer
+          // the single lo-chain buffer is drained with the LAST group of the previous action: wait for that drain
+          // before the first MMA of a new action overwrites it (never more than one completion behind: see NH)
+          if (g == 0 && f > 0) mbar_wait(acc_empty + (f - 1) % UM_NH, ((uint32_t)((f - 1) / UM_NH)) & 1u);
           tc_fence_after();
-          // TMEM columns: [0, 2BN) the hi-chain accumulators of even / odd groups, [2BN, 4BN) the lo-chain
-          // accumulators of even / odd ACTIONS (the small products keep one chain per action, see above)
-          const uint32_t d_hi = tmem_base + (uint32_t)(b * BN), d_lo = tmem_base + (uint32_t)((2 + (a & 1)) * BN);
+          // TMEM columns: [0, NH*BN) a ring of NH hi-chain accumulators (one per group in flight), [NH*BN, (NH+1)*BN)
+          // the lo-chain accumulator of the current action (the small products keep one chain per action, see above)
+          const uint32_t d_hi = tmem_base + (uint32_t)(b * BN), d_lo = tmem_base + (uint32_t)(UM_NH * BN);
           const int kb_end = min(nkb, (g + 1) * G);
           for (int kb = g * G; kb < kb_end; ++kb, ++it) {
             const int st = it % NS;
@@ -283,7 +341,8 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
               umma_tf32(d_lo, d_th + adv, d_el + adv, idesc, (first && g == 0 && k == 0) ? 0u : 1u);
               umma_tf32(d_lo, d_tl + adv, d_eh + adv, idesc, 1u);
             }
-            umma_commit(empty + st);  // the stage is free once these MMAs have read it
+            if (MC) umma_commit_mc(empty + st, mask_release);  // ... in this CTA and in the two peers that write into it
+            else umma_commit(empty + st);  // the stage is free once these MMAs have read it
           }
           umma_commit(acc_full + b);  // this group's accumulators are final
         }
@@ -305,34 +364,30 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
 #pragma unroll
       for (int i = 0; i < CW; ++i) acc[i] = 0.f;
       for (int g = 0; g < gpa; ++g, ++f) {
-        const int b = f & 1;
-        mbar_wait(acc_full + b, ((uint32_t)(f >> 1)) & 1u);
+        const int b = f % UM_NH;
+        mbar_wait(acc_full + b, ((uint32_t)(f / UM_NH)) & 1u);
         tc_fence_after();
         const uint32_t t_hi = lane_base + (uint32_t)(b * BN);
+        {  // the thread's CW columns of the group: CW / 32 loads of 32 columns in flight, ONE wait
+          float vh[CW / 32][32];
 #pragma unroll
-        for (int c = 0; c < CW / 32; ++c) {  // 2 loads in flight, one wait
-          float vh[2][16];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) tmem_ld16(t_hi + (uint32_t)(c * 32 + u * 16), vh[u]);
+          for (int c = 0; c < CW / 32; ++c) tmem_ld32(t_hi + (uint32_t)(c * 32), vh[c]);
           tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+          for (int c = 0; c < CW / 32; ++c)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[c * 32 + u * 16 + i] += vh[u][i];
+            for (int i = 0; i < 32; ++i) acc[c * 32 + i] += vh[c][i];
         }
         if (g == gpa - 1) {  // the action's last group: its lo chain is final too (commits are cumulative)
-          const uint32_t t_lo = lane_base + (uint32_t)((2 + (a & 1)) * BN);
+          const uint32_t t_lo = lane_base + (uint32_t)(UM_NH * BN);
+          float vl[CW / 32][32];
 #pragma unroll
-          for (int c = 0; c < CW / 32; ++c) {
-            float vl[2][16];
+          for (int c = 0; c < CW / 32; ++c) tmem_ld32(t_lo + (uint32_t)(c * 32), vl[c]);
+          tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 2; ++u) tmem_ld16(t_lo + (uint32_t)(c * 32 + u * 16), vl[u]);
-            tmem_ld_wait();
+          for (int c = 0; c < CW / 32; ++c)
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-              for (int i = 0; i < 16; ++i) acc[c * 32 + u * 16 + i] += vl[u][i];
-          }
+            for (int i = 0; i < 32; ++i) acc[c * 32 + i] += vl[c][i];
         }
         tc_fence_before();
         __syncwarp();
@@ -340,6 +395,14 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
       }
 #pragma unroll
       for (int i = 0; i < CW; ++i) best[i] = fminf(best[i], 1.f + acc[i]);
+    }
+    // the previous iterate of this thread's CW (target, state) pairs: every load in flight before any is used (one
+    // dependent L2 round trip per column would cost more than the tile's MMAs at S ~ 1,000)
+    float old[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      const int k = k0 + half * CW + i;
+      old[i] = (k < K && s < S) ? p.E_in[(size_t)k * p.e_stride + s] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -349,15 +412,14 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
         const bool act = p.active == nullptr || p.active[k] != 0;
         float dlt = 0.f;
         if (s < S) {
-          const float old = p.E_in[(size_t)k * p.e_stride + s];
           float nv = (s == tgt) ? 0.f : best[i];
-          if (!act) nv = old;
+          if (!act) nv = old[i];
           p.E_out[(size_t)k * p.e_stride + s] = nv;
           float hi, lo;
           tf32_split(nv, hi, lo);
           p.E_split_out[(size_t)k * p.Sk + s] = hi;
           p.E_split_out[((size_t)p.Kp + k) * p.Sk + s] = lo;
-          dlt = fabsf(nv - old);
+          dlt = fabsf(nv - old[i]);
           if (p.max_value > 0.f && nv > p.max_value && p.overflow_flag) *p.overflow_flag = 1;
         }
         const unsigned m = __reduce_max_sync(FULL, __float_as_uint(dlt));  // dlt >= 0: IEEE order == unsigned order
@@ -368,6 +430,7 @@ hitting_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_const
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // no CTA leaves while a peer's copy or commit may still be addressed to it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::NCOLS)
@@ -433,6 +496,7 @@ struct UmmaPlan {
   float* E_split = nullptr;  // [2][2][Kp][Sk]
   CUtensorMap mapT, mapE;
   int S = 0, A = 0, K = 0, Sm = 0, Sk = 0, Kp = 0, BN = 0, cur = 0, flush = 1;
+  bool mc = false;  // 2 x 2 clusters with multicast TMA
 };
 
 bool hitting_umma_supported(int S, int A, int K) {
@@ -452,9 +516,18 @@ int hitting_umma_plan(const float* T, int S, int A, int K, UmmaPlan** out, cudaS
     const char* bn = getenv("COLO_UMMA_BN");
     if (bn && (atoi(bn) == 64 || atoi(bn) == 128)) pl->BN = atoi(bn);
   }
-  pl->Sm = (S + UM_BM - 1) / UM_BM * UM_BM;
+  {
+    // 2 x 2 clusters with multicast TMA halve the L2 reads.  Measured (scripts/umma_probe.py, three hi accumulators in
+    // flight): S = 2,048 A = 8: 615 us per sweep with clusters, 741 without; no difference at S <= 1,024, where the
+    // padding to whole clusters is pure overhead.  On when the grid fills the machine; COLO_UMMA_CLUSTER=0/1 forces it.
+    const char* e = getenv("COLO_UMMA_CLUSTER");
+    const long long tiles = (long long)((K + pl->BN - 1) / pl->BN) * ((S + UM_BM - 1) / UM_BM);
+    pl->mc = e ? atoi(e) == 1 : tiles >= (long long)sm_count();
+  }
+  const int m_unit = pl->mc ? 2 * UM_BM : UM_BM, n_unit = pl->mc ? 2 * pl->BN : pl->BN;  // whole 2 x 2 clusters
+  pl->Sm = (S + m_unit - 1) / m_unit * m_unit;
   pl->Sk = (S + UM_BK - 1) / UM_BK * UM_BK;
-  pl->Kp = (K + pl->BN - 1) / pl->BN * pl->BN;
+  pl->Kp = (K + n_unit - 1) / n_unit * n_unit;
   const size_t t_elems = (size_t)2 * A * pl->Sm * pl->Sk, e_elems = (size_t)4 * pl->Kp * pl->Sk;
   cudaError_t e = cudaMallocAsync((void**)&pl->T_split, t_elems * 4, st);
   if (e == cudaSuccess) e = cudaMallocAsync((void**)&pl->E_split, e_elems * 4, st);
@@ -469,8 +542,8 @@ int hitting_umma_plan(const float* T, int S, int A, int K, UmmaPlan** out, cudaS
   const int grid = (int)((n + 255) / 256 < (long long)sm_count() * 16 ? (n + 255) / 256 : (long long)sm_count() * 16);
   umma_split_T_kernel<<<grid, 256, 0, st>>>(T, S, A, pl->Sm, pl->Sk, pl->T_split);
   int r = check_launch("umma_split_T_kernel");
-  if (r == COLO_OK) r = make_map_2d(&pl->mapT, pl->T_split, pl->Sk, (long long)2 * A * pl->Sm, UM_BM);
-  if (r == COLO_OK) r = make_map_2d(&pl->mapE, pl->E_split, pl->Sk, (long long)4 * pl->Kp, 64);
+  if (r == COLO_OK) r = make_map_2d(&pl->mapT, pl->T_split, pl->Sk, (long long)2 * A * pl->Sm, pl->mc ? UM_BM / 2 : UM_BM);
+  if (r == COLO_OK) r = make_map_2d(&pl->mapE, pl->E_split, pl->Sk, (long long)4 * pl->Kp, pl->mc ? pl->BN / 2 : 64);
   if (r != COLO_OK) {
     cudaFreeAsync(pl->T_split, st);
     cudaFreeAsync(pl->E_split, st);
@@ -521,13 +594,27 @@ int hitting_umma_sweep(UmmaPlan* pl, const float* E_in, float* E_out, long long 
   a.max_value = (float)max_value; a.overflow_flag = overflow_flag;
   a.flush = pl->flush;
   dim3 grid(pl->Kp / pl->BN, pl->Sm / UM_BM);
-  if (pl->BN == 128) {
-    { const int es = ensure_dynamic_smem((const void*)hitting_umma_kernel<128>, UmmaCfg<128>::SMEM); if (es != COLO_OK) return es; }
-    hitting_umma_kernel<128><<<grid, UM_THREADS, UmmaCfg<128>::SMEM, st>>>(pl->mapT, pl->mapE, a);
-  } else {
-    { const int es = ensure_dynamic_smem((const void*)hitting_umma_kernel<64>, UmmaCfg<64>::SMEM); if (es != COLO_OK) return es; }
-    hitting_umma_kernel<64><<<grid, UM_THREADS, UmmaCfg<64>::SMEM, st>>>(pl->mapT, pl->mapE, a);
-  }
+  auto launch = [&](auto kern, size_t smem) -> int {
+    { const int es = ensure_dynamic_smem((const void*)kern, smem); if (es != COLO_OK) return es; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(UM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl->mc ? 2 : 1;
+    attr[0].val.clusterDim.y = pl->mc ? 2 : 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    COLO_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, pl->mapT, pl->mapE, a));
+    return COLO_OK;
+  };
+  int r;
+  if (pl->BN == 128) r = pl->mc ? launch(hitting_umma_kernel<128, true>, UmmaCfg<128>::SMEM) : launch(hitting_umma_kernel<128, false>, UmmaCfg<128>::SMEM);
+  else r = pl->mc ? launch(hitting_umma_kernel<64, true>, UmmaCfg<64>::SMEM) : launch(hitting_umma_kernel<64, false>, UmmaCfg<64>::SMEM);
+  if (r != COLO_OK) return r;
   pl->cur ^= 1;
   return check_launch("hitting_umma_kernel");
 }

@@ -148,6 +148,46 @@ __global__ void __launch_bounds__(256) emit_noise_kernel(float* __restrict__ out
   }
 }
 
+// Correlated emission noises (colosseum/noises/gaussian_correlated.py:9-17, student_t_correlated.py:9-17): one covariance
+// W ~ Wishart(df = D, scale * I) is drawn ONCE per emission map -- on the host, with the reference's own scipy call --
+// and every observation then receives x ~ N(0, W) (kind 1) or the multivariate Student-t with shape W and df degrees of
+// freedom, x = L z / sqrt(chi2_df / df) (kind 2; scipy's default df = 1).  L = chol(W) lower triangular f32 [D,D]; one
+// CTA per env: the D standard normals of the env go to shared memory, thread i forms row i of L z.
+__global__ void __launch_bounds__(256) emit_noise_correlated_kernel(float* __restrict__ out,
+                                                                    const unsigned char* __restrict__ step_type,
+                                                                    const int* __restrict__ h, long long N, int H, int D,
+                                                                    const float* __restrict__ L, int kind, double df,
+                                                                    unsigned long long seed, unsigned long long t,
+                                                                    unsigned long long env0) {
+  extern __shared__ float zs[];
+  for (long long e = blockIdx.x; e < N; e += gridDim.x) {
+    const bool skip = H > 0 && (h[e] >= H || step_type[e] == COLO_STEP_LAST);  // zeros past the horizon carry no noise
+    if (!skip) {
+      for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        const uint64_t elem = (env0 + (uint64_t)e) * (uint64_t)D + (uint64_t)j;
+        const Philox4 w = philox4x32_10(seed ^ 0x2545F4914F6CDD1DULL, elem, t);
+        const double u1 = u53(w.w[0], w.w[1]) + 1.1102230246251565e-16, u2 = (double)w.w[2] * (1.0 / 4294967296.0);
+        zs[j] = (float)(sqrt(-2.0 * log(u1)) * cospi(2.0 * u2));
+      }
+    }
+    __syncthreads();
+    if (!skip) {
+      float scale = 1.f;
+      if (kind == 2) {  // one chi-square per observation (scipy multivariate_t: x = z_W / sqrt(chi2_df / df))
+        const double g = gamma_draw(0.5 * df, seed ^ 0x9FB21C651E98DF25ULL, env0 + (uint64_t)e, t);
+        scale = (float)(1.0 / sqrt(2.0 * g / df));
+      }
+      for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float* row = L + (size_t)i * D;
+        float acc = 0.f;
+        for (int j = 0; j <= i; ++j) acc = fmaf(__ldg(row + j), zs[j], acc);
+        out[(size_t)e * D + i] += acc * scale;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // N_N.sample (conjugate_rewards.py:119-127): Normal(mu, scale = tau) -> float32, rows laid out as (mu, tau, -, -)
 __global__ void __launch_bounds__(256) nn_rows_kernel(const float* __restrict__ hyper, long long rows, long long row0,
                                                       unsigned long long seed, unsigned long long t,
@@ -184,6 +224,20 @@ extern "C" int colo_emit_noise(float* out, const unsigned char* step_type, const
   colo::emit_noise_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(out, step_type, h, N, H, D, period,
                                                                                                 kind, param, seed, t, env0);
   return colo::check_launch("emit_noise_kernel");
+}
+
+extern "C" int colo_emit_noise_correlated(float* out, const unsigned char* step_type, const int* h, long long N, int H, int D,
+                                          const float* chol, int kind, double df, unsigned long long seed,
+                                          unsigned long long t, unsigned long long env0, void* stream) {
+  COLO_ARG_CHECK(out && step_type && h && chol && N >= 0 && D > 0 && D <= 12288 && (kind == 1 || kind == 2) && df > 0,
+                 "out, step_type, h, chol, N, 0 < D <= 12288, kind in {1,2}, df > 0");
+  if (N == 0) return COLO_OK;
+  const long long cap = (long long)colo::sm_count() * 8;
+  const size_t smem = (size_t)D * sizeof(float);
+  { const int es = colo::ensure_dynamic_smem((const void*)colo::emit_noise_correlated_kernel, smem); if (es != COLO_OK) return es; }
+  colo::emit_noise_correlated_kernel<<<(int)(N < cap ? N : cap), 256, smem, (cudaStream_t)stream>>>(out, step_type, h, N, H, D, chol,
+                                                                                                  kind, df, seed, t, env0);
+  return colo::check_launch("emit_noise_correlated_kernel");
 }
 
 extern "C" int colo_sample_nig_rewards(const float* hyper, long long rows, long long row0, unsigned long long seed,

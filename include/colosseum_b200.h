@@ -509,11 +509,23 @@ int colo_emit_observations(const float* table, const int* state, const int* h, c
  * GaussianUncorrelated(scale = param) (colosseum/noises/gaussian_uncorrelated.py), period = D; kind 2:
  * StudentTUncorrelated(df = param) (noises/student_t_uncorrelated.py -- sic: one draw per slice along the first axis of
  * the observation, i.e. period = prod(shape[1:]), 1 for vector observations).  Element j of env e uses Philox counter
- * ((env0 + e) * period + j % period, t).  Distributional parity.  The correlated variants are not built.
+ * ((env0 + e) * period + j % period, t).  Distributional parity.  Correlated variants: colo_emit_noise_correlated.
  */
 int colo_emit_noise(float* out, const unsigned char* step_type, const int* h, long long N, int H, int D, int period,
                     int kind, double param, unsigned long long seed, unsigned long long t, unsigned long long env0,
                     void* stream);
+/*
+ * colo_emit_noise_correlated -- the correlated noises (colosseum/noises/gaussian_correlated.py:9-17,
+ * student_t_correlated.py:9-17) on top of colo_emit_observations' rows, in place: chol f32 [D,D] is the lower Cholesky
+ * factor of the covariance W the reference draws once per emission map from Wishart(df = D, scale * I) (drawn by the
+ * caller with the reference's own scipy call and RandomState(seed): the SAME W); kind 1: x ~ N(0, W); kind 2:
+ * multivariate Student-t with shape W and `df` degrees of freedom (scipy's default df = 1).  Philox counter
+ * ((env0 + e) * D + j, t) for the normals, (env0 + e, t) for the chi-square.  All-zero terminal observations stay zero.
+ * Distributional parity.
+ */
+int colo_emit_noise_correlated(float* out, const unsigned char* step_type, const int* h, long long N, int H, int D,
+                               const float* chol, int kind, double df, unsigned long long seed, unsigned long long t,
+                               unsigned long long env0, void* stream);
 int colo_env_step_succ(const colo_mdp_tables* tb, const colo_env_batch* batch, int random_actions,
                        const double* u_next, const float* u_rew, unsigned long long t, int auto_reset,
                        void* stream);

@@ -77,9 +77,10 @@ for name, T in cases.items():
     refs[name] = fp64_sweeps(T, targets, N_ACC)
 torch.cuda.synchronize()
 emit({"event": "fp64 references done"})
-for flush, bn in ((1, 0), (2, 0), (4, 0), (1, 128), (1, 64)):
+for flush, bn, mc in ((1, 0, 1), (1, 0, 0), (2, 0, 1), (1, 128, 1), (1, 64, 1)):
     os.environ["COLO_UMMA_FLUSH"] = str(flush)
     os.environ["COLO_UMMA_BN"] = str(bn)
+    os.environ["COLO_UMMA_CLUSTER"] = str(mc)
     for name, T in cases.items():
         S, A = T.shape[0], T.shape[1]
         targets = torch.arange(S, dtype=torch.int32, device="cuda")
@@ -89,7 +90,7 @@ for flush, bn in ((1, 0), (2, 0), (4, 0), (1, 128), (1, 64)):
         flop = 2.0 * S * A * S * S
         got = run(T, targets, N_ACC).double()
         ref = refs[name]
-        emit({"flush": flush, "bn": bn, "case": name, "S": S, "A": A, "us_per_sweep": us, "tflops_fp32_equiv": flop / us / 1e6,
+        emit({"flush": flush, "bn": bn, "cluster": mc, "case": name, "S": S, "A": A, "us_per_sweep": us, "tflops_fp32_equiv": flop / us / 1e6,
               "tensor_tflops_3x": 3 * flop / us / 1e6,
               f"rel_err_after_{N_ACC}_sweeps": float((got - ref).abs().max() / ref.abs().max()),
               "mean_signed_rel": float((got - ref).sum() / ref.abs().sum())})

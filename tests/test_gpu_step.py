@@ -507,7 +507,44 @@ def test_emission_noise_distributions(bm):
     assert bool((env.step_type == 2).all()) and float(np.abs(d).max()) == 0.0
     env.set_emission_noise(None)
     with pytest.raises(NotImplementedError):
-        env.set_emission_noise("GaussianCorrelated")
+        env.set_emission_noise("NoSuchNoise")
+
+
+def test_correlated_emission_noises(bm):
+    """GaussianCorrelated / StudentTCorrelated (noises/gaussian_correlated.py:9-17, student_t_correlated.py:9-17): the
+    covariance W is the reference's own Wishart draw (same scipy call, same RandomState(seed)); the device samples
+    x = L z [/ sqrt(chi2_df / df)].  Checked: W equals scipy's draw; the empirical covariance of 200k Gaussian samples
+    equals W; every marginal of the Gaussian is N(0, W_ii) and of the Student-t (df = 3) is sqrt(W_ii) * t_3; terminal
+    observations stay zero."""
+    import scipy.stats
+
+    tb = MDPTables.from_golden(load_instance("c1_riverswim_epi"))
+    N, D = 200000, 5
+    env = bm.BatchedMDP(tb, N, mode="succ", seed=2)
+    env.set_emission_table(np.zeros((tb.H, tb.S, D), np.float32))
+    env.reset()
+    env.set_emission_noise("GaussianCorrelated", seed=7, scale=0.1)
+    W = np.atleast_2d(scipy.stats.wishart(scale=[0.1] * D).rvs(1, np.random.RandomState(7)))
+    assert np.array_equal(env._emit_cov, W)
+    x = env.emit_observations().cpu().numpy().astype(np.float64)
+    y = env.emit_observations().cpu().numpy().astype(np.float64)
+    assert not np.array_equal(x, y)
+    C_ = np.cov(x.T)
+    assert np.abs(C_ - W).max() < 0.02 * np.abs(W).max(), (C_, W)
+    for i in range(D):
+        assert scipy.stats.kstest(x[:, i], scipy.stats.norm(0, np.sqrt(W[i, i])).cdf).pvalue > 1e-4, i
+    env.set_emission_noise("StudentTCorrelated", seed=7, scale=0.1, df=3)
+    z = env.emit_observations().cpu().numpy().astype(np.float64)
+    for i in range(D):
+        assert scipy.stats.kstest(z[:, i] / np.sqrt(W[i, i]), scipy.stats.t(3).cdf).pvalue > 1e-4, i
+    # dependence through the shared chi-square and through L: |corr| of the first two features follows W
+    r_w = W[0, 1] / np.sqrt(W[0, 0] * W[1, 1])
+    assert abs(np.corrcoef(x[:, 0], x[:, 1])[0, 1] - r_w) < 0.02
+    for _ in range(tb.H):
+        env.step_async(None, auto_reset=True)
+    d = env.emit_observations().cpu().numpy()
+    last = (env.step_type == 2).cpu().numpy()
+    assert last.any() and float(np.abs(d[last]).max()) == 0.0
 
 
 @pytest.mark.parametrize("mode", ["dense_f32", "dense_f64"])

@@ -122,3 +122,22 @@ def test_diameter_dense_through_umma(monkeypatch):
     d, sweeps = hd.get_diameter(T, False, precision="f32", epsilon=2e-5, return_sweeps=True)
     assert abs(d - d_ref) < 1e-4 * d_ref, (d, d_ref)
     assert sweeps > 3 and _cabi.lib().colo_launch_count() - n0 >= sweeps
+
+
+@pytest.mark.parametrize("cluster", ["0", "1"])
+@pytest.mark.parametrize("bn", ["64", "128"])
+def test_umma_cluster_multicast_is_identical(monkeypatch, cluster, bn):
+    """2 x 2 thread-block clusters with multicast TMA (each CTA loads half of the T tile and half of the E tile for
+    the pair that shares it) against one CTA per tile: the same sweeps bit for bit, on a grid with odd tile counts
+    (padding to whole clusters) and both tile widths"""
+    monkeypatch.setenv("COLO_UMMA_BN", bn)
+    S, A, K = 400, 3, 330
+    T = dirichlet_T(S, A, 0.2, 9)
+    targets = np.random.RandomState(2).permutation(S)[:K].astype(np.int32)
+    monkeypatch.setenv("COLO_UMMA_CLUSTER", "0")
+    base = umma_sweeps(T, targets, 7)
+    monkeypatch.setenv("COLO_UMMA_CLUSTER", cluster)
+    got = umma_sweeps(T, targets, 7)
+    assert np.array_equal(got, base)
+    ref = sweeps_f64(T, targets, 7)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-6
