@@ -114,6 +114,20 @@ class PsrlArgs(C.Structure):
     ]
 
 
+class Ucrl2Args(C.Structure):
+    """mirror of `colo_ucrl2_args`"""
+
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_ulonglong), ("env0", C.c_ulonglong),
+        ("state", C.c_void_p), ("t", C.c_void_p), ("cum_reward", C.c_void_p), ("Q", C.c_void_p),
+        ("Nsas", C.c_void_p), ("Nsa", C.c_void_p), ("P", C.c_void_p), ("est_r", C.c_void_p), ("var_r", C.c_void_p),
+        ("hold", C.c_void_p), ("nu", C.c_void_p), ("seen", C.c_void_p), ("ep_len", C.c_void_p), ("ep_log", C.c_void_p),
+        ("log_cap", C.c_int), ("ended", C.c_void_p), ("iteration", C.c_void_p), ("episode", C.c_void_p),
+        ("delta", C.c_void_p), ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong),
+        ("trace_steps", C.c_int),
+    ]
+
+
 class SuiteInstance(C.Structure):
     """mirror of `colo_suite_instance` (HOST pointers)"""
 
@@ -207,6 +221,9 @@ PROTOTYPES = {
     "colo_qlearning_episodic_steps": (_I, [C.POINTER(MdpTables), C.POINTER(QLearningArgs), _I, _ULL, _P]),
     "colo_qlearning_continuous_steps": (_I, [C.POINTER(MdpTables), C.POINTER(QLearningArgs), _I, _ULL, _P]),
     "colo_psrl_episodic_steps": (_I, [C.POINTER(MdpTables), C.POINTER(PsrlArgs), _I, _ULL, _P]),
+    "colo_ucrl2_steps": (_I, [C.POINTER(MdpTables), C.POINTER(Ucrl2Args), _LL, _P]),
+    "colo_ucrl2_bounds": (_I, [C.POINTER(Ucrl2Args), _I, _I, _P, _I, _D, _D, _D, _I, _P, _P, _P]),
+    "colo_ucrl2_model_update": (_I, [C.POINTER(Ucrl2Args), _I, _I, _P, _I, _P]),
     "colo_sample_nig_rewards": (_I, [_P, _LL, _LL, _ULL, _ULL, _P, _P]),
     "colo_sample_nn_rewards": (_I, [_P, _LL, _LL, _ULL, _ULL, _P, _P]),
     "colo_emit_noise": (_I, [_P, _P, _P, _LL, _I, _I, _I, _I, _D, _ULL, _ULL, _ULL, _P]),
@@ -216,6 +233,8 @@ PROTOTYPES = {
     "colo_extended_vi_work_bytes": (C.c_size_t, [_I, _I]),
     "colo_extended_vi_f32": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P]),
     "colo_extended_vi_f64acc": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P]),
+    "colo_extended_vi_batched_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P, _P]),
+    "colo_extended_vi_batched_f64acc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P, _P]),
     "colo_sample_dirichlet_rows": (_I, [_P, _LL, _I, _LL, _ULL, _ULL, _P, _P]),
     "colo_sample_dirichlet_rows_fast": (_I, [_P, _LL, _I, _LL, _ULL, _ULL, _P, _P]),
     "colo_policy_chain": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),

@@ -277,8 +277,172 @@ class PSRLEpisodic:
         return get_policy_from_q_values(Q.cpu().numpy(), True)
 
 
+class UCRL2Continuous:
+    """N UCRL2Continuous loops (colosseum/agent/agents/infinite_horizon/ucrl2.py:34-357; Auer et al. 2008, Fruit et al.
+    2020) on one continuous MDP.  Artificial episodes end at loop-dependent times, so `steps` advances the batch in
+    rounds: `colo_ucrl2_steps` runs every loop to its episode end or the target time; the loops that wait are listed and
+    re-planned together -- `colo_ucrl2_bounds` (delta, beta_r, beta_p), `colo_extended_vi_batched_f32` (one CTA per
+    listed loop, the whole optimistic value iteration in one launch), `colo_ucrl2_model_update` -- in the reference's
+    order (plan on the old model, then update it, :183-192).  The models never leave HBM.
+
+    Constructor arguments are the reference's (`mdp_specs` -> the MDP's tables).  bound_type_rew="bernstein" is refused:
+    the reference's own branch reads `self.r_max`, which the class never defines (ucrl2.py:268)."""
+
+    episodic = False
+
+    def __init__(self, seed: int, tables: MDPTables, optimization_horizon: int, alpha_r=1.0, alpha_p=1.0,
+                 bound_type_p="_chernoff", bound_type_rew="_chernoff", epsilon_greedy=None, boltzmann_temperature=None,
+                 *, n_loops: int = 1, env_offset: int = 0, planner=None):
+        import torch
+
+        _cabi.require_cuda()
+        assert bound_type_p in ("_chernoff", "bernstein") and bound_type_rew in ("_chernoff", "bernstein")
+        if bound_type_rew == "bernstein":
+            raise NotImplementedError("bound_type_rew='bernstein' raises AttributeError in the reference (self.r_max, "
+                                      "ucrl2.py:268); only '_chernoff' is defined")
+        if boltzmann_temperature is not None:
+            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
+        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
+            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        assert tables.H == 0, "UCRL2Continuous needs a continuous MDP"
+        self.torch, self.tables = torch, tables
+        self.dev = DeviceTables(tables, "succ")
+        self.n_loops = N = int(n_loops)
+        self.seed, self.env_offset = int(seed), int(env_offset)
+        self.alpha_r, self.alpha_p = float(alpha_r), float(alpha_p)
+        self.bernstein_p = int(bound_type_p == "bernstein")
+        self.r_max = float(tables.rmax)
+        self._planner = planner
+        S, A = tables.S, tables.A
+        dev = "cuda"
+        self.state = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.h = torch.zeros(N, dtype=torch.int32, device=dev)  # (reset helper)
+        self.t = 0
+        _QLearningBatch.reset_envs(self)                        # Philox counter 0 = the reset draw
+        self.time = torch.full((N,), self.t, dtype=torch.int64, device=dev)
+        self.cumulative_reward = torch.zeros(N, dtype=torch.float64, device=dev)
+        self.n_episodes = torch.zeros(N, dtype=torch.int64, device=dev)  # MDP episodes: none in a continuous MDP
+        self.Q = torch.zeros((N, S, A), dtype=torch.float32, device=dev)
+        self.V = torch.zeros((N, S), dtype=torch.float32, device=dev)
+        self.N = torch.zeros((N, S, A, S), dtype=torch.int32, device=dev)                        # ucrl2.py:155
+        self.Nsa = torch.zeros((N, S, A), dtype=torch.int32, device=dev)
+        self.P = torch.full((N, S, A, S), float(np.float32(1.0) / np.float32(S)), dtype=torch.float32, device=dev)  # :148
+        self.estimated_rewards = torch.full((N, S, A), float(np.float32(tables.rmax)), dtype=torch.float32, device=dev)
+        self.variance_proxy_reward = torch.zeros((N, S, A), dtype=torch.float32, device=dev)
+        self.estimated_holding_times = torch.ones((N, S, A), dtype=torch.float32, device=dev)
+        self.nu = torch.zeros((N, S, A), dtype=torch.int32, device=dev)
+        self._seen = torch.zeros((N, S, A), dtype=torch.int32, device=dev)
+        # an artificial episode that starts at time t0 holds at most S*A + t0 steps and at most T - t0 of the run
+        self.log_cap = (int(optimization_horizon) + S * A) // 2 + 2
+        self.ep_len = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._ep_log = torch.zeros((N, self.log_cap, 2), dtype=torch.int32, device=dev)
+        self.ended = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.iteration = torch.zeros(N, dtype=torch.int64, device=dev)
+        self.episode = torch.zeros(N, dtype=torch.int64, device=dev)
+        self.delta = torch.ones(N, dtype=torch.float64, device=dev)
+        self.span_value = torch.zeros(N, dtype=torch.float64, device=dev)
+        self.evi_iterations = 0
+        a = _cabi.Ucrl2Args()
+        a.N, a.seed, a.env0 = N, self.seed, self.env_offset
+        a.state, a.t, a.cum_reward, a.Q = (self.state.data_ptr(), self.time.data_ptr(),
+                                           self.cumulative_reward.data_ptr(), self.Q.data_ptr())
+        a.Nsas, a.Nsa, a.P = self.N.data_ptr(), self.Nsa.data_ptr(), self.P.data_ptr()
+        a.est_r, a.var_r, a.hold = (self.estimated_rewards.data_ptr(), self.variance_proxy_reward.data_ptr(),
+                                    self.estimated_holding_times.data_ptr())
+        a.nu, a.seen, a.ep_len, a.ep_log = (self.nu.data_ptr(), self._seen.data_ptr(), self.ep_len.data_ptr(),
+                                            self._ep_log.data_ptr())
+        a.log_cap = self.log_cap
+        a.ended, a.iteration, a.episode, a.delta = (self.ended.data_ptr(), self.iteration.data_ptr(),
+                                                    self.episode.data_ptr(), self.delta.data_ptr())
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        self._args = a
+        self.episode_end_update(torch.arange(N, dtype=torch.int32, device=dev), update_model=False)  # :194-195
+
+    def bounds(self, idx):
+        """episode += 1, delta and the confidence bounds (beta_r, beta_p f64 [m,S,A]) of the loops in idx (:183-186, :223-311)"""
+        torch, S, A = self.torch, self.tables.S, self.tables.A
+        m = int(idx.numel())
+        br = torch.empty((m, S, A), dtype=torch.float64, device="cuda")
+        bp = torch.empty((m, S, A), dtype=torch.float64, device="cuda")
+        rc = _cabi.lib().colo_ucrl2_bounds(C.byref(self._args), S, A, idx.data_ptr(), m, self.alpha_r, self.alpha_p,
+                                           self.r_max, self.bernstein_p, br.data_ptr(), bp.data_ptr(),
+                                           _cabi.current_stream())
+        _cabi.check(rc, "colo_ucrl2_bounds")
+        return br, bp
+
+    def solve_optimistic_model(self, idx, beta_r, beta_p, Q=None, V=None):
+        """extended_value_iteration for the loops in idx, one launch (:313-357).  Q, V default to the loops' own."""
+        torch, S, A = self.torch, self.tables.S, self.tables.A
+        m = int(idx.numel())
+        span = torch.empty(m, dtype=torch.float64, device="cuda")
+        iters = torch.empty(m, dtype=torch.int64, device="cuda")
+        status = torch.empty(m, dtype=torch.int32, device="cuda")
+        Q = self.Q if Q is None else Q
+        V = self.V if V is None else V
+        rc = _cabi.lib().colo_extended_vi_batched_f32(
+            self.P.data_ptr(), self.estimated_rewards.data_ptr(), beta_r.data_ptr(), beta_p.data_ptr(), idx.data_ptr(), m,
+            S, A, self.r_max, 1e-3, int(1e6), Q.data_ptr(), V.data_ptr(), span.data_ptr(), iters.data_ptr(),
+            status.data_ptr(), _cabi.current_stream())
+        _cabi.check(rc, "colo_extended_vi_batched_f32")
+        return span, iters, status
+
+    def episode_end_update(self, idx, update_model=True):
+        """ucrl2.py:183-192 for the loops listed in idx (i32 device tensor)"""
+        S, A = self.tables.S, self.tables.A
+        br, bp = self.bounds(idx)
+        if self._planner is not None:
+            self._planner(self, idx, br, bp)
+        else:
+            span, iters, status = self.solve_optimistic_model(idx, br, bp)
+            self.span_value[idx.long()] = span / self.r_max
+            self.evi_iterations += int(iters.sum())
+            if int(status.max()) != 0:
+                from .dynamic_programming import DynamicProgrammingMaxIterationExceeded
+
+                raise DynamicProgrammingMaxIterationExceeded()
+        if update_model:
+            rc = _cabi.lib().colo_ucrl2_model_update(C.byref(self._args), S, A, idx.data_ptr(), int(idx.numel()),
+                                                     _cabi.current_stream())
+            _cabi.check(rc, "colo_ucrl2_model_update")
+        else:
+            self.ended.zero_()
+
+    def steps(self, n_steps: int, trace: bool = False):
+        """n_steps interactions for every loop.  trace=True returns i32 [n_steps, N, 4] = (s_t, a_t, s_tp1, reward bits)."""
+        torch = self.torch
+        tr = torch.zeros((n_steps, self.n_loops, 4), dtype=torch.int32, device="cuda") if trace else None
+        a = self._args
+        a.trace, a.trace_t0, a.trace_steps = (None if tr is None else tr.data_ptr()), self.t, int(n_steps)
+        target = self.t + int(n_steps)
+        self.rounds = 0
+        while True:
+            rc = _cabi.lib().colo_ucrl2_steps(C.byref(self.dev.c), C.byref(a), target, _cabi.current_stream())
+            _cabi.check(rc, "colo_ucrl2_steps")
+            ended = self.ended.cpu()
+            if int(ended.max()) == 2:
+                raise RuntimeError("an artificial episode outgrew its log: optimization_horizon is smaller than the run")
+            idx = torch.nonzero(ended).flatten().to(torch.int32).cuda()
+            if idx.numel() == 0:
+                break
+            self.rounds += 1
+            self.episode_end_update(idx)
+        a.trace = None
+        self.t = target
+        return tr
+
+    def current_optimal_stochastic_policy(self, i: int) -> np.ndarray:
+        """ucrl2.py:77-80: greedy policy of the discounted VI on the empirical model"""
+        from .dynamic_programming import discounted_value_iteration, get_policy_from_q_values
+
+        Q, _ = discounted_value_iteration(self.P[i].contiguous(), self.estimated_rewards[i].contiguous())
+        return get_policy_from_q_values(Q.cpu().numpy(), True)
+
+
 _CKPT_FIELDS = ("state", "h", "cumulative_reward", "n_episodes", "N", "Q", "Q_main", "V", "mu", "sigma", "beta",
-                "dir_hyper", "nig_hyper", "T_sample", "R_sample")
+                "dir_hyper", "nig_hyper", "T_sample", "R_sample",
+                # UCRL2Continuous / PSRLContinuous
+                "time", "Nsa", "P", "estimated_rewards", "variance_proxy_reward", "estimated_holding_times", "nu",
+                "ep_len", "_ep_log", "ended", "iteration", "episode", "delta", "span_value")
 
 
 def agents_state_dict(agents):

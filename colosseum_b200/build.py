@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 LIB_DIR = os.path.join(PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcolosseum_b200.so")
-SOURCES = ["lib.cu", "backup.cu", "resident.cu", "gauss_seidel.cu", "sparse_hitting.cu", "env_step.cu", "agents.cu", "builders.cu", "extended_vi.cu", "posterior.cu", "markov.cu", "synth.cu", "hitting_umma.cu", "suite_runner.cu"]
+SOURCES = ["lib.cu", "backup.cu", "resident.cu", "gauss_seidel.cu", "sparse_hitting.cu", "env_step.cu", "agents.cu", "continuous_agents.cu", "builders.cu", "extended_vi.cu", "posterior.cu", "markov.cu", "synth.cu", "hitting_umma.cu", "suite_runner.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -16,73 +16,9 @@
 //
 // Memory: the tables of a loop are contiguous ([N][H,S,A]); accesses are 4-byte gathers at (h, s, a) -- latency
 // bound, hidden by running one thread per loop with as many loops as the caller has seeds.
-#include "common.cuh"
+#include "agent_device.cuh"
 
 namespace colo {
-
-constexpr unsigned long long kAgentKey = 0x9E3779B97F4A7C15ULL;  // the agent's Philox key = seed ^ kAgentKey
-
-struct Step {
-  int nxt, cls;
-};
-
-__device__ __forceinline__ int bisect_count_d(const double* __restrict__ cum, int n, double x) {
-  int pos = 0;
-  for (int k = 0; k < n - 1; ++k) pos += (__ldg(cum + k) <= x) ? 1 : 0;
-  return pos;
-}
-
-__device__ __forceinline__ Step env_succ(const colo_mdp_tables& tb, int s, int a, double u) {
-  const size_t sa = (size_t)s * tb.A + a;
-  const size_t base = sa * tb.Ksucc;
-  const int n = __ldg(tb.succ_len + sa);
-  int pos = 0;
-  if (n > 1) {
-    const double total = __ldg(tb.succ_cum + base + n - 1) + 0.0;
-    pos = bisect_count_d(tb.succ_cum + base, n, __dmul_rn(u, total));
-  }
-  Step r;
-  r.nxt = __ldg(tb.succ_idx + base + pos);
-  r.cls = tb.rew_cls_succ ? __ldg(tb.rew_cls_succ + base + pos) : 0;
-  return r;
-}
-
-__device__ __forceinline__ float reward_from_class(const colo_mdp_tables& tb, int cls, float u) {
-  const float* q = tb.rew_q + (size_t)cls * tb.nq;
-  const float t = __fmul_rn(u, (float)(tb.nq - 1));
-  int i = (int)t;
-  i = i > tb.nq - 2 ? tb.nq - 2 : i;
-  const float f = __fsub_rn(t, (float)i);
-  const float q0 = __ldg(q + i), q1 = __ldg(q + i + 1);
-  const float r0 = fmaf(f, __fsub_rn(q1, q0), q0);
-  return fmaf(r0, __fsub_rn(tb.rmax, tb.rmin), -tb.rmin);
-}
-
-__device__ __forceinline__ int start_state(const colo_mdp_tables& tb, double u) {
-  if (tb.n_start == 1) return __ldg(tb.start_idx);
-  const double total = __ldg(tb.start_cum + tb.n_start - 1) + 0.0;
-  return __ldg(tb.start_idx + bisect_count_d(tb.start_cum, tb.n_start, __dmul_rn(u, total)));
-}
-
-// QValuesActor.select_action on one row of q-values
-__device__ __forceinline__ int select_action(const float* __restrict__ q, int A, double eps, const Philox4& w) {
-  if (eps >= 0.0 && (double)u24(w.w[0]) < eps) return act_from_word(w.w[1], A);
-  float best = q[0];
-  int ties = 1;
-  for (int a = 1; a < A; ++a) {
-    const float v = q[a];
-    if (v > best) {
-      best = v;
-      ties = 1;
-    } else if (v == best) {
-      ++ties;
-    }
-  }
-  int k = act_from_word(w.w[1], ties);
-  for (int a = 0; a < A; ++a)
-    if (q[a] == best && k-- == 0) return a;
-  return A - 1;
-}
 
 template <bool EPISODIC>
 __global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tables tb, const colo_qlearning_args p,

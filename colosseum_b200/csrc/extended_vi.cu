@@ -111,28 +111,24 @@ __global__ void __launch_bounds__(kEviSortThreads) evi_check_and_sort_kernel(TV*
   for (int i = threadIdx.x; i < S; i += blockDim.x) sorted_idx[i] = idx[i];
 }
 
+// One state of one iteration: the A optimistic rows of state s, walked by ONE WARP in ascending-u1 order.  Shared by the
+// per-iteration kernel (u1 / sorted_idx in global memory) and the one-CTA-per-instance kernel (both in shared memory):
+// same operations in the same order, so the two give the same bits.  Returns (u2[s], V[s]) in every lane; lane 0
+// stores Q[s, :].
 template <typename TV>
-__global__ void __launch_bounds__(256) evi_rows_kernel(const float* __restrict__ T, const float* __restrict__ est_r,
-                                                       const double* __restrict__ beta_r,
-                                                       const double* __restrict__ beta_p, int S, int A, double r_max,
-                                                       double eps, TV* __restrict__ u, const int* __restrict__ sorted_idx,
-                                                       TV* __restrict__ Q, TV* __restrict__ V,
-                                                       const EviState* __restrict__ st) {
-  if (st->done) return;
-  const int lane = threadIdx.x & 31;
-  const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (s >= S) return;
-  const int cur = st->cur;
-  const TV* __restrict__ u1 = u + (size_t)cur * S;
-  TV* __restrict__ u2 = u + (size_t)(cur ^ 1) * S;
+__device__ __forceinline__ void evi_state(const float* __restrict__ Ts /* T[s] = A rows */,
+                                          const float* __restrict__ est_s, const double* __restrict__ br_s,
+                                          const double* __restrict__ bp_s, int S, int A, int s, double r_max, double eps,
+                                          const TV* __restrict__ u1, const int* __restrict__ sorted_idx,
+                                          TV* __restrict__ Qs, int lane, TV* u2_out, TV* v_out) {
   const int best = sorted_idx[S - 1];
   const TV u_best = u1[best];
   const double u_s = (double)u1[s];
   double u2s = 0.0, vmax = -INFINITY;
   for (int a = 0; a < A; ++a) {
-    const float* __restrict__ p = T + ((size_t)s * A + a) * S;
+    const float* __restrict__ p = Ts + (size_t)a * S;
     const double pbest = (double)p[best];
-    const double min1 = fmin(1.0, pbest + 0.5 * beta_p[(size_t)s * A + a]);  // (:230)
+    const double min1 = fmin(1.0, pbest + 0.5 * bp_s[a]);  // (:230)
     TV dot = 0;
     if (min1 == 1.0) {
       dot = u_best;  // p2 = e_best  (:231-233)
@@ -165,18 +161,191 @@ __global__ void __launch_bounds__(256) evi_rows_kernel(const float* __restrict__
       }
       dot = warp_sum(dot);
     }
-    const double r_opt = fmin((double)(float)r_max, (double)est_r[(size_t)s * A + a] + beta_r[(size_t)s * A + a]);  // (:96-99)
+    const double r_opt = fmin((double)(float)r_max, (double)est_s[a] + br_s[a]);  // (:96-99)
     const double v = r_opt + ((double)dot - u_s);  // vec[s] -= 1  (:95,:100)
     const TV q = (TV)v;
-    if (lane == 0) Q[(size_t)s * A + a] = q;
+    if (lane == 0) Qs[a] = q;
     vmax = (double)q > vmax ? (double)q : vmax;
     const double cand = v + u_s;
     if (a == 0 || cand > u2s || fabs(cand - u2s) < eps) u2s = (double)(TV)cand;  // (:102-109), stored as float32
   }
+  *u2_out = (TV)u2s;
+  *v_out = (TV)vmax;  // (:110)
+}
+
+template <typename TV>
+__global__ void __launch_bounds__(256) evi_rows_kernel(const float* __restrict__ T, const float* __restrict__ est_r,
+                                                       const double* __restrict__ beta_r,
+                                                       const double* __restrict__ beta_p, int S, int A, double r_max,
+                                                       double eps, TV* __restrict__ u, const int* __restrict__ sorted_idx,
+                                                       TV* __restrict__ Q, TV* __restrict__ V,
+                                                       const EviState* __restrict__ st) {
+  if (st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (s >= S) return;
+  const int cur = st->cur;
+  const TV* __restrict__ u1 = u + (size_t)cur * S;
+  TV* __restrict__ u2 = u + (size_t)(cur ^ 1) * S;
+  const size_t sa = (size_t)s * A;
+  TV u2s, vs;
+  evi_state<TV>(T + sa * S, est_r + sa, beta_r + sa, beta_p + sa, S, A, s, r_max, eps, u1, sorted_idx, Q + sa, lane, &u2s,
+                &vs);
   if (lane == 0) {
-    u2[s] = (TV)u2s;
-    V[s] = (TV)vmax;  // (:110)
+    u2[s] = u2s;
+    V[s] = vs;
   }
+}
+
+// ---- batched: one CTA per listed instance, the whole solve in one launch ------------------------------------------------
+// UCRL2's artificial episodes end at loop-dependent times (ucrl2.py:173-181), so a batch of loops asks for the extended
+// VI of an arbitrary SUBSET of its models at once: `index[k]` names the instance whose T / est_rewards / Q / V are used
+// (stride = one instance), the bounds and the outputs span / iters / status are compact ([m]).  u1, u2 and the argsort
+// live in shared memory; iterations are separated by __syncthreads only.
+constexpr int kEviBatchThreads = 1024;
+
+struct EviBatchArgs {
+  const float* T;
+  const float* est_r;
+  const double* beta_r;
+  const double* beta_p;
+  const int* index;
+  int m, S, A, n_pow2;
+  double r_max, eps;
+  long long max_iter;
+  void* Q;
+  void* V;
+  double* span;
+  long long* iters;
+  int* status;
+};
+
+template <typename TV>
+__global__ void __launch_bounds__(kEviBatchThreads) evi_batched_kernel(const EviBatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red[4][kEviBatchThreads / 32];
+  __shared__ int s_stop;
+  const int S = a.S, A = a.A, n_pow2 = a.n_pow2;
+  TV* ua = reinterpret_cast<TV*>(smem_raw);
+  TV* ub = ua + S;
+  TV* key = ub + S;
+  int* idx = reinterpret_cast<int*>(key + n_pow2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = blockIdx.x; k < a.m; k += gridDim.x) {
+    const size_t inst = a.index ? (size_t)a.index[k] : (size_t)k;
+    const float* __restrict__ T = a.T + inst * S * A * S;
+    const float* __restrict__ est = a.est_r + inst * S * A;
+    const double* __restrict__ br = a.beta_r + (size_t)k * S * A;
+    const double* __restrict__ bp = a.beta_p + (size_t)k * S * A;
+    TV* __restrict__ Q = reinterpret_cast<TV*>(a.Q) + inst * S * A;
+    TV* __restrict__ V = reinterpret_cast<TV*>(a.V) + inst * S;
+    TV* u1 = ua;
+    TV* u2 = ub;
+    __syncthreads();  // the previous instance is done with the shared arrays
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      ua[i] = 0;
+      ub[i] = 0;
+      idx[i] = i;  // arange is a valid argsort of the all-zero u1 (:88)
+    }
+    __syncthreads();
+    long long it = 0;
+    int rc = COLO_MAX_ITER;
+    double span = 0.0;
+    for (; it < a.max_iter;) {
+      for (int s = warp; s < S; s += nw) {
+        const size_t sa = (size_t)s * A;
+        TV u2s, vs;
+        evi_state<TV>(T + sa * S, est + sa, br + sa, bp + sa, S, A, s, a.r_max, a.eps, u1, idx, Q + sa, lane, &u2s, &vs);
+        if (lane == 0) {
+          u2[s] = u2s;
+          V[s] = vs;
+        }
+      }
+      __syncthreads();
+      // stopping rule: ptp(u2 - u1) < eps, then span = ptp(u1)  (:111-112)
+      double lo = INFINITY, hi = -INFINITY, ulo = INFINITY, uhi = -INFINITY;
+      for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const double d = (double)u2[i] - (double)u1[i];
+        lo = d < lo ? d : lo;
+        hi = d > hi ? d : hi;
+        const double x = (double)u1[i];
+        ulo = x < ulo ? x : ulo;
+        uhi = x > uhi ? x : uhi;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(FULL, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(FULL, hi, o));
+        ulo = fmin(ulo, __shfl_xor_sync(FULL, ulo, o));
+        uhi = fmax(uhi, __shfl_xor_sync(FULL, uhi, o));
+      }
+      if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; s_red[2][warp] = ulo; s_red[3][warp] = uhi; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < nw; ++w) {
+          s_red[0][0] = fmin(s_red[0][0], s_red[0][w]); s_red[1][0] = fmax(s_red[1][0], s_red[1][w]);
+          s_red[2][0] = fmin(s_red[2][0], s_red[2][w]); s_red[3][0] = fmax(s_red[3][0], s_red[3][w]);
+        }
+        s_stop = (s_red[1][0] - s_red[0][0]) < a.eps;
+      }
+      __syncthreads();
+      ++it;
+      if (s_stop) {
+        span = s_red[3][0] - s_red[2][0];
+        rc = COLO_OK;
+        break;
+      }
+      TV* t = u1; u1 = u2; u2 = t;  // u1 = u2  (:114)
+      // sorted_indices = argsort(u1)  (:116), total order (value, index)
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        key[i] = i < S ? u1[i] : (TV)INFINITY;
+        idx[i] = i;
+      }
+      __syncthreads();
+      for (int kk = 2; kk <= n_pow2; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+          for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+            const int l = i ^ j;
+            if (l > i) {
+              const bool up = (i & kk) == 0;
+              const TV x = key[i], y = key[l];
+              const int ia = idx[i], ib = idx[l];
+              const bool gt = x > y || (x == y && ia > ib);
+              if (gt == up) { key[i] = y; key[l] = x; idx[i] = ib; idx[l] = ia; }
+            }
+          }
+          __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+      a.span[k] = span;
+      a.iters[k] = it;
+      a.status[k] = rc;
+    }
+  }
+}
+
+template <typename TV>
+int extended_vi_batched(const float* T, const float* est_r, const double* beta_r, const double* beta_p,
+                        const int* index, int m, int S, int A, double r_max, double eps, long long max_iter, TV* Q, TV* V,
+                        double* span, long long* iters, int* status, void* stream) {
+  COLO_ARG_CHECK(T && est_r && beta_r && beta_p && Q && V && span && iters && status, "null argument");
+  COLO_ARG_CHECK(m >= 0 && S > 0 && A > 0 && S <= 8192 && max_iter >= 1, "m >= 0, S in [1, 8192], A > 0, max_iter >= 1");
+  if (m == 0) return COLO_OK;
+  int n_pow2 = 1;
+  while (n_pow2 < S) n_pow2 <<= 1;
+  const size_t smem = (size_t)2 * S * sizeof(TV) + (size_t)n_pow2 * (sizeof(TV) + sizeof(int));
+  COLO_ARG_CHECK(smem <= 200 * 1024, "S too large for the one-CTA-per-instance extended VI");
+  auto kern = evi_batched_kernel<TV>;
+  { const int _es = ensure_dynamic_smem((const void*)kern, smem); if (_es != COLO_OK) return _es; }
+  EviBatchArgs a;
+  a.T = T; a.est_r = est_r; a.beta_r = beta_r; a.beta_p = beta_p; a.index = index;
+  a.m = m; a.S = S; a.A = A; a.n_pow2 = n_pow2;
+  a.r_max = r_max; a.eps = eps; a.max_iter = max_iter;
+  a.Q = Q; a.V = V; a.span = span; a.iters = iters; a.status = status;
+  const int grid = m < 4 * sm_count() ? m : 4 * sm_count();
+  kern<<<grid, kEviBatchThreads, smem, (cudaStream_t)stream>>>(a);
+  return check_launch("evi_batched_kernel");
 }
 
 template <typename TV>
@@ -242,6 +411,18 @@ int colo_extended_vi_f64acc(const float* T, const float* est_rewards, const doub
                             void* work, void* stream) {
   return colo::extended_vi<double>(T, est_rewards, beta_r, beta_p, S, A, r_max, eps, max_iter, Q, V, out_host, work,
                                    stream);
+}
+int colo_extended_vi_batched_f32(const float* T, const float* est_rewards, const double* beta_r, const double* beta_p,
+                                 const int* index, int m, int S, int A, double r_max, double eps, long long max_iter,
+                                 float* Q, float* V, double* span, long long* iters, int* status, void* stream) {
+  return colo::extended_vi_batched<float>(T, est_rewards, beta_r, beta_p, index, m, S, A, r_max, eps, max_iter, Q, V,
+                                          span, iters, status, stream);
+}
+int colo_extended_vi_batched_f64acc(const float* T, const float* est_rewards, const double* beta_r, const double* beta_p,
+                                    const int* index, int m, int S, int A, double r_max, double eps, long long max_iter,
+                                    double* Q, double* V, double* span, long long* iters, int* status, void* stream) {
+  return colo::extended_vi_batched<double>(T, est_rewards, beta_r, beta_p, index, m, S, A, r_max, eps, max_iter, Q, V,
+                                           span, iters, status, stream);
 }
 
 }  // extern "C"

@@ -307,6 +307,21 @@ int colo_extended_vi_f32(const float* T, const float* est_rewards, const double*
 int colo_extended_vi_f64acc(const float* T, const float* est_rewards, const double* beta_r, const double* beta_p, int S,
                             int A, double r_max, double eps, long long max_iter, double* Q, double* V, double* out_host,
                             void* work, void* stream);
+/*
+ * colo_extended_vi_batched_* -- the same solve for a SUBSET of a batch of models in ONE launch (one CTA per listed
+ * instance, u1 / u2 / argsort in shared memory; S <= 8192): UCRL2's artificial episodes end at loop-dependent times
+ * (agent/agents/infinite_horizon/ucrl2.py:173-192), so every round of a batch of loops re-plans the loops in `index`.
+ * T f32[*,S,A,S], est_rewards f32[*,S,A], Q [*,S,A], V [*,S] are addressed by instance index[k] (index NULL: k);
+ * beta_r, beta_p f64[m,S,A] and the outputs span f64[m], iters i64[m], status i32[m] (COLO_OK / COLO_MAX_ITER) are
+ * compact, all on the device.  Same operations in the same order as colo_extended_vi_* (bit-identical Q, V, span).
+ * Does not synchronise.
+ */
+int colo_extended_vi_batched_f32(const float* T, const float* est_rewards, const double* beta_r, const double* beta_p,
+                                 const int* index, int m, int S, int A, double r_max, double eps, long long max_iter,
+                                 float* Q, float* V, double* span, long long* iters, int* status, void* stream);
+int colo_extended_vi_batched_f64acc(const float* T, const float* est_rewards, const double* beta_r, const double* beta_p,
+                                    const int* index, int m, int S, int A, double r_max, double eps, long long max_iter,
+                                    double* Q, double* V, double* span, long long* iters, int* status, void* stream);
 
 /* ---------------------------------------------------------------- posterior sampling (PSRL) ---------------- */
 /*
@@ -656,6 +671,58 @@ typedef struct {
 } colo_psrl_args;
 int colo_psrl_episodic_steps(const colo_mdp_tables* tb, const colo_psrl_args* a, int n_steps, unsigned long long t0,
                              void* stream);
+
+/*
+ * UCRL2Continuous (colosseum/agent/agents/infinite_horizon/ucrl2.py:34-357) for N independent loops on one continuous
+ * MDP.  The batch advances in rounds because artificial episodes end at loop-dependent times:
+ *   colo_ucrl2_steps        every loop that is not waiting runs MDPLoop.run's body (select_action on Q f32[N,S,A],
+ *                           BaseMDP.step, step_update :183-199, is_episode_end :173-181) until its own time t[i] reaches
+ *                           t_target or its artificial episode ends (ended[i] = 1; 2 = the episode log overflowed);
+ *   colo_ucrl2_bounds       for the loops listed in index[m] (device): episode += 1, delta = 1/sqrt(iteration+1) and the
+ *                           confidence bounds of solve_optimistic_model (:223-311) into beta_r, beta_p f64[m,S,A]
+ *                           (rewards: _chernoff; transitions: _chernoff or, bernstein_p != 0, bernstein; beta_p is the
+ *                           [s,a,0] entry of the reference's array, the one _max_proba reads);
+ *   colo_extended_vi_batched_f32 on (P, est_r, beta_r, beta_p) -> Q, V of the listed loops;
+ *   colo_ucrl2_model_update model_update (:201-221) from the episode log, iteration += episode length, log / nu / ended
+ *                           cleared.
+ * Tables (device, per loop contiguous): Nsas i32[N,S,A,S] (init 0), Nsa i32[N,S,A] = Nsas.sum(-1), P f32[N,S,A,S]
+ * (init 1/S), est_r f32[N,S,A] (init r_max), var_r, hold f32[N,S,A] (init 0 / 1), nu i32[N,S,A] = visits inside the
+ * running episode, seen i32[N,S,A] scratch (all zero between calls), ep_log i32[N,log_cap,2] = (s*A+a, reward bits) in
+ * time order, ep_len i32[N], iteration / episode i64[N], delta f64[N], t i64[N], state i32[N], cum_reward f64[N].
+ * Randomness as colo_qlearning_*: env draws keyed (seed; env0+i, t[i]), agent draws (seed ^ 0x9E3779B97F4A7C15; ...).
+ * trace (optional) i32[trace_steps,N,4] = (s_t, a_t, s_tp1, reward bits) at row t - trace_t0.  None synchronises.
+ */
+typedef struct {
+  long long N;
+  unsigned long long seed, env0;
+  int* state;
+  long long* t;
+  double* cum_reward;
+  const float* Q;
+  int* Nsas;
+  int* Nsa;
+  float* P;
+  float* est_r;
+  float* var_r;
+  float* hold;
+  int* nu;
+  int* seen;
+  int* ep_len;
+  int* ep_log;
+  int log_cap;
+  int* ended;
+  long long* iteration;
+  long long* episode;
+  double* delta;
+  double epsilon_greedy; /* < 0: greedy */
+  int* trace;
+  long long trace_t0;
+  int trace_steps;
+} colo_ucrl2_args;
+int colo_ucrl2_steps(const colo_mdp_tables* tb, const colo_ucrl2_args* a, long long t_target, void* stream);
+int colo_ucrl2_bounds(const colo_ucrl2_args* a, int S, int A, const int* index, int m, double alpha_r, double alpha_p,
+                      double r_max, int bernstein_p, double* beta_r, double* beta_p, void* stream);
+int colo_ucrl2_model_update(const colo_ucrl2_args* a, int S, int A, const int* index, int m, void* stream);
 
 /* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
  * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */

@@ -1015,3 +1015,191 @@ int orc_psrl_steps(const orc_tables* tb, const orc_psrl_args* p, int n_steps, ui
   }
   return ORC_OK;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * UCRL2Continuous (colosseum/agent/agents/infinite_horizon/ucrl2.py:34-357) for N independent loops, restated per loop:
+ *   orc_ucrl2_steps         MDPLoop.run's body until the loop's time reaches t_target or its artificial episode ends:
+ *                           QValuesActor.select_action on Q[s], BaseMDP.step, step_update (:183-199: N[s,a,s'] += 1 and the
+ *                           episode's per-(s,a) reward / next-state lists, kept here as one time-ordered log per loop),
+ *                           is_episode_end (:173-181: nu_k >= max(1, N[s,a].sum() - nu_k));
+ *   orc_ucrl2_bounds        episode_end_update's first lines (:183-186) and the bounds of solve_optimistic_model
+ *                           (:223-311): delta = 1/sqrt(iteration+1), beta_r (_chernoff), beta_p (_chernoff / bernstein;
+ *                           only the [s,a,0] entry, the one _max_proba reads, infinite_horizon.py:230);
+ *   orc_ucrl2_model_update  model_update (:201-221) in numpy's types: a float32 table entry times / plus a float64 is
+ *                           computed in float64 and stored float32; `r - old_estimate` with a python-float reward is a
+ *                           float32 difference (NEP 50).
+ * Pinned against the unmodified reference class replayed on this restatement's trace (tests/golden/make_ucrl2_golden.py).
+ */
+typedef struct {
+  long long N;
+  uint64_t seed, env0;
+  int* state;
+  long long* t;
+  double* cum_reward;
+  const float* Q;
+  int* Nsas;
+  int* Nsa;
+  float* P;
+  float* est_r;
+  float* var_r;
+  float* hold;
+  int* nu;
+  int* seen;
+  int* ep_len;
+  int* ep_log;
+  int log_cap;
+  int* ended;
+  long long* iteration;
+  long long* episode;
+  double* delta;
+  double epsilon_greedy;
+  int* trace;
+  long long trace_t0;
+  int trace_steps;
+} orc_ucrl2_args;
+
+int orc_ucrl2_steps(const orc_tables* tb, const orc_ucrl2_args* p, long long t_target) {
+  const int S = tb->S, A = tb->A;
+  const size_t SA = (size_t)S * A;
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < p->N; ++i) {
+    if (p->ended[i] != 0) continue;
+    const float* Q = p->Q + (size_t)i * SA;
+    int* Nsas = p->Nsas + (size_t)i * SA * S;
+    int* Nsa = p->Nsa + (size_t)i * SA;
+    int* nu = p->nu + (size_t)i * SA;
+    int* log = p->ep_log + (size_t)i * p->log_cap * 2;
+    int s = p->state[i];
+    long long t = p->t[i];
+    int len = p->ep_len[i];
+    double cum = p->cum_reward[i];
+    int flag = 0;
+    while (t < t_target) {
+      if (len >= p->log_cap) { flag = 2; break; }
+      uint32_t we[4], wa[4];
+      orc_philox(p->seed, p->env0 + (uint64_t)i, (uint64_t)t, we);
+      orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, (uint64_t)t, wa);
+      const int a = orc_select_action(Q + (size_t)s * A, A, p->epsilon_greedy, wa);
+      const size_t sa = (size_t)s * A + a;
+      const size_t base = sa * tb->Ksucc;
+      const int nsucc = tb->succ_len[sa];
+      int pos = 0;
+      if (nsucc > 1) {
+        const double total = tb->succ_cum[base + nsucc - 1] + 0.0;
+        pos = bisect_pos(tb->succ_cum + base, nsucc, u53(we[0], we[1]) * total);
+      }
+      const int nxt = tb->succ_idx[base + pos];
+      const int cls = tb->rew_cls_succ ? tb->rew_cls_succ[base + pos] : 0;
+      const float r = reward_draw(tb, cls, u24(we[2]));
+      Nsas[sa * S + nxt] += 1;
+      Nsa[sa] += 1;
+      nu[sa] += 1;
+      union { float f; int i; } u;
+      u.f = r;
+      log[2 * len] = (int)sa;
+      log[2 * len + 1] = u.i;
+      ++len;
+      cum += (double)r;
+      if (p->trace) {
+        const long long k = t - p->trace_t0;
+        if (k >= 0 && k < p->trace_steps) {
+          int* tr = p->trace + ((size_t)k * p->N + i) * 4;
+          tr[0] = s; tr[1] = a; tr[2] = nxt; tr[3] = u.i;
+        }
+      }
+      s = nxt;
+      ++t;
+      const int before = Nsa[sa] - nu[sa];
+      if (nu[sa] >= (before > 1 ? before : 1)) { flag = 1; break; }
+    }
+    p->state[i] = s;
+    p->t[i] = t;
+    p->ep_len[i] = len;
+    p->cum_reward[i] = cum;
+    if (flag) p->ended[i] = flag;
+  }
+  return ORC_OK;
+}
+
+int orc_ucrl2_bounds(const orc_ucrl2_args* p, int S, int A, const int* index, int m, double alpha_r, double alpha_p,
+                     double r_max, int bernstein_p, double* beta_r, double* beta_p) {
+  const size_t SA = (size_t)S * A;
+  for (int k = 0; k < m; ++k) {
+    const size_t i = (size_t)index[k];
+    const long long it = p->iteration[i];
+    const double delta = 1.0 / sqrt((double)(it + 1));
+    for (size_t sa = 0; sa < SA; ++sa) {
+      const int nb = p->Nsa[i * SA + sa];
+      const double n1 = (double)(nb > 1 ? nb : 1);
+      const double Lr = log((double)(2LL * S * A * (it + 1)) / delta);
+      beta_r[(size_t)k * SA + sa] = alpha_r * (r_max * sqrt(3.5 * Lr / n1));
+      double bp;
+      if (!bernstein_p) {
+        const double Lp = log((double)(2LL * A * (it + 1)) / delta);
+        bp = alpha_p * sqrt((double)(14LL * S) * Lp / n1);
+      } else {
+        const double nm1 = (double)(nb - 1 > 1 ? nb - 1 : 1);
+        const float P0 = p->P[(i * SA + sa) * S];
+        const float one_m = 1.0f - P0;
+        const float var_p = P0 * one_m;
+        const float v14 = 14.0f * var_p;
+        const double L = log(2.0 * (double)S * (double)A * (double)(it + 1) / delta);
+        const double At = (double)v14 / n1 * L;
+        const double Bt = 49.0 / (3.0 * nm1) * L;
+        bp = sqrt(alpha_p) * sqrt(At) + alpha_p * Bt;
+      }
+      beta_p[(size_t)k * SA + sa] = bp;
+    }
+    p->delta[i] = delta;
+    p->episode[i] += 1;
+  }
+  return ORC_OK;
+}
+
+int orc_ucrl2_model_update(const orc_ucrl2_args* p, int S, int A, const int* index, int m) {
+  const size_t SA = (size_t)S * A;
+  for (int k = 0; k < m; ++k) {
+    const size_t i = (size_t)index[k];
+    const int* log = p->ep_log + i * (size_t)p->log_cap * 2;
+    const int len = p->ep_len[i];
+    const int* Nsa = p->Nsa + i * SA;
+    int* seen = p->seen + i * SA;
+    int* nu = p->nu + i * SA;
+    float* est = p->est_r + i * SA;
+    float* var = p->var_r + i * SA;
+    float* hold = p->hold + i * SA;
+    for (int e = 0; e < len; ++e) {
+      const int sa = log[2 * e];
+      union { float f; int i; } u;
+      u.i = log[2 * e + 1];
+      const float r = u.f;
+      const int j = ++seen[sa];
+      const double sf = (double)((long long)Nsa[sa] + j);
+      const double sf1 = sf + 1.0;
+      const double ratio = sf / sf1;
+      const float old = est[sa];
+      float x = (float)((double)old * ratio);
+      x = (float)((double)x + (double)r / sf1);
+      est[sa] = x;
+      const float d0 = r - old, d1 = r - x;
+      const float pr = d0 * d1;
+      var[sa] = var[sa] + pr;
+      float hd = (float)((double)hold[sa] * ratio);
+      hd = (float)((double)hd + 1.0 / sf1);
+      hold[sa] = hd;
+    }
+    for (int e = 0; e < len; ++e) seen[log[2 * e]] = 0;
+    for (size_t sa = 0; sa < SA; ++sa) {
+      if (nu[sa] == 0) continue;
+      const double tot = (double)Nsa[sa];
+      const int* n = p->Nsas + (i * SA + sa) * S;
+      float* P = p->P + (i * SA + sa) * S;
+      for (int j = 0; j < S; ++j) P[j] = (float)((double)n[j] / tot);
+      nu[sa] = 0;
+    }
+    p->iteration[i] += len;
+    p->ep_len[i] = 0;
+    p->ended[i] = 0;
+  }
+  return ORC_OK;
+}

@@ -496,3 +496,119 @@ class PSRLLoops:
         assert rc == 0
         self.t += n_steps
         return tr
+
+
+# ------------------------------------------------------------------------------------------------ UCRL2Continuous
+class _Ucrl2Args(C.Structure):
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_uint64), ("env0", C.c_uint64),
+        ("state", C.c_void_p), ("t", C.c_void_p), ("cum_reward", C.c_void_p), ("Q", C.c_void_p),
+        ("Nsas", C.c_void_p), ("Nsa", C.c_void_p), ("P", C.c_void_p), ("est_r", C.c_void_p), ("var_r", C.c_void_p),
+        ("hold", C.c_void_p), ("nu", C.c_void_p), ("seen", C.c_void_p), ("ep_len", C.c_void_p), ("ep_log", C.c_void_p),
+        ("log_cap", C.c_int), ("ended", C.c_void_p), ("iteration", C.c_void_p), ("episode", C.c_void_p),
+        ("delta", C.c_void_p), ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong),
+        ("trace_steps", C.c_int),
+    ]
+
+
+class UCRL2Loops:
+    """CPU restatement of N UCRL2Continuous loops (colosseum/agent/agents/infinite_horizon/ucrl2.py:34-357): the three
+    C functions orc_ucrl2_{steps,bounds,model_update} plus orc_extended_vi_f32 as the planner, driven in the rounds the
+    product uses (run every loop to its episode end or the target time; episode_end_update for the loops that wait).
+    `planner(loop, episode, T, est_r, beta_r, beta_p, r_max)` -> (span, Q, V) may replace the planner and record=True
+    keeps every (loop, episode) -> (Q, beta_r, beta_p): the GPU tests feed both sides the same Q so that trajectories
+    and model tables compare bit for bit."""
+
+    def __init__(self, tb, n_loops, optimization_horizon, seed=0, env0=0, alpha_r=1.0, alpha_p=1.0,
+                 bound_type_p="_chernoff", bound_type_rew="_chernoff", epsilon_greedy=None, planner=None, record=False):
+        assert bound_type_p in ("_chernoff", "bernstein") and bound_type_rew == "_chernoff"
+        self.history = {} if record else None
+        assert tb.c.H == 0, "UCRL2Continuous needs a continuous MDP"
+        self.tb, self.N, self.seed, self.env0 = tb, int(n_loops), int(seed), int(env0)
+        S, A, N = tb.c.S, tb.c.A, self.N
+        self.S, self.A = S, A
+        self.alpha_r, self.alpha_p, self.bernstein_p = float(alpha_r), float(alpha_p), int(bound_type_p == "bernstein")
+        self.r_max = float(tb.c.rmax)
+        self.planner = planner
+        self.state, _, _, _ = env_reset(tb, N, seed=seed, t=0, env0=env0)
+        self.t = np.ones(N, np.int64)  # counter 0 was the reset draw
+        self.cum_reward = np.zeros(N, np.float64)
+        self.Q = np.zeros((N, S, A), np.float32)
+        self.V = np.zeros((N, S), np.float32)
+        self.Nsas = np.zeros((N, S, A, S), np.int32)
+        self.Nsa = np.zeros((N, S, A), np.int32)
+        self.P = (np.ones((N, S, A, S), np.float32) / S).astype(np.float32)              # ucrl2.py:148
+        self.est_r = (np.ones((N, S, A), np.float32) * tb.c.rmax).astype(np.float32)     # :150-152
+        self.var_r = np.zeros((N, S, A), np.float32)
+        self.hold = np.ones((N, S, A), np.float32)
+        self.nu = np.zeros((N, S, A), np.int32)
+        self.seen = np.zeros((N, S, A), np.int32)
+        self.log_cap = (int(optimization_horizon) + S * A) // 2 + 2
+        self.ep_len = np.zeros(N, np.int32)
+        self.ep_log = np.zeros((N, self.log_cap, 2), np.int32)
+        self.ended = np.zeros(N, np.int32)
+        self.iteration = np.zeros(N, np.int64)
+        self.episode = np.zeros(N, np.int64)
+        self.delta = np.ones(N, np.float64)
+        self.span_value = np.zeros(N, np.float64)
+        self.episode_ends = [[] for _ in range(N)]  # interaction times at which each loop's episodes ended
+        a = _Ucrl2Args()
+        a.N, a.seed, a.env0 = N, self.seed, self.env0
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        for k in ("state", "t", "cum_reward", "Q", "Nsas", "Nsa", "P", "est_r", "var_r", "hold", "nu", "seen", "ep_len",
+                  "ep_log", "ended", "iteration", "episode", "delta"):
+            setattr(a, k, _p(getattr(self, k)))
+        a.log_cap = self.log_cap
+        self.args = a
+        self.episode_end_update(np.arange(N, dtype=np.int32))  # before_start_interacting (:194-195)
+
+    def bounds(self, idx):
+        idx = np.ascontiguousarray(idx, np.int32)
+        m = len(idx)
+        br = np.zeros((m, self.S, self.A), np.float64)
+        bp = np.zeros((m, self.S, self.A), np.float64)
+        rc = lib().orc_ucrl2_bounds(C.byref(self.args), self.S, self.A, _p(idx), m, C.c_double(self.alpha_r),
+                                    C.c_double(self.alpha_p), C.c_double(self.r_max), self.bernstein_p, _p(br), _p(bp))
+        assert rc == 0
+        return br, bp
+
+    def episode_end_update(self, idx):
+        """ucrl2.py:183-192 for the loops in idx: bounds -> extended VI -> model_update (in the reference's order)"""
+        idx = np.ascontiguousarray(idx, np.int32)
+        had_data = self.ep_len[idx] > 0
+        br, bp = self.bounds(idx)
+        for k, i in enumerate(idx):
+            if self.planner is not None:
+                res = self.planner(int(i), int(self.episode[i]), self.P[i], self.est_r[i], br[k], bp[k], self.r_max)
+            else:
+                res = extended_vi_f32(self.P[i], self.est_r[i], br[k], bp[k], self.r_max)
+            if res is not None:
+                span, Q, V = res[:3]
+                self.Q[i], self.V[i] = Q, V
+                self.span_value[i] = span / self.r_max
+            if self.history is not None:  # (loop, episode number) -> what the planner saw and returned
+                self.history[(int(i), int(self.episode[i]))] = (self.Q[i].copy(), br[k].copy(), bp[k].copy())
+        upd = np.ascontiguousarray(idx[had_data], np.int32)
+        rc = lib().orc_ucrl2_model_update(C.byref(self.args), self.S, self.A, _p(upd), len(upd))
+        assert rc == 0
+        self.ended[idx] = 0
+
+    def steps(self, n_steps, trace=False):
+        """n_steps interactions for every loop.  trace: i32 [n_steps, N, 4] = (s_t, a_t, s_tp1, reward bits)"""
+        t0 = int(self.t[0])
+        assert (self.t == t0).all()
+        tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
+        self.args.trace, self.args.trace_t0, self.args.trace_steps = _p(tr), t0, int(n_steps)
+        target = t0 + int(n_steps)
+        while True:
+            rc = lib().orc_ucrl2_steps(C.byref(self.tb.c), C.byref(self.args), C.c_longlong(target))
+            assert rc == 0
+            assert (self.ended != 2).all(), "episode log overflow: optimization_horizon is too small for this run"
+            idx = np.nonzero(self.ended)[0].astype(np.int32)
+            if len(idx) == 0:
+                break
+            for i in idx:
+                self.episode_ends[i].append(int(self.t[i]))
+            self.episode_end_update(idx)
+        self.args.trace = None
+        return tr

@@ -76,3 +76,28 @@ def test_oracle_psrl_updates_match_reference_conjugate_models():
         assert (loops.n_episodes == N_EPISODES).all()
         # transitions into the terminal observation are not counted (bayesian_model.py:89-92)
         assert np.isclose((loops.dir_hyper - loops.dir_hyper.min()).sum(), PN * N_EPISODES * (tb.H - 1), rtol=1e-3)
+
+
+def test_oracle_ucrl2_loops_match_reference_agent():
+    """oracle.UCRL2Loops == the reference's UCRL2Continuous class replayed on the committed trajectories
+    (tests/golden/make_ucrl2_golden.py): same artificial-episode ends, bit-identical model tables (N, P, estimated
+    rewards, variance proxies, holding times, iteration / episode counters, delta), and the extended-VI Q within its
+    stopping tolerance."""
+    from make_ucrl2_golden import CASES as UCASES, N_LOOPS as UN, N_STEPS as UT, SEED as USEED
+
+    gold = np.load(os.path.join(GOLDEN, "ucrl2.npz"))
+    for name, inst, kw in UCASES:
+        tb = MDPTables.from_golden(load_instance(inst))
+        loops = orc.UCRL2Loops(host_tables(tb), UN, UT, seed=USEED, **kw)
+        trace = loops.steps(UT, trace=True)
+        assert np.array_equal(trace, gold[f"{name}.trace"]), name
+        ends = gold[f"{name}.ref_ends"]
+        for i in range(UN):
+            assert loops.episode_ends[i] == [int(x) for x in ends[i] if x >= 0], (name, i)
+        for f, v in (("N", loops.Nsas), ("P", loops.P), ("est_r", loops.est_r), ("var_r", loops.var_r),
+                     ("hold", loops.hold), ("iteration", loops.iteration), ("episode", loops.episode),
+                     ("delta", loops.delta)):
+            ref = gold[f"{name}.ref_{f}"]
+            assert np.array_equal(v, ref.astype(v.dtype)), (name, f)
+        assert np.abs(loops.Q - gold[f"{name}.ref_Q"]).max() < 2e-3, name  # extended VI stops at eps = 1e-3
+        assert len(ends[0]) > 100
