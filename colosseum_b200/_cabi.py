@@ -128,6 +128,18 @@ class Ucrl2Args(C.Structure):
     ]
 
 
+class PsrlcArgs(C.Structure):
+    """mirror of `colo_psrlc_args`"""
+
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_ulonglong), ("env0", C.c_ulonglong),
+        ("state", C.c_void_p), ("t", C.c_void_p), ("cum_reward", C.c_void_p), ("Q", C.c_void_p), ("psi", C.c_int),
+        ("dir_hyper", C.c_void_p), ("nig_hyper", C.c_void_p), ("reward_model", C.c_int),
+        ("Nsas", C.c_void_p), ("Nsa", C.c_void_p), ("nu", C.c_void_p), ("ended", C.c_void_p), ("episode", C.c_void_p),
+        ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong), ("trace_steps", C.c_int),
+    ]
+
+
 class SuiteInstance(C.Structure):
     """mirror of `colo_suite_instance` (HOST pointers)"""
 
@@ -224,6 +236,9 @@ PROTOTYPES = {
     "colo_ucrl2_steps": (_I, [C.POINTER(MdpTables), C.POINTER(Ucrl2Args), _LL, _P]),
     "colo_ucrl2_bounds": (_I, [C.POINTER(Ucrl2Args), _I, _I, _P, _I, _D, _D, _D, _I, _P, _P, _P]),
     "colo_ucrl2_model_update": (_I, [C.POINTER(Ucrl2Args), _I, _I, _P, _I, _P]),
+    "colo_psrlc_steps": (_I, [C.POINTER(MdpTables), C.POINTER(PsrlcArgs), _LL, _P]),
+    "colo_psrlc_sample_models": (_I, [C.POINTER(PsrlcArgs), _I, _I, _P, _I, _D, _I, C.c_float, _I, _P, _P, _P]),
+    "colo_psrlc_finish_episode": (_I, [C.POINTER(PsrlcArgs), _I, _I, _P, _I, _P]),
     "colo_sample_nig_rewards": (_I, [_P, _LL, _LL, _ULL, _ULL, _P, _P]),
     "colo_sample_nn_rewards": (_I, [_P, _LL, _LL, _ULL, _ULL, _P, _P]),
     "colo_emit_noise": (_I, [_P, _P, _P, _LL, _I, _I, _I, _I, _D, _ULL, _ULL, _ULL, _P]),

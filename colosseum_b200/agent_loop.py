@@ -438,6 +438,190 @@ class UCRL2Continuous:
         return get_policy_from_q_values(Q.cpu().numpy(), True)
 
 
+def get_psi(n_states, n_actions, T, p):
+    """infinite_horizon/posterior_sampling.py:20-42"""
+    return n_states * np.log(n_states * n_actions / p)
+
+
+def get_omega(n_states, n_actions, T, p):
+    """:45-66"""
+    return np.log(T / p)
+
+
+def get_kappa(n_states, n_actions, T, p):
+    """:69-90"""
+    return np.log(T / p)
+
+
+def get_eta(n_states, n_actions, T, p, omega):
+    """:93-115"""
+    return np.sqrt(T * n_states / n_actions) + 12 * omega * n_states ** 4
+
+
+class PSRLContinuous:
+    """N PSRLContinuous loops (colosseum/agent/agents/infinite_horizon/posterior_sampling.py:117-452; Agrawal & Jia 2017)
+    on one continuous MDP, advanced in rounds like UCRL2Continuous: `colo_psrlc_steps` to each loop's artificial-episode
+    end; for the loops that wait, `colo_psrlc_sample_models` (optimistic sampling: psi transition samples per (s, a) --
+    Dirichlet posterior rows for visited pairs, the confidence-set rows for under-visited ones -- and one reward sample,
+    laid out as the reference's extended MDP with A * psi actions), one batched `discounted_value_iteration` (the
+    reference's gamma = 0.99, epsilon = 1e-3) and the q-values written back.  The sampled models never leave HBM.
+    Constructor arguments are the reference's (`mdp_specs` -> the MDP's tables).
+
+    sweep_order: "jacobi" (default) plans with synchronous sweeps stopped by the reference's rule -- the planner's input
+    is a random posterior sample, so no bit-level parity exists to keep, and the early-stopped iterate differs from the
+    reference's in-place one by less than the sampling noise (error bound eps gamma / (1 - gamma) for both);
+    "gauss_seidel" runs the reference's own in-place iterate (one warp per model: 5-90x slower for the few models a
+    round re-plans -- measured: RiverSwim 256 loops 18.6 s vs 2.1 s, DeepSea-30 32 loops 235 s vs 2.7 s)."""
+
+    episodic = False
+
+    def __init__(self, seed: int, tables: MDPTables, optimization_horizon: int, reward_prior_model=None,
+                 transitions_prior_model=None, rewards_prior_prms=None, transitions_prior_prms=None,
+                 epsilon_greedy=None, boltzmann_temperature=None, psi_weight=1.0, omega_weight=1.0, kappa_weight=1.0,
+                 eta_weight=1.0, get_psi=get_psi, get_omega=get_omega, get_kappa=get_kappa, get_eta=get_eta, p=0.05,
+                 no_optimistic_sampling=False, truncate_reward_with_max=False, min_steps_before_new_episode=0,
+                 max_psi=60, *, n_loops: int = 1, env_offset: int = 0, sampler: str = "fast",
+                 sweep_order: str = "jacobi", planner=None, max_plan_bytes: int = 8 << 30):
+        import torch
+
+        _cabi.require_cuda()
+        assert sampler in ("fast", "f64")
+        rname = getattr(reward_prior_model, "name", reward_prior_model)
+        tname = getattr(transitions_prior_model, "name", transitions_prior_model)
+        assert rname in (None, "N_NIG", "N_N") and tname in (None, "M_DIR")
+        if boltzmann_temperature is not None:
+            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
+        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
+            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        if min_steps_before_new_episode != 0:
+            raise NotImplementedError("min_steps_before_new_episode > 0 is not offered by the batched agent")
+        assert tables.H == 0, "PSRLContinuous needs a continuous MDP"
+        self.torch, self.tables = torch, tables
+        self.dev = DeviceTables(tables, "succ")
+        self.n_loops = N = int(n_loops)
+        self.seed, self.env_offset = int(seed), int(env_offset)
+        S, A = tables.S, tables.A
+        T = optimization_horizon
+        # posterior_sampling.py:268-303, in the reference's expressions
+        self.truncate_reward_with_max = bool(truncate_reward_with_max)
+        self.no_optimistic_sampling = bool(no_optimistic_sampling or (S ** 2 * A) > 6_000_000)
+        self.p = p
+        self.psi = min(max_psi, max(2, int(psi_weight * get_psi(S, A, T, p))))
+        self.omega = omega_weight * get_omega(S, A, T, p)
+        self.kappa = kappa_weight * get_kappa(S, A, T, p)
+        self.eta = max(5, min(10 * S, eta_weight * get_eta(S, A, T, p, self.omega)))
+        self._psi = 1 if self.no_optimistic_sampling else self.psi        # columns per real action on the device
+        self._eta = 0.0 if self.no_optimistic_sampling else float(self.eta)
+        self.reward_model = 1 if rname == "N_N" else 0
+        self._fast = int(sampler == "fast")
+        self._sweep_order = sweep_order
+        self._planner = planner
+        self._max_plan_bytes = int(max_plan_bytes)
+        rp = [tables.rmax, 1, 1, 1] if rewards_prior_prms is None else rewards_prior_prms       # bayesian_model.py:46-48
+        tp = [1.0 / S] if transitions_prior_prms is None else transitions_prior_prms              # :49-51
+        if self.reward_model == 1:
+            hp = np.zeros((S, A, 4), np.float32)
+            hp[..., :2] = np.tile(rp, (S, A, 1)).astype(np.float32)
+        else:
+            hp = np.tile(rp, (S, A, 1)).astype(np.float32)                                        # base_conjugate.py:44-47
+            mu, n_mu, tau, n_tau = (hp[..., k].copy() for k in range(4))
+            hp[..., 2], hp[..., 3] = n_tau * 0.5, (0.5 * n_tau) / tau                            # conjugate_rewards.py:45-54
+        dev = "cuda"
+        self.nig_hyper = torch.from_numpy(np.tile(hp, (N, 1, 1, 1))).cuda()
+        self.dir_hyper = torch.full((N, S, A, S), float(np.float32(tp[0])), dtype=torch.float32, device=dev)
+        self.N = torch.zeros((N, S, A, S), dtype=torch.int32, device=dev)                        # :309-311
+        self.Nsa = torch.zeros((N, S, A), dtype=torch.int32, device=dev)
+        self.nu = torch.zeros((N, S, A), dtype=torch.int32, device=dev)
+        self.Q = torch.zeros((N, S, A * self._psi), dtype=torch.float32, device=dev)
+        self.state = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.h = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.t = 0
+        _QLearningBatch.reset_envs(self)
+        self.time = torch.full((N,), self.t, dtype=torch.int64, device=dev)
+        self.cumulative_reward = torch.zeros(N, dtype=torch.float64, device=dev)
+        self.n_episodes = torch.zeros(N, dtype=torch.int64, device=dev)
+        self.ended = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros(N, dtype=torch.int64, device=dev)
+        self.vi_sweeps = 0
+        a = _cabi.PsrlcArgs()
+        a.N, a.seed, a.env0, a.psi, a.reward_model = N, self.seed, self.env_offset, self._psi, self.reward_model
+        a.state, a.t, a.cum_reward, a.Q = (self.state.data_ptr(), self.time.data_ptr(),
+                                           self.cumulative_reward.data_ptr(), self.Q.data_ptr())
+        a.dir_hyper, a.nig_hyper = self.dir_hyper.data_ptr(), self.nig_hyper.data_ptr()
+        a.Nsas, a.Nsa, a.nu = self.N.data_ptr(), self.Nsa.data_ptr(), self.nu.data_ptr()
+        a.ended, a.episode = self.ended.data_ptr(), self.episode.data_ptr()
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        self._args = a
+        # before_start_interacting (:378-382): the random q-values it sets are replaced by the first plan at once
+        self.episode_end_update(torch.arange(N, dtype=torch.int32, device=dev))
+
+    def sample_models(self, idx):
+        """optimistic_sampling + sample_R for the loops in idx: (T_ext f32[m,S,A*psi,S], R_ext f32[m,S,A*psi])"""
+        torch, S, A = self.torch, self.tables.S, self.tables.A
+        m = int(idx.numel())
+        T_ext = torch.empty((m, S, A * self._psi, S), dtype=torch.float32, device="cuda")
+        R_ext = torch.empty((m, S, A * self._psi), dtype=torch.float32, device="cuda")
+        rc = _cabi.lib().colo_psrlc_sample_models(C.byref(self._args), S, A, idx.data_ptr(), m, self._eta,
+                                                  int(self.truncate_reward_with_max), float(self.tables.rmax),
+                                                  self._fast, T_ext.data_ptr(), R_ext.data_ptr(), _cabi.current_stream())
+        _cabi.check(rc, "colo_psrlc_sample_models")
+        return T_ext, R_ext
+
+    def episode_end_update(self, idx):
+        """posterior_sampling.py:347-376 for the loops listed in idx (i32 device tensor), in chunks that keep the sampled
+        extended models under max_plan_bytes"""
+        from . import dynamic_programming as dp
+
+        S, A = self.tables.S, self.tables.A
+        per = S * A * self._psi * S * 4
+        chunk = max(1, self._max_plan_bytes // per)
+        for lo in range(0, int(idx.numel()), chunk):
+            sub = idx[lo:lo + chunk].contiguous()
+            if self._planner is not None:
+                self._planner(self, sub)
+            else:
+                T_ext, R_ext = self.sample_models(sub)
+                Q, _ = dp.discounted_value_iteration(T_ext, R_ext, precision="f32", sweep_order=self._sweep_order)
+                self.vi_sweeps += int(sum(dp.last_iterations()))
+                self.Q[sub.long()] = Q
+            rc = _cabi.lib().colo_psrlc_finish_episode(C.byref(self._args), S, A, sub.data_ptr(), int(sub.numel()),
+                                                       _cabi.current_stream())
+            _cabi.check(rc, "colo_psrlc_finish_episode")
+
+    def steps(self, n_steps: int, trace: bool = False):
+        """n_steps interactions for every loop.  trace=True returns i32 [n_steps, N, 4] = (s_t, EXTENDED action, s_tp1,
+        reward bits); the real action is column 1 // psi."""
+        torch = self.torch
+        tr = torch.zeros((n_steps, self.n_loops, 4), dtype=torch.int32, device="cuda") if trace else None
+        a = self._args
+        a.trace, a.trace_t0, a.trace_steps = (None if tr is None else tr.data_ptr()), self.t, int(n_steps)
+        target = self.t + int(n_steps)
+        self.rounds = 0
+        while True:
+            rc = _cabi.lib().colo_psrlc_steps(C.byref(self.dev.c), C.byref(a), target, _cabi.current_stream())
+            _cabi.check(rc, "colo_psrlc_steps")
+            idx = torch.nonzero(self.ended).flatten().to(torch.int32)
+            if idx.numel() == 0:
+                break
+            self.rounds += 1
+            self.episode_end_update(idx)
+        a.trace = None
+        self.t = target
+        return tr
+
+    def get_map_estimate(self):
+        """BayesianMDPModel.get_map_estimate (bayesian_model.py:71-76) for every loop"""
+        return self.dir_hyper / self.dir_hyper.sum(-1, keepdim=True), self.nig_hyper[..., 0]
+
+    def current_optimal_stochastic_policy(self, i: int) -> np.ndarray:
+        """posterior_sampling.py:176-180: greedy policy of the discounted VI on the MAP model"""
+        from .dynamic_programming import discounted_value_iteration, get_policy_from_q_values
+
+        T_map, R_map = self.get_map_estimate()
+        Q, _ = discounted_value_iteration(T_map[i].contiguous(), R_map[i].contiguous())
+        return get_policy_from_q_values(Q.cpu().numpy(), True)
+
+
 _CKPT_FIELDS = ("state", "h", "cumulative_reward", "n_episodes", "N", "Q", "Q_main", "V", "mu", "sigma", "beta",
                 "dir_hyper", "nig_hyper", "T_sample", "R_sample",
                 # UCRL2Continuous / PSRLContinuous

@@ -20,6 +20,7 @@
 // Arithmetic follows numpy's types sub-expression by sub-expression (NEP 50), with round-to-nearest intrinsics, so the
 // CPU restatement the tests compare with agrees bit for bit on trajectories and model tables.
 #include "agent_device.cuh"
+#include "gamma_device.cuh"
 
 namespace colo {
 
@@ -202,6 +203,221 @@ static int ucrl2_check(const colo_ucrl2_args* a) {
   return COLO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------- PSRLContinuous
+// select_action (posterior_sampling.py:389-392) = QValuesActor.select_action on the EXTENDED action set (A * psi columns:
+// psi sampled transition rows per real action), then extended_action_to_real: real = int(action / psi) -- applied to the
+// epsilon-greedy draw too, which the actor takes from range(A) (sic).  step_update (:394-412): BayesianMDPModel.step_update
+// (N_NIG / N_N reward posterior, Dirichlet count += 1; bayesian_model.py:78-92), N[s,a,s'] += 1, the episode's
+// transition list (here its length nu).  is_episode_end (:333-345, min_steps_before_new_episode = 0):
+// N_tau >= 2 (N_tau - nu_k).  (self.M is written by the reference and never read: not kept.)
+__global__ void __launch_bounds__(128) psrlc_steps_kernel(const colo_mdp_tables tb, const colo_psrlc_args p,
+                                                          long long t_target) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N) return;
+  if (p.ended[i] != 0) return;
+  const int S = tb.S, A = tb.A, psi = p.psi, AE = A * psi;
+  const size_t SA = (size_t)S * A;
+  const float* Q = p.Q + i * (size_t)S * AE;
+  float* dir = p.dir_hyper + i * SA * S;
+  float* nig = p.nig_hyper + i * SA * 4;
+  int* Nsas = p.Nsas + i * SA * S;
+  int* Nsa = p.Nsa + i * SA;
+  int* nu = p.nu + i * SA;
+  int s = p.state[i];
+  long long t = p.t[i];
+  double cum = p.cum_reward[i];
+  int flag = 0;
+  while (t < t_target) {
+    const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, (uint64_t)t);
+    const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, (uint64_t)t);
+    int a_ext;
+    if (p.epsilon_greedy >= 0.0 && (double)u24(wa.w[0]) < p.epsilon_greedy)
+      a_ext = act_from_word(wa.w[1], A);
+    else
+      a_ext = select_action(Q + (size_t)s * AE, AE, -1.0, wa);
+    const int a = a_ext / psi;
+    const size_t sa = (size_t)s * A + a;
+    float* hp = nig + sa * 4;
+    const float4 hp0 = *reinterpret_cast<const float4*>(hp);
+    const int n_sa = Nsa[sa] + 1, nu_k = nu[sa] + 1;
+    const Step st = env_succ(tb, s, a, u53(we.w[0], we.w[1]));
+    const float r = reward_from_class(tb, st.cls, u24(we.w[2]));
+    const float mu0 = hp0.x, l0 = hp0.y, a0 = hp0.z, b0 = hp0.w;
+    if (p.reward_model == 1) {  // N_N.update_sa (conjugate_rewards.py:112-117): float32 throughout
+      const float t1 = __fadd_rn(l0, 1.0f);
+      hp[0] = __fdiv_rn(__fadd_rn(__fmul_rn(mu0, l0), r), t1);
+      hp[1] = t1;
+    } else {  // N_NIG.update_sa with one reward (conjugate_rewards.py:56-74)
+      const double y = (double)r;
+      const float l1 = __fadd_rn(l0, 1.0f);
+      const double mu1 = __ddiv_rn(__dadd_rn((double)__fmul_rn(l0, mu0), y), (double)l1);
+      const double dy = __dsub_rn(y, (double)mu0);
+      const double disc = __ddiv_rn(__dmul_rn((double)l0, __dmul_rn(dy, dy)), (double)l1);
+      hp[0] = (float)mu1;
+      hp[1] = l1;
+      hp[2] = __fadd_rn(a0, 0.5f);
+      hp[3] = (float)__dadd_rn((double)b0, __dmul_rn(0.5, __dadd_rn(0.0, disc)));
+    }
+    float* dc = dir + sa * S + st.nxt;
+    *dc = __fadd_rn(*dc, 1.0f);
+    Nsas[sa * S + st.nxt] += 1;
+    Nsa[sa] = n_sa;
+    nu[sa] = nu_k;
+    cum = __dadd_rn(cum, (double)r);
+    if (p.trace) {
+      const long long k = t - p.trace_t0;
+      if (k >= 0 && k < p.trace_steps) {
+        int* tr = p.trace + ((size_t)k * p.N + i) * 4;
+        tr[0] = s; tr[1] = a_ext; tr[2] = st.nxt; tr[3] = __float_as_int(r);
+      }
+    }
+    s = st.nxt;
+    ++t;
+    if (n_sa >= 2 * (n_sa - nu_k)) {
+      flag = 1;
+      break;
+    }
+  }
+  p.state[i] = s;
+  p.t[i] = t;
+  p.cum_reward[i] = cum;
+  if (flag) p.ended[i] = flag;
+}
+
+constexpr uint64_t kSimpleSamplingKey = 0xC2B2AE3D27D4EB4FULL;  // the z draws of optimistic_sampling
+
+// optimistic_sampling (posterior_sampling.py:414-447) for the listed loops: T_ext[k, s, a * psi + q, :] for q < psi.
+//   N[s,a].sum() >= eta : a Dirichlet posterior sample of the row (M_DIR._sample, conjugate_transitions.py:48-54:
+//                         float32 gammas, r / (1e-5 + sum r));
+//   otherwise           : "simple sampling", P_minus = P_hat - min(sqrt(3 P_hat log(4S) / N) + 3 log(4S) / N, P_hat) with
+//                         the missing mass 1 - sum(P_minus) put on ONE state z_q drawn per sample (the same for every row
+//                         of that sample; the reference's self._rng.randint(S)), in float64, stored float32.
+// One warp per (listed loop, s, a); the psi samples of a row reuse the row statistics.  Draw counters: posterior rows
+// (seed; ((env0+i) S A + sa) S + j, episode * 64 + q), z (seed ^ kSimpleSamplingKey; env0+i, episode * 64 + q).
+template <bool FAST>
+__global__ void __launch_bounds__(256) psrlc_sample_kernel(const colo_psrlc_args p, int S, int A,
+                                                           const int* __restrict__ index, int m, double eta,
+                                                           float* __restrict__ T_ext) {
+  const size_t SA = (size_t)S * A;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)m * (long long)SA) return;
+  const int k = (int)(w / (long long)SA);
+  const size_t sa = (size_t)(w % (long long)SA);
+  const size_t s = sa / A, a = sa % A;
+  const size_t i = (size_t)index[k];
+  const int psi = p.psi;
+  const uint64_t ep = (uint64_t)p.episode[i];
+  const int nsum = p.Nsa[i * SA + sa];
+  float* out0 = T_ext + (((size_t)k * S + s) * ((size_t)A * psi) + a * psi) * S;
+  if ((double)nsum >= eta) {
+    const float* __restrict__ h = p.dir_hyper + (i * SA + sa) * S;
+    for (int q = 0; q < psi; ++q) {
+      float* out = out0 + (size_t)q * S;
+      float sum = 0.f;
+      for (int j = lane; j < S; j += 32) {
+        const uint64_t elem = ((p.env0 + (uint64_t)i) * SA + sa) * (uint64_t)S + (uint64_t)j;
+        const float g = FAST ? gamma_draw_fast(h[j], p.seed, elem, ep * 64 + q)
+                             : (float)gamma_draw((double)h[j], p.seed, elem, ep * 64 + q);
+        out[j] = g;
+        sum += g;
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / (1e-5f + sum);
+      for (int j = lane; j < S; j += 32) out[j] *= inv;
+    }
+  } else {
+    const int* __restrict__ n = p.Nsas + (i * SA + sa) * S;
+    const double tot = (double)(nsum > 1 ? nsum : 1);
+    const double L = log((double)(4 * S));
+    double part = 0.0;
+    for (int j = lane; j < S; j += 32) {
+      const int nj = n[j];
+      const double ph = __ddiv_rn((double)nj, tot);
+      const double nn = (double)(nj > 1 ? nj : 1);
+      const double rad = __dadd_rn(__dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(3.0, ph), L), nn)),
+                                   __ddiv_rn(__dmul_rn(3.0, L), nn));
+      const double pm = __dsub_rn(ph, rad < ph ? rad : ph);
+      part += pm;
+    }
+    const double summing = 1.0 - warp_sum(part);
+    for (int q = 0; q < psi; ++q) {
+      const Philox4 wz = philox4x32_10(p.seed ^ kSimpleSamplingKey, p.env0 + (uint64_t)i, ep * 64 + q);
+      const int z = act_from_word(wz.w[0], S);
+      float* out = out0 + (size_t)q * S;
+      for (int j = lane; j < S; j += 32) {
+        const int nj = n[j];
+        const double ph = __ddiv_rn((double)nj, tot);
+        const double nn = (double)(nj > 1 ? nj : 1);
+        const double rad = __dadd_rn(__dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(3.0, ph), L), nn)),
+                                     __ddiv_rn(__dmul_rn(3.0, L), nn));
+        double pm = __dsub_rn(ph, rad < ph ? rad : ph);
+        if (j == z) pm += summing;
+        out[j] = (float)pm;
+      }
+    }
+  }
+}
+
+// sample_R (N_NIG.sample / N_N.sample, conjugate_rewards.py:76-92, :119-127) for the listed loops, tiled psi times along
+// the extended action axis: R_ext[k, s, c] = R[s, c % A] (np.tile(R, (1, psi)), posterior_sampling.py:371-372 -- sic:
+// transitions are laid out action-major (c // psi is the real action), rewards sample-major); optionally
+// R = maximum(r_max, R) first (truncate_reward_with_max, :369-370, sic).  One thread per (listed loop, s, a).
+__global__ void __launch_bounds__(128) psrlc_rewards_kernel(const colo_psrlc_args p, int S, int A,
+                                                            const int* __restrict__ index, int m, int truncate,
+                                                            float r_max, float* __restrict__ R_ext) {
+  const size_t SA = (size_t)S * A;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)m * (long long)SA) return;
+  const int k = (int)(gid / (long long)SA);
+  const size_t sa = (size_t)(gid % (long long)SA);
+  const size_t s = sa / A, a = sa % A;
+  const size_t i = (size_t)index[k];
+  const uint64_t ep = (uint64_t)p.episode[i];
+  const float4 h = *reinterpret_cast<const float4*>(p.nig_hyper + (i * SA + sa) * 4);
+  const uint64_t elem = (p.env0 + (uint64_t)i) * SA + sa;
+  const Philox4 w = philox4x32_10(p.seed ^ 0x8CB92BA72F3D8DD7ULL, elem, ep);
+  const double u1 = u53(w.w[0], w.w[1]) + 1.1102230246251565e-16, u2 = (double)w.w[2] * (1.0 / 4294967296.0);
+  const double zn = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  float r;
+  if (p.reward_model == 1) {
+    r = (float)((double)h.x + (double)h.y * zn);
+  } else {
+    const float tau = (float)(gamma_draw((double)h.z, p.seed ^ 0xD1B54A32D192ED03ULL, elem, ep) / (double)h.w);
+    const float var = 1.0f / (h.y * tau);
+    r = (float)((double)h.x + sqrt((double)var) * zn);
+  }
+  if (truncate) r = fmaxf(r_max, r);
+  float* out = R_ext + ((size_t)k * S + s) * ((size_t)A * p.psi);
+  for (int c = (int)a; c < A * p.psi; c += A) out[c] = r;
+}
+
+// end of episode_end_update for the listed loops (:376): the episode's transition lists are dropped; the flag clears.
+__global__ void __launch_bounds__(256) psrlc_finish_kernel(const colo_psrlc_args p, int S, int A,
+                                                           const int* __restrict__ index, int m) {
+  const size_t SA = (size_t)S * A;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)m * (long long)SA) return;
+  const size_t i = (size_t)index[(int)(gid / (long long)SA)];
+  const size_t sa = (size_t)(gid % (long long)SA);
+  p.nu[i * SA + sa] = 0;
+  if (sa == 0) {
+    p.ended[i] = 0;
+    p.episode[i] += 1;
+  }
+}
+
+static int psrlc_check(const colo_psrlc_args* a) {
+  COLO_ARG_CHECK(a, "args are NULL");
+  COLO_ARG_CHECK(a->N >= 0 && a->psi >= 1 && a->psi <= 64, "N >= 0, 1 <= psi <= 64");
+  if (a->N == 0) return COLO_OK;
+  COLO_ARG_CHECK(a->state && a->t && a->cum_reward && a->Q && a->dir_hyper && a->nig_hyper && a->Nsas && a->Nsa &&
+                     a->nu && a->ended && a->episode,
+                 "every table pointer of colo_psrlc_args must be set");
+  COLO_ARG_CHECK((uintptr_t)a->nig_hyper % 16 == 0, "nig_hyper must be 16-byte aligned (rows are read as one float4)");
+  return COLO_OK;
+}
+
 }  // namespace colo
 
 extern "C" {
@@ -241,6 +457,47 @@ int colo_ucrl2_model_update(const colo_ucrl2_args* a, int S, int A, const int* i
   if (r != COLO_OK) return r;
   colo::ucrl2_rewards_kernel<<<(m + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*a, S, A, index, m);
   return colo::check_launch("ucrl2_rewards_kernel");
+}
+
+int colo_psrlc_steps(const colo_mdp_tables* tb, const colo_psrlc_args* a, long long t_target, void* stream) {
+  COLO_ARG_CHECK(tb, "tables are NULL");
+  int r = colo::psrlc_check(a);
+  if (r != COLO_OK || a->N == 0) return r;
+  COLO_ARG_CHECK(tb->S > 0 && tb->A > 0 && tb->H == 0 && tb->rew_q && tb->n_cls > 0 && tb->nq >= 2,
+                 "PSRLContinuous needs the tables of a continuous MDP (H == 0)");
+  COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
+  const int grid = (int)((a->N + 127) / 128);
+  colo::psrlc_steps_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*tb, *a, t_target);
+  return colo::check_launch("psrlc_steps_kernel");
+}
+
+int colo_psrlc_sample_models(const colo_psrlc_args* a, int S, int A, const int* index, int m, double eta, int truncate,
+                             float r_max, int fast, float* T_ext, float* R_ext, void* stream) {
+  int r = colo::psrlc_check(a);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(S > 0 && A > 0 && m >= 0 && (m == 0 || (index && T_ext && R_ext)), "S, A, m, index, T_ext, R_ext");
+  if (m == 0) return COLO_OK;
+  const long long warps = (long long)m * S * A;
+  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+  if (fast)
+    colo::psrlc_sample_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, S, A, index, m, eta, T_ext);
+  else
+    colo::psrlc_sample_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(*a, S, A, index, m, eta, T_ext);
+  r = colo::check_launch("psrlc_sample_kernel");
+  if (r != COLO_OK) return r;
+  colo::psrlc_rewards_kernel<<<(unsigned)((warps + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*a, S, A, index, m, truncate,
+                                                                                             r_max, R_ext);
+  return colo::check_launch("psrlc_rewards_kernel");
+}
+
+int colo_psrlc_finish_episode(const colo_psrlc_args* a, int S, int A, const int* index, int m, void* stream) {
+  int r = colo::psrlc_check(a);
+  if (r != COLO_OK) return r;
+  COLO_ARG_CHECK(S > 0 && A > 0 && m >= 0 && (m == 0 || index), "S, A, m, index");
+  if (m == 0) return COLO_OK;
+  const long long n = (long long)m * S * A;
+  colo::psrlc_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a, S, A, index, m);
+  return colo::check_launch("psrlc_finish_kernel");
 }
 
 }  // extern "C"

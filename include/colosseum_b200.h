@@ -724,6 +724,50 @@ int colo_ucrl2_bounds(const colo_ucrl2_args* a, int S, int A, const int* index, 
                       double r_max, int bernstein_p, double* beta_r, double* beta_p, void* stream);
 int colo_ucrl2_model_update(const colo_ucrl2_args* a, int S, int A, const int* index, int m, void* stream);
 
+/*
+ * PSRLContinuous (colosseum/agent/agents/infinite_horizon/posterior_sampling.py:117-452; Agrawal & Jia 2017) for N
+ * independent loops on one continuous MDP, in the same rounds as UCRL2Continuous:
+ *   colo_psrlc_steps          select_action on the extended q-values Q f32[N,S,A*psi] (real action = extended / psi,
+ *                             :449-452), BaseMDP.step, step_update (:394-412: BayesianMDPModel.step_update on nig_hyper
+ *                             f32[N,S,A,4] / dir_hyper f32[N,S,A,S], N[s,a,s'] += 1), is_episode_end (:333-345:
+ *                             N_tau >= 2 (N_tau - nu_k)) until t[i] reaches t_target or the artificial episode ends;
+ *   colo_psrlc_sample_models  for the loops in index[m]: optimistic_sampling (:414-447) into T_ext f32[m,S,A*psi,S]
+ *                             (rows with N[s,a].sum() >= eta: psi Dirichlet posterior samples; the others: the
+ *                             "simple sampling" rows P_minus + the missing mass on one random state per sample) and the
+ *                             reward sample tiled psi times into R_ext f32[m,S,A*psi] (:368-372; truncate != 0:
+ *                             maximum(r_max, R) first).  fast != 0: single-precision gamma draws.  The caller solves
+ *                             (T_ext, R_ext) with colo_solve_discounted_* (B = m) and writes the q-values back;
+ *   colo_psrlc_finish_episode the episode's visit counts nu are dropped, ended cleared, episode += 1.
+ * psi = 1 and eta = 0 give no_optimistic_sampling (T = sample_T()).  Tables per loop contiguous; Nsas i32[N,S,A,S],
+ * Nsa i32[N,S,A], nu i32[N,S,A], t / episode i64[N], ended i32[N].  Randomness and trace as colo_ucrl2_* (trace column
+ * 1 is the EXTENDED action).  None synchronises.
+ */
+typedef struct {
+  long long N;
+  unsigned long long seed, env0;
+  int* state;
+  long long* t;
+  double* cum_reward;
+  const float* Q;
+  int psi;
+  float* dir_hyper;
+  float* nig_hyper;
+  int reward_model; /* 0 = N_NIG, 1 = N_N */
+  int* Nsas;
+  int* Nsa;
+  int* nu;
+  int* ended;
+  long long* episode;
+  double epsilon_greedy; /* < 0: greedy */
+  int* trace;
+  long long trace_t0;
+  int trace_steps;
+} colo_psrlc_args;
+int colo_psrlc_steps(const colo_mdp_tables* tb, const colo_psrlc_args* a, long long t_target, void* stream);
+int colo_psrlc_sample_models(const colo_psrlc_args* a, int S, int A, const int* index, int m, double eta, int truncate,
+                             float r_max, int fast, float* T_ext, float* R_ext, void* stream);
+int colo_psrlc_finish_episode(const colo_psrlc_args* a, int S, int A, const int* index, int m, void* stream);
+
 /* Dense CDF builder on device: cdf[s,a,0..ld) from T[s,a,0..S) (sequential fp64 running sum per row, one thread
  * per row -- the DEFINED summation order the oracle shares).  out_is_f64: 0 float, 1 double. */
 int colo_build_dense_cdf(const float* T, int S, int A, int ld, void* cdf, int out_is_f64, void* stream);

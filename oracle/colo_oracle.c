@@ -1203,3 +1203,114 @@ int orc_ucrl2_model_update(const orc_ucrl2_args* p, int S, int A, const int* ind
   }
   return ORC_OK;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * PSRLContinuous between two re-plannings (colosseum/agent/agents/infinite_horizon/posterior_sampling.py:333-345,
+ * :389-412, :449-452) for N independent loops: QValuesActor.select_action on the EXTENDED q-values Q[N,S,A*psi], real
+ * action = int(action / psi) (also for the epsilon-greedy draw, which comes from range(A), sic),
+ * BayesianMDPModel.step_update (N_NIG / N_N posterior, Dirichlet count += 1), N[s,a,s'] += 1, and is_episode_end:
+ * N_tau >= 2 (N_tau - nu_k).  Each loop stops at t_target or when its artificial episode ends (ended[i] = 1).
+ */
+typedef struct {
+  long long N;
+  uint64_t seed, env0;
+  int* state;
+  long long* t;
+  double* cum_reward;
+  const float* Q;
+  int psi;
+  float* dir_hyper;
+  float* nig_hyper;
+  int reward_model;
+  int* Nsas;
+  int* Nsa;
+  int* nu;
+  int* ended;
+  long long* episode;
+  double epsilon_greedy;
+  int* trace;
+  long long trace_t0;
+  int trace_steps;
+} orc_psrlc_args;
+
+int orc_psrlc_steps(const orc_tables* tb, const orc_psrlc_args* p, long long t_target) {
+  const int S = tb->S, A = tb->A, psi = p->psi, AE = A * psi;
+  const size_t SA = (size_t)S * A;
+#pragma omp parallel for schedule(static)
+  for (long long i = 0; i < p->N; ++i) {
+    if (p->ended[i] != 0) continue;
+    const float* Q = p->Q + (size_t)i * S * AE;
+    float* dir = p->dir_hyper + (size_t)i * SA * S;
+    float* nig = p->nig_hyper + (size_t)i * SA * 4;
+    int* Nsas = p->Nsas + (size_t)i * SA * S;
+    int* Nsa = p->Nsa + (size_t)i * SA;
+    int* nu = p->nu + (size_t)i * SA;
+    int s = p->state[i];
+    long long t = p->t[i];
+    double cum = p->cum_reward[i];
+    int flag = 0;
+    while (t < t_target) {
+      uint32_t we[4], wa[4];
+      orc_philox(p->seed, p->env0 + (uint64_t)i, (uint64_t)t, we);
+      orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, (uint64_t)t, wa);
+      int a_ext;
+      if (p->epsilon_greedy >= 0.0 && (double)u24(wa[0]) < p->epsilon_greedy)
+        a_ext = act_from_word(wa[1], A);
+      else
+        a_ext = orc_select_action(Q + (size_t)s * AE, AE, -1.0, wa);
+      const int a = a_ext / psi;
+      const size_t sa = (size_t)s * A + a;
+      const size_t base = sa * tb->Ksucc;
+      const int nsucc = tb->succ_len[sa];
+      int pos = 0;
+      if (nsucc > 1) {
+        const double total = tb->succ_cum[base + nsucc - 1] + 0.0;
+        pos = bisect_pos(tb->succ_cum + base, nsucc, u53(we[0], we[1]) * total);
+      }
+      const int nxt = tb->succ_idx[base + pos];
+      const int cls = tb->rew_cls_succ ? tb->rew_cls_succ[base + pos] : 0;
+      const float r = reward_draw(tb, cls, u24(we[2]));
+      float* hp = nig + sa * 4;
+      const float mu0 = hp[0], l0 = hp[1], a0 = hp[2], b0 = hp[3];
+      if (p->reward_model == 1) {
+        const float t1 = l0 + 1.0f;
+        const float num = mu0 * l0 + r;
+        hp[0] = num / t1;
+        hp[1] = t1;
+      } else {
+        const double y = (double)r;
+        const float l1 = l0 + 1.0f;
+        const float lm = l0 * mu0;
+        const double mu1 = ((double)lm + y) / (double)l1;
+        const double dy = y - (double)mu0;
+        const double disc = (double)l0 * (dy * dy) / (double)l1;
+        hp[0] = (float)mu1;
+        hp[1] = l1;
+        hp[2] = a0 + 0.5f;
+        hp[3] = (float)((double)b0 + 0.5 * (0.0 + disc));
+      }
+      dir[sa * S + nxt] += 1.0f;
+      Nsas[sa * S + nxt] += 1;
+      Nsa[sa] += 1;
+      nu[sa] += 1;
+      cum += (double)r;
+      if (p->trace) {
+        const long long k = t - p->trace_t0;
+        if (k >= 0 && k < p->trace_steps) {
+          int* tr = p->trace + ((size_t)k * p->N + i) * 4;
+          union { float f; int i; } u;
+          u.f = r;
+          tr[0] = s; tr[1] = a_ext; tr[2] = nxt; tr[3] = u.i;
+        }
+      }
+      s = nxt;
+      ++t;
+      if (Nsa[sa] >= 2 * (Nsa[sa] - nu[sa])) { flag = 1; break; }
+    }
+    p->state[i] = s;
+    p->t[i] = t;
+    p->cum_reward[i] = cum;
+    if (flag) p->ended[i] = flag;
+  }
+  return ORC_OK;
+}

@@ -612,3 +612,113 @@ class UCRL2Loops:
             self.episode_end_update(idx)
         self.args.trace = None
         return tr
+
+
+# ------------------------------------------------------------------------------------------------- PSRLContinuous
+class _PsrlcArgs(C.Structure):
+    _fields_ = [
+        ("N", C.c_longlong), ("seed", C.c_uint64), ("env0", C.c_uint64),
+        ("state", C.c_void_p), ("t", C.c_void_p), ("cum_reward", C.c_void_p), ("Q", C.c_void_p), ("psi", C.c_int),
+        ("dir_hyper", C.c_void_p), ("nig_hyper", C.c_void_p), ("reward_model", C.c_int),
+        ("Nsas", C.c_void_p), ("Nsa", C.c_void_p), ("nu", C.c_void_p), ("ended", C.c_void_p), ("episode", C.c_void_p),
+        ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong), ("trace_steps", C.c_int),
+    ]
+
+
+def psrlc_parameters(S, A, optimization_horizon, p=0.05, psi_weight=1.0, omega_weight=1.0, kappa_weight=1.0,
+                     eta_weight=1.0, max_psi=60, no_optimistic_sampling=False):
+    """psi, omega, kappa, eta of PSRLContinuous.__init__ (posterior_sampling.py:20-115, :268-303), in its expressions"""
+    T = optimization_horizon
+    no_opt = bool(no_optimistic_sampling or (S ** 2 * A) > 6_000_000)
+    psi = min(max_psi, max(2, int(psi_weight * (S * np.log(S * A / p)))))
+    omega = omega_weight * np.log(T / p)
+    kappa = kappa_weight * np.log(T / p)
+    eta = max(5, min(10 * S, eta_weight * (np.sqrt(T * S / A) + 12 * omega * S ** 4)))
+    return dict(psi=1 if no_opt else psi, omega=omega, kappa=kappa, eta=0.0 if no_opt else float(eta),
+                no_optimistic_sampling=no_opt)
+
+
+def psrlc_simple_rows(Nsas, z):
+    """the "simple sampling" rows of optimistic_sampling (posterior_sampling.py:424-446) for ONE sample: P_minus with the
+    missing mass on state z, float32 [S,A,S].  The reference's own numpy expressions."""
+    S = Nsas.shape[-1]
+    Nsum = Nsas.sum(-1)
+    P_hat = Nsas / np.maximum(Nsum[..., None], 1)
+    N = np.maximum(Nsas, 1)
+    P_minus = P_hat - np.minimum(np.sqrt(3 * P_hat * np.log(4 * S) / N) + 3 * np.log(4 * S) / N, P_hat)
+    summing = 1 - P_minus.sum(-1)
+    P_minus[:, :, z] += summing
+    return P_minus.astype(np.float32)
+
+
+def psrlc_z(seed, env, episode, q, S):
+    """the state that receives the missing mass in sample q of the loop's `episode`-th re-planning"""
+    w = philox(seed ^ 0xC2B2AE3D27D4EB4F, env, episode * 64 + q)
+    return int((int(w[0]) * S) >> 32)
+
+
+class PSRLCLoops:
+    """CPU restatement of N PSRLContinuous loops BETWEEN re-plannings (orc_psrlc_steps): the caller supplies the
+    extended q-values of each loop (`Q[i] = ...` inside `planner(loops, idx)`), as the product does after
+    colo_psrlc_sample_models + the discounted VI.  Priors as BayesianMDPModel (bayesian_model.py:44-57)."""
+
+    def __init__(self, tb, n_loops, psi, seed=0, env0=0, epsilon_greedy=None, rewards_prior_prms=None,
+                 transitions_prior_prms=None, reward_prior_model="N_NIG", planner=None):
+        assert tb.c.H == 0
+        self.tb, self.N, self.seed, self.env0, self.psi = tb, int(n_loops), int(seed), int(env0), int(psi)
+        self.reward_model = {"N_NIG": 0, "N_N": 1}[reward_prior_model]
+        S, A, N = tb.c.S, tb.c.A, self.N
+        self.S, self.A = S, A
+        self.planner = planner
+        self.state, _, _, _ = env_reset(tb, N, seed=seed, t=0, env0=env0)
+        self.t = np.ones(N, np.int64)
+        self.cum_reward = np.zeros(N, np.float64)
+        rp = [tb.c.rmax, 1, 1, 1] if rewards_prior_prms is None else rewards_prior_prms
+        tp = [1.0 / S] if transitions_prior_prms is None else transitions_prior_prms
+        if self.reward_model == 1:
+            hp = np.zeros((S, A, 4), np.float32)
+            hp[..., :2] = np.tile(rp, (S, A, 1)).astype(np.float32)
+        else:
+            hp = np.tile(rp, (S, A, 1)).astype(np.float32)
+            mu, n_mu, tau, n_tau = hp[..., 0].copy(), hp[..., 1].copy(), hp[..., 2].copy(), hp[..., 3].copy()
+            hp[..., 0], hp[..., 1], hp[..., 2], hp[..., 3] = mu, n_mu, n_tau * 0.5, (0.5 * n_tau) / tau
+        self.nig_hyper = np.tile(hp, (N, 1, 1, 1)).astype(np.float32)
+        self.dir_hyper = np.tile(np.float32(tp[0]), (N, S, A, S)).astype(np.float32)
+        self.Q = np.zeros((N, S, A * self.psi), np.float32)
+        self.Nsas = np.zeros((N, S, A, S), np.int32)
+        self.Nsa = np.zeros((N, S, A), np.int32)
+        self.nu = np.zeros((N, S, A), np.int32)
+        self.ended = np.zeros(N, np.int32)
+        self.episode = np.zeros(N, np.int64)
+        self.episode_ends = [[] for _ in range(N)]
+        a = _PsrlcArgs()
+        a.N, a.seed, a.env0, a.psi, a.reward_model = N, self.seed, self.env0, self.psi, self.reward_model
+        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
+        for k in ("state", "t", "cum_reward", "Q", "dir_hyper", "nig_hyper", "Nsas", "Nsa", "nu", "ended", "episode"):
+            setattr(a, k, _p(getattr(self, k)))
+        self.args = a
+        self.episode_end_update(np.arange(N))  # before_start_interacting (posterior_sampling.py:378-382)
+
+    def episode_end_update(self, idx):
+        self.planner(self, np.asarray(idx))   # fills self.Q[idx]
+        self.nu[idx] = 0
+        self.ended[idx] = 0
+        self.episode[idx] += 1
+
+    def steps(self, n_steps, trace=False):
+        t0 = int(self.t[0])
+        assert (self.t == t0).all()
+        tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
+        self.args.trace, self.args.trace_t0, self.args.trace_steps = _p(tr), t0, int(n_steps)
+        target = t0 + int(n_steps)
+        while True:
+            rc = lib().orc_psrlc_steps(C.byref(self.tb.c), C.byref(self.args), C.c_longlong(target))
+            assert rc == 0
+            idx = np.nonzero(self.ended)[0]
+            if len(idx) == 0:
+                break
+            for i in idx:
+                self.episode_ends[i].append(int(self.t[i]))
+            self.episode_end_update(idx)
+        self.args.trace = None
+        return tr

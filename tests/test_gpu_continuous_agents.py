@@ -200,3 +200,187 @@ def test_ucrl2_learns_river_swim():
     rate = (float(ag.cumulative_reward.mean()) - before) / (T // 5)
     assert rate > 0.7, rate
     assert int(ag.time.min()) == int(ag.time.max()) == T + 1 and int(ag.ended.max()) == 0
+
+
+# ------------------------------------------------------------------------------------------------- PSRLContinuous
+import make_psrlc_golden as pmk  # noqa: E402
+
+
+def _psrlc_pairs(dev, cpu):
+    return [("N", dev.N, cpu.Nsas), ("Nsa", dev.Nsa, cpu.Nsa), ("dir", dev.dir_hyper, cpu.dir_hyper),
+            ("nig", dev.nig_hyper, cpu.nig_hyper), ("episode", dev.episode, cpu.episode), ("state", dev.state, cpu.state),
+            ("time", dev.time, cpu.t), ("cum_reward", dev.cumulative_reward, cpu.cum_reward), ("nu", dev.nu, cpu.nu),
+            ("Q", dev.Q, cpu.Q)]
+
+
+def _agent_kwargs(kw):
+    return {k: v for k, v in kw.items() if k != "reward_prior_model"} | (
+        {"reward_prior_model": kw["reward_prior_model"]} if "reward_prior_model" in kw else {})
+
+
+@pytest.mark.parametrize("name,inst,kw", pmk.CASES, ids=[c[0] for c in pmk.CASES])
+def test_psrl_continuous_kernels_equal_oracle_bit_for_bit(name, inst, kw):
+    """steps, extended-action decoding, posterior updates and artificial-episode ends of N loops: kernel == oracle bit
+    for bit, both sides acting on the same extended q-values after every re-planning (the oracle's deterministic
+    planner, looked up by (loop, episode)).  At every re-planning the device's optimistic sampling is checked on the same
+    posterior: the under-visited rows against the reference's own expressions with the same z, the Dirichlet rows and
+    the reward layout structurally."""
+    import torch
+
+    import colosseum_b200.agent_loop as al
+
+    tb = MDPTables.from_golden(load_instance(inst))
+    N, n_steps, seed = 29, 1200, 7
+    prm = pmk.parameters(tb, kw, n_steps + 1)
+    hist = {}
+    base = pmk.make_planner(prm)
+
+    def cpu_planner(loops, idx):
+        base(loops, idx)
+        for i in idx:
+            hist[(int(i), int(loops.episode[i]))] = loops.Q[i].copy()
+
+    cpu = orc.PSRLCLoops(host_tables(tb), N, prm["psi"], seed=seed, planner=cpu_planner, **pmk.loop_kwargs(kw))
+    tr_c = cpu.steps(n_steps, trace=True)
+    seen = {"simple_rows": 0, "posterior_rows": 0, "worst_simple": 0.0, "worst_rowsum": 0.0}
+    S, A = tb.S, tb.A
+
+    def planner(ag, idx):
+        ids = idx.cpu().numpy()
+        ep = ag.episode.cpu().numpy()
+        T_ext, R_ext = ag.sample_models(idx)
+        psi = ag._psi
+        Tn = T_ext.cpu().numpy().reshape(len(ids), S, A, psi, S)
+        Rn = R_ext.cpu().numpy()
+        assert np.isfinite(Tn).all() and np.isfinite(Rn).all() and (Tn >= 0).all()
+        assert np.array_equal(Rn, np.tile(Rn[:, :, :A], (1, 1, psi)))  # np.tile(R, (1, psi)), :371-372
+        Nn = ag.N[idx.long()].cpu().numpy()
+        for k, i in enumerate(ids):
+            cond = Nn[k].sum(-1) < ag._eta
+            for q in range(psi):
+                if cond.any():
+                    z = orc.psrlc_z(seed, int(i), int(ep[i]), q, S)
+                    want = orc.psrlc_simple_rows(Nn[k], z)
+                    seen["worst_simple"] = max(seen["worst_simple"], float(np.abs(Tn[k][:, :, q][cond] - want[cond]).max()))
+                if (~cond).any():
+                    seen["worst_rowsum"] = max(seen["worst_rowsum"], float(np.abs(Tn[k][:, :, q][~cond].sum(-1) - 1).max()))
+            seen["simple_rows"] += int(cond.sum())
+            seen["posterior_rows"] += int((~cond).sum())
+        ag.Q[idx.long()] = torch.from_numpy(np.stack([hist[(int(i), int(ep[i]))] for i in ids])).cuda()
+
+    akw = {k: v for k, v in kw.items()}
+    dev = al.PSRLContinuous(seed, tb, n_steps + 1, n_loops=N, planner=planner, **akw)
+    assert (dev._psi, dev.omega, dev.kappa, dev._eta) == (prm["psi"], prm["omega"], prm["kappa"], prm["eta"])
+    tr_d = torch.cat([dev.steps(500, trace=True), dev.steps(n_steps - 500, trace=True)]).cpu().numpy()
+    assert np.array_equal(tr_d, tr_c)
+    for f, d, c in _psrlc_pairs(dev, cpu):
+        assert np.array_equal(d.cpu().numpy(), c), f
+    assert seen["posterior_rows"] > 0
+    assert seen["worst_simple"] < 1e-7 and seen["worst_rowsum"] < 1e-4, seen
+    if not prm["no_optimistic_sampling"]:
+        assert seen["simple_rows"] > 0
+
+
+def test_psrl_continuous_sampled_models_follow_the_posterior():
+    """moments of the device's model samples against the posterior they are drawn from: Dirichlet rows (mean alpha /
+    alpha_0, variance alpha_j (alpha_0 - alpha_j) / (alpha_0^2 (alpha_0 + 1))) and the N_NIG reward marginal (mean mu),
+    over 600 re-plannings of one fixed posterior, for both samplers."""
+    import torch
+
+    import colosseum_b200.agent_loop as al
+
+    tb = MDPTables.from_golden(load_instance("riverswimcontinuous_ergo0"))
+    S, A = tb.S, tb.A
+    for sampler in ("fast", "f64"):
+        ag = al.PSRLContinuous(3, tb, 10_000, psi_weight=0.02, eta_weight=1e-9, n_loops=2, sampler=sampler)
+        ag.steps(3000)
+        idx = torch.tensor([1], dtype=torch.int32, device="cuda")
+        alpha = ag.dir_hyper[1].double().cpu().numpy()
+        visited = (ag.Nsa[1].cpu().numpy() >= ag._eta)
+        assert visited.sum() >= 4
+        acc, acc2, racc, n = 0.0, 0.0, 0.0, 0
+        for rep in range(600):
+            ag.episode[1] = 10_000 + rep  # a fresh draw counter, the posterior untouched
+            T_ext, R_ext = ag.sample_models(idx)
+            t = T_ext[0].double().cpu().numpy().reshape(S, A, ag._psi, S)
+            acc, acc2 = acc + t.sum(2), acc2 + (t ** 2).sum(2)
+            racc = racc + R_ext[0, :, :A].double().cpu().numpy()
+            n += ag._psi
+        mean, var = acc / n, acc2 / n - (acc / n) ** 2
+        a0 = alpha.sum(-1, keepdims=True)
+        want_mean, want_var = alpha / a0, alpha * (a0 - alpha) / (a0 ** 2 * (a0 + 1))
+        se = np.sqrt(want_var / n) + 1e-4
+        assert (np.abs(mean - want_mean)[visited] < 6 * se[visited]).all(), sampler
+        big = visited[..., None] & (want_var > 1e-4)
+        ratio = var[big] / want_var[big]  # sample variances of skewed marginals from 600 * psi draws: noisy one by one
+        assert big.sum() > 4 and abs(np.median(ratio) - 1) < 0.1 and (np.abs(ratio - 1) < 0.6).mean() > 0.98, sampler
+        hp = ag.nig_hyper[1].double().cpu().numpy()
+        # marginal of the mean: Student-t centred at mu with scale sqrt(beta / (alpha lambda)); alpha > 1 after visits
+        ok = visited & (hp[..., 2] > 2)
+        sd = np.sqrt(hp[..., 3] / ((hp[..., 2] - 1) * hp[..., 1]))
+        assert ok.sum() >= 4 and (np.abs(racc / 600 - hp[..., 0])[ok] < 6 * sd[ok] / np.sqrt(600) + 1e-4).all(), sampler
+
+
+def test_psrl_continuous_device_loop_replays_and_learns():
+    """the complete device agent (its own sampling and batched value iteration): the oracle, acting on the DEVICE's
+    extended q-values of each re-planning, reproduces every trajectory and posterior bit for bit; and the batch learns
+    RiverSwim (optimal average reward 0.889, random policy 0.017)."""
+    import colosseum_b200.agent_loop as al
+
+    tb = MDPTables.from_golden(load_instance("riverswimcontinuous_ergo0"))
+    N, n_steps, seed = 48, 6000, 9
+    kw = dict(psi_weight=0.015, eta_weight=1e-9)
+    prm = pmk.parameters(tb, kw, n_steps + 1)
+    hist = {}
+
+    class Recording(al.PSRLContinuous):
+        def episode_end_update(self, idx):
+            ep = self.episode.cpu().numpy().copy()
+            super().episode_end_update(idx)
+            Q = self.Q[idx.long()].cpu().numpy()
+            for k, i in enumerate(idx.cpu().numpy()):
+                hist[(int(i), int(ep[i]))] = Q[k]
+
+    dev = Recording(seed, tb, n_steps + 1, n_loops=N, **kw)
+    tr_d = dev.steps(n_steps, trace=True).cpu().numpy()
+    assert dev.rounds > 20 and dev.vi_sweeps > 0
+
+    def planner(loops, idx):
+        for i in idx:
+            loops.Q[i] = hist[(int(i), int(loops.episode[i]))]
+
+    cpu = orc.PSRLCLoops(host_tables(tb), N, prm["psi"], seed=seed, planner=planner)
+    tr_c = cpu.steps(n_steps, trace=True)
+    assert np.array_equal(tr_d, tr_c)
+    for f, d, c in _psrlc_pairs(dev, cpu):
+        assert np.array_equal(d.cpu().numpy(), c), f
+    r = tr_d[..., 3].view(np.float32)
+    assert r[-n_steps // 4:].mean() > 0.5, r[-n_steps // 4:].mean()
+
+
+def test_psrl_continuous_device_loop_through_the_reference_class():
+    """where the reference package is staged: the device loops' trajectories through the UNMODIFIED PSRLContinuous -- its
+    episode ends, visit counts and posteriors must be the device's, bit for bit."""
+    from oracle.reference_import import reference_available
+
+    if not reference_available():
+        pytest.skip("the reference package is not staged (baseline/_ref)")
+    import colosseum_b200.agent_loop as al
+    from make_qlearning_golden import reference_models
+    from make_ucrl2_golden import mdp_spec
+
+    reference_models()
+    psrl = importlib.import_module("colosseum.agent.agents.infinite_horizon.posterior_sampling")
+    for name, inst, kw in pmk.CASES[:2]:
+        tb = MDPTables.from_golden(load_instance(inst))
+        N, n_steps, seed = 3, 1500, pmk.SEED
+        dev = al.PSRLContinuous(seed, tb, n_steps + 1, n_loops=N, **kw)
+        tr = dev.steps(n_steps, trace=True).cpu().numpy()
+        for i in (0, N - 1):
+            ag, ends = pmk.replay_reference(psrl, mdp_spec(tb), tr[:, i], dev._psi, n_steps + 1, kw, seed=seed)
+            assert int(dev.episode[i]) == len(ends) + 1, name  # + the plan of before_start_interacting
+            assert (ag.psi, ag.omega, ag.kappa, ag.eta) == (dev.psi, dev.omega, dev.kappa, dev.eta)
+            assert np.array_equal(dev.N[i].cpu().numpy(), ag.N), name
+            assert np.array_equal(dev.dir_hyper[i].cpu().numpy(), ag._mdp_model._transitions_model.hyper_params), name
+            k = ag._mdp_model._rewards_model.hyper_params.shape[-1]
+            assert np.array_equal(dev.nig_hyper[i, ..., :k].cpu().numpy(), ag._mdp_model._rewards_model.hyper_params), name

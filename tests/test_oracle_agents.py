@@ -101,3 +101,36 @@ def test_oracle_ucrl2_loops_match_reference_agent():
             assert np.array_equal(v, ref.astype(v.dtype)), (name, f)
         assert np.abs(loops.Q - gold[f"{name}.ref_Q"]).max() < 2e-3, name  # extended VI stops at eps = 1e-3
         assert len(ends[0]) > 100
+
+
+def test_oracle_psrl_continuous_loops_match_reference_agent():
+    """oracle.PSRLCLoops == the reference's PSRLContinuous class replayed on the committed trajectories
+    (tests/golden/make_psrlc_golden.py): same artificial-episode ends, bit-identical visit counts and posteriors, the
+    reference's own (psi, omega, kappa, eta), and the reference's own "simple sampling" rows of optimistic_sampling."""
+    import make_psrlc_golden as mk
+
+    gold = np.load(os.path.join(GOLDEN, "psrlc.npz"))
+    for name, inst, kw in mk.CASES:
+        tb = MDPTables.from_golden(load_instance(inst))
+        prm = mk.parameters(tb, kw)
+        assert np.array_equal(gold[f"{name}.ref_prm"][0], [prm["psi"], prm["omega"], prm["kappa"], prm["eta"]]), name
+        loops = orc.PSRLCLoops(host_tables(tb), mk.N_LOOPS, prm["psi"], seed=mk.SEED, planner=mk.make_planner(prm),
+                               **mk.loop_kwargs(kw))
+        trace = loops.steps(mk.N_STEPS, trace=True)
+        assert np.array_equal(trace, gold[f"{name}.trace"]), name
+        ends = gold[f"{name}.ref_ends"]
+        for i in range(mk.N_LOOPS):
+            assert loops.episode_ends[i] == [int(x) for x in ends[i] if x >= 0], (name, i)
+        k = gold[f"{name}.ref_nig"].shape[-1]
+        for f, v, ref in (("N", loops.Nsas, gold[f"{name}.ref_N"]), ("rew", loops.nig_hyper[..., :k], gold[f"{name}.ref_nig"]),
+                          ("dir", loops.dir_hyper, gold[f"{name}.ref_dir"])):
+            assert np.array_equal(v, ref.astype(v.dtype)), (name, f)
+        if f"{name}.ref_simple" in gold.files:
+            for i in range(mk.N_LOOPS):
+                cond = gold[f"{name}.ref_cond"][i]
+                assert cond.any()
+                ep = int(loops.episode[i])
+                for q in range(prm["psi"]):
+                    z = orc.psrlc_z(mk.SEED, i, ep, q, tb.S)
+                    ours = orc.psrlc_simple_rows(loops.Nsas[i], z)
+                    np.testing.assert_allclose(ours[cond], gold[f"{name}.ref_simple"][i, q][cond], atol=1e-7, rtol=0)
