@@ -252,6 +252,8 @@ PROTOTYPES = {
     "colo_extended_vi_batched_f64acc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _D, _D, _LL, _P, _P, _P, _P, _P, _P]),
     "colo_sample_dirichlet_rows": (_I, [_P, _LL, _I, _LL, _ULL, _ULL, _P, _P]),
     "colo_sample_dirichlet_rows_fast": (_I, [_P, _LL, _I, _LL, _ULL, _ULL, _P, _P]),
+    "colo_average_rewards_work_bytes": (C.c_size_t, [_I, _I]),
+    "colo_average_rewards_f64": (_I, [_P, _P, _P, _I, _I, _I, _D, _I, _P, _P, _P, _P, _P]),
     "colo_policy_chain": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "colo_stationary_distribution_work_bytes": (C.c_size_t, [_I]),
     "colo_stationary_distribution_f64": (_I, [_P, _I, _P, _D, _I, _P, _P, _P, _P]),

@@ -714,7 +714,9 @@ class BatchedMDPLoop:
         from . import dynamic_programming as dp
 
         ag, tb = self.agents, self.agents.tables
-        assert ag.episodic and self.T is not None
+        assert self.T is not None
+        if not ag.episodic:
+            return self._expected_regret_all_continuous(chunk)
         S, A, H = tb.S, tb.A, tb.H
         if not hasattr(self, "_dev_TR"):
             Td, Rd = dp.to_device(self.T), dp.to_device(self.R)
@@ -751,6 +753,56 @@ class BatchedMDPLoop:
         self._agent_average_reward = avg.cpu().numpy()  # agent_mdp_interaction.py:514-518
         return out.cpu().numpy()
 
+    def _greedy_q_continuous(self):
+        """the q-values whose greedy policy is `current_optimal_stochastic_policy` of every loop, f32 [N,S,A] on the
+        device: the agent's own table (Q-learning, q_learning.py:164-166), or the discounted value iteration on each
+        loop's empirical (ucrl2.py:77-80) / MAP (posterior_sampling.py:176-180) model, all loops in one batched solve"""
+        from . import dynamic_programming as dp
+
+        ag = self.agents
+        if isinstance(ag, UCRL2Continuous):
+            return dp.discounted_value_iteration(ag.P, ag.estimated_rewards, precision="f32")[0]
+        if isinstance(ag, PSRLContinuous):
+            T_map, R_map = ag.get_map_estimate()
+            return dp.discounted_value_iteration(T_map.contiguous(), R_map.contiguous(), precision="f32")[0]
+        return ag.Q
+
+    def _expected_regret_all_continuous(self, chunk: int = 4096):
+        """continuous: the expected per-step regret of EVERY loop's greedy policy (agent_mdp_interaction.py:567-578:
+        optimal average reward minus the policy's, zero when within 1e-3), all policies through one batched
+        stationary-distribution solve per chunk (markov_chain.get_average_reward_batched)."""
+        import torch
+
+        from . import dynamic_programming as dp
+        from . import markov_chain
+
+        ag, tb = self.agents, self.agents.tables
+        A = tb.A
+        if not hasattr(self, "_opt_ar"):
+            Q, _ = dp.discounted_value_iteration(self.T, self.R)
+            self._opt_ar = markov_chain.get_average_reward(self.T, self.R, dp.get_policy_from_q_values(Q, True))
+        if not hasattr(self, "_dev_TR_c"):
+            self._dev_TR_c = (dp.to_device(self.T), dp.to_device(self.R))
+        Td, Rd = self._dev_TR_c
+        Qall = self._greedy_q_continuous()
+        states = ag.state.cpu().numpy()
+        gen = torch.Generator(device="cuda").manual_seed(dp.ARGMAX_SEED)
+        out = np.empty(ag.n_loops)
+        avg = np.empty(ag.n_loops)
+        self._greedy_actions = torch.empty(Qall.shape[:2], dtype=torch.int64, device="cuda")  # the policies evaluated
+        for lo in range(0, ag.n_loops, chunk):
+            Qc = Qall[lo:lo + chunk]
+            tie = torch.rand(Qc.shape, generator=gen, device="cuda")
+            idx = torch.where(Qc == Qc.max(-1, keepdim=True).values, tie, torch.full_like(tie, -1.0)).argmax(-1)
+            self._greedy_actions[lo:lo + chunk] = idx
+            pi = torch.nn.functional.one_hot(idx, A).to(torch.float32).contiguous()
+            ar = markov_chain.get_average_reward_batched(Td, Rd, pi, states[lo:lo + chunk])
+            r = self._opt_ar - ar
+            out[lo:lo + len(ar)] = np.where(np.isclose(r, 0.0, atol=1e-3) | (r < 0), 0.0, r)
+            avg[lo:lo + len(ar)] = ar
+        self._agent_average_reward = avg
+        return out
+
     def episodic_baselines(self):
         """per-step average rewards of the optimal, worst and uniformly random policies of an episodic MDP
         (mdp/base_finite.py:211-253: start-distribution average of V[0] divided by H; the worst policy is the optimal one
@@ -777,18 +829,18 @@ class BatchedMDPLoop:
     def run(self, T: int, log_every: int = -1, regret_for=None):
         """T interaction steps for every loop, `log_every` steps per launch.  Returns the list of log records
         (steps, cumulative_reward f64[N], n_episodes i64[N], and -- for the loops listed in `regret_for`, when T/R were
-        given -- regret and cumulative_regret).  regret_for="all" (episodic agents): every loop, evaluated on the device
-        in one launch per tick."""
+        given -- regret and cumulative_regret).  regret_for="all": every loop, evaluated on the device in one batched
+        solve per tick (episodic: colo_episodic_policies_f32; continuous: colo_average_rewards_f64)."""
         ag = self.agents
         log_every = T if log_every in (0, -1, None) else int(log_every)
         all_loops = isinstance(regret_for, str) and regret_for == "all"
         if all_loops:
-            assert ag.episodic and self.T is not None, "regret_for='all' needs an episodic agent batch and T, R"
+            assert self.T is not None, "regret_for='all' needs T, R"
             regret_for = list(range(ag.n_loops))
         regret_for = [] if (regret_for is None or self.T is None) else list(regret_for)
         cum_regret = np.zeros(len(regret_for))
         cum_expected = np.zeros(len(regret_for))
-        base = self.episodic_baselines() if (all_loops or (regret_for and ag.episodic)) else None
+        base = self.episodic_baselines() if (ag.episodic and (all_loops or regret_for)) else None
         t_start = time.perf_counter()
         done = 0
         while done < T:
@@ -809,9 +861,9 @@ class BatchedMDPLoop:
                         rec[f"{k}_cumulative_expected_reward"] = base[k] * done
                     rec["random_cumulative_regret"] = (base["optimal"] - base["random"]) * done
                     rec["worst_cumulative_regret"] = span * done
-                    if all_loops:
-                        cum_expected = cum_expected + self._agent_average_reward * n
-                        rec["cumulative_expected_reward"] = cum_expected.copy()
+                if all_loops:
+                    cum_expected = cum_expected + self._agent_average_reward * n
+                    rec["cumulative_expected_reward"] = cum_expected.copy()
             rec["steps_per_second"] = done * ag.n_loops / (time.perf_counter() - t_start)
             self.logs.append(rec)
         return self.logs

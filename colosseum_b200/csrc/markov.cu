@@ -23,6 +23,10 @@ namespace colo {
 __global__ void __launch_bounds__(256) policy_chain_kernel(const float* __restrict__ T, const float* __restrict__ R,
                                                            const float* __restrict__ pi, int S, int A,
                                                            float* __restrict__ P, float* __restrict__ r) {
+  // blockIdx.y = policy of a batch evaluated on ONE MDP (T, R shared; pi, P, r per policy)
+  pi += (size_t)blockIdx.y * S * A;
+  P += (size_t)blockIdx.y * S * S;
+  if (r != nullptr) r += (size_t)blockIdx.y * S;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -59,7 +63,9 @@ __global__ void lazy_transpose_kernel(const float* __restrict__ P, int S, float*
 
 // ---- limiting matrix by repeated squaring (robust for nearly reducible chains, where power iteration stalls) ----
 __global__ void lazy_matrix_f64_kernel(const float* __restrict__ P, int S, double* __restrict__ L) {
-  // L = (I + P)/2 with rows rescaled to sum exactly (to rounding) 1; one warp per row
+  // L = (I + P)/2 with rows rescaled to sum exactly (to rounding) 1; one warp per row; blockIdx.y = chain of a batch
+  P += (size_t)blockIdx.y * S * S;
+  L += (size_t)blockIdx.y * S * S;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -74,8 +80,13 @@ __global__ void lazy_matrix_f64_kernel(const float* __restrict__ P, int S, doubl
 
 constexpr int kGemmTile = 64, kGemmBK = 16;
 
-__global__ void __launch_bounds__(256) dsquare_kernel(const double* __restrict__ A, int S, double* __restrict__ C) {
-  // C = A * A (row-major fp64, S x S): 64 x 64 tile per CTA, 4 x 4 per thread, k-major shared tiles
+__global__ void __launch_bounds__(256) dsquare_kernel(const double* __restrict__ A, int S, double* __restrict__ C,
+                                                      const int* __restrict__ frozen = nullptr) {
+  // C = A * A (row-major fp64, S x S): 64 x 64 tile per CTA, 4 x 4 per thread, k-major shared tiles;
+  // blockIdx.z = chain of a batch (frozen[z] != 0: that chain has converged, its buffers are left alone)
+  if (frozen != nullptr && frozen[blockIdx.z]) return;
+  A += (size_t)blockIdx.z * S * S;
+  C += (size_t)blockIdx.z * S * S;
   __shared__ __align__(16) double As[kGemmBK][kGemmTile + 2];
   __shared__ __align__(16) double Bs[kGemmBK][kGemmTile + 2];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -120,8 +131,13 @@ __global__ void __launch_bounds__(256) dsquare_kernel(const double* __restrict__
 }
 
 __global__ void row_normalize_diff_kernel(double* __restrict__ C, const double* __restrict__ Prev, int S,
-                                          unsigned long long* __restrict__ diff) {
-  // rows of C rescaled to unit sum (the powers stay stochastic); diff = max |C - Prev| after the rescale
+                                          unsigned long long* __restrict__ diff, const int* __restrict__ frozen = nullptr) {
+  // rows of C rescaled to unit sum (the powers stay stochastic); diff = max |C - Prev| after the rescale;
+  // blockIdx.y = chain of a batch
+  if (frozen != nullptr && frozen[blockIdx.y]) return;
+  C += (size_t)blockIdx.y * S * S;
+  Prev += (size_t)blockIdx.y * S * S;
+  diff += blockIdx.y;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -168,9 +184,126 @@ __global__ void unit_sum_kernel(double* __restrict__ x, int S) {
   for (int i = threadIdx.x; i < S; i += blockDim.x) x[i] /= tot;
 }
 
+// ---- a batch of policies on one MDP (the continuous regret tick of N agent loops) -------------------------------------
+// after every squaring: chains whose product moved by less than tol freeze (their limit stays in the buffer the
+// squaring wrote); `left` counts the chains still moving
+__global__ void chain_freeze_kernel(const unsigned long long* __restrict__ diff, int B, double tol, int k,
+                                    int* __restrict__ frozen, int* __restrict__ where, int* __restrict__ squarings,
+                                    int* __restrict__ left) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || frozen[b]) return;
+  const double d = __longlong_as_double((long long)diff[b]);
+  if (d < tol) {
+    frozen[b] = 1;
+    where[b] = (k + 1) & 1;  // the buffer squaring k wrote
+    squarings[b] = k + 1;
+  } else {
+    atomicAdd(left, 1);
+  }
+}
+
+// the average reward of a chain from its limiting matrix M = lim L^n: with ONE recurrent class every row of M is the
+// stationary distribution (markov_chain.py:12-31: (average_rewards * sd).sum()); rows that disagree mean several
+// classes, whose weights follow the reference's first-reachable-class rule -- flagged for the caller.  One CTA per chain.
+__global__ void __launch_bounds__(256) chain_average_reward_kernel(const double* __restrict__ M0, const double* __restrict__ M1,
+                                                                   const int* __restrict__ where, const float* __restrict__ r,
+                                                                   int S, double row_tol, double* __restrict__ ar,
+                                                                   int* __restrict__ multichain) {
+  __shared__ double s_val[8], s_dev[8];
+  const int b = blockIdx.x;
+  const double* M = (where[b] ? M1 : M0) + (size_t)b * S * S;
+  const float* rb = r + (size_t)b * S;
+  double val = 0.0, sum = 0.0, dev = 0.0;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) {
+    const double m0 = M[j];
+    val += m0 * (double)rb[j];
+    sum += m0;
+  }
+  for (size_t e = threadIdx.x; e < (size_t)S * S; e += blockDim.x) {
+    const double d = fabs(M[e] - M[e % S]);
+    dev = d > dev ? d : dev;
+  }
+  __shared__ double s_sum[8];
+  val = warp_sum(val);
+  sum = warp_sum(sum);
+  dev = warp_max(dev);
+  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = val; s_sum[threadIdx.x >> 5] = sum; s_dev[threadIdx.x >> 5] = dev; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0, t = 0.0, d = 0.0;
+    for (int w = 0; w < 8; ++w) { v += s_val[w]; t += s_sum[w]; d = s_dev[w] > d ? s_dev[w] : d; }
+    ar[b] = v / t;
+    multichain[b] = d > row_tol;
+  }
+}
+
 }  // namespace colo
 
 extern "C" {
+
+size_t colo_average_rewards_work_bytes(int B, int S) {
+  return (size_t)B * S * S * (4 + 8 + 8) + (size_t)B * S * 4 + (size_t)B * (8 + 4 * 3) + 1024;
+}
+
+int colo_average_rewards_f64(const float* T, const float* R, const float* pi, int B, int S, int A, double tol,
+                             int max_squarings, double* ar_out, int* multichain_out, int* squarings_out, void* work,
+                             void* stream) {
+  COLO_ARG_CHECK(T && R && pi && ar_out && multichain_out && work && B >= 0 && S > 0 && A > 0 && max_squarings > 0,
+                 "T, R, pi, ar_out, multichain_out, work, B, S, A");
+  if (B == 0) return COLO_OK;
+  COLO_ARG_CHECK(B <= 65535, "B <= 65535 per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = (char*)work;
+  double* M0 = (double*)w; w += (size_t)B * S * S * 8;
+  double* M1 = (double*)w; w += (size_t)B * S * S * 8;
+  unsigned long long* diff = (unsigned long long*)w; w += (size_t)B * 8;
+  float* P = (float*)w; w += (size_t)B * S * S * 4;
+  float* r = (float*)w; w += (size_t)B * S * 4;
+  int* frozen = (int*)w; w += (size_t)B * 4;
+  int* where = (int*)w; w += (size_t)B * 4;
+  int* squarings = (int*)w; w += (size_t)B * 4;
+  w = (char*)(((uintptr_t)w + 255) / 256 * 256);
+  int* left = (int*)w;
+  COLO_CUDA_TRY(cudaMemsetAsync(frozen, 0, (size_t)B * 12, st));
+  const long long wb = ((long long)S + 7) / 8;
+  const int wgrid = (int)(wb < 1024 ? wb : 1024);
+  colo::policy_chain_kernel<<<dim3(wgrid, B), 256, 0, st>>>(T, R, pi, S, A, P, r);
+  int rc = colo::check_launch("policy_chain_kernel");
+  if (rc != COLO_OK) return rc;
+  colo::lazy_matrix_f64_kernel<<<dim3(wgrid, B), 256, 0, st>>>(P, S, M0);
+  rc = colo::check_launch("lazy_matrix_f64_kernel");
+  if (rc != COLO_OK) return rc;
+  const int tiles = (S + colo::kGemmTile - 1) / colo::kGemmTile;
+  int status = COLO_MAX_ITER;
+  for (int k = 0; k < max_squarings; ++k) {
+    double* cur = (k & 1) ? M1 : M0;
+    double* nxt = (k & 1) ? M0 : M1;
+    COLO_CUDA_TRY(cudaMemsetAsync(diff, 0, (size_t)B * 8, st));
+    COLO_CUDA_TRY(cudaMemsetAsync(left, 0, sizeof(int), st));
+    colo::dsquare_kernel<<<dim3(tiles, tiles, B), 256, 0, st>>>(cur, S, nxt, frozen);
+    rc = colo::check_launch("dsquare_kernel");
+    if (rc != COLO_OK) return rc;
+    colo::row_normalize_diff_kernel<<<dim3(wgrid, B), 256, 0, st>>>(nxt, cur, S, diff, frozen);
+    rc = colo::check_launch("row_normalize_diff_kernel");
+    if (rc != COLO_OK) return rc;
+    colo::chain_freeze_kernel<<<(B + 127) / 128, 128, 0, st>>>(diff, B, tol, k, frozen, where, squarings, left);
+    rc = colo::check_launch("chain_freeze_kernel");
+    if (rc != COLO_OK) return rc;
+    if (k >= 8) {  // no chain of interest converges in fewer squarings; afterwards look every time
+      int h = 0;
+      COLO_CUDA_TRY(cudaMemcpyAsync(&h, left, sizeof(int), cudaMemcpyDeviceToHost, st));
+      COLO_CUDA_TRY(cudaStreamSynchronize(st));
+      if (h == 0) { status = COLO_OK; break; }
+    }
+  }
+  if (status != COLO_OK) return status;
+  colo::chain_average_reward_kernel<<<B, 256, 0, st>>>(M0, M1, where, r, S, 1e-9, ar_out, multichain_out);
+  rc = colo::check_launch("chain_average_reward_kernel");
+  if (rc != COLO_OK) return rc;
+  if (squarings_out) COLO_CUDA_TRY(cudaMemcpyAsync(squarings_out, squarings, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  return COLO_OK;
+}
+
 
 size_t colo_stationary_distribution_work_bytes(int S) { return (size_t)2 * S * S * sizeof(double) + 512; }
 

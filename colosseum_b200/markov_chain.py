@@ -132,3 +132,38 @@ def get_average_reward(T, R, policy, next_states_and_probs=None, sparse_threshol
     P, r = _chain(T, R, policy)
     sd = get_stationary_distribution(P, next_states_and_probs, tol=tol)
     return float((r.double() * sd).sum().item())
+
+
+def get_average_reward_batched(T, R, policies, start_states=None, *, tol=1e-13, max_squarings=200,
+                               max_work_bytes=8 << 30):
+    """markov_chain.py:12-31 for a batch of policies f32 [B,S,A] on one MDP: f64 [B] average rewards, one batched
+    repeated-squaring solve per chunk (colo_average_rewards_f64).  Policies whose chain has several recurrent classes
+    (the rows of the limiting matrix disagree) go through `get_average_reward` one by one with the reference's
+    first-reachable-class rule, which needs `start_states` (i [B]: where each policy's loop currently is)."""
+    torch = _torch()
+    Td, Rd = to_device(T), to_device(R)
+    pid = to_device(policies)
+    B, S, A = pid.shape
+    lib = _cabi.lib()
+    chunk = max(1, min(65535, int(max_work_bytes // max(1, lib.colo_average_rewards_work_bytes(1, S)))))
+    ar = torch.empty(B, dtype=torch.float64, device="cuda")
+    multi = torch.empty(B, dtype=torch.int32, device="cuda")
+    for lo in range(0, B, chunk):
+        n = min(chunk, B - lo)
+        work = _scratch(lib.colo_average_rewards_work_bytes(n, S))
+        rc = lib.colo_average_rewards_f64(_cabi.ptr(Td), _cabi.ptr(Rd), _cabi.ptr(pid[lo:lo + n]), n, S, A, float(tol),
+                                          int(max_squarings), _cabi.ptr(ar[lo:lo + n]), _cabi.ptr(multi[lo:lo + n]), None,
+                                          _cabi.ptr(work), _cabi.current_stream())
+        _cabi.check(rc, "colo_average_rewards_f64")
+        if rc == _cabi.MAX_ITER:
+            raise DynamicProgrammingMaxIterationExceeded()
+    out = ar.cpu().numpy()
+    flagged = np.nonzero(multi.cpu().numpy())[0]
+    get_average_reward_batched.last_multichain = len(flagged)
+    for b in flagged:
+        start = None if start_states is None else [(int(start_states[b]), 1.0)]
+        out[b] = get_average_reward(Td, Rd, pid[b], start, tol=tol)
+    return out
+
+
+get_average_reward_batched.last_multichain = 0

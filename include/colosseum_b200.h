@@ -363,6 +363,21 @@ int colo_sample_dirichlet_rows_fast(const float* hyper, long long rows, int S, l
 int colo_policy_chain(const float* T, const float* R, const float* pi, int S, int A, float* P_out, float* r_out,
                       void* stream);
 /*
+ * colo_average_rewards_f64 -- get_average_reward (colosseum/mdp/utils/markov_chain.py:12-31) for a BATCH of B policies on
+ * one MDP: the continuous-MDP regret tick of N agent loops (experiment/agent_mdp_interaction.py:518-578) in a handful of
+ * launches.  T f32[S,A,S], R f32[S,A] shared; pi f32[B,S,A].  Per policy: the chain P = min(1, sum_a T pi), its lazy
+ * version (I + P)/2 squared repeatedly in fp64 (batched 64x64-tile GEMM; a chain freezes once a squaring moves it by
+ * less than tol), and ar_out[b] = row 0 of the limit . r.  multichain_out[b] = 1 when the rows of the limit disagree
+ * (several recurrent classes): the reference then weighs the classes by its first-reachable-class rule (:113-126), which
+ * the caller resolves per policy (colo_stationary_distribution_f64 with the rule's start vector).  squarings_out i32[B]
+ * (device, may be NULL).  Synchronises.  Returns COLO_MAX_ITER if a chain is still moving after max_squarings.
+ * work: colo_average_rewards_work_bytes(B, S) device bytes.  B <= 65535.
+ */
+size_t colo_average_rewards_work_bytes(int B, int S);
+int colo_average_rewards_f64(const float* T, const float* R, const float* pi, int B, int S, int A, double tol,
+                             int max_squarings, double* ar_out, int* multichain_out, int* squarings_out, void* work,
+                             void* stream);
+/*
  * colo_stationary_distribution_f64 -- get_stationary_distribution (markov_chain.py:64-137): x_out = x0 * lim L^(2^k),
  * L = (I + P)/2, by repeated squaring in fp64 (rows rescaled to unit sum after every product) until max|L^(2^(k+1)) -
  * L^(2^k)| < tol or max_squarings products.  Exact limit of the start distribution x0 for every chain: with one

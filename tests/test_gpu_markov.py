@@ -135,3 +135,69 @@ def test_multichain_policies_follow_the_reference_rule():
         np.testing.assert_allclose(sd, g[f"{name}_sd"], atol=2e-6, err_msg=str(name))
     with pytest.raises(TypeError):  # the reference needs the start distribution for a multichain policy
         mc.get_stationary_distribution(g["two_classes_tps"], None)
+
+
+def test_batched_average_rewards(g):
+    """colo_average_rewards_f64: the reference's optimal / worst / random policies of every fixture MDP plus 61 random
+    deterministic policies, all in ONE batched solve, against the reference's recorded average rewards and the
+    one-policy-at-a-time path; a multichain policy is flagged and resolved by the reference's class rule."""
+    import colosseum_b200.markov_chain as mc
+
+    rng = np.random.RandomState(0)
+    for name in g["names"]:
+        T, R = g[f"{name}_T"], g[f"{name}_R"]
+        S, A = R.shape
+        pis = [g[f"{name}_{k}_pi"] for k in ("opt", "worst", "rand")]
+        pis += [np.eye(A, dtype=np.float32)[rng.randint(A, size=S)] for _ in range(61)]
+        pis = np.stack(pis).astype(np.float32)
+        start = int(g[f"{name}_start_idx"][0])
+        ar = mc.get_average_reward_batched(T, R, pis, np.full(len(pis), start))
+        for b, k in enumerate(("opt", "worst", "rand")):
+            assert abs(ar[b] - float(g[f"{name}_{k}_ar"])) < 2e-6 * max(1.0, abs(ar[b])), (name, k)
+        for b in range(3, len(pis), 7):
+            one = mc.get_average_reward(T, R, pis[b], [(start, 1.0)])
+            assert abs(ar[b] - one) < 1e-9, (name, b)
+    # a policy with two closed classes: state 0 stays (reward 0), state 2 stays (reward 1), state 1 moves to 0
+    T = np.zeros((3, 2, 3), np.float32)
+    T[0, :, 0] = 1
+    T[2, :, 2] = 1
+    T[1, 0, 0] = 1
+    T[1, 1, 2] = 1
+    R = np.zeros((3, 2), np.float32)
+    R[2] = 1
+    pis = np.stack([np.eye(2, dtype=np.float32)[[0, 0, 0]], np.eye(2, dtype=np.float32)[[0, 1, 0]]])
+    ar = mc.get_average_reward_batched(T, R, pis, np.array([1, 1]))
+    assert mc.get_average_reward_batched.last_multichain == 2
+    assert abs(ar[0] - 0.0) < 1e-12 and abs(ar[1] - 1.0) < 1e-12  # from state 1: into class {0} / into class {2}
+    assert abs(mc.get_average_reward_batched(T, R, pis, np.array([2, 0]))[0] - 1.0) < 1e-12
+
+
+def test_continuous_regret_of_every_loop():
+    """BatchedMDPLoop.run(regret_for="all") on a continuous MDP: every loop's greedy policy through the batched
+    stationary-distribution solve == the per-loop indicator, for the three continuous agents."""
+    import colosseum_b200.agent_loop as al
+    from colosseum_b200.tables import MDPTables
+
+    gi = load_instance("riverswimcontinuous_ergo0")
+    tb = MDPTables.from_golden(gi)
+    T, R = np.asarray(gi["T"], np.float32), np.asarray(gi["R"], np.float32)
+    for make in (lambda: al.QLearningContinuous(3, tb, 4000, n_loops=40),
+                 lambda: al.UCRL2Continuous(3, tb, 4001, alpha_r=0.1, alpha_p=0.05, n_loops=40),
+                 lambda: al.PSRLContinuous(3, tb, 4001, psi_weight=0.015, eta_weight=1e-9, n_loops=40)):
+        ag = make()
+        loop = al.BatchedMDPLoop(ag, T, R)
+        logs = loop.run(4000, log_every=2000, regret_for="all")
+        assert len(logs) == 2 and logs[-1]["regret"].shape == (40,)
+        import colosseum_b200.dynamic_programming as dp
+        import colosseum_b200.markov_chain as mc
+
+        Qo, _ = dp.discounted_value_iteration(T, R)
+        opt = mc.get_average_reward(T, R, dp.get_policy_from_q_values(Qo, True))
+        acts, states = loop._greedy_actions.cpu().numpy(), ag.state.cpu().numpy()
+        for i in (0, 7, 39):  # the same policy through the one-policy-at-a-time indicator
+            ar = mc.get_average_reward(T, R, np.eye(tb.A, dtype=np.float32)[acts[i]], [(int(states[i]), 1.0)])
+            r = opt - ar
+            want = 0.0 if (np.isclose(r, 0.0, atol=1e-3) or r < 0) else r
+            assert abs(logs[-1]["regret"][i] - want) < 2e-6, i
+        assert (logs[-1]["regret"] >= 0).all() and (logs[-1]["cumulative_regret"] >= logs[0]["cumulative_regret"]).all()
+        assert np.isfinite(logs[-1]["cumulative_expected_reward"]).all()
