@@ -88,6 +88,13 @@ class EnvServer(C.Structure):
                 ("share", C.c_int), ("idle_timeout_ms", C.c_uint)]
 
 
+class ActorArgs(C.Structure):
+    """mirror of `colo_actor_args`"""
+
+    _fields_ = [("epsilon_schedule", C.c_void_p), ("temperature_schedule", C.c_void_p), ("t0", C.c_longlong),
+                ("len", C.c_int), ("boltzmann", C.c_int), ("boltzmann_temperature", C.c_double)]
+
+
 class QLearningArgs(C.Structure):
     """mirror of `colo_qlearning_args`"""
 
@@ -99,7 +106,7 @@ class QLearningArgs(C.Structure):
         ("c_1", C.c_double), ("c_2", C.c_double), ("min_at", C.c_double), ("log_term", C.c_double),
         ("sqrt_h7sa", C.c_double), ("H_eff", C.c_double), ("gamma", C.c_double), ("span_approx", C.c_double),
         ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p), ("n_episodes", C.c_void_p),
-        ("trace", C.c_void_p),
+        ("trace", C.c_void_p), ("actor", ActorArgs),
     ]
 
 
@@ -110,7 +117,7 @@ class PsrlArgs(C.Structure):
         ("N", C.c_longlong), ("seed", C.c_ulonglong), ("env0", C.c_ulonglong),
         ("state", C.c_void_p), ("h", C.c_void_p), ("Q", C.c_void_p), ("dir_hyper", C.c_void_p),
         ("nig_hyper", C.c_void_p), ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p),
-        ("n_episodes", C.c_void_p), ("trace", C.c_void_p), ("reward_model", C.c_int),
+        ("n_episodes", C.c_void_p), ("trace", C.c_void_p), ("reward_model", C.c_int), ("actor", ActorArgs),
     ]
 
 
@@ -124,7 +131,7 @@ class Ucrl2Args(C.Structure):
         ("hold", C.c_void_p), ("nu", C.c_void_p), ("seen", C.c_void_p), ("ep_len", C.c_void_p), ("ep_log", C.c_void_p),
         ("log_cap", C.c_int), ("ended", C.c_void_p), ("iteration", C.c_void_p), ("episode", C.c_void_p),
         ("delta", C.c_void_p), ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong),
-        ("trace_steps", C.c_int),
+        ("trace_steps", C.c_int), ("actor", ActorArgs),
     ]
 
 
@@ -137,6 +144,7 @@ class PsrlcArgs(C.Structure):
         ("dir_hyper", C.c_void_p), ("nig_hyper", C.c_void_p), ("reward_model", C.c_int),
         ("Nsas", C.c_void_p), ("Nsa", C.c_void_p), ("nu", C.c_void_p), ("ended", C.c_void_p), ("episode", C.c_void_p),
         ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong), ("trace_steps", C.c_int),
+        ("actor", ActorArgs),
     ]
 
 

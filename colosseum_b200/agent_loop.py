@@ -11,7 +11,8 @@ body execute per launch.  Classes keep the reference's names and constructor arg
                         regret of each loop's greedy policy (experiment/indicators.py:29-45 / markov_chain.py:12-31)
 
 `mdp_specs` is replaced by the `MDPTables` of the MDP (the kernel needs the sampler tables, not only the sizes).
-Boltzmann exploration and callable epsilon schedules are not offered on the device.
+`epsilon_greedy` and `boltzmann_temperature` are constants or, as in the reference, functions of the actor's interaction
+counter (tabulated per launch, `_set_actor`).
 """
 import ctypes as C
 import time
@@ -29,6 +30,33 @@ def get_H(n_states, n_actions, T, span_approx, confidence):
                (T / n_states / n_actions / np.log(4 * T / confidence)) ** 0.333)
 
 
+def _set_actor(agents, t0, n):
+    """QValuesActor's exploration for the interaction counts t0 .. t0 + n - 1 (Q_values_actor.py:20-82) into the
+    argument struct of `agents`: constants as they are; functions of the actor's interaction counter -- the only form the
+    reference itself can run, its float branch wraps the number into a lambda that returns itself (:44-49) -- are
+    tabulated on the host and uploaded (f64 [n])."""
+    import torch
+
+    args, a = agents._args, agents._args.actor
+    eps, temp = agents._explore
+    a.t0, a.len = int(t0), int(n)
+    a.epsilon_schedule = a.temperature_schedule = None
+    args.epsilon_greedy = -1.0
+    agents._schedules = keep = {}
+    if callable(eps):
+        keep["eps"] = torch.tensor([float(eps(t0 + k)) for k in range(n)], dtype=torch.float64).cuda()
+        a.epsilon_schedule = keep["eps"].data_ptr()
+        args.epsilon_greedy = 0.0
+    elif eps is not None:
+        args.epsilon_greedy = float(eps)
+    a.boltzmann = int(temp is not None)
+    if callable(temp):
+        keep["temp"] = torch.tensor([float(temp(t0 + k)) for k in range(n)], dtype=torch.float64).cuda()
+        a.temperature_schedule = keep["temp"].data_ptr()
+    elif temp is not None:
+        a.boltzmann_temperature = float(temp)
+
+
 class _QLearningBatch:
     episodic = None
 
@@ -36,10 +64,7 @@ class _QLearningBatch:
         import torch
 
         _cabi.require_cuda()
-        if boltzmann_temperature is not None:
-            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
-        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
-            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        self._explore = (epsilon_greedy, boltzmann_temperature)
         assert (tables.H > 0) == self.episodic, "episodic agents need an episodic MDP and vice versa"
         self.torch = torch
         self.tables = tables
@@ -56,7 +81,6 @@ class _QLearningBatch:
         a.N, a.seed, a.env0 = N, self.seed, self.env_offset
         a.state, a.h = self.state.data_ptr(), self.h.data_ptr()
         a.cum_reward, a.n_episodes = self.cumulative_reward.data_ptr(), self.n_episodes.data_ptr()
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         self._args = a
         self._fn = (_cabi.lib().colo_qlearning_episodic_steps if self.episodic
                     else _cabi.lib().colo_qlearning_continuous_steps)
@@ -87,6 +111,7 @@ class _QLearningBatch:
         torch = self.torch
         tr = torch.empty((n_steps, self.n_loops, 4), dtype=torch.int32, device="cuda") if trace else None
         self._args.trace = None if tr is None else tr.data_ptr()
+        _set_actor(self, self.t, n_steps)
         rc = self._fn(C.byref(self.dev.c), C.byref(self._args), int(n_steps), self.t, _cabi.current_stream())
         _cabi.check(rc, "colo_qlearning_steps")
         self.t += int(n_steps)
@@ -181,10 +206,7 @@ class PSRLEpisodic:
         assert rname in (None, "N_NIG", "N_N") and tname in (None, "M_DIR"), \
             "the batched PSRL offers the N_NIG / N_N reward models and the M_DIR transition model"
         self.reward_model = 1 if rname == "N_N" else 0
-        if boltzmann_temperature is not None:
-            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
-        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
-            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        self._explore = (epsilon_greedy, boltzmann_temperature)
         assert tables.H > 0, "PSRLEpisodic needs an episodic MDP"
         self.torch, self.tables = torch, tables
         self.dev = DeviceTables(tables, "succ")
@@ -217,7 +239,6 @@ class PSRLEpisodic:
         a.state, a.h, a.Q = self.state.data_ptr(), self.h.data_ptr(), self.Q.data_ptr()
         a.dir_hyper, a.nig_hyper = self.dir_hyper.data_ptr(), self.nig_hyper.data_ptr()
         a.cum_reward, a.n_episodes = self.cumulative_reward.data_ptr(), self.n_episodes.data_ptr()
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         a.reward_model = self.reward_model
         self._args = a
         _QLearningBatch.reset_envs(self)
@@ -254,6 +275,7 @@ class PSRLEpisodic:
         while done < n_steps:
             n = min(H - self._h_episode, n_steps - done)
             self._args.trace = None if tr is None else tr[done:].data_ptr()
+            _set_actor(self, self.t, n)
             rc = _cabi.lib().colo_psrl_episodic_steps(C.byref(self.dev.c), C.byref(self._args), n, self.t,
                                                       _cabi.current_stream())
             _cabi.check(rc, "colo_psrl_episodic_steps")
@@ -300,10 +322,7 @@ class UCRL2Continuous:
         if bound_type_rew == "bernstein":
             raise NotImplementedError("bound_type_rew='bernstein' raises AttributeError in the reference (self.r_max, "
                                       "ucrl2.py:268); only '_chernoff' is defined")
-        if boltzmann_temperature is not None:
-            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
-        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
-            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        self._explore = (epsilon_greedy, boltzmann_temperature)
         assert tables.H == 0, "UCRL2Continuous needs a continuous MDP"
         self.torch, self.tables = torch, tables
         self.dev = DeviceTables(tables, "succ")
@@ -354,7 +373,6 @@ class UCRL2Continuous:
         a.log_cap = self.log_cap
         a.ended, a.iteration, a.episode, a.delta = (self.ended.data_ptr(), self.iteration.data_ptr(),
                                                     self.episode.data_ptr(), self.delta.data_ptr())
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         self._args = a
         self.episode_end_update(torch.arange(N, dtype=torch.int32, device=dev), update_model=False)  # :194-195
 
@@ -414,6 +432,7 @@ class UCRL2Continuous:
         a = self._args
         a.trace, a.trace_t0, a.trace_steps = (None if tr is None else tr.data_ptr()), self.t, int(n_steps)
         target = self.t + int(n_steps)
+        _set_actor(self, self.t, n_steps)
         self.rounds = 0
         while True:
             rc = _cabi.lib().colo_ucrl2_steps(C.byref(self.dev.c), C.byref(a), target, _cabi.current_stream())
@@ -489,10 +508,7 @@ class PSRLContinuous:
         rname = getattr(reward_prior_model, "name", reward_prior_model)
         tname = getattr(transitions_prior_model, "name", transitions_prior_model)
         assert rname in (None, "N_NIG", "N_N") and tname in (None, "M_DIR")
-        if boltzmann_temperature is not None:
-            raise NotImplementedError("Boltzmann exploration is not offered by the batched agents")
-        if epsilon_greedy is not None and not isinstance(epsilon_greedy, (int, float)):
-            raise NotImplementedError("epsilon_greedy must be a constant for the batched agents")
+        self._explore = (epsilon_greedy, boltzmann_temperature)
         if min_steps_before_new_episode != 0:
             raise NotImplementedError("min_steps_before_new_episode > 0 is not offered by the batched agent")
         assert tables.H == 0, "PSRLContinuous needs a continuous MDP"
@@ -550,7 +566,6 @@ class PSRLContinuous:
         a.dir_hyper, a.nig_hyper = self.dir_hyper.data_ptr(), self.nig_hyper.data_ptr()
         a.Nsas, a.Nsa, a.nu = self.N.data_ptr(), self.Nsa.data_ptr(), self.nu.data_ptr()
         a.ended, a.episode = self.ended.data_ptr(), self.episode.data_ptr()
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         self._args = a
         # before_start_interacting (:378-382): the random q-values it sets are replaced by the first plan at once
         self.episode_end_update(torch.arange(N, dtype=torch.int32, device=dev))
@@ -596,6 +611,7 @@ class PSRLContinuous:
         a = self._args
         a.trace, a.trace_t0, a.trace_steps = (None if tr is None else tr.data_ptr()), self.t, int(n_steps)
         target = self.t + int(n_steps)
+        _set_actor(self, self.t, n_steps)
         self.rounds = 0
         while True:
             rc = _cabi.lib().colo_psrlc_steps(C.byref(self.dev.c), C.byref(a), target, _cabi.current_stream())

@@ -72,4 +72,53 @@ __device__ __forceinline__ int select_action(const float* __restrict__ q, int A,
   return A - 1;
 }
 
+constexpr unsigned long long kBoltzmannKey = 0x94D049BB133111EBULL;  // the Boltzmann draw's Philox key = seed ^ this
+
+// the exploration parameters at the actor's interaction count `total` (colo_actor_args: schedule tables or constants)
+__device__ __forceinline__ double actor_epsilon(const colo_actor_args& ac, double eps_const, long long total) {
+  if (ac.epsilon_schedule == nullptr) return eps_const;
+  long long k = total - ac.t0;
+  k = k < 0 ? 0 : (k >= ac.len ? ac.len - 1 : k);
+  return __ldg(ac.epsilon_schedule + k);
+}
+__device__ __forceinline__ double actor_temperature(const colo_actor_args& ac, long long total) {
+  if (ac.temperature_schedule == nullptr) return ac.boltzmann_temperature;
+  long long k = total - ac.t0;
+  k = k < 0 ? 0 : (k >= ac.len ? ac.len - 1 : k);
+  return __ldg(ac.temperature_schedule + k);
+}
+
+// Boltzmann exploration (Q_values_actor.py:73-78): q = exp(temperature * q) in float32, p = q / q.sum() in float32,
+// numpy's choice(p): cdf = cumsum(p) in float64, normalised by its last entry, index = #(cdf <= u)
+__device__ __forceinline__ float boltz_weight(float temp, float q) {
+  return (float)exp((double)__fmul_rn(temp, q));
+}
+__device__ __forceinline__ int boltzmann_action(const float* __restrict__ q, int A, double temperature, double u) {
+  const float temp = (float)temperature;
+  float sum = 0.f;
+  for (int a = 0; a < A; ++a) sum = __fadd_rn(sum, boltz_weight(temp, q[a]));
+  double tot = 0.0;
+  for (int a = 0; a < A; ++a) tot = __dadd_rn(tot, (double)__fdiv_rn(boltz_weight(temp, q[a]), sum));
+  double run = 0.0;
+  int idx = 0;
+  for (int a = 0; a < A; ++a) {
+    run = __dadd_rn(run, (double)__fdiv_rn(boltz_weight(temp, q[a]), sum));
+    idx += (__ddiv_rn(run, tot) <= u) ? 1 : 0;
+  }
+  return idx < A ? idx : A - 1;
+}
+
+// QValuesActor.select_action with the full exploration set; A_random = the range of the epsilon-greedy draw
+__device__ __forceinline__ int actor_select(const float* __restrict__ q, int A, int A_random, double eps_const,
+                                            const colo_actor_args& ac, long long total, const Philox4& w,
+                                            unsigned long long seed, unsigned long long loop) {
+  const double eps = actor_epsilon(ac, eps_const, total);
+  if (eps >= 0.0 && (double)u24(w.w[0]) < eps) return act_from_word(w.w[1], A_random);
+  if (ac.boltzmann) {
+    const Philox4 wb = philox4x32_10(seed ^ kBoltzmannKey, loop, (uint64_t)total);
+    return boltzmann_action(q, A, actor_temperature(ac, total), u53(wb.w[0], wb.w[1]));
+  }
+  return select_action(q, A, -1.0, w);
+}
+
 }  // namespace colo

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128) qlearning_steps_kernel(const colo_mdp_tab
     const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, t);
     const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, t);
     const size_t row = ((size_t)(EPISODIC ? h : 0) * S + s) * A;
-    const int a = select_action(Q + row, A, p.epsilon_greedy, wa);
+    const int a = actor_select(Q + row, A, A, p.epsilon_greedy, p.actor, (long long)t, wa, p.seed, p.env0 + (uint64_t)i);
     const size_t idx = row + a;
     // every table entry the update needs is requested as soon as its address is known, and consumed only after the
     // sampler's own (dependent) table walk: the loop body is a chain of cold gathers, the fewer in series the better
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(128) psrl_steps_kernel(const colo_mdp_tables t
     const unsigned long long t = t0 + step;
     const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, t);
     const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, t);
-    const int a = select_action(Q + ((size_t)h * S + s) * A, A, p.epsilon_greedy, wa);
+    const int a = actor_select(Q + ((size_t)h * S + s) * A, A, A, p.epsilon_greedy, p.actor, (long long)t, wa, p.seed,
+                               p.env0 + (uint64_t)i);
     float* hp = nig + ((size_t)s * A + a) * 4;
     const float4 hp0 = *reinterpret_cast<const float4*>(hp);  // requested before the sampler's dependent table walk
     const Step st = env_succ(tb, s, a, u53(we.w[0], we.w[1]));

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) ucrl2_steps_kernel(const colo_mdp_tables 
     }
     const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, (uint64_t)t);
     const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, (uint64_t)t);
-    const int a = select_action(Q + (size_t)s * A, A, p.epsilon_greedy, wa);
+    const int a = actor_select(Q + (size_t)s * A, A, A, p.epsilon_greedy, p.actor, t, wa, p.seed, p.env0 + (uint64_t)i);
     const size_t sa = (size_t)s * A + a;
     const int n_sa = Nsa[sa] + 1, nu_k = nu[sa] + 1;
     const Step st = env_succ(tb, s, a, u53(we.w[0], we.w[1]));
@@ -230,11 +230,7 @@ __global__ void __launch_bounds__(128) psrlc_steps_kernel(const colo_mdp_tables 
   while (t < t_target) {
     const Philox4 we = philox4x32_10(p.seed, p.env0 + (uint64_t)i, (uint64_t)t);
     const Philox4 wa = philox4x32_10(p.seed ^ kAgentKey, p.env0 + (uint64_t)i, (uint64_t)t);
-    int a_ext;
-    if (p.epsilon_greedy >= 0.0 && (double)u24(wa.w[0]) < p.epsilon_greedy)
-      a_ext = act_from_word(wa.w[1], A);
-    else
-      a_ext = select_action(Q + (size_t)s * AE, AE, -1.0, wa);
+    const int a_ext = actor_select(Q + (size_t)s * AE, AE, A, p.epsilon_greedy, p.actor, t, wa, p.seed, p.env0 + (uint64_t)i);
     const int a = a_ext / psi;
     const size_t sa = (size_t)s * A + a;
     float* hp = nig + sa * 4;

@@ -619,6 +619,27 @@ int colo_env_server_wait(const colo_env_server* srv, unsigned long long step_ind
 int colo_env_server_stop(const colo_env_server* srv, void* stream);
 
 /*
+ * The actor's exploration (QValuesActor, colosseum/agent/actors/Q_values_actor.py:20-82), shared by every agent-loop entry
+ * point below as the LAST field of its argument struct.  The reference takes `epsilon_greedy` and `boltzmann_temperature`
+ * as functions of the actor's interaction counter (its float forms are wrapped into a lambda that returns itself, :44-49,
+ * and cannot be called); here a CONSTANT goes into the struct's `epsilon_greedy` / `boltzmann_temperature`, a FUNCTION is
+ * tabulated by the caller for the interaction counts a launch covers: schedule[k] = f(t0 + k), k < len (device f64; the
+ * counter of a step is the loop's time t, 1 at its first action).
+ * Order as in select_action (:58-82): with probability epsilon a uniformly random action; else, boltzmann != 0: an action
+ * drawn from softmax(temperature * q) -- exp in float32, p = e / e.sum() in float32, then numpy's choice: the first index
+ * whose normalised float64 running sum exceeds a uniform (draw keyed seed ^ 0x94D049BB133111EB); else greedy with uniform
+ * tie-breaking.  All zero / NULL = the constant-epsilon greedy actor.
+ */
+typedef struct {
+  const double* epsilon_schedule;
+  const double* temperature_schedule;
+  long long t0;
+  int len;
+  int boltzmann;
+  double boltzmann_temperature;
+} colo_actor_args;
+
+/*
  * Batched agent/MDP interaction loops: N independent (Q-learning agent, env) pairs on one
  * MDP, one thread per loop, n_steps iterations of MDPLoop.run's body (experiment/agent_mdp_interaction.py:238-298)
  * per launch: QValuesActor.select_action (agent/actors/Q_values_actor.py:58-82; epsilon-greedy or uniform among the
@@ -655,6 +676,7 @@ typedef struct {
   double* cum_reward;    /* f64[N], accumulated across calls */
   long long* n_episodes; /* i64[N] or NULL */
   int* trace;
+  colo_actor_args actor;
 } colo_qlearning_args;
 int colo_qlearning_episodic_steps(const colo_mdp_tables* tb, const colo_qlearning_args* a, int n_steps,
                                   unsigned long long t0, void* stream);
@@ -683,6 +705,7 @@ typedef struct {
   long long* n_episodes;
   int* trace;
   int reward_model; /* 0 = N_NIG (mu, lambda, alpha, beta); 1 = N_N (mu, tau, -, -): N_N.update_sa, conjugate_rewards.py:112-117 */
+  colo_actor_args actor;
 } colo_psrl_args;
 int colo_psrl_episodic_steps(const colo_mdp_tables* tb, const colo_psrl_args* a, int n_steps, unsigned long long t0,
                              void* stream);
@@ -733,6 +756,7 @@ typedef struct {
   int* trace;
   long long trace_t0;
   int trace_steps;
+  colo_actor_args actor;
 } colo_ucrl2_args;
 int colo_ucrl2_steps(const colo_mdp_tables* tb, const colo_ucrl2_args* a, long long t_target, void* stream);
 int colo_ucrl2_bounds(const colo_ucrl2_args* a, int S, int A, const int* index, int m, double alpha_r, double alpha_p,
@@ -777,6 +801,7 @@ typedef struct {
   int* trace;
   long long trace_t0;
   int trace_steps;
+  colo_actor_args actor;
 } colo_psrlc_args;
 int colo_psrlc_steps(const colo_mdp_tables* tb, const colo_psrlc_args* a, long long t_target, void* stream);
 int colo_psrlc_sample_models(const colo_psrlc_args* a, int S, int A, const int* index, int m, double eta, int truncate,

@@ -761,6 +761,17 @@ int orc_extended_vi_f32(const float* T, const float* est, const double* beta_r, 
  * Philox (env key = seed, agent key = seed ^ 0x9E3779B97F4A7C15) because numpy's RandomState stream cannot be
  * reproduced on a GPU; the update rule itself is pinned against the reference's model classes replayed on this
  * function's trace (tests/golden/make_qlearning_golden.py). */
+/* QValuesActor's exploration (colosseum/agent/actors/Q_values_actor.py:20-82): constant or tabulated epsilon and Boltzmann
+ * temperature as functions of the actor's interaction counter; see orc_actor_select below. */
+typedef struct {
+  const double* epsilon_schedule;
+  const double* temperature_schedule;
+  long long t0;
+  int len;
+  int boltzmann;
+  double boltzmann_temperature;
+} orc_actor_args;
+
 typedef struct {
   long long N;
   uint64_t seed, env0;
@@ -780,6 +791,7 @@ typedef struct {
   double* cum_reward;
   long long* n_episodes;
   int* trace;
+  orc_actor_args actor;
 } orc_qlearning_args;
 
 static int orc_select_action(const float* q, int A, double eps, const uint32_t w[4]) {
@@ -793,6 +805,55 @@ static int orc_select_action(const float* q, int A, double eps, const uint32_t w
   for (int a = 0; a < A; ++a)
     if (q[a] == best && k-- == 0) return a;
   return A - 1;
+}
+
+static double orc_actor_value(const double* schedule, long long t0, int len, double constant, long long total) {
+  if (!schedule) return constant;
+  long long k = total - t0;
+  k = k < 0 ? 0 : (k >= len ? len - 1 : k);
+  return schedule[k];
+}
+
+/* Boltzmann exploration (Q_values_actor.py:73-78): q = np.exp(temperature * q) (float32: a python float times a float32
+ * array), p = q / q.sum() (float32), rng.choice(range(A), p=p): numpy takes cdf = p.cumsum() in float64, cdf /= cdf[-1]
+ * and returns cdf.searchsorted(u, side="right").  exp is evaluated in double and rounded (one rounding, like a correctly
+ * rounded float32 exp). */
+static float orc_boltz_weight(float temp, float q) {
+  const float x = temp * q;
+  return (float)exp((double)x);
+}
+int orc_boltzmann_action(const float* q, int A, double temperature, double u) {
+  const float temp = (float)temperature;
+  float sum = 0.f;
+  for (int a = 0; a < A; ++a) sum = sum + orc_boltz_weight(temp, q[a]);
+  double tot = 0.0;
+  for (int a = 0; a < A; ++a) {
+    const float pa = orc_boltz_weight(temp, q[a]) / sum;
+    tot += (double)pa;
+  }
+  double run = 0.0;
+  int idx = 0;
+  for (int a = 0; a < A; ++a) {
+    const float pa = orc_boltz_weight(temp, q[a]) / sum;
+    run += (double)pa;
+    idx += (run / tot <= u) ? 1 : 0;
+  }
+  return idx < A ? idx : A - 1;
+}
+
+/* QValuesActor.select_action (:58-82) at interaction count `total`: epsilon-greedy draw from range(A_random), else
+ * Boltzmann (if enabled), else greedy with uniform tie-breaking */
+static int orc_actor_select(const float* q, int A, int A_random, double eps_const, const orc_actor_args* ac,
+                            long long total, const uint32_t w[4], uint64_t seed, uint64_t loop) {
+  const double eps = orc_actor_value(ac->epsilon_schedule, ac->t0, ac->len, eps_const, total);
+  if (eps >= 0.0 && (double)u24(w[0]) < eps) return act_from_word(w[1], A_random);
+  if (ac->boltzmann) {
+    uint32_t wb[4];
+    orc_philox(seed ^ 0x94D049BB133111EBULL, loop, (uint64_t)total, wb);
+    const double temp = orc_actor_value(ac->temperature_schedule, ac->t0, ac->len, ac->boltzmann_temperature, total);
+    return orc_boltzmann_action(q, A, temp, u53(wb[0], wb[1]));
+  }
+  return orc_select_action(q, A, -1.0, w);
 }
 
 int orc_qlearning_steps(const orc_tables* tb, const orc_qlearning_args* p, int episodic, int n_steps, uint64_t t0) {
@@ -817,7 +878,7 @@ int orc_qlearning_steps(const orc_tables* tb, const orc_qlearning_args* p, int e
       orc_philox(p->seed, p->env0 + (uint64_t)i, t, we);
       orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, t, wa);
       const size_t row = ((size_t)(episodic ? h : 0) * S + s) * A;
-      const int a = orc_select_action(Q + row, A, p->epsilon_greedy, wa);
+      const int a = orc_actor_select(Q + row, A, A, p->epsilon_greedy, &p->actor, (long long)t, wa, p->seed, p->env0 + (uint64_t)i);
       /* BaseMDP.step: NextStateSampler.sample + sample_reward (as orc_env_step, mode 2) */
       const size_t base = ((size_t)s * A + a) * tb->Ksucc;
       const int nsucc = tb->succ_len[(size_t)s * A + a];
@@ -944,6 +1005,7 @@ typedef struct {
   long long* n_episodes;
   int* trace;
   int reward_model; /* 0 N_NIG, 1 N_N (conjugate_rewards.py:112-117) */
+  orc_actor_args actor;
 } orc_psrl_args;
 
 int orc_psrl_steps(const orc_tables* tb, const orc_psrl_args* p, int n_steps, uint64_t t0) {
@@ -960,7 +1022,8 @@ int orc_psrl_steps(const orc_tables* tb, const orc_psrl_args* p, int n_steps, ui
       uint32_t we[4], wa[4];
       orc_philox(p->seed, p->env0 + (uint64_t)i, t, we);
       orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, t, wa);
-      const int a = orc_select_action(Q + ((size_t)h * S + s) * A, A, p->epsilon_greedy, wa);
+      const int a = orc_actor_select(Q + ((size_t)h * S + s) * A, A, A, p->epsilon_greedy, &p->actor, (long long)t, wa, p->seed,
+                                     p->env0 + (uint64_t)i);
       const size_t base = ((size_t)s * A + a) * tb->Ksucc;
       const int nsucc = tb->succ_len[(size_t)s * A + a];
       int pos = 0;
@@ -1056,6 +1119,7 @@ typedef struct {
   int* trace;
   long long trace_t0;
   int trace_steps;
+  orc_actor_args actor;
 } orc_ucrl2_args;
 
 int orc_ucrl2_steps(const orc_tables* tb, const orc_ucrl2_args* p, long long t_target) {
@@ -1079,7 +1143,7 @@ int orc_ucrl2_steps(const orc_tables* tb, const orc_ucrl2_args* p, long long t_t
       uint32_t we[4], wa[4];
       orc_philox(p->seed, p->env0 + (uint64_t)i, (uint64_t)t, we);
       orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, (uint64_t)t, wa);
-      const int a = orc_select_action(Q + (size_t)s * A, A, p->epsilon_greedy, wa);
+      const int a = orc_actor_select(Q + (size_t)s * A, A, A, p->epsilon_greedy, &p->actor, t, wa, p->seed, p->env0 + (uint64_t)i);
       const size_t sa = (size_t)s * A + a;
       const size_t base = sa * tb->Ksucc;
       const int nsucc = tb->succ_len[sa];
@@ -1231,6 +1295,7 @@ typedef struct {
   int* trace;
   long long trace_t0;
   int trace_steps;
+  orc_actor_args actor;
 } orc_psrlc_args;
 
 int orc_psrlc_steps(const orc_tables* tb, const orc_psrlc_args* p, long long t_target) {
@@ -1253,11 +1318,8 @@ int orc_psrlc_steps(const orc_tables* tb, const orc_psrlc_args* p, long long t_t
       uint32_t we[4], wa[4];
       orc_philox(p->seed, p->env0 + (uint64_t)i, (uint64_t)t, we);
       orc_philox(p->seed ^ 0x9E3779B97F4A7C15ULL, p->env0 + (uint64_t)i, (uint64_t)t, wa);
-      int a_ext;
-      if (p->epsilon_greedy >= 0.0 && (double)u24(wa[0]) < p->epsilon_greedy)
-        a_ext = act_from_word(wa[1], A);
-      else
-        a_ext = orc_select_action(Q + (size_t)s * AE, AE, -1.0, wa);
+      const int a_ext = orc_actor_select(Q + (size_t)s * AE, AE, A, p->epsilon_greedy, &p->actor, t, wa, p->seed,
+                                         p->env0 + (uint64_t)i);
       const int a = a_ext / psi;
       const size_t sa = (size_t)s * A + a;
       const size_t base = sa * tb->Ksucc;

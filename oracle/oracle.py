@@ -370,6 +370,38 @@ def stationary_distribution_f64(P, x0, tol=1e-14, max_iter=int(1e7)):
 
 
 # ---------------------------------------------------------------------------------------------- agent loops
+class _ActorArgs(C.Structure):
+    _fields_ = [("epsilon_schedule", C.c_void_p), ("temperature_schedule", C.c_void_p), ("t0", C.c_longlong),
+                ("len", C.c_int), ("boltzmann", C.c_int), ("boltzmann_temperature", C.c_double)]
+
+
+def set_actor(args, keep, epsilon_greedy, boltzmann_temperature, t0, n):
+    """fills args.epsilon_greedy and args.actor for the interaction counts t0 .. t0 + n - 1: constants as they are,
+    functions of the actor's interaction counter (Q_values_actor.py:58-78) tabulated.  `keep` holds the tables alive."""
+    a = args.actor
+    a.t0, a.len = int(t0), int(n)
+    a.epsilon_schedule = a.temperature_schedule = None
+    args.epsilon_greedy = -1.0
+    if callable(epsilon_greedy):
+        keep["eps"] = np.array([float(epsilon_greedy(t0 + k)) for k in range(n)], np.float64)
+        a.epsilon_schedule = _p(keep["eps"])
+        args.epsilon_greedy = 0.0
+    elif epsilon_greedy is not None:
+        args.epsilon_greedy = float(epsilon_greedy)
+    a.boltzmann = int(boltzmann_temperature is not None)
+    if callable(boltzmann_temperature):
+        keep["temp"] = np.array([float(boltzmann_temperature(t0 + k)) for k in range(n)], np.float64)
+        a.temperature_schedule = _p(keep["temp"])
+    elif boltzmann_temperature is not None:
+        a.boltzmann_temperature = float(boltzmann_temperature)
+
+
+def boltzmann_action(q, temperature, u):
+    """Q_values_actor.py:73-78 given the uniform numpy's choice consumes: index of the action"""
+    q = _f32(q)
+    return int(lib().orc_boltzmann_action(_p(q), len(q), C.c_double(temperature), C.c_double(u)))
+
+
 class _QLArgs(C.Structure):
     _fields_ = [
         ("N", C.c_longlong), ("seed", C.c_uint64), ("env0", C.c_uint64),
@@ -379,7 +411,7 @@ class _QLArgs(C.Structure):
         ("c_1", C.c_double), ("c_2", C.c_double), ("min_at", C.c_double), ("log_term", C.c_double),
         ("sqrt_h7sa", C.c_double), ("H_eff", C.c_double), ("gamma", C.c_double), ("span_approx", C.c_double),
         ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p), ("n_episodes", C.c_void_p),
-        ("trace", C.c_void_p),
+        ("trace", C.c_void_p), ("actor", _ActorArgs),
     ]
 
 
@@ -390,8 +422,10 @@ class QLearningLoops:
     successor tables."""
 
     def __init__(self, tb, n_loops, optimization_horizon, seed=0, env0=0, epsilon_greedy=None, *, p=0.05, c_1=1.0,
-                 c_2=None, min_at=0.0, UCB_type="hoeffding", confidence=0.95, span_approx_weight=1.0, h_weight=1.0):
+                 c_2=None, min_at=0.0, UCB_type="hoeffding", confidence=0.95, span_approx_weight=1.0, h_weight=1.0,
+                 boltzmann_temperature=None):
         self.tb, self.N, self.seed, self.env0 = tb, int(n_loops), int(seed), int(env0)
+        self._explore, self._keep = (epsilon_greedy, boltzmann_temperature), {}
         S, A, H = tb.c.S, tb.c.A, tb.c.H
         self.episodic = H > 0
         N = self.N
@@ -401,7 +435,6 @@ class QLearningLoops:
         self.n_episodes = np.zeros(N, np.int64)
         a = _QLArgs()
         a.N, a.seed, a.env0 = N, self.seed, self.env0
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         if self.episodic:
             self.cnt = np.ones((N, H, S, A), np.int32)
             self.Q = np.full((N, H, S, A), H, np.float32)
@@ -433,6 +466,7 @@ class QLearningLoops:
     def steps(self, n_steps, trace=False):
         tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
         self.args.trace = _p(tr)
+        set_actor(self.args, self._keep, *self._explore, self.t, n_steps)
         rc = lib().orc_qlearning_steps(C.byref(self.tb.c), C.byref(self.args), int(self.episodic), int(n_steps),
                                        C.c_uint64(self.t))
         assert rc == 0
@@ -446,6 +480,7 @@ class _PsrlArgs(C.Structure):
         ("state", C.c_void_p), ("h", C.c_void_p), ("Q", C.c_void_p), ("dir_hyper", C.c_void_p),
         ("nig_hyper", C.c_void_p), ("epsilon_greedy", C.c_double), ("cum_reward", C.c_void_p),
         ("n_episodes", C.c_void_p), ("trace", C.c_void_p), ("reward_model", C.c_int),
+        ("actor", _ActorArgs),
     ]
 
 
@@ -456,8 +491,9 @@ class PSRLLoops:
     (bayesian_models/conjugate_rewards.py:45-54)."""
 
     def __init__(self, tb, n_loops, seed=0, env0=0, epsilon_greedy=None, rewards_prior_prms=None,
-                 transitions_prior_prms=None, reward_prior_model="N_NIG"):
+                 transitions_prior_prms=None, reward_prior_model="N_NIG", boltzmann_temperature=None):
         self.tb, self.N, self.seed, self.env0 = tb, int(n_loops), int(seed), int(env0)
+        self._explore, self._keep = (epsilon_greedy, boltzmann_temperature), {}
         self.reward_model = {"N_NIG": 0, "N_N": 1}[reward_prior_model]
         S, A, H = tb.c.S, tb.c.A, tb.c.H
         N = self.N
@@ -479,7 +515,6 @@ class PSRLLoops:
         self.Q = np.zeros((N, H + 1, S, A), np.float32)
         a = _PsrlArgs()
         a.N, a.seed, a.env0 = N, self.seed, self.env0
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         a.state, a.h, a.Q = _p(self.state), _p(self.h), _p(self.Q)
         a.dir_hyper, a.nig_hyper = _p(self.dir_hyper), _p(self.nig_hyper)
         a.cum_reward, a.n_episodes = _p(self.cum_reward), _p(self.n_episodes)
@@ -492,6 +527,7 @@ class PSRLLoops:
     def steps(self, n_steps, trace=False):
         tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
         self.args.trace = _p(tr)
+        set_actor(self.args, self._keep, *self._explore, self.t, n_steps)
         rc = lib().orc_psrl_steps(C.byref(self.tb.c), C.byref(self.args), int(n_steps), C.c_uint64(self.t))
         assert rc == 0
         self.t += n_steps
@@ -508,6 +544,7 @@ class _Ucrl2Args(C.Structure):
         ("log_cap", C.c_int), ("ended", C.c_void_p), ("iteration", C.c_void_p), ("episode", C.c_void_p),
         ("delta", C.c_void_p), ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong),
         ("trace_steps", C.c_int),
+        ("actor", _ActorArgs),
     ]
 
 
@@ -520,8 +557,10 @@ class UCRL2Loops:
     and model tables compare bit for bit."""
 
     def __init__(self, tb, n_loops, optimization_horizon, seed=0, env0=0, alpha_r=1.0, alpha_p=1.0,
-                 bound_type_p="_chernoff", bound_type_rew="_chernoff", epsilon_greedy=None, planner=None, record=False):
+                 bound_type_p="_chernoff", bound_type_rew="_chernoff", epsilon_greedy=None, planner=None, record=False,
+                 boltzmann_temperature=None):
         assert bound_type_p in ("_chernoff", "bernstein") and bound_type_rew == "_chernoff"
+        self._explore, self._keep = (epsilon_greedy, boltzmann_temperature), {}
         self.history = {} if record else None
         assert tb.c.H == 0, "UCRL2Continuous needs a continuous MDP"
         self.tb, self.N, self.seed, self.env0 = tb, int(n_loops), int(seed), int(env0)
@@ -554,7 +593,6 @@ class UCRL2Loops:
         self.episode_ends = [[] for _ in range(N)]  # interaction times at which each loop's episodes ended
         a = _Ucrl2Args()
         a.N, a.seed, a.env0 = N, self.seed, self.env0
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         for k in ("state", "t", "cum_reward", "Q", "Nsas", "Nsa", "P", "est_r", "var_r", "hold", "nu", "seen", "ep_len",
                   "ep_log", "ended", "iteration", "episode", "delta"):
             setattr(a, k, _p(getattr(self, k)))
@@ -600,6 +638,7 @@ class UCRL2Loops:
         tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
         self.args.trace, self.args.trace_t0, self.args.trace_steps = _p(tr), t0, int(n_steps)
         target = t0 + int(n_steps)
+        set_actor(self.args, self._keep, *self._explore, t0, n_steps)
         while True:
             rc = lib().orc_ucrl2_steps(C.byref(self.tb.c), C.byref(self.args), C.c_longlong(target))
             assert rc == 0
@@ -622,6 +661,7 @@ class _PsrlcArgs(C.Structure):
         ("dir_hyper", C.c_void_p), ("nig_hyper", C.c_void_p), ("reward_model", C.c_int),
         ("Nsas", C.c_void_p), ("Nsa", C.c_void_p), ("nu", C.c_void_p), ("ended", C.c_void_p), ("episode", C.c_void_p),
         ("epsilon_greedy", C.c_double), ("trace", C.c_void_p), ("trace_t0", C.c_longlong), ("trace_steps", C.c_int),
+        ("actor", _ActorArgs),
     ]
 
 
@@ -663,8 +703,9 @@ class PSRLCLoops:
     colo_psrlc_sample_models + the discounted VI.  Priors as BayesianMDPModel (bayesian_model.py:44-57)."""
 
     def __init__(self, tb, n_loops, psi, seed=0, env0=0, epsilon_greedy=None, rewards_prior_prms=None,
-                 transitions_prior_prms=None, reward_prior_model="N_NIG", planner=None):
+                 transitions_prior_prms=None, reward_prior_model="N_NIG", planner=None, boltzmann_temperature=None):
         assert tb.c.H == 0
+        self._explore, self._keep = (epsilon_greedy, boltzmann_temperature), {}
         self.tb, self.N, self.seed, self.env0, self.psi = tb, int(n_loops), int(seed), int(env0), int(psi)
         self.reward_model = {"N_NIG": 0, "N_N": 1}[reward_prior_model]
         S, A, N = tb.c.S, tb.c.A, self.N
@@ -693,7 +734,6 @@ class PSRLCLoops:
         self.episode_ends = [[] for _ in range(N)]
         a = _PsrlcArgs()
         a.N, a.seed, a.env0, a.psi, a.reward_model = N, self.seed, self.env0, self.psi, self.reward_model
-        a.epsilon_greedy = -1.0 if epsilon_greedy is None else float(epsilon_greedy)
         for k in ("state", "t", "cum_reward", "Q", "dir_hyper", "nig_hyper", "Nsas", "Nsa", "nu", "ended", "episode"):
             setattr(a, k, _p(getattr(self, k)))
         self.args = a
@@ -711,6 +751,7 @@ class PSRLCLoops:
         tr = np.zeros((n_steps, self.N, 4), np.int32) if trace else None
         self.args.trace, self.args.trace_t0, self.args.trace_steps = _p(tr), t0, int(n_steps)
         target = t0 + int(n_steps)
+        set_actor(self.args, self._keep, *self._explore, t0, n_steps)
         while True:
             rc = lib().orc_psrlc_steps(C.byref(self.tb.c), C.byref(self.args), C.c_longlong(target))
             assert rc == 0

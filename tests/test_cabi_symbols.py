@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     for cname, mirror in (("colo_backup_args", _cabi.BackupArgs), ("colo_mdp_tables", _cabi.MdpTables),
                           ("colo_env_batch", _cabi.EnvBatch), ("colo_resident_args", _cabi.ResidentArgs),
                           ("colo_env_server", _cabi.EnvServer), ("colo_qlearning_args", _cabi.QLearningArgs), ("colo_psrl_args", _cabi.PsrlArgs),
-                          ("colo_ucrl2_args", _cabi.Ucrl2Args), ("colo_psrlc_args", _cabi.PsrlcArgs),
+                          ("colo_ucrl2_args", _cabi.Ucrl2Args), ("colo_actor_args", _cabi.ActorArgs), ("colo_psrlc_args", _cabi.PsrlcArgs),
                           ("colo_suite_instance", _cabi.SuiteInstance), ("colo_suite_config", _cabi.SuiteConfig),
                           ("colo_suite_result", _cabi.SuiteResult)):
         end = txt.index("} " + cname + ";")

@@ -258,3 +258,64 @@ def test_loops_sharded_over_ranks_equal_the_unsharded_batch():
         tl, th = lo.steps(n, trace=True).cpu().numpy(), hi.steps(n, trace=True).cpu().numpy()
         assert np.array_equal(tw[:, :32], tl) and np.array_equal(tw[:, 32:], th)
         assert np.array_equal(whole.cumulative_reward.cpu().numpy()[32:], hi.cumulative_reward.cpu().numpy())
+
+
+EXPLORE = [("eps_schedule", dict(epsilon_greedy=lambda t: 1.0 / (1.0 + 0.01 * t))),
+           ("boltzmann_const", dict(boltzmann_temperature=0.8)),
+           ("boltzmann_schedule_eps", dict(boltzmann_temperature=lambda t: 0.2 + 0.001 * t, epsilon_greedy=0.05))]
+
+
+@pytest.mark.parametrize("tag,ex", EXPLORE, ids=[e[0] for e in EXPLORE])
+def test_exploration_kernel_equals_oracle_bit_for_bit(tag, ex):
+    """QValuesActor's full exploration set on the device -- epsilon / temperature as constants or as functions of the
+    interaction counter, Boltzmann action draws (pinned to the reference actor by tests/golden/actor.npz) -- for the
+    Q-learning agents (episodic + continuous), PSRLEpisodic, UCRL2Continuous and PSRLContinuous: trajectories and tables
+    equal the oracle's bit for bit, across launches that split the schedule."""
+    import torch
+
+    import colosseum_b200.agent_loop as al
+
+    N, seed = 77, 13
+    # Q-learning, episodic and continuous
+    for inst, kw in (("frozenlake4_epi", dict(optimization_horizon=3000, p=0.05, c_1=0.4, c_2=0.9, min_at=0.05, UCB_type="bernstein")),
+                     ("frozenlakecontinuous_ergo0", dict(optimization_horizon=5000, min_at=0.02))):
+        tb = MDPTables.from_golden(load_instance(inst))
+        dev = make_agents(tb, {**kw, **ex}, N, seed)
+        cpu = orc.QLearningLoops(host_tables(tb), N, seed=seed, **kw, **ex)
+        tr_d = torch.cat([dev.steps(90, trace=True), dev.steps(160, trace=True)]).cpu().numpy()
+        assert np.array_equal(tr_d, cpu.steps(250, trace=True)), inst
+        assert np.array_equal(dev.Q.cpu().numpy(), cpu.Q) and np.array_equal(dev.N.cpu().numpy(), cpu.cnt)
+        assert len(np.unique(tr_d[..., 1])) == tb.A
+    # PSRLEpisodic between posterior samples (the oracle has no sampler: both act on the device's sampled Q)
+    tb = MDPTables.from_golden(load_instance("frozenlake4_epi"))
+    dev = al.PSRLEpisodic(seed, tb, 2000, n_loops=N, **ex)
+    cpu = orc.PSRLLoops(host_tables(tb), N, seed=seed, **ex)
+    cpu.set_q(dev.Q.cpu().numpy())
+    assert np.array_equal(dev.steps(tb.H - 1, trace=True).cpu().numpy(), cpu.steps(tb.H - 1, trace=True))
+    assert np.array_equal(dev.nig_hyper.cpu().numpy(), cpu.nig_hyper)
+    # the continuous model-based agents, with the planners replaced by one fixed random q-table on both sides
+    tb = MDPTables.from_golden(load_instance("riverswimcontinuous_ergo0"))
+    rng = np.random.RandomState(1)
+    Qfix = rng.rand(tb.S, tb.A).astype(np.float32)
+
+    def dev_planner_u(ag, idx, br, bp):
+        ag.Q[idx.long()] = torch.from_numpy(Qfix).cuda()
+
+    du = al.UCRL2Continuous(seed, tb, 801, n_loops=N, planner=dev_planner_u, **ex)
+    cu = orc.UCRL2Loops(host_tables(tb), N, 801, seed=seed, planner=lambda i, e, *a: (0.0, Qfix, np.zeros(tb.S, np.float32)), **ex)
+    assert np.array_equal(torch.cat([du.steps(300, trace=True), du.steps(500, trace=True)]).cpu().numpy(), cu.steps(800, trace=True))
+    assert np.array_equal(du.P.cpu().numpy(), cu.P) and np.array_equal(du.episode.cpu().numpy(), cu.episode)
+    psi = 3
+    Qext = rng.rand(tb.S, tb.A * psi).astype(np.float32)
+
+    def dev_planner_p(ag, idx):
+        ag.Q[idx.long()] = torch.from_numpy(Qext).cuda()
+
+    def cpu_planner_p(loops, idx):
+        loops.Q[idx] = Qext
+
+    dp_ = al.PSRLContinuous(seed, tb, 801, psi_weight=0.015, eta_weight=1e-9, n_loops=N, planner=dev_planner_p, **ex)
+    assert dp_._psi == psi
+    cp = orc.PSRLCLoops(host_tables(tb), N, psi, seed=seed, planner=cpu_planner_p, **ex)
+    assert np.array_equal(torch.cat([dp_.steps(300, trace=True), dp_.steps(500, trace=True)]).cpu().numpy(), cp.steps(800, trace=True))
+    assert np.array_equal(dp_.dir_hyper.cpu().numpy(), cp.dir_hyper) and np.array_equal(dp_.episode.cpu().numpy(), cp.episode)

@@ -134,3 +134,37 @@ def test_oracle_psrl_continuous_loops_match_reference_agent():
                     z = orc.psrlc_z(mk.SEED, i, ep, q, tb.S)
                     ours = orc.psrlc_simple_rows(loops.Nsas[i], z)
                     np.testing.assert_allclose(ours[cond], gold[f"{name}.ref_simple"][i, q][cond], atol=1e-7, rtol=0)
+
+
+def test_oracle_boltzmann_matches_reference_actor():
+    """orc_boltzmann_action == the reference's QValuesActor.select_action with a temperature schedule, on the committed
+    (q row, temperature, uniform) triples recorded from the unmodified class (tests/golden/make_actor_golden.py)."""
+    gold = np.load(os.path.join(GOLDEN, "actor.npz"))
+    names = sorted({k.split(".")[0] for k in gold.files})
+    assert len(names) == 3
+    for nm in names:
+        Q, st, u, temp, act = (gold[f"{nm}.{k}"] for k in ("Q", "states", "u", "temp", "action"))
+        ours = np.array([orc.boltzmann_action(Q[s], t, x) for s, t, x in zip(st, temp, u)])
+        assert np.array_equal(ours, act), nm
+
+
+def test_oracle_exploration_schedules():
+    """epsilon / temperature as functions of the interaction counter: a schedule that is constant equals the constant;
+    a step schedule equals its two constants applied in turn"""
+    tb = MDPTables.from_golden(load_instance("frozenlakecontinuous_ergo0"))
+    kw = dict(optimization_horizon=5000, min_at=0.02)
+    a = orc.QLearningLoops(host_tables(tb), 8, seed=4, epsilon_greedy=0.3, **kw)
+    b = orc.QLearningLoops(host_tables(tb), 8, seed=4, epsilon_greedy=lambda t: 0.3, **kw)
+    assert np.array_equal(a.steps(300, trace=True), np.concatenate([b.steps(100, trace=True), b.steps(200, trace=True)]))
+    c = orc.QLearningLoops(host_tables(tb), 8, seed=4, boltzmann_temperature=0.7, **kw)
+    d = orc.QLearningLoops(host_tables(tb), 8, seed=4, boltzmann_temperature=lambda t: 0.7, **kw)
+    tc = c.steps(300, trace=True)
+    assert np.array_equal(tc, d.steps(300, trace=True)) and not np.array_equal(tc, a.steps(300, trace=True)[:300])
+    assert len(np.unique(tc[..., 1])) == tb.A
+    # a step schedule == the two constants applied in turn (interaction counts 1..50 / 51..)
+    e = orc.QLearningLoops(host_tables(tb), 64, seed=4, epsilon_greedy=lambda t: 0.2 if t <= 50 else 0.9, **kw)
+    g = orc.QLearningLoops(host_tables(tb), 64, seed=4, epsilon_greedy=0.2, **kw)
+    te = e.steps(120, trace=True)
+    tg1 = g.steps(50, trace=True)
+    g._explore = (0.9, None)
+    assert np.array_equal(te, np.concatenate([tg1, g.steps(70, trace=True)]))
