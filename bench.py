@@ -338,7 +338,7 @@ def bench_step_gpu(args, rank, world):
     # ---- end to end through the public API: pinned host actions in, TimeStep fields out on the host, every step.
     # host_io=True: the step kernel reads the pinned action buffer and writes obs/reward/step_type into pinned host
     # memory itself (zero-copy over PCIe) -- one launch + one stream sync per step, no copy launches.
-    n_e2e = max(args.steps, 2000)  # >= 50 ms of timed region at ~30 us per step, whatever --steps says
+    n_e2e = max(args.steps, 4000)  # >= 50 ms of timed region at ~20-30 us per step, whatever --steps says
     env_h = BatchedMDP(tb, N, mode="dense_f32", seed=1234, env_offset=rank * N, host_io=True)
     env_h.reset()
     h_act = [a.cpu().pin_memory() for a in actions]
@@ -413,6 +413,43 @@ def bench_step_gpu(args, rank, world):
     except Exception as exc:
         native = {"error": repr(exc)[:200]}
 
+    # ---- the two-group pipeline with COMPACT host I/O: actions cross PCIe as uint8 and observations as int16 (the
+    # same information in 8 instead of 13 bytes per env-step; BatchedMDP(compact_io=True)), Python loop and native loop
+    compact = {}
+    try:
+        env_c = PipelinedBatchedMDP(tb, N, groups=2, mode="dense_f32", seed=1234, env_offset=rank * N, compact_io=True)
+        env_c.reset()
+        c_act = [[a.to(torch.uint8).pin_memory() for a in acts] for acts in p_act]
+        for g in range(2):
+            env_c.send(g, c_act[0][g])
+        for i in range(1, max(3, args.warmup)):
+            for g in range(2):
+                env_c.recv(g)
+                env_c.send(g, c_act[i % n_act][g])
+        barrier_sync(world)
+        w0 = time.perf_counter()
+        for i in range(n_e2e):
+            for g in range(2):
+                env_c.recv(g)
+                env_c.send(g, c_act[i % n_act][g])
+        for g in range(2):
+            env_c.recv(g)
+        py_ms = (time.perf_counter() - w0) * 1e3
+        barrier_sync(world)
+        env_c.run_native(c_act, max(3, args.warmup))
+        barrier_sync(world)
+        w0 = time.perf_counter()
+        env_c.run_native(c_act, n_e2e)
+        nat_ms = (time.perf_counter() - w0) * 1e3
+        barrier_sync(world)
+        assert all(int(sh.status.item()) == 0 for sh in env_c.shards)
+        # same trajectories as the int32 pipeline (same seed, same actions, same number of steps so far)
+        compact = {"py_ms": max_over_ranks(py_ms, world), "native_ms": max_over_ranks(nat_ms, world), "groups": 2,
+                   "h2d": N, "d2h": 7 * N}
+        del env_c
+    except Exception as exc:
+        compact = {"error": repr(exc)[:200]}
+
     # ---- and through the persistent step server (no launch, no stream sync per step)
     served = {}
     try:
@@ -433,7 +470,7 @@ def bench_step_gpu(args, rank, world):
     except Exception as exc:
         served = {"error": repr(exc)[:200]}
     return dict(tb=tb, N=N, ms=ms, launches=launches, e2e_ms=e2e_ms, h2d=4 * N, d2h=9 * N, b2b=b2b, det=det,
-                pipe=pipe, served=served, native=native, sweep=sweep, fused=fused, n_e2e=n_e2e)
+                pipe=pipe, served=served, native=native, sweep=sweep, fused=fused, n_e2e=n_e2e, compact=compact)
 
 
 def bench_agents_gpu(args, rank, world):
@@ -462,6 +499,46 @@ def bench_agents_gpu(args, rank, world):
                         f"{n_loops * tb.S * tb.A * 12 / 2**20:.0f} MiB per GPU"}
     except Exception as exc:
         return {"error": repr(exc)[:200]}
+
+
+def bench_model_based_agents_gpu(args, rank, world):
+    """the model-based continuous agents as device loops, planners included (UCRL2Continuous: batched
+    extended VI over the loops whose artificial episode ended; PSRLContinuous: optimistic sampling + batched discounted
+    VI) -- 256 loops per GPU on RiverSwimContinuous (tests/golden), wall clock around a synchronised region"""
+    import time
+
+    import torch
+
+    import colosseum_b200.agent_loop as al
+    from colosseum_b200.tables import MDPTables
+
+    out = {}
+    try:
+        tb = MDPTables.from_golden(np.load(os.path.join(ROOT, "tests", "golden", "inst_riverswimcontinuous_ergo0.npz")))
+        n_loops, T = 256, 10000
+        for name, make in (("ucrl2_continuous", lambda: al.UCRL2Continuous(7, tb, 2 * T + 1, alpha_r=0.1, alpha_p=0.05,
+                                                                           n_loops=n_loops, env_offset=rank * n_loops)),
+                           ("psrl_continuous", lambda: al.PSRLContinuous(7, tb, 2 * T + 1, psi_weight=0.015, eta_weight=1e-9,
+                                                                         n_loops=n_loops, env_offset=rank * n_loops))):
+            ag = make()
+            ag.steps(T)  # the early, planning-heavy phase is the warm-up
+            barrier_sync(world)
+            t0 = time.perf_counter()
+            c0 = float(ag.cumulative_reward.mean())
+            ag.steps(T)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            barrier_sync(world)
+            secs = max_over_ranks(float(dt.item()), world)
+            out[name] = {"value": world * n_loops * T / secs, "unit": "agent-steps/s", "loops_per_gpu": n_loops,
+                         "steps": T, "rounds": int(ag.rounds),
+                         "reward_rate": (float(ag.cumulative_reward.mean()) - c0) / T,
+                         "replannings_per_loop": float(ag.episode.double().mean())}
+        out["what"] = ("N independent agent loops on RiverSwimContinuous (S=30, A=2; optimal average reward 0.889), steps "
+                       "10,001..20,000 of each loop, planners included; the reference runs ~1e4 agent-steps/s per process")
+    except Exception as exc:
+        out["error"] = repr(exc)[:200]
+    return out
 
 
 C1_V0 = [0.45454547, 0.36414355, 0.2737823, 0.3346822, 0.4166667]  # SURVEY section 8d, the parity anchor
@@ -970,6 +1047,8 @@ def main():
     c3 = bench_c3_gpu(args, rank, world) if args.workload in ("all", "c3") else None
     c1 = bench_c1(args) if args.workload == "all" and world == 1 and rank == 0 else None
     agents = bench_agents_gpu(args, rank, world) if args.workload == "all" else None
+    if agents is not None:
+        agents["model_based"] = bench_model_based_agents_gpu(args, rank, world)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
@@ -1174,6 +1253,26 @@ def main():
                 line["e2e_native_loop"] = rec
         elif "error" in nat:
             line["e2e_native_loop"] = {"error": nat["error"]}
+        cpt = step.get("compact") or {}
+        if "py_ms" in cpt:
+            best_ms, how = min((cpt["py_ms"], "driven from Python (recv / send per group)"),
+                               (cpt["native_ms"], "with the recv/send loop inside the library (colo_env_pipeline_run)"))
+            v = world * N * step["n_e2e"] / (best_ms / 1e3)
+            rec = {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": cpt["h2d"], "d2h_bytes_per_step": cpt["d2h"],
+                   "timed_steps": step["n_e2e"], "timed_region_s": best_ms / 1e3,
+                   "python_loop_value": world * N * step["n_e2e"] / (cpt["py_ms"] / 1e3),
+                   "native_loop_value": world * N * step["n_e2e"] / (cpt["native_ms"] / 1e3),
+                   "what": "PipelinedBatchedMDP(groups=2, compact_io=True) " + how + ": pinned host actions in as uint8, "
+                           "TimeStep out into pinned host memory as reward f32 | observation int16 (-1 = terminal) | "
+                           "step_type u8 -- the same information in 8 instead of 13 bytes per env-step; every env steps "
+                           "once per step, all bytes cross PCIe inside the timed region, wall clock"}
+            if v > line["e2e"]["value"]:
+                line["e2e_int32_io"] = line["e2e"]
+                line["e2e"] = rec
+            else:
+                line["e2e_compact_io"] = rec
+        elif "error" in cpt:
+            line["e2e_compact_io"] = {"error": cpt["error"]}
         if "ms" in served:
             line["e2e_served"] = {"value": world * N * step["n_e2e"] / (served["ms"] / 1e3), "unit": "env-steps/s",
                                   "what": "BatchedMDP.serve(): persistent step kernel driven by a doorbell in pinned "

@@ -77,7 +77,7 @@ class EnvBatch(C.Structure):
         ("state", C.c_void_p), ("h", C.c_void_p), ("step_type", C.c_void_p), ("action", C.c_void_p),
         ("reward", C.c_void_p), ("obs", C.c_void_p), ("visits_s", C.c_void_p), ("visits_sa", C.c_void_p),
         ("visits_copies", C.c_int), ("status", C.c_void_p), ("step_type_mirror", C.c_void_p),
-        ("discount", C.c_void_p),
+        ("discount", C.c_void_p), ("io_compact", C.c_int),
     ]
 
 

@@ -91,7 +91,7 @@ class BatchedMDP:
 
     def __init__(self, tables: MDPTables, n_envs: int, mode: str = "dense_f32", seed: int = 0,
                  track_visits: bool = True, env_offset: int = 0, host_io: bool = False, stream=None,
-                 device_tables=None, scalar_api: bool = False):
+                 device_tables=None, scalar_api: bool = False, compact_io: bool = False):
         """scalar_api=True (n_envs must be 1): `reset()` / `step(action: int)` / `random_step()` return the reference's
         SCALAR dm_env.TimeStep (`TimeStep(FIRST, None, None, obs)`, `(MID, r, 1.0, obs)`, `(LAST, r, 0.0, -1)`,
         mdp/base.py:1277,1316-1317), so the object can stand where a `BaseMDP` stood.
@@ -99,7 +99,9 @@ class BatchedMDP:
         kernel writes directly over PCIe (zero-copy), and `step_host` reads the actions straight from a pinned host
         tensor: an agent running on the host gets its TimeStep with one launch and one stream sync per step, no
         copy launches (include/colosseum_b200.h, colo_env_batch).  stream: a torch.cuda.Stream the host_io lean path
-        (`step_host`, `send_host`/`recv_host`) launches on instead of the current stream (see PipelinedBatchedMDP)."""
+        (`step_host`, `send_host`/`recv_host`) launches on instead of the current stream (see PipelinedBatchedMDP).
+        compact_io=True (with host_io): actions cross PCIe as uint8 and observations as int16 (-1 = terminal) --
+        8 instead of 13 bytes per env-step; S <= 32767, A <= 256, auto-resetting dense f32 steps with supplied actions."""
         import torch
 
         assert mode in _MODES
@@ -122,10 +124,19 @@ class BatchedMDP:
         # the three TimeStep fields a host-side agent reads back live in ONE buffer (obs | reward | step_type), so an
         # end-to-end step is a single device->host copy
         self.host_io = bool(host_io)
+        self.compact_io = bool(compact_io)
+        assert not self.compact_io or (self.host_io and mode == "dense_f32" and track_visits and tables.S <= 32767
+                                       and tables.A <= 256), "compact_io: host_io dense_f32 batches with counters"
         # (obs | reward | [discount |] step_type).  The device-resident block also carries dm_env's discount, written by
         # the step kernel's epilogue (no eager-PyTorch tail after a step); the pinned-host block does not (4 more
         # bytes per env over PCIe): there the discount is derived from step_type on the host when it is asked for.
-        if self.host_io:
+        if self.compact_io:  # reward f32 | obs i16 | step_type u8: 7 bytes per env written over PCIe
+            self._out = torch.zeros(7 * N, dtype=torch.uint8).pin_memory()
+            self.step_type = torch.full((N,), _cabi.STEP_LAST, dtype=torch.uint8, device="cuda")
+            self.step_type_host = self._out[6 * N:]
+            self.step_type_host.fill_(_cabi.STEP_LAST)
+            self.discount = None
+        elif self.host_io:
             self._out = torch.zeros(9 * N, dtype=torch.uint8).pin_memory()
             self.step_type = torch.full((N,), _cabi.STEP_LAST, dtype=torch.uint8, device="cuda")  # kernel input too
             self.step_type_host = self._out[8 * N:]
@@ -136,9 +147,14 @@ class BatchedMDP:
             self.step_type = self._out[12 * N:]
             self.step_type.fill_(_cabi.STEP_LAST)
             self.discount = self._out[8 * N: 12 * N].view(torch.float32)
-        self.obs = self._out[: 4 * N].view(torch.int32)
-        self.reward = self._out[4 * N: 8 * N].view(torch.float32)
-        self.action = torch.zeros(N, dtype=torch.int32, device="cuda")
+        if self.compact_io:
+            self.reward = self._out[: 4 * N].view(torch.float32)
+            self.obs = self._out[4 * N: 6 * N].view(torch.int16)
+        else:
+            self.obs = self._out[: 4 * N].view(torch.int32)
+            self.reward = self._out[4 * N: 8 * N].view(torch.float32)
+        self.action_dtype = torch.uint8 if self.compact_io else torch.int32
+        self.action = torch.zeros(N, dtype=self.action_dtype, device="cuda")
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
         vc = self.VISIT_COPIES
         self._visits_s = torch.zeros((vc, tables.S), dtype=torch.int64, device="cuda") if track_visits else None
@@ -160,6 +176,7 @@ class BatchedMDP:
         b.status = _cabi.ptr(self.status)
         b.step_type_mirror = self.step_type_host.data_ptr() if self.host_io else None
         b.discount = _cabi.ptr(self.discount)
+        b.io_compact = int(self.compact_io)
         self._batch = b
         self._batch_ref = C.byref(b)
         self._own_action_ptr = b.action
@@ -234,9 +251,12 @@ class BatchedMDP:
             torch.cuda.current_stream().synchronize()
         N = self.n_envs
         out = self._out.clone()  # ONE copy: the fields of this TimeStep survive the next step
-        obs, reward = out[: 4 * N].view(torch.int32), out[4 * N: 8 * N].view(torch.float32)
+        if self.compact_io:
+            reward, obs = out[: 4 * N].view(torch.float32), out[4 * N: 6 * N].view(torch.int16)
+        else:
+            obs, reward = out[: 4 * N].view(torch.int32), out[4 * N: 8 * N].view(torch.float32)
         if self.host_io:  # host tensors: derive dm_env's discount from step_type on the host (no GPU work)
-            st = out[8 * N:]
+            st = out[6 * N:] if self.compact_io else out[8 * N:]
             discount = torch.full((N,), float("nan"))
             discount[st == _cabi.STEP_MID] = 1.0
             discount[st == _cabi.STEP_LAST] = 0.0
@@ -264,7 +284,7 @@ class BatchedMDP:
         act_ptr = self._own_action_ptr
         if not random_actions:
             if isinstance(action, torch.Tensor):
-                if (action.is_cuda or (self.host_io and action.is_pinned())) and action.dtype == torch.int32 \
+                if (action.is_cuda or (self.host_io and action.is_pinned())) and action.dtype == self.action_dtype \
                         and action.is_contiguous():
                     act_ptr = action.data_ptr()  # read in place (device, or pinned host memory over PCIe): no copy
                 else:
@@ -298,7 +318,7 @@ class BatchedMDP:
         itself.  Returns host views (obs i32[N], reward f32[N], step_type u8[N]) of the pinned output buffer,
         valid until the next step."""
         assert self.host_io, "construct the BatchedMDP with host_io=True"
-        if not (auto_reset and action.dtype == self.torch.int32 and action.is_pinned() and action.is_contiguous()):
+        if not (auto_reset and action.dtype == self.action_dtype and action.is_pinned() and action.is_contiguous()):
             self.step_async(action, auto_reset=auto_reset)  # general path (checks, staging copies)
             self._sync(_cabi.current_stream())
             return self.obs, self.reward, self.step_type_host
@@ -340,7 +360,7 @@ class BatchedMDP:
         pinned views `wait()` returns.  One step then costs no launch and no stream sync, only PCIe round trips.
         The kernel retires by itself after `idle_timeout_ms` without a step and is restarted transparently."""
         torch = self.torch
-        assert self.host_io, "construct the BatchedMDP with host_io=True"
+        assert self.host_io and not self.compact_io, "construct the BatchedMDP with host_io=True (and without compact_io)"
         assert action.dtype == torch.int32 and action.is_pinned() and action.is_contiguous() \
             and action.numel() == self.n_envs, "action: pinned contiguous int32 [N]"
         assert getattr(self, "_srv", None) is None, "already serving"
@@ -605,10 +625,11 @@ class PipelinedBatchedMDP:
     """
 
     def __init__(self, tables: MDPTables, n_envs: int, groups: int = 2, mode: str = "dense_f32", seed: int = 0,
-                 track_visits: bool = True, env_offset: int = 0):
+                 track_visits: bool = True, env_offset: int = 0, compact_io: bool = False):
         import torch
 
         self._serving = False
+        self.compact_io = bool(compact_io)  # uint8 actions in, int16 observations out (BatchedMDP.compact_io)
 
         self.groups = int(groups)
         self.n_envs = int(n_envs)
@@ -617,7 +638,7 @@ class PipelinedBatchedMDP:
         dev = DeviceTables(tables, mode)
         self.shards = [BatchedMDP(tables, self.sizes[g], mode=mode, seed=seed, track_visits=track_visits,
                                   env_offset=env_offset + self.offsets[g], host_io=True,
-                                  stream=torch.cuda.Stream(), device_tables=dev)
+                                  stream=torch.cuda.Stream(), device_tables=dev, compact_io=compact_io)
                        for g in range(groups)]
         torch.cuda.synchronize()  # the buffers were initialised on the default stream
 
@@ -669,7 +690,7 @@ class PipelinedBatchedMDP:
         ring = (C.c_void_p * (Rn * G))()
         for i, acts in enumerate(action_ring):
             for g, a in enumerate(acts):
-                assert a.dtype == self.shards[g].torch.int32 and a.is_pinned() and a.numel() == self.sizes[g]
+                assert a.dtype == self.shards[g].action_dtype and a.is_pinned() and a.numel() == self.sizes[g]
                 ring[i * G + g] = a.data_ptr()
         t0 = self.shards[0].t
         assert all(sh.t == t0 for sh in self.shards)

@@ -42,6 +42,7 @@ struct StepIO {
   unsigned char* step_type_mirror;  // write-only second target of step_type (pinned host memory) or null
   float* discount;                  // dm_env discount of the emitted TimeStep (1 MID, 0 LAST, NaN FIRST) or null
   int n_steps;  // > 1: that many consecutive steps in ONE launch (random actions; Philox counter t, t+1, ...)
+  int io_compact;  // action u8[N] in, obs i16[N] out (colo_env_batch.io_compact)
   // persistent step server (colo_env_server_*; SERVER kernels only): the kernel stays resident and runs one pass per
   // doorbell value posted by the host instead of one pass per launch
   const unsigned long long* srv_doorbell;  // pinned host, written by the host: index of the newest requested step
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
 // 4 Mi envs: 505 warp instructions per env-step, issue slots 68 % busy, DRAM 11 % -- the kernel is ISSUE bound once
 // the batch fills the machine, so instructions are what the asymptotic env-steps/s is made of.
 constexpr int kLeanThreads = 128;
-template <int NCH>
+template <int NCH, bool COMPACT>
 __global__ void __launch_bounds__(kLeanThreads) env_step_kary_lean_kernel(const colo_mdp_tables tb, const StepIO io) {
   constexpr int ld = 128 * NCH, NB = 4 * NCH;
   const unsigned e = blockIdx.x * kLeanThreads + threadIdx.x;
@@ -584,7 +585,10 @@ __global__ void __launch_bounds__(kLeanThreads) env_step_kary_lean_kernel(const 
     st = io.step_type[e];
     s = io.state[e];
     h = io.h[e];
-    a = io.srv_go ? __ldcv(io.action + e) : io.action[e];
+    if (COMPACT)
+      a = reinterpret_cast<const unsigned char*>(io.action)[e];
+    else
+      a = io.srv_go ? __ldcv(io.action + e) : io.action[e];
   }
   const Philox4 w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, io.t);
   bool bad = false;
@@ -641,7 +645,10 @@ __global__ void __launch_bounds__(kLeanThreads) env_step_kary_lean_kernel(const 
     if (io.step_type_mirror) io.step_type_mirror[e] = COLO_STEP_FIRST;
     io.reward[e] = __int_as_float(0x7fc00000);
     if (io.discount) io.discount[e] = __int_as_float(0x7fc00000);
-    io.obs[e] = nxt;
+    if (COMPACT)
+      reinterpret_cast<short*>(io.obs)[e] = (short)nxt;
+    else
+      io.obs[e] = nxt;
   } else if (stepping) {
     const int hh = h + 1;
     const bool last = tb.H > 0 && hh >= tb.H;
@@ -652,7 +659,10 @@ __global__ void __launch_bounds__(kLeanThreads) env_step_kary_lean_kernel(const 
     io.step_type[e] = nst;
     if (io.step_type_mirror) io.step_type_mirror[e] = nst;
     if (io.discount) io.discount[e] = last ? 0.f : 1.f;
-    io.obs[e] = last ? -1 : nxt;
+    if (COMPACT)
+      reinterpret_cast<short*>(io.obs)[e] = last ? (short)-1 : (short)nxt;
+    else
+      io.obs[e] = last ? -1 : nxt;
   }
   const unsigned copy = blockIdx.x & (unsigned)io.visits_mask;
   aggregated_inc(io.visits_s + (size_t)copy * io.n_s, nxt, stepping || resetting);
@@ -722,7 +732,10 @@ __global__ void __launch_bounds__(kStepThreads) env_reset_kernel(const colo_mdp_
       if (io.step_type_mirror) io.step_type_mirror[e] = COLO_STEP_FIRST;
       if (io.discount) io.discount[e] = __int_as_float(0x7fc00000);
       if (io.reward) io.reward[e] = __int_as_float(0x7fc00000);  // the reference's reward of a FIRST TimeStep is None
-      io.obs[e] = s0;
+      if (io.io_compact)
+        reinterpret_cast<short*>(io.obs)[e] = (short)s0;
+      else
+        io.obs[e] = s0;
     }
     const long long copy = blockIdx.x & io.visits_mask;
     if (io.visits_s) aggregated_inc(io.visits_s + copy * io.n_s, s0, valid);
@@ -839,7 +852,8 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
       const int gl = (int)((io.N + kLeanThreads - 1) / kLeanThreads);
 #define COLO_LEAN(NCH)                                                              \
   case NCH:                                                                         \
-    env_step_kary_lean_kernel<NCH><<<gl, kLeanThreads, 0, st>>>(*tb, io);           \
+    if (io.io_compact) env_step_kary_lean_kernel<NCH, true><<<gl, kLeanThreads, 0, st>>>(*tb, io);   \
+    else env_step_kary_lean_kernel<NCH, false><<<gl, kLeanThreads, 0, st>>>(*tb, io);                 \
     break
       switch (ld / 128) {
         COLO_LEAN(1);
@@ -854,6 +868,8 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
 #undef COLO_LEAN
       return check_launch("env_step_kary_lean_kernel");
     }
+    COLO_ARG_CHECK(!io.io_compact, "io_compact is offered by the common call of the dense f32 step only (supplied actions, "
+                                   "in-kernel uniforms, auto_reset, CDF index present, counters on, no server)");
     if (!coop) {
       const int gk = grid_for(kStepThreads, io.N);
 #define COLO_KARY(NCH)                                                                              \
@@ -892,6 +908,7 @@ static int launch_dense(const colo_mdp_tables* tb, const StepIO& io, void* strea
     }
 #undef COLO_SHORT
   } else {
+    COLO_ARG_CHECK(!io.io_compact, "io_compact needs rows of at most 1024 states");
     const int grid = grid_for(kStepThreads / 32, (io.N + 31) / 32);
     launch_step(env_step_dense_kernel<TC, 8, SERVER>, grid, SERVER, share, tb, io, st);
   }
@@ -902,6 +919,7 @@ template <bool SERVER>
 static int launch_succ(const colo_mdp_tables* tb, const StepIO& io, void* stream, int share = 1) {
   COLO_ARG_CHECK(tb->succ_cum && tb->succ_idx && tb->succ_len && tb->Ksucc > 0, "successor tables");
   COLO_ARG_CHECK(io.reward && io.action, "env buffers");
+  COLO_ARG_CHECK(!io.io_compact, "io_compact is offered by the dense f32 step only");
   if (io.N == 0) return COLO_OK;
   launch_step(env_step_succ_kernel<SERVER>, grid_for(kStepThreads, io.N), SERVER, share, tb, io, (cudaStream_t)stream);
   return check_launch("env_step_succ_kernel");
@@ -925,6 +943,8 @@ static int make_io(const colo_mdp_tables* tb, const colo_env_batch* b, int rando
   io->step_type_mirror = b->step_type_mirror;
   io->discount = b->discount;
   io->n_steps = 1;
+  io->io_compact = b->io_compact;
+  COLO_ARG_CHECK(!b->io_compact || (tb->S <= 32767 && tb->A <= 256), "io_compact needs S <= 32767 and A <= 256");
   return COLO_OK;
 }
 

@@ -343,8 +343,11 @@ int extended_vi_batched(const float* T, const float* est_r, const double* beta_r
   a.m = m; a.S = S; a.A = A; a.n_pow2 = n_pow2;
   a.r_max = r_max; a.eps = eps; a.max_iter = max_iter;
   a.Q = Q; a.V = V; a.span = span; a.iters = iters; a.status = status;
-  const int grid = m < 4 * sm_count() ? m : 4 * sm_count();
-  kern<<<grid, kEviBatchThreads, smem, (cudaStream_t)stream>>>(a);
+  // one warp per state and iteration: small models take small CTAs (cheaper barriers, more models resident per SM)
+  const int threads = S > 256 ? kEviBatchThreads : (S > 64 ? 512 : 256);
+  const int per_sm = 2048 / threads;
+  const int grid = m < per_sm * 2 * sm_count() ? m : per_sm * 2 * sm_count();
+  kern<<<grid, threads, smem, (cudaStream_t)stream>>>(a);
   return check_launch("evi_batched_kernel");
 }
 

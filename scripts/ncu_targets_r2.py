@@ -56,5 +56,40 @@ elif what == "epi_batched":
     R = torch.rand((B, S, A), device="cuda")
     for _ in range(3):
         dp.episodic_value_iteration(H, T, R, precision="f32")
+elif what in ("evi_batched", "psrlc_sample", "avg_rewards"):
+    # the model-based continuous agents (round 2b): 1,024 FrozenLake loops a few thousand steps in, then ONE planning round
+    # for all loops at once
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_instance
+    import colosseum_b200.agent_loop as al
+    from colosseum_b200.tables import MDPTables
+
+    gi = load_instance("frozenlakecontinuous_ergo0")
+    tb = MDPTables.from_golden(gi)
+    N = 1024
+    idx = torch.arange(N, dtype=torch.int32, device="cuda")
+    if what == "evi_batched":
+        ag = al.UCRL2Continuous(0, tb, 20001, alpha_r=0.1, alpha_p=0.05, bound_type_p="bernstein", n_loops=N)
+        ag.steps(3000)
+        br, bp = ag.bounds(idx)
+        Q, V = torch.zeros_like(ag.Q), torch.zeros_like(ag.V)
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: only the all-loops planning round is captured
+        for _ in range(2):
+            ag.solve_optimistic_model(idx, br, bp, Q, V)
+    elif what == "psrlc_sample":
+        ag = al.PSRLContinuous(0, tb, 20001, psi_weight=0.02, eta_weight=1e-8, n_loops=N)
+        ag.steps(3000)
+        torch.cuda.profiler.start()
+        for _ in range(2):
+            ag.sample_models(idx)
+    else:
+        import colosseum_b200.markov_chain as mc
+
+        ag = al.QLearningContinuous(0, tb, 20000, n_loops=N)
+        ag.steps(3000)
+        pi = torch.nn.functional.one_hot(ag.Q.argmax(-1), tb.A).float().contiguous()
+        torch.cuda.profiler.start()
+        mc.get_average_reward_batched(np.asarray(gi["T"], np.float32), np.asarray(gi["R"], np.float32), pi,
+                                      ag.state.cpu().numpy())
 torch.cuda.synchronize()
 print("ok", what)

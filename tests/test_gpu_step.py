@@ -673,3 +673,52 @@ def test_native_pipeline_loop_is_identical(bm):
             assert torch.equal(x, y) or (torch.isnan(x) == torch.isnan(y)).all() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
         assert torch.equal(a.shards[k].state, b.shards[k].state) and a.shards[k].t == b.shards[k].t
     assert torch.equal(a.get_visitation_counts(), b.get_visitation_counts())
+
+
+def test_compact_host_io_is_identical(bm):
+    """compact_io=True (uint8 actions in, int16 observations out: 8 instead of 13 bytes per env-step over PCIe) emits
+    exactly the TimeSteps of the int32 host_io batch -- single batch, pipelined groups and the native loop -- on a
+    continuous and an episodic MDP (terminal observation -1, auto-reset); calls the compact layout cannot serve fail
+    loudly."""
+    import torch
+
+    from colosseum_b200._cabi import ColosseumB200Error
+
+    for name in ("c2_deepsea30_prand", "minigridempty5_epi"):
+        tb = MDPTables.from_golden(load_instance(name))
+        N = 3001
+        ref = bm.BatchedMDP(tb, N, seed=11, host_io=True)
+        cpt = bm.BatchedMDP(tb, N, seed=11, host_io=True, compact_io=True)
+        pipe = bm.PipelinedBatchedMDP(tb, N, groups=2, seed=11, compact_io=True)
+        a0, b0 = ref.reset(), cpt.reset()
+        pipe.reset()
+        assert cpt.obs.dtype == torch.int16 and torch.equal(a0.observation, b0.observation.to(torch.int32))
+        gen = torch.Generator().manual_seed(3)
+        n0 = pipe.sizes[0]
+        for t in range(3 * max(tb.H, 10)):
+            a = torch.randint(0, tb.A, (N,), dtype=torch.int32, generator=gen).pin_memory()
+            a8 = a.to(torch.uint8).pin_memory()
+            o, r, st = ref.step_host(a, auto_reset=True)
+            o2, r2, st2 = cpt.step_host(a8, auto_reset=True)
+            parts = pipe.step_all([a8[:n0].clone().pin_memory(), a8[n0:].clone().pin_memory()])
+            assert torch.equal(o, o2.to(torch.int32)) and torch.equal(st, st2)
+            assert np.array_equal(r.numpy(), r2.numpy(), equal_nan=True)
+            assert torch.equal(o, torch.cat([p[0] for p in parts]).to(torch.int32))
+            assert np.array_equal(r.numpy(), torch.cat([p[1] for p in parts]).numpy(), equal_nan=True)
+            if tb.H > 0:
+                assert bool(((o2 == -1) == (st2 == 2)).all())
+        assert torch.equal(ref.visits_sa, cpt.visits_sa) and torch.equal(ref.state, cpt.state)
+        # the native loop continues the same trajectories
+        ring = [[torch.randint(0, tb.A, (n,), dtype=torch.int32, generator=gen).to(torch.uint8).pin_memory()
+                 for n in pipe.sizes] for _ in range(3)]
+        pipe.run_native(ring, 7)
+        for i in range(7):
+            a8 = torch.cat(ring[i % 3]).pin_memory()
+            o2, r2, st2 = cpt.step_host(a8, auto_reset=True)
+        assert torch.equal(o2, torch.cat([sh.obs for sh in pipe.shards]))
+        assert np.array_equal(r2.numpy(), torch.cat([sh.reward for sh in pipe.shards]).numpy(), equal_nan=True)
+        with pytest.raises(ColosseumB200Error):  # no auto-reset: not the lean call
+            cpt.step_async(a8, auto_reset=False)
+            torch.cuda.synchronize()
+    with pytest.raises(AssertionError):
+        bm.BatchedMDP(tb, 8, mode="succ", host_io=True, compact_io=True)
