@@ -446,6 +446,22 @@ def bench_step_gpu(args, rank, world):
         # same trajectories as the int32 pipeline (same seed, same actions, same number of steps so far)
         compact = {"py_ms": max_over_ranks(py_ms, world), "native_ms": max_over_ranks(nat_ms, world), "groups": 2,
                    "h2d": N, "d2h": 7 * N}
+        # measured alternatives of the host loop: stream memory operations instead of sync + launch
+        # (one triple at a time / CUDA-graph replays), and one host thread per group
+        for key, run in (("queued_stream_memops", lambda k: env_c.run_queued(c_act, k, graph=False)),
+                         ("queued_graph_replays", lambda k: env_c.run_queued(c_act, k, graph=True)),
+                         ("thread_per_group", lambda k: env_c.run_native(c_act, k, threads=True))):
+            try:
+                run(max(3, args.warmup))
+                barrier_sync(world)
+                w0 = time.perf_counter()
+                run(n_e2e)
+                v_ms = (time.perf_counter() - w0) * 1e3
+                barrier_sync(world)
+                compact.setdefault("variants", {})[key] = max_over_ranks(v_ms, world)
+            except Exception as exc:
+                compact.setdefault("variants", {})[key] = repr(exc)[:160]
+        assert all(int(sh.status.item()) == 0 for sh in env_c.shards)
         del env_c
     except Exception as exc:
         compact = {"error": repr(exc)[:200]}
@@ -765,11 +781,21 @@ def bench_c3_gpu(args, rank, world):
     gdir = os.path.join(ROOT, "tests", "golden")
     n_suite = suite_size(gdir)
     B = args.c3_instances
-    i0, i1 = shard_range(B, rank, world)
+    # instance i of the list goes to rank i % world (every rank gets the same mix of families and sizes; a contiguous
+    # range left the slowest of 8 ranks 20 % behind the mean), and a rank starts its most expensive instances first
+    # (its workers pull from one queue: longest-first keeps the tail short -- the slowest single instance is ~0.2 s of a
+    # ~0.35 s region at 128 instances per GPU)
+    my_ids = list(range(rank, B, world))
+    i0, i1 = 0, len(my_ids)
     lib = _cabi.lib()
-    mine = load_suite_all(gdir, indices=sorted({i % n_suite for i in range(i0, i1)}))
-    by_index = dict(zip(sorted({i % n_suite for i in range(i0, i1)}), mine))
-    work = [(by_index[i % n_suite], 0) for i in range(i0, i1)]
+    mine = load_suite_all(gdir, indices=sorted({i % n_suite for i in my_ids}))
+    by_index = dict(zip(sorted({i % n_suite for i in my_ids}), mine))
+
+    def cost(inst):  # targets x states x actions of the diameter solve
+        n = len(inst.nodes) if inst.episodic and inst.nodes is not None else inst.S
+        return float(n) * n * inst.tables.A
+
+    work = sorted(((by_index[i % n_suite], 0) for i in my_ids), key=lambda w: -cost(w[0]))
     suite = mine
     # the workers block in cudaStreamSynchronize (blocking-sync schedule inside colo_suite_run): 8 per GPU whatever the
     # number of ranks sharing the host
@@ -1185,19 +1211,19 @@ def main():
                     "what": "BatchedMDP(host_io=True).step_host: pinned host actions read, and obs/reward/step_type "
                             "written to pinned host memory, by the step kernel itself over PCIe (zero-copy), then a "
                             "stream sync, every step"},
-            # NOT an HBM achievement at this size: 65,536 envs are a fraction of a wave (ncu: 0.38 waves/SM) of one-thread-per-env work and the
+            # NOT an HBM achievement at this size: 65,536 envs are a fraction of a wave (ncu: 0.22 waves/SM) of one-thread-per-env work and the
             # 2.9 MB of tables live in L1/L2, so a step is ONE env's dependency chain (env scalars -> coarse index ->
             # mid index + reward classes -> crossing quad -> reward quantiles), not a stream.  `achieved` is the
             # env-state stream the launch really has to move (STEP_IO_BYTES per env-step); `at_saturation` is the same
             # kernel at the env count where that stream is what it waits for.
             "roofline": {"bound": "latency", "achieved": io_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": io_bytes / sec / 1e9 / peak, "traffic": ncu_traffic("step", N),
-                         "peak_source": peak_src, "kernel": "env_step_dense_kary_kernel<float,4>",
+                         "peak_source": peak_src, "kernel": "env_step_kary_lean_kernel<4>",
                          "algorithmic_bytes_per_launch": io_bytes,
                          "algorithmic_bytes_per_env_step": STEP_IO_BYTES,
                          "nominal_bytes_per_env_step_survey_8d": STEP_BYTES(tb.S),
                          "limiter": "dependent-load latency of one env's chain (4 L2/L1 round trips) plus the graph-node "
-                                    "launch; 0.38 waves per SM at 65,536 envs -- see `env_sweep` for the throughput regime",
+                                    "launch; 0.22 waves per SM at 65,536 envs (ncu) -- see `env_sweep` for the throughput regime",
                          "at_saturation": None if sat is None else {
                              "n_envs": sat["n_envs"], "env_steps_per_s": sat["env_steps_per_s"],
                              "bound": "issue",
@@ -1266,6 +1292,16 @@ def main():
                            "TimeStep out into pinned host memory as reward f32 | observation int16 (-1 = terminal) | "
                            "step_type u8 -- the same information in 8 instead of 13 bytes per env-step; every env steps "
                            "once per step, all bytes cross PCIe inside the timed region, wall clock"}
+            if cpt.get("variants"):
+                rec["host_loop_variants"] = {
+                    k: (world * N * step["n_e2e"] / (ms / 1e3) if isinstance(ms, float) else ms)
+                    for k, ms in cpt["variants"].items()}
+                rec["host_loop_variants"]["what"] = (
+                    "env-steps/s of the same compact two-group pipeline with (a) the group-step handshake done by the GPU "
+                    "front end (cuStreamWaitValue32 -> kernel -> cuStreamWriteValue32 on pinned flags, enqueued ahead; "
+                    "colo_env_pipeline_run_queued), one triple at a time and as replayed CUDA graphs of 64 steps, and (b) "
+                    "one host thread per group (colo_env_pipeline_run_threads); bit-identical TimeSteps, reported as "
+                    "measured alternatives")
             if v > line["e2e"]["value"]:
                 line["e2e_int32_io"] = line["e2e"]
                 line["e2e"] = rec

@@ -231,6 +231,10 @@ PROTOTYPES = {
     "colo_env_random_steps": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _I, _ULL, _I, _P]),
     "colo_emit_noise_correlated": (_I, [_P, _P, _P, _LL, _I, _I, _P, _I, _D, _ULL, _ULL, _ULL, _P]),
     "colo_env_pipeline_run": (_I, [_P, _I, _P, _I, _ULL, _I, _P, _P]),
+    "colo_env_pipeline_run_threads": (_I, [_P, _I, _P, _I, _ULL, _I, _P, _P]),
+    "colo_env_pipeline_create": (_I, [_P, _I, C.POINTER(C.c_void_p)]),
+    "colo_env_pipeline_run_queued": (_I, [_P, _P, _I, _ULL, _I, _P, _P, _I]),
+    "colo_env_pipeline_destroy": (None, [_P]),
     "colo_env_stepper_create": (_I, [C.POINTER(MdpTables), C.POINTER(EnvBatch), _I, _P, C.POINTER(C.c_void_p)]),
     "colo_env_stepper_launch": (_I, [_P, _P, _ULL]),
     "colo_env_stepper_destroy": (None, [_P]),

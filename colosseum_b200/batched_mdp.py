@@ -673,12 +673,13 @@ class PipelinedBatchedMDP:
     def recv(self, g: int):
         return self.shards[g].wait() if self._serving else self.shards[g].recv_host()
 
-    def run_native(self, action_ring, n_steps, on_timestep=None):
+    def run_native(self, action_ring, n_steps, on_timestep=None, threads=False):
         """`n_steps` steps of every env with the recv/send loop run by the library (colo_env_pipeline_run): step i of
         group g reads `action_ring[i % len(action_ring)][g]` (pinned int32 tensors).  `on_timestep`: an optional
         ctypes callback `void(void* user, int group, int step)` -- a host agent written in C -- called when group g's
         TimeStep of `step` is in the pinned views (`shards[g].obs / reward / step_type_host`) and before its next
-        launch.  Bit-identical to `n_steps` rounds of recv / send."""
+        launch.  Bit-identical to `n_steps` rounds of recv / send.  `threads=True`: one host thread per group
+        (colo_env_pipeline_run_threads; `on_timestep` is then called on the group's own thread)."""
         import ctypes as C
 
         assert not self._serving
@@ -694,11 +695,54 @@ class PipelinedBatchedMDP:
                 ring[i * G + g] = a.data_ptr()
         t0 = self.shards[0].t
         assert all(sh.t == t0 for sh in self.shards)
-        rc = _cabi.lib().colo_env_pipeline_run(hs, G, ring, Rn, t0, int(n_steps), on_timestep, None)
-        _cabi.check(rc, "colo_env_pipeline_run")
+        run = _cabi.lib().colo_env_pipeline_run_threads if threads else _cabi.lib().colo_env_pipeline_run
+        rc = run(hs, G, ring, Rn, t0, int(n_steps), on_timestep, None)
+        _cabi.check(rc, "colo_env_pipeline_run_threads" if threads else "colo_env_pipeline_run")
         for sh in self.shards:
             sh.t += int(n_steps)
         return [(sh.obs, sh.reward, sh.step_type_host) for sh in self.shards]
+
+    def run_queued(self, action_ring, n_steps, on_timestep=None, graph=True):
+        """`run_native` without a stream synchronisation and a launch on the host per group-step
+        (colo_env_pipeline_run_queued): every group's steps sit on a library-owned stream behind stream memory
+        operations -- wait (go == i) -> step kernel -> write (done = i) -- enqueued ahead of time (`graph=True`: as
+        replays of one CUDA graph of >= 64 steps per group), and the host loop per group-step is: spin on the pinned
+        `done` word, `on_timestep`, store the pinned `go` word.  Same arguments, same order of events and bit-identical
+        TimeSteps as `run_native`; the action ring must stay alive (and, for the graphs to be reused, the same) between
+        calls."""
+        import ctypes as C
+
+        assert not self._serving
+        G, Rn = self.groups, len(action_ring)
+        for sh in self.shards:
+            if sh._stepper is None:
+                sh._make_stepper()
+        if getattr(self, "_pipeline", None) is None:
+            hs = (C.c_void_p * G)(*[sh._stepper for sh in self.shards])
+            out = C.c_void_p()
+            _cabi.check(_cabi.lib().colo_env_pipeline_create(hs, G, C.byref(out)), "colo_env_pipeline_create")
+            self._pipeline = out.value
+        ring = (C.c_void_p * (Rn * G))()
+        for i, acts in enumerate(action_ring):
+            for g, a in enumerate(acts):
+                assert a.dtype == self.shards[g].action_dtype and a.is_pinned() and a.numel() == self.sizes[g]
+                ring[i * G + g] = a.data_ptr()
+        t0 = self.shards[0].t
+        assert all(sh.t == t0 for sh in self.shards)
+        rc = _cabi.lib().colo_env_pipeline_run_queued(self._pipeline, ring, Rn, t0, int(n_steps), on_timestep, None,
+                                                      1 if graph else 0)
+        _cabi.check(rc, "colo_env_pipeline_run_queued")
+        for sh in self.shards:
+            sh.t += int(n_steps)
+        return [(sh.obs, sh.reward, sh.step_type_host) for sh in self.shards]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pipeline", None):
+                _cabi.lib().colo_env_pipeline_destroy(self._pipeline)
+                self._pipeline = None
+        except Exception:
+            pass
 
     def step_all(self, actions):
         """one step of every env: launches all groups, then waits for each (actions: list of pinned int32 [N/groups])"""

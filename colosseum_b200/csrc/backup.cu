@@ -16,7 +16,7 @@
 
 #include <vector>
 
-#include "common.cuh"
+#include "tma_device.cuh"
 
 extern "C" size_t colo_diameter_continuous_work_bytes(int K, int S, int f64);
 
@@ -216,6 +216,172 @@ __global__ void __launch_bounds__(kThreads, COLO_BACKUP_MIN_BLOCKS) backup_kerne
   }
 }
 
+// ---- the same sweep with the rows of T staged in shared memory by the TMA (BASELINE north star: "TMA-staged T tiles") --
+// One persistent CTA per SM slot: a producer thread keeps a ring of NST stages full -- one cp.async.bulk per state (its A
+// rows are A*S*4 contiguous bytes), completion signalled on the stage's `full` mbarrier -- and 8 consumer warps each take
+// every 8th stage: dot products from shared memory against V (L1), warp-shuffle fold over the actions, the same epilogue
+// as backup_kernel, then an arrive on the stage's `empty` mbarrier.  States are dealt to CTAs round-robin, so consecutive
+// CTAs stream consecutive 8 KB chunks.  Built to MEASURE the north star's suggestion against the LDG path:
+// selected with COLO_BACKUP_TMA=1 (COLO_BACKUP_TMA_{STAGES,CTAS,WARPS} size the ring, the CTAs per SM and the consumer
+// warps per CTA), f32 / contiguous rows / no exclude, pin or peer options.
+constexpr int kTmaProducers = 8;
+template <int FOLD, int kTmaConsumers>
+__global__ void __launch_bounds__((kTmaConsumers + 1) * 32) backup_tma_kernel(const colo_backup_args p, int n_stages,
+                                                                             uint32_t stage_bytes) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = p.S, A = p.A, nrows = p.nrows;
+  const uint32_t row_bytes = (uint32_t)A * S * 4;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)n_stages * stage_bytes);
+  uint64_t* empty = full + n_stages;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < n_stages; ++k) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gs_smem_u32(full + k)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gs_smem_u32(empty + k)) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long items = (long long)p.B * nrows;
+  const long long mine = (items - blockIdx.x + gridDim.x - 1) / gridDim.x;  // items blockIdx.x, + gridDim.x, ...
+  if (warp == kTmaConsumers) {  // producer warp: kTmaProducers lanes, lane l re-arms the stages k = l (mod kTmaProducers)
+    // (one lane alone -- wait on `empty`, proxy fence, expect_tx, bulk copy -- re-arms a stage every ~0.45 us: measured,
+    // 2.6 TB/s with one CTA per SM; the lanes issue independently)
+    if (lane < kTmaProducers) {
+      for (long long k = lane; k < mine; k += kTmaProducers) {
+        const int slot = (int)(k % n_stages);
+        if (k >= n_stages) {
+          gs_bar_wait(empty + slot, (uint32_t)(((k / n_stages) - 1) & 1));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the stage before the async write
+        }
+        const long long it = blockIdx.x + k * gridDim.x;
+        const int b = (int)(it / nrows);
+        const int sl = (int)(it - (long long)b * nrows);
+        if (p.active != nullptr && p.active[b] == 0) {  // nothing to stage: the consumer only carries V forward
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs_smem_u32(full + slot)) : "memory");
+          continue;
+        }
+        gs_bulk_load(smem_raw + (size_t)slot * stage_bytes, p.T + (size_t)b * p.t_stride + (size_t)sl * A * S, row_bytes,
+                     full + slot);
+      }
+    }
+    return;
+  }
+  const float* V_in = reinterpret_cast<const float*>(p.V_in);
+  float* V_out = reinterpret_cast<float*>(p.V_out);
+  float* Q = reinterpret_cast<float*>(p.Q);
+  const float gamma = (float)p.gamma;
+  const int S4 = S >> 2;
+  for (long long k = warp; k < mine; k += kTmaConsumers) {
+    const int slot = (int)(k % n_stages);
+    const long long it = blockIdx.x + k * gridDim.x;
+    const int b = (int)(it / nrows);
+    const int sl = (int)(it - (long long)b * nrows);
+    const int s = p.row0 + sl;
+    const float* Vb = V_in + (size_t)b * p.v_in_stride;
+    gs_bar_wait(full + slot, (uint32_t)((k / n_stages) & 1));
+    if (p.active != nullptr && p.active[b] == 0) {
+      if (lane == 0 && V_out != nullptr) V_out[(size_t)b * p.v_out_stride + s] = Vb[s];
+    } else {
+      const float* Ts = reinterpret_cast<const float*>(smem_raw + (size_t)slot * stage_bytes);
+      float folded = FOLD == COLO_FOLD_MIN ? INFINITY : (FOLD == COLO_FOLD_MAX ? -INFINITY : 0.f);
+      for (int a0 = 0; a0 < A; a0 += kAT) {
+        const int na = min(kAT, A - a0);
+        float acc[kAT];
+#pragma unroll
+        for (int i = 0; i < kAT; ++i) acc[i] = 0.f;
+        for (int j4 = lane; j4 < S4; j4 += 32) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(Vb) + j4);
+#pragma unroll
+          for (int i = 0; i < kAT; ++i)
+            if (i < na) {
+              const float4 t = *reinterpret_cast<const float4*>(Ts + (size_t)(a0 + i) * S + 4 * j4);
+              acc[i] += t.x * v.x + t.y * v.y + t.z * v.z + t.w * v.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kAT; ++i) acc[i] = warp_sum(acc[i]);
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < kAT; ++i)
+            if (i < na) {
+              const int a = a0 + i;
+              const float r = p.R ? p.R[(size_t)b * p.r_stride + (size_t)sl * A + a] : (float)p.r_const;
+              const float q = r + gamma * acc[i];
+              if (Q) Q[(size_t)b * p.q_stride + (size_t)sl * A + a] = q;
+              if (FOLD == COLO_FOLD_MAX) folded = q > folded ? q : folded;
+              if (FOLD == COLO_FOLD_MIN) folded = q < folded ? q : folded;
+              if (FOLD == COLO_FOLD_PI) folded += q * p.pi[(size_t)b * p.pi_stride + (size_t)sl * A + a];
+            }
+        }
+      }
+      if (lane == 0 && V_out != nullptr) {
+        float* vo = V_out + (size_t)b * p.v_out_stride + s;
+        const float old = p.resid_vs_out ? *vo : Vb[s];
+        *vo = folded;
+        if (p.resid != nullptr) {
+          const float d = fabsf(folded - old);
+          if (d > 0.f) atomic_max_nonneg(reinterpret_cast<unsigned int*>(p.resid) + b, d);
+        }
+        if (p.max_abs > 0.0 && p.overflow_flag &&
+            (p.overflow_signed ? (double)folded : fabs((double)folded)) > p.max_abs)
+          *p.overflow_flag = 1;
+      }
+    }
+    __syncwarp();  // every lane is done with the stage
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs_smem_u32(empty + slot)) : "memory");
+  }
+}
+
+// returns COLO_OK and *handled = 1 when the TMA-staged variant took the sweep
+static int launch_backup_tma(const colo_backup_args& p, cudaStream_t st, int* handled) {
+  *handled = 0;
+  static const char* env = getenv("COLO_BACKUP_TMA");
+  if (!env || env[0] == '0') return COLO_OK;
+  const size_t row_bytes = (size_t)p.A * p.S * 4;
+  if (p.exclude_index || p.pin_index || p.n_peers || p.v_action_stride != 0 || row_bytes % 16 || row_bytes > 32768 ||
+      p.S % 4 || (uintptr_t)p.T % 16 || p.t_stride % 4 || (uintptr_t)p.V_in % 16 || p.v_in_stride % 4)
+    return COLO_OK;
+  const long long items = (long long)p.B * p.nrows;
+  if (items < (long long)sm_count() * 64) return COLO_OK;
+  const uint32_t stage_bytes = (uint32_t)((row_bytes + 127) & ~(size_t)127);
+  static const int want = getenv("COLO_BACKUP_TMA_STAGES") ? atoi(getenv("COLO_BACKUP_TMA_STAGES")) : 24;
+  static const int ctas_per_sm = getenv("COLO_BACKUP_TMA_CTAS") ? atoi(getenv("COLO_BACKUP_TMA_CTAS")) : 1;
+  const size_t budget = (size_t)(227 * 1024) / ctas_per_sm - 2048;
+  int n_stages = (int)((budget - 1024) / stage_bytes);
+  if (n_stages > want) n_stages = want;
+  // every stage must belong to ONE producer lane (slot = k % n_stages, lane = k % kTmaProducers): a parity wait only
+  // tells the current phase from the previous one, so two lanes sharing a slot could run a whole phase apart
+  n_stages -= n_stages % kTmaProducers;
+  if (n_stages < 2) return COLO_OK;
+  const size_t smem = (size_t)n_stages * stage_bytes + (size_t)n_stages * 16 + 128;
+  const int grid = sm_count() * ctas_per_sm;
+  static const int ncons_env = getenv("COLO_BACKUP_TMA_WARPS") ? atoi(getenv("COLO_BACKUP_TMA_WARPS")) : 8;
+  // a consumer warp owns every ncons-th stage: more consumers than stages would wait on a stage that was never filled
+  const int ncons = n_stages >= 16 ? ncons_env : 8;
+  if (n_stages < 8) return COLO_OK;
+#define COLO_TMA(FOLD)                                                                                   \
+  if (ncons >= 16) {                                                                                     \
+    auto k = backup_tma_kernel<FOLD, 16>;                                                                \
+    const int es = ensure_dynamic_smem((const void*)k, smem);                                            \
+    if (es != COLO_OK) return es;                                                                        \
+    k<<<grid, 17 * 32, smem, st>>>(p, n_stages, stage_bytes);                                            \
+  } else {                                                                                               \
+    auto k = backup_tma_kernel<FOLD, 8>;                                                                 \
+    const int es = ensure_dynamic_smem((const void*)k, smem);                                            \
+    if (es != COLO_OK) return es;                                                                        \
+    k<<<grid, 9 * 32, smem, st>>>(p, n_stages, stage_bytes);                                             \
+  }
+  switch (p.fold) {
+    case COLO_FOLD_MAX: COLO_TMA(COLO_FOLD_MAX); break;
+    case COLO_FOLD_PI: COLO_TMA(COLO_FOLD_PI); break;
+    default: COLO_TMA(COLO_FOLD_MIN); break;
+  }
+#undef COLO_TMA
+  *handled = 1;
+  return check_launch("backup_tma_kernel");
+}
+
 template <typename TV, int FOLD, bool VEC>
 static int launch_backup_2(const colo_backup_args& p, bool group_cta, cudaStream_t st) {
   const long long items = (long long)p.B * p.nrows;
@@ -248,6 +414,11 @@ int launch_backup(const colo_backup_args* pp, void* stream) {
   // one warp per state while that still fills the machine; one CTA per state for few, long rows
   const long long items = (long long)p.B * p.nrows;
   const bool group_cta = (items < (long long)sm_count() * 64) && ((long long)p.S * p.A >= 4096);
+  if (sizeof(TV) == 4 && vec && !group_cta) {
+    int handled = 0;
+    const int r = launch_backup_tma(p, st, &handled);
+    if (r != COLO_OK || handled) return r;
+  }
 #define COLO_DISPATCH(FOLD)                                                            \
   return vec ? launch_backup_2<TV, FOLD, true>(p, group_cta, st) : launch_backup_2<TV, FOLD, false>(p, group_cta, st)
   switch (p.fold) {

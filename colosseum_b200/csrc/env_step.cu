@@ -15,6 +15,11 @@
 #include <string.h>
 #include <time.h>
 
+#include <cuda.h>
+
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace colo {
@@ -43,6 +48,9 @@ struct StepIO {
   float* discount;                  // dm_env discount of the emitted TimeStep (1 MID, 0 LAST, NaN FIRST) or null
   int n_steps;  // > 1: that many consecutive steps in ONE launch (random actions; Philox counter t, t+1, ...)
   int io_compact;  // action u8[N] in, obs i16[N] out (colo_env_batch.io_compact)
+  // queued pipeline (colo_env_pipeline_run_queued): the launch is a node of a replayed CUDA graph, so the Philox step
+  // counter cannot be a baked kernel argument: t = t + *t_dev (device word rewritten in stream order before each replay)
+  const unsigned long long* t_dev;
   // persistent step server (colo_env_server_*; SERVER kernels only): the kernel stays resident and runs one pass per
   // doorbell value posted by the host instead of one pass per launch
   const unsigned long long* srv_doorbell;  // pinned host, written by the host: index of the newest requested step
@@ -52,6 +60,8 @@ struct StepIO {
   unsigned long long srv_seq0;             // steps served before this launch
   unsigned long long srv_idle_ns;          // the server retires after this long without a doorbell
 };
+
+__device__ __forceinline__ unsigned long long step_t0(const StepIO& io) { return io.t_dev ? io.t + *io.t_dev : io.t; }
 
 constexpr unsigned long long kSrvExit = ~0ULL, kSrvLapsed = ~0ULL - 1;
 #ifndef COLO_SRV_POLL_NS
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kernel(const colo
   constexpr bool F32U = sizeof(TC) == 4;
 
   for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
-  unsigned long long t_pass = io.t;
+  unsigned long long t_pass = step_t0(io);
   if (SERVER) {
     if (!server_wait(io, pass)) return;
     t_pass += pass - io.srv_seq0 - 1;
@@ -376,7 +386,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_short_kernel(cons
   constexpr bool F32U = sizeof(TC) == 4;
 
   for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
-  unsigned long long t_pass = io.t;
+  unsigned long long t_pass = step_t0(io);
   if (SERVER) {
     if (!server_wait(io, pass)) return;
     t_pass += pass - io.srv_seq0 - 1;
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_dense_kary_kernel(const
   const TC* __restrict__ coarse = tb.cdf_mid ? reinterpret_cast<const TC*>(tb.cdf_coarse) : nullptr;
   constexpr bool F32U = sizeof(TC) == 4;
   for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
-  unsigned long long t_pass = io.t;
+  unsigned long long t_pass = step_t0(io);
   if (SERVER) {
     if (!server_wait(io, pass)) return;
     t_pass += pass - io.srv_seq0 - 1;
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(kLeanThreads) env_step_kary_lean_kernel(const 
     else
       a = io.srv_go ? __ldcv(io.action + e) : io.action[e];
   }
-  const Philox4 w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, io.t);
+  const Philox4 w = philox4x32_10(io.seed, io.env0 + (uint64_t)e, step_t0(io));
   bool bad = false;
   if ((unsigned)a >= (unsigned)A) {
     if (io.status) *io.status = COLO_BAD_ACTION;
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__(kStepThreads) env_step_succ_kernel(const colo_
   // round the loop bound up to whole warps: finish_env uses warp collectives
   const long long n_pad = (io.N + 31) & ~31LL;
   for (unsigned long long pass = io.srv_seq0 + 1;; ++pass) {  // SERVER: one pass per doorbell; else exactly one pass
-  unsigned long long t_pass = io.t;
+  unsigned long long t_pass = step_t0(io);
   if (SERVER) {
     if (!server_wait(io, pass)) return;
     t_pass += pass - io.srv_seq0 - 1;
@@ -1063,6 +1073,297 @@ int colo_env_pipeline_run(colo_env_stepper* const* steppers, int n_groups, const
         if (r != COLO_OK) return r;
       }
     }
+  return COLO_OK;
+}
+
+
+// One host thread per group: every group runs its own recv / send loop (stream sync, on_timestep, launch), so a group's
+// cycle -- launch latency, PCIe reads and writes of the kernel, completion latency -- overlaps with every other group's
+// instead of being stepped through by one thread.  Per-group order of events and TimeSteps are those of
+// colo_env_pipeline_run; on_timestep is called on the group's own thread, concurrently for different groups.
+int colo_env_pipeline_run_threads(colo_env_stepper* const* steppers, int n_groups, const int* const* action_ring, int ring,
+                                  unsigned long long t0, int n_steps, colo_env_pipeline_callback on_timestep, void* user) {
+  COLO_ARG_CHECK(steppers && action_ring && n_groups >= 1 && ring >= 1 && n_steps >= 1, "steppers, action_ring, n_groups, ring, n_steps");
+  int dev = 0;
+  COLO_CUDA_TRY(cudaGetDevice(&dev));
+  std::vector<int> rcs((size_t)n_groups, COLO_OK);
+  auto group_loop = [&](int g) {
+    if (cudaSetDevice(dev) != cudaSuccess) {
+      rcs[g] = COLO_ERR_CUDA;
+      return;
+    }
+    int r = colo_env_stepper_launch(steppers[g], action_ring[g], t0);
+    for (int i = 1; i <= n_steps && r == COLO_OK; ++i) {
+      if (cudaStreamSynchronize((cudaStream_t)steppers[g]->stream) != cudaSuccess) {
+        r = COLO_ERR_CUDA;
+        break;
+      }
+      if (on_timestep) on_timestep(user, g, i - 1);
+      if (i < n_steps) r = colo_env_stepper_launch(steppers[g], action_ring[(size_t)(i % ring) * n_groups + g], t0 + (unsigned long long)i);
+    }
+    rcs[g] = r;
+  };
+  std::vector<std::thread> workers;
+  for (int g = 1; g < n_groups; ++g) workers.emplace_back(group_loop, g);
+  group_loop(0);
+  for (auto& w : workers) w.join();
+  for (int g = 0; g < n_groups; ++g)
+    if (rcs[g] != COLO_OK) {
+      colo::set_error("colo_env_pipeline_run_threads: group %d failed (status %d)", g, rcs[g]);
+      return rcs[g];
+    }
+  return COLO_OK;
+}
+
+// ---- queued pipeline ---------------------------------------------------------------------------------------------------
+// colo_env_pipeline_run pays a stream synchronisation and a launch on the host for every group-step (~10 us per
+// group-step: the measured bound of the end-to-end step).  Here the per-step handshake is two words in pinned host memory
+// and the GPU's own front end does the waiting: every group's stream holds, for step i,
+//     wait32(go[g] == i % L + 1)  ->  step kernel  ->  write32(done[g] = i % L + 1)
+// (stream memory operations, cuStreamWaitValue32 / cuStreamWriteValue32), enqueued AHEAD of time -- as replays of one
+// CUDA graph of L steps per group when graphs are on, or one triple at a time during the host's waits.  In the steady
+// state a group-step costs the host one flag store and one flag poll; no CUDA call is on the critical path.
+constexpr int kMaxPipelineGroups = 8;
+constexpr int kFlagStride = 32;  // u32 words between flags: go[g] and done[g] on their own 128-byte lines
+
+typedef CUresult (*colo_stream_value32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct StreamMemOps {
+  colo_stream_value32_fn wait32 = nullptr, write32 = nullptr;
+};
+static const StreamMemOps& stream_mem_ops() {
+  // resolved through the runtime: the library carries no link dependency on libcuda (it must load on a CPU-only box)
+  static const StreamMemOps ops = [] {
+    StreamMemOps r;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      r.wait32 = (colo_stream_value32_fn)f;
+    f = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      r.write32 = (colo_stream_value32_fn)f;
+    (void)cudaGetLastError();
+    return r;
+  }();
+  return ops;
+}
+
+struct colo_env_pipeline {
+  int G;
+  colo_env_stepper* steppers[kMaxPipelineGroups];  // borrowed
+  cudaStream_t streams[kMaxPipelineGroups];        // own non-blocking streams: nothing else may ever wait behind a flag
+  unsigned* flags;                                 // pinned host: go[g] = flags[(2g) * kFlagStride], done[g] = flags[(2g+1) * kFlagStride]
+  unsigned long long* t_dev;                       // device: one Philox step-counter base per group (graph replays)
+  // one instantiated graph of L steps per group, valid for one action ring
+  int L, ring;
+  const int** ring_ptrs;
+  cudaGraphExec_t exec[kMaxPipelineGroups];
+  int graphs_failed;
+};
+
+static volatile unsigned* pl_go(colo_env_pipeline* p, int g) { return p->flags + (size_t)(2 * g) * kFlagStride; }
+static volatile unsigned* pl_done(colo_env_pipeline* p, int g) { return p->flags + (size_t)(2 * g + 1) * kFlagStride; }
+
+static int pl_launch(colo_env_pipeline* p, int g, const int* action, unsigned long long t, const unsigned long long* t_dev) {
+  colo_env_stepper* h = p->steppers[g];
+  colo::StepIO io = h->io;
+  io.action = const_cast<int*>(action);
+  io.t = t;
+  io.t_dev = t_dev;
+  if (h->mode == 0) return colo::launch_dense<float, false>(&h->tb, io, p->streams[g]);
+  if (h->mode == 1) return colo::launch_dense<double, false>(&h->tb, io, p->streams[g]);
+  return colo::launch_succ<false>(&h->tb, io, p->streams[g]);
+}
+
+#define COLO_CU_TRY(expr)                                                               \
+  do {                                                                                  \
+    CUresult _r = (expr);                                                               \
+    if (_r != CUDA_SUCCESS) {                                                           \
+      colo::set_error("%s failed: CUresult %d (%s:%d)", #expr, (int)_r, __FILE__, __LINE__); \
+      return COLO_ERR_CUDA;                                                             \
+    }                                                                                   \
+  } while (0)
+
+// wait(go == v) -> step kernel -> write(done = v) on group g's stream
+static int pl_enqueue_step(colo_env_pipeline* p, int g, unsigned v, const int* action, unsigned long long t,
+                           const unsigned long long* t_dev) {
+  const StreamMemOps& mo = stream_mem_ops();
+  COLO_CU_TRY(mo.wait32((CUstream)p->streams[g], (CUdeviceptr)(uintptr_t)pl_go(p, g), v, CU_STREAM_WAIT_VALUE_EQ));
+  const int r = pl_launch(p, g, action, t, t_dev);
+  if (r != COLO_OK) return r;
+  COLO_CU_TRY(mo.write32((CUstream)p->streams[g], (CUdeviceptr)(uintptr_t)pl_done(p, g), v, CU_STREAM_WRITE_VALUE_DEFAULT));
+  return COLO_OK;
+}
+
+static void pl_drop_graphs(colo_env_pipeline* p) {
+  for (int g = 0; g < p->G; ++g)
+    if (p->exec[g]) {
+      cudaGraphExecDestroy(p->exec[g]);
+      p->exec[g] = nullptr;
+    }
+  free(p->ring_ptrs);
+  p->ring_ptrs = nullptr;
+  p->L = p->ring = 0;
+}
+
+// L steps of every group as one graph per group (stream capture of the same triples); the kernels read the step counter
+// as j + *t_dev, the action pointers repeat with period `ring` (L is a multiple of it)
+static int pl_build_graphs(colo_env_pipeline* p, const int* const* action_ring, int ring) {
+  const size_t n = (size_t)ring * p->G;
+  if (p->exec[0] && p->ring == ring && memcmp(p->ring_ptrs, action_ring, n * sizeof(int*)) == 0) return COLO_OK;
+  pl_drop_graphs(p);
+  if (ring > 256) return COLO_ERR_ARG;  // a graph of a multiple of `ring` steps would be unreasonably long
+  const int L = ring * ((64 + ring - 1) / ring) < 2 ? 2 : ring * ((64 + ring - 1) / ring);
+  for (int g = 0; g < p->G; ++g) {
+    COLO_CUDA_TRY(cudaStreamBeginCapture(p->streams[g], cudaStreamCaptureModeRelaxed));
+    int r = COLO_OK;
+    for (int j = 0; j < L && r == COLO_OK; ++j)
+      r = pl_enqueue_step(p, g, (unsigned)j + 1, action_ring[(size_t)(j % ring) * p->G + g], (unsigned long long)j, p->t_dev + g);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(p->streams[g], &graph);
+    if (r == COLO_OK && e == cudaSuccess && graph) {
+      if (cudaGraphInstantiate(&p->exec[g], graph, 0) != cudaSuccess) r = COLO_ERR_CUDA;
+    } else if (r == COLO_OK) {
+      r = COLO_ERR_CUDA;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (r != COLO_OK) {
+      (void)cudaGetLastError();
+      pl_drop_graphs(p);
+      return r;
+    }
+  }
+  p->ring_ptrs = (const int**)malloc(n * sizeof(int*));
+  memcpy(p->ring_ptrs, action_ring, n * sizeof(int*));
+  p->L = L;
+  p->ring = ring;
+  return COLO_OK;
+}
+
+int colo_env_pipeline_create(colo_env_stepper* const* steppers, int n_groups, colo_env_pipeline** out) {
+  COLO_ARG_CHECK(steppers && out && n_groups >= 1 && n_groups <= kMaxPipelineGroups, "steppers, out, 1 <= n_groups <= 8");
+  const StreamMemOps& mo = stream_mem_ops();
+  if (!mo.wait32 || !mo.write32) {
+    colo::set_error("colo_env_pipeline_create: the driver does not offer cuStreamWaitValue32 / cuStreamWriteValue32");
+    return COLO_ERR_CUDA;
+  }
+  colo_env_pipeline* p = (colo_env_pipeline*)calloc(1, sizeof(colo_env_pipeline));
+  COLO_ARG_CHECK(p != nullptr, "out of host memory");
+  p->G = n_groups;
+  for (int g = 0; g < n_groups; ++g) p->steppers[g] = steppers[g];
+  cudaError_t e = cudaHostAlloc((void**)&p->flags, (size_t)2 * n_groups * kFlagStride * sizeof(unsigned), cudaHostAllocPortable);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->t_dev, sizeof(unsigned long long) * 2 * n_groups);
+  for (int g = 0; g < n_groups && e == cudaSuccess; ++g) e = cudaStreamCreateWithFlags(&p->streams[g], cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    colo::set_error("colo_env_pipeline_create: %s", cudaGetErrorString(e));
+    colo_env_pipeline_destroy(p);
+    return COLO_ERR_CUDA;
+  }
+  memset(p->flags, 0, (size_t)2 * n_groups * kFlagStride * sizeof(unsigned));
+  *out = p;
+  return COLO_OK;
+}
+
+void colo_env_pipeline_destroy(colo_env_pipeline* p) {
+  if (!p) return;
+  pl_drop_graphs(p);
+  for (int g = 0; g < p->G; ++g)
+    if (p->streams[g]) cudaStreamDestroy(p->streams[g]);
+  if (p->t_dev) cudaFree(p->t_dev);
+  if (p->flags) cudaFreeHost(p->flags);
+  free(p);
+}
+
+int colo_env_pipeline_run_queued(colo_env_pipeline* p, const int* const* action_ring, int ring, unsigned long long t0,
+                                 int n_steps, colo_env_pipeline_callback on_timestep, void* user, int use_graph) {
+  COLO_ARG_CHECK(p && action_ring && ring >= 1 && n_steps >= 1, "pipeline, action_ring, ring, n_steps");
+  const int G = p->G;
+  const StreamMemOps& mo = stream_mem_ops();
+  // whatever was enqueued on the groups' own streams (reset, earlier steps) comes first
+  for (int g = 0; g < G; ++g) COLO_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)p->steppers[g]->stream));
+  if (use_graph && !p->graphs_failed && n_steps >= 2 * 64) {
+    if (pl_build_graphs(p, action_ring, ring) != COLO_OK) p->graphs_failed = 1;  // the triples still work one at a time
+  }
+  const bool graphs = use_graph && !p->graphs_failed && p->exec[0] != nullptr && n_steps >= p->L;
+  const int L = graphs ? p->L : (1 << 30);  // flag values are i % L + 1
+  const int lead = graphs ? L / 2 + 1 : 3;  // group-steps kept enqueued ahead of the newest finished one
+  for (int g = 0; g < G; ++g) {
+    *pl_go(p, g) = 0;
+    *pl_done(p, g) = 0;
+  }
+  __atomic_thread_fence(__ATOMIC_SEQ_CST);
+  int enq[kMaxPipelineGroups] = {0}, fin[kMaxPipelineGroups] = {0};
+  int rc = COLO_OK;
+  auto top_up = [&](int g) -> int {
+    while (enq[g] < n_steps && enq[g] - fin[g] < lead) {
+      const int i = enq[g];
+      if (graphs && i % L == 0 && n_steps - i >= L) {
+        const unsigned long long base = t0 + (unsigned long long)i;
+        unsigned* td = reinterpret_cast<unsigned*>(p->t_dev + g);
+        COLO_CU_TRY(mo.write32((CUstream)p->streams[g], (CUdeviceptr)(uintptr_t)td, (unsigned)base, CU_STREAM_WRITE_VALUE_DEFAULT));
+        COLO_CU_TRY(mo.write32((CUstream)p->streams[g], (CUdeviceptr)(uintptr_t)(td + 1), (unsigned)(base >> 32), CU_STREAM_WRITE_VALUE_DEFAULT));
+        COLO_CUDA_TRY(cudaGraphLaunch(p->exec[g], p->streams[g]));
+        colo::count_launch((unsigned long long)L);
+        enq[g] += L;
+      } else {
+        const int r = pl_enqueue_step(p, g, (unsigned)(i % L) + 1, action_ring[(size_t)(i % ring) * G + g],
+                                      t0 + (unsigned long long)i, nullptr);
+        if (r != COLO_OK) return r;
+        enq[g] += 1;
+      }
+    }
+    return COLO_OK;
+  };
+  for (int g = 0; g < G && rc == COLO_OK; ++g) rc = top_up(g);
+  if (rc == COLO_OK)
+    for (int g = 0; g < G; ++g) __atomic_store_n(const_cast<unsigned*>(pl_go(p, g)), 1u, __ATOMIC_RELEASE);  // step 0's actions are in place
+  bool stuck = false;
+  for (int i = 1; i <= n_steps && rc == COLO_OK && !stuck; ++i)
+    for (int g = 0; g < G; ++g) {
+      const unsigned want = (unsigned)((i - 1) % L) + 1;
+      unsigned long long spins = 0;
+      struct timespec w0 = {0, 0};
+      while (__atomic_load_n(const_cast<unsigned*>(pl_done(p, g)), __ATOMIC_ACQUIRE) != want) {
+        if ((++spins & 0xffff) == 0) {  // look at the clock every 65,536 polls only
+          struct timespec now;
+          clock_gettime(CLOCK_MONOTONIC, &now);
+          if (w0.tv_sec == 0 && w0.tv_nsec == 0) w0 = now;
+          if ((now.tv_sec - w0.tv_sec) + (now.tv_nsec - w0.tv_nsec) * 1e-9 > 10.0) {
+            stuck = true;
+            break;
+          }
+        }
+      }
+      if (stuck) break;
+      fin[g] = i;  // step i-1 of group g is in host memory
+      if ((rc = top_up(g)) != COLO_OK) break;
+      if (on_timestep) on_timestep(user, g, i - 1);
+      if (i < n_steps) __atomic_store_n(const_cast<unsigned*>(pl_go(p, g)), (unsigned)(i % L) + 1, __ATOMIC_RELEASE);
+    }
+  if (stuck || rc != COLO_OK) {
+    // never leave a stream blocked behind a flag: feed every group the values it waits for until the queues are empty
+    // (the steps run with whatever actions are in the ring; the call reports the failure)
+    struct timespec d0;
+    clock_gettime(CLOCK_MONOTONIC, &d0);
+    for (;;) {
+      bool idle = true;
+      for (int g = 0; g < G; ++g) {
+        if (cudaStreamQuery(p->streams[g]) == cudaSuccess) continue;
+        idle = false;
+        const unsigned v = __atomic_load_n(const_cast<unsigned*>(pl_done(p, g)), __ATOMIC_ACQUIRE);
+        __atomic_store_n(const_cast<unsigned*>(pl_go(p, g)), v % (unsigned)L + 1, __ATOMIC_RELEASE);
+      }
+      struct timespec now;
+      clock_gettime(CLOCK_MONOTONIC, &now);
+      if (idle || (now.tv_sec - d0.tv_sec) > 20) break;
+    }
+    (void)cudaGetLastError();
+    if (stuck) {
+      colo::set_error("colo_env_pipeline_run_queued: no progress for 10 s (streams sharing a hardware queue?); drained");
+      return COLO_ERR_CUDA;
+    }
+    return rc;
+  }
+  for (int g = 0; g < G; ++g) COLO_CUDA_TRY(cudaStreamSynchronize(p->streams[g]));
   return COLO_OK;
 }
 

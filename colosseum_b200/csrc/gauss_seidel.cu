@@ -17,7 +17,7 @@
 
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tma_device.cuh"
 
 namespace colo {
 
@@ -158,27 +158,6 @@ __global__ void __launch_bounds__(256) gs_solve_kernel(const GsArgs p) {
 // (measured on C4: 4.4 TB/s); here the warp only ever waits for a stage that was requested NST-1 states ago.
 // Warps take MDP instances from a device counter (no wave quantisation when B is not a multiple of the warps in flight).
 constexpr int kGsStages = 3;
-
-__device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void gs_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem_u32(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   gs_smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(gs_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void gs_bar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "GSW_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra GSD_%=;\n\t"
-      "bra GSW_%=;\n\t"
-      "GSD_%=:\n\t"
-      "}" ::"r"(gs_smem_u32(bar)), "r"(parity)
-      : "memory");
-}
 
 template <typename TV>
 __global__ void __launch_bounds__(256) gs_solve_tma_kernel(const GsArgs p, int* __restrict__ next_instance) {

@@ -591,6 +591,38 @@ int colo_env_pipeline_run(colo_env_stepper* const* steppers, int n_groups, const
                           unsigned long long t0, int n_steps, colo_env_pipeline_callback on_timestep, void* user);
 
 /*
+ * colo_env_pipeline_run_threads -- colo_env_pipeline_run with one host thread per group (the caller's thread runs group 0):
+ * a group's cycle (launch latency, the kernel's PCIe reads and writes, completion latency, on_timestep) overlaps with
+ * every other group's.  Same per-group order of events, same Philox counters, bit-identical TimeSteps; on_timestep is
+ * called on the group's own thread, concurrently for different groups (a host agent with per-group state).
+ */
+int colo_env_pipeline_run_threads(colo_env_stepper* const* steppers, int n_groups, const int* const* action_ring, int ring,
+                                  unsigned long long t0, int n_steps, colo_env_pipeline_callback on_timestep, void* user);
+
+/*
+ * Queued pipeline -- the same n_steps steps of every env of the groups as colo_env_pipeline_run (same recv / send order,
+ * same Philox counters, bit-identical TimeSteps), without a stream synchronisation and a launch on the host per
+ * group-step.  The handshake of a group-step is two 32-bit words in pinned host memory: on the group's (library-owned,
+ * non-blocking) stream step i is   wait (go[g] == i % L + 1) -> step kernel -> write (done[g] = i % L + 1)   with the
+ * wait and the write done by the GPU front end (stream memory operations, cuStreamWaitValue32 / cuStreamWriteValue32,
+ * resolved at run time: no link dependency on libcuda), enqueued ahead of time.  The host loop per group-step is: spin
+ * on done[g], on_timestep(user, group, step) -- the host agent reads the TimeStep and writes the next actions --, store
+ * go[g].  use_graph != 0: the triples of L consecutive steps (L a multiple of `ring`, >= 64) are one instantiated CUDA
+ * graph per group, replayed every L steps (the kernels then read the Philox counter as node index + a device word the
+ * library rewrites in stream order before each replay); otherwise, and for the last n_steps % L steps, the triples
+ * are enqueued one at a time, three group-steps ahead.  The action ring must hold pinned buffers (read over PCIe by
+ * the kernels) and, with graphs, stay the same between calls for the graphs to be reused.  Fails with COLO_ERR_CUDA --
+ * after feeding the queued waits so that no stream stays blocked -- if no step finishes for 10 s.
+ * Reference path: BaseMDP.step (colosseum/mdp/base.py:1279-1317) driven by a host agent (MDPLoop,
+ * colosseum/experiment/agent_mdp_interaction.py:236-298).
+ */
+typedef struct colo_env_pipeline colo_env_pipeline;
+int colo_env_pipeline_create(colo_env_stepper* const* steppers, int n_groups, colo_env_pipeline** out);
+int colo_env_pipeline_run_queued(colo_env_pipeline* p, const int* const* action_ring, int ring, unsigned long long t0,
+                                 int n_steps, colo_env_pipeline_callback on_timestep, void* user, int use_graph);
+void colo_env_pipeline_destroy(colo_env_pipeline* p);
+
+/*
  * Step server -- BaseMDP.step (base.py:1279-1317) for an agent living on the host, without a launch and a stream
  * synchronisation per step.  colo_env_server_start launches the step kernel of `mode` (0 dense f32 rows, 1 dense f64
  * rows, 2 successor tables; auto_reset on, Philox uniforms) as a PERSISTENT kernel on `stream` (which must be a

@@ -675,6 +675,65 @@ def test_native_pipeline_loop_is_identical(bm):
     assert torch.equal(a.get_visitation_counts(), b.get_visitation_counts())
 
 
+def test_queued_pipeline_is_identical(bm):
+    """colo_env_pipeline_run_queued (stream memory operations instead of a stream sync + launch per group-step; one at a
+    time and as replayed CUDA graphs of 64 steps) == colo_env_pipeline_run, bit for bit -- int32 and compact I/O, three
+    groups of uneven sizes, step counts that are not multiples of the graph length, two calls in a row, the variant with
+    one host thread per group (colo_env_pipeline_run_threads), and a host agent (ctypes callback) that derives every action from the TimeStep it has just been handed."""
+    import ctypes as C
+
+    import torch
+
+    tb = MDPTables.from_golden(load_instance("c2_deepsea30_prand"))
+    N, G = 6000 + 5, 3
+    for compact in (False, True):
+        gen = torch.Generator().manual_seed(5)
+        envs = [bm.PipelinedBatchedMDP(tb, N, groups=G, seed=21, compact_io=compact) for _ in range(4)]
+        for e in envs:
+            e.reset()
+        ring = [[torch.randint(0, tb.A, (n,), dtype=torch.int32, generator=gen).to(envs[0].shards[0].action_dtype).pin_memory()
+                 for n in envs[0].sizes] for _ in range(8)]
+        for K in (5, 64 * 3 + 17, 130):
+            ref = envs[0].run_native(ring, K)
+            for e, graph in ((envs[1], False), (envs[2], True), (envs[3], "threads")):
+                out = e.run_native(ring, K, threads=True) if graph == "threads" else e.run_queued(ring, K, graph=graph)
+                for k in range(G):
+                    for x, y in zip(ref[k], out[k]):
+                        assert np.array_equal(x.numpy(), y.numpy(), equal_nan=True), (compact, K, graph, k)
+                    assert torch.equal(envs[0].shards[k].state, e.shards[k].state) and envs[0].shards[k].t == e.shards[k].t
+                assert torch.equal(envs[0].get_visitation_counts(), e.get_visitation_counts())
+
+    # a host agent in the loop: the action of step i+1 is a function of the observation of step i
+    cb_t = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)
+    finals = []
+    for runner in ("native", "queued", "graph", "threads"):
+        env = bm.PipelinedBatchedMDP(tb, 2048, groups=2, seed=9)
+        env.reset()
+        acts = [torch.zeros(n, dtype=torch.int32).pin_memory() for n in env.sizes]
+        seen = []
+
+        def agent(user, g, step, env=env, acts=acts, seen=seen):
+            obs = env.shards[g].obs.numpy()
+            seen.append((g, step, int(obs.sum())))
+            acts[g].numpy()[:] = (obs + step) % tb.A
+
+        cb = cb_t(agent)
+        K = 200
+        if runner in ("native", "threads"):
+            env.run_native([acts], K, on_timestep=cb, threads=runner == "threads")
+        else:
+            env.run_queued([acts], K, on_timestep=cb, graph=runner == "graph")
+        if runner == "threads":  # one host thread per group: only the order within a group is defined
+            seen.sort(key=lambda x: (x[1], x[0]))
+        else:
+            assert [x[:2] for x in seen[:4]] == [(0, 0), (1, 0), (0, 1), (1, 1)]
+        finals.append((list(seen), [sh.state.cpu().numpy().copy() for sh in env.shards]))
+        assert len(seen) == 2 * K
+    for other in finals[1:]:
+        assert other[0] == finals[0][0]
+        assert all(np.array_equal(a, b) for a, b in zip(other[1], finals[0][1]))
+
+
 def test_compact_host_io_is_identical(bm):
     """compact_io=True (uint8 actions in, int16 observations out: 8 instead of 13 bytes per env-step over PCIe) emits
     exactly the TimeSteps of the int32 host_io batch -- single batch, pipelined groups and the native loop -- on a
