@@ -201,6 +201,7 @@ PROTOTYPES = {
     "colo_solve_discounted_f64acc": (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _LL, _I, _P, _P, _P, _P, _P]),
     "colo_solve_discounted_gs_f32": (_I, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _LL, _I, _P, _P, _P, _P, _P]),
     "colo_solve_discounted_gs_f64acc": (_I, [_P, _P, _P, _I, _I, _I, _D, _D, _D, _LL, _I, _P, _P, _P, _P, _P]),
+    "colo_suite_release_caches": (_I, []),
     "colo_suite_run": (_I, [C.POINTER(SuiteInstance), _I, C.POINTER(SuiteConfig), C.POINTER(SuiteResult), _I]),
     "colo_continuous_form_values_f32": (_I, [_P, _P, _I, _I, _I, _D, _P, _P, _P, _I, _D, _I, _P, C.POINTER(C.c_double), _P]),
     "colo_continuous_form_values_f64acc": (_I, [_P, _P, _I, _I, _I, _D, _P, _P, _P, _I, _D, _I, _P, C.POINTER(C.c_double), _P]),

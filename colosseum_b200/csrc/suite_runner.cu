@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -34,14 +35,45 @@ __global__ void suite_iota_kernel(int* x, int n) {
   if (i < n) x[i] = i;
 }
 
+// Large tensors of an instance (T_epi, T_cf up to gigabytes, the diameter's work buffers) do not go through the
+// stream-ordered pool every time: a worker keeps its k-th large buffer from instance to instance (grow-only; the worker
+// runs its instances one after the other on ONE stream, so reuse is ordered).  Measured reason: with 8 workers carving
+// multi-gigabyte requests out of the shared pool, an instance that takes 10 ms alone sporadically took 0.3-1.6 s (the
+// pool grows / defragments under its lock and every other worker's allocation waits behind it).
+struct WorkerCache {
+  std::vector<std::pair<void*, size_t>> bufs;
+  int dev = -1;
+  void drop(cudaStream_t st) {
+    for (auto& b : bufs)
+      if (b.first) cudaFreeAsync(b.first, st);
+    bufs.clear();
+  }
+};
+constexpr size_t kCachedAllocBytes = (size_t)4 << 20;
+
 struct StreamArena {  // stream-ordered allocations of one instance, released together
   cudaStream_t st;
+  WorkerCache* cache;
+  size_t next_cached = 0;
   std::vector<void*> ptrs;
-  explicit StreamArena(cudaStream_t s) : st(s) {}
+  explicit StreamArena(cudaStream_t s, WorkerCache* c = nullptr) : st(s), cache(c) {}
   template <typename T>
   T* alloc(size_t n) {
     void* p = nullptr;
-    if (cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st) != cudaSuccess) return nullptr;
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    if (cache && bytes >= kCachedAllocBytes) {
+      if (next_cached == cache->bufs.size()) cache->bufs.emplace_back(nullptr, 0);
+      auto& slot = cache->bufs[next_cached++];
+      if (slot.second < bytes) {
+        if (slot.first) cudaFreeAsync(slot.first, st);
+        slot = {nullptr, 0};
+        const size_t cap = bytes + bytes / 4;
+        if (cudaMallocAsync(&p, cap, st) != cudaSuccess) return nullptr;
+        slot = {p, cap};
+      }
+      return (T*)slot.first;
+    }
+    if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) return nullptr;
     ptrs.push_back(p);
     return (T*)p;
   }
@@ -81,10 +113,11 @@ static int d2h_double(const double* d, double* h, cudaStream_t st) {
   return COLO_OK;
 }
 
-static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, cudaStream_t st, colo_suite_result* out) {
+static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, cudaStream_t st, WorkerCache* cache,
+                   colo_suite_result* out) {
   const int S = in.S, A = in.A, H = in.H, K = in.K;
   const size_t SA = (size_t)S * A;
-  StreamArena ar(st);
+  StreamArena ar(st, cache);
   cudaGetLastError();  // a failure of this thread's previous instance must not be reported against this one
   const double t0 = now_s();
   // ---------------------------------------------------------------- tables
@@ -150,6 +183,20 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
   suite_iota_kernel<<<(S + 255) / 256, 256, 0, st>>>(targets, S);
   SUITE_TRY(check_launch("suite_iota_kernel"));
   out->gaps = out->value_norm = out->diameter = out->diameter_sweeps = NAN;
+  // COLO_SUITE_VERBOSE: wall time of every phase of the instance on stderr (the stream is synchronised at each mark)
+  static const bool verbose = getenv("COLO_SUITE_VERBOSE") != nullptr;
+  double tm = t1;
+  char phases[512];
+  int plen = 0;
+  phases[0] = 0;
+  auto mark = [&](const char* what) {
+    if (!verbose) return;
+    cudaStreamSynchronize(st);
+    const double t = now_s();
+    plen += snprintf(phases + plen, sizeof(phases) - (size_t)plen, " %s %.1f", what, (t - tm) * 1e3);
+    if (plen > (int)sizeof(phases) - 32) plen = (int)sizeof(phases) - 32;
+    tm = t;
+  };
   if (H == 0) {
     // continuous MDP: T, R and discounted VI (base.py:635-647, :1042-1100)
     double* Q = ar.alloc<double>(SA);
@@ -158,6 +205,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
     SUITE_PTR(Q); SUITE_PTR(V); SUITE_PTR(work);
     long long iters = 0;
     SUITE_TRY(colo_solve_discounted_f64acc(T, R, nullptr, 1, S, A, gamma, eps, 0.0, 1000000, COLO_FOLD_MAX, Q, V, &iters, work, st));
+    mark("vi");
     SUITE_TRY(colo_gaps_f64(Q, V, nullptr, S, A, 0.1, scal, st));
     SUITE_TRY(d2h_double(scal, &out->gaps, st));
     if (in.deterministic) {
@@ -168,6 +216,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
       SUITE_TRY(colo_value_norm_f64acc(T, V, S, A, w2, scal + 1, st));
       SUITE_TRY(d2h_double(scal + 1, &out->value_norm, st));
     }
+    mark("gaps+norm");
     if (cfg.diameter) {
       void* w3 = ar.alloc<unsigned char>(colo_diameter_continuous_work_bytes(S, S, 1));
       SUITE_PTR(w3);
@@ -175,6 +224,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
       SUITE_TRY(colo_diameter_continuous_f64acc(T, targets, S, S, A, eps, 0.0, 1000000, w3, dh, st));
       out->diameter = dh[0];
       out->diameter_sweeps = dh[1];
+      mark("diameter");
     }
   } else {
     // episodic MDP: backward induction + reachable (h,s) pairs for the gaps (base.py:1018-1040), the episodic tensor for
@@ -184,11 +234,13 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
     double* V = ar.alloc<double>((size_t)(H + 1) * S);
     SUITE_PTR(Q); SUITE_PTR(V);
     SUITE_TRY(colo_episodic_f64acc(T, R, nullptr, 1, S, A, H, COLO_FOLD_MAX, 0.0, Q, V, st));
+    mark("episodic_vi");
     double* start_prob = ar.upload(in.start_prob, (size_t)in.n_start);
     float* T_epi = ar.alloc<float>((size_t)H * SA * S);
     unsigned char* reach = ar.alloc<unsigned char>((size_t)H * S);
     SUITE_PTR(start_prob); SUITE_PTR(T_epi); SUITE_PTR(reach);
     SUITE_TRY(colo_build_episodic_tensor(T, R, start_idx, start_prob, in.n_start, H, S, A, T_epi, nullptr, reach, st));
+    mark("T_epi");
     std::vector<unsigned char> mask((size_t)(H + 1) * S, 0);
     std::vector<int> pos((size_t)H * S, -1);
     for (int i = 0; i < n; ++i) {
@@ -199,6 +251,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
     SUITE_PTR(mask_d);
     SUITE_TRY(colo_gaps_f64(Q, V, mask_d, (long long)(H + 1) * S, A, 0.1, scal, st));
     SUITE_TRY(d2h_double(scal, &out->gaps, st));
+    mark("gaps");
     if (in.deterministic) {
       out->value_norm = 0.0;
     } else if ((size_t)4 * n * n * A <= cfg.max_cf_bytes) {
@@ -212,6 +265,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
       COLO_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
       SUITE_TRY(colo_build_continuous_form(T, R, node_h, node_s, n, pos_d, start_idx, start_prob, in.n_start, H, S, A, T_cf,
                                            R_cf, flag, st));
+      mark("T_cf");
       // V* of the continuous form from its structure (colo_continuous_form_values_*): the node at list position start_k
       std::vector<int> ph((size_t)in.n_start), ps((size_t)in.n_start);
       std::vector<float> p32((size_t)in.n_start);
@@ -232,6 +286,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
       SUITE_PTR(ph_d); SUITE_PTR(ps_d); SUITE_PTR(p_d); SUITE_PTR(V_hs); SUITE_PTR(V_cf);
       double cf_out[2] = {0, 0};
       SUITE_TRY(colo_continuous_form_values_f64acc(T, R, S, A, H, gamma, ph_d, ps_d, p_d, in.n_start, eps, 200, V_hs, cf_out, st));
+      mark("cf_values");
       suite_gather_nodes_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(V_hs, node_h, node_s, n, S, V_cf);
       SUITE_TRY(check_launch("suite_gather_nodes_kernel"));
       void* w2 = ar.alloc<unsigned char>(colo_value_norm_work_bytes(n, A, 1));
@@ -245,6 +300,7 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
         set_error("suite: a positive-probability successor is missing from the node list");
         return COLO_ERR_ARG;
       }
+      mark("cf_norm");
     }  // else: the reference raises "Its continuous form is too large" (mdp_creation.py:152-155): NaN
     if (cfg.diameter) {
       void* w3 = ar.alloc<unsigned char>(colo_diameter_episodic_work_bytes(S, H, S, A, 1));
@@ -253,17 +309,55 @@ static int run_one(const colo_suite_instance& in, const colo_suite_config& cfg, 
       SUITE_TRY(colo_diameter_episodic_f64acc(T_epi, targets, S, H, S, A, eps, 0.0, 1000000, w3, dh, st));
       out->diameter = dh[0];
       out->diameter_sweeps = dh[1];
+      mark("diameter");
     }
   }
-  ar.release();
+  // synchronise BEFORE the blocks go back to the pool: a block freed behind pending work can be handed to another
+  // worker's stream with a dependency on that work (the pool's "internal dependencies" reuse), i.e. the other
+  // instance would wait for this one's solves
   COLO_CUDA_TRY(cudaStreamSynchronize(st));
+  ar.release();
   out->hardness_s = now_s() - t1;
+  if (verbose)
+    fprintf(stderr, "[suite] S=%d A=%d H=%d nodes=%d step %.1f ms hardness %.1f ms:%s\n", S, A, H, in.n_nodes, out->step_s * 1e3,
+            out->hardness_s * 1e3, phases);
   return COLO_OK;
+}
+
+std::mutex& suite_run_mutex() {
+  static std::mutex m;
+  return m;
+}
+std::vector<WorkerCache>& suite_caches() {
+  static std::vector<WorkerCache> c;
+  return c;
 }
 
 }  // namespace colo
 
 extern "C" {
+
+int colo_suite_release_caches(void) {
+  std::lock_guard<std::mutex> run_lock(colo::suite_run_mutex());
+  int dev = 0;
+  COLO_CUDA_TRY(cudaGetDevice(&dev));
+  for (auto& c : colo::suite_caches()) {
+    if (c.dev >= 0 && cudaSetDevice(c.dev) == cudaSuccess) {
+      c.drop((cudaStream_t)0);
+      cudaStreamSynchronize((cudaStream_t)0);
+    }
+    c.bufs.clear();
+    c.dev = -1;
+  }
+  COLO_CUDA_TRY(cudaSetDevice(dev));
+  cudaMemPool_t mp;
+  if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+    cudaDeviceSynchronize();
+    cudaMemPoolTrimTo(mp, 0);  // colo_suite_run keeps freed blocks in the pool: hand them back to the device
+  }
+  cudaGetLastError();
+  return COLO_OK;
+}
 
 int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_config* cfg, colo_suite_result* out,
                    int n_workers) {
@@ -289,6 +383,9 @@ int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_conf
     if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
       unsigned long long thr = ~0ULL;
       cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+      // never let an allocation of one worker's stream wait for the pending work of another worker's stream
+      int no = 0;
+      cudaMemPoolSetAttribute(mp, cudaMemPoolReuseAllowInternalDependencies, &no);
       std::vector<size_t> need((size_t)n);
       for (int i = 0; i < n; ++i) {
         const size_t S = inst[i].S, A = inst[i].A, H = inst[i].H, nn = inst[i].n_nodes;
@@ -320,8 +417,23 @@ int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_conf
   std::atomic<int> first_error{COLO_OK};
   std::vector<std::thread> pool;
   const int W = n_workers < n ? n_workers : (n > 0 ? n : 1);
+  // the workers' large-buffer caches outlive the call (a warm-up pass leaves them filled); one call at a time
+  std::mutex& run_mutex = colo::suite_run_mutex();
+  std::vector<colo::WorkerCache>& caches = colo::suite_caches();
+  std::lock_guard<std::mutex> run_lock(run_mutex);
+  if ((int)caches.size() < W) caches.resize((size_t)W);
+  for (auto& c : caches)
+    if (c.dev != dev) {
+      if (c.dev >= 0 && cudaSetDevice(c.dev) == cudaSuccess) {
+        c.drop((cudaStream_t)0);
+        cudaStreamSynchronize((cudaStream_t)0);
+      }
+      c.bufs.clear();
+      c.dev = dev;
+    }
+  cudaSetDevice(dev);
   for (int w = 0; w < W; ++w)
-    pool.emplace_back([&, dev]() {
+    pool.emplace_back([&, dev, w]() {
       cudaSetDevice(dev);
       cudaStream_t st = nullptr;
       if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
@@ -332,7 +444,7 @@ int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_conf
         const int i = next.fetch_add(1);
         if (i >= n) break;
         memset(&out[i], 0, sizeof(out[i]));
-        const int r = colo::run_one(inst[i], *cfg, st, &out[i]);
+        const int r = colo::run_one(inst[i], *cfg, st, &caches[(size_t)w], &out[i]);
         out[i].status = r;
         if (r != COLO_OK) {
           strncpy(out[i].error, colo_last_error(), sizeof(out[i].error) - 1);

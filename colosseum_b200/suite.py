@@ -256,6 +256,13 @@ def run_many(work, n_workers=4, **kw):
         sys.setswitchinterval(old)
 
 
+def release_caches():
+    """frees the large device buffers colo_suite_run's workers keep between instances and calls"""
+    from . import _cabi
+
+    _cabi.check(_cabi.lib().colo_suite_release_caches(), "colo_suite_release_caches")
+
+
 def run_many_native(work, n_workers=8, n_envs=1024, n_steps=1000, diameter=True, max_cf_bytes=8 << 30, eps=1e-9):
     """The same C3 work items as `run_many`, scheduled by the library (colo_suite_run, csrc/suite_runner.cu): `n_workers`
     C++ host threads with one CUDA stream each run whole instances -- every step the public C-ABI entry point the Python

@@ -919,6 +919,11 @@ typedef struct {
 } colo_suite_result;
 int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_config* cfg, colo_suite_result* out,
                    int n_workers);
+/*
+ * colo_suite_release_caches -- colo_suite_run's workers keep their large device buffers (episodic tensor, continuous form,
+ * diameter work space) from one instance and one call to the next; this frees them (to the stream-ordered pool).
+ */
+int colo_suite_release_caches(void);
 
 #ifdef __cplusplus
 }
