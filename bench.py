@@ -797,9 +797,10 @@ def bench_c3_gpu(args, rank, world):
 
     work = sorted(((by_index[i % n_suite], 0) for i in my_ids), key=lambda w: -cost(w[0]))
     suite = mine
-    # the workers block in cudaStreamSynchronize (blocking-sync schedule inside colo_suite_run): 8 per GPU whatever the
-    # number of ranks sharing the host
-    workers = args.c3_workers or 8
+    # one spinning worker per core this rank may use, at most 8 (colo_suite_run spins in cudaStreamSynchronize when it has
+    # a core per worker and blocks otherwise; measured on 4 cores: 4 spinning workers 0.29-0.35 s per 128 instances,
+    # 8 blocking ones 0.31-0.45 s; on 32 cores 8 spinning workers 0.25 s)
+    workers = args.c3_workers or max(2, min(8, len(os.sched_getaffinity(0))))
     native = args.c3_runner == "native" and args.c3_precision == "f64"
     if native:
         # untimed warm-up: one short pass over every distinct (family, size) of the shard, so that module loading and

@@ -9,6 +9,7 @@
 // 125 / 169 / 120 / 116 instances/s).  Here the workers are C++ threads; every solver call is the public C ABI of
 // include/colosseum_b200.h, exactly what the Python path calls, so the numbers are the same numbers.
 #include <math.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -365,15 +366,25 @@ int colo_suite_run(const colo_suite_instance* inst, int n, const colo_suite_conf
   COLO_ARG_CHECK(cfg->n_envs >= 1 && cfg->n_steps >= 1 && cfg->eps > 0.0, "n_envs, n_steps, eps");
   int dev = 0;
   COLO_CUDA_TRY(cudaGetDevice(&dev));
-  // the workers spend their time waiting in cudaStreamSynchronize; the default schedule spins there, which turns
-  // n_workers x ranks waiting threads into as many busy cores.  Ask the runtime to block instead for the duration of
-  // this call (honoured when the primary context accepts a flag change; harmless otherwise).
+  // The workers spend their time waiting in cudaStreamSynchronize.  Spinning there (the default schedule) wakes a worker
+  // at once -- measured on 128 instances, 8 workers: 0.25 s spinning against 0.31-0.36 s with blocking waits, whose
+  // wake-up latency stretches the most expensive episodic instances (dozens of host round trips) from ~60 ms to ~230 ms --
+  // but n_workers x ranks spinning threads need as many cores.  So: spin when this process may run on at least n_workers
+  // cores (sched_getaffinity), otherwise ask the runtime to block for the duration of the call (honoured when the
+  // primary context accepts a flag change).  COLO_SUITE_SPIN=1 / COLO_SUITE_BLOCK=1 force either.
+  int cores = 0;
+  {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set);
+  }
+  const bool want_block = getenv("COLO_SUITE_BLOCK") != nullptr || (getenv("COLO_SUITE_SPIN") == nullptr && cores < n_workers);
   unsigned old_flags = 0;
   const bool have_flags = cudaGetDeviceFlags(&old_flags) == cudaSuccess;
-  const bool blocking = have_flags && getenv("COLO_SUITE_SPIN") == nullptr &&
+  const bool blocking = have_flags && want_block &&
                         cudaSetDeviceFlags((old_flags & ~(unsigned)cudaDeviceScheduleMask) | cudaDeviceScheduleBlockingSync) == cudaSuccess;
   cudaGetLastError();
-  if (getenv("COLO_SUITE_VERBOSE")) fprintf(stderr, "[colo_suite_run] blocking-sync schedule: %s\n", blocking ? "on" : "unavailable");
+  if (getenv("COLO_SUITE_VERBOSE")) fprintf(stderr, "[colo_suite_run] %d cores, %d workers: %s\n", cores, n_workers, blocking ? "blocking waits" : "spinning waits");
   // Warm the stream-ordered memory pool: every instance allocates its tensors with cudaMallocAsync (T_epi, T_cf: up
   // to gigabytes), and a pool that has to grow from the OS in the middle of the run stalls every worker (measured: the
   // first pass over a shard ran at a third of the rate of the second).  Keep freed blocks in the pool and reserve the
