@@ -20,7 +20,7 @@ for tag, pat in (("backup_kernel_f32_max_vec_warp", r"_ZN4colo13backup_kernelIfL
         print("symbol not found:", tag)
         continue
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", m.group(0), so], capture_output=True, text=True).stdout
-    body = [l for l in sass.splitlines() if re.match(r"\s+/\*[0-9a-f]{4}\*/", l)]
+    body = [l for l in sass.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
     hist = collections.Counter()
     for l in body:
         t = re.sub(r"^\s*/\*[0-9a-f]+\*/\s*", "", l).split()
