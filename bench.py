@@ -776,26 +776,21 @@ def bench_c3_gpu(args, rank, world):
 
     from colosseum_b200 import _cabi
     from colosseum_b200.sharded import shard_range
-    from colosseum_b200.suite import load_suite_all, run_instance, run_many, run_many_native, suite_size
+    from colosseum_b200.suite import (load_suite_all, longest_first, run_instance, run_many, run_many_native,
+                                       shard_instances, suite_costs, suite_size)
 
     gdir = os.path.join(ROOT, "tests", "golden")
     n_suite = suite_size(gdir)
     B = args.c3_instances
-    # instance i of the list goes to rank i % world (every rank gets the same mix of families and sizes; a contiguous
-    # range left the slowest of 8 ranks 20 % behind the mean), and a rank starts its most expensive instances first
-    # (its workers pull from one queue: longest-first keeps the tail short -- the slowest single instance is ~0.2 s of a
-    # ~0.35 s region at 128 instances per GPU)
-    my_ids = list(range(rank, B, world))
+    # the B instances, sorted by decreasing estimated time (suite.instance_cost: a fit of measured instance times, from the
+    # fixtures' metadata), are dealt to the ranks in snake order: same count, nearly the same total cost, longest first (a rank's
+    # workers pull from one queue, and the most expensive instance is a large part of a 128-instance region)
+    my_ids = shard_instances(B, rank, world, costs=suite_costs(gdir))
     i0, i1 = 0, len(my_ids)
     lib = _cabi.lib()
     mine = load_suite_all(gdir, indices=sorted({i % n_suite for i in my_ids}))
     by_index = dict(zip(sorted({i % n_suite for i in my_ids}), mine))
-
-    def cost(inst):  # targets x states x actions of the diameter solve
-        n = len(inst.nodes) if inst.episodic and inst.nodes is not None else inst.S
-        return float(n) * n * inst.tables.A
-
-    work = sorted(((by_index[i % n_suite], 0) for i in my_ids), key=lambda w: -cost(w[0]))
+    work = longest_first([(by_index[i % n_suite], 0) for i in my_ids])
     suite = mine
     # one spinning worker per core this rank may use, at most 8 (colo_suite_run spins in cudaStreamSynchronize when it has
     # a core per worker and blocks otherwise; measured on 4 cores: 4 spinning workers 0.29-0.35 s per 128 instances,

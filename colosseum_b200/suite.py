@@ -256,6 +256,59 @@ def run_many(work, n_workers=4, **kw):
         sys.setswitchinterval(old)
 
 
+def _cost_ms(episodic: bool, n: int) -> float:
+    # least-squares fit of the measured wall time of an instance (step + hardness phases, 8 instances in flight on one
+    # B200, profiles/r2_c3_phases.txt): a fixed ~10-12 ms of launch / synchronise round trips plus a mild size term
+    return 12.5 + 0.0029 * n if episodic else 10.4 + 0.0133 * n
+
+
+def instance_cost(inst: "SuiteInstance") -> float:
+    """estimated milliseconds of the C3 work item of an instance: grows with the reachable (h, s) nodes of an episodic
+    MDP (its episodic / continuous-form tensors, mdp/base.py:996-1056), with the states of a continuous one"""
+    ep = inst.episodic and inst.nodes is not None
+    return _cost_ms(ep, len(inst.nodes) if ep else inst.S)
+
+
+def suite_costs(golden_dir) -> np.ndarray:
+    """`instance_cost` of every instance of the C3 list from the fixtures' metadata alone (S, number of reachable (h, s)
+    nodes): cheap enough for every rank to compute for the whole list"""
+    out = []
+    for f in suite_files(golden_dir):
+        z = np.load(f, allow_pickle=False)
+        for i in range(len(json.loads(str(z["names"])))):
+            k = f"i{i}_"
+            ep = (k + "reach_h") in z.files
+            out.append(_cost_ms(ep, int(z[k + "reach_h"].shape[0]) if ep else int(z[k + "S"])))
+    return np.asarray(out)
+
+
+def shard_instances(n_items: int, rank: int, world: int, costs=None):
+    """Indices of the C3 instance list (cycled to n_items) a rank owns; no communication.  With `costs` (one per list
+    entry, `suite_costs`): the items sorted by decreasing cost are dealt to the ranks in snake order (0..w-1, w-1..0, ...),
+    so every rank gets the same number of instances (+-1), nearly the same total cost, and its share already longest
+    first -- a contiguous range gives every rank a different partial cycle of the 94 parameter sets.  Without costs:
+    i % world == rank."""
+    n_items, rank, world = int(n_items), int(rank), int(world)
+    if costs is None:
+        return list(range(rank, n_items, world))
+    c = np.asarray(costs, np.float64)
+    order = sorted(range(n_items), key=lambda i: (-c[i % len(c)], i))
+    mine = []
+    for j, i in enumerate(order):
+        r = j % world
+        if (j // world) % 2:
+            r = world - 1 - r
+        if r == rank:
+            mine.append(i)
+    return mine
+
+
+def longest_first(work):
+    """`work` = [(SuiteInstance, seed), ...] ordered by decreasing `instance_cost`: the workers of `run_many_native` pull
+    from one queue, and the most expensive instance is a large part of a 128-instance shard's wall time"""
+    return sorted(work, key=lambda w: -instance_cost(w[0]))
+
+
 def release_caches():
     """frees the large device buffers colo_suite_run's workers keep between instances and calls"""
     from . import _cabi

@@ -37,6 +37,28 @@ def test_suite_fixture_is_the_reference_benchmark(suite):
         assert (inst.nodes is not None) == inst.episodic
 
 
+def test_shard_scheduling(suite):
+    """C3 sharding: every index exactly once, equal counts, nearly equal cost per rank, each rank's share longest first"""
+    from colosseum_b200.suite import instance_cost, longest_first, shard_instances, suite_costs
+
+    costs = suite_costs(GOLDEN)
+    assert len(costs) >= 80 and all(costs[i] == instance_cost(inst) for i, inst in enumerate(suite))
+    for n, world in ((1024, 8), (len(costs), 8), (128, 1), (256, 2), (7, 3), (2, 4)):
+        for cs in (None, costs):
+            parts = [shard_instances(n, r, world, costs=cs) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        tot = [sum(costs[i % len(costs)] for i in p) for p in parts]
+        if n >= 128:
+            assert max(tot) <= 1.01 * min(tot), (n, world, tot)
+        for p in parts:
+            c = [costs[i % len(costs)] for i in p]
+            assert c == sorted(c, reverse=True)
+    work = longest_first([(inst, 0) for inst in suite])
+    c = [instance_cost(w[0]) for w in work]
+    assert c == sorted(c, reverse=True) and sorted(id(w[0]) for w in work) == sorted(id(i) for i in suite)
+
+
 def test_oracle_on_small_suite_instances(suite):
     """the CPU oracle against the reference's recorded measures on the small instances (keeps the CPU suite fast)"""
     n = 0
