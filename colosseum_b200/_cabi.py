@@ -190,6 +190,7 @@ PROTOTYPES = {
     "colo_version": (_I, []),
     "colo_launch_count": (_ULL, []),
     "colo_reset_launch_count": (None, []),
+    "colo_backup_tma_sweeps": (_ULL, []),
     "colo_stream_synchronize": (_I, [_P]),
     "colo_backup_f32": (_I, [C.POINTER(BackupArgs), _P]),
     "colo_backup_f64acc": (_I, [C.POINTER(BackupArgs), _P]),

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "tma_device.cuh"
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__((kTmaConsumers + 1) * 32) backup_tma_kernel(co
   }
 }
 
+static std::atomic<unsigned long long> g_tma_sweeps{0};
 // returns COLO_OK and *handled = 1 when the TMA-staged variant took the sweep
 static int launch_backup_tma(const colo_backup_args& p, cudaStream_t st, int* handled) {
   *handled = 0;
@@ -379,6 +381,7 @@ static int launch_backup_tma(const colo_backup_args& p, cudaStream_t st, int* ha
   }
 #undef COLO_TMA
   *handled = 1;
+  g_tma_sweeps.fetch_add(1);
   return check_launch("backup_tma_kernel");
 }
 
@@ -1507,3 +1510,5 @@ int colo_gaps_f64(const double* Q, const double* V, const unsigned char* mask, l
 }
 
 }  // extern "C"
+
+extern "C" unsigned long long colo_backup_tma_sweeps(void) { return colo::g_tma_sweeps.load(); }

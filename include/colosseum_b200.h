@@ -56,6 +56,8 @@ unsigned long long colo_launch_count(void);
 /* cudaStreamSynchronize(stream): the host-side wait of a zero-copy env step (one ctypes call, no Python layers) */
 int colo_stream_synchronize(void* stream);
 void colo_reset_launch_count(void);
+/* sweeps taken by the TMA-staged variant of the streaming backup kernel (COLO_BACKUP_TMA=1) since load */
+unsigned long long colo_backup_tma_sweeps(void);
 
 /* ---------------------------------------------------------------- (B) Bellman backups ------------------- */
 /*

@@ -309,3 +309,44 @@ def test_batched_small_episodic_solves(dp, S, A, H, precision):
         Q1, V1 = dp.episodic_value_iteration(H, Td[b], Rd[b], precision=precision)
         np.testing.assert_allclose(V[b].cpu().numpy(), V1.cpu().numpy(), rtol=tol, atol=tol)
     assert float(Q[:, H].abs().max()) == 0.0 and float(V[:, H].abs().max()) == 0.0
+
+
+def test_tma_staged_backup_matches_the_streaming_kernel(tmp_path):
+    """The TMA-staged variant of the synchronous sweep (COLO_BACKUP_TMA=1: cp.async.bulk ring + mbarriers, DESIGN 4.1;
+    the switch is read once per process, hence the child processes) returns the values of the shipped LDG kernel --
+    fixed sweeps of max / policy-weighted backups with per-instance freezing, Q stored -- and really ran."""
+    import os
+    import subprocess
+    import sys
+
+    child = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import colosseum_b200.dynamic_programming as dp
+from colosseum_b200 import _cabi
+B, S, A = 80, 256, 4
+gen = torch.Generator(device="cuda").manual_seed(7)
+T = torch._standard_gamma(torch.full((B, S, A, S), 0.05, device="cuda"), generator=gen).float() + 1e-30
+T = (T / T.sum(-1, keepdim=True)).contiguous()
+R = torch.rand((B, S, A), device="cuda", generator=gen)
+vi = dp.BatchedValueIteration(T, R, gamma=0.99, precision="f32")
+vi.sweep(25)
+Q, V = dp.discounted_value_iteration(T, R, 0.99, 1e-3, precision="f32")
+pi = torch.softmax(R * 3, -1).contiguous()
+Qp, Vp = dp.discounted_policy_evaluation(T, R, pi, 0.99, 1e-5, precision="f32")
+torch.cuda.synchronize()
+np.savez(sys.argv[2], V25=vi.values.cpu().numpy(), Q=Q.cpu().numpy(), V=V.cpu().numpy(), Vp=Vp.cpu().numpy(),
+         tma=np.int64(_cabi.lib().colo_backup_tma_sweeps()))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag, env in (("ldg", {}), ("tma", {"COLO_BACKUP_TMA": "1"})):
+        path = str(tmp_path / f"{tag}.npz")
+        e = {k: v for k, v in os.environ.items() if not k.startswith("COLO_BACKUP_TMA")}
+        r = subprocess.run([sys.executable, "-c", child, root, path], env={**e, **env}, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = np.load(path)
+    assert int(outs["ldg"]["tma"]) == 0 and int(outs["tma"]["tma"]) >= 25
+    for k in ("V25", "Q", "V", "Vp"):
+        np.testing.assert_allclose(outs["tma"][k], outs["ldg"][k], rtol=2e-6, atol=1e-6, err_msg=k)
