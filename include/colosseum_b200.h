@@ -883,6 +883,10 @@ int colo_synth_dense_rows(float* T_rows, float* R_rows, int row0, int nrows, int
  * solves are in flight at once without an interpreter in between.  ALL pointers of colo_suite_instance are HOST
  * pointers (numpy arrays of the caller); out[i] receives instance i's results.  Runs on the current device.
  * Synchronises.  Returns the first non-zero status (out[i].status / out[i].error say which instance and why).
+ * The workers spin in their stream synchronisations when the process may run on at least n_workers cores
+ * (sched_getaffinity) and block otherwise (environment: COLO_SUITE_SPIN / COLO_SUITE_BLOCK force either;
+ * COLO_SUITE_VERBOSE prints the wall time of every phase of every instance on stderr); they keep their large device
+ * buffers between instances and calls (colo_suite_release_caches), and one call runs at a time per process.
  */
 typedef struct {
   int S, A, H, K;                /* H = 0: continuous; K = successor slots per (s, a) */
